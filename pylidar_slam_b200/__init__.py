@@ -1,0 +1,16 @@
+"""pylidar_slam_b200 -- B200-native ICP-odometry hot path of pyLiDAR-SLAM.
+
+Python host code mirroring the reference's plug-in interfaces (OdometryAlgorithm, LocalMap,
+RigidAlignment, Filter) over hand-written sm_100a CUDA behind a C ABI (include/plslam_b200.h).
+Importing the package does not need a GPU; creating a context does (no CPU fallback).
+"""
+from . import _lib  # noqa: F401
+from .common import (Pose, SphericalProjector, compute_neighbors, compute_normal_map, grid_sample,  # noqa: F401
+                     voxel_hashing, voxelise)
+from .odometry import (LOCAL_MAP, ODOMETRY, RIGID_ALIGNMENT, GaussNewtonPointToPlaneAlignment,  # noqa: F401
+                       GaussNewtonPointToPlaneConfig, ICPFrameToModel, ICPFrameToModelConfig, KdTreeLocalMap,
+                       KdTreeLocalMapConfig, LocalMap, OdometryAlgorithm, ProjectiveLocalMap,
+                       ProjectiveLocalMapConfig)
+from .preprocessing import FILTER, GridSample, GridSampleConfig, Preprocessing, PreprocessingConfig, ToTensor  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,159 @@
+"""ctypes binding of libplslam_b200.so (include/plslam_b200.h).
+
+There is NO CPU fallback: if the shared library is missing it is built with nvcc; if that is
+impossible, or no CUDA device is present when a context is created, an exception is raised.
+"""
+import ctypes as C
+import logging
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libplslam_b200.so")
+
+PLS_OK, PLS_E_INVALID, PLS_E_CUDA, PLS_E_SINGULAR, PLS_W_TINY_RESIDUAL, PLS_E_STATE, PLS_E_COMM = range(7)
+SCHEMES = {"default": 0, "least_square": 1, "huber": 2, "exp": 3, "neighborhood": 4, "geman_mcclure": 5,
+           "square_geman_mcclure": 6, "cauchy": 7}
+MAP_KDTREE, MAP_PROJECTIVE = 0, 1
+INPUT_NDARRAY, INPUT_TENSOR, INPUT_VERTEX_MAP = 0, 1, 2
+
+
+class PlsConfig(C.Structure):
+    _fields_ = [("height", C.c_int32), ("width", C.c_int32), ("up_fov_deg", C.c_float), ("down_fov_deg", C.c_float),
+                ("local_map_type", C.c_int32), ("local_map_size", C.c_int32), ("num_neighbors_normals", C.c_int32),
+                ("normals_kernel_size", C.c_int32), ("scheme", C.c_int32), ("sigma", C.c_float),
+                ("gn_max_iters", C.c_int32), ("gn_norm_stop", C.c_float), ("max_num_alignments", C.c_int32),
+                ("threshold_delta_pose", C.c_float), ("threshold_trans", C.c_float), ("threshold_rot", C.c_float),
+                ("device", C.c_int32), ("stream", C.c_void_p)]
+
+
+_P, _I, _L, _D, _F = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_float
+_SIGNATURES = {
+    "pls_config_default": [C.POINTER(PlsConfig)],
+    "pls_create": [C.POINTER(PlsConfig), C.POINTER(_P)],
+    "pls_destroy": [_P],
+    "pls_synchronize": [_P],
+    "pls_voxel_hash": [_P, _P, _I, _L, _D, _P, _P],
+    "pls_grid_sample": [_P, _P, _I, _L, _D, _P, _P, C.POINTER(_L)],
+    "pls_project_pixels": [_P, _P, _L, _I, _I, _F, _F, _P],
+    "pls_build_projection_map": [_P, _P, _P, _I, _L, _I, _I, _I, _F, _F, _P],
+    "pls_normal_map": [_P, _P, _I, _I, _I, _I, _P],
+    "pls_compute_neighbors": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
+    "pls_build_pose_matrix": [_P, _P, _I, _P],
+    "pls_from_pose_matrix": [_P, _P, _I, _P],
+    "pls_align_p2plane": [_P, _P, _P, _P, _L, _I, _I, _D, _I, _D, _P, _P, _P, _P],
+    "pls_map_init": [_P],
+    "pls_kdmap_update_points": [_P, _P, _P, _L],
+    "pls_kdmap_update_vertex_map": [_P, _P, _P, _I, _I],
+    "pls_kdmap_size": [_P, C.POINTER(_L)],
+    "pls_kdmap_points": [_P, _P],
+    "pls_kdmap_nn_search": [_P, _P, _L, _P, _P, _P],
+    "pls_projmap_update": [_P, _P, _P],
+    "pls_projmap_num_frames": [_P, C.POINTER(_I)],
+    "pls_projmap_model": [_P, _P, _P],
+    "pls_projmap_nn_search": [_P, _P, _L, _P, _P, _P, C.POINTER(_L)],
+    "pls_odometry_init": [_P],
+    "pls_register_frame": [_P, _P, _L, _P, _P, _P, _P, C.POINTER(_I)],
+    "pls_process_frame": [_P, _P, _I, _L, _P, _P, _P, C.POINTER(_I), _P],
+    "pls_process_frame_grid_sample": [_P, _P, _L, _D, _I, _P, _P, _P, C.POINTER(_I), _P],
+    "pls_comm_init": [_P, _I, _I, _P, C.c_char_p],
+    "pls_comm_unique_id": [C.c_char_p, _P],
+    "pls_comm_destroy": [_P],
+    "pls_profile_enable": [_P, _I, _I],
+    "pls_profile_read": [_P, _I, C.POINTER(_D), C.POINTER(_L), C.POINTER(_D), _I],
+}
+
+_lib = None
+
+
+def load():
+    """Loads (building first if needed) the shared library.  Raises if it cannot be had."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        _build.build()
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing and could not be built: the CUDA extension is required")
+    lib = C.CDLL(LIB_PATH)
+    for name, args in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+        fn.argtypes = args
+        fn.restype = C.c_int
+    lib.pls_last_error.argtypes = [_P]
+    lib.pls_last_error.restype = C.c_char_p
+    lib.pls_version.argtypes = []
+    lib.pls_version.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    """Every entry point include/plslam_b200.h declares (used by the CPU-side ABI test)."""
+    return sorted(list(_SIGNATURES) + ["pls_last_error", "pls_version"])
+
+
+def ptr(x):
+    """Raw address of a numpy array / torch tensor (host or CUDA) / None."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"], "arrays passed to the C ABI must be C-contiguous"
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):
+        assert x.is_contiguous(), "tensors passed to the C ABI must be contiguous"
+        return x.data_ptr()
+    raise TypeError(f"cannot take the address of {type(x)}")
+
+
+def check(ctx_handle, status):
+    """Maps status codes onto the reference's error behaviour (SURVEY.md section 8b 'Errors')."""
+    if status == PLS_OK:
+        return status
+    msg = load().pls_last_error(ctx_handle).decode() if ctx_handle else "plslam_b200 error"
+    if status == PLS_W_TINY_RESIDUAL:
+        logging.warning("The residual norm is lower than threshold 1e-7. "
+                        "This would lead to invalid jacobian. We prefer Stopping ICP")
+        return status
+    if status == PLS_E_SINGULAR:
+        logging.error("Invalid Jacobian in Gauss Newton minimization, the hessian is not invertible")
+        raise RuntimeError("Invalid Jacobian in Gauss Newton minimization")
+    if status == PLS_E_INVALID:
+        raise AssertionError(msg)
+    raise RuntimeError(f"plslam_b200 status {status}: {msg}")
+
+
+class Context:
+    """Owns one pls_context (one CUDA device, one stream, one local map + odometry state)."""
+
+    def __init__(self, **kwargs):
+        lib = load()
+        cfg = PlsConfig()
+        lib.pls_config_default(C.byref(cfg))
+        for k, v in kwargs.items():
+            if not hasattr(cfg, k):
+                raise AssertionError(f"unknown pls_config field {k}")
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        self.handle = _P()
+        st = lib.pls_create(C.byref(cfg), C.byref(self.handle))
+        if st != PLS_OK:
+            raise RuntimeError(f"pls_create failed with status {st}: a CUDA device and the sm_100a library are "
+                               f"required (there is no CPU fallback)")
+        self.lib = lib
+
+    def call(self, name, *args):
+        return check(self.handle, getattr(self.lib, name)(self.handle, *args))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.pls_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,219 @@
+"""Host-side mirrors of the reference's `slam/common` helpers on the hot path, each a thin call
+into the C ABI (names, argument meaning and error behaviour follow the reference; arithmetic
+runs in the CUDA library).
+
+Arrays may be numpy arrays, CPU torch tensors or CUDA torch tensors; outputs are returned in the
+same container kind / device as the first input.
+"""
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_default_ctx = None
+
+
+def default_context() -> _lib.Context:
+    """A lazily created context on cuda:0 for the stateless helpers."""
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = _lib.Context()
+    return _default_ctx
+
+
+def assert_debug(condition: bool, message: str = ""):
+    """slam/common/utils.py:30-38"""
+    if not condition:
+        raise AssertionError(message)
+
+
+def check_tensor(tensor, sizes: list):
+    """slam/common/utils.py:54-74 (shape check; -1 matches any size)."""
+    shape = list(tensor.shape)
+    ok = len(shape) == len(sizes) and all(s == -1 or s == t for s, t in zip(sizes, shape))
+    assert_debug(ok, f"[BAD TENSOR SHAPE] Wrong tensor shape got {tuple(tensor.shape)} expected {sizes}")
+
+
+def _as_f32(x):
+    if isinstance(x, np.ndarray):
+        return np.ascontiguousarray(x, dtype=np.float32)
+    return x.to(torch.float32).contiguous()
+
+
+def _empty_like_kind(x, shape, dtype=np.float32):
+    if isinstance(x, np.ndarray):
+        return np.empty(shape, dtype=dtype)
+    tdt = {np.float32: torch.float32, np.float64: torch.float64, np.int64: torch.int64}[dtype]
+    return torch.empty(shape, dtype=tdt, device=x.device)
+
+
+# ------------------------------------------------------------------------------------------
+# slam/common/pointcloud.py
+# ------------------------------------------------------------------------------------------
+def voxelise(pointcloud, voxel_x: float = 0.2, voxel_y: float = -1.0, voxel_z: float = -1.0, ctx=None):
+    """int64 voxel coordinates `(n, 3)` (pointcloud.py:54-79).  Only cubic voxels are on the hot path."""
+    ctx = ctx or default_context()
+    assert_debug(voxel_y in (-1.0, voxel_x) and voxel_z in (-1.0, voxel_x), "cubic voxels only")
+    check_tensor(pointcloud, [-1, 3])
+    is64 = (pointcloud.dtype == np.float64) if isinstance(pointcloud, np.ndarray) else (pointcloud.dtype == torch.float64)
+    pc = np.ascontiguousarray(pointcloud) if isinstance(pointcloud, np.ndarray) else pointcloud.contiguous()
+    if not is64:
+        pc = _as_f32(pc)
+    n = pc.shape[0]
+    coords = _empty_like_kind(pc, (n, 3), np.int64)
+    hashes = _empty_like_kind(pc, (n,), np.int64)
+    ctx.call("pls_voxel_hash", _lib.ptr(pc), int(is64), n, float(voxel_x), _lib.ptr(coords), _lib.ptr(hashes))
+    return coords
+
+
+def voxel_hashing(pointcloud, voxel_size: float, ctx=None):
+    """Signed 64-bit voxel hashes `(n,)` of a point cloud (pointcloud.py:13-23,40-51 fused with voxelise)."""
+    ctx = ctx or default_context()
+    check_tensor(pointcloud, [-1, 3])
+    is64 = (pointcloud.dtype == np.float64) if isinstance(pointcloud, np.ndarray) else (pointcloud.dtype == torch.float64)
+    pc = np.ascontiguousarray(pointcloud) if isinstance(pointcloud, np.ndarray) else pointcloud.contiguous()
+    if not is64:
+        pc = _as_f32(pc)
+    hashes = _empty_like_kind(pc, (pc.shape[0],), np.int64)
+    ctx.call("pls_voxel_hash", _lib.ptr(pc), int(is64), pc.shape[0], float(voxel_size), None, _lib.ptr(hashes))
+    return hashes
+
+
+def grid_sample(pointcloud, voxel_size: float, ctx=None):
+    """One point per voxel hash: `(sample_points, sample_indices)` (pointcloud.py:182-195)."""
+    ctx = ctx or default_context()
+    check_tensor(pointcloud, [-1, 3])
+    is64 = (pointcloud.dtype == np.float64) if isinstance(pointcloud, np.ndarray) else (pointcloud.dtype == torch.float64)
+    pc = np.ascontiguousarray(pointcloud) if isinstance(pointcloud, np.ndarray) else pointcloud.contiguous()
+    if not is64:
+        pc = _as_f32(pc)
+    n = pc.shape[0]
+    out = _empty_like_kind(pc, (n, 3), np.float64 if is64 else np.float32)
+    idx = _empty_like_kind(pc, (n,), np.int64)
+    count = C.c_int64(0)
+    ctx.call("pls_grid_sample", _lib.ptr(pc), int(is64), n, float(voxel_size), _lib.ptr(out), _lib.ptr(idx), C.byref(count))
+    return out[:count.value], idx[:count.value]
+
+
+# ------------------------------------------------------------------------------------------
+# slam/common/projection.py
+# ------------------------------------------------------------------------------------------
+class SphericalProjector:
+    """SphericalProjector (projection.py:426-508): spherical range-image projection."""
+
+    def __init__(self, height: Optional[int] = None, width: Optional[int] = None, num_channels: Optional[int] = None,
+                 up_fov: Optional[float] = None, down_fov: Optional[float] = None, ctx=None, **kwargs):
+        self.height, self.width, self.num_channels = height, width, num_channels
+        self.up_fov, self.down_fov = up_fov, down_fov
+        self._ctx = ctx
+
+    @property
+    def ctx(self):
+        return self._ctx or default_context()
+
+    def project_pointcloud(self, pointcloud, height=None, width=None, up_fov=None, down_fov=None, **kwargs):
+        """[B,N,K>=3] -> float pixel coordinates [B,N,2] (row, col) (projection.py:452-484)."""
+        check_tensor(pointcloud, [-1, -1, -1])
+        H, W = height or self.height, width or self.width
+        up, down = (self.up_fov if up_fov is None else up_fov), (self.down_fov if down_fov is None else down_fov)
+        xyz = _as_f32(pointcloud[:, :, :3])
+        B, N, _ = xyz.shape
+        out = _empty_like_kind(xyz, (B, N, 2))
+        self.ctx.call("pls_project_pixels", _lib.ptr(xyz), B * N, H, W, float(up), float(down), _lib.ptr(out))
+        return out
+
+    def build_projection_map(self, pointcloud, default_value: float = 0.0, height=None, width=None,
+                             transform=None, **kwargs):
+        """[B,N,C>=3] -> [B,C_dest,H,W]; the closest point per pixel survives (projection.py:331-418)."""
+        assert_debug(default_value == 0.0, "only default_value == 0 is on the hot path")
+        check_tensor(pointcloud, [-1, -1, -1])
+        H, W = height or self.height, width or self.width
+        pc = _as_f32(pointcloud)
+        B, N, _ = pc.shape
+        channels = _as_f32(transform(pc)) if transform is not None else (pc if pc.shape[2] != 3 else None)
+        xyz = _as_f32(pc[:, :, :3])
+        Cd = 3 if channels is None else channels.shape[2]
+        out = _empty_like_kind(xyz, (B, Cd, H, W))
+        self.ctx.call("pls_build_projection_map", _lib.ptr(xyz), _lib.ptr(channels), B, N, Cd, H, W,
+                      float(self.up_fov), float(self.down_fov), _lib.ptr(out))
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+# slam/common/geometry.py
+# ------------------------------------------------------------------------------------------
+def compute_normal_map(vertex_map, kernel_size: int = 5, ctx=None):
+    """[B,3,H,W] -> unit normals [B,3,H,W] (geometry.py:240-295)."""
+    ctx = ctx or default_context()
+    check_tensor(vertex_map, [-1, 3, -1, -1])
+    vm = _as_f32(vertex_map)
+    B, _, H, W = vm.shape
+    out = _empty_like_kind(vm, (B, 3, H, W))
+    ctx.call("pls_normal_map", _lib.ptr(vm), B, H, W, int(kernel_size), _lib.ptr(out))
+    return out
+
+
+def compute_neighbors(vm_target, vm_reference, reference_fields=None, ctx=None, **kwargs):
+    """Per pixel nearest of D reference vertex maps (geometry.py:397-439)."""
+    ctx = ctx or default_context()
+    check_tensor(vm_target, [1, 3, -1, -1])
+    _, _, H, W = vm_target.shape
+    check_tensor(vm_reference, [-1, 3, H, W])
+    tgt, ref = _as_f32(vm_target), _as_f32(vm_reference)
+    K = ref.shape[0]
+    fields = None if reference_fields is None else _as_f32(reference_fields)
+    Cf = 0 if fields is None else fields.shape[1]
+    nb = _empty_like_kind(tgt, (1, 3, H, W))
+    nf = None if fields is None else _empty_like_kind(tgt, (1, Cf, H, W))
+    ctx.call("pls_compute_neighbors", _lib.ptr(tgt), _lib.ptr(ref), _lib.ptr(fields), K, Cf, H, W, _lib.ptr(nb), _lib.ptr(nf))
+    return nb, nf
+
+
+# ------------------------------------------------------------------------------------------
+# slam/common/pose.py (Euler xyz only: the hot path's representation)
+# ------------------------------------------------------------------------------------------
+class Pose:
+    def __init__(self, pose_type: str = "euler", ctx=None):
+        assert_debug(pose_type == "euler", "only the euler pose representation is on the hot path")
+        self.pose_type = pose_type
+        self._ctx = ctx
+
+    @property
+    def ctx(self):
+        return self._ctx or default_context()
+
+    @staticmethod
+    def num_params() -> int:
+        return 6
+
+    def build_pose_matrix(self, params):
+        """[B,6] -> [B,4,4] (pose.py:120-144)."""
+        check_tensor(params, [-1, 6])
+        p = _as_f32(params)
+        out = _empty_like_kind(p, (p.shape[0], 4, 4))
+        self.ctx.call("pls_build_pose_matrix", _lib.ptr(p), p.shape[0], _lib.ptr(out))
+        return out
+
+    def from_pose_matrix(self, mats):
+        """[B,4,4] -> [B,6] (pose.py:188-207)."""
+        check_tensor(mats, [-1, 4, 4])
+        m = _as_f32(mats)
+        out = _empty_like_kind(m, (m.shape[0], 6))
+        self.ctx.call("pls_from_pose_matrix", _lib.ptr(m), m.shape[0], _lib.ptr(out))
+        return out
+
+
+def euler_pose_matrix_f64(params: np.ndarray) -> np.ndarray:
+    """float64 host build_pose_matrix for the absolute-pose bookkeeping (icp_odometry.py:200-202)."""
+    tx, ty, tz, ex, ey, ez = [float(v) for v in params]
+    cx, sx, cy, sy, cz, sz = np.cos(ex), np.sin(ex), np.cos(ey), np.sin(ey), np.cos(ez), np.sin(ez)
+    rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    T = np.eye(4)
+    T[:3, :3] = rz @ ry @ rx
+    T[:3, 3] = [tx, ty, tz]
+    return T

@@ -1,0 +1,242 @@
+// Context lifetime, host<->device argument staging, profiling slots.
+#include "internal.cuh"
+
+namespace pls {
+
+void DBuf::reserve(size_t bytes, cudaStream_t s, bool keep) {
+    if (bytes <= cap) return;
+    size_t want = bytes + bytes / 4 + 256;
+    void* np = nullptr;
+    PLS_CUDA(cudaStreamSynchronize(s));
+    PLS_CUDA(cudaMalloc(&np, want));
+    if (p) {
+        if (keep) PLS_CUDA(cudaMemcpy(np, p, cap, cudaMemcpyDeviceToDevice));
+        PLS_CUDA(cudaFree(p));
+    }
+    p = np;
+    cap = want;
+}
+
+void DBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+
+void HBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return;
+    if (p) PLS_CUDA(cudaFreeHost(p));
+    PLS_CUDA(cudaMallocHost(&p, bytes));
+    cap = bytes;
+}
+
+void HBuf::release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+}
+
+bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+const void* to_device(pls_context* ctx, const void* p, size_t bytes, DBuf& stage) {
+    if (!p || bytes == 0) return p;
+    if (is_device_ptr(p)) return p;
+    stage.reserve(bytes, ctx->stream);
+    PLS_CUDA(cudaMemcpyAsync(stage.p, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return stage.p;
+}
+
+OutArg out_arg(pls_context* ctx, void* p, size_t bytes, DBuf& stage) {
+    OutArg o;
+    o.bytes = bytes;
+    if (!p) return o;
+    if (is_device_ptr(p)) {
+        o.dev = p;
+        return o;
+    }
+    stage.reserve(bytes, ctx->stream);
+    o.host = p;
+    o.dev = stage.p;
+    return o;
+}
+
+void finish_out(pls_context* ctx, const OutArg& o, size_t bytes_used) {
+    if (!o.host) return;
+    size_t b = bytes_used == (size_t)-1 ? o.bytes : bytes_used;
+    if (b) PLS_CUDA(cudaMemcpyAsync(o.host, o.dev, b, cudaMemcpyDeviceToHost, ctx->stream));
+}
+
+ProfileScope::ProfileScope(pls_context* c, int w, double bytes) : ctx(c), which(w) {
+    ProfileSlot& s = ctx->prof[which];
+    if (!s.enabled) return;
+    if (s.used >= 4096) {
+        cudaStreamSynchronize(ctx->stream);
+        profile_collect(ctx, which);
+    }
+    if (s.used + 2 > s.pool.size()) {
+        for (int i = 0; i < 64; ++i) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return;
+            s.pool.push_back(e);
+        }
+    }
+    e0 = s.pool[s.used++];
+    e1 = s.pool[s.used++];
+    s.bytes += bytes;
+    s.launches += 1;
+    cudaEventRecord(e0, ctx->stream);
+}
+
+ProfileScope::~ProfileScope() {
+    if (e1) cudaEventRecord(e1, ctx->stream);
+}
+
+void profile_collect(pls_context* ctx, int which) {
+    ProfileSlot& s = ctx->prof[which];
+    for (size_t i = 0; i + 1 < s.used; i += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.pool[i], s.pool[i + 1]) == cudaSuccess) s.ms += ms;
+    }
+    s.used = 0;
+}
+
+}  // namespace pls
+
+using namespace pls;
+
+extern "C" {
+
+const char* pls_version(void) { return "plslam_b200 0.1 (sm_100a)"; }
+
+int pls_config_default(pls_config* c) {
+    if (!c) return PLS_E_INVALID;
+    memset(c, 0, sizeof(*c));
+    c->height = 64;
+    c->width = 2048;
+    c->up_fov_deg = 3.0f;
+    c->down_fov_deg = -24.0f;
+    c->local_map_type = PLS_MAP_KDTREE;
+    c->local_map_size = 20;
+    c->num_neighbors_normals = 10;
+    c->normals_kernel_size = 5;
+    c->scheme = PLS_SCHEME_DEFAULT;
+    c->sigma = 0.5f;
+    c->gn_max_iters = 1;
+    c->gn_norm_stop = 1e-3f;
+    c->max_num_alignments = 100;
+    c->threshold_delta_pose = 1e-4f;
+    c->threshold_trans = 0.1f;
+    c->threshold_rot = 0.3f;
+    c->device = 0;
+    c->stream = nullptr;
+    return PLS_OK;
+}
+
+int pls_create(const pls_config* cfg, pls_context** out) {
+    if (!cfg || !out) return PLS_E_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return PLS_E_CUDA;  // no CPU fallback: the product path needs the GPU
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return PLS_E_INVALID;
+    if (cfg->height <= 0 || cfg->width <= 0 || cfg->local_map_size <= 0) return PLS_E_INVALID;
+    if (cfg->max_num_alignments < 1 || cfg->max_num_alignments > kMaxAlign) return PLS_E_INVALID;
+    if (cfg->num_neighbors_normals < 3 || cfg->num_neighbors_normals > 31) return PLS_E_INVALID;
+    if (cfg->normals_kernel_size < 1 || cfg->normals_kernel_size > 9 || (cfg->normals_kernel_size % 2) == 0)
+        return PLS_E_INVALID;
+    pls_context* ctx = new pls_context();
+    ctx->cfg = *cfg;
+    try {
+        PLS_CUDA(cudaSetDevice(cfg->device));
+        if (cfg->stream) {
+            ctx->stream = (cudaStream_t)cfg->stream;
+        } else {
+            PLS_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+            ctx->own_stream = true;
+        }
+        ctx->pinned.reserve(sizeof(FrameResult) + 256);
+        ctx->scalars.reserve(sizeof(FrameResult) + 4096, ctx->stream);
+        PLS_CUDA(cudaMemsetAsync(ctx->scalars.p, 0, ctx->scalars.cap, ctx->stream));
+        odometry_reset(ctx);
+    } catch (const pls::Error& e) {
+        fprintf(stderr, "pls_create: %s\n", e.msg.c_str());
+        delete ctx;
+        return e.code;
+    }
+    *out = ctx;
+    return PLS_OK;
+}
+
+int pls_destroy(pls_context* ctx) {
+    if (!ctx) return PLS_E_INVALID;
+    cudaSetDevice(ctx->cfg.device);
+    cudaStreamSynchronize(ctx->stream);
+    comm_free(ctx);
+    for (auto& b : ctx->stage_in) b.release();
+    for (auto& b : ctx->stage_out) b.release();
+    for (auto& b : ctx->tmp) b.release();
+    ctx->pinned.release();
+    ctx->scalars.release();
+    ctx->sort.keys_alt.release(); ctx->sort.vals_alt.release(); ctx->sort.hist.release();
+    ctx->sort.status.release(); ctx->sort.plan.release();
+    ctx->scan.status.release();
+    for (auto& b : ctx->kd.store) b.release();
+    ctx->kd.morton.release(); ctx->kd.order.release(); ctx->kd.sorted.release(); ctx->kd.normals.release();
+    ctx->kd.nodes.release(); ctx->kd.parent.release(); ctx->kd.visit.release(); ctx->kd.bbox.release();
+    ctx->kd.inv_order.release();
+    ctx->pm.vmaps.release(); ctx->pm.nmaps.release(); ctx->pm.poses.release();
+    ctx->pm.model_v.release(); ctx->pm.model_n.release(); ctx->pm.zbuf.release();
+    ctx->frame_vmap.release(); ctx->frame_pts.release(); ctx->queries.release(); ctx->nn_prev.release();
+    ctx->partials.release(); ctx->gs_keys.release(); ctx->gs_vals.release(); ctx->gs_out_xyz.release();
+    ctx->gs_out_idx.release();
+    for (auto& s : ctx->prof)
+        for (auto e : s.pool) cudaEventDestroy(e);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return PLS_OK;
+}
+
+const char* pls_last_error(pls_context* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int pls_synchronize(pls_context* ctx) {
+    PLS_API_BEGIN(ctx)
+    PLS_CUDA(cudaStreamSynchronize(ctx->stream));
+    PLS_API_END(ctx)
+}
+
+int pls_profile_enable(pls_context* ctx, int which, int enable) {
+    PLS_API_BEGIN(ctx)
+    PLS_REQUIRE(which >= 0 && which < kProfileSlots, "pls_profile_enable: bad slot");
+    ctx->prof[which].enabled = enable != 0;
+    PLS_API_END(ctx)
+}
+
+int pls_profile_read(pls_context* ctx, int which, double* ms_total, int64_t* launches, double* bytes, int reset) {
+    PLS_API_BEGIN(ctx)
+    PLS_REQUIRE(which >= 0 && which < kProfileSlots, "pls_profile_read: bad slot");
+    PLS_CUDA(cudaStreamSynchronize(ctx->stream));
+    profile_collect(ctx, which);
+    ProfileSlot& s = ctx->prof[which];
+    if (ms_total) *ms_total = s.ms;
+    if (launches) *launches = s.launches;
+    if (bytes) *bytes = s.bytes;
+    if (reset) {
+        s.ms = 0;
+        s.launches = 0;
+        s.bytes = 0;
+    }
+    PLS_API_END(ctx)
+}
+
+}  // extern "C"

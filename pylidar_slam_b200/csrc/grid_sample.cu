@@ -1,0 +1,147 @@
+// K1 -- voxel-grid subsample.
+//
+//   voxel_hash_kernel : voxel coordinate = int64(round_half_even(double(p) / voxel)) per axis
+//                       and hash = 73856093 x + 19349669 y + 83492791 z in signed 64-bit
+//                       (slam/common/pointcloud.py:13-23,40-79).  Also emits the sort key
+//                       (hash with the sign bit flipped -> unsigned order == signed order).
+//   radix sort        : stable, so equal hashes keep ascending point index.
+//   head flags + scan : first element of each run of equal hashes == np.unique(...,
+//                       return_index=True)'s first occurrence (pointcloud.py:177,193).
+//   gather            : sample_points / sample_indices in ascending-hash order.
+#include "internal.cuh"
+
+namespace pls {
+
+namespace {
+
+constexpr long long HX = 73856093ll, HY = 19349669ll, HZ = 83492791ll;
+
+template <typename T>
+__global__ void voxel_hash_kernel(const T* __restrict__ xyz, int64_t n, double voxel, long long* __restrict__ coords,
+                                  long long* __restrict__ hashes, uint64_t* __restrict__ keys,
+                                  uint32_t* __restrict__ vals) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double x = (double)xyz[3 * i], y = (double)xyz[3 * i + 1], z = (double)xyz[3 * i + 2];
+        long long cx = __double2ll_rn(x / voxel);
+        long long cy = __double2ll_rn(y / voxel);
+        long long cz = __double2ll_rn(z / voxel);
+        long long h = HX * cx + HY * cy + HZ * cz;
+        if (coords) {
+            coords[3 * i] = cx;
+            coords[3 * i + 1] = cy;
+            coords[3 * i + 2] = cz;
+        }
+        if (hashes) hashes[i] = h;
+        if (keys) {
+            keys[i] = (uint64_t)h ^ 0x8000000000000000ull;
+            vals[i] = (uint32_t)i;
+        }
+    }
+}
+
+__global__ void head_flags_kernel(const uint64_t* __restrict__ keys, int64_t n, uint8_t* __restrict__ flags) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+
+template <typename T>
+__global__ void gather_samples_kernel(const T* __restrict__ xyz, const uint32_t* __restrict__ vals,
+                                      const uint8_t* __restrict__ flags, const uint32_t* __restrict__ pos, int64_t n,
+                                      T* __restrict__ out_xyz, long long* __restrict__ out_idx) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (!flags[i]) continue;
+        uint32_t src = vals[i];
+        uint32_t dst = pos[i];
+        if (out_idx) out_idx[dst] = (long long)src;
+        out_xyz[3 * (size_t)dst] = xyz[3 * (size_t)src];
+        out_xyz[3 * (size_t)dst + 1] = xyz[3 * (size_t)src + 1];
+        out_xyz[3 * (size_t)dst + 2] = xyz[3 * (size_t)src + 2];
+    }
+}
+
+inline int grid_for(int64_t n, int threads = 256) {
+    int64_t b = (n + threads - 1) / threads;
+    int64_t cap = 8 * kNumSMs;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+// Device-resident grid sample: xyz_dev [n,3] -> out_xyz_dev [<=n,3], out_idx_dev [<=n] (nullable);
+// the sample count lands in the device scalar SC_GS_COUNT.
+template <typename T>
+void grid_sample_device(pls_context* ctx, const T* xyz_dev, int64_t n, double voxel, T* out_xyz_dev,
+                        long long* out_idx_dev) {
+    cudaStream_t st = ctx->stream;
+    ProfileScope ps(ctx, 4, (double)n * 3 * sizeof(T));
+    ctx->gs_keys.reserve((size_t)n * sizeof(uint64_t), st);
+    ctx->gs_vals.reserve((size_t)n * sizeof(uint32_t), st);
+    ctx->tmp[1].reserve((size_t)n, st);                    // head flags
+    ctx->tmp[2].reserve((size_t)n * sizeof(uint32_t), st); // positions
+    voxel_hash_kernel<T><<<grid_for(n), 256, 0, st>>>(xyz_dev, n, voxel, nullptr, nullptr, ctx->gs_keys.as<uint64_t>(),
+                                                      ctx->gs_vals.as<uint32_t>());
+    PLS_CHECK_LAUNCH();
+    uint64_t* sk;
+    uint32_t* sv;
+    radix_sort_pairs(ctx, ctx->gs_keys.as<uint64_t>(), ctx->gs_vals.as<uint32_t>(), n, 8, &sk, &sv);
+    head_flags_kernel<<<grid_for(n), 256, 0, st>>>(sk, n, ctx->tmp[1].as<uint8_t>());
+    PLS_CHECK_LAUNCH();
+    exclusive_scan_flags(ctx, ctx->tmp[1].as<uint8_t>(), n, ctx->tmp[2].as<uint32_t>(), scalar_u32(ctx, SC_GS_COUNT));
+    gather_samples_kernel<T><<<grid_for(n), 256, 0, st>>>(xyz_dev, sv, ctx->tmp[1].as<uint8_t>(),
+                                                          ctx->tmp[2].as<uint32_t>(), n, out_xyz_dev, out_idx_dev);
+    PLS_CHECK_LAUNCH();
+}
+
+template void grid_sample_device<float>(pls_context*, const float*, int64_t, double, float*, long long*);
+template void grid_sample_device<double>(pls_context*, const double*, int64_t, double, double*, long long*);
+
+}  // namespace pls
+
+using namespace pls;
+
+extern "C" {
+
+int pls_voxel_hash(pls_context* ctx, const void* xyz, int is_f64, int64_t n, double voxel, int64_t* coords_out,
+                   int64_t* hashes_out) {
+    PLS_API_BEGIN(ctx)
+    PLS_REQUIRE(xyz && n > 0 && voxel > 0.0, "pls_voxel_hash: need [n,3] points and voxel > 0");
+    const size_t esz = is_f64 ? sizeof(double) : sizeof(float);
+    const void* d_xyz = to_device(ctx, xyz, (size_t)n * 3 * esz, ctx->stage_in[0]);
+    OutArg oc = out_arg(ctx, coords_out, (size_t)n * 3 * sizeof(int64_t), ctx->stage_out[0]);
+    OutArg oh = out_arg(ctx, hashes_out, (size_t)n * sizeof(int64_t), ctx->stage_out[1]);
+    if (is_f64)
+        voxel_hash_kernel<double><<<grid_for(n), 256, 0, ctx->stream>>>((const double*)d_xyz, n, voxel, (long long*)oc.dev,
+                                                                       (long long*)oh.dev, nullptr, nullptr);
+    else
+        voxel_hash_kernel<float><<<grid_for(n), 256, 0, ctx->stream>>>((const float*)d_xyz, n, voxel, (long long*)oc.dev,
+                                                                      (long long*)oh.dev, nullptr, nullptr);
+    PLS_CHECK_LAUNCH();
+    finish_out(ctx, oc);
+    finish_out(ctx, oh);
+    PLS_CUDA(cudaStreamSynchronize(ctx->stream));
+    PLS_API_END(ctx)
+}
+
+int pls_grid_sample(pls_context* ctx, const void* xyz, int is_f64, int64_t n, double voxel, void* out_xyz,
+                    int64_t* out_idx, int64_t* out_count) {
+    PLS_API_BEGIN(ctx)
+    PLS_REQUIRE(xyz && out_xyz && out_count && n > 0 && voxel > 0.0, "pls_grid_sample: bad arguments");
+    const size_t esz = is_f64 ? sizeof(double) : sizeof(float);
+    const void* d_xyz = to_device(ctx, xyz, (size_t)n * 3 * esz, ctx->stage_in[0]);
+    OutArg ox = out_arg(ctx, out_xyz, (size_t)n * 3 * esz, ctx->stage_out[0]);
+    OutArg oi = out_arg(ctx, out_idx, (size_t)n * sizeof(int64_t), ctx->stage_out[1]);
+    if (is_f64)
+        grid_sample_device<double>(ctx, (const double*)d_xyz, n, voxel, (double*)ox.dev, (long long*)oi.dev);
+    else
+        grid_sample_device<float>(ctx, (const float*)d_xyz, n, voxel, (float*)ox.dev, (long long*)oi.dev);
+    uint32_t count = 0;
+    PLS_CUDA(cudaMemcpyAsync(&count, scalar_u32(ctx, SC_GS_COUNT), sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PLS_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out_count = count;
+    finish_out(ctx, ox, (size_t)count * 3 * esz);
+    finish_out(ctx, oi, (size_t)count * sizeof(int64_t));
+    PLS_CUDA(cudaStreamSynchronize(ctx->stream));
+    PLS_API_END(ctx)
+}
+
+}  // extern "C"

@@ -1,0 +1,296 @@
+// Internal declarations shared by the translation units of libplslam_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <deque>
+#include <string>
+#include <vector>
+
+#include "../../include/plslam_b200.h"
+
+namespace pls {
+
+constexpr int kNumSMs = 148;  // B200
+constexpr int NACC = 30;      // 21 JtJ upper + 6 Jtr + sum (w r)^2 + sum r^2 + count
+constexpr int kMaxAlign = 128;
+constexpr int kProfileSlots = 6;
+constexpr size_t kScalarOffset = 2048;  // FrameResult first, then u32 scalar slots
+
+struct Error {
+    int code;
+    std::string msg;
+};
+
+#define PLS_CUDA(expr)                                                                            \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            throw pls::Error{PLS_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) +     \
+                                             " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"}; \
+        }                                                                                         \
+    } while (0)
+
+#define PLS_CHECK_LAUNCH() PLS_CUDA(cudaGetLastError())
+
+#define PLS_REQUIRE(cond, text)                                   \
+    do {                                                          \
+        if (!(cond)) throw pls::Error{PLS_E_INVALID, (text)};     \
+    } while (0)
+
+// Growable device buffer.  Growth synchronises the stream (only before steady state).
+struct DBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    template <typename T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+    void reserve(size_t bytes, cudaStream_t s, bool keep = false);
+    void release();
+};
+
+// Pinned host buffer.
+struct HBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    template <typename T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+    void reserve(size_t bytes);
+    void release();
+};
+
+struct ProfileSlot {
+    bool enabled = false;
+    std::vector<cudaEvent_t> pool;  // pairs
+    size_t used = 0;
+    double ms = 0.0;
+    int64_t launches = 0;
+    double bytes = 0.0;
+};
+
+// ---- radix sort / scan scratch ---------------------------------------------------------
+struct SortScratch {
+    DBuf keys_alt, vals_alt;  // ping-pong partners of the caller's arrays
+    DBuf hist;                // [8][256] u32 histograms, then exclusive bases
+    DBuf status;              // [passes][tiles][256] look-back words + tile counters
+    DBuf plan;                // device-side SortPlan
+};
+
+struct ScanScratch {
+    DBuf status;  // look-back words + tile counter + total
+};
+
+// ---- LBVH over the kd local map -------------------------------------------------------------
+struct KdMap {
+    // insertion-ordered storage, float4 (x,y,z,unused); ping-pong for the per-frame move
+    DBuf store[2];
+    int cur = 0;
+    int64_t count = 0;                // points in store[cur]
+    std::deque<int64_t> frame_counts; // per inserted frame
+    // search index
+    DBuf morton, order;     // u64 keys, u32 original index (sorted)
+    DBuf sorted;            // float4 (x,y,z, bitcast original index), Morton order
+    DBuf normals;           // float4 (nx,ny,nz, flag) in Morton order, cleared per rebuild
+    DBuf nodes;             // 64-byte BVH nodes
+    DBuf parent, visit;     // build-time parents (internal then leaves), arrival counters
+    DBuf bbox;              // 6 ordered-int words
+    DBuf inv_order;         // sorted position of each stored point (for out_idx)
+    int64_t indexed = 0;    // points covered by the index
+    bool valid = false;
+};
+
+struct ProjMap {
+    int K = 0;              // frames held
+    DBuf vmaps, nmaps;      // [Kmax][3][H][W] ring in insertion order (slot = frame order)
+    DBuf poses;             // device copy of [Kmax][16] poses (frame -> newest frame)
+    std::vector<float> host_poses;  // [K][16]
+    DBuf model_v, model_n;  // [Kmax][3][H][W] re-projected model
+    DBuf zbuf;              // [Kmax][H][W] u64
+    bool valid = false;
+};
+
+struct FrameResult {        // mirrored to pinned host memory at the end of a frame
+    float T[16];
+    float params[6];
+    float losses[kMaxAlign];
+    int iters;
+    int status;
+    int done;
+    int pad;
+    double last_sums[NACC];
+    long long counts[8];    // [0]=samples S, [1]=queries, [2]=valid rows of the frame's points
+    float first_pt[4];      // first non-null pixel (vertex-map input quirk)
+};
+
+struct Comm;  // NCCL glue (comm.cu)
+
+static_assert(sizeof(FrameResult) <= kScalarOffset, "FrameResult must fit before the scalar slots");
+
+}  // namespace pls
+
+struct pls_context {
+    pls_config cfg;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+
+    // staging for host<->device argument traffic
+    pls::DBuf stage_in[4], stage_out[6];
+    pls::HBuf pinned;       // FrameResult + small scalars
+    pls::DBuf scalars;      // device scalars (counts, flags, FrameResult)
+
+    pls::SortScratch sort;
+    pls::ScanScratch scan;
+
+    // generic scratch
+    pls::DBuf tmp[8];
+
+    // odometry state (icp_odometry.py:100-121)
+    pls::KdMap kd;
+    pls::ProjMap pm;
+    int frame_index = 0;
+    int sample_pointcloud = 0;          // _sample_pointcloud
+    float delta_since_update[16];       // _delta_since_map_update
+    pls::DBuf frame_vmap;               // [3][H][W] of the current frame
+    pls::DBuf frame_pts;                // float4 packed valid points of the current frame
+    pls::DBuf queries;                  // float4 queries P0 (owned storage)
+    const float4* query_ptr = nullptr;  // the queries of the current frame (may alias frame_pts)
+    pls::DBuf nn_prev;                  // previous-iteration match per query
+    pls::DBuf partials;                 // [blocks][NACC] doubles
+    pls::DBuf gs_keys, gs_vals, gs_out_xyz, gs_out_idx;
+    int64_t last_query_count = 0;
+
+    pls::Comm* comm = nullptr;
+    pls::ProfileSlot prof[pls::kProfileSlots];
+};
+
+#define PLS_API_BEGIN(ctx)                               \
+    if (!(ctx)) return PLS_E_INVALID;                    \
+    try {                                                \
+        cudaSetDevice((ctx)->cfg.device);
+
+#define PLS_API_END(ctx)                                 \
+    }                                                    \
+    catch (const pls::Error& e) {                        \
+        (ctx)->err = e.msg;                              \
+        return e.code;                                   \
+    }                                                    \
+    catch (const std::exception& e) {                    \
+        (ctx)->err = e.what();                           \
+        return PLS_E_INVALID;                            \
+    }                                                    \
+    return PLS_OK;
+
+namespace pls {
+
+// device scalar slots (u32) living behind the FrameResult in ctx->scalars
+enum { SC_GS_COUNT = 0, SC_QUERY_COUNT = 1, SC_NAN_COUNT = 2, SC_INSERT_COUNT = 3, SC_PROJ_NC = 4,
+       SC_TMP0 = 5, SC_TMP1 = 6, SC_NUM = 16 };
+
+// ---- pointer classification + staging ---------------------------------------------------
+bool is_device_ptr(const void* p);
+// Returns a device pointer holding `bytes` of `p` (copying through `stage` if p is host).
+const void* to_device(pls_context* ctx, const void* p, size_t bytes, DBuf& stage);
+// Returns a device pointer results may be written to; if `p` is host, it is `stage` and
+// finish_out() copies back.
+struct OutArg {
+    void* host = nullptr;
+    void* dev = nullptr;
+    size_t bytes = 0;
+};
+OutArg out_arg(pls_context* ctx, void* p, size_t bytes, DBuf& stage);
+void finish_out(pls_context* ctx, const OutArg& o, size_t bytes_used = (size_t)-1);
+
+inline uint32_t* scalar_u32(pls_context* ctx, int i) {
+    return reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ctx->scalars.p) + kScalarOffset) + i;
+}
+inline FrameResult* frame_result_dev(pls_context* ctx) { return reinterpret_cast<FrameResult*>(ctx->scalars.p); }
+inline FrameResult* frame_result_host(pls_context* ctx) { return reinterpret_cast<FrameResult*>(ctx->pinned.p); }
+
+// ---- profiling ------------------------------------------------------------------------------
+struct ProfileScope {
+    pls_context* ctx;
+    int which;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ProfileScope(pls_context* c, int w, double bytes);
+    ~ProfileScope();
+};
+void profile_collect(pls_context* ctx, int which);
+
+// ---- primitives (sort.cu / scan.cu) ------------------------------------------------------------
+// Stable LSD radix sort of (u64 key, u32 value) pairs on bits [0, 8*num_passes).
+// keys/vals are sorted in place from the caller's view: on return *keys_out/*vals_out point at
+// the arrays holding the result (either the inputs or the scratch partners) -- they are device
+// pointers stored in DEVICE memory (the plan), and also returned on the host when the number of
+// executed passes is statically known (no skipping), which is how it is used here.
+void radix_sort_pairs(pls_context* ctx, uint64_t* keys, uint32_t* vals, int64_t n, int num_passes,
+                      uint64_t** keys_out, uint32_t** vals_out);
+
+// Exclusive scan / stream compaction with a single-pass decoupled look-back.
+// flags[i] in {0,1}; pos_out[i] = number of set flags before i; *total_dev = number set.
+void exclusive_scan_flags(pls_context* ctx, const uint8_t* flags, int64_t n, uint32_t* pos_out,
+                          uint32_t* total_dev);
+
+// ---- device-side math shared by kernels ---------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// float <-> order-preserving int (for atomicMin/Max on floats)
+__device__ __forceinline__ int float_to_ordered(float f) {
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_float(int i) {
+    return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff);
+}
+#endif
+
+// ---- module entry points used across translation units -----------------------------------------
+// projection.cu
+void launch_projection(pls_context* ctx, const float* xyz, const float* channels, int batch, int64_t n,
+                       int C, int H, int W, float up, float down, float* out, unsigned long long* zbuf);
+// normal_map.cu
+void launch_normal_map(pls_context* ctx, const float* vmap, int batch, int H, int W, int ksize, float* out);
+// gn.cu
+struct GnParams {
+    int scheme;
+    double sigma;
+};
+// kdmap.cu
+void kdmap_reset(pls_context* ctx);
+// raw rows [n,3] or a vertex map [3,H,W] are packed (NaN rows / near-null pixels dropped) and
+// inserted; known_count >= 0 skips the host sync that otherwise reads the packed count.
+void kdmap_update(pls_context* ctx, const float* rel_pose_host, const float* pts_dev, int64_t n,
+                  const float* vmap_dev, int H, int W, int64_t known_count);
+// insertion of already packed float4 points (nullable) whose count the host knows
+void kdmap_update_packed(pls_context* ctx, const float* rel_pose_host, const float4* fresh_dev, int64_t num_new,
+                         bool has_new);
+// one fused ICP iteration over ctx->queries; returns the number of partial rows written
+int kdmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int num_ranks);
+// pack [n,3] rows without NaN into float4 (stable); count -> *count_dev (u32)
+void pack_valid_rows(pls_context* ctx, const float* pts_dev, int64_t n, float4* out, uint32_t* count_dev);
+// pack the non-null pixels (any channel != 0) of a [3,H,W] map into float4, row-major order
+void pack_nonnull_pixels(pls_context* ctx, const float* vmap_dev, int64_t hw, float4* out, uint32_t* count_dev);
+// grid_sample.cu
+template <typename T>
+void grid_sample_device(pls_context* ctx, const T* xyz_dev, int64_t n, double voxel, T* out_xyz_dev,
+                        long long* out_idx_dev);
+// projmap.cu
+void projmap_reset(pls_context* ctx);
+void projmap_update(pls_context* ctx, const float* rel_pose_host, const float* vmap_dev);
+// odometry.cu
+void odometry_reset(pls_context* ctx);
+// comm.cu
+void comm_allreduce_sums(pls_context* ctx, double* sums_dev);
+void comm_free(pls_context* ctx);
+
+}  // namespace pls

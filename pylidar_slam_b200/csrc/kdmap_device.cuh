@@ -1,0 +1,274 @@
+// Exact nearest-neighbour search over the kd local map: a linear BVH (Karras 2012) over the
+// Morton-sorted map points, traversed with a per-thread stack.  Device side only.
+//
+// Index layout (all in HBM, L2-resident for the BASELINE map sizes):
+//   sorted[M]   float4  map points in Morton order; .w = bit-cast insertion index
+//   nodes[M-1]  64 B    internal node i covers sorted[first..last], split after `gamma`:
+//                       left child = [first..gamma], right child = [gamma+1..last]; the node
+//                       stores BOTH child boxes, so one 64-byte fetch decides both descents.
+//                       Child ids are implicit (Karras): internal(left) = gamma,
+//                       internal(right) = gamma + 1.  Ranges of <= LEAF points are scanned
+//                       linearly (contiguous float4 loads) instead of being descended.
+//   normals[M]  float4  lazily computed unit normal of each map point, .w = 1 once valid
+#pragma once
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+namespace pls {
+
+constexpr int KD_LEAF = 4;
+constexpr int KD_STACK = 96;
+constexpr int KD_KMAX = 32;  // k + 1 <= 32
+
+struct BvhNode {
+    float lmin[3], lmax[3], rmin[3], rmax[3];
+    int first, gamma, last, pad;
+};
+static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
+
+struct KdIndex {
+    const float4* sorted;
+    const float4* nodes;  // 4 float4 per node
+    float4* normals;
+    int M;
+};
+
+__device__ __forceinline__ float dist2_point(float x, float y, float z, const float4& p) {
+    float dx = x - p.x, dy = y - p.y, dz = z - p.z;
+    return dx * dx + dy * dy + dz * dz;
+}
+
+__device__ __forceinline__ float dist2_box(float x, float y, float z, float mnx, float mny, float mnz, float mxx,
+                                           float mxy, float mxz) {
+    float dx = fmaxf(fmaxf(mnx - x, x - mxx), 0.f);
+    float dy = fmaxf(fmaxf(mny - y, y - mxy), 0.f);
+    float dz = fmaxf(fmaxf(mnz - z, z - mxz), 0.f);
+    return dx * dx + dy * dy + dz * dz;
+}
+
+// Exact 1-NN.  `hint` (a sorted position or -1) only seeds the pruning bound.
+__device__ __forceinline__ int kd_nearest(const KdIndex& ix, float x, float y, float z, int hint, float* best_out) {
+    float best = FLT_MAX;
+    int best_i = -1;
+    if (hint >= 0 && hint < ix.M) {
+        best = dist2_point(x, y, z, __ldg(ix.sorted + hint));
+        best_i = hint;
+    }
+    if (ix.M <= KD_LEAF) {
+        for (int i = 0; i < ix.M; ++i) {
+            float d = dist2_point(x, y, z, __ldg(ix.sorted + i));
+            if (d < best) { best = d; best_i = i; }
+        }
+        if (best_out) *best_out = best;
+        return best_i;
+    }
+    int stack_n[KD_STACK];
+    float stack_d[KD_STACK];
+    int sp = 0;
+    int node = 0;
+    while (true) {
+        const float4 a = __ldg(ix.nodes + 4 * (size_t)node);
+        const float4 b = __ldg(ix.nodes + 4 * (size_t)node + 1);
+        const float4 c = __ldg(ix.nodes + 4 * (size_t)node + 2);
+        const float4 dd = __ldg(ix.nodes + 4 * (size_t)node + 3);
+        const int first = __float_as_int(dd.x), gamma = __float_as_int(dd.y), last = __float_as_int(dd.z);
+        float dl = dist2_box(x, y, z, a.x, a.y, a.z, a.w, b.x, b.y);
+        float dr = dist2_box(x, y, z, b.z, b.w, c.x, c.y, c.z, c.w);
+        const bool lleaf = (gamma - first + 1) <= KD_LEAF;
+        const bool rleaf = (last - gamma) <= KD_LEAF;
+        if (lleaf && dl < best) {
+            for (int i = first; i <= gamma; ++i) {
+                float d = dist2_point(x, y, z, __ldg(ix.sorted + i));
+                if (d < best) { best = d; best_i = i; }
+            }
+        }
+        if (rleaf && dr < best) {
+            for (int i = gamma + 1; i <= last; ++i) {
+                float d = dist2_point(x, y, z, __ldg(ix.sorted + i));
+                if (d < best) { best = d; best_i = i; }
+            }
+        }
+        const bool cl = !lleaf && dl < best;
+        const bool cr = !rleaf && dr < best;
+        if (cl && cr) {
+            if (dl <= dr) {
+                if (sp < KD_STACK) { stack_n[sp] = gamma + 1; stack_d[sp] = dr; ++sp; }
+                node = gamma;
+            } else {
+                if (sp < KD_STACK) { stack_n[sp] = gamma; stack_d[sp] = dl; ++sp; }
+                node = gamma + 1;
+            }
+            continue;
+        }
+        if (cl) { node = gamma; continue; }
+        if (cr) { node = gamma + 1; continue; }
+        // pop
+        bool found = false;
+        while (sp > 0) {
+            --sp;
+            if (stack_d[sp] < best) { node = stack_n[sp]; found = true; break; }
+        }
+        if (!found) break;
+    }
+    if (best_out) *best_out = best;
+    return best_i;
+}
+
+// Sorted insertion into an ascending (d, i) list of capacity k.
+__device__ __forceinline__ void knn_insert(float* d, int* idx, int k, int& count, float dn, int in) {
+    int pos = count < k ? count : k - 1;
+    if (count == k && dn >= d[k - 1]) return;
+    while (pos > 0 && d[pos - 1] > dn) {
+        d[pos] = d[pos - 1];
+        idx[pos] = idx[pos - 1];
+        --pos;
+    }
+    d[pos] = dn;
+    idx[pos] = in;
+    if (count < k) ++count;
+}
+
+// Exact k-NN (k <= KD_KMAX): fills d[]/idx[] ascending, returns the number found (min(k, M)).
+__device__ __forceinline__ int kd_knn(const KdIndex& ix, float x, float y, float z, int k, float* d, int* idx) {
+    int count = 0;
+    if (ix.M <= KD_LEAF) {
+        for (int i = 0; i < ix.M; ++i) knn_insert(d, idx, k, count, dist2_point(x, y, z, __ldg(ix.sorted + i)), i);
+        return count;
+    }
+    int stack_n[KD_STACK];
+    float stack_d[KD_STACK];
+    int sp = 0;
+    int node = 0;
+    while (true) {
+        const float4 a = __ldg(ix.nodes + 4 * (size_t)node);
+        const float4 b = __ldg(ix.nodes + 4 * (size_t)node + 1);
+        const float4 c = __ldg(ix.nodes + 4 * (size_t)node + 2);
+        const float4 dd = __ldg(ix.nodes + 4 * (size_t)node + 3);
+        const int first = __float_as_int(dd.x), gamma = __float_as_int(dd.y), last = __float_as_int(dd.z);
+        float dl = dist2_box(x, y, z, a.x, a.y, a.z, a.w, b.x, b.y);
+        float dr = dist2_box(x, y, z, b.z, b.w, c.x, c.y, c.z, c.w);
+        const bool lleaf = (gamma - first + 1) <= KD_LEAF;
+        const bool rleaf = (last - gamma) <= KD_LEAF;
+        float worst = count < k ? FLT_MAX : d[k - 1];
+        if (lleaf && dl < worst) {
+            for (int i = first; i <= gamma; ++i)
+                knn_insert(d, idx, k, count, dist2_point(x, y, z, __ldg(ix.sorted + i)), i);
+            worst = count < k ? FLT_MAX : d[k - 1];
+        }
+        if (rleaf && dr < worst) {
+            for (int i = gamma + 1; i <= last; ++i)
+                knn_insert(d, idx, k, count, dist2_point(x, y, z, __ldg(ix.sorted + i)), i);
+            worst = count < k ? FLT_MAX : d[k - 1];
+        }
+        const bool cl = !lleaf && dl < worst;
+        const bool cr = !rleaf && dr < worst;
+        if (cl && cr) {
+            if (dl <= dr) {
+                if (sp < KD_STACK) { stack_n[sp] = gamma + 1; stack_d[sp] = dr; ++sp; }
+                node = gamma;
+            } else {
+                if (sp < KD_STACK) { stack_n[sp] = gamma; stack_d[sp] = dl; ++sp; }
+                node = gamma + 1;
+            }
+            continue;
+        }
+        if (cl) { node = gamma; continue; }
+        if (cr) { node = gamma + 1; continue; }
+        bool found = false;
+        while (sp > 0) {
+            --sp;
+            float w2 = count < k ? FLT_MAX : d[k - 1];
+            if (stack_d[sp] < w2) { node = stack_n[sp]; found = true; break; }
+        }
+        if (!found) break;
+    }
+    return count;
+}
+
+// Eigenvector of the smallest eigenvalue of a symmetric 3x3 matrix (cyclic Jacobi, fp64).
+__device__ __forceinline__ void smallest_eigenvector(const float* c /*xx,xy,xz,yy,yz,zz*/, float* n) {
+    double A[3][3] = {{c[0], c[1], c[2]}, {c[1], c[3], c[4]}, {c[2], c[4], c[5]}};
+    double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+        double diag = fabs(A[0][0]) + fabs(A[1][1]) + fabs(A[2][2]);
+        if (off <= 1e-18 * diag || off == 0.0) break;
+#pragma unroll
+        for (int pq = 0; pq < 3; ++pq) {
+            const int p = pq == 2 ? 1 : 0;
+            const int q = pq == 0 ? 1 : 2;
+            double apq = A[p][q];
+            if (apq == 0.0) continue;
+            double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+            double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                double akp = A[k][p], akq = A[k][q];
+                A[k][p] = cs * akp - sn * akq;
+                A[k][q] = sn * akp + cs * akq;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                double apk = A[p][k], aqk = A[q][k];
+                A[p][k] = cs * apk - sn * aqk;
+                A[q][k] = sn * apk + cs * aqk;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                double vkp = V[k][p], vkq = V[k][q];
+                V[k][p] = cs * vkp - sn * vkq;
+                V[k][q] = sn * vkp + cs * vkq;
+            }
+        }
+    }
+    int m = 0;
+    if (A[1][1] < A[m][m]) m = 1;
+    if (A[2][2] < A[m][m]) m = 2;
+    double nx = V[0][m], ny = V[1][m], nz = V[2][m];
+    double inv = 1.0 / sqrt(nx * nx + ny * ny + nz * nz);
+    n[0] = (float)(nx * inv);
+    n[1] = (float)(ny * inv);
+    n[2] = (float)(nz * inv);
+}
+
+// Normal of map point `pos` (sorted position): the k nearest OTHER map points, second moments
+// about the point itself (not the mean), float32 sequential sums, smallest-eigenvalue direction
+// (slam/odometry/local_map.py:397-422).
+__device__ __forceinline__ void kd_point_normal(const KdIndex& ix, int pos, int k, float* n) {
+    const float4 c = __ldg(ix.sorted + pos);
+    float d[KD_KMAX];
+    int idx[KD_KMAX];
+    int found = kd_knn(ix, c.x, c.y, c.z, k + 1, d, idx);
+    float sxx = 0.f, sxy = 0.f, sxz = 0.f, syy = 0.f, syz = 0.f, szz = 0.f;
+    for (int j = 1; j < found; ++j) {  // entry 0 is the point itself (distance 0)
+        const float4 q = __ldg(ix.sorted + idx[j]);
+        float dx = __fsub_rn(q.x, c.x), dy = __fsub_rn(q.y, c.y), dz = __fsub_rn(q.z, c.z);
+        sxx = __fadd_rn(sxx, __fmul_rn(dx, dx));
+        sxy = __fadd_rn(sxy, __fmul_rn(dx, dy));
+        sxz = __fadd_rn(sxz, __fmul_rn(dx, dz));
+        syy = __fadd_rn(syy, __fmul_rn(dy, dy));
+        syz = __fadd_rn(syz, __fmul_rn(dy, dz));
+        szz = __fadd_rn(szz, __fmul_rn(dz, dz));
+    }
+    const float kk = (float)k;
+    float cov[6] = {__fdiv_rn(sxx, kk), __fdiv_rn(sxy, kk), __fdiv_rn(sxz, kk),
+                    __fdiv_rn(syy, kk), __fdiv_rn(syz, kk), __fdiv_rn(szz, kk)};
+    smallest_eigenvector(cov, n);
+}
+
+// Cached normal of map point `pos`; computes and publishes it on first use.  The 16-byte
+// store carries normal and valid flag together, so a concurrent reader sees either the old
+// (flag 0) or the complete new value; concurrent writers store identical bits.
+__device__ __forceinline__ void kd_cached_normal(const KdIndex& ix, int pos, int k, float* n) {
+    float4 v = __ldcg(ix.normals + pos);
+    if (v.w == 0.f) {
+        kd_point_normal(ix, pos, k, n);
+        __stcg(ix.normals + pos, make_float4(n[0], n[1], n[2], 1.f));
+    } else {
+        n[0] = v.x; n[1] = v.y; n[2] = v.z;
+    }
+}
+
+}  // namespace pls

@@ -1,0 +1,391 @@
+// The frame-to-model ICP odometry state machine (replaces ICPFrameToModel,
+// slam/odometry/icp_odometry.py:72-380) driven from the host with NO per-iteration host sync:
+// every ICP iteration is {correspondence+reduction kernel, [allreduce], icp_step_kernel}; the
+// convergence test (icp_odometry.py:292), the Gauss-Newton guards (optimization.py:323-336) and
+// the pose composition with its Euler round trip (icp_odometry.py:296-297) run on the device
+// and latch a `done` flag that turns the remaining launches of the frame into no-ops.
+// One device->host copy of the FrameResult ends the frame.
+#include "internal.cuh"
+#include "pose_device.cuh"
+
+namespace pls {
+
+// projmap.cu
+int projmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int num_ranks);
+// comm.cu
+int comm_rank(pls_context* ctx);
+int comm_size(pls_context* ctx);
+
+namespace {
+
+__global__ void frame_begin_kernel(FrameResult* fr, const float* T0 /*16, device or null*/, int max_iters) {
+    int t = threadIdx.x;
+    if (t < 16) fr->T[t] = T0 ? T0[t] : ((t % 5 == 0) ? 1.f : 0.f);
+    if (t < 6) fr->params[t] = 0.f;
+    if (t < kMaxAlign) fr->losses[t] = __int_as_float(0x7fc00000);
+    if (t == 0) {
+        fr->iters = 0;
+        fr->status = 0;
+        fr->done = 0;
+    }
+    if (t < NACC) fr->last_sums[t] = 0.0;
+}
+
+__global__ void reduce_partials_kernel(FrameResult* fr, const double* __restrict__ partials, int num_blocks) {
+    if (fr->done) return;
+    if (threadIdx.x < NACC) {
+        double s = 0.0;
+        for (int b = 0; b < num_blocks; ++b) s += partials[(size_t)b * NACC + threadIdx.x];
+        fr->last_sums[threadIdx.x] = s;
+    }
+}
+
+// K7: normal-equation solve + ICP bookkeeping.  num_blocks == 0: last_sums already holds the
+// (all-reduced) sums.
+__global__ void icp_step_kernel(FrameResult* fr, const double* __restrict__ partials, int num_blocks,
+                                float threshold_delta) {
+    if (fr->done) return;
+    __shared__ double sums[NACC];
+    if (threadIdx.x < NACC) {
+        double s = 0.0;
+        if (num_blocks > 0) {
+            for (int b = 0; b < num_blocks; ++b) s += partials[(size_t)b * NACC + threadIdx.x];
+            fr->last_sums[threadIdx.x] = s;
+        } else {
+            s = fr->last_sums[threadIdx.x];
+        }
+        sums[threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const int it = fr->iters;
+    fr->iters = it + 1;
+    // optimization.py:323-327: |r| < 1e-7 -> warning, x stays 0, residuals r^2; then delta = 0 breaks the loop
+    if (sqrt(sums[28]) < 1e-7) {
+        fr->losses[it] = (float)sums[28];
+        fr->status = PLS_W_TINY_RESIDUAL;
+        fr->done = 1;
+        return;
+    }
+    double dx[6];
+    const double det = solve6(sums, dx);
+    if (!(fabs(det) >= 1e-7)) {  // optimization.py:334-336
+        fr->status = PLS_E_SINGULAR;
+        fr->done = 1;
+        return;
+    }
+    fr->losses[it] = (float)sums[27];
+    float delta[6];
+    float n2 = 0.f;
+    for (int i = 0; i < 6; ++i) {
+        delta[i] = (float)dx[i];
+        n2 += delta[i] * delta[i];
+    }
+    if (sqrtf(n2) < threshold_delta) {  // icp_odometry.py:292-293: the last delta is not applied
+        fr->done = 1;
+        return;
+    }
+    float dT[16], Tn[16], prm[6];
+    build_pose(delta, dT);
+    mat4_mul(dT, fr->T, Tn);
+    from_pose(Tn, prm);          // icp_odometry.py:296
+    build_pose(prm, fr->T);      // icp_odometry.py:297
+    for (int i = 0; i < 6; ++i) fr->params[i] = prm[i];
+}
+
+__global__ void scrub_vertex_map_kernel(const float* __restrict__ in, int64_t hw, float* __restrict__ out) {
+    // modify_nan_pmap (utils.py:187-196): a pixel with any NaN channel becomes 0
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (int64_t)gridDim.x * blockDim.x) {
+        float x = in[i], y = in[hw + i], z = in[2 * hw + i];
+        bool bad = !(x == x) || !(y == y) || !(z == z);
+        out[i] = bad ? 0.f : x;
+        out[hw + i] = bad ? 0.f : y;
+        out[2 * hw + i] = bad ? 0.f : z;
+    }
+}
+
+__global__ void first_point_kernel(const float4* __restrict__ packed, const uint32_t* __restrict__ count,
+                                   float4* __restrict__ out, uint32_t* __restrict__ out_count, FrameResult* fr) {
+    // reference quirk (icp_odometry.py:342-344,356-358): with a vertex-map input `_tgt_pc` keeps
+    // only the first non-null pixel
+    if (threadIdx.x == 0) {
+        uint32_t c = *count;
+        if (c > 0) {
+            out[0] = packed[0];
+            fr->first_pt[0] = packed[0].x; fr->first_pt[1] = packed[0].y; fr->first_pt[2] = packed[0].z;
+        }
+        *out_count = c > 0 ? 1u : 0u;
+    }
+}
+
+inline int grid_for(int64_t n, int threads = 256) {
+    int64_t b = (n + threads - 1) / threads;
+    int64_t cap = 8 * kNumSMs;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+uint32_t* count_slot(pls_context* ctx, int i) { return reinterpret_cast<uint32_t*>(&frame_result_dev(ctx)->counts[i]); }
+
+// The ICP loop (icp_odometry.py:248-299) over ctx->queries / counts[1].
+void run_icp(pls_context* ctx, const float* T0_dev, int64_t query_bound) {
+    cudaStream_t st = ctx->stream;
+    FrameResult* fr = frame_result_dev(ctx);
+    frame_begin_kernel<<<1, kMaxAlign, 0, st>>>(fr, T0_dev, ctx->cfg.max_num_alignments);
+    PLS_CHECK_LAUNCH();
+    if (query_bound < 1) query_bound = 1;
+    ctx->nn_prev.reserve((size_t)query_bound * sizeof(int), st);
+    PLS_CUDA(cudaMemsetAsync(ctx->nn_prev.p, 0xff, (size_t)query_bound * sizeof(int), st));
+    const int rank = comm_rank(ctx), size = comm_size(ctx);
+    for (int it = 0; it < ctx->cfg.max_num_alignments; ++it) {
+        int blocks;
+        if (ctx->cfg.local_map_type == PLS_MAP_KDTREE) blocks = kdmap_icp_iteration(ctx, query_bound, rank, size);
+        else blocks = projmap_icp_iteration(ctx, query_bound, rank, size);
+        if (size > 1) {
+            reduce_partials_kernel<<<1, 32, 0, st>>>(fr, ctx->partials.as<double>(), blocks);
+            PLS_CHECK_LAUNCH();
+            comm_allreduce_sums(ctx, fr->last_sums);
+            blocks = 0;
+        }
+        icp_step_kernel<<<1, 32, 0, st>>>(fr, ctx->partials.as<double>(), blocks, ctx->cfg.threshold_delta_pose);
+        PLS_CHECK_LAUNCH();
+    }
+}
+
+void fetch_result(pls_context* ctx) {
+    PLS_CUDA(cudaMemcpyAsync(ctx->pinned.p, ctx->scalars.p, sizeof(FrameResult), cudaMemcpyDeviceToHost, ctx->stream));
+    PLS_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+void raise_status(pls_context* ctx, int status) {
+    if (status == PLS_E_SINGULAR) throw pls::Error{PLS_E_SINGULAR, "Invalid Jacobian in Gauss Newton minimization"};
+}
+
+// __update_map (icp_odometry.py:360-380), host side: key-frame policy on the accumulated motion.
+bool keyframe_decision(pls_context* ctx, const float* T) {
+    float nd[16], prm[6];
+    mat4_mul(ctx->delta_since_update, T, nd);
+    from_pose(nd, prm);
+    const float tn = sqrtf(prm[0] * prm[0] + prm[1] * prm[1] + prm[2] * prm[2]);
+    const float rn = sqrtf(prm[3] * prm[3] + prm[4] * prm[4] + prm[5] * prm[5]);
+    const bool insert = tn > ctx->cfg.threshold_trans || rn * 180.0f / 3.14159265358979323846f > ctx->cfg.threshold_rot;
+    if (insert) {
+        for (int i = 0; i < 16; ++i) ctx->delta_since_update[i] = (i % 5 == 0) ? 1.f : 0.f;
+    } else {
+        memcpy(ctx->delta_since_update, nd, sizeof(nd));
+    }
+    return insert;
+}
+
+void process_frame_device(pls_context* ctx, const float* data_dev, int layout, int64_t n, const float* init_pose,
+                          float* out_pose, float* out_params, int* out_has_pose, double* out_info) {
+    cudaStream_t st = ctx->stream;
+    const int H = ctx->cfg.height, W = ctx->cfg.width;
+    const int64_t hw = (int64_t)H * W;
+    const bool kd = ctx->cfg.local_map_type == PLS_MAP_KDTREE;
+    FrameResult* fr = frame_result_dev(ctx);
+    PLS_CUDA(cudaMemsetAsync(fr->counts, 0, sizeof(fr->counts), st));
+    if (layout == PLS_INPUT_NDARRAY) ctx->sample_pointcloud = 1;  // icp_odometry.py:330
+    const bool first = ctx->frame_index == 0;
+
+    // ---- _read_input (icp_odometry.py:319-358)
+    ctx->frame_vmap.reserve((size_t)3 * hw * sizeof(float), st);
+    int64_t pts_bound = 0;
+    if (layout == PLS_INPUT_VERTEX_MAP) {
+        scrub_vertex_map_kernel<<<grid_for(hw), 256, 0, st>>>(data_dev, hw, ctx->frame_vmap.as<float>());
+        PLS_CHECK_LAUNCH();
+        ctx->tmp[5].reserve((size_t)hw * sizeof(float4), st);
+        pack_nonnull_pixels(ctx, ctx->frame_vmap.as<float>(), hw, ctx->tmp[5].as<float4>(), count_slot(ctx, 1));
+        ctx->frame_pts.reserve(sizeof(float4) * 4, st);
+        first_point_kernel<<<1, 32, 0, st>>>(ctx->tmp[5].as<float4>(), count_slot(ctx, 1), ctx->frame_pts.as<float4>(),
+                                              count_slot(ctx, 2), fr);
+        PLS_CHECK_LAUNCH();
+        pts_bound = 1;
+    } else {
+        PLS_REQUIRE(n > 0, "process_frame: empty point cloud");
+        ctx->frame_pts.reserve((size_t)n * sizeof(float4), st);
+        pack_valid_rows(ctx, data_dev, n, ctx->frame_pts.as<float4>(), count_slot(ctx, 2));
+        pts_bound = n;
+        // the vertex map of the points is needed on frame 0 (map initialisation), as the query
+        // source when _sample_pointcloud is False, and by the projective map's update
+        if (first || !ctx->sample_pointcloud || !kd) {
+            ctx->tmp[3].reserve((size_t)hw * sizeof(unsigned long long), st);
+            launch_projection(ctx, data_dev, nullptr, 1, n, 3, H, W, ctx->cfg.up_fov_deg, ctx->cfg.down_fov_deg,
+                              ctx->frame_vmap.as<float>(), ctx->tmp[3].as<unsigned long long>());
+            }
+    }
+
+    float eye[16];
+    for (int i = 0; i < 16; ++i) eye[i] = (i % 5 == 0) ? 1.f : 0.f;
+
+    if (first) {
+        // icp_odometry.py:171-181: the first frame only initialises the map, via its vertex map
+        if (kd) kdmap_update(ctx, eye, nullptr, 0, ctx->frame_vmap.as<float>(), H, W, -1);
+        else projmap_update(ctx, eye, ctx->frame_vmap.as<float>());
+        ctx->frame_index = 1;
+        if (out_has_pose) *out_has_pose = 0;
+        if (out_pose) memcpy(out_pose, eye, sizeof(eye));
+        if (out_params) memset(out_params, 0, 6 * sizeof(float));
+        fetch_result(ctx);
+        if (out_info) {
+            FrameResult* h = frame_result_host(ctx);
+            for (int i = 0; i < 12; ++i) out_info[i] = 0.0;
+            out_info[3] = (double)ctx->kd.count;
+            out_info[5] = (double)(pts_bound - (int64_t)h->counts[2]);
+        }
+        return;
+    }
+
+    // ---- sample_points (icp_odometry.py:301-308)
+    int64_t query_bound;
+    if (ctx->sample_pointcloud && layout != PLS_INPUT_VERTEX_MAP) {
+        // queries = the (NaN-free) input points themselves
+        ctx->query_ptr = ctx->frame_pts.as<float4>();
+        PLS_CUDA(cudaMemcpyAsync(count_slot(ctx, 1), count_slot(ctx, 2), sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        query_bound = n;
+    } else if (layout == PLS_INPUT_VERTEX_MAP) {
+        ctx->query_ptr = ctx->tmp[5].as<float4>();
+        query_bound = hw;
+    } else {
+        ctx->queries.reserve((size_t)hw * sizeof(float4), st);
+        pack_nonnull_pixels(ctx, ctx->frame_vmap.as<float>(), hw, ctx->queries.as<float4>(), count_slot(ctx, 1));
+        ctx->query_ptr = ctx->queries.as<float4>();
+        query_bound = n < hw ? n : hw;
+    }
+
+    // ---- register_new_frame
+    const float* T0_dev = nullptr;
+    if (init_pose) {
+        ctx->tmp[6].reserve(16 * sizeof(float), st);
+        PLS_CUDA(cudaMemcpyAsync(ctx->tmp[6].p, init_pose, 16 * sizeof(float), cudaMemcpyHostToDevice, st));
+        T0_dev = ctx->tmp[6].as<float>();
+    }
+    run_icp(ctx, T0_dev, query_bound);
+    fetch_result(ctx);
+    FrameResult* h = frame_result_host(ctx);
+    raise_status(ctx, h->status);
+
+    // ---- __update_map
+    const bool insert = keyframe_decision(ctx, h->T);
+    if (kd) {
+        if (insert) kdmap_update_packed(ctx, h->T, ctx->frame_pts.as<float4>(), (int64_t)h->counts[2], true);
+        else kdmap_update_packed(ctx, h->T, nullptr, 0, false);
+    } else {
+        projmap_update(ctx, h->T, insert ? ctx->frame_vmap.as<float>() : nullptr);
+    }
+    ctx->frame_index += 1;
+    if (out_pose) memcpy(out_pose, h->T, 16 * sizeof(float));
+    if (out_params) memcpy(out_params, h->params, 6 * sizeof(float));
+    if (out_has_pose) *out_has_pose = 1;
+    if (out_info) {
+        out_info[0] = (double)h->iters;
+        out_info[1] = h->iters > 0 ? (double)h->losses[h->iters - 1] : 0.0;
+        out_info[2] = (double)h->counts[1];
+        out_info[3] = (double)ctx->kd.count;
+        out_info[4] = (double)h->counts[0];
+        out_info[5] = (double)(pts_bound - (int64_t)h->counts[2]);
+        out_info[6] = (double)h->status;
+        out_info[7] = insert ? 1.0 : 0.0;
+        out_info[8] = h->first_pt[0]; out_info[9] = h->first_pt[1]; out_info[10] = h->first_pt[2];
+        out_info[11] = 0.0;
+    }
+}
+
+}  // namespace
+
+void odometry_reset(pls_context* ctx) {
+    kdmap_reset(ctx);
+    projmap_reset(ctx);
+    ctx->frame_index = 0;
+    ctx->sample_pointcloud = 0;
+    for (int i = 0; i < 16; ++i) ctx->delta_since_update[i] = (i % 5 == 0) ? 1.f : 0.f;
+}
+
+}  // namespace pls
+
+using namespace pls;
+
+extern "C" {
+
+int pls_map_init(pls_context* ctx) {
+    PLS_API_BEGIN(ctx)
+    kdmap_reset(ctx);
+    projmap_reset(ctx);
+    PLS_API_END(ctx)
+}
+
+int pls_odometry_init(pls_context* ctx) {
+    PLS_API_BEGIN(ctx)
+    PLS_CUDA(cudaStreamSynchronize(ctx->stream));
+    odometry_reset(ctx);
+    PLS_API_END(ctx)
+}
+
+int pls_register_frame(pls_context* ctx, const float* points, int64_t n, const float* T0, float* out_T,
+                       float* out_params, float* out_losses, int* out_iters) {
+    PLS_API_BEGIN(ctx)
+    PLS_REQUIRE(points && n > 0, "pls_register_frame: points must be [n,3] with n > 0");
+    PLS_REQUIRE(ctx->cfg.gn_max_iters == 1, "fused ICP path supports gauss_newton_config.max_iters == 1");
+    cudaStream_t st = ctx->stream;
+    const float* d = (const float*)to_device(ctx, points, (size_t)n * 3 * sizeof(float), ctx->stage_in[0]);
+    FrameResult* fr = frame_result_dev(ctx);
+    PLS_CUDA(cudaMemsetAsync(fr->counts, 0, sizeof(fr->counts), st));
+    ctx->queries.reserve((size_t)n * sizeof(float4), st);
+    pack_valid_rows(ctx, d, n, ctx->queries.as<float4>(), count_slot(ctx, 1));
+    ctx->query_ptr = ctx->queries.as<float4>();
+    const float* T0_dev = nullptr;
+    if (T0) {
+        ctx->tmp[6].reserve(16 * sizeof(float), st);
+        PLS_CUDA(cudaMemcpyAsync(ctx->tmp[6].p, T0, 16 * sizeof(float),
+                                 is_device_ptr(T0) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        T0_dev = ctx->tmp[6].as<float>();
+    }
+    run_icp(ctx, T0_dev, n);
+    fetch_result(ctx);
+    FrameResult* h = frame_result_host(ctx);
+    auto put = [&](void* dst, const void* src, size_t bytes) {
+        if (!dst) return;
+        if (is_device_ptr(dst)) PLS_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+        else memcpy(dst, src, bytes);
+    };
+    put(out_T, h->T, 16 * sizeof(float));
+    put(out_params, h->params, 6 * sizeof(float));
+    put(out_losses, h->losses, (size_t)ctx->cfg.max_num_alignments * sizeof(float));
+    if (out_iters) *out_iters = h->iters;
+    raise_status(ctx, h->status);
+    PLS_API_END(ctx)
+}
+
+int pls_process_frame(pls_context* ctx, const float* data, int layout, int64_t n, const float* init_pose,
+                      float* out_pose, float* out_params, int* out_has_pose, double* out_info) {
+    PLS_API_BEGIN(ctx)
+    PLS_REQUIRE(data, "pls_process_frame: null data");
+    PLS_REQUIRE(layout >= PLS_INPUT_NDARRAY && layout <= PLS_INPUT_VERTEX_MAP, "pls_process_frame: unknown layout");
+    PLS_REQUIRE(ctx->cfg.gn_max_iters == 1, "fused ICP path supports gauss_newton_config.max_iters == 1");
+    const size_t bytes = layout == PLS_INPUT_VERTEX_MAP ? (size_t)3 * ctx->cfg.height * ctx->cfg.width * sizeof(float)
+                                                        : (size_t)n * 3 * sizeof(float);
+    const float* d = (const float*)to_device(ctx, data, bytes, ctx->stage_in[0]);
+    process_frame_device(ctx, d, layout, n, init_pose, out_pose, out_params, out_has_pose, out_info);
+    PLS_API_END(ctx)
+}
+
+int pls_process_frame_grid_sample(pls_context* ctx, const float* raw_points, int64_t n, double voxel, int layout,
+                                  const float* init_pose, float* out_pose, float* out_params, int* out_has_pose,
+                                  double* out_info) {
+    PLS_API_BEGIN(ctx)
+    PLS_REQUIRE(raw_points && n > 0 && voxel > 0.0, "pls_process_frame_grid_sample: bad arguments");
+    PLS_REQUIRE(layout == PLS_INPUT_NDARRAY || layout == PLS_INPUT_TENSOR, "grid-sampled input is a point layout");
+    PLS_REQUIRE(ctx->cfg.gn_max_iters == 1, "fused ICP path supports gauss_newton_config.max_iters == 1");
+    const float* d = (const float*)to_device(ctx, raw_points, (size_t)n * 3 * sizeof(float), ctx->stage_in[0]);
+    ctx->gs_out_xyz.reserve((size_t)n * 3 * sizeof(float), ctx->stream);
+    grid_sample_device<float>(ctx, d, n, voxel, ctx->gs_out_xyz.as<float>(), nullptr);
+    // the sample count is needed on the host to size the point-layout frame: one small sync
+    uint32_t S = 0;
+    PLS_CUDA(cudaMemcpyAsync(&S, scalar_u32(ctx, SC_GS_COUNT), sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PLS_CUDA(cudaStreamSynchronize(ctx->stream));
+    process_frame_device(ctx, ctx->gs_out_xyz.as<float>(), layout, (int64_t)S, init_pose, out_pose, out_params,
+                         out_has_pose, out_info);
+    if (out_info) out_info[4] = (double)S;
+    PLS_API_END(ctx)
+}
+
+}  // extern "C"

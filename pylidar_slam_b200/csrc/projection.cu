@@ -1,0 +1,136 @@
+// K2 -- spherical range-image projection with a closest-wins z-buffer.
+//
+//   pixel math     : r = |p|, theta = -atan2(y, x), phi = asin(z / r),
+//                    col = W * 0.5 (theta/pi + 1), row = H (1 - (phi + |fov_down|)/fov), float32
+//                    in the reference's operation order (slam/common/projection.py:11-73).
+//   zbuf_kernel    : rounds half-to-even, keeps 0 <= row <= H-1, 0 <= col <= W-1, r > 0 and does
+//                    one 64-bit atomicMin of (float_bits(r) << 32 | point index) per point --
+//                    the closest point per pixel wins, lowest index on exact range ties.  This is
+//                    the deterministic form of "sort by descending range, scatter"
+//                    (projection.py:393-415).
+//   resolve_kernel : one thread per pixel gathers the winner's C channels into the planar
+//                    [B,C,H,W] image; empty pixels are 0.
+#include "internal.cuh"
+#include "projection_device.cuh"
+
+namespace pls {
+
+namespace {
+
+__global__ void project_pixels_kernel(const float* __restrict__ xyz, int64_t n, ProjConst pc,
+                                      float* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float row, col, r;
+        project_point(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], pc, row, col, r);
+        out[2 * i] = row;
+        out[2 * i + 1] = col;
+    }
+}
+
+__global__ void zbuf_kernel(const float* __restrict__ xyz, int batch, int64_t n, ProjConst pc,
+                            unsigned long long* __restrict__ zbuf) {
+    const int64_t total = (int64_t)batch * n;
+    const int64_t hw = (int64_t)pc.H * pc.W;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        int64_t b = g / n, i = g - b * n;
+        int pix;
+        float r;
+        if (project_to_pixel(xyz[3 * g], xyz[3 * g + 1], xyz[3 * g + 2], pc, pix, r)) {
+            unsigned long long key = ((unsigned long long)__float_as_uint(r) << 32) | (unsigned long long)(uint32_t)i;
+            atomicMin(&zbuf[b * hw + pix], key);
+        }
+    }
+}
+
+__global__ void resolve_kernel(const unsigned long long* __restrict__ zbuf, const float* __restrict__ values,
+                               int batch, int64_t n, int C, int64_t hw, float* __restrict__ out) {
+    const int64_t total = (int64_t)batch * hw;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        int64_t b = g / hw, pix = g - b * hw;
+        unsigned long long key = zbuf[g];
+        float* o = out + (size_t)b * C * hw + pix;
+        if (key == ~0ull) {
+            for (int c = 0; c < C; ++c) o[(size_t)c * hw] = 0.f;
+        } else {
+            const float* v = values + ((size_t)b * n + (uint32_t)(key & 0xffffffffull)) * C;
+            for (int c = 0; c < C; ++c) o[(size_t)c * hw] = v[c];
+        }
+    }
+}
+
+inline int grid_for(int64_t n, int threads = 256) {
+    int64_t b = (n + threads - 1) / threads;
+    int64_t cap = 16 * kNumSMs;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+ProjConst make_proj_const(int H, int W, float up_deg, float down_deg) {
+    ProjConst pc;
+    pc.H = H;
+    pc.W = W;
+    double up = (double)up_deg / 180.0 * 3.141592653589793;
+    double down = (double)down_deg / 180.0 * 3.141592653589793;
+    pc.abs_down = (float)fabs(down);
+    pc.fov = (float)(fabs(down) + fabs(up));
+    pc.Wf = (float)W;
+    pc.Hf = (float)H;
+    return pc;
+}
+
+void launch_projection(pls_context* ctx, const float* xyz, const float* channels, int batch, int64_t n, int C, int H,
+                       int W, float up, float down, float* out, unsigned long long* zbuf) {
+    cudaStream_t st = ctx->stream;
+    const int64_t hw = (int64_t)H * W;
+    PLS_REQUIRE(n < (1ll << 32), "projection: at most 2^32 points per cloud");
+    ProjConst pc = make_proj_const(H, W, up, down);
+    PLS_CUDA(cudaMemsetAsync(zbuf, 0xff, (size_t)batch * hw * sizeof(unsigned long long), st));
+    if (n > 0) {
+        zbuf_kernel<<<grid_for((int64_t)batch * n), 256, 0, st>>>(xyz, batch, n, pc, zbuf);
+        PLS_CHECK_LAUNCH();
+    }
+    resolve_kernel<<<grid_for((int64_t)batch * hw), 256, 0, st>>>(zbuf, channels ? channels : xyz, batch, n, C, hw, out);
+    PLS_CHECK_LAUNCH();
+}
+
+}  // namespace pls
+
+using namespace pls;
+
+extern "C" {
+
+int pls_project_pixels(pls_context* ctx, const float* xyz, int64_t n, int height, int width, float up_fov_deg,
+                       float down_fov_deg, float* rows_cols_out) {
+    PLS_API_BEGIN(ctx)
+    PLS_REQUIRE(xyz && rows_cols_out && n > 0 && height > 0 && width > 0, "pls_project_pixels: bad arguments");
+    const float* d = (const float*)to_device(ctx, xyz, (size_t)n * 3 * sizeof(float), ctx->stage_in[0]);
+    OutArg o = out_arg(ctx, rows_cols_out, (size_t)n * 2 * sizeof(float), ctx->stage_out[0]);
+    project_pixels_kernel<<<grid_for(n), 256, 0, ctx->stream>>>(d, n, make_proj_const(height, width, up_fov_deg, down_fov_deg),
+                                                               (float*)o.dev);
+    PLS_CHECK_LAUNCH();
+    finish_out(ctx, o);
+    PLS_CUDA(cudaStreamSynchronize(ctx->stream));
+    PLS_API_END(ctx)
+}
+
+int pls_build_projection_map(pls_context* ctx, const float* xyz, const float* channels, int batch, int64_t n,
+                             int num_channels, int height, int width, float up_fov_deg, float down_fov_deg,
+                             float* out) {
+    PLS_API_BEGIN(ctx)
+    PLS_REQUIRE(xyz && out && batch > 0 && n >= 0 && height > 0 && width > 0, "pls_build_projection_map: bad arguments");
+    const int C = channels ? num_channels : 3;
+    PLS_REQUIRE(C >= 1 && C <= 64, "pls_build_projection_map: 1..64 channels");
+    const int64_t hw = (int64_t)height * width;
+    const float* d_xyz = (const float*)to_device(ctx, xyz, (size_t)batch * n * 3 * sizeof(float), ctx->stage_in[0]);
+    const float* d_ch = (const float*)to_device(ctx, channels, (size_t)batch * n * C * sizeof(float), ctx->stage_in[1]);
+    OutArg o = out_arg(ctx, out, (size_t)batch * C * hw * sizeof(float), ctx->stage_out[0]);
+    ctx->tmp[3].reserve((size_t)batch * hw * sizeof(unsigned long long), ctx->stream);
+    launch_projection(ctx, d_xyz, d_ch, batch, n, C, height, width, up_fov_deg, down_fov_deg, (float*)o.dev,
+                      ctx->tmp[3].as<unsigned long long>());
+    finish_out(ctx, o);
+    PLS_CUDA(cudaStreamSynchronize(ctx->stream));
+    PLS_API_END(ctx)
+}
+
+}  // extern "C"

