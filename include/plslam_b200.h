@@ -219,6 +219,8 @@ PLS_API int pls_comm_destroy(pls_context* ctx);
  * kernel, 2 = model rebuild, 3 = index build, 4 = grid sample, 5 = Gauss-Newton solve.
  * pls_profile_read returns the accumulated device milliseconds, launch count and the
  * algorithmic bytes the launches moved (DESIGN.md states the per-unit figures). */
+/* Number of CUDA kernels this library has launched in this process (all contexts). */
+PLS_API int pls_launch_count(int64_t* out);
 PLS_API int pls_profile_enable(pls_context* ctx, int which, int enable);
 PLS_API int pls_profile_read(pls_context* ctx, int which, double* ms_total, int64_t* launches,
                      double* algorithmic_bytes, int reset);

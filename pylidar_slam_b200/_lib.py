@@ -60,6 +60,7 @@ _SIGNATURES = {
     "pls_comm_init": [_P, _I, _I, _P, C.c_char_p],
     "pls_comm_unique_id": [C.c_char_p, _P],
     "pls_comm_destroy": [_P],
+    "pls_launch_count": [C.POINTER(_L)],
     "pls_profile_enable": [_P, _I, _I],
     "pls_profile_read": [_P, _I, C.POINTER(_D), C.POINTER(_L), C.POINTER(_D), _I],
 }
@@ -143,6 +144,17 @@ class Context:
             raise RuntimeError(f"pls_create failed with status {st}: a CUDA device and the sm_100a library are "
                                f"required (there is no CPU fallback)")
         self.lib = lib
+
+    def launch_count(self) -> int:
+        n = C.c_int64(0)
+        self.lib.pls_launch_count(C.byref(n))
+        return n.value
+
+    def profile(self, which: int, reset: bool = True):
+        """(device ms, launches, algorithmic bytes) accumulated in profile slot `which`."""
+        ms, n, b = C.c_double(0), C.c_int64(0), C.c_double(0)
+        self.call("pls_profile_read", which, C.byref(ms), C.byref(n), C.byref(b), int(reset))
+        return ms.value, n.value, b.value
 
     def call(self, name, *args):
         return check(self.handle, getattr(self.lib, name)(self.handle, *args))

@@ -3,6 +3,8 @@
 
 namespace pls {
 
+long long g_kernel_launches = 0;
+
 void DBuf::reserve(size_t bytes, cudaStream_t s, bool keep) {
     if (bytes <= cap) return;
     size_t want = bytes + bytes / 4 + 256;
@@ -75,7 +77,7 @@ void finish_out(pls_context* ctx, const OutArg& o, size_t bytes_used) {
     if (b) PLS_CUDA(cudaMemcpyAsync(o.host, o.dev, b, cudaMemcpyDeviceToHost, ctx->stream));
 }
 
-ProfileScope::ProfileScope(pls_context* c, int w, double bytes) : ctx(c), which(w) {
+ProfileScope::ProfileScope(pls_context* c, int w, double bytes, bool count) : ctx(c), which(w) {
     ProfileSlot& s = ctx->prof[which];
     if (!s.enabled) return;
     if (s.used >= 4096) {
@@ -91,8 +93,10 @@ ProfileScope::ProfileScope(pls_context* c, int w, double bytes) : ctx(c), which(
     }
     e0 = s.pool[s.used++];
     e1 = s.pool[s.used++];
-    s.bytes += bytes;
-    s.launches += 1;
+    if (count) {
+        s.bytes += bytes;
+        s.launches += 1;
+    }
     cudaEventRecord(e0, ctx->stream);
 }
 
@@ -116,6 +120,12 @@ using namespace pls;
 extern "C" {
 
 const char* pls_version(void) { return "plslam_b200 0.1 (sm_100a)"; }
+
+int pls_launch_count(int64_t* out) {
+    if (!out) return PLS_E_INVALID;
+    *out = (int64_t)pls::g_kernel_launches;
+    return PLS_OK;
+}
 
 int pls_config_default(pls_config* c) {
     if (!c) return PLS_E_INVALID;

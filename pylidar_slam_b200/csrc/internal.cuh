@@ -24,6 +24,8 @@ struct Error {
     std::string msg;
 };
 
+extern long long g_kernel_launches;
+
 #define PLS_CUDA(expr)                                                                            \
     do {                                                                                          \
         cudaError_t _e = (expr);                                                                  \
@@ -33,7 +35,12 @@ struct Error {
         }                                                                                         \
     } while (0)
 
-#define PLS_CHECK_LAUNCH() PLS_CUDA(cudaGetLastError())
+// every kernel launch of the library is followed by this check, which also counts it
+#define PLS_CHECK_LAUNCH()            \
+    do {                              \
+        ++pls::g_kernel_launches;     \
+        PLS_CUDA(cudaGetLastError()); \
+    } while (0)
 
 #define PLS_REQUIRE(cond, text)                                   \
     do {                                                          \
@@ -213,10 +220,17 @@ struct ProfileScope {
     pls_context* ctx;
     int which;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    ProfileScope(pls_context* c, int w, double bytes);
+    // count = false: the launch may be a device-side no-op (ICP already converged); the caller
+    // credits launches/bytes afterwards with profile_credit() once the executed count is known
+    ProfileScope(pls_context* c, int w, double bytes, bool count = true);
     ~ProfileScope();
 };
 void profile_collect(pls_context* ctx, int which);
+inline void profile_credit(pls_context* ctx, int which, int64_t launches, double bytes) {
+    if (!ctx->prof[which].enabled) return;
+    ctx->prof[which].launches += launches;
+    ctx->prof[which].bytes += bytes;
+}
 
 // ---- primitives (sort.cu / scan.cu) ------------------------------------------------------------
 // Stable LSD radix sort of (u64 key, u32 value) pairs on bits [0, 8*num_passes).

@@ -461,8 +461,8 @@ int kdmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int num
     const int64_t mine = (query_bound + num_ranks - 1) / num_ranks;
     const int blocks = grid_for(mine, KD_ITER_THREADS, 8 * kNumSMs);
     ctx->partials.reserve((size_t)blocks * NACC * sizeof(double), ctx->stream);
-    // algorithmic bytes (SURVEY 8d lower bound): query 16 B + matched point 16 B + normal 16 B
-    ProfileScope ps(ctx, 0, (double)mine * 48.0 + NACC * 8.0);
+    // credited per executed iteration by the caller (the launch is a no-op once ICP converged)
+    ProfileScope ps(ctx, 0, 0.0, false);
     kd_icp_iter_kernel<<<blocks, KD_ITER_THREADS, 0, ctx->stream>>>(
         make_index(ctx), ctx->cfg.num_neighbors_normals, ctx->query_ptr,
         reinterpret_cast<const uint32_t*>(&frame_result_dev(ctx)->counts[1]),

@@ -127,7 +127,7 @@ inline int grid_for(int64_t n, int threads = 256) {
 uint32_t* count_slot(pls_context* ctx, int i) { return reinterpret_cast<uint32_t*>(&frame_result_dev(ctx)->counts[i]); }
 
 // The ICP loop (icp_odometry.py:248-299) over ctx->queries / counts[1].
-void run_icp(pls_context* ctx, const float* T0_dev, int64_t query_bound) {
+int run_icp(pls_context* ctx, const float* T0_dev, int64_t query_bound) {
     cudaStream_t st = ctx->stream;
     FrameResult* fr = frame_result_dev(ctx);
     frame_begin_kernel<<<1, kMaxAlign, 0, st>>>(fr, T0_dev, ctx->cfg.max_num_alignments);
@@ -136,10 +136,12 @@ void run_icp(pls_context* ctx, const float* T0_dev, int64_t query_bound) {
     ctx->nn_prev.reserve((size_t)query_bound * sizeof(int), st);
     PLS_CUDA(cudaMemsetAsync(ctx->nn_prev.p, 0xff, (size_t)query_bound * sizeof(int), st));
     const int rank = comm_rank(ctx), size = comm_size(ctx);
+    int last_blocks = 0;
     for (int it = 0; it < ctx->cfg.max_num_alignments; ++it) {
         int blocks;
         if (ctx->cfg.local_map_type == PLS_MAP_KDTREE) blocks = kdmap_icp_iteration(ctx, query_bound, rank, size);
         else blocks = projmap_icp_iteration(ctx, query_bound, rank, size);
+        last_blocks = blocks;
         if (size > 1) {
             reduce_partials_kernel<<<1, 32, 0, st>>>(fr, ctx->partials.as<double>(), blocks);
             PLS_CHECK_LAUNCH();
@@ -149,11 +151,20 @@ void run_icp(pls_context* ctx, const float* T0_dev, int64_t query_bound) {
         icp_step_kernel<<<1, 32, 0, st>>>(fr, ctx->partials.as<double>(), blocks, ctx->cfg.threshold_delta_pose);
         PLS_CHECK_LAUNCH();
     }
+    return last_blocks;
 }
 
 void fetch_result(pls_context* ctx) {
     PLS_CUDA(cudaMemcpyAsync(ctx->pinned.p, ctx->scalars.p, sizeof(FrameResult), cudaMemcpyDeviceToHost, ctx->stream));
     PLS_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+// Algorithmic bytes of one executed correspondence+reduction launch (DESIGN.md "K5/K6"):
+// kd map: per query 16 B query + 4+4 B previous-match read/write + 16 B matched point + 16 B normal;
+// plus one 30-double partial row per block.
+void credit_icp_profile(pls_context* ctx, const FrameResult* h, int blocks) {
+    if (ctx->cfg.local_map_type == PLS_MAP_KDTREE)
+        profile_credit(ctx, 0, h->iters, (double)h->iters * ((double)h->counts[1] * 56.0 + (double)blocks * NACC * 8.0));
 }
 
 void raise_status(pls_context* ctx, int status) {
@@ -259,9 +270,10 @@ void process_frame_device(pls_context* ctx, const float* data_dev, int layout, i
         PLS_CUDA(cudaMemcpyAsync(ctx->tmp[6].p, init_pose, 16 * sizeof(float), cudaMemcpyHostToDevice, st));
         T0_dev = ctx->tmp[6].as<float>();
     }
-    run_icp(ctx, T0_dev, query_bound);
+    const int icp_blocks = run_icp(ctx, T0_dev, query_bound);
     fetch_result(ctx);
     FrameResult* h = frame_result_host(ctx);
+    credit_icp_profile(ctx, h, icp_blocks);
     raise_status(ctx, h->status);
 
     // ---- __update_map
@@ -339,9 +351,10 @@ int pls_register_frame(pls_context* ctx, const float* points, int64_t n, const f
                                  is_device_ptr(T0) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
         T0_dev = ctx->tmp[6].as<float>();
     }
-    run_icp(ctx, T0_dev, n);
+    const int icp_blocks = run_icp(ctx, T0_dev, n);
     fetch_result(ctx);
     FrameResult* h = frame_result_host(ctx);
+    credit_icp_profile(ctx, h, icp_blocks);
     auto put = [&](void* dst, const void* src, size_t bytes) {
         if (!dst) return;
         if (is_device_ptr(dst)) PLS_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));

