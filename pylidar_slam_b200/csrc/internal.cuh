@@ -109,7 +109,8 @@ struct KdMap {
 
 struct ProjMap {
     int K = 0;              // frames held
-    DBuf vmaps, nmaps;      // [Kmax][3][H][W] ring in insertion order (slot = frame order)
+    int head = 0;           // ring slot of the oldest frame
+    DBuf vmaps, nmaps;      // [Kmax+1][3][H][W] ring; logical frame k lives in slot (head + k) % (Kmax+1)
     DBuf poses;             // device copy of [Kmax][16] poses (frame -> newest frame)
     std::vector<float> host_poses;  // [K][16]
     DBuf model_v, model_n;  // [Kmax][3][H][W] re-projected model

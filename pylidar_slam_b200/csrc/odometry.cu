@@ -163,8 +163,15 @@ void fetch_result(pls_context* ctx) {
 // kd map: per query 16 B query + 4+4 B previous-match read/write + 16 B matched point + 16 B normal;
 // plus one 30-double partial row per block.
 void credit_icp_profile(pls_context* ctx, const FrameResult* h, int blocks) {
-    if (ctx->cfg.local_map_type == PLS_MAP_KDTREE)
+    if (ctx->cfg.local_map_type == PLS_MAP_KDTREE) {
         profile_credit(ctx, 0, h->iters, (double)h->iters * ((double)h->counts[1] * 56.0 + (double)blocks * NACC * 8.0));
+    } else {
+        // projective map: HW*12*(K+1) (target + K candidate vertex maps, each read once)
+        // + N_c*12 (winner normals) + one partial row per block
+        const double hw = (double)ctx->cfg.height * ctx->cfg.width;
+        profile_credit(ctx, 1, h->iters, (double)h->iters * (hw * 12.0 * (ctx->pm.K + 1) + h->last_sums[29] * 12.0 +
+                                                              (double)blocks * NACC * 8.0));
+    }
 }
 
 void raise_status(pls_context* ctx, int status) {

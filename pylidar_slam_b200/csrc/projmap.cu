@@ -1,16 +1,548 @@
-// placeholder until the projective local map lands (K3/K4)
+// K3/K4 -- the projective local map (replaces ProjectiveLocalMap, slam/odometry/local_map.py:91-240,
+// compute_normal_map and compute_neighbors, slam/common/geometry.py:240-295,397-439).
+//
+//   normal_map_kernel       5x5 (k x k) zero-padded box sums of v and v v^T from a shared-memory
+//                           tile, n ~ (sum v v^T)^-1 sum v through the cofactor matrix, float32
+//   model_zbuf_kernel       build_model (local_map.py:177-202): every stored frame k is re-expressed
+//   model_resolve_kernel    in the newest frame (p' = R_k v + t_k, n' = R_k n, masked) and re-projected
+//                           with its own closest-wins z-buffer into _model_vmap / _model_nmap [K,3,H,W]
+//   query_zbuf_kernel       nearest_neighbor_search (local_map.py:205-235): the transformed queries
+//                           are z-buffered into the target vertex map (one survivor per pixel)
+//   proj_icp_iter_kernel    per pixel: argmin_k |p - v_k| over the K model maps (first minimum wins,
+//                           null candidates skipped), gather the winner's point and normal, point-to-
+//                           plane residual / Jacobian / weight and the block-reduced normal equations.
+//                           Streams HW*12*(K+1) bytes per launch: the HBM-bound correspondence kernel.
+//   proj_pairs_kernel       the same association materialised per pixel for the fine-grained API
+#include "gn_device.cuh"
 #include "internal.cuh"
+#include "pose_device.cuh"
+#include "projection_device.cuh"
+
 namespace pls {
-void projmap_reset(pls_context* ctx) { ctx->pm.K = 0; ctx->pm.valid = false; ctx->pm.host_poses.clear(); }
-void projmap_update(pls_context*, const float*, const float*) { throw Error{PLS_E_STATE, "projective map: not built yet"}; }
-int projmap_icp_iteration(pls_context*, int64_t, int, int) { throw Error{PLS_E_STATE, "projective map: not built yet"}; }
-void launch_normal_map(pls_context*, const float*, int, int, int, int, float*) { throw Error{PLS_E_STATE, "normal map: not built yet"}; }
+
+namespace {
+
+inline int grid_for(int64_t n, int threads, int cap_blocks = 16 * kNumSMs) {
+    int64_t b = (n + threads - 1) / threads;
+    return (int)(b < 1 ? 1 : (b > cap_blocks ? cap_blocks : b));
 }
+
+// ------------------------------------------------------------------------------------------ K3
+constexpr int NM_TX = 32, NM_TY = 8, NM_MAXR = 4;  // kernel sizes up to 9
+
+__global__ void __launch_bounds__(NM_TX* NM_TY)
+normal_map_kernel(const float* __restrict__ vmap, int batch, int H, int W, int ksize, float* __restrict__ out) {
+    __shared__ float tile[3][NM_TY + 2 * NM_MAXR][NM_TX + 2 * NM_MAXR + 1];
+    const int r = ksize / 2;
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * NM_TX, y0 = blockIdx.y * NM_TY;
+    const int64_t hw = (int64_t)H * W;
+    const float* v = vmap + (size_t)b * 3 * hw;
+    const int tw = NM_TX + 2 * r, th = NM_TY + 2 * r;
+    for (int i = threadIdx.y * NM_TX + threadIdx.x; i < tw * th; i += NM_TX * NM_TY) {
+        int ty = i / tw, tx = i - ty * tw;
+        int gx = x0 + tx - r, gy = y0 + ty - r;
+        bool in = gx >= 0 && gx < W && gy >= 0 && gy < H;
+        int64_t g = (int64_t)gy * W + gx;
+        tile[0][ty][tx] = in ? v[g] : 0.f;
+        tile[1][ty][tx] = in ? v[hw + g] : 0.f;
+        tile[2][ty][tx] = in ? v[2 * hw + g] : 0.f;
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    float sx = 0.f, sy = 0.f, sz = 0.f, sxx = 0.f, sxy = 0.f, sxz = 0.f, syy = 0.f, syz = 0.f, szz = 0.f;
+    for (int dy = 0; dy < ksize; ++dy)
+        for (int dx = 0; dx < ksize; ++dx) {
+            float px = tile[0][threadIdx.y + dy][threadIdx.x + dx];
+            float py = tile[1][threadIdx.y + dy][threadIdx.x + dx];
+            float pz = tile[2][threadIdx.y + dy][threadIdx.x + dx];
+            sx += px; sy += py; sz += pz;
+            sxx += px * px; sxy += px * py; sxz += px * pz;
+            syy += py * py; syz += py * pz; szz += pz * pz;
+        }
+    // rows of the cofactor matrix: c_i = A[i-2] x A[i-1]  (geometry.py:65-76)
+    const float A0[3] = {sxx, sxy, sxz}, A1[3] = {sxy, syy, syz}, A2[3] = {sxz, syz, szz};
+    auto cross = [](const float* a, const float* b, float* c) {
+        c[0] = __fsub_rn(__fmul_rn(a[1], b[2]), __fmul_rn(a[2], b[1]));
+        c[1] = __fsub_rn(__fmul_rn(a[2], b[0]), __fmul_rn(a[0], b[2]));
+        c[2] = __fsub_rn(__fmul_rn(a[0], b[1]), __fmul_rn(a[1], b[0]));
+    };
+    float c0[3], c1[3], c2[3];
+    cross(A1, A2, c0);
+    cross(A2, A0, c1);
+    cross(A0, A1, c2);
+    const float d0 = c0[0] * A0[0] + c0[1] * A0[1] + c0[2] * A0[2];
+    const float d1 = c1[0] * A1[0] + c1[1] * A1[1] + c1[2] * A1[2];
+    const float d2 = c2[0] * A2[0] + c2[1] * A2[1] + c2[2] * A2[2];
+    const float det = (d0 + d1 + d2) / 3.0f;
+    float n[3] = {0.f, 0.f, 0.f};
+    if (fabsf(det) > 1e-6f) {
+        // n = (cof / det)^T ... transposed back: n_i = sum_j (cof[i][j] / det) * b_j  (geometry.py:79-114,273)
+        n[0] = (c0[0] / det) * sx + (c0[1] / det) * sy + (c0[2] / det) * sz;
+        n[1] = (c1[0] / det) * sx + (c1[1] / det) * sy + (c1[2] / det) * sz;
+        n[2] = (c2[0] / det) * sx + (c2[1] / det) * sy + (c2[2] / det) * sz;
+        float nn = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        if (nn == 0.f) nn = 1.f;
+        n[0] /= nn; n[1] /= nn; n[2] /= nn;
+    }
+    const float cx = tile[0][threadIdx.y + r][threadIdx.x + r], cy = tile[1][threadIdx.y + r][threadIdx.x + r],
+                cz = tile[2][threadIdx.y + r][threadIdx.x + r];
+    if (sqrtf(cx * cx + cy * cy + cz * cz) == 0.f) n[0] = n[1] = n[2] = 0.f;
+    float* o = out + (size_t)b * 3 * hw + (int64_t)y * W + x;
+    o[0] = n[0];
+    o[hw] = n[1];
+    o[2 * hw] = n[2];
+}
+
+// ------------------------------------------------------------------------------------------ model rebuild
+struct PoseSet {
+    const float* poses;  // [K][16] device
+};
+
+__device__ __forceinline__ bool model_point(const float* __restrict__ vmaps, const float* __restrict__ P, int64_t hw,
+                                            int64_t src, float* p) {
+    const float x = vmaps[src], y = vmaps[hw + src], z = vmaps[2 * hw + src];
+    // mask_not_null (geometry.py:157-177): any channel non-zero
+    if (fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) > 0.f) {
+        p[0] = x * P[0] + y * P[1] + z * P[2] + P[3];
+        p[1] = x * P[4] + y * P[5] + z * P[6] + P[7];
+        p[2] = x * P[8] + y * P[9] + z * P[10] + P[11];
+        return true;
+    }
+    return false;
+}
+
+__global__ void model_zbuf_kernel(const float* __restrict__ vmaps, const float* __restrict__ poses, int K, int head,
+                                  int slots, ProjConst pc, unsigned long long* __restrict__ zbuf) {
+    const int64_t hw = (int64_t)pc.H * pc.W;
+    const int64_t total = (int64_t)K * hw;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = g / hw, src = g - k * hw;
+        float p[3];
+        if (!model_point(vmaps + (size_t)((head + k) % slots) * 3 * hw, poses + 16 * k, hw, src, p)) continue;
+        int pix;
+        float r;
+        if (project_to_pixel(p[0], p[1], p[2], pc, pix, r)) {
+            unsigned long long key = ((unsigned long long)__float_as_uint(r) << 32) | (unsigned long long)(uint32_t)src;
+            atomicMin(&zbuf[k * hw + pix], key);
+        }
+    }
+}
+
+__global__ void model_resolve_kernel(const float* __restrict__ vmaps, const float* __restrict__ nmaps,
+                                     const float* __restrict__ poses, int K, int head, int slots, int64_t hw,
+                                     const unsigned long long* __restrict__ zbuf, float* __restrict__ model_v,
+                                     float* __restrict__ model_n) {
+    const int64_t total = (int64_t)K * hw;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = g / hw, pix = g - k * hw;
+        const unsigned long long key = zbuf[g];
+        float p[3] = {0.f, 0.f, 0.f}, n[3] = {0.f, 0.f, 0.f};
+        if (key != ~0ull) {
+            const int64_t src = (int64_t)(uint32_t)(key & 0xffffffffull);
+            const float* P = poses + 16 * k;
+            const size_t slot = (size_t)((head + k) % slots);
+            model_point(vmaps + slot * 3 * hw, P, hw, src, p);
+            const float* nm = nmaps + slot * 3 * hw;
+            const float nx = nm[src], ny = nm[hw + src], nz = nm[2 * hw + src];
+            n[0] = P[0] * nx + P[1] * ny + P[2] * nz;
+            n[1] = P[4] * nx + P[5] * ny + P[6] * nz;
+            n[2] = P[8] * nx + P[9] * ny + P[10] * nz;
+        }
+        float* ov = model_v + (size_t)k * 3 * hw + pix;
+        float* on = model_n + (size_t)k * 3 * hw + pix;
+        ov[0] = p[0]; ov[hw] = p[1]; ov[2 * hw] = p[2];
+        on[0] = n[0]; on[hw] = n[1]; on[2 * hw] = n[2];
+    }
+}
+
+// ------------------------------------------------------------------------------------------ search
+__device__ __forceinline__ void load_T(const float* __restrict__ T, float* sT) {
+    if (threadIdx.x < 12) sT[threadIdx.x] = T[threadIdx.x];
+    __syncthreads();
+}
+
+__global__ void query_zbuf_kernel(const float4* __restrict__ queries, const uint32_t* __restrict__ nq_dev, int64_t nq_host,
+                                  const float* __restrict__ T, const int* __restrict__ done, ProjConst pc,
+                                  unsigned long long* __restrict__ zbuf) {
+    if (done && *done) return;
+    __shared__ float sT[12];
+    if (T) load_T(T, sT);
+    const int64_t nq = nq_dev ? (int64_t)*nq_dev : nq_host;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 p0 = queries[i];
+        float p[3] = {p0.x, p0.y, p0.z};
+        if (T) {
+            p[0] = p0.x * sT[0] + p0.y * sT[1] + p0.z * sT[2] + sT[3];
+            p[1] = p0.x * sT[4] + p0.y * sT[5] + p0.z * sT[6] + sT[7];
+            p[2] = p0.x * sT[8] + p0.y * sT[9] + p0.z * sT[10] + sT[11];
+        }
+        int pix;
+        float r;
+        if (project_to_pixel(p[0], p[1], p[2], pc, pix, r)) {
+            unsigned long long key = ((unsigned long long)__float_as_uint(r) << 32) | (unsigned long long)(uint32_t)i;
+            atomicMin(&zbuf[pix], key);
+        }
+    }
+}
+
+// argmin over the K candidates at one pixel; returns false if none is valid
+__device__ __forceinline__ bool pixel_argmin(const float* __restrict__ model_v, const float* __restrict__ model_n, int K,
+                                             int64_t hw, int64_t pix, const float* p, float* q, float* n) {
+    float best = __int_as_float(0x7f800000);
+    int kbest = -1;
+    float bq[3] = {0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+        const float* mv = model_v + (size_t)k * 3 * hw + pix;
+        const float x = mv[0], y = mv[hw], z = mv[2 * hw];
+        if (fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) > 0.f) {
+            const float dx = p[0] - x, dy = p[1] - y, dz = p[2] - z;
+            const float d = sqrtf(dx * dx + dy * dy + dz * dz);
+            if (d < best) {  // torch.min keeps the first minimum
+                best = d;
+                kbest = k;
+                bq[0] = x; bq[1] = y; bq[2] = z;
+            }
+        }
+    }
+    if (kbest < 0) return false;
+    q[0] = bq[0]; q[1] = bq[1]; q[2] = bq[2];
+    const float* mn = model_n + (size_t)kbest * 3 * hw + pix;
+    n[0] = mn[0]; n[1] = mn[hw]; n[2] = mn[2 * hw];
+    return true;
+}
+
+constexpr int PJ_THREADS = 256;
+
+__global__ void __launch_bounds__(PJ_THREADS)
+proj_icp_iter_kernel(const float* __restrict__ model_v, const float* __restrict__ model_n, int K, int64_t hw,
+                     const unsigned long long* __restrict__ zbuf, const float4* __restrict__ queries,
+                     const FrameResult* __restrict__ fr, int64_t pix_begin, int64_t pix_end, int scheme, float sigma,
+                     double* __restrict__ partials) {
+    if (fr->done) return;
+    __shared__ float sT[12];
+    load_T(fr->T, sT);
+    double acc[NACC];
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
+    for (int64_t pix = pix_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < pix_end;
+         pix += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long key = zbuf[pix];
+        if (key == ~0ull) continue;
+        const float4 p0 = queries[(uint32_t)(key & 0xffffffffull)];
+        float p[3], q[3], n[3];
+        p[0] = p0.x * sT[0] + p0.y * sT[1] + p0.z * sT[2] + sT[3];
+        p[1] = p0.x * sT[4] + p0.y * sT[5] + p0.z * sT[6] + sT[7];
+        p[2] = p0.x * sT[8] + p0.y * sT[9] + p0.z * sT[10] + sT[11];
+        if (!pixel_argmin(model_v, model_n, K, hw, pix, p, q, n)) continue;
+        float J[6];
+        const float r = p2plane_residual_jacobian_identity(p, q, n, J);
+        const float w = ls_weight<float>(scheme, sigma, r, p, q);
+        accumulate_normal_equations<float>(acc, J, w, r * w, r);
+    }
+    block_reduce_store<PJ_THREADS>(acc, partials + (size_t)blockIdx.x * NACC);
+}
+
+// per-pixel association for the fine-grained API: flag + (q, n, p)
+__global__ void proj_pairs_kernel(const float* __restrict__ model_v, const float* __restrict__ model_n, int K, int64_t hw,
+                                  const unsigned long long* __restrict__ zbuf, const float4* __restrict__ queries,
+                                  uint8_t* __restrict__ flags, float* __restrict__ pairs /* [hw][9] */) {
+    for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < hw; pix += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long key = zbuf[pix];
+        uint8_t ok = 0;
+        if (key != ~0ull) {
+            const float4 p0 = queries[(uint32_t)(key & 0xffffffffull)];
+            float p[3] = {p0.x, p0.y, p0.z}, q[3], n[3];
+            if (pixel_argmin(model_v, model_n, K, hw, pix, p, q, n)) {
+                ok = 1;
+                float* o = pairs + 9 * pix;
+                o[0] = q[0]; o[1] = q[1]; o[2] = q[2];
+                o[3] = n[0]; o[4] = n[1]; o[5] = n[2];
+                o[6] = p[0]; o[7] = p[1]; o[8] = p[2];
+            }
+        }
+        flags[pix] = ok;
+    }
+}
+
+__global__ void proj_compact_kernel(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ pos,
+                                    const float* __restrict__ pairs, int64_t hw, float* __restrict__ out_q,
+                                    float* __restrict__ out_n, float* __restrict__ out_p) {
+    for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < hw; pix += (int64_t)gridDim.x * blockDim.x) {
+        if (!flags[pix]) continue;
+        const uint32_t d = pos[pix];
+        const float* s = pairs + 9 * pix;
+        for (int c = 0; c < 3; ++c) {
+            out_q[3 * (size_t)d + c] = s[c];
+            if (out_n) out_n[3 * (size_t)d + c] = s[3 + c];
+            if (out_p) out_p[3 * (size_t)d + c] = s[6 + c];
+        }
+    }
+}
+
+// stateless compute_neighbors (geometry.py:397-439)
+__global__ void compute_neighbors_kernel(const float* __restrict__ tgt, const float* __restrict__ ref,
+                                         const float* __restrict__ fields, int K, int C, int64_t hw,
+                                         float* __restrict__ out_nb, float* __restrict__ out_f) {
+    for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < hw; pix += (int64_t)gridDim.x * blockDim.x) {
+        const float p[3] = {tgt[pix], tgt[hw + pix], tgt[2 * hw + pix]};
+        const bool tgt_ok = fmaxf(fmaxf(fabsf(p[0]), fabsf(p[1])), fabsf(p[2])) > 0.f;
+        float best = __int_as_float(0x7f800000);
+        int kbest = 0;  // torch.min over all-inf returns index 0
+        if (tgt_ok) {
+            for (int k = 0; k < K; ++k) {
+                const float* mv = ref + (size_t)k * 3 * hw + pix;
+                const float x = mv[0], y = mv[hw], z = mv[2 * hw];
+                if (fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) > 0.f) {
+                    const float dx = p[0] - x, dy = p[1] - y, dz = p[2] - z;
+                    const float d = sqrtf(dx * dx + dy * dy + dz * dz);
+                    if (d < best) { best = d; kbest = k; }
+                }
+            }
+        }
+        const float* mv = ref + (size_t)kbest * 3 * hw + pix;
+        out_nb[pix] = tgt_ok ? mv[0] : 0.f;
+        out_nb[hw + pix] = tgt_ok ? mv[hw] : 0.f;
+        out_nb[2 * hw + pix] = tgt_ok ? mv[2 * hw] : 0.f;
+        if (fields)
+            for (int c = 0; c < C; ++c) out_f[(size_t)c * hw + pix] = fields[((size_t)kbest * C + c) * hw + pix];
+    }
+}
+
+void rebuild_model(pls_context* ctx) {
+    ProjMap& pm = ctx->pm;
+    cudaStream_t st = ctx->stream;
+    const int H = ctx->cfg.height, W = ctx->cfg.width;
+    const int64_t hw = (int64_t)H * W;
+    const int K = pm.K;
+    if (K == 0) return;
+    ProfileScope ps(ctx, 2, (double)K * hw * (24.0 + 24.0 + 16.0));
+    pm.poses.reserve((size_t)ctx->cfg.local_map_size * 16 * sizeof(float) + 64, st);
+    PLS_CUDA(cudaMemcpyAsync(pm.poses.p, pm.host_poses.data(), (size_t)K * 16 * sizeof(float), cudaMemcpyHostToDevice, st));
+    pm.zbuf.reserve((size_t)(K > 1 ? K : 1) * hw * sizeof(unsigned long long), st);
+    pm.model_v.reserve((size_t)ctx->cfg.local_map_size * 3 * hw * sizeof(float), st);
+    pm.model_n.reserve((size_t)ctx->cfg.local_map_size * 3 * hw * sizeof(float), st);
+    PLS_CUDA(cudaMemsetAsync(pm.zbuf.p, 0xff, (size_t)K * hw * sizeof(unsigned long long), st));
+    ProjConst pc = make_proj_const(H, W, ctx->cfg.up_fov_deg, ctx->cfg.down_fov_deg);
+    const int slots = ctx->cfg.local_map_size + 1;
+    model_zbuf_kernel<<<grid_for(K * hw, 256), 256, 0, st>>>(pm.vmaps.as<float>(), pm.poses.as<float>(), K, pm.head, slots,
+                                                             pc, pm.zbuf.as<unsigned long long>());
+    PLS_CHECK_LAUNCH();
+    model_resolve_kernel<<<grid_for(K * hw, 256), 256, 0, st>>>(pm.vmaps.as<float>(), pm.nmaps.as<float>(),
+                                                                pm.poses.as<float>(), K, pm.head, slots, hw,
+                                                                pm.zbuf.as<unsigned long long>(),
+                                                                pm.model_v.as<float>(), pm.model_n.as<float>());
+    PLS_CHECK_LAUNCH();
+    pm.valid = true;
+}
+
+}  // namespace
+
+void launch_normal_map(pls_context* ctx, const float* vmap, int batch, int H, int W, int ksize, float* out) {
+    PLS_REQUIRE(ksize >= 1 && ksize <= 2 * NM_MAXR + 1 && (ksize & 1), "normal map: odd kernel size 1..9");
+    dim3 grid((W + NM_TX - 1) / NM_TX, (H + NM_TY - 1) / NM_TY, batch), block(NM_TX, NM_TY);
+    normal_map_kernel<<<grid, block, 0, ctx->stream>>>(vmap, batch, H, W, ksize, out);
+    PLS_CHECK_LAUNCH();
+}
+
+void projmap_reset(pls_context* ctx) {
+    ctx->pm.K = 0;
+    ctx->pm.head = 0;
+    ctx->pm.valid = false;
+    ctx->pm.host_poses.clear();
+}
+
+// ProjectiveLocalMap.update (local_map.py:126-174): poses_k <- rel^-1 poses_k, append, evict, rebuild.
+void projmap_update(pls_context* ctx, const float* rel_pose_host, const float* vmap_dev) {
+    ProjMap& pm = ctx->pm;
+    cudaStream_t st = ctx->stream;
+    const int H = ctx->cfg.height, W = ctx->cfg.width;
+    const int64_t hw = (int64_t)H * W;
+    const int cap = ctx->cfg.local_map_size;
+    const size_t frame_bytes = (size_t)3 * hw * sizeof(float);
+    pm.vmaps.reserve((size_t)(cap + 1) * frame_bytes, st, true);
+    pm.nmaps.reserve((size_t)(cap + 1) * frame_bytes, st, true);
+    if (pm.K == 0) {
+        PLS_REQUIRE(vmap_dev != nullptr, "projective map: the first update needs a vertex map");
+        pm.host_poses.assign(rel_pose_host, rel_pose_host + 16);
+        PLS_CUDA(cudaMemcpyAsync(pm.vmaps.p, vmap_dev, frame_bytes, cudaMemcpyDeviceToDevice, st));
+        launch_normal_map(ctx, vmap_dev, 1, H, W, ctx->cfg.normals_kernel_size, pm.nmaps.as<float>());
+        pm.K = 1;
+    } else {
+        float inv[16], tmp[16];
+        rigid_inverse(rel_pose_host, inv);
+        for (int k = 0; k < pm.K; ++k) {
+            mat4_mul(inv, &pm.host_poses[16 * k], tmp);
+            memcpy(&pm.host_poses[16 * k], tmp, sizeof(tmp));
+        }
+        const int slots = cap + 1;
+        if (vmap_dev) {
+            float eye[16];
+            for (int i = 0; i < 16; ++i) eye[i] = (i % 5 == 0) ? 1.f : 0.f;
+            pm.host_poses.insert(pm.host_poses.end(), eye, eye + 16);
+            const size_t slot = (size_t)((pm.head + pm.K) % slots);  // ring of cap+1 frame slots
+            char* vdst = reinterpret_cast<char*>(pm.vmaps.p) + slot * frame_bytes;
+            char* ndst = reinterpret_cast<char*>(pm.nmaps.p) + slot * frame_bytes;
+            PLS_CUDA(cudaMemcpyAsync(vdst, vmap_dev, frame_bytes, cudaMemcpyDeviceToDevice, st));
+            launch_normal_map(ctx, vmap_dev, 1, H, W, ctx->cfg.normals_kernel_size, reinterpret_cast<float*>(ndst));
+            pm.K += 1;
+        }
+        if (pm.K > cap) {  // drop the oldest frame: advance the ring head
+            pm.head = (pm.head + 1) % slots;
+            pm.host_poses.erase(pm.host_poses.begin(), pm.host_poses.begin() + 16);
+            pm.K -= 1;
+        }
+    }
+    rebuild_model(ctx);
+}
+
+// one ICP iteration on the projective map; pixels [rank*hw/R, (rank+1)*hw/R) are reduced by this rank
+int projmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int num_ranks) {
+    ProjMap& pm = ctx->pm;
+    PLS_REQUIRE(pm.valid, "projective map: search before any update");
+    cudaStream_t st = ctx->stream;
+    const int H = ctx->cfg.height, W = ctx->cfg.width;
+    const int64_t hw = (int64_t)H * W;
+    FrameResult* fr = frame_result_dev(ctx);
+    ctx->tmp[3].reserve((size_t)hw * sizeof(unsigned long long), st);
+    unsigned long long* zbuf = ctx->tmp[3].as<unsigned long long>();
+    PLS_CUDA(cudaMemsetAsync(zbuf, 0xff, (size_t)hw * sizeof(unsigned long long), st));
+    ProjConst pc = make_proj_const(H, W, ctx->cfg.up_fov_deg, ctx->cfg.down_fov_deg);
+    query_zbuf_kernel<<<grid_for(query_bound, 256), 256, 0, st>>>(
+        ctx->query_ptr, reinterpret_cast<const uint32_t*>(&fr->counts[1]), 0, fr->T, &fr->done, pc, zbuf);
+    PLS_CHECK_LAUNCH();
+    const int64_t pix_begin = hw * rank / num_ranks, pix_end = hw * (rank + 1) / num_ranks;
+    const int blocks = grid_for(pix_end - pix_begin, PJ_THREADS, 4 * kNumSMs);
+    ctx->partials.reserve((size_t)blocks * NACC * sizeof(double), st);
+    {
+        ProfileScope ps(ctx, 1, 0.0, false);
+        proj_icp_iter_kernel<<<blocks, PJ_THREADS, 0, st>>>(pm.model_v.as<float>(), pm.model_n.as<float>(), pm.K, hw, zbuf,
+                                                            ctx->query_ptr, fr, pix_begin, pix_end, ctx->cfg.scheme,
+                                                            ctx->cfg.sigma, ctx->partials.as<double>());
+        PLS_CHECK_LAUNCH();
+    }
+    return blocks;
+}
+
+}  // namespace pls
+
+using namespace pls;
+
 extern "C" {
-int pls_normal_map(pls_context* ctx, const float*, int, int, int, int, float*) { return PLS_E_STATE; }
-int pls_compute_neighbors(pls_context* ctx, const float*, const float*, const float*, int, int, int, int, float*, float*) { return PLS_E_STATE; }
-int pls_projmap_update(pls_context* ctx, const float*, const float*) { return PLS_E_STATE; }
-int pls_projmap_num_frames(pls_context* ctx, int*) { return PLS_E_STATE; }
-int pls_projmap_model(pls_context* ctx, float*, float*) { return PLS_E_STATE; }
-int pls_projmap_nn_search(pls_context* ctx, const float*, int64_t, float*, float*, float*, int64_t*) { return PLS_E_STATE; }
+
+int pls_normal_map(pls_context* ctx, const float* vertex_map, int batch, int height, int width, int kernel_size, float* out) {
+    PLS_API_BEGIN(ctx)
+    PLS_REQUIRE(vertex_map && out && batch > 0 && height > 0 && width > 0, "pls_normal_map: bad arguments");
+    const size_t bytes = (size_t)batch * 3 * height * width * sizeof(float);
+    const float* d = (const float*)to_device(ctx, vertex_map, bytes, ctx->stage_in[0]);
+    OutArg o = out_arg(ctx, out, bytes, ctx->stage_out[0]);
+    launch_normal_map(ctx, d, batch, height, width, kernel_size, (float*)o.dev);
+    finish_out(ctx, o);
+    PLS_CUDA(cudaStreamSynchronize(ctx->stream));
+    PLS_API_END(ctx)
 }
+
+int pls_compute_neighbors(pls_context* ctx, const float* tgt, const float* ref, const float* fields, int num_ref,
+                          int num_field_channels, int height, int width, float* out_nb, float* out_fields) {
+    PLS_API_BEGIN(ctx)
+    PLS_REQUIRE(tgt && ref && out_nb && num_ref > 0 && height > 0 && width > 0, "pls_compute_neighbors: bad arguments");
+    PLS_REQUIRE(!fields || (out_fields && num_field_channels > 0), "pls_compute_neighbors: fields need an output");
+    const int64_t hw = (int64_t)height * width;
+    const float* d_t = (const float*)to_device(ctx, tgt, (size_t)3 * hw * sizeof(float), ctx->stage_in[0]);
+    const float* d_r = (const float*)to_device(ctx, ref, (size_t)num_ref * 3 * hw * sizeof(float), ctx->stage_in[1]);
+    const float* d_f = (const float*)to_device(ctx, fields, (size_t)num_ref * num_field_channels * hw * sizeof(float), ctx->stage_in[2]);
+    OutArg onb = out_arg(ctx, out_nb, (size_t)3 * hw * sizeof(float), ctx->stage_out[0]);
+    OutArg of = out_arg(ctx, fields ? out_fields : nullptr, (size_t)num_field_channels * hw * sizeof(float), ctx->stage_out[1]);
+    compute_neighbors_kernel<<<grid_for(hw, 256), 256, 0, ctx->stream>>>(d_t, d_r, d_f, num_ref, num_field_channels, hw,
+                                                                         (float*)onb.dev, (float*)of.dev);
+    PLS_CHECK_LAUNCH();
+    finish_out(ctx, onb);
+    finish_out(ctx, of);
+    PLS_CUDA(cudaStreamSynchronize(ctx->stream));
+    PLS_API_END(ctx)
+}
+
+int pls_projmap_update(pls_context* ctx, const float* rel_pose, const float* vertex_map) {
+    PLS_API_BEGIN(ctx)
+    PLS_REQUIRE(rel_pose, "pls_projmap_update: rel_pose required");
+    PLS_REQUIRE(ctx->cfg.local_map_type == PLS_MAP_PROJECTIVE, "context holds a kd map");
+    float rel[16];
+    if (is_device_ptr(rel_pose)) PLS_CUDA(cudaMemcpy(rel, rel_pose, sizeof(rel), cudaMemcpyDeviceToHost));
+    else memcpy(rel, rel_pose, sizeof(rel));
+    const size_t bytes = (size_t)3 * ctx->cfg.height * ctx->cfg.width * sizeof(float);
+    const float* d = (const float*)to_device(ctx, vertex_map, bytes, ctx->stage_in[0]);
+    projmap_update(ctx, rel, d);
+    PLS_CUDA(cudaStreamSynchronize(ctx->stream));
+    PLS_API_END(ctx)
+}
+
+int pls_projmap_num_frames(pls_context* ctx, int* num_frames) {
+    PLS_API_BEGIN(ctx)
+    PLS_REQUIRE(num_frames, "pls_projmap_num_frames: null output");
+    *num_frames = ctx->pm.K;
+    PLS_API_END(ctx)
+}
+
+int pls_projmap_model(pls_context* ctx, float* out_vmap, float* out_nmap) {
+    PLS_API_BEGIN(ctx)
+    PLS_REQUIRE(ctx->pm.valid, "pls_projmap_model: empty map");
+    const size_t bytes = (size_t)ctx->pm.K * 3 * ctx->cfg.height * ctx->cfg.width * sizeof(float);
+    auto put = [&](float* dst, const void* src) {
+        if (!dst) return;
+        PLS_CUDA(cudaMemcpyAsync(dst, src, bytes, is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    };
+    put(out_vmap, ctx->pm.model_v.p);
+    put(out_nmap, ctx->pm.model_n.p);
+    PLS_CUDA(cudaStreamSynchronize(ctx->stream));
+    PLS_API_END(ctx)
+}
+
+int pls_projmap_nn_search(pls_context* ctx, const float* queries, int64_t n, float* out_neighbors, float* out_normals,
+                          float* out_targets, int64_t* out_count) {
+    PLS_API_BEGIN(ctx)
+    PLS_REQUIRE(queries && out_neighbors && out_count && n > 0, "pls_projmap_nn_search: bad arguments");
+    if (!ctx->pm.valid) throw pls::Error{PLS_E_STATE, "pls_projmap_nn_search: the map is empty"};
+    cudaStream_t st = ctx->stream;
+    const int H = ctx->cfg.height, W = ctx->cfg.width;
+    const int64_t hw = (int64_t)H * W;
+    const float* d = (const float*)to_device(ctx, queries, (size_t)n * 3 * sizeof(float), ctx->stage_in[0]);
+    // queries as float4 (no NaN filtering here: the reference passes them through unchanged)
+    ctx->queries.reserve((size_t)n * sizeof(float4), st);
+    uint32_t* cnt = scalar_u32(ctx, SC_TMP0);
+    pack_valid_rows(ctx, d, n, ctx->queries.as<float4>(), cnt);
+    ctx->tmp[3].reserve((size_t)hw * sizeof(unsigned long long), st);
+    unsigned long long* zbuf = ctx->tmp[3].as<unsigned long long>();
+    PLS_CUDA(cudaMemsetAsync(zbuf, 0xff, (size_t)hw * sizeof(unsigned long long), st));
+    ProjConst pc = make_proj_const(H, W, ctx->cfg.up_fov_deg, ctx->cfg.down_fov_deg);
+    query_zbuf_kernel<<<grid_for(n, 256), 256, 0, st>>>(ctx->queries.as<float4>(), cnt, 0, nullptr, nullptr, pc, zbuf);
+    PLS_CHECK_LAUNCH();
+    ctx->tmp[1].reserve((size_t)hw, st);
+    ctx->tmp[2].reserve((size_t)hw * sizeof(uint32_t), st);
+    ctx->tmp[7].reserve((size_t)hw * 9 * sizeof(float), st);
+    proj_pairs_kernel<<<grid_for(hw, 256), 256, 0, st>>>(ctx->pm.model_v.as<float>(), ctx->pm.model_n.as<float>(), ctx->pm.K, hw,
+                                                          zbuf, ctx->queries.as<float4>(), ctx->tmp[1].as<uint8_t>(),
+                                                          ctx->tmp[7].as<float>());
+    PLS_CHECK_LAUNCH();
+    uint32_t* total = scalar_u32(ctx, SC_PROJ_NC);
+    exclusive_scan_flags(ctx, ctx->tmp[1].as<uint8_t>(), hw, ctx->tmp[2].as<uint32_t>(), total);
+    OutArg oq = out_arg(ctx, out_neighbors, (size_t)hw * 3 * sizeof(float), ctx->stage_out[0]);
+    OutArg on = out_arg(ctx, out_normals, (size_t)hw * 3 * sizeof(float), ctx->stage_out[1]);
+    OutArg op = out_arg(ctx, out_targets, (size_t)hw * 3 * sizeof(float), ctx->stage_out[2]);
+    proj_compact_kernel<<<grid_for(hw, 256), 256, 0, st>>>(ctx->tmp[1].as<uint8_t>(), ctx->tmp[2].as<uint32_t>(),
+                                                            ctx->tmp[7].as<float>(), hw, (float*)oq.dev, (float*)on.dev,
+                                                            (float*)op.dev);
+    PLS_CHECK_LAUNCH();
+    uint32_t nc = 0;
+    PLS_CUDA(cudaMemcpyAsync(&nc, total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PLS_CUDA(cudaStreamSynchronize(st));
+    *out_count = nc;
+    finish_out(ctx, oq, (size_t)nc * 3 * sizeof(float));
+    finish_out(ctx, on, (size_t)nc * 3 * sizeof(float));
+    finish_out(ctx, op, (size_t)nc * 3 * sizeof(float));
+    PLS_CUDA(cudaStreamSynchronize(st));
+    PLS_API_END(ctx)
+}
+
+}  // extern "C"

@@ -391,3 +391,116 @@ def test_preprocessing_chain_matches_reference_layout(b200, orc, syn):
     s_ref, i_ref = orc.grid_sample(dd["numpy_pc"], 0.3)
     np.testing.assert_array_equal(dd["sample_indices"], i_ref)
     np.testing.assert_array_equal(dd["input_data"].numpy(), s_ref)
+
+
+# ------------------------------------------------------------------------------------- a4 / a5 / a6
+def _normal_agreement(a, b, vmap):
+    """Fraction of non-null pixels whose unit normals agree (sign-free) to 1e-2 rad, and to 0.1 rad."""
+    valid = (np.abs(vmap).max(0) > 0) & (np.linalg.norm(b, axis=0) > 0.5)
+    dots = np.abs((a * b).sum(0))[valid]
+    return float(np.mean(dots > np.cos(1e-2))), float(np.mean(dots > np.cos(0.1)))
+
+
+def test_a4_normal_map_golden_and_oracle(b200, orc, syn, golden_helpers):
+    g = golden_helpers
+    for k, key in ((5, "a4_nmap"), (3, "a4_nmap_k3")):
+        n = b200.compute_normal_map(g["a4_vmap"][None], kernel_size=k)[0]
+        assert n.shape == g[key].shape
+        # identical null pattern (null vertex -> zero normal)
+        null = np.abs(g["a4_vmap"]).max(0) == 0
+        assert np.all(n[:, null] == 0)
+        tight, loose = _normal_agreement(n, g[key], g["a4_vmap"])
+        # the reference inverts the UNCENTRED second-moment matrix in float32 (cond ~ r^2/sigma^2): its own
+        # normals carry summation-order noise, so agreement is statistical, not bitwise
+        assert tight > 0.80 and loose > 0.97, (k, tight, loose)
+        norms = np.linalg.norm(n, axis=0)
+        assert np.all((np.abs(norms - 1) < 1e-4) | (norms == 0))
+    H, W = 64, 2048
+    vm = syn.vertex_map_from_scan(syn.scan(5, H, W), H, W)
+    ref = orc.normal_map(torch.from_numpy(vm), 5)[0].numpy()
+    out = b200.compute_normal_map(torch.from_numpy(vm).cuda(), 5)[0].cpu().numpy()
+    tight, loose = _normal_agreement(out, ref, vm[0])
+    assert tight > 0.80 and loose > 0.97, (tight, loose)
+
+
+def test_a6_compute_neighbors_golden(b200, golden_helpers):
+    g = golden_helpers
+    nb, nf = b200.compute_neighbors(g["a6_tgt"][None], g["a6_ref"], g["a6_fields"])
+    np.testing.assert_array_equal(nb[0], g["a6_nb"])
+    np.testing.assert_array_equal(nf[0], g["a6_nf"])
+
+
+def test_a6_reference_geometry_property(b200):
+    """tests/test_geometry.py:6-24 of the reference on the CUDA path."""
+    torch.manual_seed(0)
+    tgt, ref = torch.randn(1, 3, 10, 10), torch.randn(10, 3, 10, 10)
+    tgt[0, :, 0, 0] = 0.0
+    nb, _ = b200.compute_neighbors(tgt.cuda(), ref.cuda())
+    nb = nb.cpu()
+    assert nb[0, :, 0, 0].norm() == 0.0
+    d_nb = (nb - tgt).norm(dim=1)[0]
+    d_all = (ref - tgt).norm(dim=1)
+    mask = torch.ones(10, 10, dtype=torch.bool)
+    mask[0, 0] = False
+    assert bool(((d_nb.unsqueeze(0) <= d_all)[:, mask]).all())
+
+
+def test_a5_projective_map_lifecycle_vs_oracle(b200, orc, syn):
+    """update / evict / move-only, the re-projected model maps and the pixel association vs the oracle."""
+    H, W = 32, 512
+    proj = b200.SphericalProjector(height=H, width=W, up_fov=3.0, down_fov=-24.0)
+    mine = b200.ProjectiveLocalMap(b200.ProjectiveLocalMapConfig(local_map_size=3), projector=proj)
+    theirs = orc.ProjectiveLocalMap(orc.Projector(H, W), local_map_size=3)
+    mine.init()
+    for k in range(6):
+        rel = np.eye(4, dtype=np.float32) if k == 0 else syn.gt_relative_pose(k).astype(np.float32)
+        vm = syn.vertex_map_from_scan(syn.scan(k, H, W), H, W)
+        if k == 4:
+            mine.update(rel[None])
+            theirs.update(torch.from_numpy(rel)[None])
+        else:
+            mine.update(rel[None], new_vertex_map=vm)
+            theirs.update(torch.from_numpy(rel)[None], new_vertex_map=torch.from_numpy(vm))
+        mv, mn = mine.model()
+        assert mv.shape == tuple(theirs.model_vmap.shape)
+        tv = theirs.model_vmap.numpy()
+        for j in range(mv.shape[0]):
+            assert _pixel_mismatch(mv[j], tv[j]) < 5e-3, (k, j)   # z-buffer winners; poses differ by ~1e-7
+            same = np.all(np.abs(mv[j] - tv[j]) < 1e-3, axis=0) & (np.abs(tv[j]).max(0) > 0)
+            assert np.mean(same) > 0.95
+    q = syn.scan(6, H, W)
+    T = syn.gt_relative_pose(6).astype(np.float32)
+    q = q @ T[:3, :3].T + T[:3, 3]
+    res = mine.nearest_neighbor_search(q)
+    tq, tn, tp = theirs.nearest_neighbor_search(torch.from_numpy(q))
+    assert abs(res.neighbor_points.shape[1] - tq.shape[1]) <= 0.01 * tq.shape[1]
+    # compare through a per-pixel dictionary keyed on the (exactly preserved) target point
+    key = {tuple(p): (a, b) for p, a, b in zip(tp[0].numpy().round(5).tolist(), tq[0].numpy(), tn[0].numpy())}
+    hits = close = 0
+    for p, a in zip(res.new_target_points[0].round(5).tolist(), res.neighbor_points[0]):
+        if tuple(p) in key:
+            hits += 1
+            close += np.linalg.norm(a - key[tuple(p)][0]) < 1e-3
+    assert hits > 0.95 * tq.shape[1] and close > 0.97 * hits
+
+
+PROJ_SMALL = [("proj_vmap", "vertex_map", "vertex_map"), ("proj_ndarray", "ndarray", "numpy_pc")]
+
+
+@pytest.mark.parametrize("name,layout,key", PROJ_SMALL)
+def test_icp_projective_small_vs_reference_golden(b200, syn, golden_icp_small, name, layout, key):
+    algo = _make(b200, "projective", 32, 512, key, 8, lm_size=4)
+    iters = []
+    poses = _drive(algo, _frames(syn, b200.grid_sample, layout, 32, 512, None), 7, iters)
+    flips, worst = check_pose_sequence(poses, iters, golden_icp_small[f"{name}_poses"], golden_icp_small[f"{name}_losses"], name=name)
+    print(name, "flips", flips, "worst", worst)
+
+
+def test_icp_cfg3_projective_full_size_vs_reference_golden(b200, syn, golden_icp_full):
+    """BASELINE config 3 (128x2048 vertex-map input, projective map K<=20, normals kernel 5)."""
+    ref = golden_icp_full["cfg3_proj_poses"]
+    algo = _make(b200, "projective", 128, 2048, "vertex_map", 10)
+    iters = []
+    poses = _drive(algo, _frames(syn, b200.grid_sample, "vertex_map", 128, 2048, None, device="cuda"), len(ref) + 1, iters)
+    flips, worst = check_pose_sequence(poses, iters, ref, golden_icp_full["cfg3_proj_losses"], name="cfg3_proj")
+    print("cfg3", "flips", flips, "worst", worst)
