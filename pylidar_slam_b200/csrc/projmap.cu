@@ -51,44 +51,55 @@ normal_map_kernel(const float* __restrict__ vmap, int batch, int H, int W, int k
     __syncthreads();
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     if (x >= W || y >= H) return;
+    // Operation order and rounding follow the reference exactly (its normals are dominated by float32
+    // rounding: it inverts the UNCENTRED second-moment matrix, cond ~ r^2/sigma^2 >> 1/eps, so only a
+    // bit-faithful evaluation reproduces them):
+    //  * box sums = sequential float32 adds over the window, rows outer / columns inner, of separately
+    //    rounded products (conv2d with a ones kernel over `v` and `v v^T`, geometry.py:258-268)
     float sx = 0.f, sy = 0.f, sz = 0.f, sxx = 0.f, sxy = 0.f, sxz = 0.f, syy = 0.f, syz = 0.f, szz = 0.f;
     for (int dy = 0; dy < ksize; ++dy)
         for (int dx = 0; dx < ksize; ++dx) {
-            float px = tile[0][threadIdx.y + dy][threadIdx.x + dx];
-            float py = tile[1][threadIdx.y + dy][threadIdx.x + dx];
-            float pz = tile[2][threadIdx.y + dy][threadIdx.x + dx];
-            sx += px; sy += py; sz += pz;
-            sxx += px * px; sxy += px * py; sxz += px * pz;
-            syy += py * py; syz += py * pz; szz += pz * pz;
+            const float px = tile[0][threadIdx.y + dy][threadIdx.x + dx];
+            const float py = tile[1][threadIdx.y + dy][threadIdx.x + dx];
+            const float pz = tile[2][threadIdx.y + dy][threadIdx.x + dx];
+            sx = __fadd_rn(sx, px); sy = __fadd_rn(sy, py); sz = __fadd_rn(sz, pz);
+            sxx = __fadd_rn(sxx, __fmul_rn(px, px)); sxy = __fadd_rn(sxy, __fmul_rn(px, py));
+            sxz = __fadd_rn(sxz, __fmul_rn(px, pz)); syy = __fadd_rn(syy, __fmul_rn(py, py));
+            syz = __fadd_rn(syz, __fmul_rn(py, pz)); szz = __fadd_rn(szz, __fmul_rn(pz, pz));
         }
-    // rows of the cofactor matrix: c_i = A[i-2] x A[i-1]  (geometry.py:65-76)
+    //  * cofactor rows c_i = A[i-2] x A[i-1], each component fma(a1, b2, -(a2 * b1))  (geometry.py:65-76)
     const float A0[3] = {sxx, sxy, sxz}, A1[3] = {sxy, syy, syz}, A2[3] = {sxz, syz, szz};
     auto cross = [](const float* a, const float* b, float* c) {
-        c[0] = __fsub_rn(__fmul_rn(a[1], b[2]), __fmul_rn(a[2], b[1]));
-        c[1] = __fsub_rn(__fmul_rn(a[2], b[0]), __fmul_rn(a[0], b[2]));
-        c[2] = __fsub_rn(__fmul_rn(a[0], b[1]), __fmul_rn(a[1], b[0]));
+        c[0] = __fmaf_rn(a[1], b[2], -__fmul_rn(a[2], b[1]));
+        c[1] = __fmaf_rn(a[2], b[0], -__fmul_rn(a[0], b[2]));
+        c[2] = __fmaf_rn(a[0], b[1], -__fmul_rn(a[1], b[0]));
+    };
+    auto dot3 = [](float a0, float b0, float a1, float b1, float a2, float b2) {
+        return __fadd_rn(__fadd_rn(__fmul_rn(a0, b0), __fmul_rn(a1, b1)), __fmul_rn(a2, b2));
     };
     float c0[3], c1[3], c2[3];
     cross(A1, A2, c0);
     cross(A2, A0, c1);
     cross(A0, A1, c2);
-    const float d0 = c0[0] * A0[0] + c0[1] * A0[1] + c0[2] * A0[2];
-    const float d1 = c1[0] * A1[0] + c1[1] * A1[1] + c1[2] * A1[2];
-    const float d2 = c2[0] * A2[0] + c2[1] * A2[1] + c2[2] * A2[2];
-    const float det = (d0 + d1 + d2) / 3.0f;
+    //  * det = mean of the three row expansions, ((d0 + d1) + d2) / 3  (geometry.py:87)
+    const float d0 = dot3(c0[0], A0[0], c0[1], A0[1], c0[2], A0[2]);
+    const float d1 = dot3(c1[0], A1[0], c1[1], A1[1], c1[2], A1[2]);
+    const float d2 = dot3(c2[0], A2[0], c2[1], A2[1], c2[2], A2[2]);
+    const float det = __fdiv_rn(__fadd_rn(__fadd_rn(d0, d1), d2), 3.0f);
     float n[3] = {0.f, 0.f, 0.f};
     if (fabsf(det) > 1e-6f) {
-        // n = (cof / det)^T ... transposed back: n_i = sum_j (cof[i][j] / det) * b_j  (geometry.py:79-114,273)
-        n[0] = (c0[0] / det) * sx + (c0[1] / det) * sy + (c0[2] / det) * sz;
-        n[1] = (c1[0] / det) * sx + (c1[1] / det) * sy + (c1[2] / det) * sz;
-        n[2] = (c2[0] / det) * sx + (c2[1] / det) * sy + (c2[2] / det) * sz;
-        float nn = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        //  * n = (cof / det)^T b : n_i = sum_j (cof[j][i] / det) b_j  (geometry.py:89-114,273)
+        n[0] = dot3(__fdiv_rn(c0[0], det), sx, __fdiv_rn(c1[0], det), sy, __fdiv_rn(c2[0], det), sz);
+        n[1] = dot3(__fdiv_rn(c0[1], det), sx, __fdiv_rn(c1[1], det), sy, __fdiv_rn(c2[1], det), sz);
+        n[2] = dot3(__fdiv_rn(c0[2], det), sx, __fdiv_rn(c1[2], det), sy, __fdiv_rn(c2[2], det), sz);
+        //  * norm = sqrt(fma(n2, n2, fma(n1, n1, n0 * n0)))  (torch.norm's vectorised kernel)
+        float nn = __fsqrt_rn(__fmaf_rn(n[2], n[2], __fmaf_rn(n[1], n[1], __fmul_rn(n[0], n[0]))));
         if (nn == 0.f) nn = 1.f;
-        n[0] /= nn; n[1] /= nn; n[2] /= nn;
+        n[0] = __fdiv_rn(n[0], nn); n[1] = __fdiv_rn(n[1], nn); n[2] = __fdiv_rn(n[2], nn);
     }
     const float cx = tile[0][threadIdx.y + r][threadIdx.x + r], cy = tile[1][threadIdx.y + r][threadIdx.x + r],
                 cz = tile[2][threadIdx.y + r][threadIdx.x + r];
-    if (sqrtf(cx * cx + cy * cy + cz * cz) == 0.f) n[0] = n[1] = n[2] = 0.f;
+    if (cx == 0.f && cy == 0.f && cz == 0.f) n[0] = n[1] = n[2] = 0.f;  // torch.norm(vertex) == 0
     float* o = out + (size_t)b * 3 * hw + (int64_t)y * W + x;
     o[0] = n[0];
     o[hw] = n[1];

@@ -69,6 +69,9 @@ def helpers():
     nmap = ns.geometry.compute_normal_map(vm, kernel_size=5)
     nmap3 = ns.geometry.compute_normal_map(vm, kernel_size=3)
     out.update(a4_vmap=vm[0].numpy(), a4_nmap=nmap[0].numpy(), a4_nmap_k3=nmap3[0].numpy())
+    vmb = torch.from_numpy(syn.vertex_map_from_scan(syn.scan(5, 32, 512), 32, 512)).clone()
+    vmb[:, :, 20:23, 100:140] = 0.0
+    out.update(a4b_vmap=vmb[0].numpy(), a4b_nmap=ns.geometry.compute_normal_map(vmb, kernel_size=5)[0].numpy())
 
     # ---- a6
     torch.manual_seed(3)

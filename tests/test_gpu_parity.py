@@ -402,17 +402,13 @@ def _normal_agreement(a, b, vmap):
 
 
 def test_a4_normal_map_golden_and_oracle(b200, orc, syn, golden_helpers):
+    """The reference's normals are float32-rounding dominated (it inverts the uncentred second-moment
+    matrix), so the kernel reproduces its exact operation order; the goldens are matched BIT-EXACTLY."""
     g = golden_helpers
-    for k, key in ((5, "a4_nmap"), (3, "a4_nmap_k3")):
-        n = b200.compute_normal_map(g["a4_vmap"][None], kernel_size=k)[0]
+    for k, vkey, key in ((5, "a4_vmap", "a4_nmap"), (3, "a4_vmap", "a4_nmap_k3"), (5, "a4b_vmap", "a4b_nmap")):
+        n = b200.compute_normal_map(g[vkey][None], kernel_size=k)[0]
         assert n.shape == g[key].shape
-        # identical null pattern (null vertex -> zero normal)
-        null = np.abs(g["a4_vmap"]).max(0) == 0
-        assert np.all(n[:, null] == 0)
-        tight, loose = _normal_agreement(n, g[key], g["a4_vmap"])
-        # the reference inverts the UNCENTRED second-moment matrix in float32 (cond ~ r^2/sigma^2): its own
-        # normals carry summation-order noise, so agreement is statistical, not bitwise
-        assert tight > 0.80 and loose > 0.97, (k, tight, loose)
+        assert np.mean(n == g[key]) > 0.9999, (key, np.mean(n == g[key]))
         norms = np.linalg.norm(n, axis=0)
         assert np.all((np.abs(norms - 1) < 1e-4) | (norms == 0))
     H, W = 64, 2048
@@ -420,7 +416,11 @@ def test_a4_normal_map_golden_and_oracle(b200, orc, syn, golden_helpers):
     ref = orc.normal_map(torch.from_numpy(vm), 5)[0].numpy()
     out = b200.compute_normal_map(torch.from_numpy(vm).cuda(), 5)[0].cpu().numpy()
     tight, loose = _normal_agreement(out, ref, vm[0])
-    assert tight > 0.80 and loose > 0.97, (tight, loose)
+    assert tight > 0.995 and loose > 0.999, (tight, loose)
+    B = 2                                                    # batched call
+    both = np.concatenate([vm, syn.vertex_map_from_scan(syn.scan(6, H, W), H, W)], 0)
+    outb = b200.compute_normal_map(both, 5)
+    assert outb.shape == (B, 3, H, W) and np.array_equal(outb[0], out)
 
 
 def test_a6_compute_neighbors_golden(b200, golden_helpers):
@@ -465,9 +465,11 @@ def test_a5_projective_map_lifecycle_vs_oracle(b200, orc, syn):
         assert mv.shape == tuple(theirs.model_vmap.shape)
         tv = theirs.model_vmap.numpy()
         for j in range(mv.shape[0]):
-            assert _pixel_mismatch(mv[j], tv[j]) < 5e-3, (k, j)   # z-buffer winners; poses differ by ~1e-7
-            same = np.all(np.abs(mv[j] - tv[j]) < 1e-3, axis=0) & (np.abs(tv[j]).max(0) > 0)
-            assert np.mean(same) > 0.95
+            # same z-buffer winners up to the ~1e-7 difference between the rigid and the LU pose inverse
+            occupied = np.abs(tv[j]).max(0) > 0
+            same = np.all(np.abs(mv[j] - tv[j]) < 1e-3, axis=0)
+            assert np.mean(same[occupied]) > 0.995, (k, j, np.mean(same[occupied]))
+            assert np.mean((np.abs(mv[j]).max(0) > 0) == occupied) > 0.999
     q = syn.scan(6, H, W)
     T = syn.gt_relative_pose(6).astype(np.float32)
     q = q @ T[:3, :3].T + T[:3, 3]
