@@ -32,8 +32,16 @@ from pylidar_slam_b200 import synthetic as syn  # noqa: E402
 # index_put_ with duplicate pixel indices) is only "closest point wins" when ATen runs the
 # scatter on ONE thread; with several intra-op threads the chunks race and ~3% of colliding
 # pixels keep a farther point, differently on every run.  Goldens pin the deterministic,
-# intended semantics.
+# intended semantics.  NOTE: numba's OpenMP threading layer resets the process-wide thread count
+# the first time a jitted `parallel=True` function runs (grid_sample), silently undoing
+# torch.set_num_threads(1) -- so single_thread() is re-asserted before every reference call.
 torch.set_num_threads(1)
+
+
+def single_thread():
+    if torch.get_num_threads() != 1:
+        torch.set_num_threads(1)
+
 
 ns = ref_shims.load_reference(kdtree_workers=-1)
 SCHEMES = ["default", "huber", "exp", "neighborhood", "geman_mcclure", "square_geman_mcclure", "cauchy"]
@@ -53,6 +61,7 @@ def helpers():
     s64, i64 = ns.pointcloud.grid_sample(pts64, 0.1)
     out.update(a1_points64=pts64, a1_sample64=s64, a1_indices64=i64)
 
+    single_thread()
     # ---- a2/a3 on a real scan (dense collisions: 2 frames' worth of points into one map)
     H, W = 16, 256
     proj = ns.projection.SphericalProjector(height=H, width=W, up_fov=3.0, down_fov=-24.0)
@@ -138,6 +147,7 @@ def helpers():
     lm.update(rel, new_pc_data=torch.from_numpy(syn.scan(1, H2, W2)).unsqueeze(0))
     q = torch.from_numpy(syn.scan(2, H2, W2)[::3])
     q = pose.apply_transformation(q.unsqueeze(0), torch.from_numpy(syn.gt_relative_pose(2).astype(np.float32)).unsqueeze(0))[0]
+    single_thread()
     res = lm.nearest_neighbor_search(q)
     out.update(kd_v0=v0[0].numpy(), kd_rel=rel[0].numpy(), kd_pc1=syn.scan(1, H2, W2), kd_queries=q.numpy(),
                kd_map=lm._model_points.copy(), kd_nb=res.neighbor_points[0].numpy(),
@@ -176,6 +186,7 @@ def drive(algo, frame_fn, n_frames, with_losses=True):
     for k in range(n_frames):
         dd = frame_fn(k)
         dd["init_rpose"] = prev
+        single_thread()
         algo.process_next_frame(dd)
         if "odometry_pose" in dd:
             poses.append(dd["odometry_pose"].copy())
