@@ -57,7 +57,7 @@ def pose_errors(T, T_ref):
     return dt, ang
 
 
-def check_pose_sequence(poses, iters, ref_poses, ref_losses, threshold_delta_pose=1e-4, name=""):
+def check_pose_sequence(poses, iters, ref_poses, ref_losses, threshold_delta_pose=1e-4, name="", tol_t=1e-4, tol_r=1e-5):
     """Per-frame pose parity against reference goldens, aware of the ICP stop rule.
 
     North-star tolerance: 1e-4 relative translation, 1e-5 rad.  It is enforced on every frame whose
@@ -73,11 +73,11 @@ def check_pose_sequence(poses, iters, ref_poses, ref_losses, threshold_delta_pos
         dt, ang = pose_errors(T, Tr)
         t_norm = max(np.linalg.norm(np.asarray(Tr)[:3, 3]), 1e-12)
         if int(iters[k]) == n_ref:
-            assert dt <= 1e-4 and ang <= 1e-5, (name, k, dt, ang)
+            assert dt <= tol_t and ang <= tol_r, (name, k, dt, ang)
             worst = (max(worst[0], dt), max(worst[1], ang))
         else:
             flips += 1
-            assert dt <= 1e-4 + 1.5 * threshold_delta_pose / t_norm and ang <= 1e-5 + 1.5 * threshold_delta_pose, \
+            assert dt <= tol_t + 1.5 * threshold_delta_pose / t_norm and ang <= tol_r + 1.5 * threshold_delta_pose, \
                 (name, k, dt, ang, "iteration-count flip", int(iters[k]), n_ref)
     assert flips <= max(2, len(ref_poses) // 4), (name, "too many stop-rule flips", flips)
     return flips, worst

