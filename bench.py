@@ -180,6 +180,7 @@ def b200_arm(args):
         algo = b200.ICPFrameToModel(cfg, projector=projector, device=dev, stream=stream.cuda_stream)
         algo.init()
         if world > 1:
+            from pylidar_slam_b200.distributed import init_comm
             init_comm(algo.ctx, dist, rank, world, dev)
         return algo
 
@@ -328,30 +329,6 @@ def b200_arm(args):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-
-
-def init_comm(ctx, dist, rank, world, dev):
-    """Creates the library's NCCL communicator: unique id from rank 0, broadcast with torch.distributed."""
-    import ctypes as C
-    import torch
-    nccl_path = find_nccl()
-    uid = torch.zeros(128, dtype=torch.uint8)
-    if rank == 0:
-        buf = (C.c_ubyte * 128)()
-        st = ctx.lib.pls_comm_unique_id(nccl_path.encode(), buf)
-        assert st == 0, "pls_comm_unique_id failed"
-        uid = torch.tensor(list(buf), dtype=torch.uint8)
-    uid = uid.to(dev)
-    dist.broadcast(uid, 0)
-    raw = bytes(uid.cpu().tolist())
-    ctx.call("pls_comm_init", world, rank, raw, nccl_path.encode())
-
-
-def find_nccl():
-    import glob
-    import torch
-    cands = glob.glob(os.path.join(os.path.dirname(os.path.dirname(torch.__file__)), "nvidia", "nccl", "lib", "libnccl.so*"))
-    return cands[0] if cands else "libnccl.so.2"
 
 
 def main():

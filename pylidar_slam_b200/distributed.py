@@ -1,0 +1,52 @@
+"""Multi-GPU plumbing: one process per GPU; every rank holds the whole local
+map (kd) or all model maps (projective) and reduces a shard of the correspondences; the 30
+normal-equation accumulators are all-reduced once per ICP iteration inside the library (NCCL on the
+context's stream).  torch.distributed only carries the rendezvous (the 128-byte ncclUniqueId)."""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+
+
+def query_shard(num_queries: int, rank: int, world: int) -> np.ndarray:
+    """kd map: rank r reduces queries r, r + world, ... (kd_icp_iter_kernel's q_begin/q_stride)."""
+    return np.arange(rank, num_queries, world)
+
+
+def pixel_shard(num_pixels: int, rank: int, world: int):
+    """projective map: rank r reduces pixels [hw*r/world, hw*(r+1)/world) (proj_icp_iter_kernel)."""
+    return num_pixels * rank // world, num_pixels * (rank + 1) // world
+
+
+def find_nccl() -> str:
+    import torch
+    cands = sorted(glob.glob(os.path.join(os.path.dirname(os.path.dirname(torch.__file__)), "nvidia", "nccl", "lib",
+                                          "libnccl.so*")))
+    return cands[0] if cands else "libnccl.so.2"
+
+
+def broadcast_unique_id(make_id, dist, rank: int, device=None) -> bytes:
+    """Rank 0 creates the 128-byte id with `make_id()`; every rank returns the same bytes."""
+    import torch
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        uid = torch.tensor(list(make_id()), dtype=torch.uint8)
+    if device is not None:
+        uid = uid.to(device)
+    dist.broadcast(uid, 0)
+    return bytes(uid.cpu().tolist())
+
+
+def init_comm(ctx, dist, rank: int, world: int, device) -> None:
+    """Creates the library's NCCL communicator for `ctx` (collective over all ranks)."""
+    nccl_path = find_nccl().encode()
+
+    def make_id():
+        buf = (C.c_ubyte * 128)()
+        st = ctx.lib.pls_comm_unique_id(nccl_path, buf)
+        assert st == 0, "pls_comm_unique_id failed"
+        return bytes(buf)
+
+    raw = broadcast_unique_id(make_id, dist, rank, device)
+    ctx.call("pls_comm_init", world, rank, raw, nccl_path)

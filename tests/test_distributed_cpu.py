@@ -1,0 +1,74 @@
+"""World-size-2 gloo tests (CPU) of the N>1 host logic: shard partitions cover every correspondence
+exactly once, the all-reduced shard accumulators equal the unsharded normal equations (same Gauss-Newton
+step), and the unique-id rendezvous delivers identical bytes to every rank."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from pylidar_slam_b200.distributed import broadcast_unique_id, pixel_shard, query_shard
+
+
+def test_shards_partition_exactly():
+    for n in (0, 1, 7, 32514, 262144):
+        for world in (1, 2, 4, 8):
+            q = np.concatenate([query_shard(n, r, world) for r in range(world)])
+            assert sorted(q.tolist()) == list(range(n))
+            edges = [pixel_shard(n, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
+
+
+def _accumulators(ref, tgt, nrm, scheme, sigma):
+    """The 30 accumulators (21 upper JtWJ, 6 JtWr, sum (w r)^2, sum r^2, count) in float64."""
+    from oracle import icp_oracle as orc
+    x = torch.zeros(1, 6, dtype=ref.dtype)
+    J = orc.p2plane_jacobian(x, tgt, nrm)[0]
+    r = orc.p2plane_residual(x, tgt, ref, nrm)[0]
+    w = orc.ls_weights(scheme, sigma, r.unsqueeze(0), tgt, ref)[0]
+    if w.dim() == 0 or w.numel() == 1:
+        w = torch.ones_like(r) * w.reshape(-1)[0]
+    wj = (J * w.unsqueeze(-1)).double()
+    wr = (r * w).double()
+    H = wj.t() @ wj
+    acc = [H[a, b] for a in range(6) for b in range(a, 6)] + list(wj.t() @ wr) + [(wr * wr).sum(), (r.double() ** 2).sum(),
+                                                                                 torch.tensor(float(r.numel()), dtype=torch.float64)]
+    return torch.stack([torch.as_tensor(v, dtype=torch.float64) for v in acc])
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    N = 5001
+    tgt = torch.randn(1, N, 3) * 10
+    nrm = torch.randn(1, N, 3)
+    nrm /= nrm.norm(dim=-1, keepdim=True)
+    ref = tgt + 0.01 * torch.randn(1, N, 3) + torch.tensor([0.05, -0.02, 0.01])
+    full = _accumulators(ref, tgt, nrm, "geman_mcclure", 0.3)
+    idx = torch.from_numpy(query_shard(N, rank, world))
+    part = _accumulators(ref[:, idx], tgt[:, idx], nrm[:, idx], "geman_mcclure", 0.3)
+    dist.all_reduce(part, op=dist.ReduceOp.SUM)               # what ncclAllReduce does on the device
+    lo, hi = pixel_shard(N, rank, world)
+    part2 = _accumulators(ref[:, lo:hi], tgt[:, lo:hi], nrm[:, lo:hi], "geman_mcclure", 0.3)
+    dist.all_reduce(part2, op=dist.ReduceOp.SUM)
+    uid = broadcast_unique_id(lambda: bytes(range(128)), dist, rank)
+    ok = bool(torch.allclose(part, full, rtol=1e-10, atol=1e-9)) and bool(torch.allclose(part2, full, rtol=1e-10, atol=1e-9))
+    ok = ok and uid == bytes(range(128)) and int(part[29]) == N
+    out[rank] = ok
+    dist.destroy_process_group()
+
+
+def test_sharded_reduction_equals_unsharded_gloo_world2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] and out[1]

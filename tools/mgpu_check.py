@@ -1,0 +1,66 @@
+"""Run under torchrun: the sharded (N-rank) odometry must reproduce the single-GPU poses.
+Every rank runs the N-rank context; rank 0 also runs a private 1-rank context on the same frames.
+Fixed iteration count (threshold_delta_pose = 0) so the ICP stop rule cannot flip."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import torch.distributed as dist
+import pylidar_slam_b200 as b200
+from pylidar_slam_b200 import synthetic as syn
+from pylidar_slam_b200.distributed import init_comm
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+mode = sys.argv[1] if len(sys.argv) > 1 else "kdtree"
+H, W, F = (64, 2048, 8) if mode == "kdtree" else (64, 1024, 6)
+
+
+def make(with_comm):
+    lm = b200.KdTreeLocalMapConfig(local_map_size=20) if mode == "kdtree" else b200.ProjectiveLocalMapConfig(local_map_size=20)
+    cfg = b200.ICPFrameToModelConfig(local_map=lm, alignment=b200.GaussNewtonPointToPlaneConfig(
+        gauss_newton_config=dict(scheme="geman_mcclure", sigma=0.3, max_iters=1)), max_num_alignments=6,
+        threshold_delta_pose=0.0, data_key="numpy_pc" if mode == "kdtree" else "vertex_map")
+    algo = b200.ICPFrameToModel(cfg, projector=b200.SphericalProjector(height=H, width=W, up_fov=3.0, down_fov=-24.0), device=dev)
+    algo.init()
+    if with_comm:
+        init_comm(algo.ctx, dist, rank, world, dev)
+    return algo
+
+
+def drive(algo):
+    prev, poses = None, []
+    for k in range(F):
+        pc = syn.scan(k, H, W)
+        if mode == "kdtree":
+            s, _ = b200.grid_sample(pc, 0.3, ctx=algo.ctx)
+            dd = {"numpy_pc": s}
+        else:
+            dd = {"vertex_map": torch.from_numpy(syn.vertex_map_from_scan(pc, H, W))}
+        dd["init_rpose"] = prev
+        algo.process_next_frame(dd)
+        if "odometry_pose" in dd:
+            prev = dd["odometry_pose"].astype(np.float64)
+            poses.append(prev)
+    return np.stack(poses)
+
+
+sharded = drive(make(True))
+gathered = [torch.zeros_like(torch.from_numpy(sharded)).to(dev) for _ in range(world)]
+dist.all_gather(gathered, torch.from_numpy(sharded).to(dev))
+ok = True
+if rank == 0:
+    single = drive(make(False))
+    for r in range(world):
+        g = gathered[r].cpu().numpy()
+        same_across = np.abs(g - sharded).max()
+        ok = ok and same_across == 0.0          # every rank returns bit-identical poses
+    dt = np.linalg.norm(sharded[:, :3, 3] - single[:, :3, 3], axis=1) / np.linalg.norm(single[:, :3, 3], axis=1)
+    dr = np.abs(sharded[:, :3, :3] - single[:, :3, :3]).max()
+    print(f"[mgpu_check {mode} world={world}] identical across ranks: {ok}; vs 1 GPU: max rel dt {dt.max():.2e}, max |dR| {dr:.2e}")
+    ok = ok and dt.max() <= 1e-4 and dr <= 1e-5
+flag = torch.tensor([1 if ok else 0], device=dev)
+dist.broadcast(flag, 0)
+dist.destroy_process_group()
+sys.exit(0 if int(flag.item()) == 1 else 1)
