@@ -75,11 +75,15 @@ __global__ void gn_solve_kernel(GnState<T>* state, const double* __restrict__ pa
                                 T norm_stop) {
     if (state->done) return;
     __shared__ double sums[NACC];
-    if (threadIdx.x < NACC) {
-        double s = 0.0;
-        for (int b = 0; b < num_blocks; ++b) s += partials[(size_t)b * NACC + threadIdx.x];
-        sums[threadIdx.x] = s;
-        state->sums[threadIdx.x] = s;
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int a = warp; a < NACC; a += 8) {
+            double s = 0.0;
+            for (int b = lane; b < num_blocks; b += 32) s += partials[(size_t)b * NACC + a];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+            if (lane == 0) { sums[a] = s; state->sums[a] = s; }
+        }
     }
     __syncthreads();
     if (threadIdx.x != 0) return;
@@ -144,7 +148,7 @@ void align_impl(pls_context* ctx, const void* ref, const void* tgt, const void* 
                                                                   (T*)o_loss.dev, ctx->partials.as<double>());
             PLS_CHECK_LAUNCH();
         }
-        gn_solve_kernel<T><<<1, 32, 0, st>>>(d_state, ctx->partials.as<double>(), blocks, (T)norm_stop);
+        gn_solve_kernel<T><<<1, 256, 0, st>>>(d_state, ctx->partials.as<double>(), blocks, (T)norm_stop);
         PLS_CHECK_LAUNCH();
     }
     PLS_CUDA(cudaMemcpyAsync(&h_state, d_state, sizeof(h_state), cudaMemcpyDeviceToHost, st));

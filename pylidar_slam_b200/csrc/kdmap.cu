@@ -69,12 +69,19 @@ kd_move_append_kernel(const float4* __restrict__ src, int64_t skip, int64_t kept
             mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
         }
     }
-    if ((threadIdx.x & 31) == 0) {
+    __shared__ float smn[8][3], smx[8][3];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            if (mn[a] != FLT_MAX) atomicMin(&bbox[a], float_to_ordered(mn[a]));
-            if (mx[a] != -FLT_MAX) atomicMax(&bbox[3 + a], float_to_ordered(mx[a]));
-        }
+        for (int a = 0; a < 3; ++a) { smn[warp][a] = mn[a]; smx[warp][a] = mx[a]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {  // one atomic pair per axis per block
+        const int a = threadIdx.x;
+        float lo = smn[0][a], hi = smx[0][a];
+        for (int w = 1; w < 8; ++w) { lo = fminf(lo, smn[w][a]); hi = fmaxf(hi, smx[w][a]); }
+        if (lo != FLT_MAX) atomicMin(&bbox[a], float_to_ordered(lo));
+        if (hi != -FLT_MAX) atomicMax(&bbox[3 + a], float_to_ordered(hi));
     }
 }
 
@@ -142,14 +149,15 @@ __global__ void kd_gather_kernel(const float4* __restrict__ pts, const uint32_t*
     }
 }
 
+// keys of the chunk leaders: chunk i is represented by the Morton key of its first point
 __device__ __forceinline__ int delta_fn(const uint64_t* __restrict__ keys, int n, int i, int j) {
     if (j < 0 || j >= n) return -1;
-    uint64_t a = keys[i], b = keys[j];
+    uint64_t a = keys[(size_t)i * KD_CHUNK], b = keys[(size_t)j * KD_CHUNK];
     if (a == b) return 64 + __clz(i ^ j);
     return __clzll((long long)(a ^ b));
 }
 
-// Karras 2012: internal node i in [0, n-2]
+// Karras 2012 over the n chunk leaders: internal node i in [0, n-2]
 __global__ void kd_hierarchy_kernel(const uint64_t* __restrict__ keys, int n, int4* __restrict__ ranges,
                                     int* __restrict__ parent /* [n-1 internal][n leaves] */) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n - 1; i += gridDim.x * blockDim.x) {
@@ -177,11 +185,17 @@ __global__ void kd_hierarchy_kernel(const uint64_t* __restrict__ keys, int n, in
     }
 }
 
-__device__ __forceinline__ void child_box(const float4* __restrict__ sorted, const float4* nodes, int lo, int hi,
-                                          int internal_id, float* mn, float* mx) {
-    if (lo == hi) {
-        float4 p = sorted[lo];
+__device__ __forceinline__ void child_box(const float4* __restrict__ sorted, int num_points, const float4* nodes,
+                                          int lo, int hi, int internal_id, float* mn, float* mx) {
+    if (lo == hi) {  // leaf chunk: union of its <= KD_CHUNK points
+        const int p0 = lo * KD_CHUNK, p1 = min(p0 + KD_CHUNK, num_points);
+        float4 p = sorted[p0];
         mn[0] = mx[0] = p.x; mn[1] = mx[1] = p.y; mn[2] = mx[2] = p.z;
+        for (int i = p0 + 1; i < p1; ++i) {
+            p = sorted[i];
+            mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+            mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+        }
     } else {
         const float4 a = __ldcg(nodes + 4 * (size_t)internal_id);
         const float4 b = __ldcg(nodes + 4 * (size_t)internal_id + 1);
@@ -191,8 +205,9 @@ __device__ __forceinline__ void child_box(const float4* __restrict__ sorted, con
     }
 }
 
-__global__ void kd_boxes_kernel(const float4* __restrict__ sorted, int n, const int4* __restrict__ ranges,
-                                const int* __restrict__ parent, int* __restrict__ visit, float4* nodes) {
+__global__ void kd_boxes_kernel(const float4* __restrict__ sorted, int num_points, int n,
+                                const int4* __restrict__ ranges, const int* __restrict__ parent,
+                                int* __restrict__ visit, float4* nodes) {
     for (int leaf = blockIdx.x * blockDim.x + threadIdx.x; leaf < n; leaf += gridDim.x * blockDim.x) {
         int cur = parent[(n - 1) + leaf];
         while (cur >= 0) {
@@ -200,8 +215,8 @@ __global__ void kd_boxes_kernel(const float4* __restrict__ sorted, int n, const 
             if (atomicAdd(&visit[cur], 1) == 0) break;  // first arrival: the sibling subtree is not done
             const int4 rg = ranges[cur];
             float lmn[3], lmx[3], rmn[3], rmx[3];
-            child_box(sorted, nodes, rg.x, rg.y, rg.y, lmn, lmx);
-            child_box(sorted, nodes, rg.y + 1, rg.z, rg.y + 1, rmn, rmx);
+            child_box(sorted, num_points, nodes, rg.x, rg.y, rg.y, lmn, lmx);
+            child_box(sorted, num_points, nodes, rg.y + 1, rg.z, rg.y + 1, rmn, rmx);
             float4* o = nodes + 4 * (size_t)cur;
             __stcg(o + 0, make_float4(lmn[0], lmn[1], lmn[2], lmx[0]));
             __stcg(o + 1, make_float4(lmx[1], lmx[2], rmn[0], rmn[1]));
@@ -282,6 +297,7 @@ KdIndex make_index(pls_context* ctx) {
     ix.nodes = ctx->kd.nodes.as<float4>();
     ix.normals = ctx->kd.normals.as<float4>();
     ix.M = (int)ctx->kd.indexed;
+    ix.C = (int)((ctx->kd.indexed + KD_CHUNK - 1) / KD_CHUNK);
     return ix;
 }
 
@@ -313,13 +329,14 @@ void build_index(pls_context* ctx) {
     kd_gather_kernel<<<grid_for(M, 256, 8 * kNumSMs), 256, 0, st>>>(pts, sv, M, kd.sorted.as<float4>(),
                                                                      kd.inv_order.as<uint32_t>());
     PLS_CHECK_LAUNCH();
-    if (M > 1) {
+    const int64_t C = (M + KD_CHUNK - 1) / KD_CHUNK;  // leaves of the tree = chunks of sorted points
+    if (C > 1) {
         int* visit = kd.visit.as<int>();
         int4* ranges = reinterpret_cast<int4*>(reinterpret_cast<char*>(kd.visit.p) + (((size_t)M * sizeof(int) + 15) / 16) * 16);
-        PLS_CUDA(cudaMemsetAsync(visit, 0, (size_t)M * sizeof(int), st));
-        kd_hierarchy_kernel<<<grid_for(M - 1, 128, 16 * kNumSMs), 128, 0, st>>>(sk, (int)M, ranges, kd.parent.as<int>());
+        PLS_CUDA(cudaMemsetAsync(visit, 0, (size_t)C * sizeof(int), st));
+        kd_hierarchy_kernel<<<grid_for(C - 1, 128, 16 * kNumSMs), 128, 0, st>>>(sk, (int)C, ranges, kd.parent.as<int>());
         PLS_CHECK_LAUNCH();
-        kd_boxes_kernel<<<grid_for(M, 128, 16 * kNumSMs), 128, 0, st>>>(kd.sorted.as<float4>(), (int)M, ranges,
+        kd_boxes_kernel<<<grid_for(C, 128, 16 * kNumSMs), 128, 0, st>>>(kd.sorted.as<float4>(), (int)M, (int)C, ranges,
                                                                         kd.parent.as<int>(), visit, kd.nodes.as<float4>());
         PLS_CHECK_LAUNCH();
     }

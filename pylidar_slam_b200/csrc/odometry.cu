@@ -31,32 +31,42 @@ __global__ void frame_begin_kernel(FrameResult* fr, const float* T0 /*16, device
     if (t < NACC) fr->last_sums[t] = 0.0;
 }
 
-__global__ void reduce_partials_kernel(FrameResult* fr, const double* __restrict__ partials, int num_blocks) {
-    if (fr->done) return;
-    if (threadIdx.x < NACC) {
+
+// Deterministic parallel sum of the block partial rows: warp w owns accumulators w, w+8, ...; its lanes
+// stride over the rows and a fixed shuffle tree combines them (same order every run).
+__device__ __forceinline__ void sum_partials_256(const double* __restrict__ partials, int num_blocks, double* sums) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int a = warp; a < NACC; a += 8) {
         double s = 0.0;
-        for (int b = 0; b < num_blocks; ++b) s += partials[(size_t)b * NACC + threadIdx.x];
-        fr->last_sums[threadIdx.x] = s;
+        for (int b = lane; b < num_blocks; b += 32) s += partials[(size_t)b * NACC + a];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if (lane == 0) sums[a] = s;
     }
 }
 
-// K7: normal-equation solve + ICP bookkeeping.  num_blocks == 0: last_sums already holds the
-// (all-reduced) sums.
-__global__ void icp_step_kernel(FrameResult* fr, const double* __restrict__ partials, int num_blocks,
-                                float threshold_delta) {
+__global__ void __launch_bounds__(256) reduce_partials_kernel(FrameResult* fr, const double* __restrict__ partials,
+                                                              int num_blocks) {
     if (fr->done) return;
     __shared__ double sums[NACC];
-    if (threadIdx.x < NACC) {
-        double s = 0.0;
-        if (num_blocks > 0) {
-            for (int b = 0; b < num_blocks; ++b) s += partials[(size_t)b * NACC + threadIdx.x];
-            fr->last_sums[threadIdx.x] = s;
-        } else {
-            s = fr->last_sums[threadIdx.x];
-        }
-        sums[threadIdx.x] = s;
+    sum_partials_256(partials, num_blocks, sums);
+    __syncthreads();
+    if (threadIdx.x < NACC) fr->last_sums[threadIdx.x] = sums[threadIdx.x];
+}
+
+// K7: normal-equation solve + ICP bookkeeping (256 threads).  num_blocks == 0: last_sums already holds
+// the (all-reduced) sums.
+__global__ void __launch_bounds__(256) icp_step_kernel(FrameResult* fr, const double* __restrict__ partials,
+                                                       int num_blocks, float threshold_delta) {
+    if (fr->done) return;
+    __shared__ double sums[NACC];
+    if (num_blocks > 0) {
+        sum_partials_256(partials, num_blocks, sums);
+    } else if (threadIdx.x < NACC) {
+        sums[threadIdx.x] = fr->last_sums[threadIdx.x];
     }
     __syncthreads();
+    if (num_blocks > 0 && threadIdx.x < NACC) fr->last_sums[threadIdx.x] = sums[threadIdx.x];
     if (threadIdx.x != 0) return;
     const int it = fr->iters;
     fr->iters = it + 1;
@@ -143,12 +153,12 @@ int run_icp(pls_context* ctx, const float* T0_dev, int64_t query_bound) {
         else blocks = projmap_icp_iteration(ctx, query_bound, rank, size);
         last_blocks = blocks;
         if (size > 1) {
-            reduce_partials_kernel<<<1, 32, 0, st>>>(fr, ctx->partials.as<double>(), blocks);
+            reduce_partials_kernel<<<1, 256, 0, st>>>(fr, ctx->partials.as<double>(), blocks);
             PLS_CHECK_LAUNCH();
             comm_allreduce_sums(ctx, fr->last_sums);
             blocks = 0;
         }
-        icp_step_kernel<<<1, 32, 0, st>>>(fr, ctx->partials.as<double>(), blocks, ctx->cfg.threshold_delta_pose);
+        icp_step_kernel<<<1, 256, 0, st>>>(fr, ctx->partials.as<double>(), blocks, ctx->cfg.threshold_delta_pose);
         PLS_CHECK_LAUNCH();
     }
     return last_blocks;
