@@ -149,15 +149,14 @@ __global__ void kd_gather_kernel(const float4* __restrict__ pts, const uint32_t*
     }
 }
 
-// keys of the chunk leaders: chunk i is represented by the Morton key of its first point
 __device__ __forceinline__ int delta_fn(const uint64_t* __restrict__ keys, int n, int i, int j) {
     if (j < 0 || j >= n) return -1;
-    uint64_t a = keys[(size_t)i * KD_CHUNK], b = keys[(size_t)j * KD_CHUNK];
+    uint64_t a = keys[i], b = keys[j];
     if (a == b) return 64 + __clz(i ^ j);
     return __clzll((long long)(a ^ b));
 }
 
-// Karras 2012 over the n chunk leaders: internal node i in [0, n-2]
+// Karras 2012: internal node i in [0, n-2]
 __global__ void kd_hierarchy_kernel(const uint64_t* __restrict__ keys, int n, int4* __restrict__ ranges,
                                     int* __restrict__ parent /* [n-1 internal][n leaves] */) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n - 1; i += gridDim.x * blockDim.x) {
@@ -185,13 +184,13 @@ __global__ void kd_hierarchy_kernel(const uint64_t* __restrict__ keys, int n, in
     }
 }
 
-__device__ __forceinline__ void child_box(const float4* __restrict__ sorted, int num_points, const float4* nodes,
-                                          int lo, int hi, int internal_id, float* mn, float* mx) {
-    if (lo == hi) {  // leaf chunk: union of its <= KD_CHUNK points
-        const int p0 = lo * KD_CHUNK, p1 = min(p0 + KD_CHUNK, num_points);
-        float4 p = sorted[p0];
+// Box of a child of a "big" node: a treelet (<= KD_LEAF points, scanned directly) or a completed big node.
+__device__ __forceinline__ void child_box(const float4* __restrict__ sorted, const float4* nodes, int lo, int hi,
+                                          int internal_id, float* mn, float* mx) {
+    if (hi - lo + 1 <= KD_LEAF) {
+        float4 p = sorted[lo];
         mn[0] = mx[0] = p.x; mn[1] = mx[1] = p.y; mn[2] = mx[2] = p.z;
-        for (int i = p0 + 1; i < p1; ++i) {
+        for (int i = lo + 1; i <= hi; ++i) {
             p = sorted[i];
             mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
             mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
@@ -205,18 +204,34 @@ __device__ __forceinline__ void child_box(const float4* __restrict__ sorted, int
     }
 }
 
-__global__ void kd_boxes_kernel(const float4* __restrict__ sorted, int num_points, int n,
-                                const int4* __restrict__ ranges, const int* __restrict__ parent,
-                                int* __restrict__ visit, float4* nodes) {
-    for (int leaf = blockIdx.x * blockDim.x + threadIdx.x; leaf < n; leaf += gridDim.x * blockDim.x) {
-        int cur = parent[(n - 1) + leaf];
+// Bottom-up child boxes of the BIG nodes (> KD_LEAF points).  Subtrees of <= KD_LEAF points ("treelets")
+// are never descended by the search (they are scanned linearly), so the pass starts at the treelet roots:
+// thread t < n-1 is internal node t, thread t >= n-1 is point leaf t-(n-1); a thread whose node is small
+// while its parent is big "arrives" at the parent; the second arrival at a node computes its child boxes
+// and continues upward.  Chains are ~log2(KD_LEAF) levels shorter than a per-point pass.
+__global__ void kd_boxes_kernel(const float4* __restrict__ sorted, int n, const int4* __restrict__ ranges,
+                                const int* __restrict__ parent, int* __restrict__ visit, float4* nodes) {
+    const int total = 2 * n - 1;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        int cur;
+        if (t < n - 1) {
+            const int4 rg = ranges[t];
+            if (rg.z - rg.x + 1 > KD_LEAF || t == 0) continue;  // big node (completed by its children) or root
+            cur = parent[t];
+        } else {
+            cur = parent[t];  // point leaf
+        }
+        {
+            const int4 pr = ranges[cur];
+            if (pr.z - pr.x + 1 <= KD_LEAF) continue;  // inside a treelet: nothing to do
+        }
         while (cur >= 0) {
             __threadfence();
             if (atomicAdd(&visit[cur], 1) == 0) break;  // first arrival: the sibling subtree is not done
             const int4 rg = ranges[cur];
             float lmn[3], lmx[3], rmn[3], rmx[3];
-            child_box(sorted, num_points, nodes, rg.x, rg.y, rg.y, lmn, lmx);
-            child_box(sorted, num_points, nodes, rg.y + 1, rg.z, rg.y + 1, rmn, rmx);
+            child_box(sorted, nodes, rg.x, rg.y, rg.y, lmn, lmx);
+            child_box(sorted, nodes, rg.y + 1, rg.z, rg.y + 1, rmn, rmx);
             float4* o = nodes + 4 * (size_t)cur;
             __stcg(o + 0, make_float4(lmn[0], lmn[1], lmn[2], lmx[0]));
             __stcg(o + 1, make_float4(lmx[1], lmx[2], rmn[0], rmn[1]));
@@ -297,7 +312,6 @@ KdIndex make_index(pls_context* ctx) {
     ix.nodes = ctx->kd.nodes.as<float4>();
     ix.normals = ctx->kd.normals.as<float4>();
     ix.M = (int)ctx->kd.indexed;
-    ix.C = (int)((ctx->kd.indexed + KD_CHUNK - 1) / KD_CHUNK);
     return ix;
 }
 
@@ -329,14 +343,13 @@ void build_index(pls_context* ctx) {
     kd_gather_kernel<<<grid_for(M, 256, 8 * kNumSMs), 256, 0, st>>>(pts, sv, M, kd.sorted.as<float4>(),
                                                                      kd.inv_order.as<uint32_t>());
     PLS_CHECK_LAUNCH();
-    const int64_t C = (M + KD_CHUNK - 1) / KD_CHUNK;  // leaves of the tree = chunks of sorted points
-    if (C > 1) {
+    if (M > 1) {
         int* visit = kd.visit.as<int>();
         int4* ranges = reinterpret_cast<int4*>(reinterpret_cast<char*>(kd.visit.p) + (((size_t)M * sizeof(int) + 15) / 16) * 16);
-        PLS_CUDA(cudaMemsetAsync(visit, 0, (size_t)C * sizeof(int), st));
-        kd_hierarchy_kernel<<<grid_for(C - 1, 128, 16 * kNumSMs), 128, 0, st>>>(sk, (int)C, ranges, kd.parent.as<int>());
+        PLS_CUDA(cudaMemsetAsync(visit, 0, (size_t)M * sizeof(int), st));
+        kd_hierarchy_kernel<<<grid_for(M - 1, 128, 16 * kNumSMs), 128, 0, st>>>(sk, (int)M, ranges, kd.parent.as<int>());
         PLS_CHECK_LAUNCH();
-        kd_boxes_kernel<<<grid_for(C, 128, 16 * kNumSMs), 128, 0, st>>>(kd.sorted.as<float4>(), (int)M, (int)C, ranges,
+        kd_boxes_kernel<<<grid_for(2 * M, 128, 16 * kNumSMs), 128, 0, st>>>(kd.sorted.as<float4>(), (int)M, ranges,
                                                                         kd.parent.as<int>(), visit, kd.nodes.as<float4>());
         PLS_CHECK_LAUNCH();
     }

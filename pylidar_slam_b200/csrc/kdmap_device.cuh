@@ -3,14 +3,12 @@
 //
 // Index layout (all in HBM, L2-resident for the BASELINE map sizes):
 //   sorted[M]   float4  map points in Morton order; .w = bit-cast insertion index
-//   nodes[C-1]  64 B    the tree is built over CHUNKS of KD_CHUNK consecutive sorted points (C =
-//                       ceil(M / KD_CHUNK) leaves: 8x fewer nodes and a 3-level shallower bottom-up
-//                       box pass than a per-point tree).  Internal node i covers chunks
-//                       [first..last], split after `gamma`: left = [first..gamma], right =
-//                       [gamma+1..last]; the node stores BOTH child boxes, so one 64-byte fetch
-//                       decides both descents.  Child ids are implicit (Karras): internal(left) =
-//                       gamma, internal(right) = gamma + 1.  A single-chunk child is a leaf: its
-//                       <= 8 points (128 contiguous bytes) are scanned linearly.
+//   nodes[M-1]  64 B    internal node i covers sorted[first..last], split after `gamma`:
+//                       left child = [first..gamma], right child = [gamma+1..last]; the node
+//                       stores BOTH child boxes, so one 64-byte fetch decides both descents.
+//                       Child ids are implicit (Karras): internal(left) = gamma,
+//                       internal(right) = gamma + 1.  Ranges of <= LEAF points are scanned
+//                       linearly (contiguous float4 loads) instead of being descended.
 //   normals[M]  float4  lazily computed unit normal of each map point, .w = 1 once valid
 #pragma once
 #include <cuda_runtime.h>
@@ -19,7 +17,7 @@
 
 namespace pls {
 
-constexpr int KD_CHUNK = 8;
+constexpr int KD_LEAF = 8;
 constexpr int KD_STACK = 96;
 constexpr int KD_KMAX = 32;  // k + 1 <= 32
 
@@ -33,8 +31,7 @@ struct KdIndex {
     const float4* sorted;
     const float4* nodes;  // 4 float4 per node
     float4* normals;
-    int M;  // points
-    int C;  // chunks (leaves)
+    int M;
 };
 
 __device__ __forceinline__ float dist2_point(float x, float y, float z, const float4& p) {
@@ -58,7 +55,7 @@ __device__ __forceinline__ int kd_nearest(const KdIndex& ix, float x, float y, f
         best = dist2_point(x, y, z, __ldg(ix.sorted + hint));
         best_i = hint;
     }
-    if (ix.C <= 1) {
+    if (ix.M <= KD_LEAF) {
         for (int i = 0; i < ix.M; ++i) {
             float d = dist2_point(x, y, z, __ldg(ix.sorted + i));
             if (d < best) { best = d; best_i = i; }
@@ -78,18 +75,16 @@ __device__ __forceinline__ int kd_nearest(const KdIndex& ix, float x, float y, f
         const int first = __float_as_int(dd.x), gamma = __float_as_int(dd.y), last = __float_as_int(dd.z);
         float dl = dist2_box(x, y, z, a.x, a.y, a.z, a.w, b.x, b.y);
         float dr = dist2_box(x, y, z, b.z, b.w, c.x, c.y, c.z, c.w);
-        const bool lleaf = first == gamma;
-        const bool rleaf = last == gamma + 1;
+        const bool lleaf = (gamma - first + 1) <= KD_LEAF;
+        const bool rleaf = (last - gamma) <= KD_LEAF;
         if (lleaf && dl < best) {
-            const int lo = gamma * KD_CHUNK, hi = min(lo + KD_CHUNK, ix.M);
-            for (int i = lo; i < hi; ++i) {
+            for (int i = first; i <= gamma; ++i) {
                 float d = dist2_point(x, y, z, __ldg(ix.sorted + i));
                 if (d < best) { best = d; best_i = i; }
             }
         }
         if (rleaf && dr < best) {
-            const int lo = (gamma + 1) * KD_CHUNK, hi = min(lo + KD_CHUNK, ix.M);
-            for (int i = lo; i < hi; ++i) {
+            for (int i = gamma + 1; i <= last; ++i) {
                 float d = dist2_point(x, y, z, __ldg(ix.sorted + i));
                 if (d < best) { best = d; best_i = i; }
             }
@@ -137,7 +132,7 @@ __device__ __forceinline__ void knn_insert(float* d, int* idx, int k, int& count
 // Exact k-NN (k <= KD_KMAX): fills d[]/idx[] ascending, returns the number found (min(k, M)).
 __device__ __forceinline__ int kd_knn(const KdIndex& ix, float x, float y, float z, int k, float* d, int* idx) {
     int count = 0;
-    if (ix.C <= 1) {
+    if (ix.M <= KD_LEAF) {
         for (int i = 0; i < ix.M; ++i) knn_insert(d, idx, k, count, dist2_point(x, y, z, __ldg(ix.sorted + i)), i);
         return count;
     }
@@ -153,18 +148,16 @@ __device__ __forceinline__ int kd_knn(const KdIndex& ix, float x, float y, float
         const int first = __float_as_int(dd.x), gamma = __float_as_int(dd.y), last = __float_as_int(dd.z);
         float dl = dist2_box(x, y, z, a.x, a.y, a.z, a.w, b.x, b.y);
         float dr = dist2_box(x, y, z, b.z, b.w, c.x, c.y, c.z, c.w);
-        const bool lleaf = first == gamma;
-        const bool rleaf = last == gamma + 1;
+        const bool lleaf = (gamma - first + 1) <= KD_LEAF;
+        const bool rleaf = (last - gamma) <= KD_LEAF;
         float worst = count < k ? FLT_MAX : d[k - 1];
         if (lleaf && dl < worst) {
-            const int lo = gamma * KD_CHUNK, hi = min(lo + KD_CHUNK, ix.M);
-            for (int i = lo; i < hi; ++i)
+            for (int i = first; i <= gamma; ++i)
                 knn_insert(d, idx, k, count, dist2_point(x, y, z, __ldg(ix.sorted + i)), i);
             worst = count < k ? FLT_MAX : d[k - 1];
         }
         if (rleaf && dr < worst) {
-            const int lo = (gamma + 1) * KD_CHUNK, hi = min(lo + KD_CHUNK, ix.M);
-            for (int i = lo; i < hi; ++i)
+            for (int i = gamma + 1; i <= last; ++i)
                 knn_insert(d, idx, k, count, dist2_point(x, y, z, __ldg(ix.sorted + i)), i);
             worst = count < k ? FLT_MAX : d[k - 1];
         }
