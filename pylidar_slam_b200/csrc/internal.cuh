@@ -103,6 +103,10 @@ struct KdMap {
     DBuf parent, visit;     // build-time parents (internal then leaves), arrival counters
     DBuf bbox;              // 6 ordered-int words
     DBuf inv_order;         // sorted position of each stored point (for out_idx)
+    DBuf grid_hdr;          // KdGridHeader (quantisation + cell levels)
+    DBuf cells;             // cell hash tables of all levels
+    size_t table_offset[4] = {0, 0, 0, 0};
+    uint32_t table_mask[4] = {0, 0, 0, 0};
     int64_t indexed = 0;    // points covered by the index
     bool valid = false;
 };

@@ -121,13 +121,29 @@ __device__ __forceinline__ uint64_t spread3(uint64_t x) {
     return x;
 }
 
-__global__ void kd_morton_kernel(const float4* __restrict__ pts, int64_t n, const int* __restrict__ bbox,
-                                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+// Quantisation of the map: 256 Morton units per metre (3.9 mm) when the map extent allows it (<= 255 m),
+// else the 16-bit range is stretched over the extent.  Level-0 cells are 2^b0 units with a side in
+// [KD_CELL_TARGET, 2 KD_CELL_TARGET).
+__global__ void kd_grid_header_kernel(const int* __restrict__ bbox, KdGridHeader* __restrict__ hdr) {
+    if (threadIdx.x != 0) return;
     const float mnx = ordered_to_float(bbox[0]), mny = ordered_to_float(bbox[1]), mnz = ordered_to_float(bbox[2]);
     const float ex = ordered_to_float(bbox[3]) - mnx, ey = ordered_to_float(bbox[4]) - mny,
                 ez = ordered_to_float(bbox[5]) - mnz;
     const float ext = fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-6f));
-    const float scale = 65535.0f / ext;
+    const float scale = fminf(256.0f, 65535.0f / ext);
+    int b0 = 0;
+    while (b0 < 12 && (float)(1 << b0) < KD_CELL_TARGET * scale) ++b0;
+    hdr->mn[0] = mnx; hdr->mn[1] = mny; hdr->mn[2] = mnz;
+    hdr->scale = scale;
+    hdr->b0 = b0;
+    hdr->cell0 = (float)(1 << b0) / scale;
+    for (int l = 0; l < KD_LEVELS; ++l) hdr->overflow[l] = 0;
+}
+
+__global__ void kd_morton_kernel(const float4* __restrict__ pts, int64_t n, const KdGridHeader* __restrict__ hdr,
+                                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const float mnx = hdr->mn[0], mny = hdr->mn[1], mnz = hdr->mn[2];
+    const float scale = hdr->scale;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float4 p = pts[i];
         uint32_t qx = (uint32_t)fminf(fmaxf((p.x - mnx) * scale, 0.f), 65535.f);
@@ -135,6 +151,51 @@ __global__ void kd_morton_kernel(const float4* __restrict__ pts, int64_t n, cons
         uint32_t qz = (uint32_t)fminf(fmaxf((p.z - mnz) * scale, 0.f), 65535.f);
         keys[i] = spread3(qx) | (spread3(qy) << 1) | (spread3(qz) << 2);
         vals[i] = (uint32_t)i;
+    }
+}
+
+// Cell tables of all levels in one pass over the sorted keys: thread i is the head of a cell run at
+// level l if its prefix differs from key[i-1]'s, the tail if it differs from key[i+1]'s; heads store
+// `start`, tails store `end` into the slot they find-or-claim (64-bit CAS on the id words).
+struct CellTables {
+    uint4* table[KD_LEVELS];
+    uint32_t mask[KD_LEVELS];
+};
+
+__device__ __forceinline__ int cell_slot(uint4* table, uint32_t mask, uint64_t id) {
+    uint32_t h = kd_hash(id) & mask;
+    const unsigned long long want = id + 1;
+    for (int probe = 0; probe < 64; ++probe) {
+        unsigned long long* word = reinterpret_cast<unsigned long long*>(&table[h]);
+        const unsigned long long old = atomicCAS(word, 0ull, want);
+        if (old == 0ull || old == want) return (int)h;
+        h = (h + 1) & mask;
+    }
+    return -1;
+}
+
+__global__ void kd_cells_kernel(const uint64_t* __restrict__ keys, int64_t n, CellTables T, KdGridHeader* hdr) {
+    const int b0 = hdr->b0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = keys[i];
+        const uint64_t kp = i > 0 ? keys[i - 1] : ~0ull;
+        const uint64_t kn = i + 1 < n ? keys[i + 1] : ~0ull;
+#pragma unroll
+        for (int l = 0; l < KD_LEVELS; ++l) {
+            const int sh = 3 * (b0 + l);
+            const uint64_t id = k >> sh;
+            const bool head = (i == 0) || ((kp >> sh) != id);
+            const bool tail = (i + 1 == n) || ((kn >> sh) != id);
+            if (head || tail) {
+                const int slot = cell_slot(T.table[l], T.mask[l], id);
+                if (slot < 0) {
+                    hdr->overflow[l] = 1;
+                } else {
+                    if (head) T.table[l][slot].z = (uint32_t)i;
+                    if (tail) T.table[l][slot].w = (uint32_t)i;
+                }
+            }
+        }
     }
 }
 
@@ -248,7 +309,7 @@ kd_search_kernel(KdIndex ix, int k_normals, const float* __restrict__ queries, i
                  float* __restrict__ out_nrm, long long* __restrict__ out_idx) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float x = queries[3 * i], y = queries[3 * i + 1], z = queries[3 * i + 2];
-        int pos = kd_nearest(ix, x, y, z, -1, nullptr);
+        int pos = kd_nearest_fast(ix, x, y, z, -1, nullptr);
         float4 q = __ldg(ix.sorted + pos);
         out_nb[3 * i] = q.x; out_nb[3 * i + 1] = q.y; out_nb[3 * i + 2] = q.z;
         if (out_idx) out_idx[i] = (long long)__float_as_uint(q.w);
@@ -285,7 +346,7 @@ kd_icp_iter_kernel(KdIndex ix, int k_normals, const float4* __restrict__ queries
         p[0] = p0.x * sT[0] + p0.y * sT[1] + p0.z * sT[2] + sT[3];
         p[1] = p0.x * sT[4] + p0.y * sT[5] + p0.z * sT[6] + sT[7];
         p[2] = p0.x * sT[8] + p0.y * sT[9] + p0.z * sT[10] + sT[11];
-        const int pos = kd_nearest(ix, p[0], p[1], p[2], nn_prev[qi], nullptr);
+        const int pos = kd_nearest_fast(ix, p[0], p[1], p[2], nn_prev[qi], nullptr);
         nn_prev[qi] = pos;
         const float4 qq = __ldg(ix.sorted + pos);
         float q[3] = {qq.x, qq.y, qq.z};
@@ -312,6 +373,11 @@ KdIndex make_index(pls_context* ctx) {
     ix.nodes = ctx->kd.nodes.as<float4>();
     ix.normals = ctx->kd.normals.as<float4>();
     ix.M = (int)ctx->kd.indexed;
+    ix.grid = ctx->kd.grid_hdr.as<KdGridHeader>();
+    for (int l = 0; l < KD_LEVELS; ++l) {
+        ix.table[l] = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(ctx->kd.cells.p) + ctx->kd.table_offset[l]);
+        ix.mask[l] = ctx->kd.table_mask[l];
+    }
     return ix;
 }
 
@@ -334,8 +400,11 @@ void build_index(pls_context* ctx) {
     kd.parent.reserve((size_t)(2 * M) * sizeof(int), st);
     kd.visit.reserve((size_t)M * sizeof(int) + (size_t)M * sizeof(int4), st);
     PLS_CUDA(cudaMemsetAsync(kd.normals.p, 0, (size_t)M * sizeof(float4), st));
-    kd_morton_kernel<<<grid_for(M, 256, 8 * kNumSMs), 256, 0, st>>>(pts, M, kd.bbox.as<int>(), kd.morton.as<uint64_t>(),
-                                                                     kd.order.as<uint32_t>());
+    kd.grid_hdr.reserve(sizeof(KdGridHeader), st);
+    kd_grid_header_kernel<<<1, 32, 0, st>>>(kd.bbox.as<int>(), kd.grid_hdr.as<KdGridHeader>());
+    PLS_CHECK_LAUNCH();
+    kd_morton_kernel<<<grid_for(M, 256, 8 * kNumSMs), 256, 0, st>>>(pts, M, kd.grid_hdr.as<KdGridHeader>(),
+                                                                     kd.morton.as<uint64_t>(), kd.order.as<uint32_t>());
     PLS_CHECK_LAUNCH();
     uint64_t* sk;
     uint32_t* sv;
@@ -343,6 +412,26 @@ void build_index(pls_context* ctx) {
     kd_gather_kernel<<<grid_for(M, 256, 8 * kNumSMs), 256, 0, st>>>(pts, sv, M, kd.sorted.as<float4>(),
                                                                      kd.inv_order.as<uint32_t>());
     PLS_CHECK_LAUNCH();
+    {   // cell tables: level l gets a power-of-two table of >= 1.5 M / 2^l slots (overflow falls back to the BVH)
+        CellTables T;
+        size_t off = 0;
+        for (int l = 0; l < KD_LEVELS; ++l) {
+            uint64_t want = (uint64_t)(1.5 * (double)M) >> l;
+            uint32_t sz = 1024;
+            while (sz < want) sz <<= 1;
+            kd.table_mask[l] = sz - 1;
+            kd.table_offset[l] = off;
+            off += (size_t)sz * sizeof(uint4);
+        }
+        kd.cells.reserve(off, st);
+        PLS_CUDA(cudaMemsetAsync(kd.cells.p, 0, off, st));
+        for (int l = 0; l < KD_LEVELS; ++l) {
+            T.table[l] = reinterpret_cast<uint4*>(reinterpret_cast<char*>(kd.cells.p) + kd.table_offset[l]);
+            T.mask[l] = kd.table_mask[l];
+        }
+        kd_cells_kernel<<<grid_for(M, 256, 8 * kNumSMs), 256, 0, st>>>(sk, M, T, kd.grid_hdr.as<KdGridHeader>());
+        PLS_CHECK_LAUNCH();
+    }
     if (M > 1) {
         int* visit = kd.visit.as<int>();
         int4* ranges = reinterpret_cast<int4*>(reinterpret_cast<char*>(kd.visit.p) + (((size_t)M * sizeof(int) + 15) / 16) * 16);

@@ -27,16 +27,107 @@ struct BvhNode {
 };
 static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
 
+__device__ __forceinline__ float dist2_point(float x, float y, float z, const float4& p) {
+    float dx = x - p.x, dy = y - p.y, dz = z - p.z;
+    return dx * dx + dy * dy + dz * dz;
+}
+
+// Multi-level cell tables over the SAME Morton-sorted array: at level l a cell is the key prefix
+// key >> 3 (b0 + l) (cubic cell of side cell0 * 2^l metres) and owns a contiguous range of `sorted`.
+// Open-addressing hash tables (linear probing) map cell id -> [start, end].  A query probes the 27
+// cells around it (independent loads) and scans their ranges (contiguous float4 reads): memory-level
+// parallelism instead of the BVH's dependent node chain.  The result is exact whenever the k-th best
+// squared distance is below (cell - margin)^2, because every point that close lies inside the 27-block;
+// otherwise the next coarser level is tried and finally the BVH.
+constexpr int KD_LEVELS = 3;
+constexpr float KD_CELL_TARGET = 0.16f;   // level-0 cell side in [0.16, 0.32) m
+constexpr float KD_CELL_MARGIN = 2e-3f;   // quantisation slack, metres
+
+struct KdGridHeader {
+    float mn[3];
+    float scale;      // Morton units per metre
+    int b0;           // bits dropped per axis at level 0
+    float cell0;      // level-0 cell side, metres
+    int overflow[KD_LEVELS];
+};
+
 struct KdIndex {
     const float4* sorted;
     const float4* nodes;  // 4 float4 per node
     float4* normals;
     int M;
+    const KdGridHeader* grid;
+    const uint4* table[KD_LEVELS];  // {id+1 lo, id+1 hi, start, end}
+    uint32_t mask[KD_LEVELS];
 };
 
-__device__ __forceinline__ float dist2_point(float x, float y, float z, const float4& p) {
-    float dx = x - p.x, dy = y - p.y, dz = z - p.z;
-    return dx * dx + dy * dy + dz * dz;
+__device__ __forceinline__ uint64_t kd_spread3(uint64_t x) {
+    x &= 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+__device__ __forceinline__ uint32_t kd_hash(uint64_t id) {
+    uint64_t h = id * 0x9E3779B97F4A7C15ull;
+    return (uint32_t)(h >> 32);
+}
+
+// Looks up cell `id` at one level; returns false if the cell is empty.
+__device__ __forceinline__ bool kd_cell_lookup(const uint4* __restrict__ table, uint32_t mask, uint64_t id, int& start,
+                                               int& end) {
+    const uint32_t lo = (uint32_t)(id + 1), hi = (uint32_t)((id + 1) >> 32);
+    uint32_t h = kd_hash(id) & mask;
+    for (int probe = 0; probe < 64; ++probe) {
+        const uint4 e = __ldg(table + h);
+        if (e.x == lo && e.y == hi) {
+            start = (int)e.z;
+            end = (int)e.w;
+            return true;
+        }
+        if (e.x == 0u && e.y == 0u) return false;
+        h = (h + 1) & mask;
+    }
+    return false;
+}
+
+// Grid search of one level.  Calls visit(i, d2) for every point of the 27-block; returns the
+// squared exactness radius (cell - margin)^2 of that level, or -1 if the level is unusable.
+template <typename Visit>
+__device__ __forceinline__ float kd_grid_scan(const KdIndex& ix, int level, float x, float y, float z, Visit visit) {
+    const KdGridHeader* g = ix.grid;
+    if (g->overflow[level]) return -1.f;
+    const int b = g->b0 + level;
+    const float fx = (x - g->mn[0]) * g->scale, fy = (y - g->mn[1]) * g->scale, fz = (z - g->mn[2]) * g->scale;
+    // the same truncating quantisation as kd_morton_kernel for in-range points; floor for the rest
+    const int cx = ((int)floorf(fx)) >> b, cy = ((int)floorf(fy)) >> b, cz = ((int)floorf(fz)) >> b;
+    const int cmax = 65535 >> b;
+    const uint4* __restrict__ table = ix.table[level];
+    const uint32_t mask = ix.mask[level];
+#pragma unroll 1
+    for (int dz = -1; dz <= 1; ++dz) {
+        const int zz = cz + dz;
+        if (zz < 0 || zz > cmax) continue;
+        const uint64_t kz = kd_spread3((uint64_t)zz) << 2;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int yy = cy + dy;
+            if (yy < 0 || yy > cmax) continue;
+            const uint64_t kyz = kz | (kd_spread3((uint64_t)yy) << 1);
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int xx = cx + dx;
+                if (xx < 0 || xx > cmax) continue;
+                int s, e;
+                if (!kd_cell_lookup(table, mask, kyz | kd_spread3((uint64_t)xx), s, e)) continue;
+                for (int i = s; i <= e; ++i) visit(i, dist2_point(x, y, z, __ldg(ix.sorted + i)));
+            }
+        }
+    }
+    const float cell = g->cell0 * (float)(1 << level) - KD_CELL_MARGIN;
+    return cell > 0.f ? cell * cell : -1.f;
 }
 
 __device__ __forceinline__ float dist2_box(float x, float y, float z, float mnx, float mny, float mnz, float mxx,
@@ -113,6 +204,26 @@ __device__ __forceinline__ int kd_nearest(const KdIndex& ix, float x, float y, f
     }
     if (best_out) *best_out = best;
     return best_i;
+}
+
+// Exact 1-NN, grid first: levels 0..KD_LEVELS-1, then the BVH seeded with the best candidate so far.
+__device__ __forceinline__ int kd_nearest_fast(const KdIndex& ix, float x, float y, float z, int hint, int* used_bvh) {
+    float best = FLT_MAX;
+    int best_i = -1;
+    if (hint >= 0 && hint < ix.M) {
+        best = dist2_point(x, y, z, __ldg(ix.sorted + hint));
+        best_i = hint;
+    }
+    if (ix.M > KD_LEAF) {
+        for (int level = 0; level < KD_LEVELS; ++level) {
+            const float r2 = kd_grid_scan(ix, level, x, y, z, [&](int i, float d) {
+                if (d < best) { best = d; best_i = i; }
+            });
+            if (r2 > 0.f && best <= r2) return best_i;
+        }
+    }
+    if (used_bvh) *used_bvh = 1;
+    return kd_nearest(ix, x, y, z, best_i, nullptr);
 }
 
 // Sorted insertion into an ascending (d, i) list of capacity k.
@@ -240,7 +351,17 @@ __device__ __forceinline__ void kd_point_normal(const KdIndex& ix, int pos, int 
     const float4 c = __ldg(ix.sorted + pos);
     float d[KD_KMAX];
     int idx[KD_KMAX];
-    int found = kd_knn(ix, c.x, c.y, c.z, k + 1, d, idx);
+    int found = 0;
+    bool exact = false;
+    if (ix.M > KD_LEAF) {
+        for (int level = 0; level < KD_LEVELS && !exact; ++level) {
+            found = 0;
+            const float r2 = kd_grid_scan(ix, level, c.x, c.y, c.z,
+                                          [&](int i, float dd) { knn_insert(d, idx, k + 1, found, dd, i); });
+            exact = r2 > 0.f && found == k + 1 && d[k] <= r2;
+        }
+    }
+    if (!exact) found = kd_knn(ix, c.x, c.y, c.z, k + 1, d, idx);
     float sxx = 0.f, sxy = 0.f, sxz = 0.f, syy = 0.f, syz = 0.f, szz = 0.f;
     for (int j = 1; j < found; ++j) {  // entry 0 is the point itself (distance 0)
         const float4 q = __ldg(ix.sorted + idx[j]);
