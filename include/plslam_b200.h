@@ -162,6 +162,8 @@ PLS_API int pls_kdmap_update_points(pls_context* ctx, const float* rel_pose, con
 PLS_API int pls_kdmap_update_vertex_map(pls_context* ctx, const float* rel_pose, const float* vertex_map,
                                 int height, int width);
 PLS_API int pls_kdmap_size(pls_context* ctx, int64_t* num_points);
+/* Debug counters of the kd search (enabled by the environment variable PLS_KD_STATS=1), 16 u64. */
+PLS_API int pls_kdmap_stats(pls_context* ctx, unsigned long long* out16);
 PLS_API int pls_kdmap_points(pls_context* ctx, float* out /* [M,3], insertion order */);
 /* KdTreeLocalMap.nearest_neighbor_search (local_map.py:372-422): exact 1-NN; normals from
  * the 10 nearest map neighbours of the matched map point (smallest-eigenvalue direction),

@@ -47,6 +47,7 @@ _SIGNATURES = {
     "pls_kdmap_update_points": [_P, _P, _P, _L],
     "pls_kdmap_update_vertex_map": [_P, _P, _P, _I, _I],
     "pls_kdmap_size": [_P, C.POINTER(_L)],
+    "pls_kdmap_stats": [_P, _P],
     "pls_kdmap_points": [_P, _P],
     "pls_kdmap_nn_search": [_P, _P, _L, _P, _P, _P],
     "pls_projmap_update": [_P, _P, _P],

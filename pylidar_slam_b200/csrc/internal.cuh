@@ -105,6 +105,7 @@ struct KdMap {
     DBuf inv_order;         // sorted position of each stored point (for out_idx)
     DBuf grid_hdr;          // KdGridHeader (quantisation + cell levels)
     DBuf cells;             // cell hash tables of all levels
+    DBuf stats;             // optional debug counters (PLS_KD_STATS=1)
     size_t table_offset[4] = {0, 0, 0, 0};
     uint32_t table_mask[4] = {0, 0, 0, 0};
     int64_t indexed = 0;    // points covered by the index

@@ -13,6 +13,8 @@
 // Search (local_map.py:372-422): kd_search_kernel (fine-grained API) and kd_icp_iter_kernel
 // (one launch per ICP iteration: transform, exact 1-NN, lazy 10-NN normals, point-to-plane
 // residual/Jacobian/weight and the block-reduced normal equations).
+#include <stdlib.h>
+
 #include "gn_device.cuh"
 #include "internal.cuh"
 #include "kdmap_device.cuh"
@@ -378,6 +380,7 @@ KdIndex make_index(pls_context* ctx) {
         ix.table[l] = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(ctx->kd.cells.p) + ctx->kd.table_offset[l]);
         ix.mask[l] = ctx->kd.table_mask[l];
     }
+    ix.stats = ctx->kd.stats.p ? ctx->kd.stats.as<unsigned long long>() : nullptr;
     return ix;
 }
 
@@ -447,6 +450,10 @@ void build_index(pls_context* ctx) {
 }  // namespace
 
 void kdmap_reset(pls_context* ctx) {
+    if (getenv("PLS_KD_STATS") && !ctx->kd.stats.p) {
+        ctx->kd.stats.reserve(16 * sizeof(unsigned long long), ctx->stream);
+        cudaMemsetAsync(ctx->kd.stats.p, 0, 16 * sizeof(unsigned long long), ctx->stream);
+    }
     ctx->kd.count = 0;
     ctx->kd.cur = 0;
     ctx->kd.frame_counts.clear();
@@ -620,6 +627,17 @@ int pls_kdmap_update_vertex_map(pls_context* ctx, const float* rel_pose, const f
     const float* d = (const float*)to_device(ctx, vertex_map, (size_t)3 * height * width * sizeof(float), ctx->stage_in[0]);
     kdmap_update(ctx, rel, nullptr, 0, d, height, width, -1);
     PLS_CUDA(cudaStreamSynchronize(ctx->stream));
+    PLS_API_END(ctx)
+}
+
+int pls_kdmap_stats(pls_context* ctx, unsigned long long* out16) {
+    PLS_API_BEGIN(ctx)
+    PLS_REQUIRE(out16, "pls_kdmap_stats: null output");
+    memset(out16, 0, 16 * sizeof(unsigned long long));
+    if (ctx->kd.stats.p) {
+        PLS_CUDA(cudaMemcpyAsync(out16, ctx->kd.stats.p, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        PLS_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     PLS_API_END(ctx)
 }
 

@@ -39,7 +39,7 @@ __device__ __forceinline__ float dist2_point(float x, float y, float z, const fl
 // parallelism instead of the BVH's dependent node chain.  The result is exact whenever the k-th best
 // squared distance is below (cell - margin)^2, because every point that close lies inside the 27-block;
 // otherwise the next coarser level is tried and finally the BVH.
-constexpr int KD_LEVELS = 3;
+constexpr int KD_LEVELS = 1;
 constexpr float KD_CELL_TARGET = 0.16f;   // level-0 cell side in [0.16, 0.32) m
 constexpr float KD_CELL_MARGIN = 2e-3f;   // quantisation slack, metres
 
@@ -59,7 +59,13 @@ struct KdIndex {
     const KdGridHeader* grid;
     const uint4* table[KD_LEVELS];  // {id+1 lo, id+1 hi, start, end}
     uint32_t mask[KD_LEVELS];
+    unsigned long long* stats;      // optional debug counters (PLS_KD_STATS=1), else null
 };
+// stats slots: 0 nn queries, 1 nn exact@L0, 2 nn exact@L1, 3 nn exact@L2, 4 nn bvh, 5 nn candidates,
+//              6 knn queries, 7 knn exact@L0, 8 @L1, 9 @L2, 10 knn bvh, 11 knn candidates
+__device__ __forceinline__ void kd_stat(const KdIndex& ix, int slot, unsigned long long v = 1ull) {
+    if (ix.stats) atomicAdd(ix.stats + slot, v);
+}
 
 __device__ __forceinline__ uint64_t kd_spread3(uint64_t x) {
     x &= 0x1fffffull;
@@ -95,6 +101,7 @@ __device__ __forceinline__ bool kd_cell_lookup(const uint4* __restrict__ table, 
 
 // Grid search of one level.  Calls visit(i, d2) for every point of the 27-block; returns the
 // squared exactness radius (cell - margin)^2 of that level, or -1 if the level is unusable.
+// The nine probes of a z-slab are issued together (independent loads) before any range is scanned.
 template <typename Visit>
 __device__ __forceinline__ float kd_grid_scan(const KdIndex& ix, int level, float x, float y, float z, Visit visit) {
     const KdGridHeader* g = ix.grid;
@@ -106,24 +113,49 @@ __device__ __forceinline__ float kd_grid_scan(const KdIndex& ix, int level, floa
     const int cmax = 65535 >> b;
     const uint4* __restrict__ table = ix.table[level];
     const uint32_t mask = ix.mask[level];
+    uint64_t sx[3];
+    bool okx[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const int xx = cx + d - 1;
+        okx[d] = xx >= 0 && xx <= cmax;
+        sx[d] = okx[d] ? kd_spread3((uint64_t)xx) : 0ull;
+    }
 #pragma unroll 1
     for (int dz = -1; dz <= 1; ++dz) {
         const int zz = cz + dz;
         if (zz < 0 || zz > cmax) continue;
         const uint64_t kz = kd_spread3((uint64_t)zz) << 2;
+        uint64_t id[9];
+        uint32_t hh[9];
+        uint4 ent[9];
+        bool ok[9];
 #pragma unroll
-        for (int dy = -1; dy <= 1; ++dy) {
-            const int yy = cy + dy;
-            if (yy < 0 || yy > cmax) continue;
-            const uint64_t kyz = kz | (kd_spread3((uint64_t)yy) << 1);
+        for (int j = 0; j < 9; ++j) {
+            const int yy = cy + j / 3 - 1;
+            ok[j] = okx[j % 3] && yy >= 0 && yy <= cmax;
+            id[j] = kz | (kd_spread3((uint64_t)(ok[j] ? yy : 0)) << 1) | sx[j % 3];
+            hh[j] = kd_hash(id[j]) & mask;
+        }
 #pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-                const int xx = cx + dx;
-                if (xx < 0 || xx > cmax) continue;
-                int s, e;
-                if (!kd_cell_lookup(table, mask, kyz | kd_spread3((uint64_t)xx), s, e)) continue;
-                for (int i = s; i <= e; ++i) visit(i, dist2_point(x, y, z, __ldg(ix.sorted + i)));
+        for (int j = 0; j < 9; ++j) ent[j] = ok[j] ? __ldg(table + hh[j]) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            if (!ok[j]) continue;
+            const uint32_t lo = (uint32_t)(id[j] + 1), hi = (uint32_t)((id[j] + 1) >> 32);
+            uint4 e = ent[j];
+            bool hit = e.x == lo && e.y == hi;
+            if (!hit && (e.x | e.y) != 0u) {  // collision: keep probing
+                uint32_t h = hh[j];
+                for (int probe = 0; probe < 64 && !hit; ++probe) {
+                    h = (h + 1) & mask;
+                    e = __ldg(table + h);
+                    hit = e.x == lo && e.y == hi;
+                    if ((e.x | e.y) == 0u) break;
+                }
             }
+            if (hit)
+                for (int i = (int)e.z; i <= (int)e.w; ++i) visit(i, dist2_point(x, y, z, __ldg(ix.sorted + i)));
         }
     }
     const float cell = g->cell0 * (float)(1 << level) - KD_CELL_MARGIN;
@@ -214,22 +246,27 @@ __device__ __forceinline__ int kd_nearest_fast(const KdIndex& ix, float x, float
         best = dist2_point(x, y, z, __ldg(ix.sorted + hint));
         best_i = hint;
     }
+    kd_stat(ix, 0);
     if (ix.M > KD_LEAF) {
         for (int level = 0; level < KD_LEVELS; ++level) {
+            int cand = 0;
             const float r2 = kd_grid_scan(ix, level, x, y, z, [&](int i, float d) {
+                ++cand;
                 if (d < best) { best = d; best_i = i; }
             });
-            if (r2 > 0.f && best <= r2) return best_i;
+            kd_stat(ix, 5, cand);
+            if (r2 > 0.f && best <= r2) { kd_stat(ix, 1 + level); return best_i; }
         }
     }
+    kd_stat(ix, 4);
     if (used_bvh) *used_bvh = 1;
     return kd_nearest(ix, x, y, z, best_i, nullptr);
 }
 
 // Sorted insertion into an ascending (d, i) list of capacity k.
 __device__ __forceinline__ void knn_insert(float* d, int* idx, int k, int& count, float dn, int in) {
-    int pos = count < k ? count : k - 1;
     if (count == k && dn >= d[k - 1]) return;
+    int pos = count < k ? count : k - 1;
     while (pos > 0 && d[pos - 1] > dn) {
         d[pos] = d[pos - 1];
         idx[pos] = idx[pos - 1];
@@ -241,8 +278,9 @@ __device__ __forceinline__ void knn_insert(float* d, int* idx, int k, int& count
 }
 
 // Exact k-NN (k <= KD_KMAX): fills d[]/idx[] ascending, returns the number found (min(k, M)).
-__device__ __forceinline__ int kd_knn(const KdIndex& ix, float x, float y, float z, int k, float* d, int* idx) {
-    int count = 0;
+// `count` entries of d[]/idx[] may already hold candidates (seeds): they bound the search from the start.
+__device__ __forceinline__ int kd_knn(const KdIndex& ix, float x, float y, float z, int k, float* d, int* idx,
+                                      int count = 0) {
     if (ix.M <= KD_LEAF) {
         for (int i = 0; i < ix.M; ++i) knn_insert(d, idx, k, count, dist2_point(x, y, z, __ldg(ix.sorted + i)), i);
         return count;
@@ -297,6 +335,101 @@ __device__ __forceinline__ int kd_knn(const KdIndex& ix, float x, float y, float
     return count;
 }
 
+// Register-resident ascending list of the K best (distance, index) pairs: fully unrolled, branch-free
+// bubble insertion -- no local memory, no per-lane loops (the local-memory insertion sort ran with ~2.5
+// active lanes per instruction and dominated the first version of the correspondence kernel).
+template <int K>
+struct KBest {
+    float d[K];
+    int i[K];
+    __device__ __forceinline__ void reset() {
+#pragma unroll
+        for (int j = 0; j < K; ++j) { d[j] = FLT_MAX; i[j] = -1; }
+    }
+    __device__ __forceinline__ bool full() const { return i[K - 1] >= 0; }
+    // strict: a candidate equal to the current K-th distance does not displace it
+    __device__ __forceinline__ void insert(float dn, int in) {
+        if (dn < d[K - 1]) {
+            d[K - 1] = dn;
+            i[K - 1] = in;
+#pragma unroll
+            for (int j = K - 1; j > 0; --j) {
+                const bool sw = d[j] < d[j - 1];
+                const float td = sw ? d[j - 1] : d[j];
+                const int ti = sw ? i[j - 1] : i[j];
+                d[j - 1] = sw ? d[j] : d[j - 1];
+                i[j - 1] = sw ? i[j] : i[j - 1];
+                d[j] = td;
+                i[j] = ti;
+            }
+        }
+    }
+};
+
+// Exact K-NN over the BVH into a fresh list, pruned from the start by `bound2` (an upper bound of the
+// K-th squared distance, inclusive; FLT_MAX if none).  Every point is visited at most once.
+template <int K>
+__device__ __forceinline__ void kd_knn_bounded(const KdIndex& ix, float x, float y, float z, float bound2, KBest<K>& L) {
+    L.reset();
+    if (ix.M <= KD_LEAF) {
+        for (int i = 0; i < ix.M; ++i) L.insert(dist2_point(x, y, z, __ldg(ix.sorted + i)), i);
+        return;
+    }
+    // until the list is full, the bound (nudged up one ulp so that equality passes the strict tests) prunes
+    const float open_bound = bound2 < FLT_MAX ? __int_as_float(__float_as_int(bound2) + 1) : FLT_MAX;
+    int stack_n[KD_STACK];
+    float stack_d[KD_STACK];
+    int sp = 0;
+    int node = 0;
+    while (true) {
+        const float4 a = __ldg(ix.nodes + 4 * (size_t)node);
+        const float4 b = __ldg(ix.nodes + 4 * (size_t)node + 1);
+        const float4 c = __ldg(ix.nodes + 4 * (size_t)node + 2);
+        const float4 dd = __ldg(ix.nodes + 4 * (size_t)node + 3);
+        const int first = __float_as_int(dd.x), gamma = __float_as_int(dd.y), last = __float_as_int(dd.z);
+        const float dl = dist2_box(x, y, z, a.x, a.y, a.z, a.w, b.x, b.y);
+        const float dr = dist2_box(x, y, z, b.z, b.w, c.x, c.y, c.z, c.w);
+        const bool lleaf = (gamma - first + 1) <= KD_LEAF;
+        const bool rleaf = (last - gamma) <= KD_LEAF;
+        float worst = L.full() ? L.d[K - 1] : open_bound;
+        if (lleaf && dl < worst) {
+            for (int i = first; i <= gamma; ++i) {
+                const float dp = dist2_point(x, y, z, __ldg(ix.sorted + i));
+                if (dp < open_bound) L.insert(dp, i);
+            }
+            worst = L.full() ? L.d[K - 1] : open_bound;
+        }
+        if (rleaf && dr < worst) {
+            for (int i = gamma + 1; i <= last; ++i) {
+                const float dp = dist2_point(x, y, z, __ldg(ix.sorted + i));
+                if (dp < open_bound) L.insert(dp, i);
+            }
+            worst = L.full() ? L.d[K - 1] : open_bound;
+        }
+        const bool cl = !lleaf && dl < worst;
+        const bool cr = !rleaf && dr < worst;
+        if (cl && cr) {
+            if (dl <= dr) {
+                if (sp < KD_STACK) { stack_n[sp] = gamma + 1; stack_d[sp] = dr; ++sp; }
+                node = gamma;
+            } else {
+                if (sp < KD_STACK) { stack_n[sp] = gamma; stack_d[sp] = dl; ++sp; }
+                node = gamma + 1;
+            }
+            continue;
+        }
+        if (cl) { node = gamma; continue; }
+        if (cr) { node = gamma + 1; continue; }
+        bool found = false;
+        while (sp > 0) {
+            --sp;
+            const float w2 = L.full() ? L.d[K - 1] : open_bound;
+            if (stack_d[sp] < w2) { node = stack_n[sp]; found = true; break; }
+        }
+        if (!found) break;
+    }
+}
+
 // Eigenvector of the smallest eigenvalue of a symmetric 3x3 matrix (cyclic Jacobi, fp64).
 __device__ __forceinline__ void smallest_eigenvector(const float* c /*xx,xy,xz,yy,yz,zz*/, float* n) {
     double A[3][3] = {{c[0], c[1], c[2]}, {c[1], c[3], c[4]}, {c[2], c[4], c[5]}};
@@ -344,27 +477,15 @@ __device__ __forceinline__ void smallest_eigenvector(const float* c /*xx,xy,xz,y
     n[2] = (float)(nz * inv);
 }
 
-// Normal of map point `pos` (sorted position): the k nearest OTHER map points, second moments
-// about the point itself (not the mean), float32 sequential sums, smallest-eigenvalue direction
-// (slam/odometry/local_map.py:397-422).
-__device__ __forceinline__ void kd_point_normal(const KdIndex& ix, int pos, int k, float* n) {
-    const float4 c = __ldg(ix.sorted + pos);
-    float d[KD_KMAX];
-    int idx[KD_KMAX];
-    int found = 0;
-    bool exact = false;
-    if (ix.M > KD_LEAF) {
-        for (int level = 0; level < KD_LEVELS && !exact; ++level) {
-            found = 0;
-            const float r2 = kd_grid_scan(ix, level, c.x, c.y, c.z,
-                                          [&](int i, float dd) { knn_insert(d, idx, k + 1, found, dd, i); });
-            exact = r2 > 0.f && found == k + 1 && d[k] <= r2;
-        }
-    }
-    if (!exact) found = kd_knn(ix, c.x, c.y, c.z, k + 1, d, idx);
+// Second moments about the point itself of its k nearest OTHER map points (entry 0 of the (k+1)-NN list is
+// the point itself), float32 sequential sums in ascending-distance order, then the smallest-eigenvalue
+// direction (slam/odometry/local_map.py:397-422).
+template <typename GetIdx>
+__device__ __forceinline__ void kd_normal_from_neighbours(const KdIndex& ix, const float4& c, int k, int found,
+                                                          GetIdx get_idx, float* n) {
     float sxx = 0.f, sxy = 0.f, sxz = 0.f, syy = 0.f, syz = 0.f, szz = 0.f;
-    for (int j = 1; j < found; ++j) {  // entry 0 is the point itself (distance 0)
-        const float4 q = __ldg(ix.sorted + idx[j]);
+    for (int j = 1; j < found; ++j) {
+        const float4 q = __ldg(ix.sorted + get_idx(j));
         float dx = __fsub_rn(q.x, c.x), dy = __fsub_rn(q.y, c.y), dz = __fsub_rn(q.z, c.z);
         sxx = __fadd_rn(sxx, __fmul_rn(dx, dx));
         sxy = __fadd_rn(sxy, __fmul_rn(dx, dy));
@@ -377,6 +498,48 @@ __device__ __forceinline__ void kd_point_normal(const KdIndex& ix, int pos, int 
     float cov[6] = {__fdiv_rn(sxx, kk), __fdiv_rn(sxy, kk), __fdiv_rn(sxz, kk),
                     __fdiv_rn(syy, kk), __fdiv_rn(syz, kk), __fdiv_rn(szz, kk)};
     smallest_eigenvector(cov, n);
+}
+
+// Fast path for the default k = 10: grid block into a register list; if that is not provably exact, a fresh
+// BVH pass bounded by the grid's K-th distance.
+__device__ __forceinline__ void kd_point_normal_k10(const KdIndex& ix, int pos, float* n) {
+    constexpr int K = 11;
+    const float4 c = __ldg(ix.sorted + pos);
+    KBest<K> L;
+    L.reset();
+    bool exact = false;
+    kd_stat(ix, 6);
+    if (ix.M > KD_LEAF) {
+        const float r2 = kd_grid_scan(ix, 0, c.x, c.y, c.z, [&](int i, float dd) { L.insert(dd, i); });
+        exact = r2 > 0.f && L.full() && L.d[K - 1] <= r2;
+        if (exact) kd_stat(ix, 7);
+    }
+    if (!exact) {
+        kd_stat(ix, 10);
+        const float bound = L.full() ? L.d[K - 1] : FLT_MAX;
+        kd_knn_bounded<K>(ix, c.x, c.y, c.z, bound, L);
+    }
+    int found = 0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) found += (L.i[j] >= 0) ? 1 : 0;
+    // copy the indices out through a small switch-free accessor (keeps the list in registers)
+    int idx[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) idx[j] = L.i[j];
+    kd_normal_from_neighbours(ix, c, 10, found, [&](int j) { return idx[j]; }, n);
+}
+
+// Generic k (3..31): local-memory list over the BVH.
+__device__ __forceinline__ void kd_point_normal(const KdIndex& ix, int pos, int k, float* n) {
+    if (k == 10) {
+        kd_point_normal_k10(ix, pos, n);
+        return;
+    }
+    const float4 c = __ldg(ix.sorted + pos);
+    float d[KD_KMAX];
+    int idx[KD_KMAX];
+    const int found = kd_knn(ix, c.x, c.y, c.z, k + 1, d, idx);
+    kd_normal_from_neighbours(ix, c, k, found, [&](int j) { return idx[j]; }, n);
 }
 
 // Cached normal of map point `pos`; computes and publishes it on first use.  The 16-byte

@@ -32,3 +32,11 @@ for k in range(F):
             print(k, "S", s.shape[0], "iters", int(algo.last_info[0]), "queries", int(algo.last_info[2]), "map", int(algo.last_info[3]),
                   f"gs {1e3*tg[-1]:.3f} ms icp {1e3*ti[-1]:.3f} ms terr {np.abs(prev[:3,3]-gt[:3,3]).max():.4f}")
 print(f"steady-state (last 10): grid_sample {1e3*np.mean(tg[-10:]):.3f} ms, process_next_frame {1e3*np.mean(ti[-10:]):.3f} ms")
+
+import ctypes
+st = (ctypes.c_ulonglong * 16)()
+algo.ctx.call("pls_kdmap_stats", st)
+st = list(st)
+if st[0]:
+    print(f"nn: {st[0]} queries, exact L0/L1/L2 = {st[1]/st[0]:.3f}/{st[2]/st[0]:.3f}/{st[3]/st[0]:.3f}, bvh {st[4]/st[0]:.4f}, cand/query {st[5]/st[0]:.1f}")
+    print(f"knn: {st[6]} queries, exact L0/L1/L2 = {st[7]/max(st[6],1):.3f}/{st[8]/max(st[6],1):.3f}/{st[9]/max(st[6],1):.3f}, bvh {st[10]/max(st[6],1):.4f}, cand/query {st[11]/max(st[6],1):.1f}")
