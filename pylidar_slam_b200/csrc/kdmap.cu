@@ -18,6 +18,7 @@
 #include "gn_device.cuh"
 #include "internal.cuh"
 #include "kdmap_device.cuh"
+#include "kdmap_warp.cuh"
 #include "pose_device.cuh"
 
 namespace pls {
@@ -369,6 +370,86 @@ __global__ void kd_export_kernel(const float4* __restrict__ pts, int64_t n, floa
     }
 }
 
+constexpr int KD_WARP_THREADS = 256;
+
+// One ICP iteration on the kd map, ONE WARP PER QUERY (see kdmap_warp.cuh): transform, exact 1-NN, lazily
+// cached 10-NN normal, point-to-plane residual / J = [n, p x n] / robust weight.  The 30 normal-equation
+// accumulators are distributed over the lanes (lane a owns accumulator a: its term is v[ia] * v[ib] with
+// v = (wJ_0..5, w r, r, 1)), so the epilogue is one shared-memory pass instead of 30 shuffle trees.
+__global__ void __launch_bounds__(KD_WARP_THREADS)
+kd_icp_warp_kernel(KdIndex ix, const float4* __restrict__ queries, const uint32_t* __restrict__ nq_dev, int64_t q_begin,
+                   int64_t q_stride, const FrameResult* __restrict__ fr, int scheme, float sigma,
+                   int* __restrict__ nn_prev, double* __restrict__ partials) {
+    if (fr->done) return;
+    __shared__ float sT[12];
+    __shared__ double red[KD_WARP_THREADS / 32][32];
+    if (threadIdx.x < 12) sT[threadIdx.x] = fr->T[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // operand selectors of this lane's accumulator
+    int ia = 8, ib = 8;
+    if (lane < 21) {
+        int k = 0;
+        for (int a = 0; a < 6; ++a)
+            for (int b = a; b < 6; ++b) {
+                if (k == lane) { ia = a; ib = b; }
+                ++k;
+            }
+    } else if (lane < 27) {
+        ia = lane - 21; ib = 6;
+    } else if (lane == 27) {
+        ia = 6; ib = 6;
+    } else if (lane == 28) {
+        ia = 7; ib = 7;
+    }
+    const int64_t nq = (int64_t)*nq_dev;
+    double acc = 0.0;
+    const int64_t warps_total = (int64_t)gridDim.x * (KD_WARP_THREADS / 32);
+    for (int64_t s = (int64_t)blockIdx.x * (KD_WARP_THREADS / 32) + warp;; s += warps_total) {
+        const int64_t qi = q_begin + s * q_stride;
+        if (qi >= nq) break;
+        const float4 p0 = queries[qi];
+        float p[3];
+        p[0] = p0.x * sT[0] + p0.y * sT[1] + p0.z * sT[2] + sT[3];
+        p[1] = p0.x * sT[4] + p0.y * sT[5] + p0.z * sT[6] + sT[7];
+        p[2] = p0.x * sT[8] + p0.y * sT[9] + p0.z * sT[10] + sT[11];
+        const int pos = warp_nearest(ix, p[0], p[1], p[2], nn_prev[qi]);
+        if (lane == 0) nn_prev[qi] = pos;
+        const float4 qq = __ldg(ix.sorted + pos);
+        float q[3] = {qq.x, qq.y, qq.z};
+        float nn[3];
+        const float4 cached = __ldcg(ix.normals + pos);
+        if (cached.w == 0.f) {
+            warp_point_normal_k10(ix, pos, nn);
+            if (lane == 0) __stcg(ix.normals + pos, make_float4(nn[0], nn[1], nn[2], 1.f));
+        } else {
+            nn[0] = cached.x; nn[1] = cached.y; nn[2] = cached.z;
+        }
+        float J[6];
+        const float r = p2plane_residual_jacobian_identity(p, q, nn, J);
+        const float w = ls_weight<float>(scheme, sigma, r, p, q);
+        const float wr = r * w;
+        // v_m lives in lane m (m < 9); the lane's term is v[ia] * v[ib]
+        double v = 1.0;
+#pragma unroll
+        for (int m = 0; m < 6; ++m)
+            if (lane == m) v = (double)(J[m] * w);
+        if (lane == 6) v = (double)wr;
+        if (lane == 7) v = (double)r;
+        const double va = __shfl_sync(FULL, v, ia);
+        const double vb = __shfl_sync(FULL, v, ib);
+        acc += va * vb;
+    }
+    red[warp][lane] = acc;
+    __syncthreads();
+    if (threadIdx.x < NACC) {
+        double sum = 0.0;
+#pragma unroll
+        for (int wq = 0; wq < KD_WARP_THREADS / 32; ++wq) sum += red[wq][threadIdx.x];
+        partials[(size_t)blockIdx.x * NACC + threadIdx.x] = sum;
+    }
+}
+
 KdIndex make_index(pls_context* ctx) {
     KdIndex ix;
     ix.sorted = ctx->kd.sorted.as<float4>();
@@ -585,15 +666,24 @@ void kdmap_update(pls_context* ctx, const float* rel_pose_host, const float* pts
 int kdmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int num_ranks) {
     PLS_REQUIRE(ctx->kd.valid, "kd map: search before any update");
     const int64_t mine = (query_bound + num_ranks - 1) / num_ranks;
-    const int blocks = grid_for(mine, KD_ITER_THREADS, 8 * kNumSMs);
-    ctx->partials.reserve((size_t)blocks * NACC * sizeof(double), ctx->stream);
+    const uint32_t* nq_dev = reinterpret_cast<const uint32_t*>(&frame_result_dev(ctx)->counts[1]);
     // credited per executed iteration by the caller (the launch is a no-op once ICP converged)
     ProfileScope ps(ctx, 0, 0.0, false);
+    if (ctx->cfg.num_neighbors_normals == 10) {
+        const int wpb = KD_WARP_THREADS / 32;
+        const int blocks = grid_for(mine, wpb, 8 * kNumSMs);
+        ctx->partials.reserve((size_t)blocks * NACC * sizeof(double), ctx->stream);
+        kd_icp_warp_kernel<<<blocks, KD_WARP_THREADS, 0, ctx->stream>>>(
+            make_index(ctx), ctx->query_ptr, nq_dev, (int64_t)rank, (int64_t)num_ranks, frame_result_dev(ctx),
+            ctx->cfg.scheme, ctx->cfg.sigma, ctx->nn_prev.as<int>(), ctx->partials.as<double>());
+        PLS_CHECK_LAUNCH();
+        return blocks;
+    }
+    const int blocks = grid_for(mine, KD_ITER_THREADS, 8 * kNumSMs);
+    ctx->partials.reserve((size_t)blocks * NACC * sizeof(double), ctx->stream);
     kd_icp_iter_kernel<<<blocks, KD_ITER_THREADS, 0, ctx->stream>>>(
-        make_index(ctx), ctx->cfg.num_neighbors_normals, ctx->query_ptr,
-        reinterpret_cast<const uint32_t*>(&frame_result_dev(ctx)->counts[1]),
-        (int64_t)rank, (int64_t)num_ranks, frame_result_dev(ctx), ctx->cfg.scheme, ctx->cfg.sigma,
-        ctx->nn_prev.as<int>(), ctx->partials.as<double>());
+        make_index(ctx), ctx->cfg.num_neighbors_normals, ctx->query_ptr, nq_dev, (int64_t)rank, (int64_t)num_ranks,
+        frame_result_dev(ctx), ctx->cfg.scheme, ctx->cfg.sigma, ctx->nn_prev.as<int>(), ctx->partials.as<double>());
     PLS_CHECK_LAUNCH();
     return blocks;
 }
