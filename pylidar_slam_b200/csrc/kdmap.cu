@@ -127,7 +127,7 @@ __device__ __forceinline__ uint64_t spread3(uint64_t x) {
 // Quantisation of the map: 256 Morton units per metre (3.9 mm) when the map extent allows it (<= 255 m),
 // else the 16-bit range is stretched over the extent.  Level-0 cells are 2^b0 units with a side in
 // [KD_CELL_TARGET, 2 KD_CELL_TARGET).
-__global__ void kd_grid_header_kernel(const int* __restrict__ bbox, KdGridHeader* __restrict__ hdr) {
+__global__ void kd_grid_header_kernel(const int* __restrict__ bbox, KdGridHeader* __restrict__ hdr, float cell_target) {
     if (threadIdx.x != 0) return;
     const float mnx = ordered_to_float(bbox[0]), mny = ordered_to_float(bbox[1]), mnz = ordered_to_float(bbox[2]);
     const float ex = ordered_to_float(bbox[3]) - mnx, ey = ordered_to_float(bbox[4]) - mny,
@@ -135,7 +135,7 @@ __global__ void kd_grid_header_kernel(const int* __restrict__ bbox, KdGridHeader
     const float ext = fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-6f));
     const float scale = fminf(256.0f, 65535.0f / ext);
     int b0 = 0;
-    while (b0 < 12 && (float)(1 << b0) < KD_CELL_TARGET * scale) ++b0;
+    while (b0 < 12 && (float)(1 << b0) < cell_target * scale) ++b0;
     hdr->mn[0] = mnx; hdr->mn[1] = mny; hdr->mn[2] = mnz;
     hdr->scale = scale;
     hdr->b0 = b0;
@@ -485,7 +485,8 @@ void build_index(pls_context* ctx) {
     kd.visit.reserve((size_t)M * sizeof(int) + (size_t)M * sizeof(int4), st);
     PLS_CUDA(cudaMemsetAsync(kd.normals.p, 0, (size_t)M * sizeof(float4), st));
     kd.grid_hdr.reserve(sizeof(KdGridHeader), st);
-    kd_grid_header_kernel<<<1, 32, 0, st>>>(kd.bbox.as<int>(), kd.grid_hdr.as<KdGridHeader>());
+    static const float cell_target = getenv("PLS_KD_CELL") ? (float)atof(getenv("PLS_KD_CELL")) : KD_CELL_TARGET;
+    kd_grid_header_kernel<<<1, 32, 0, st>>>(kd.bbox.as<int>(), kd.grid_hdr.as<KdGridHeader>(), cell_target);
     PLS_CHECK_LAUNCH();
     kd_morton_kernel<<<grid_for(M, 256, 8 * kNumSMs), 256, 0, st>>>(pts, M, kd.grid_hdr.as<KdGridHeader>(),
                                                                      kd.morton.as<uint64_t>(), kd.order.as<uint32_t>());
@@ -669,7 +670,8 @@ int kdmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int num
     const uint32_t* nq_dev = reinterpret_cast<const uint32_t*>(&frame_result_dev(ctx)->counts[1]);
     // credited per executed iteration by the caller (the launch is a no-op once ICP converged)
     ProfileScope ps(ctx, 0, 0.0, false);
-    if (ctx->cfg.num_neighbors_normals == 10) {
+    static const bool use_warp = getenv("PLS_KD_WARP") != nullptr;
+    if (use_warp && ctx->cfg.num_neighbors_normals == 10) {
         const int wpb = KD_WARP_THREADS / 32;
         const int blocks = grid_for(mine, wpb, 8 * kNumSMs);
         ctx->partials.reserve((size_t)blocks * NACC * sizeof(double), ctx->stream);

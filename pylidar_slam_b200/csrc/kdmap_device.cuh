@@ -40,7 +40,7 @@ __device__ __forceinline__ float dist2_point(float x, float y, float z, const fl
 // squared distance is below (cell - margin)^2, because every point that close lies inside the 27-block;
 // otherwise the next coarser level is tried and finally the BVH.
 constexpr int KD_LEVELS = 1;
-constexpr float KD_CELL_TARGET = 0.16f;   // level-0 cell side in [0.16, 0.32) m
+constexpr float KD_CELL_TARGET = 0.16f;   // default level-0 cell side in [0.16, 0.32) m (PLS_KD_CELL overrides)
 constexpr float KD_CELL_MARGIN = 2e-3f;   // quantisation slack, metres
 
 struct KdGridHeader {
@@ -99,9 +99,11 @@ __device__ __forceinline__ bool kd_cell_lookup(const uint4* __restrict__ table, 
     return false;
 }
 
-// Grid search of one level.  Calls visit(i, d2) for every point of the 27-block; returns the
-// squared exactness radius (cell - margin)^2 of that level, or -1 if the level is unusable.
-// The nine probes of a z-slab are issued together (independent loads) before any range is scanned.
+// Grid search of one level.  Calls visit(i, d2) for every point of the 27-block; returns the squared
+// exactness radius (cell - margin)^2 of that level, or -1 if the level is unusable.
+// Phase 1 probes the 27 cells (nine independent table loads per z-slab) and records the non-empty ranges;
+// phase 2 walks the lane's ranges in ONE flattened loop, so a warp runs max_lane(sum of counts)
+// iterations instead of sum_cells(max_lane(count)) -- the nested form diverged ~7x.
 template <typename Visit>
 __device__ __forceinline__ float kd_grid_scan(const KdIndex& ix, int level, float x, float y, float z, Visit visit) {
     const KdGridHeader* g = ix.grid;
@@ -121,6 +123,8 @@ __device__ __forceinline__ float kd_grid_scan(const KdIndex& ix, int level, floa
         okx[d] = xx >= 0 && xx <= cmax;
         sx[d] = okx[d] ? kd_spread3((uint64_t)xx) : 0ull;
     }
+    int rs[27], re[27];
+    int nr = 0;
 #pragma unroll 1
     for (int dz = -1; dz <= 1; ++dz) {
         const int zz = cz + dz;
@@ -154,9 +158,24 @@ __device__ __forceinline__ float kd_grid_scan(const KdIndex& ix, int level, floa
                     if ((e.x | e.y) == 0u) break;
                 }
             }
-            if (hit)
-                for (int i = (int)e.z; i <= (int)e.w; ++i) visit(i, dist2_point(x, y, z, __ldg(ix.sorted + i)));
+            if (hit) {
+                rs[nr] = (int)e.z;
+                re[nr] = (int)e.w;
+                ++nr;
+            }
         }
+    }
+    int j = 0, i = 0, end = -1;
+    while (true) {
+        if (i > end) {
+            if (j == nr) break;
+            i = rs[j];
+            end = re[j];
+            ++j;
+            continue;
+        }
+        visit(i, dist2_point(x, y, z, __ldg(ix.sorted + i)));
+        ++i;
     }
     const float cell = g->cell0 * (float)(1 << level) - KD_CELL_MARGIN;
     return cell > 0.f ? cell * cell : -1.f;
@@ -516,7 +535,16 @@ __device__ __forceinline__ void kd_point_normal_k10(const KdIndex& ix, int pos, 
     }
     if (!exact) {
         kd_stat(ix, 10);
-        const float bound = L.full() ? L.d[K - 1] : FLT_MAX;
+        float bound = L.full() ? L.d[K - 1] : FLT_MAX;
+        if (ix.M > 2 * K + 2) {
+            // the K-th smallest distance among the point's 2K+3 neighbours in Morton order (contiguous loads)
+            // is an upper bound of its K-NN radius: the BVH walk below starts pruned even in sparse regions
+            KBest<K> S;
+            S.reset();
+            const int lo = min(max(pos - (K + 1), 0), ix.M - (2 * K + 3));
+            for (int i = lo; i < lo + 2 * K + 3; ++i) S.insert(dist2_point(c.x, c.y, c.z, __ldg(ix.sorted + i)), i);
+            bound = fminf(bound, S.d[K - 1]);
+        }
         kd_knn_bounded<K>(ix, c.x, c.y, c.z, bound, L);
     }
     int found = 0;
