@@ -199,7 +199,11 @@ def b200_arm(args):
     dev_scans = torch.from_numpy(np.stack(scans)).to(dev)
     torch.cuda.synchronize(dev)
 
-    def device_pass(profile_slot=None):
+    def device_pass(profile_slot=None, flush_each_step=False):
+        """W warm-up frames, then exactly K timed frames inside ONE CUDA-event bracket on the library's
+        stream (the local-map update of frame k runs on the library's second stream and overlaps frame
+        k+1, so per-step brackets with untimed gaps would hide work; the bracket closes only after
+        pls_synchronize has drained both streams)."""
         algo = make_algo()
         ctx = algo.ctx
         pose = np.zeros((4, 4), np.float32)
@@ -208,32 +212,34 @@ def b200_arm(args):
         import ctypes as C
         has = C.c_int(0)
         prev = None
-        events, launches0, iters = [], 0, []
+        launches0, iters = 0, []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for k in range(n_frames):
             timed = k > W_
-            if timed and len(events) == 0:
+            if k == W_ + 1:
+                ctx.call("pls_synchronize")
+                flush_l2()
                 barrier()
                 launches0 = ctx.launch_count()
                 if profile_slot is not None:
                     ctx.call("pls_profile_enable", profile_slot, 1)
-            flush_l2()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            if timed:
                 e0.record(stream)
+            if timed and flush_each_step:
+                flush_l2()        # inside the bracket: counted
             ctx.call("pls_process_frame_grid_sample", dev_scans[k].data_ptr(), n_raw, VOXEL, _lib.INPUT_TENSOR,
                      _lib.ptr(prev), _lib.ptr(pose), _lib.ptr(params), C.byref(has), _lib.ptr(info))
             if timed:
-                e1.record(stream)
-                events.append((e0, e1))
                 iters.append(int(info[0]))
             if has.value:
                 prev = pose.copy()
+        ctx.call("pls_synchronize")
+        e1.record(stream)
         barrier()
         launches = ctx.launch_count() - launches0
-        ms = [a.elapsed_time(b) for a, b in events]
+        total_ms = e0.elapsed_time(e1)
         prof = ctx.profile(profile_slot) if profile_slot is not None else None
         stats = {"samples": int(info[4]), "queries": int(info[2]), "map_points": int(info[3]), "iters_mean": float(np.mean(iters))}
-        return ms, launches, prof, stats, ctx
+        return total_ms, launches, prof, stats, ctx
 
     clocks = ClockSampler(local_rank)
     clocks.start()
@@ -241,9 +247,10 @@ def b200_arm(args):
     clock_info = clocks.stop()
     if args.quick:
         if rank == 0:
-            print(json.dumps({"quick": True, "ms_per_step": float(np.mean(ms_dev)), "gpu_launches": launches, **stats}))
+            print(json.dumps({"quick": True, "ms_per_step": ms_dev / K_, "gpu_launches": launches, **stats}))
         return
-    # roofline pass: same frames with CUDA events around the correspondence kernel inside the library
+    ms_dev_flushed, _, _, _, _ = device_pass(flush_each_step=True)
+    # roofline passes: same frames with CUDA events around one kernel family inside the library
     _, _, prof_nn, _, _ = device_pass(profile_slot=0)
     _, _, prof_idx, _, _ = device_pass(profile_slot=3)
     _, _, prof_gs, _, _ = device_pass(profile_slot=4)
@@ -259,31 +266,30 @@ def b200_arm(args):
     for f in pre.filters:
         if hasattr(f, "ctx"):
             f.ctx = gs_ctx
-    prev, t_e2e, h2d, d2h = None, [], 0, 0
+    prev, h2d, d2h = None, 0, 0
+    t_start = 0.0
     for k in range(n_frames):
         timed = k > W_
-        if timed and not t_e2e:
+        if k == W_ + 1:
+            gs_ctx.call("pls_synchronize")
+            flush_l2()
             barrier()
-        flush_l2()
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
+            t_start = time.perf_counter()
         dd = {"numpy_pc": host_scans[k], "init_rpose": prev}
         pre.forward(dd)
         algo.process_next_frame(dd)
-        torch.cuda.synchronize(dev)
-        dt = time.perf_counter() - t0
         if "odometry_pose" in dd:
             prev = dd["odometry_pose"].astype(np.float64)
         if timed:
-            t_e2e.append(dt)
             S = dd["sample_points"].shape[0]
             h2d += host_scans[k].nbytes + S * 12 + 64
             d2h += S * 12 + S * 8 + 8 + 1400  # samples + indices + count + FrameResult
+    gs_ctx.call("pls_synchronize")
+    t_e = time.perf_counter() - t_start
     barrier()
 
     # ---------------- aggregate over ranks (max of the per-rank time)
-    t_dev = float(np.sum(ms_dev)) / 1e3
-    t_e = float(np.sum(t_e2e))
+    t_dev = ms_dev / 1e3
     if world > 1:
         t = torch.tensor([t_dev, t_e], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -296,13 +302,16 @@ def b200_arm(args):
     peak, peak_src = measured_peaks()
     nn_ms, nn_launches, nn_bytes = prof_nn
     achieved = (nn_bytes / max(nn_launches, 1)) / (nn_ms / max(nn_launches, 1) * 1e-3) / 1e9 if nn_ms > 0 else 0.0
-    frame_ms = float(np.mean(ms_dev))
+    frame_ms = ms_dev / K_
     line = {
         "metric": "icp_odometry_frames_per_sec", "value": K_ / t_dev, "unit": "frames/s", "n_gpus": world,
         "steps": K_, "warmup": W_, "ms_per_step": 1e3 * t_dev / K_, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "height": H, "width": W, "voxel": VOXEL,
-                   "l2": "flushed between frames (256 MiB memset, untimed); every step is a new scan",
+                   "l2": "L2 flushed once before the timed bracket; every step streams a NEW 1.5 MB scan from HBM while the "
+                         "62 MB local map legitimately stays L2-resident across frames (production behaviour); "
+                         "value_l2_flushed_every_step re-measures with a 256 MiB flush INSIDE the bracket before every frame",
+                   "value_l2_flushed_every_step": K_ / (ms_dev_flushed / 1e3),
                    "parallelism": "1 GPU" if world == 1 else f"queries sharded over {world} GPUs, map replicated, "
                                                              f"one 30-double allreduce per ICP iteration",
                    **stats},

@@ -1,4 +1,6 @@
 // Context lifetime, host<->device argument staging, profiling slots.
+#include <utility>
+
 #include "internal.cuh"
 
 namespace pls {
@@ -36,6 +38,31 @@ void HBuf::release() {
     if (p) cudaFreeHost(p);
     p = nullptr;
     cap = 0;
+}
+
+void map_stream_begin(pls_context* ctx) {
+    ctx->stream = ctx->stream_map;
+    std::swap(ctx->sort, ctx->sort_map);
+}
+
+void map_stream_end(pls_context* ctx) {
+    cudaEventRecord(ctx->ev_map_done, ctx->stream_map);
+    ctx->map_pending = true;
+    std::swap(ctx->sort, ctx->sort_map);
+    ctx->stream = ctx->stream_main;
+}
+
+void map_stream_wait(pls_context* ctx) {
+    if (ctx->map_pending) {
+        cudaStreamWaitEvent(ctx->stream_main, ctx->ev_map_done, 0);
+        ctx->map_pending = false;
+    }
+}
+
+void sync_all(pls_context* ctx) {
+    PLS_CUDA(cudaStreamSynchronize(ctx->stream_map));
+    PLS_CUDA(cudaStreamSynchronize(ctx->stream_main));
+    ctx->map_pending = false;
 }
 
 bool is_device_ptr(const void* p) {
@@ -81,7 +108,8 @@ ProfileScope::ProfileScope(pls_context* c, int w, double bytes, bool count) : ct
     ProfileSlot& s = ctx->prof[which];
     if (!s.enabled) return;
     if (s.used >= 4096) {
-        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->stream_map);
+        cudaStreamSynchronize(ctx->stream_main);
         profile_collect(ctx, which);
     }
     if (s.used + 2 > s.pool.size()) {
@@ -175,6 +203,9 @@ int pls_create(const pls_config* cfg, pls_context** out) {
             PLS_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
             ctx->own_stream = true;
         }
+        ctx->stream_main = ctx->stream;
+        PLS_CUDA(cudaStreamCreateWithFlags(&ctx->stream_map, cudaStreamNonBlocking));
+        PLS_CUDA(cudaEventCreateWithFlags(&ctx->ev_map_done, cudaEventDisableTiming));
         ctx->pinned.reserve(sizeof(FrameResult) + 256);
         ctx->scalars.reserve(sizeof(FrameResult) + 4096, ctx->stream);
         PLS_CUDA(cudaMemsetAsync(ctx->scalars.p, 0, ctx->scalars.cap, ctx->stream));
@@ -191,7 +222,8 @@ int pls_create(const pls_config* cfg, pls_context** out) {
 int pls_destroy(pls_context* ctx) {
     if (!ctx) return PLS_E_INVALID;
     cudaSetDevice(ctx->cfg.device);
-    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->stream_map);
+    cudaStreamSynchronize(ctx->stream_main);
     comm_free(ctx);
     for (auto& b : ctx->stage_in) b.release();
     for (auto& b : ctx->stage_out) b.release();
@@ -200,6 +232,8 @@ int pls_destroy(pls_context* ctx) {
     ctx->scalars.release();
     ctx->sort.keys_alt.release(); ctx->sort.vals_alt.release(); ctx->sort.hist.release();
     ctx->sort.status.release(); ctx->sort.plan.release();
+    ctx->sort_map.keys_alt.release(); ctx->sort_map.vals_alt.release(); ctx->sort_map.hist.release();
+    ctx->sort_map.status.release(); ctx->sort_map.plan.release();
     ctx->scan.status.release();
     for (auto& b : ctx->kd.store) b.release();
     ctx->kd.morton.release(); ctx->kd.order.release(); ctx->kd.sorted.release(); ctx->kd.normals.release();
@@ -207,12 +241,16 @@ int pls_destroy(pls_context* ctx) {
     ctx->kd.inv_order.release(); ctx->kd.grid_hdr.release(); ctx->kd.cells.release();
     ctx->pm.vmaps.release(); ctx->pm.nmaps.release(); ctx->pm.poses.release();
     ctx->pm.model_v.release(); ctx->pm.model_n.release(); ctx->pm.zbuf.release();
-    ctx->frame_vmap.release(); ctx->frame_pts.release(); ctx->queries.release(); ctx->nn_prev.release();
+    for (auto& b : ctx->frame_vmap_buf) b.release();
+    for (auto& b : ctx->frame_pts_buf) b.release();
+    ctx->queries.release(); ctx->nn_prev.release();
     ctx->partials.release(); ctx->gs_keys.release(); ctx->gs_vals.release(); ctx->gs_out_xyz.release();
     ctx->gs_out_idx.release();
     for (auto& s : ctx->prof)
         for (auto e : s.pool) cudaEventDestroy(e);
-    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->ev_map_done) cudaEventDestroy(ctx->ev_map_done);
+    if (ctx->stream_map) cudaStreamDestroy(ctx->stream_map);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream_main);
     delete ctx;
     return PLS_OK;
 }
@@ -221,7 +259,7 @@ const char* pls_last_error(pls_context* ctx) { return ctx ? ctx->err.c_str() : "
 
 int pls_synchronize(pls_context* ctx) {
     PLS_API_BEGIN(ctx)
-    PLS_CUDA(cudaStreamSynchronize(ctx->stream));
+    sync_all(ctx);
     PLS_API_END(ctx)
 }
 
@@ -235,7 +273,7 @@ int pls_profile_enable(pls_context* ctx, int which, int enable) {
 int pls_profile_read(pls_context* ctx, int which, double* ms_total, int64_t* launches, double* bytes, int reset) {
     PLS_API_BEGIN(ctx)
     PLS_REQUIRE(which >= 0 && which < kProfileSlots, "pls_profile_read: bad slot");
-    PLS_CUDA(cudaStreamSynchronize(ctx->stream));
+    sync_all(ctx);
     profile_collect(ctx, which);
     ProfileSlot& s = ctx->prof[which];
     if (ms_total) *ms_total = s.ms;

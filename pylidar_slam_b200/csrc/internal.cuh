@@ -144,7 +144,11 @@ static_assert(sizeof(FrameResult) <= kScalarOffset, "FrameResult must fit before
 
 struct pls_context {
     pls_config cfg;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // the stream kernels are currently enqueued on
+    cudaStream_t stream_main = nullptr; // caller-visible stream (== stream outside a map-update scope)
+    cudaStream_t stream_map = nullptr;  // local-map update stream (overlaps the next frame's preprocessing)
+    cudaEvent_t ev_map_done = nullptr;  // recorded on stream_map after every asynchronous map update
+    bool map_pending = false;
     bool own_stream = false;
     std::string err;
 
@@ -154,6 +158,7 @@ struct pls_context {
     pls::DBuf scalars;      // device scalars (counts, flags, FrameResult)
 
     pls::SortScratch sort;
+    pls::SortScratch sort_map;          // radix-sort scratch of the map-update stream
     pls::ScanScratch scan;
 
     // generic scratch
@@ -165,8 +170,9 @@ struct pls_context {
     int frame_index = 0;
     int sample_pointcloud = 0;          // _sample_pointcloud
     float delta_since_update[16];       // _delta_since_map_update
-    pls::DBuf frame_vmap;               // [3][H][W] of the current frame
-    pls::DBuf frame_pts;                // float4 packed valid points of the current frame
+    pls::DBuf frame_vmap_buf[2];        // [3][H][W] of the current frame (double-buffered: the previous one may
+    pls::DBuf frame_pts_buf[2];         // still be read by the map-update stream); float4 packed valid points
+    int frame_slot = 0;
     pls::DBuf queries;                  // float4 queries P0 (owned storage)
     const float4* query_ptr = nullptr;  // the queries of the current frame (may alias frame_pts)
     pls::DBuf nn_prev;                  // previous-iteration match per query
@@ -220,6 +226,14 @@ inline uint32_t* scalar_u32(pls_context* ctx, int i) {
 }
 inline FrameResult* frame_result_dev(pls_context* ctx) { return reinterpret_cast<FrameResult*>(ctx->scalars.p); }
 inline FrameResult* frame_result_host(pls_context* ctx) { return reinterpret_cast<FrameResult*>(ctx->pinned.p); }
+
+// The asynchronous map-update scope: kernels enqueued inside run on stream_map with its own sort scratch.
+void map_stream_begin(pls_context* ctx);
+void map_stream_end(pls_context* ctx);
+// Makes the main stream wait for the last asynchronous map update (no-op if none is pending).
+void map_stream_wait(pls_context* ctx);
+// Host-blocking: both streams idle.
+void sync_all(pls_context* ctx);
 
 // ---- profiling ------------------------------------------------------------------------------
 struct ProfileScope {

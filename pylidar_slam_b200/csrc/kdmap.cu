@@ -698,6 +698,7 @@ extern "C" {
 
 int pls_kdmap_update_points(pls_context* ctx, const float* rel_pose, const float* points, int64_t n) {
     PLS_API_BEGIN(ctx)
+    map_stream_wait(ctx);
     PLS_REQUIRE(rel_pose, "pls_kdmap_update_points: rel_pose required");
     PLS_REQUIRE(ctx->cfg.local_map_type == PLS_MAP_KDTREE, "context holds a projective map");
     float rel[16];
@@ -711,6 +712,7 @@ int pls_kdmap_update_points(pls_context* ctx, const float* rel_pose, const float
 
 int pls_kdmap_update_vertex_map(pls_context* ctx, const float* rel_pose, const float* vertex_map, int height, int width) {
     PLS_API_BEGIN(ctx)
+    map_stream_wait(ctx);
     PLS_REQUIRE(rel_pose && vertex_map && height > 0 && width > 0, "pls_kdmap_update_vertex_map: bad arguments");
     PLS_REQUIRE(ctx->cfg.local_map_type == PLS_MAP_KDTREE, "context holds a projective map");
     float rel[16];
@@ -742,6 +744,7 @@ int pls_kdmap_size(pls_context* ctx, int64_t* num_points) {
 
 int pls_kdmap_points(pls_context* ctx, float* out) {
     PLS_API_BEGIN(ctx)
+    map_stream_wait(ctx);
     PLS_REQUIRE(out, "pls_kdmap_points: null output");
     const int64_t M = ctx->kd.count;
     if (M > 0) {
@@ -758,6 +761,7 @@ int pls_kdmap_points(pls_context* ctx, float* out) {
 int pls_kdmap_nn_search(pls_context* ctx, const float* queries, int64_t n, float* out_neighbors, float* out_normals,
                         int64_t* out_idx) {
     PLS_API_BEGIN(ctx)
+    map_stream_wait(ctx);
     PLS_REQUIRE(queries && out_neighbors && n > 0, "pls_kdmap_nn_search: bad arguments");
     if (!ctx->kd.valid) throw pls::Error{PLS_E_STATE, "pls_kdmap_nn_search: the map is empty"};
     const float* d = (const float*)to_device(ctx, queries, (size_t)n * 3 * sizeof(float), ctx->stage_in[0]);

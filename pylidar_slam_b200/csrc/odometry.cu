@@ -214,31 +214,35 @@ void process_frame_device(pls_context* ctx, const float* data_dev, int layout, i
     PLS_CUDA(cudaMemsetAsync(fr->counts, 0, sizeof(fr->counts), st));
     if (layout == PLS_INPUT_NDARRAY) ctx->sample_pointcloud = 1;  // icp_odometry.py:330
     const bool first = ctx->frame_index == 0;
+    // the previous frame's buffers may still feed the asynchronous map update: use the other pair
+    ctx->frame_slot ^= 1;
+    DBuf& frame_vmap = ctx->frame_vmap_buf[ctx->frame_slot];
+    DBuf& frame_pts = ctx->frame_pts_buf[ctx->frame_slot];
 
     // ---- _read_input (icp_odometry.py:319-358)
-    ctx->frame_vmap.reserve((size_t)3 * hw * sizeof(float), st);
+    frame_vmap.reserve((size_t)3 * hw * sizeof(float), st);
     int64_t pts_bound = 0;
     if (layout == PLS_INPUT_VERTEX_MAP) {
-        scrub_vertex_map_kernel<<<grid_for(hw), 256, 0, st>>>(data_dev, hw, ctx->frame_vmap.as<float>());
+        scrub_vertex_map_kernel<<<grid_for(hw), 256, 0, st>>>(data_dev, hw, frame_vmap.as<float>());
         PLS_CHECK_LAUNCH();
         ctx->tmp[5].reserve((size_t)hw * sizeof(float4), st);
-        pack_nonnull_pixels(ctx, ctx->frame_vmap.as<float>(), hw, ctx->tmp[5].as<float4>(), count_slot(ctx, 1));
-        ctx->frame_pts.reserve(sizeof(float4) * 4, st);
-        first_point_kernel<<<1, 32, 0, st>>>(ctx->tmp[5].as<float4>(), count_slot(ctx, 1), ctx->frame_pts.as<float4>(),
+        pack_nonnull_pixels(ctx, frame_vmap.as<float>(), hw, ctx->tmp[5].as<float4>(), count_slot(ctx, 1));
+        frame_pts.reserve(sizeof(float4) * 4, st);
+        first_point_kernel<<<1, 32, 0, st>>>(ctx->tmp[5].as<float4>(), count_slot(ctx, 1), frame_pts.as<float4>(),
                                               count_slot(ctx, 2), fr);
         PLS_CHECK_LAUNCH();
         pts_bound = 1;
     } else {
         PLS_REQUIRE(n > 0, "process_frame: empty point cloud");
-        ctx->frame_pts.reserve((size_t)n * sizeof(float4), st);
-        pack_valid_rows(ctx, data_dev, n, ctx->frame_pts.as<float4>(), count_slot(ctx, 2));
+        frame_pts.reserve((size_t)n * sizeof(float4), st);
+        pack_valid_rows(ctx, data_dev, n, frame_pts.as<float4>(), count_slot(ctx, 2));
         pts_bound = n;
         // the vertex map of the points is needed on frame 0 (map initialisation), as the query
         // source when _sample_pointcloud is False, and by the projective map's update
         if (first || !ctx->sample_pointcloud || !kd) {
             ctx->tmp[3].reserve((size_t)hw * sizeof(unsigned long long), st);
             launch_projection(ctx, data_dev, nullptr, 1, n, 3, H, W, ctx->cfg.up_fov_deg, ctx->cfg.down_fov_deg,
-                              ctx->frame_vmap.as<float>(), ctx->tmp[3].as<unsigned long long>());
+                              frame_vmap.as<float>(), ctx->tmp[3].as<unsigned long long>());
             }
     }
 
@@ -247,8 +251,9 @@ void process_frame_device(pls_context* ctx, const float* data_dev, int layout, i
 
     if (first) {
         // icp_odometry.py:171-181: the first frame only initialises the map, via its vertex map
-        if (kd) kdmap_update(ctx, eye, nullptr, 0, ctx->frame_vmap.as<float>(), H, W, -1);
-        else projmap_update(ctx, eye, ctx->frame_vmap.as<float>());
+        map_stream_wait(ctx);
+        if (kd) kdmap_update(ctx, eye, nullptr, 0, frame_vmap.as<float>(), H, W, -1);
+        else projmap_update(ctx, eye, frame_vmap.as<float>());
         ctx->frame_index = 1;
         if (out_has_pose) *out_has_pose = 0;
         if (out_pose) memcpy(out_pose, eye, sizeof(eye));
@@ -267,7 +272,7 @@ void process_frame_device(pls_context* ctx, const float* data_dev, int layout, i
     int64_t query_bound;
     if (ctx->sample_pointcloud && layout != PLS_INPUT_VERTEX_MAP) {
         // queries = the (NaN-free) input points themselves
-        ctx->query_ptr = ctx->frame_pts.as<float4>();
+        ctx->query_ptr = frame_pts.as<float4>();
         PLS_CUDA(cudaMemcpyAsync(count_slot(ctx, 1), count_slot(ctx, 2), sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
         query_bound = n;
     } else if (layout == PLS_INPUT_VERTEX_MAP) {
@@ -275,7 +280,7 @@ void process_frame_device(pls_context* ctx, const float* data_dev, int layout, i
         query_bound = hw;
     } else {
         ctx->queries.reserve((size_t)hw * sizeof(float4), st);
-        pack_nonnull_pixels(ctx, ctx->frame_vmap.as<float>(), hw, ctx->queries.as<float4>(), count_slot(ctx, 1));
+        pack_nonnull_pixels(ctx, frame_vmap.as<float>(), hw, ctx->queries.as<float4>(), count_slot(ctx, 1));
         ctx->query_ptr = ctx->queries.as<float4>();
         query_bound = n < hw ? n : hw;
     }
@@ -287,20 +292,28 @@ void process_frame_device(pls_context* ctx, const float* data_dev, int layout, i
         PLS_CUDA(cudaMemcpyAsync(ctx->tmp[6].p, init_pose, 16 * sizeof(float), cudaMemcpyHostToDevice, st));
         T0_dev = ctx->tmp[6].as<float>();
     }
+    map_stream_wait(ctx);  // the ICP below reads the local map the previous frame's update is still building
     const int icp_blocks = run_icp(ctx, T0_dev, query_bound);
     fetch_result(ctx);
     FrameResult* h = frame_result_host(ctx);
     credit_icp_profile(ctx, h, icp_blocks);
     raise_status(ctx, h->status);
 
-    // ---- __update_map
+    // ---- __update_map: enqueued on the map stream, it overlaps the NEXT frame's preprocessing
     const bool insert = keyframe_decision(ctx, h->T);
-    if (kd) {
-        if (insert) kdmap_update_packed(ctx, h->T, ctx->frame_pts.as<float4>(), (int64_t)h->counts[2], true);
-        else kdmap_update_packed(ctx, h->T, nullptr, 0, false);
-    } else {
-        projmap_update(ctx, h->T, insert ? ctx->frame_vmap.as<float>() : nullptr);
+    map_stream_begin(ctx);
+    try {
+        if (kd) {
+            if (insert) kdmap_update_packed(ctx, h->T, frame_pts.as<float4>(), (int64_t)h->counts[2], true);
+            else kdmap_update_packed(ctx, h->T, nullptr, 0, false);
+        } else {
+            projmap_update(ctx, h->T, insert ? frame_vmap.as<float>() : nullptr);
+        }
+    } catch (...) {
+        map_stream_end(ctx);
+        throw;
     }
+    map_stream_end(ctx);
     ctx->frame_index += 1;
     if (out_pose) memcpy(out_pose, h->T, 16 * sizeof(float));
     if (out_params) memcpy(out_params, h->params, 6 * sizeof(float));
@@ -337,6 +350,7 @@ extern "C" {
 
 int pls_map_init(pls_context* ctx) {
     PLS_API_BEGIN(ctx)
+    sync_all(ctx);
     kdmap_reset(ctx);
     projmap_reset(ctx);
     PLS_API_END(ctx)
@@ -344,7 +358,7 @@ int pls_map_init(pls_context* ctx) {
 
 int pls_odometry_init(pls_context* ctx) {
     PLS_API_BEGIN(ctx)
-    PLS_CUDA(cudaStreamSynchronize(ctx->stream));
+    sync_all(ctx);
     odometry_reset(ctx);
     PLS_API_END(ctx)
 }
@@ -355,6 +369,7 @@ int pls_register_frame(pls_context* ctx, const float* points, int64_t n, const f
     PLS_REQUIRE(points && n > 0, "pls_register_frame: points must be [n,3] with n > 0");
     PLS_REQUIRE(ctx->cfg.gn_max_iters == 1, "fused ICP path supports gauss_newton_config.max_iters == 1");
     cudaStream_t st = ctx->stream;
+    map_stream_wait(ctx);
     const float* d = (const float*)to_device(ctx, points, (size_t)n * 3 * sizeof(float), ctx->stage_in[0]);
     FrameResult* fr = frame_result_dev(ctx);
     PLS_CUDA(cudaMemsetAsync(fr->counts, 0, sizeof(fr->counts), st));

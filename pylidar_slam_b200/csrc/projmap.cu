@@ -477,6 +477,7 @@ int pls_compute_neighbors(pls_context* ctx, const float* tgt, const float* ref, 
 
 int pls_projmap_update(pls_context* ctx, const float* rel_pose, const float* vertex_map) {
     PLS_API_BEGIN(ctx)
+    map_stream_wait(ctx);
     PLS_REQUIRE(rel_pose, "pls_projmap_update: rel_pose required");
     PLS_REQUIRE(ctx->cfg.local_map_type == PLS_MAP_PROJECTIVE, "context holds a kd map");
     float rel[16];
@@ -498,6 +499,7 @@ int pls_projmap_num_frames(pls_context* ctx, int* num_frames) {
 
 int pls_projmap_model(pls_context* ctx, float* out_vmap, float* out_nmap) {
     PLS_API_BEGIN(ctx)
+    map_stream_wait(ctx);
     PLS_REQUIRE(ctx->pm.valid, "pls_projmap_model: empty map");
     const size_t bytes = (size_t)ctx->pm.K * 3 * ctx->cfg.height * ctx->cfg.width * sizeof(float);
     auto put = [&](float* dst, const void* src) {
@@ -513,6 +515,7 @@ int pls_projmap_model(pls_context* ctx, float* out_vmap, float* out_nmap) {
 int pls_projmap_nn_search(pls_context* ctx, const float* queries, int64_t n, float* out_neighbors, float* out_normals,
                           float* out_targets, int64_t* out_count) {
     PLS_API_BEGIN(ctx)
+    map_stream_wait(ctx);
     PLS_REQUIRE(queries && out_neighbors && out_count && n > 0, "pls_projmap_nn_search: bad arguments");
     if (!ctx->pm.valid) throw pls::Error{PLS_E_STATE, "pls_projmap_nn_search: the map is empty"};
     cudaStream_t st = ctx->stream;
