@@ -521,9 +521,9 @@ void build_index(pls_context* ctx) {
         int* visit = kd.visit.as<int>();
         int4* ranges = reinterpret_cast<int4*>(reinterpret_cast<char*>(kd.visit.p) + (((size_t)M * sizeof(int) + 15) / 16) * 16);
         PLS_CUDA(cudaMemsetAsync(visit, 0, (size_t)M * sizeof(int), st));
-        kd_hierarchy_kernel<<<grid_for(M - 1, 128, 16 * kNumSMs), 128, 0, st>>>(sk, (int)M, ranges, kd.parent.as<int>());
+        kd_hierarchy_kernel<<<grid_for(M - 1, 128, 1 << 20), 128, 0, st>>>(sk, (int)M, ranges, kd.parent.as<int>());
         PLS_CHECK_LAUNCH();
-        kd_boxes_kernel<<<grid_for(2 * M, 128, 16 * kNumSMs), 128, 0, st>>>(kd.sorted.as<float4>(), (int)M, ranges,
+        kd_boxes_kernel<<<grid_for(2 * M, 128, 1 << 20), 128, 0, st>>>(kd.sorted.as<float4>(), (int)M, ranges,
                                                                         kd.parent.as<int>(), visit, kd.nodes.as<float4>());
         PLS_CHECK_LAUNCH();
     }

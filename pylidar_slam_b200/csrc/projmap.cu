@@ -13,6 +13,8 @@
 //                           plane residual / Jacobian / weight and the block-reduced normal equations.
 //                           Streams HW*12*(K+1) bytes per launch: the HBM-bound correspondence kernel.
 //   proj_pairs_kernel       the same association materialised per pixel for the fine-grained API
+#include <stdlib.h>
+
 #include "gn_device.cuh"
 #include "internal.cuh"
 #include "pose_device.cuh"
@@ -256,6 +258,129 @@ proj_icp_iter_kernel(const float* __restrict__ model_v, const float* __restrict_
     block_reduce_store<PJ_THREADS>(acc, partials + (size_t)blockIdx.x * NACC);
 }
 
+// ---- TMA-staged variant ---------------------------------------------------------------------------
+// Persistent CTAs (2 per SM); each loops over 128-pixel tiles.  For a tile, ONE thread issues K*3 bulk
+// async copies (cp.async.bulk, the TMA engine; 512 contiguous bytes per candidate plane) that land in a
+// [K*3][128] shared-memory stage and complete on that stage's mbarrier; 3 stages keep two tiles (up to
+// 60 KB per CTA) in flight while the third is consumed, with no registers tied up by outstanding loads.
+// The consumers (one thread per pixel) read conflict-free from shared memory.
+constexpr int PT_TILE = 128;
+constexpr int PT_STAGES = 3;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(PT_TILE)
+proj_icp_tma_kernel(const float* __restrict__ model_v, const float* __restrict__ model_n, int K, int64_t hw,
+                    const unsigned long long* __restrict__ zbuf, const float4* __restrict__ queries,
+                    const FrameResult* __restrict__ fr, int64_t tile_begin, int64_t tile_end, int scheme, float sigma,
+                    double* __restrict__ partials) {
+    if (fr->done) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[PT_STAGES];
+    __shared__ float sT[12];
+    float* stage_base = reinterpret_cast<float*>(smem_raw);
+    const int rows = K * 3;
+    const uint32_t stage_floats = (uint32_t)rows * PT_TILE;
+    const uint32_t stage_bytes = stage_floats * sizeof(float);
+    if (threadIdx.x < 12) sT[threadIdx.x] = fr->T[threadIdx.x];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < PT_STAGES; ++s) mbar_init(&full_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int64_t first_tile = tile_begin + blockIdx.x;
+    const int64_t stride = gridDim.x;
+    auto issue = [&](int64_t tile, int s) {  // thread 0 only
+        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+        float* dst = stage_base + (size_t)s * stage_floats;
+        const float* src = model_v + tile * PT_TILE;
+        for (int r = 0; r < rows; ++r) bulk_copy_g2s(dst + r * PT_TILE, src + (size_t)r * hw, PT_TILE * sizeof(float), &full_bar[s]);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < PT_STAGES; ++s) {
+            const int64_t t = first_tile + (int64_t)s * stride;
+            if (t < tile_end) issue(t, s);
+        }
+    }
+    double acc[NACC];
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
+    int it = 0;
+    for (int64_t tile = first_tile; tile < tile_end; tile += stride, ++it) {
+        const int s = it % PT_STAGES;
+        const uint32_t parity = (uint32_t)((it / PT_STAGES) & 1);
+        const int64_t pix = tile * PT_TILE + threadIdx.x;
+        // independent of the staged tile: fetch the pixel's surviving query while the copies are in flight
+        const unsigned long long key = zbuf[pix];
+        float p[3] = {0.f, 0.f, 0.f};
+        const bool has = key != ~0ull;
+        if (has) {
+            const float4 p0 = queries[(uint32_t)(key & 0xffffffffull)];
+            p[0] = p0.x * sT[0] + p0.y * sT[1] + p0.z * sT[2] + sT[3];
+            p[1] = p0.x * sT[4] + p0.y * sT[5] + p0.z * sT[6] + sT[7];
+            p[2] = p0.x * sT[8] + p0.y * sT[9] + p0.z * sT[10] + sT[11];
+        }
+        mbar_wait(&full_bar[s], parity);
+        if (has) {
+            const float* st = stage_base + (size_t)s * stage_floats + threadIdx.x;
+            float best = __int_as_float(0x7f800000);
+            int kbest = -1;
+            float q[3] = {0.f, 0.f, 0.f};
+#pragma unroll 4
+            for (int k = 0; k < K; ++k) {
+                const float x = st[(3 * k) * PT_TILE], y = st[(3 * k + 1) * PT_TILE], z = st[(3 * k + 2) * PT_TILE];
+                if (fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) > 0.f) {
+                    const float dx = p[0] - x, dy = p[1] - y, dz = p[2] - z;
+                    const float d = sqrtf(dx * dx + dy * dy + dz * dz);
+                    if (d < best) {  // torch.min keeps the first minimum
+                        best = d;
+                        kbest = k;
+                        q[0] = x; q[1] = y; q[2] = z;
+                    }
+                }
+            }
+            if (kbest >= 0) {
+                const float* mn = model_n + (size_t)kbest * 3 * hw + pix;
+                const float n[3] = {mn[0], mn[hw], mn[2 * hw]};
+                float J[6];
+                const float r = p2plane_residual_jacobian_identity(p, q, n, J);
+                const float w = ls_weight<float>(scheme, sigma, r, p, q);
+                accumulate_normal_equations<float>(acc, J, w, r * w, r);
+            }
+        }
+        __syncthreads();  // every consumer is done with stage s before the async proxy refills it
+        if (threadIdx.x == 0) {
+            const int64_t nt = tile + (int64_t)PT_STAGES * stride;
+            if (nt < tile_end) issue(nt, s);
+        }
+    }
+    block_reduce_store<PT_TILE>(acc, partials + (size_t)blockIdx.x * NACC);
+}
+
 // per-pixel association for the fine-grained API: flag + (q, n, p)
 __global__ void proj_pairs_kernel(const float* __restrict__ model_v, const float* __restrict__ model_n, int K, int64_t hw,
                                   const unsigned long long* __restrict__ zbuf, const float4* __restrict__ queries,
@@ -424,8 +549,33 @@ int projmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int n
     query_zbuf_kernel<<<grid_for(query_bound, 256), 256, 0, st>>>(
         ctx->query_ptr, reinterpret_cast<const uint32_t*>(&fr->counts[1]), 0, fr->T, &fr->done, pc, zbuf);
     PLS_CHECK_LAUNCH();
+    const int K = pm.K;
+    const size_t stage_bytes = (size_t)K * 3 * PT_TILE * sizeof(float);
+    static const bool no_tma = getenv("PLS_PROJ_NO_TMA") != nullptr;
+    int blocks;
+    if (!no_tma && hw % PT_TILE == 0 && stage_bytes * PT_STAGES <= 200 * 1024) {
+        // TMA-staged persistent kernel over 128-pixel tiles; ranks take contiguous tile ranges
+        const int64_t tiles = hw / PT_TILE;
+        const int64_t tile_begin = tiles * rank / num_ranks, tile_end = tiles * (rank + 1) / num_ranks;
+        const size_t smem = stage_bytes * PT_STAGES;
+        static bool attr_set = false;
+        if (!attr_set) {
+            PLS_CUDA(cudaFuncSetAttribute(proj_icp_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+        int per_sm = (int)((220 * 1024) / (smem + 2048));
+        per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+        blocks = grid_for(tile_end - tile_begin, 1, per_sm * kNumSMs);
+        ctx->partials.reserve((size_t)blocks * NACC * sizeof(double), st);
+        ProfileScope ps(ctx, 1, 0.0, false);
+        proj_icp_tma_kernel<<<blocks, PT_TILE, smem, st>>>(pm.model_v.as<float>(), pm.model_n.as<float>(), K, hw, zbuf,
+                                                           ctx->query_ptr, fr, tile_begin, tile_end, ctx->cfg.scheme,
+                                                           ctx->cfg.sigma, ctx->partials.as<double>());
+        PLS_CHECK_LAUNCH();
+        return blocks;
+    }
     const int64_t pix_begin = hw * rank / num_ranks, pix_end = hw * (rank + 1) / num_ranks;
-    const int blocks = grid_for(pix_end - pix_begin, PJ_THREADS, 4 * kNumSMs);
+    blocks = grid_for(pix_end - pix_begin, PJ_THREADS, 4 * kNumSMs);
     ctx->partials.reserve((size_t)blocks * NACC * sizeof(double), st);
     {
         ProfileScope ps(ctx, 1, 0.0, false);
