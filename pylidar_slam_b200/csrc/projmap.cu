@@ -108,6 +108,17 @@ normal_map_kernel(const float* __restrict__ vmap, int batch, int H, int W, int k
     o[2 * hw] = n[2];
 }
 
+// ------------------------------------------------------------------------------------------ model layout
+// The re-projected model maps are stored TILE-INTERLEAVED in HBM: [tile = pix / 128][row = k * 3 + c][pix % 128]
+// with a fixed tile stride of Kcap * 3 * 128 floats (Kcap = local_map_size).  All candidates of a 128-pixel
+// tile are then ONE contiguous block (K * 3 * 512 bytes): a single TMA bulk copy per tile and a purely
+// sequential HBM stream for the correspondence kernel.  The reference's planar [K,3,H,W] view exists only
+// at the API boundary (pls_projmap_model converts).
+constexpr int PT_TILE = 128;
+__device__ __host__ __forceinline__ size_t model_off(int64_t pix, int row, int kcap) {
+    return (size_t)(pix / PT_TILE) * ((size_t)kcap * 3 * PT_TILE) + (size_t)row * PT_TILE + (size_t)(pix % PT_TILE);
+}
+
 // ------------------------------------------------------------------------------------------ model rebuild
 struct PoseSet {
     const float* poses;  // [K][16] device
@@ -144,7 +155,7 @@ __global__ void model_zbuf_kernel(const float* __restrict__ vmaps, const float* 
 }
 
 __global__ void model_resolve_kernel(const float* __restrict__ vmaps, const float* __restrict__ nmaps,
-                                     const float* __restrict__ poses, int K, int head, int slots, int64_t hw,
+                                     const float* __restrict__ poses, int K, int head, int slots, int kcap, int64_t hw,
                                      const unsigned long long* __restrict__ zbuf, float* __restrict__ model_v,
                                      float* __restrict__ model_n) {
     const int64_t total = (int64_t)K * hw;
@@ -163,10 +174,9 @@ __global__ void model_resolve_kernel(const float* __restrict__ vmaps, const floa
             n[1] = P[4] * nx + P[5] * ny + P[6] * nz;
             n[2] = P[8] * nx + P[9] * ny + P[10] * nz;
         }
-        float* ov = model_v + (size_t)k * 3 * hw + pix;
-        float* on = model_n + (size_t)k * 3 * hw + pix;
-        ov[0] = p[0]; ov[hw] = p[1]; ov[2 * hw] = p[2];
-        on[0] = n[0]; on[hw] = n[1]; on[2 * hw] = n[2];
+        const size_t o = model_off(pix, (int)k * 3, kcap);
+        model_v[o] = p[0]; model_v[o + PT_TILE] = p[1]; model_v[o + 2 * PT_TILE] = p[2];
+        model_n[o] = n[0]; model_n[o + PT_TILE] = n[1]; model_n[o + 2 * PT_TILE] = n[2];
     }
 }
 
@@ -202,14 +212,15 @@ __global__ void query_zbuf_kernel(const float4* __restrict__ queries, const uint
 
 // argmin over the K candidates at one pixel; returns false if none is valid
 __device__ __forceinline__ bool pixel_argmin(const float* __restrict__ model_v, const float* __restrict__ model_n, int K,
-                                             int64_t hw, int64_t pix, const float* p, float* q, float* n) {
+                                             int kcap, int64_t pix, const float* p, float* q, float* n) {
     float best = __int_as_float(0x7f800000);
     int kbest = -1;
     float bq[3] = {0.f, 0.f, 0.f};
+    const float* mvb = model_v + model_off(pix, 0, kcap);
 #pragma unroll 4
     for (int k = 0; k < K; ++k) {
-        const float* mv = model_v + (size_t)k * 3 * hw + pix;
-        const float x = mv[0], y = mv[hw], z = mv[2 * hw];
+        const float* mv = mvb + (size_t)k * 3 * PT_TILE;
+        const float x = mv[0], y = mv[PT_TILE], z = mv[2 * PT_TILE];
         if (fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) > 0.f) {
             const float dx = p[0] - x, dy = p[1] - y, dz = p[2] - z;
             const float d = sqrtf(dx * dx + dy * dy + dz * dz);
@@ -222,15 +233,15 @@ __device__ __forceinline__ bool pixel_argmin(const float* __restrict__ model_v, 
     }
     if (kbest < 0) return false;
     q[0] = bq[0]; q[1] = bq[1]; q[2] = bq[2];
-    const float* mn = model_n + (size_t)kbest * 3 * hw + pix;
-    n[0] = mn[0]; n[1] = mn[hw]; n[2] = mn[2 * hw];
+    const float* mn = model_n + model_off(pix, kbest * 3, kcap);
+    n[0] = mn[0]; n[1] = mn[PT_TILE]; n[2] = mn[2 * PT_TILE];
     return true;
 }
 
 constexpr int PJ_THREADS = 256;
 
 __global__ void __launch_bounds__(PJ_THREADS)
-proj_icp_iter_kernel(const float* __restrict__ model_v, const float* __restrict__ model_n, int K, int64_t hw,
+proj_icp_iter_kernel(const float* __restrict__ model_v, const float* __restrict__ model_n, int K, int kcap,
                      const unsigned long long* __restrict__ zbuf, const float4* __restrict__ queries,
                      const FrameResult* __restrict__ fr, int64_t pix_begin, int64_t pix_end, int scheme, float sigma,
                      double* __restrict__ partials) {
@@ -249,7 +260,7 @@ proj_icp_iter_kernel(const float* __restrict__ model_v, const float* __restrict_
         p[0] = p0.x * sT[0] + p0.y * sT[1] + p0.z * sT[2] + sT[3];
         p[1] = p0.x * sT[4] + p0.y * sT[5] + p0.z * sT[6] + sT[7];
         p[2] = p0.x * sT[8] + p0.y * sT[9] + p0.z * sT[10] + sT[11];
-        if (!pixel_argmin(model_v, model_n, K, hw, pix, p, q, n)) continue;
+        if (!pixel_argmin(model_v, model_n, K, kcap, pix, p, q, n)) continue;
         float J[6];
         const float r = p2plane_residual_jacobian_identity(p, q, n, J);
         const float w = ls_weight<float>(scheme, sigma, r, p, q);
@@ -264,7 +275,6 @@ proj_icp_iter_kernel(const float* __restrict__ model_v, const float* __restrict_
 // [K*3][128] shared-memory stage and complete on that stage's mbarrier; 3 stages keep two tiles (up to
 // 60 KB per CTA) in flight while the third is consumed, with no registers tied up by outstanding loads.
 // The consumers (one thread per pixel) read conflict-free from shared memory.
-constexpr int PT_TILE = 128;
 constexpr int PT_STAGES = 3;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -293,7 +303,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 __global__ void __launch_bounds__(PT_TILE)
-proj_icp_tma_kernel(const float* __restrict__ model_v, const float* __restrict__ model_n, int K, int64_t hw,
+proj_icp_tma_kernel(const float* __restrict__ model_v, const float* __restrict__ model_n, int K, int kcap,
                     const unsigned long long* __restrict__ zbuf, const float4* __restrict__ queries,
                     const FrameResult* __restrict__ fr, int64_t tile_begin, int64_t tile_end, int scheme, float sigma,
                     double* __restrict__ partials) {
@@ -316,9 +326,9 @@ proj_icp_tma_kernel(const float* __restrict__ model_v, const float* __restrict__
     const int64_t stride = gridDim.x;
     auto issue = [&](int64_t tile, int s) {  // thread 0 only
         mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-        float* dst = stage_base + (size_t)s * stage_floats;
-        const float* src = model_v + tile * PT_TILE;
-        for (int r = 0; r < rows; ++r) bulk_copy_g2s(dst + r * PT_TILE, src + (size_t)r * hw, PT_TILE * sizeof(float), &full_bar[s]);
+        // the tile's K*3 rows are contiguous in the tile-interleaved layout: one bulk copy
+        bulk_copy_g2s(stage_base + (size_t)s * stage_floats, model_v + (size_t)tile * ((size_t)kcap * 3 * PT_TILE), stage_bytes,
+                      &full_bar[s]);
     };
     if (threadIdx.x == 0) {
         for (int s = 0; s < PT_STAGES; ++s) {
@@ -364,8 +374,8 @@ proj_icp_tma_kernel(const float* __restrict__ model_v, const float* __restrict__
                 }
             }
             if (kbest >= 0) {
-                const float* mn = model_n + (size_t)kbest * 3 * hw + pix;
-                const float n[3] = {mn[0], mn[hw], mn[2 * hw]};
+                const float* mn = model_n + model_off(pix, kbest * 3, kcap);
+                const float n[3] = {mn[0], mn[PT_TILE], mn[2 * PT_TILE]};
                 float J[6];
                 const float r = p2plane_residual_jacobian_identity(p, q, n, J);
                 const float w = ls_weight<float>(scheme, sigma, r, p, q);
@@ -382,8 +392,8 @@ proj_icp_tma_kernel(const float* __restrict__ model_v, const float* __restrict__
 }
 
 // per-pixel association for the fine-grained API: flag + (q, n, p)
-__global__ void proj_pairs_kernel(const float* __restrict__ model_v, const float* __restrict__ model_n, int K, int64_t hw,
-                                  const unsigned long long* __restrict__ zbuf, const float4* __restrict__ queries,
+__global__ void proj_pairs_kernel(const float* __restrict__ model_v, const float* __restrict__ model_n, int K, int kcap,
+                                  int64_t hw, const unsigned long long* __restrict__ zbuf, const float4* __restrict__ queries,
                                   uint8_t* __restrict__ flags, float* __restrict__ pairs /* [hw][9] */) {
     for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < hw; pix += (int64_t)gridDim.x * blockDim.x) {
         const unsigned long long key = zbuf[pix];
@@ -391,7 +401,7 @@ __global__ void proj_pairs_kernel(const float* __restrict__ model_v, const float
         if (key != ~0ull) {
             const float4 p0 = queries[(uint32_t)(key & 0xffffffffull)];
             float p[3] = {p0.x, p0.y, p0.z}, q[3], n[3];
-            if (pixel_argmin(model_v, model_n, K, hw, pix, p, q, n)) {
+            if (pixel_argmin(model_v, model_n, K, kcap, pix, p, q, n)) {
                 ok = 1;
                 float* o = pairs + 9 * pix;
                 o[0] = q[0]; o[1] = q[1]; o[2] = q[2];
@@ -447,6 +457,15 @@ __global__ void compute_neighbors_kernel(const float* __restrict__ tgt, const fl
     }
 }
 
+// tile-interleaved -> the reference's planar [K,3,H,W]
+__global__ void model_export_kernel(const float* __restrict__ tiled, int K, int kcap, int64_t hw, float* __restrict__ planar) {
+    const int64_t total = (int64_t)K * 3 * hw;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = g / hw, pix = g - row * hw;
+        planar[g] = tiled[model_off(pix, (int)row, kcap)];
+    }
+}
+
 void rebuild_model(pls_context* ctx) {
     ProjMap& pm = ctx->pm;
     cudaStream_t st = ctx->stream;
@@ -458,8 +477,10 @@ void rebuild_model(pls_context* ctx) {
     pm.poses.reserve((size_t)ctx->cfg.local_map_size * 16 * sizeof(float) + 64, st);
     PLS_CUDA(cudaMemcpyAsync(pm.poses.p, pm.host_poses.data(), (size_t)K * 16 * sizeof(float), cudaMemcpyHostToDevice, st));
     pm.zbuf.reserve((size_t)(K > 1 ? K : 1) * hw * sizeof(unsigned long long), st);
-    pm.model_v.reserve((size_t)ctx->cfg.local_map_size * 3 * hw * sizeof(float), st);
-    pm.model_n.reserve((size_t)ctx->cfg.local_map_size * 3 * hw * sizeof(float), st);
+    const int kcap = ctx->cfg.local_map_size;
+    const size_t model_floats = (size_t)((hw + PT_TILE - 1) / PT_TILE) * kcap * 3 * PT_TILE;
+    pm.model_v.reserve(model_floats * sizeof(float), st);
+    pm.model_n.reserve(model_floats * sizeof(float), st);
     PLS_CUDA(cudaMemsetAsync(pm.zbuf.p, 0xff, (size_t)K * hw * sizeof(unsigned long long), st));
     ProjConst pc = make_proj_const(H, W, ctx->cfg.up_fov_deg, ctx->cfg.down_fov_deg);
     const int slots = ctx->cfg.local_map_size + 1;
@@ -467,7 +488,7 @@ void rebuild_model(pls_context* ctx) {
                                                              pc, pm.zbuf.as<unsigned long long>());
     PLS_CHECK_LAUNCH();
     model_resolve_kernel<<<grid_for(K * hw, 256), 256, 0, st>>>(pm.vmaps.as<float>(), pm.nmaps.as<float>(),
-                                                                pm.poses.as<float>(), K, pm.head, slots, hw,
+                                                                pm.poses.as<float>(), K, pm.head, slots, kcap, hw,
                                                                 pm.zbuf.as<unsigned long long>(),
                                                                 pm.model_v.as<float>(), pm.model_n.as<float>());
     PLS_CHECK_LAUNCH();
@@ -568,7 +589,8 @@ int projmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int n
         blocks = grid_for(tile_end - tile_begin, 1, per_sm * kNumSMs);
         ctx->partials.reserve((size_t)blocks * NACC * sizeof(double), st);
         ProfileScope ps(ctx, 1, 0.0, false);
-        proj_icp_tma_kernel<<<blocks, PT_TILE, smem, st>>>(pm.model_v.as<float>(), pm.model_n.as<float>(), K, hw, zbuf,
+        proj_icp_tma_kernel<<<blocks, PT_TILE, smem, st>>>(pm.model_v.as<float>(), pm.model_n.as<float>(), K,
+                                                           ctx->cfg.local_map_size, zbuf,
                                                            ctx->query_ptr, fr, tile_begin, tile_end, ctx->cfg.scheme,
                                                            ctx->cfg.sigma, ctx->partials.as<double>());
         PLS_CHECK_LAUNCH();
@@ -579,7 +601,8 @@ int projmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int n
     ctx->partials.reserve((size_t)blocks * NACC * sizeof(double), st);
     {
         ProfileScope ps(ctx, 1, 0.0, false);
-        proj_icp_iter_kernel<<<blocks, PJ_THREADS, 0, st>>>(pm.model_v.as<float>(), pm.model_n.as<float>(), pm.K, hw, zbuf,
+        proj_icp_iter_kernel<<<blocks, PJ_THREADS, 0, st>>>(pm.model_v.as<float>(), pm.model_n.as<float>(), pm.K,
+                                                            ctx->cfg.local_map_size, zbuf,
                                                             ctx->query_ptr, fr, pix_begin, pix_end, ctx->cfg.scheme,
                                                             ctx->cfg.sigma, ctx->partials.as<double>());
         PLS_CHECK_LAUNCH();
@@ -651,13 +674,18 @@ int pls_projmap_model(pls_context* ctx, float* out_vmap, float* out_nmap) {
     PLS_API_BEGIN(ctx)
     map_stream_wait(ctx);
     PLS_REQUIRE(ctx->pm.valid, "pls_projmap_model: empty map");
-    const size_t bytes = (size_t)ctx->pm.K * 3 * ctx->cfg.height * ctx->cfg.width * sizeof(float);
-    auto put = [&](float* dst, const void* src) {
+    const int64_t hw = (int64_t)ctx->cfg.height * ctx->cfg.width;
+    const size_t bytes = (size_t)ctx->pm.K * 3 * hw * sizeof(float);
+    auto put = [&](float* dst, const float* tiled, DBuf& stage) {
         if (!dst) return;
-        PLS_CUDA(cudaMemcpyAsync(dst, src, bytes, is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+        OutArg o = out_arg(ctx, dst, bytes, stage);
+        model_export_kernel<<<grid_for((int64_t)ctx->pm.K * 3 * hw, 256), 256, 0, ctx->stream>>>(tiled, ctx->pm.K, ctx->cfg.local_map_size,
+                                                                                              hw, (float*)o.dev);
+        PLS_CHECK_LAUNCH();
+        finish_out(ctx, o);
     };
-    put(out_vmap, ctx->pm.model_v.p);
-    put(out_nmap, ctx->pm.model_n.p);
+    put(out_vmap, ctx->pm.model_v.as<float>(), ctx->stage_out[0]);
+    put(out_nmap, ctx->pm.model_n.as<float>(), ctx->stage_out[1]);
     PLS_CUDA(cudaStreamSynchronize(ctx->stream));
     PLS_API_END(ctx)
 }
@@ -685,8 +713,8 @@ int pls_projmap_nn_search(pls_context* ctx, const float* queries, int64_t n, flo
     ctx->tmp[1].reserve((size_t)hw, st);
     ctx->tmp[2].reserve((size_t)hw * sizeof(uint32_t), st);
     ctx->tmp[7].reserve((size_t)hw * 9 * sizeof(float), st);
-    proj_pairs_kernel<<<grid_for(hw, 256), 256, 0, st>>>(ctx->pm.model_v.as<float>(), ctx->pm.model_n.as<float>(), ctx->pm.K, hw,
-                                                          zbuf, ctx->queries.as<float4>(), ctx->tmp[1].as<uint8_t>(),
+    proj_pairs_kernel<<<grid_for(hw, 256), 256, 0, st>>>(ctx->pm.model_v.as<float>(), ctx->pm.model_n.as<float>(), ctx->pm.K,
+                                                          ctx->cfg.local_map_size, hw, zbuf, ctx->queries.as<float4>(), ctx->tmp[1].as<uint8_t>(),
                                                           ctx->tmp[7].as<float>());
     PLS_CHECK_LAUNCH();
     uint32_t* total = scalar_u32(ctx, SC_PROJ_NC);
