@@ -118,6 +118,11 @@ constexpr int PT_TILE = 128;
 __device__ __host__ __forceinline__ size_t model_off(int64_t pix, int row, int kcap) {
     return (size_t)(pix / PT_TILE) * ((size_t)kcap * 3 * PT_TILE) + (size_t)row * PT_TILE + (size_t)(pix % PT_TILE);
 }
+// The model NORMALS are only ever gathered for the winning candidate of a pixel, so they are stored as one
+// float4 per (tile, k, pixel): the gather is a single 16-byte access (one 32-byte sector) instead of three.
+__device__ __host__ __forceinline__ size_t normal_off(int64_t pix, int k, int kcap) {
+    return ((size_t)(pix / PT_TILE) * kcap + (size_t)k) * PT_TILE + (size_t)(pix % PT_TILE);  // float4 units
+}
 
 // ------------------------------------------------------------------------------------------ model rebuild
 struct PoseSet {
@@ -157,7 +162,7 @@ __global__ void model_zbuf_kernel(const float* __restrict__ vmaps, const float* 
 __global__ void model_resolve_kernel(const float* __restrict__ vmaps, const float* __restrict__ nmaps,
                                      const float* __restrict__ poses, int K, int head, int slots, int kcap, int64_t hw,
                                      const unsigned long long* __restrict__ zbuf, float* __restrict__ model_v,
-                                     float* __restrict__ model_n) {
+                                     float4* __restrict__ model_n) {
     const int64_t total = (int64_t)K * hw;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
         const int64_t k = g / hw, pix = g - k * hw;
@@ -176,7 +181,7 @@ __global__ void model_resolve_kernel(const float* __restrict__ vmaps, const floa
         }
         const size_t o = model_off(pix, (int)k * 3, kcap);
         model_v[o] = p[0]; model_v[o + PT_TILE] = p[1]; model_v[o + 2 * PT_TILE] = p[2];
-        model_n[o] = n[0]; model_n[o + PT_TILE] = n[1]; model_n[o + 2 * PT_TILE] = n[2];
+        model_n[normal_off(pix, (int)k, kcap)] = make_float4(n[0], n[1], n[2], 0.f);
     }
 }
 
@@ -210,8 +215,29 @@ __global__ void query_zbuf_kernel(const float4* __restrict__ queries, const uint
     }
 }
 
+// z-buffer winners -> the target vertex map of this iteration, float4 (p transformed, valid flag) per pixel
+__global__ void query_resolve_kernel(const unsigned long long* __restrict__ zbuf, const float4* __restrict__ queries,
+                                     const float* __restrict__ T, const int* __restrict__ done, int64_t hw,
+                                     float4* __restrict__ tgt) {
+    if (done && *done) return;
+    __shared__ float sT[12];
+    load_T(T, sT);
+    for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < hw; pix += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long key = zbuf[pix];
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (key != ~0ull) {
+            const float4 p0 = queries[(uint32_t)(key & 0xffffffffull)];
+            o.x = p0.x * sT[0] + p0.y * sT[1] + p0.z * sT[2] + sT[3];
+            o.y = p0.x * sT[4] + p0.y * sT[5] + p0.z * sT[6] + sT[7];
+            o.z = p0.x * sT[8] + p0.y * sT[9] + p0.z * sT[10] + sT[11];
+            o.w = 1.f;
+        }
+        tgt[pix] = o;
+    }
+}
+
 // argmin over the K candidates at one pixel; returns false if none is valid
-__device__ __forceinline__ bool pixel_argmin(const float* __restrict__ model_v, const float* __restrict__ model_n, int K,
+__device__ __forceinline__ bool pixel_argmin(const float* __restrict__ model_v, const float4* __restrict__ model_n, int K,
                                              int kcap, int64_t pix, const float* p, float* q, float* n) {
     float best = __int_as_float(0x7f800000);
     int kbest = -1;
@@ -233,15 +259,15 @@ __device__ __forceinline__ bool pixel_argmin(const float* __restrict__ model_v, 
     }
     if (kbest < 0) return false;
     q[0] = bq[0]; q[1] = bq[1]; q[2] = bq[2];
-    const float* mn = model_n + model_off(pix, kbest * 3, kcap);
-    n[0] = mn[0]; n[1] = mn[PT_TILE]; n[2] = mn[2 * PT_TILE];
+    const float4 mn = model_n[normal_off(pix, kbest, kcap)];
+    n[0] = mn.x; n[1] = mn.y; n[2] = mn.z;
     return true;
 }
 
 constexpr int PJ_THREADS = 256;
 
 __global__ void __launch_bounds__(PJ_THREADS)
-proj_icp_iter_kernel(const float* __restrict__ model_v, const float* __restrict__ model_n, int K, int kcap,
+proj_icp_iter_kernel(const float* __restrict__ model_v, const float4* __restrict__ model_n, int K, int kcap,
                      const unsigned long long* __restrict__ zbuf, const float4* __restrict__ queries,
                      const FrameResult* __restrict__ fr, int64_t pix_begin, int64_t pix_end, int scheme, float sigma,
                      double* __restrict__ partials) {
@@ -303,21 +329,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 __global__ void __launch_bounds__(PT_TILE)
-proj_icp_tma_kernel(const float* __restrict__ model_v, const float* __restrict__ model_n, int K, int kcap,
-                    const unsigned long long* __restrict__ zbuf, const float4* __restrict__ queries,
-                    const FrameResult* __restrict__ fr, int64_t tile_begin, int64_t tile_end, int scheme, float sigma,
-                    double* __restrict__ partials) {
+proj_icp_tma_kernel(const float* __restrict__ model_v, const float4* __restrict__ model_n, int K, int kcap,
+                    const float4* __restrict__ tgt, const FrameResult* __restrict__ fr, int64_t tile_begin, int64_t tile_end, int scheme, float sigma,
+                    int stages, double* __restrict__ partials) {
     if (fr->done) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[PT_STAGES];
-    __shared__ float sT[12];
     float* stage_base = reinterpret_cast<float*>(smem_raw);
     const int rows = K * 3;
-    const uint32_t stage_floats = (uint32_t)rows * PT_TILE;
+    const uint32_t model_bytes = (uint32_t)rows * PT_TILE * sizeof(float);
+    const uint32_t stage_floats = (uint32_t)(rows + 4) * PT_TILE;  // + the tile of the target vertex map (float4 per pixel)
     const uint32_t stage_bytes = stage_floats * sizeof(float);
-    if (threadIdx.x < 12) sT[threadIdx.x] = fr->T[threadIdx.x];
     if (threadIdx.x == 0) {
-        for (int s = 0; s < PT_STAGES; ++s) mbar_init(&full_bar[s], 1);
+        for (int s = 0; s < stages; ++s) mbar_init(&full_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -326,12 +350,14 @@ proj_icp_tma_kernel(const float* __restrict__ model_v, const float* __restrict__
     const int64_t stride = gridDim.x;
     auto issue = [&](int64_t tile, int s) {  // thread 0 only
         mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-        // the tile's K*3 rows are contiguous in the tile-interleaved layout: one bulk copy
-        bulk_copy_g2s(stage_base + (size_t)s * stage_floats, model_v + (size_t)tile * ((size_t)kcap * 3 * PT_TILE), stage_bytes,
-                      &full_bar[s]);
+        // the tile's K*3 candidate rows are contiguous in the tile-interleaved layout: one bulk copy; a second
+        // one brings the tile of the (z-buffered, already transformed) target vertex map
+        float* dst = stage_base + (size_t)s * stage_floats;
+        bulk_copy_g2s(dst, model_v + (size_t)tile * ((size_t)kcap * 3 * PT_TILE), model_bytes, &full_bar[s]);
+        bulk_copy_g2s(dst + (size_t)rows * PT_TILE, tgt + tile * PT_TILE, PT_TILE * sizeof(float4), &full_bar[s]);
     };
     if (threadIdx.x == 0) {
-        for (int s = 0; s < PT_STAGES; ++s) {
+        for (int s = 0; s < stages; ++s) {
             const int64_t t = first_tile + (int64_t)s * stride;
             if (t < tile_end) issue(t, s);
         }
@@ -339,27 +365,23 @@ proj_icp_tma_kernel(const float* __restrict__ model_v, const float* __restrict__
     double acc[NACC];
 #pragma unroll
     for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
+    bool pend = false;
+    float pp[3] = {0.f, 0.f, 0.f}, pq[3] = {0.f, 0.f, 0.f}, pn[3] = {0.f, 0.f, 0.f};
     int it = 0;
     for (int64_t tile = first_tile; tile < tile_end; tile += stride, ++it) {
-        const int s = it % PT_STAGES;
-        const uint32_t parity = (uint32_t)((it / PT_STAGES) & 1);
+        const int s = it % stages;
+        const uint32_t parity = (uint32_t)((it / stages) & 1);
         const int64_t pix = tile * PT_TILE + threadIdx.x;
-        // independent of the staged tile: fetch the pixel's surviving query while the copies are in flight
-        const unsigned long long key = zbuf[pix];
-        float p[3] = {0.f, 0.f, 0.f};
-        const bool has = key != ~0ull;
-        if (has) {
-            const float4 p0 = queries[(uint32_t)(key & 0xffffffffull)];
-            p[0] = p0.x * sT[0] + p0.y * sT[1] + p0.z * sT[2] + sT[3];
-            p[1] = p0.x * sT[4] + p0.y * sT[5] + p0.z * sT[6] + sT[7];
-            p[2] = p0.x * sT[8] + p0.y * sT[9] + p0.z * sT[10] + sT[11];
-        }
         mbar_wait(&full_bar[s], parity);
+        bool matched = false;
+        float q[3] = {0.f, 0.f, 0.f};
+        int kbest = -1;
+        const float4 tp = reinterpret_cast<const float4*>(stage_base + (size_t)s * stage_floats + (size_t)rows * PT_TILE)[threadIdx.x];
+        const float p[3] = {tp.x, tp.y, tp.z};
+        const bool has = tp.w != 0.f;
         if (has) {
             const float* st = stage_base + (size_t)s * stage_floats + threadIdx.x;
             float best = __int_as_float(0x7f800000);
-            int kbest = -1;
-            float q[3] = {0.f, 0.f, 0.f};
 #pragma unroll 4
             for (int k = 0; k < K; ++k) {
                 const float x = st[(3 * k) * PT_TILE], y = st[(3 * k + 1) * PT_TILE], z = st[(3 * k + 2) * PT_TILE];
@@ -373,26 +395,41 @@ proj_icp_tma_kernel(const float* __restrict__ model_v, const float* __restrict__
                     }
                 }
             }
-            if (kbest >= 0) {
-                const float* mn = model_n + model_off(pix, kbest * 3, kcap);
-                const float n[3] = {mn[0], mn[PT_TILE], mn[2 * PT_TILE]};
-                float J[6];
-                const float r = p2plane_residual_jacobian_identity(p, q, n, J);
-                const float w = ls_weight<float>(scheme, sigma, r, p, q);
-                accumulate_normal_equations<float>(acc, J, w, r * w, r);
-            }
+            matched = kbest >= 0;
         }
         __syncthreads();  // every consumer is done with stage s before the async proxy refills it
         if (threadIdx.x == 0) {
-            const int64_t nt = tile + (int64_t)PT_STAGES * stride;
+            const int64_t nt = tile + (int64_t)stages * stride;
             if (nt < tile_end) issue(nt, s);
         }
+        // issue the winner-normal gather of THIS tile now; it is consumed one iteration later, after the next
+        // tile's arg-min, so its latency is hidden
+        float nn[3] = {0.f, 0.f, 0.f};
+        if (matched) {
+            const float4 mn = model_n[normal_off(pix, kbest, kcap)];
+            nn[0] = mn.x; nn[1] = mn.y; nn[2] = mn.z;
+        }
+        if (pend) {
+            float J[6];
+            const float r = p2plane_residual_jacobian_identity(pp, pq, pn, J);
+            const float w = ls_weight<float>(scheme, sigma, r, pp, pq);
+            accumulate_normal_equations<float>(acc, J, w, r * w, r);
+        }
+        pend = matched;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { pp[c] = p[c]; pq[c] = q[c]; pn[c] = nn[c]; }
+    }
+    if (pend) {
+        float J[6];
+        const float r = p2plane_residual_jacobian_identity(pp, pq, pn, J);
+        const float w = ls_weight<float>(scheme, sigma, r, pp, pq);
+        accumulate_normal_equations<float>(acc, J, w, r * w, r);
     }
     block_reduce_store<PT_TILE>(acc, partials + (size_t)blockIdx.x * NACC);
 }
 
 // per-pixel association for the fine-grained API: flag + (q, n, p)
-__global__ void proj_pairs_kernel(const float* __restrict__ model_v, const float* __restrict__ model_n, int K, int kcap,
+__global__ void proj_pairs_kernel(const float* __restrict__ model_v, const float4* __restrict__ model_n, int K, int kcap,
                                   int64_t hw, const unsigned long long* __restrict__ zbuf, const float4* __restrict__ queries,
                                   uint8_t* __restrict__ flags, float* __restrict__ pairs /* [hw][9] */) {
     for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < hw; pix += (int64_t)gridDim.x * blockDim.x) {
@@ -466,6 +503,17 @@ __global__ void model_export_kernel(const float* __restrict__ tiled, int K, int 
     }
 }
 
+__global__ void normal_export_kernel(const float4* __restrict__ tiled, int K, int kcap, int64_t hw, float* __restrict__ planar) {
+    const int64_t total = (int64_t)K * hw;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = g / hw, pix = g - k * hw;
+        const float4 n = tiled[normal_off(pix, (int)k, kcap)];
+        planar[(k * 3 + 0) * hw + pix] = n.x;
+        planar[(k * 3 + 1) * hw + pix] = n.y;
+        planar[(k * 3 + 2) * hw + pix] = n.z;
+    }
+}
+
 void rebuild_model(pls_context* ctx) {
     ProjMap& pm = ctx->pm;
     cudaStream_t st = ctx->stream;
@@ -480,7 +528,7 @@ void rebuild_model(pls_context* ctx) {
     const int kcap = ctx->cfg.local_map_size;
     const size_t model_floats = (size_t)((hw + PT_TILE - 1) / PT_TILE) * kcap * 3 * PT_TILE;
     pm.model_v.reserve(model_floats * sizeof(float), st);
-    pm.model_n.reserve(model_floats * sizeof(float), st);
+    pm.model_n.reserve((size_t)((hw + PT_TILE - 1) / PT_TILE) * kcap * PT_TILE * sizeof(float4), st);
     PLS_CUDA(cudaMemsetAsync(pm.zbuf.p, 0xff, (size_t)K * hw * sizeof(unsigned long long), st));
     ProjConst pc = make_proj_const(H, W, ctx->cfg.up_fov_deg, ctx->cfg.down_fov_deg);
     const int slots = ctx->cfg.local_map_size + 1;
@@ -490,7 +538,7 @@ void rebuild_model(pls_context* ctx) {
     model_resolve_kernel<<<grid_for(K * hw, 256), 256, 0, st>>>(pm.vmaps.as<float>(), pm.nmaps.as<float>(),
                                                                 pm.poses.as<float>(), K, pm.head, slots, kcap, hw,
                                                                 pm.zbuf.as<unsigned long long>(),
-                                                                pm.model_v.as<float>(), pm.model_n.as<float>());
+                                                                pm.model_v.as<float>(), pm.model_n.as<float4>());
     PLS_CHECK_LAUNCH();
     pm.valid = true;
 }
@@ -571,28 +619,38 @@ int projmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int n
         ctx->query_ptr, reinterpret_cast<const uint32_t*>(&fr->counts[1]), 0, fr->T, &fr->done, pc, zbuf);
     PLS_CHECK_LAUNCH();
     const int K = pm.K;
-    const size_t stage_bytes = (size_t)K * 3 * PT_TILE * sizeof(float);
+    const size_t stage_bytes = (size_t)(K * 3 + 4) * PT_TILE * sizeof(float);
     static const bool no_tma = getenv("PLS_PROJ_NO_TMA") != nullptr;
+    static const int stages = getenv("PLS_PROJ_STAGES") ? atoi(getenv("PLS_PROJ_STAGES")) : 2;
     int blocks;
-    if (!no_tma && hw % PT_TILE == 0 && stage_bytes * PT_STAGES <= 200 * 1024) {
+    if (!no_tma && hw % PT_TILE == 0 && stages >= 1 && stages <= PT_STAGES && stage_bytes * stages <= 200 * 1024) {
         // TMA-staged persistent kernel over 128-pixel tiles; ranks take contiguous tile ranges
         const int64_t tiles = hw / PT_TILE;
         const int64_t tile_begin = tiles * rank / num_ranks, tile_end = tiles * (rank + 1) / num_ranks;
-        const size_t smem = stage_bytes * PT_STAGES;
+        const size_t smem = stage_bytes * stages;
         static bool attr_set = false;
         if (!attr_set) {
             PLS_CUDA(cudaFuncSetAttribute(proj_icp_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             attr_set = true;
         }
         int per_sm = (int)((220 * 1024) / (smem + 2048));
-        per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
-        blocks = grid_for(tile_end - tile_begin, 1, per_sm * kNumSMs);
+        per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+        {   // equal tile counts per CTA: ceil(tiles / ceil(tiles / max_ctas)) persistent CTAs
+            const int64_t my_tiles = tile_end - tile_begin;
+            const int64_t max_ctas = (int64_t)per_sm * kNumSMs;
+            const int64_t per_cta = (my_tiles + max_ctas - 1) / max_ctas;
+            blocks = (int)((my_tiles + (per_cta > 0 ? per_cta : 1) - 1) / (per_cta > 0 ? per_cta : 1));
+            if (blocks < 1) blocks = 1;
+        }
         ctx->partials.reserve((size_t)blocks * NACC * sizeof(double), st);
+        ctx->tmp[7].reserve((size_t)hw * sizeof(float4), st);
+        query_resolve_kernel<<<grid_for(hw, 256), 256, 0, st>>>(zbuf, ctx->query_ptr, fr->T, &fr->done, hw, ctx->tmp[7].as<float4>());
+        PLS_CHECK_LAUNCH();
         ProfileScope ps(ctx, 1, 0.0, false);
-        proj_icp_tma_kernel<<<blocks, PT_TILE, smem, st>>>(pm.model_v.as<float>(), pm.model_n.as<float>(), K,
-                                                           ctx->cfg.local_map_size, zbuf,
-                                                           ctx->query_ptr, fr, tile_begin, tile_end, ctx->cfg.scheme,
-                                                           ctx->cfg.sigma, ctx->partials.as<double>());
+        proj_icp_tma_kernel<<<blocks, PT_TILE, smem, st>>>(pm.model_v.as<float>(), pm.model_n.as<float4>(), K,
+                                                           ctx->cfg.local_map_size, ctx->tmp[7].as<float4>(), fr, tile_begin,
+                                                           tile_end, ctx->cfg.scheme, ctx->cfg.sigma, stages,
+                                                           ctx->partials.as<double>());
         PLS_CHECK_LAUNCH();
         return blocks;
     }
@@ -601,7 +659,7 @@ int projmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int n
     ctx->partials.reserve((size_t)blocks * NACC * sizeof(double), st);
     {
         ProfileScope ps(ctx, 1, 0.0, false);
-        proj_icp_iter_kernel<<<blocks, PJ_THREADS, 0, st>>>(pm.model_v.as<float>(), pm.model_n.as<float>(), pm.K,
+        proj_icp_iter_kernel<<<blocks, PJ_THREADS, 0, st>>>(pm.model_v.as<float>(), pm.model_n.as<float4>(), pm.K,
                                                             ctx->cfg.local_map_size, zbuf,
                                                             ctx->query_ptr, fr, pix_begin, pix_end, ctx->cfg.scheme,
                                                             ctx->cfg.sigma, ctx->partials.as<double>());
@@ -685,7 +743,13 @@ int pls_projmap_model(pls_context* ctx, float* out_vmap, float* out_nmap) {
         finish_out(ctx, o);
     };
     put(out_vmap, ctx->pm.model_v.as<float>(), ctx->stage_out[0]);
-    put(out_nmap, ctx->pm.model_n.as<float>(), ctx->stage_out[1]);
+    if (out_nmap) {
+        OutArg o = out_arg(ctx, out_nmap, bytes, ctx->stage_out[1]);
+        normal_export_kernel<<<grid_for((int64_t)ctx->pm.K * hw, 256), 256, 0, ctx->stream>>>(ctx->pm.model_n.as<float4>(), ctx->pm.K,
+                                                                                           ctx->cfg.local_map_size, hw, (float*)o.dev);
+        PLS_CHECK_LAUNCH();
+        finish_out(ctx, o);
+    }
     PLS_CUDA(cudaStreamSynchronize(ctx->stream));
     PLS_API_END(ctx)
 }
@@ -713,7 +777,7 @@ int pls_projmap_nn_search(pls_context* ctx, const float* queries, int64_t n, flo
     ctx->tmp[1].reserve((size_t)hw, st);
     ctx->tmp[2].reserve((size_t)hw * sizeof(uint32_t), st);
     ctx->tmp[7].reserve((size_t)hw * 9 * sizeof(float), st);
-    proj_pairs_kernel<<<grid_for(hw, 256), 256, 0, st>>>(ctx->pm.model_v.as<float>(), ctx->pm.model_n.as<float>(), ctx->pm.K,
+    proj_pairs_kernel<<<grid_for(hw, 256), 256, 0, st>>>(ctx->pm.model_v.as<float>(), ctx->pm.model_n.as<float4>(), ctx->pm.K,
                                                           ctx->cfg.local_map_size, hw, zbuf, ctx->queries.as<float4>(), ctx->tmp[1].as<uint8_t>(),
                                                           ctx->tmp[7].as<float>());
     PLS_CHECK_LAUNCH();
