@@ -121,6 +121,7 @@ struct ProjMap {
     DBuf model_v, model_n;  // [Kmax][3][H][W] re-projected model
     DBuf zbuf;              // [Kmax][H][W] u64
     bool valid = false;
+    bool zbuf_clean = false; // the query z-buffer (tmp[3]) is known to be all-empty
 };
 
 struct FrameResult {        // mirrored to pinned host memory at the end of a frame

@@ -143,6 +143,7 @@ int run_icp(pls_context* ctx, const float* T0_dev, int64_t query_bound) {
     frame_begin_kernel<<<1, kMaxAlign, 0, st>>>(fr, T0_dev, ctx->cfg.max_num_alignments);
     PLS_CHECK_LAUNCH();
     if (query_bound < 1) query_bound = 1;
+    ctx->pm.zbuf_clean = false;  // tmp[3] may have been used by the frame's own projection
     ctx->nn_prev.reserve((size_t)query_bound * sizeof(int), st);
     PLS_CUDA(cudaMemsetAsync(ctx->nn_prev.p, 0xff, (size_t)query_bound * sizeof(int), st));
     const int rank = comm_rank(ctx), size = comm_size(ctx);

@@ -216,7 +216,7 @@ __global__ void query_zbuf_kernel(const float4* __restrict__ queries, const uint
 }
 
 // z-buffer winners -> the target vertex map of this iteration, float4 (p transformed, valid flag) per pixel
-__global__ void query_resolve_kernel(const unsigned long long* __restrict__ zbuf, const float4* __restrict__ queries,
+__global__ void query_resolve_kernel(unsigned long long* __restrict__ zbuf, const float4* __restrict__ queries,
                                      const float* __restrict__ T, const int* __restrict__ done, int64_t hw,
                                      float4* __restrict__ tgt) {
     if (done && *done) return;
@@ -224,6 +224,7 @@ __global__ void query_resolve_kernel(const unsigned long long* __restrict__ zbuf
     load_T(T, sT);
     for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < hw; pix += (int64_t)gridDim.x * blockDim.x) {
         const unsigned long long key = zbuf[pix];
+        zbuf[pix] = ~0ull;  // leave the z-buffer cleared for the next iteration (no separate memset)
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
         if (key != ~0ull) {
             const float4 p0 = queries[(uint32_t)(key & 0xffffffffull)];
@@ -402,22 +403,23 @@ proj_icp_tma_kernel(const float* __restrict__ model_v, const float4* __restrict_
             const int64_t nt = tile + (int64_t)stages * stride;
             if (nt < tile_end) issue(nt, s);
         }
-        // issue the winner-normal gather of THIS tile now; it is consumed one iteration later, after the next
-        // tile's arg-min, so its latency is hidden
-        float nn[3] = {0.f, 0.f, 0.f};
-        if (matched) {
-            const float4 mn = model_n[normal_off(pix, kbest, kcap)];
-            nn[0] = mn.x; nn[1] = mn.y; nn[2] = mn.z;
-        }
+        // software pipeline: first consume the PREVIOUS tile's correspondence (its normal gather was issued
+        // one iteration ago and has had this tile's wait + arg-min to land) ...
         if (pend) {
             float J[6];
             const float r = p2plane_residual_jacobian_identity(pp, pq, pn, J);
             const float w = ls_weight<float>(scheme, sigma, r, pp, pq);
             accumulate_normal_equations<float>(acc, J, w, r * w, r);
         }
+        // ... then issue THIS tile's winner-normal gather straight into the pending registers (no copy that
+        // would force the load to complete here)
         pend = matched;
+        if (matched) {
+            const float4 mn = model_n[normal_off(pix, kbest, kcap)];
+            pn[0] = mn.x; pn[1] = mn.y; pn[2] = mn.z;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { pp[c] = p[c]; pq[c] = q[c]; pn[c] = nn[c]; }
+            for (int c = 0; c < 3; ++c) { pp[c] = p[c]; pq[c] = q[c]; }
+        }
     }
     if (pend) {
         float J[6];
@@ -613,7 +615,9 @@ int projmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int n
     FrameResult* fr = frame_result_dev(ctx);
     ctx->tmp[3].reserve((size_t)hw * sizeof(unsigned long long), st);
     unsigned long long* zbuf = ctx->tmp[3].as<unsigned long long>();
-    PLS_CUDA(cudaMemsetAsync(zbuf, 0xff, (size_t)hw * sizeof(unsigned long long), st));
+    // the TMA path's resolve kernel leaves the z-buffer cleared, so only the first iteration of a frame memsets
+    if (!pm.zbuf_clean) PLS_CUDA(cudaMemsetAsync(zbuf, 0xff, (size_t)hw * sizeof(unsigned long long), st));
+    pm.zbuf_clean = false;
     ProjConst pc = make_proj_const(H, W, ctx->cfg.up_fov_deg, ctx->cfg.down_fov_deg);
     query_zbuf_kernel<<<grid_for(query_bound, 256), 256, 0, st>>>(
         ctx->query_ptr, reinterpret_cast<const uint32_t*>(&fr->counts[1]), 0, fr->T, &fr->done, pc, zbuf);
@@ -652,6 +656,7 @@ int projmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int n
                                                            tile_end, ctx->cfg.scheme, ctx->cfg.sigma, stages,
                                                            ctx->partials.as<double>());
         PLS_CHECK_LAUNCH();
+        pm.zbuf_clean = true;
         return blocks;
     }
     const int64_t pix_begin = hw * rank / num_ranks, pix_end = hw * (rank + 1) / num_ranks;
