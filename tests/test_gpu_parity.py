@@ -512,3 +512,128 @@ def test_icp_cfg3_projective_full_size_vs_reference_golden(b200, syn, golden_icp
     poses = _drive(algo, _frames(syn, b200.grid_sample, "vertex_map", 128, 2048, None, device="cuda"), len(ref) + 1, iters)
     flips, worst = check_pose_sequence(poses, iters, ref, golden_icp_full["cfg3_proj_losses"], name="cfg3_proj")
     print("cfg3", "flips", flips, "worst", worst)
+
+
+# ------------------------------------------------------------------------------ BASELINE configs 4 / 5, edge cases
+def test_cfg4_5M_point_map_exact_search(b200):
+    """BASELINE config 4: a 5M-point accumulated local map, one 64x2048 scan (131072 queries): exact 1-NN
+    against scipy's cKDTree (float64) and, sign-free, the 10-NN normals on a sample."""
+    from scipy.spatial import cKDTree
+    rng = np.random.RandomState(4)
+    M = 5_000_000
+    # surfaces (ground + walls) with noise, LiDAR-like density falling with range
+    r = rng.gamma(2.0, 12.0, M).astype(np.float32)
+    a = rng.uniform(-np.pi, np.pi, M).astype(np.float32)
+    ground = rng.rand(M) < 0.7
+    pts = np.stack([r * np.cos(a), r * np.sin(a), np.where(ground, -1.8 + 0.01 * rng.randn(M), rng.uniform(-1.8, 6, M))], 1).astype(np.float32)
+    lm = b200.KdTreeLocalMap(b200.KdTreeLocalMapConfig(local_map_size=2))
+    lm.init()
+    lm.update(np.eye(4, dtype=np.float32)[None], new_pc_data=pts)
+    assert lm.num_points() == M
+    q = pts[rng.choice(M, 131072, replace=False)] + (0.05 * rng.randn(131072, 3)).astype(np.float32)
+    res = lm.nearest_neighbor_search(q)
+    tree = cKDTree(pts.astype(np.float64))
+    d_ref, _ = tree.query(q.astype(np.float64), workers=-1)
+    d_mine = np.linalg.norm(q.astype(np.float64) - res.neighbor_points.astype(np.float64), axis=1)
+    np.testing.assert_allclose(d_mine, d_ref, rtol=1e-5, atol=1e-7)
+    # normals: compare 2000 of them with the numpy restatement
+    sel = rng.choice(131072, 2000, replace=False)
+    _, nb = tree.query(res.neighbor_points[sel].astype(np.float64), k=11, workers=-1)
+    d = pts[nb[:, 1:].reshape(-1)].reshape(-1, 10, 3) - res.neighbor_points[sel][:, None, :]
+    cov = (d[:, :, :, None] * d[:, :, None, :]).mean(axis=1)
+    _, _, vh = np.linalg.svd(cov)
+    dots = np.abs((vh[:, 2, :] * res.neighbor_normals[sel]).sum(-1))
+    assert np.mean(dots > 1 - 1e-3) > 0.98
+
+
+def test_cfg5_projective_128x4096_20_iterations(b200, orc, syn):
+    """BASELINE config 5 shape: 128x4096 vertex-map input, projective map, 20 alignments forced
+    (threshold_delta_pose = 0).  GPU vs the CPU oracle on identical frames.  Tolerance: strict on the first
+    registered frame; 3e-4 relative translation on the second (the reference's float32 normal maps amplify
+    1-ulp input noise to 8e-5 by then, see tests/test_gpu_parity.py::test_icp_projective_small...)."""
+    H, W = 128, 4096
+    algo = _make(b200, "projective", H, W, "vertex_map", 20, thr=0.0)
+    ocfg = orc.ICPConfig(max_num_alignments=20, data_key="vertex_map", local_map="projective", local_map_size=20,
+                         scheme="geman_mcclure", sigma=0.3, threshold_delta_pose=0.0)
+    torch.set_num_threads(1)   # deterministic closest-wins scatter in the oracle's index_put_
+    ref = orc.ICPFrameToModelOracle(ocfg, orc.Projector(H, W))
+    pa = pb = None
+    for k in range(3):
+        vm = torch.from_numpy(syn.vertex_map_from_scan(syn.scan(k, H, W), H, W))
+        da, db = {"vertex_map": vm.cuda(), "init_rpose": pa}, {"vertex_map": vm, "init_rpose": pb}
+        algo.process_next_frame(da)
+        ref.process_next_frame(db)
+        if k == 0:
+            continue
+        assert int(algo.last_info[0]) == 20
+        dt, ang = pose_errors(da["odometry_pose"], db["odometry_pose"])
+        assert dt <= (1e-4 if k == 1 else 3e-4) and ang <= 1e-5, (k, dt, ang)
+        pa, pb = da["odometry_pose"].astype(np.float64), db["odometry_pose"].astype(np.float64)
+
+
+def test_nan_rows_and_nan_pixels_match_oracle(b200, orc, syn):
+    """remove_nan / modify_nan_pmap (utils.py:169-196): NaN rows are dropped from the point layouts, NaN pixels
+    are zeroed in the vertex-map layout; poses follow the oracle fed with the same corrupted inputs."""
+    H, W = 32, 512
+    for layout, key in (("ndarray", "numpy_pc"), ("vertex_map", "vertex_map")):
+        lm = "kdtree" if layout == "ndarray" else "projective"
+        algo = _make(b200, lm, H, W, key, 8, lm_size=4, thr=0.0)
+        ref = orc.ICPFrameToModelOracle(orc.ICPConfig(max_num_alignments=8, data_key=key, local_map=lm, local_map_size=4,
+                                                      scheme="geman_mcclure", sigma=0.3, threshold_delta_pose=0.0), orc.Projector(H, W))
+        pa = pb = None
+        for k in range(3):
+            pc = syn.scan(k, H, W).copy()
+            pc[5::97] = np.nan
+            if layout == "ndarray":
+                pc, _ = orc.grid_sample(pc[~np.isnan(pc).any(1)], 0.4)
+                pc = pc.copy()
+                pc[3::41, 1] = np.nan
+                da, db = {"numpy_pc": pc.copy()}, {"numpy_pc": pc.copy()}
+            else:
+                vm = torch.from_numpy(syn.vertex_map_from_scan(pc, H, W))
+                da, db = {"vertex_map": vm.clone()}, {"vertex_map": vm.clone()}
+            da["init_rpose"], db["init_rpose"] = pa, pb
+            algo.process_next_frame(da)
+            ref.process_next_frame(db)
+            if k == 0:
+                continue
+            dt, ang = pose_errors(da["odometry_pose"], db["odometry_pose"])
+            assert dt <= 6e-4 and ang <= 1e-5, (layout, k, dt, ang)
+            if layout == "ndarray":
+                assert not np.isnan(da["odometry_pc"]).any()
+                assert da["odometry_pc"].shape == db["odometry_pc"].shape
+            pa, pb = da["odometry_pose"].astype(np.float64), db["odometry_pose"].astype(np.float64)
+
+
+def test_empty_and_degenerate_inputs(b200):
+    with pytest.raises(AssertionError):
+        b200.grid_sample(np.zeros((0, 3), np.float32), 0.3)
+    with pytest.raises(AssertionError):
+        b200.grid_sample(np.zeros((10, 2), np.float32), 0.3)
+    # all points in one voxel -> exactly one sample, index 0
+    s, i = b200.grid_sample(np.full((1000, 3), 0.01, np.float32), 0.3)
+    assert s.shape == (1, 3) and i.tolist() == [0]
+    # projection of points that all fall outside the image / are null -> all-zero map
+    proj = b200.SphericalProjector(height=8, width=64, up_fov=3.0, down_fov=-24.0)
+    up = np.tile(np.array([[0.0, 0.0, 5.0]], np.float32), (100, 1))      # straight up: outside the vertical FOV
+    assert np.all(proj.build_projection_map(np.concatenate([up, np.zeros((10, 3), np.float32)])[None]) == 0)
+    # a kd map searched before any update is a state error, not a crash
+    lm = b200.KdTreeLocalMap(b200.KdTreeLocalMapConfig())
+    lm.init()
+    with pytest.raises(RuntimeError):
+        lm.nearest_neighbor_search(np.zeros((4, 3), np.float32))
+    # first frame with an empty point cloud
+    algo = _make(b200, "kdtree", 16, 256, "numpy_pc", 4)
+    with pytest.raises(AssertionError):
+        algo.process_next_frame({"numpy_pc": np.zeros((0, 3), np.float32)})
+
+
+def test_odometry_reinit_is_clean(b200, syn):
+    """init() between sequences (slam.py:106) resets map, poses and frame counter."""
+    algo = _make(b200, "kdtree", 32, 512, "numpy_pc", 8, lm_size=4)
+    fr = _frames(syn, b200.grid_sample, "ndarray", 32, 512, 0.4)
+    a = _drive(algo, fr, 4)
+    algo.init()
+    b = _drive(algo, fr, 4)
+    np.testing.assert_array_equal(a, b)
+    assert algo.get_relative_poses().shape == (4, 4, 4)
