@@ -300,6 +300,11 @@ def b200_arm(args):
         return
 
     peak, peak_src = measured_peaks()
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_kd_traffic.json")))["traffic_bytes_per_launch"]
+    except Exception:
+        pass
     nn_ms, nn_launches, nn_bytes = prof_nn
     achieved = (nn_bytes / max(nn_launches, 1)) / (nn_ms / max(nn_launches, 1) * 1e-3) / 1e9 if nn_ms > 0 else 0.0
     frame_ms = ms_dev / K_
@@ -321,7 +326,7 @@ def b200_arm(args):
         "clocks": clock_info,
         "roofline": {"bound": "hbm", "kernel": "kd_icp_iter_kernel (exact 1-NN + lazy 10-NN normals + point-to-plane reduction)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                     "frac": achieved / peak if peak else None, "traffic": None,
+                     "frac": achieved / peak if peak else None, "traffic": traffic,
                      "launches": int(nn_launches), "avg_us": 1e3 * nn_ms / max(nn_launches, 1),
                      "algorithmic_bytes_per_launch": nn_bytes / max(nn_launches, 1),
                      "share_of_step": (nn_ms / K_) / frame_ms},
