@@ -136,19 +136,13 @@ inline int grid_for(int64_t n, int threads = 256) {
 
 uint32_t* count_slot(pls_context* ctx, int i) { return reinterpret_cast<uint32_t*>(&frame_result_dev(ctx)->counts[i]); }
 
-// The ICP loop (icp_odometry.py:248-299) over ctx->queries / counts[1].
-int run_icp(pls_context* ctx, const float* T0_dev, int64_t query_bound) {
+// Enqueues ICP iterations [first, last) (icp_odometry.py:274-297).
+int enqueue_icp_iterations(pls_context* ctx, int64_t query_bound, int first, int last) {
     cudaStream_t st = ctx->stream;
     FrameResult* fr = frame_result_dev(ctx);
-    frame_begin_kernel<<<1, kMaxAlign, 0, st>>>(fr, T0_dev, ctx->cfg.max_num_alignments);
-    PLS_CHECK_LAUNCH();
-    if (query_bound < 1) query_bound = 1;
-    ctx->pm.zbuf_clean = false;  // tmp[3] may have been used by the frame's own projection
-    ctx->nn_prev.reserve((size_t)query_bound * sizeof(int), st);
-    PLS_CUDA(cudaMemsetAsync(ctx->nn_prev.p, 0xff, (size_t)query_bound * sizeof(int), st));
     const int rank = comm_rank(ctx), size = comm_size(ctx);
     int last_blocks = 0;
-    for (int it = 0; it < ctx->cfg.max_num_alignments; ++it) {
+    for (int it = first; it < last; ++it) {
         int blocks;
         if (ctx->cfg.local_map_type == PLS_MAP_KDTREE) blocks = kdmap_icp_iteration(ctx, query_bound, rank, size);
         else blocks = projmap_icp_iteration(ctx, query_bound, rank, size);
@@ -163,6 +157,38 @@ int run_icp(pls_context* ctx, const float* T0_dev, int64_t query_bound) {
         PLS_CHECK_LAUNCH();
     }
     return last_blocks;
+}
+
+// The ICP loop (icp_odometry.py:248-299) over ctx->query_ptr / counts[1]: iterations are enqueued without
+// host syncs and turn into no-ops once the device-side `done` flag latches.  To avoid paying for
+// max_num_alignments launches when ICP converges in 2-3, only `previous frame's count + 2` iterations are
+// enqueued up front; the rare frame that needs more continues after the result fetch (same arithmetic,
+// one extra sync).  Returns the block count of the correspondence kernel.
+int run_icp(pls_context* ctx, const float* T0_dev, int64_t query_bound) {
+    cudaStream_t st = ctx->stream;
+    FrameResult* fr = frame_result_dev(ctx);
+    frame_begin_kernel<<<1, kMaxAlign, 0, st>>>(fr, T0_dev, ctx->cfg.max_num_alignments);
+    PLS_CHECK_LAUNCH();
+    if (query_bound < 1) query_bound = 1;
+    ctx->pm.zbuf_clean = false;  // tmp[3] may have been used by the frame's own projection
+    ctx->nn_prev.reserve((size_t)query_bound * sizeof(int), st);
+    PLS_CUDA(cudaMemsetAsync(ctx->nn_prev.p, 0xff, (size_t)query_bound * sizeof(int), st));
+    const int max_it = ctx->cfg.max_num_alignments;
+    int upfront = ctx->last_icp_iters > 0 ? ctx->last_icp_iters + 2 : max_it;
+    if (upfront > max_it) upfront = max_it;
+    int blocks = enqueue_icp_iterations(ctx, query_bound, 0, upfront);
+    int enq = upfront;
+    while (enq < max_it) {
+        // continue only if the device has not latched `done` (checked on the host: rare path)
+        int flags[3];
+        PLS_CUDA(cudaMemcpyAsync(flags, &fr->iters, sizeof(flags), cudaMemcpyDeviceToHost, st));
+        PLS_CUDA(cudaStreamSynchronize(st));
+        if (flags[2] /*done*/) break;
+        const int more = (max_it - enq) < 4 ? (max_it - enq) : 4;
+        blocks = enqueue_icp_iterations(ctx, query_bound, enq, enq + more);
+        enq += more;
+    }
+    return blocks;
 }
 
 void fetch_result(pls_context* ctx) {
@@ -297,6 +323,7 @@ void process_frame_device(pls_context* ctx, const float* data_dev, int layout, i
     const int icp_blocks = run_icp(ctx, T0_dev, query_bound);
     fetch_result(ctx);
     FrameResult* h = frame_result_host(ctx);
+    ctx->last_icp_iters = h->iters;
     credit_icp_profile(ctx, h, icp_blocks);
     raise_status(ctx, h->status);
 
@@ -339,6 +366,7 @@ void odometry_reset(pls_context* ctx) {
     kdmap_reset(ctx);
     projmap_reset(ctx);
     ctx->frame_index = 0;
+    ctx->last_icp_iters = 0;
     ctx->sample_pointcloud = 0;
     for (int i = 0; i < 16; ++i) ctx->delta_since_update[i] = (i % 5 == 0) ? 1.f : 0.f;
 }
