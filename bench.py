@@ -181,7 +181,7 @@ def b200_arm(args):
         algo.init()
         if world > 1:
             from pylidar_slam_b200.distributed import init_comm
-            init_comm(algo.ctx, dist, rank, world, dev)
+            init_comm(algo.ctx, dist, rank, world, dev, mode=args.comm)
         return algo
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -318,7 +318,7 @@ def b200_arm(args):
                          "value_l2_flushed_every_step re-measures with a 256 MiB flush INSIDE the bracket before every frame",
                    "value_l2_flushed_every_step": K_ / (ms_dev_flushed / 1e3),
                    "parallelism": "1 GPU" if world == 1 else f"queries sharded over {world} GPUs, map replicated, "
-                                                             f"one 30-double allreduce per ICP iteration",
+                                                             f"one 30-double all-reduce per ICP iteration ({args.comm})",
                    **stats},
         "e2e": {"value": K_ / t_e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d / K_), "d2h_bytes_per_step": int(d2h / K_),
                 "ms_per_step": 1e3 * t_e / K_},
@@ -353,6 +353,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true", help="device-resident pass only (for ncu captures)")
+    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1 exchange: one-shot NVLink peer-to-peer all-reduce fused into the solve kernel, or NCCL")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

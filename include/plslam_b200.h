@@ -213,6 +213,12 @@ PLS_API int pls_process_frame_grid_sample(pls_context* ctx, const float* raw_poi
 PLS_API int pls_comm_init(pls_context* ctx, int num_ranks, int rank, const void* nccl_unique_id,
                   const char* nccl_library);
 PLS_API int pls_comm_unique_id(const char* nccl_library, void* out_id_128_bytes);
+/* One-shot peer-to-peer mode (NVLink / NVSwitch peer memory, no NCCL on the data path): the all-reduce is
+ * fused into the solve kernel -- every rank stores its 30 partial sums and a sequence flag directly into each
+ * peer's exchange slots and sums the slots in rank order.  Step 1: each rank exports the 64-byte CUDA IPC
+ * handle of its exchange buffer; the host program all-gathers the handles; step 2 maps them. */
+PLS_API int pls_comm_p2p_handle(pls_context* ctx, int num_ranks, void* out_handle_64_bytes);
+PLS_API int pls_comm_p2p_init(pls_context* ctx, int num_ranks, int rank, const void* all_handles /* [num_ranks][64] */);
 PLS_API int pls_comm_destroy(pls_context* ctx);
 
 /* ---- measurement ---------------------------------------------------------------------

@@ -60,6 +60,8 @@ _SIGNATURES = {
     "pls_process_frame_grid_sample": [_P, _P, _L, _D, _I, _P, _P, _P, C.POINTER(_I), _P],
     "pls_comm_init": [_P, _I, _I, _P, C.c_char_p],
     "pls_comm_unique_id": [C.c_char_p, _P],
+    "pls_comm_p2p_handle": [_P, _I, _P],
+    "pls_comm_p2p_init": [_P, _I, _I, _P],
     "pls_comm_destroy": [_P],
     "pls_launch_count": [C.POINTER(_L)],
     "pls_profile_enable": [_P, _I, _I],

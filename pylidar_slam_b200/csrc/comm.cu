@@ -5,6 +5,8 @@
 // context's stream between the correspondence+reduction kernel and icp_step_kernel: no host sync.
 #include <dlfcn.h>
 
+#include <vector>
+
 #include "internal.cuh"
 
 namespace pls {
@@ -44,11 +46,23 @@ bool load_nccl(const char* path, NcclApi& api, std::string& err) {
 }
 }  // namespace
 
+constexpr size_t kP2PSlotBytes = 256;  // sizeof(P2PSlot): 30 doubles + seq + pad
+
 struct Comm {
     NcclApi api;
     ncclComm_t comm = nullptr;
     int rank = 0, size = 1;
+    // one-shot peer-to-peer mode
+    bool p2p = false;
+    void* xchg = nullptr;            // this rank's exchange buffer [2][size] slots (written by the peers)
+    std::vector<void*> peer_ptrs;    // every rank's exchange buffer mapped into this process (own = xchg)
+    void* peer_table_dev = nullptr;  // device copy of peer_ptrs
+    unsigned long long seq = 0;
 };
+
+bool comm_is_p2p(pls_context* ctx) { return ctx->comm && ctx->comm->p2p; }
+void* comm_p2p_peers(pls_context* ctx) { return ctx->comm->peer_table_dev; }
+unsigned long long comm_p2p_next_seq(pls_context* ctx) { return ++ctx->comm->seq; }
 
 int comm_rank(pls_context* ctx) { return ctx->comm ? ctx->comm->rank : 0; }
 int comm_size(pls_context* ctx) { return ctx->comm ? ctx->comm->size : 1; }
@@ -63,6 +77,11 @@ void comm_allreduce_sums(pls_context* ctx, double* sums_dev) {
 
 void comm_free(pls_context* ctx) {
     if (!ctx->comm) return;
+    if (ctx->comm->p2p) {
+        for (int r = 0; r < (int)ctx->comm->peer_ptrs.size(); ++r)
+            if (r != ctx->comm->rank && ctx->comm->peer_ptrs[r]) cudaIpcCloseMemHandle(ctx->comm->peer_ptrs[r]);
+        if (ctx->comm->peer_table_dev) cudaFree(ctx->comm->peer_table_dev);
+    }
     if (ctx->comm->comm) ctx->comm->api.CommDestroy(ctx->comm->comm);
     delete ctx->comm;
     ctx->comm = nullptr;
@@ -110,6 +129,59 @@ int pls_comm_init(pls_context* ctx, int num_ranks, int rank, const void* nccl_un
     }
     c->rank = rank;
     c->size = num_ranks;
+    ctx->comm = c;
+    PLS_API_END(ctx)
+}
+
+// ---- one-shot P2P mode: step 1, every rank allocates its exchange buffer and exports an IPC handle
+static void* g_p2p_pending_xchg = nullptr;  // handed from pls_comm_p2p_handle to pls_comm_p2p_init
+
+int pls_comm_p2p_handle(pls_context* ctx, int num_ranks, void* out_handle_64_bytes) {
+    PLS_API_BEGIN(ctx)
+    PLS_REQUIRE(num_ranks >= 2 && num_ranks <= 16 && out_handle_64_bytes, "pls_comm_p2p_handle: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* buf = nullptr;
+    const size_t bytes = 2 * (size_t)num_ranks * kP2PSlotBytes;
+    PLS_CUDA(cudaMalloc(&buf, bytes));
+    PLS_CUDA(cudaMemset(buf, 0, bytes));
+    cudaIpcMemHandle_t h;
+    PLS_CUDA(cudaIpcGetMemHandle(&h, buf));
+    memcpy(out_handle_64_bytes, &h, 64);
+    if (g_p2p_pending_xchg) cudaFree(g_p2p_pending_xchg);
+    g_p2p_pending_xchg = buf;
+    PLS_API_END(ctx)
+}
+
+// step 2 (after the host program all-gathered the handles): map every peer's buffer
+int pls_comm_p2p_init(pls_context* ctx, int num_ranks, int rank, const void* all_handles) {
+    PLS_API_BEGIN(ctx)
+    PLS_REQUIRE(num_ranks >= 2 && rank >= 0 && rank < num_ranks && all_handles && g_p2p_pending_xchg,
+                "pls_comm_p2p_init: call pls_comm_p2p_handle first");
+    sync_all(ctx);
+    comm_free(ctx);
+    Comm* c = new Comm();
+    c->p2p = true;
+    c->rank = rank;
+    c->size = num_ranks;
+    c->xchg = g_p2p_pending_xchg;
+    g_p2p_pending_xchg = nullptr;
+    c->peer_ptrs.assign(num_ranks, nullptr);
+    for (int r = 0; r < num_ranks; ++r) {
+        if (r == rank) {
+            c->peer_ptrs[r] = c->xchg;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)all_handles + 64 * (size_t)r, 64);
+        cudaError_t e = cudaIpcOpenMemHandle(&c->peer_ptrs[r], h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            std::string msg = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e);
+            delete c;
+            throw pls::Error{PLS_E_COMM, msg};
+        }
+    }
+    PLS_CUDA(cudaMalloc(&c->peer_table_dev, num_ranks * sizeof(void*)));
+    PLS_CUDA(cudaMemcpy(c->peer_table_dev, c->peer_ptrs.data(), num_ranks * sizeof(void*), cudaMemcpyHostToDevice));
     ctx->comm = c;
     PLS_API_END(ctx)
 }

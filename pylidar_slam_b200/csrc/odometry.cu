@@ -5,6 +5,8 @@
 // the pose composition with its Euler round trip (icp_odometry.py:296-297) run on the device
 // and latch a `done` flag that turns the remaining launches of the frame into no-ops.
 // One device->host copy of the FrameResult ends the frame.
+#include <stdlib.h>
+
 #include "internal.cuh"
 #include "pose_device.cuh"
 
@@ -15,6 +17,9 @@ int projmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int n
 // comm.cu
 int comm_rank(pls_context* ctx);
 int comm_size(pls_context* ctx);
+bool comm_is_p2p(pls_context* ctx);
+void* comm_p2p_peers(pls_context* ctx);
+unsigned long long comm_p2p_next_seq(pls_context* ctx);
 
 namespace {
 
@@ -54,20 +59,8 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(FrameResult* fr, c
     if (threadIdx.x < NACC) fr->last_sums[threadIdx.x] = sums[threadIdx.x];
 }
 
-// K7: normal-equation solve + ICP bookkeeping (256 threads).  num_blocks == 0: last_sums already holds
-// the (all-reduced) sums.
-__global__ void __launch_bounds__(256) icp_step_kernel(FrameResult* fr, const double* __restrict__ partials,
-                                                       int num_blocks, float threshold_delta) {
-    if (fr->done) return;
-    __shared__ double sums[NACC];
-    if (num_blocks > 0) {
-        sum_partials_256(partials, num_blocks, sums);
-    } else if (threadIdx.x < NACC) {
-        sums[threadIdx.x] = fr->last_sums[threadIdx.x];
-    }
-    __syncthreads();
-    if (num_blocks > 0 && threadIdx.x < NACC) fr->last_sums[threadIdx.x] = sums[threadIdx.x];
-    if (threadIdx.x != 0) return;
+// The serial tail of an ICP iteration (thread 0): Gauss-Newton guards, 6x6 solve, stop test, pose update.
+__device__ __forceinline__ void icp_solve_and_update(FrameResult* fr, const double* sums, float threshold_delta) {
     const int it = fr->iters;
     fr->iters = it + 1;
     // optimization.py:323-327: |r| < 1e-7 -> warning, x stays 0, residuals r^2; then delta = 0 breaks the loop
@@ -101,6 +94,85 @@ __global__ void __launch_bounds__(256) icp_step_kernel(FrameResult* fr, const do
     from_pose(Tn, prm);          // icp_odometry.py:296
     build_pose(prm, fr->T);      // icp_odometry.py:297
     for (int i = 0; i < 6; ++i) fr->params[i] = prm[i];
+}
+
+// K7: normal-equation solve + ICP bookkeeping (256 threads).  num_blocks == 0: last_sums already holds
+// the (all-reduced) sums.
+__global__ void __launch_bounds__(256) icp_step_kernel(FrameResult* fr, const double* __restrict__ partials,
+                                                       int num_blocks, float threshold_delta) {
+    if (fr->done) return;
+    __shared__ double sums[NACC];
+    if (num_blocks > 0) {
+        sum_partials_256(partials, num_blocks, sums);
+    } else if (threadIdx.x < NACC) {
+        sums[threadIdx.x] = fr->last_sums[threadIdx.x];
+    }
+    __syncthreads();
+    if (num_blocks > 0 && threadIdx.x < NACC) fr->last_sums[threadIdx.x] = sums[threadIdx.x];
+    if (threadIdx.x != 0) return;
+    icp_solve_and_update(fr, sums, threshold_delta);
+}
+
+// K9 fused: block-partial sum + ONE-SHOT all-reduce over NVLink peer memory + solve, in one kernel.
+// Every rank owns an exchange buffer mapped into all peers (CUDA IPC): slot[parity][r] is written by rank r.
+// A rank stores its 30 sums into slot[parity][me] of EVERY peer (plain stores to peer-mapped addresses), fences
+// system-wide, then stores the launch's sequence number; it then spins on its LOCAL slots until all peers'
+// sequence numbers arrived and adds the slots in rank order -- the same order on every rank, so all ranks
+// obtain bit-identical sums and hence bit-identical poses without any broadcast.  Two parities make the
+// overwrite of a slot wait for a full further round.  The spin is bounded: a peer that never shows up turns
+// into PLS_E_COMM instead of a hang.
+struct P2PSlot {
+    double sums[NACC];
+    unsigned long long seq;
+    unsigned long long pad;
+};
+static_assert(sizeof(P2PSlot) == 256, "P2PSlot must match comm.cu's kP2PSlotBytes");
+__global__ void __launch_bounds__(256)
+icp_step_p2p_kernel(FrameResult* fr, const double* __restrict__ partials, int num_blocks, float threshold_delta,
+                    P2PSlot* const* __restrict__ peers, int world, int rank, unsigned long long seq) {
+    if (fr->done) return;
+    __shared__ double sums[NACC];
+    __shared__ int timed_out;
+    if (threadIdx.x == 0) timed_out = 0;
+    sum_partials_256(partials, num_blocks, sums);
+    __syncthreads();
+    const int parity = (int)(seq & 1ull);
+    if (threadIdx.x < NACC)
+        for (int r = 0; r < world; ++r) peers[r][parity * world + rank].sums[threadIdx.x] = sums[threadIdx.x];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < world) {
+        volatile unsigned long long* flag = &peers[threadIdx.x][parity * world + rank].seq;
+        *flag = seq;
+    }
+    if (threadIdx.x < world) {
+        volatile unsigned long long* mine = &peers[rank][parity * world + threadIdx.x].seq;
+        const long long t0 = clock64();
+        while (*mine < seq) {
+            if (clock64() - t0 > 6000000000ll) {  // ~3 s: a peer is gone
+                timed_out = 1;
+                break;
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (timed_out) {
+        if (threadIdx.x == 0) {
+            fr->status = PLS_E_COMM;
+            fr->done = 1;
+        }
+        return;
+    }
+    if (threadIdx.x < NACC) {
+        double s = 0.0;
+        for (int r = 0; r < world; ++r) s += __ldcv(&peers[rank][parity * world + r].sums[threadIdx.x]);
+        sums[threadIdx.x] = s;
+        fr->last_sums[threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    icp_solve_and_update(fr, sums, threshold_delta);
 }
 
 __global__ void scrub_vertex_map_kernel(const float* __restrict__ in, int64_t hw, float* __restrict__ out) {
@@ -147,6 +219,12 @@ int enqueue_icp_iterations(pls_context* ctx, int64_t query_bound, int first, int
         if (ctx->cfg.local_map_type == PLS_MAP_KDTREE) blocks = kdmap_icp_iteration(ctx, query_bound, rank, size);
         else blocks = projmap_icp_iteration(ctx, query_bound, rank, size);
         last_blocks = blocks;
+        if (size > 1 && comm_is_p2p(ctx)) {
+            icp_step_p2p_kernel<<<1, 256, 0, st>>>(fr, ctx->partials.as<double>(), blocks, ctx->cfg.threshold_delta_pose,
+                                                   (P2PSlot* const*)comm_p2p_peers(ctx), size, rank, comm_p2p_next_seq(ctx));
+            PLS_CHECK_LAUNCH();
+            continue;
+        }
         if (size > 1) {
             reduce_partials_kernel<<<1, 256, 0, st>>>(fr, ctx->partials.as<double>(), blocks);
             PLS_CHECK_LAUNCH();
@@ -174,7 +252,8 @@ int run_icp(pls_context* ctx, const float* T0_dev, int64_t query_bound) {
     ctx->nn_prev.reserve((size_t)query_bound * sizeof(int), st);
     PLS_CUDA(cudaMemsetAsync(ctx->nn_prev.p, 0xff, (size_t)query_bound * sizeof(int), st));
     const int max_it = ctx->cfg.max_num_alignments;
-    int upfront = ctx->last_icp_iters > 0 ? ctx->last_icp_iters + 2 : max_it;
+    static const bool all_upfront = getenv("PLS_ICP_UPFRONT_ALL") != nullptr;
+    int upfront = (ctx->last_icp_iters > 0 && !all_upfront) ? ctx->last_icp_iters + 2 : max_it;
     if (upfront > max_it) upfront = max_it;
     int blocks = enqueue_icp_iterations(ctx, query_bound, 0, upfront);
     int enq = upfront;
@@ -212,6 +291,7 @@ void credit_icp_profile(pls_context* ctx, const FrameResult* h, int blocks) {
 }
 
 void raise_status(pls_context* ctx, int status) {
+    if (status == PLS_E_COMM) throw pls::Error{PLS_E_COMM, "peer-to-peer all-reduce timed out waiting for a peer rank"};
     if (status == PLS_E_SINGULAR) throw pls::Error{PLS_E_SINGULAR, "Invalid Jacobian in Gauss Newton minimization"};
 }
 

@@ -38,8 +38,22 @@ def broadcast_unique_id(make_id, dist, rank: int, device=None) -> bytes:
     return bytes(uid.cpu().tolist())
 
 
-def init_comm(ctx, dist, rank: int, world: int, device) -> None:
-    """Creates the library's NCCL communicator for `ctx` (collective over all ranks)."""
+def init_comm(ctx, dist, rank: int, world: int, device, mode: str = "p2p") -> None:
+    """Connects `ctx` to its peer ranks (collective over all ranks).
+
+    mode "p2p" : one-shot all-reduce over NVLink peer memory fused into the solve kernel (CUDA IPC handles
+                 all-gathered with torch.distributed); mode "nccl": ncclAllReduce on the library's stream."""
+    if mode == "p2p":
+        import torch
+        buf = (C.c_ubyte * 64)()
+        ctx.call("pls_comm_p2p_handle", world, buf)
+        mine = torch.tensor(list(buf), dtype=torch.uint8, device=device)
+        gathered = [torch.zeros(64, dtype=torch.uint8, device=device) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        raw = b"".join(bytes(t.cpu().tolist()) for t in gathered)
+        ctx.call("pls_comm_p2p_init", world, rank, raw)
+        dist.barrier()
+        return
     nccl_path = find_nccl().encode()
 
     def make_id():

@@ -14,6 +14,7 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 mode = sys.argv[1] if len(sys.argv) > 1 else "kdtree"
+comm_mode = sys.argv[2] if len(sys.argv) > 2 else "p2p"
 H, W, F = (64, 2048, 8) if mode == "kdtree" else (64, 1024, 6)
 
 
@@ -25,7 +26,7 @@ def make(with_comm):
     algo = b200.ICPFrameToModel(cfg, projector=b200.SphericalProjector(height=H, width=W, up_fov=3.0, down_fov=-24.0), device=dev)
     algo.init()
     if with_comm:
-        init_comm(algo.ctx, dist, rank, world, dev)
+        init_comm(algo.ctx, dist, rank, world, dev, mode=comm_mode)
     return algo
 
 
@@ -58,7 +59,7 @@ if rank == 0:
         ok = ok and same_across == 0.0          # every rank returns bit-identical poses
     dt = np.linalg.norm(sharded[:, :3, 3] - single[:, :3, 3], axis=1) / np.linalg.norm(single[:, :3, 3], axis=1)
     dr = np.abs(sharded[:, :3, :3] - single[:, :3, :3]).max()
-    print(f"[mgpu_check {mode} world={world}] identical across ranks: {ok}; vs 1 GPU: max rel dt {dt.max():.2e}, max |dR| {dr:.2e}")
+    print(f"[mgpu_check {mode} {comm_mode} world={world}] identical across ranks: {ok}; vs 1 GPU: max rel dt {dt.max():.2e}, max |dR| {dr:.2e}")
     ok = ok and dt.max() <= 1e-4 and dr <= 1e-5
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.broadcast(flag, 0)
