@@ -246,8 +246,14 @@ def b200_arm(args):
     ms_dev, launches, _, stats, _ = device_pass()
     clock_info = clocks.stop()
     if args.quick:
+        if world > 1:
+            t = torch.tensor([ms_dev], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_dev = float(t[0])
+            dist.destroy_process_group()
         if rank == 0:
-            print(json.dumps({"quick": True, "ms_per_step": ms_dev / K_, "gpu_launches": launches, **stats}))
+            print(json.dumps({"quick": True, "n_gpus": world, "comm": args.comm if world > 1 else None,
+                              "ms_per_step": ms_dev / K_, "gpu_launches": launches, **stats}))
         return
     ms_dev_flushed, _, _, _, _ = device_pass(flush_each_step=True)
     # roofline passes: same frames with CUDA events around one kernel family inside the library
