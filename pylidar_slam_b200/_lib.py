@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libplslam_b200.so")
+LIB_PATH = os.environ.get("PLS_LIB_PATH", os.path.join(_HERE, "libplslam_b200.so"))  # override: development A/B builds
 
 PLS_OK, PLS_E_INVALID, PLS_E_CUDA, PLS_E_SINGULAR, PLS_W_TINY_RESIDUAL, PLS_E_STATE, PLS_E_COMM = range(7)
 SCHEMES = {"default": 0, "least_square": 1, "huber": 2, "exp": 3, "neighborhood": 4, "geman_mcclure": 5,

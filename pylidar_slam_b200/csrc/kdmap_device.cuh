@@ -17,7 +17,10 @@
 
 namespace pls {
 
-constexpr int KD_LEAF = 8;
+#ifndef PLS_KD_LEAF
+#define PLS_KD_LEAF 8
+#endif
+constexpr int KD_LEAF = PLS_KD_LEAF;  // treelet size: subtrees of <= KD_LEAF points are scanned linearly
 constexpr int KD_STACK = 96;
 constexpr int KD_KMAX = 32;  // k + 1 <= 32
 

@@ -332,12 +332,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __global__ void __launch_bounds__(PT_TILE)
 proj_icp_tma_kernel(const float* __restrict__ model_v, const float4* __restrict__ model_n, int K, int kcap,
                     const float4* __restrict__ tgt, const FrameResult* __restrict__ fr, int64_t tile_begin, int64_t tile_end, int scheme, float sigma,
-                    int stages, double* __restrict__ partials) {
+                    int stages, int ktma, double* __restrict__ partials) {
     if (fr->done) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[PT_STAGES];
     float* stage_base = reinterpret_cast<float*>(smem_raw);
-    const int rows = K * 3;
+    // candidates [0, ktma) are staged through shared memory by the TMA engine; candidates [ktma, K) are read by
+    // the consumers themselves with coalesced loads (the tile-interleaved rows are 512 contiguous bytes), issued
+    // BEFORE the mbarrier wait: the LSU path and the TMA path pull from HBM concurrently
+    const int rows = ktma * 3;
     const uint32_t model_bytes = (uint32_t)rows * PT_TILE * sizeof(float);
     const uint32_t stage_floats = (uint32_t)(rows + 4) * PT_TILE;  // + the tile of the target vertex map (float4 per pixel)
     const uint32_t stage_bytes = stage_floats * sizeof(float);
@@ -373,6 +376,14 @@ proj_icp_tma_kernel(const float* __restrict__ model_v, const float4* __restrict_
         const int s = it % stages;
         const uint32_t parity = (uint32_t)((it / stages) & 1);
         const int64_t pix = tile * PT_TILE + threadIdx.x;
+        constexpr int KDIRECT_MAX = 10;
+        float dv[3 * KDIRECT_MAX];
+        {
+            const float* g = model_v + (size_t)tile * ((size_t)kcap * 3 * PT_TILE) + (size_t)ktma * 3 * PT_TILE + threadIdx.x;
+#pragma unroll
+            for (int j = 0; j < 3 * KDIRECT_MAX; ++j)
+                dv[j] = (j < (K - ktma) * 3) ? __ldg(g + (size_t)j * PT_TILE) : 0.f;
+        }
         mbar_wait(&full_bar[s], parity);
         bool matched = false;
         float q[3] = {0.f, 0.f, 0.f};
@@ -384,7 +395,7 @@ proj_icp_tma_kernel(const float* __restrict__ model_v, const float4* __restrict_
             const float* st = stage_base + (size_t)s * stage_floats + threadIdx.x;
             float best = __int_as_float(0x7f800000);
 #pragma unroll 4
-            for (int k = 0; k < K; ++k) {
+            for (int k = 0; k < ktma; ++k) {
                 const float x = st[(3 * k) * PT_TILE], y = st[(3 * k + 1) * PT_TILE], z = st[(3 * k + 2) * PT_TILE];
                 if (fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) > 0.f) {
                     const float dx = p[0] - x, dy = p[1] - y, dz = p[2] - z;
@@ -393,6 +404,21 @@ proj_icp_tma_kernel(const float* __restrict__ model_v, const float4* __restrict_
                         best = d;
                         kbest = k;
                         q[0] = x; q[1] = y; q[2] = z;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < KDIRECT_MAX; ++j) {
+                if (j < K - ktma) {
+                    const float x = dv[3 * j], y = dv[3 * j + 1], z = dv[3 * j + 2];
+                    if (fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) > 0.f) {
+                        const float dx = p[0] - x, dy = p[1] - y, dz = p[2] - z;
+                        const float d = sqrtf(dx * dx + dy * dy + dz * dz);
+                        if (d < best) {
+                            best = d;
+                            kbest = ktma + j;
+                            q[0] = x; q[1] = y; q[2] = z;
+                        }
                     }
                 }
             }
@@ -623,7 +649,12 @@ int projmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int n
         ctx->query_ptr, reinterpret_cast<const uint32_t*>(&fr->counts[1]), 0, fr->T, &fr->done, pc, zbuf);
     PLS_CHECK_LAUNCH();
     const int K = pm.K;
-    const size_t stage_bytes = (size_t)(K * 3 + 4) * PT_TILE * sizeof(float);
+    // split of the K candidates between the TMA path and the direct-load path (at most 10 direct)
+    static const int kdirect_env = getenv("PLS_PROJ_KDIRECT") ? atoi(getenv("PLS_PROJ_KDIRECT")) : 4;
+    int kdirect = kdirect_env < 0 ? 0 : (kdirect_env > 10 ? 10 : kdirect_env);
+    if (kdirect > K - 1) kdirect = K > 1 ? K - 1 : 0;
+    const int ktma = K - kdirect;
+    const size_t stage_bytes = (size_t)(ktma * 3 + 4) * PT_TILE * sizeof(float);
     static const bool no_tma = getenv("PLS_PROJ_NO_TMA") != nullptr;
     static const int stages = getenv("PLS_PROJ_STAGES") ? atoi(getenv("PLS_PROJ_STAGES")) : 2;
     int blocks;
@@ -653,7 +684,7 @@ int projmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int n
         ProfileScope ps(ctx, 1, 0.0, false);
         proj_icp_tma_kernel<<<blocks, PT_TILE, smem, st>>>(pm.model_v.as<float>(), pm.model_n.as<float4>(), K,
                                                            ctx->cfg.local_map_size, ctx->tmp[7].as<float4>(), fr, tile_begin,
-                                                           tile_end, ctx->cfg.scheme, ctx->cfg.sigma, stages,
+                                                           tile_end, ctx->cfg.scheme, ctx->cfg.sigma, stages, ktma,
                                                            ctx->partials.as<double>());
         PLS_CHECK_LAUNCH();
         pm.zbuf_clean = true;
