@@ -1,0 +1,91 @@
+// Device-side tail of an ICP iteration, shared by the stand-alone step kernels (odometry.cu) and the
+// correspondence kernels that finish the iteration in their last block (kdmap.cu).
+#pragma once
+#include "internal.cuh"
+#include "pose_device.cuh"
+
+namespace pls {
+
+// Deterministic parallel sum of the block partial rows (256 threads, all must call): warp w sums the rows
+// w, w+8, ... of every accumulator (lane = accumulator, so a row is one coalesced 240-byte read and the loads
+// of a lane are independent), then the eight slices are added in fixed order.
+__device__ __forceinline__ void sum_partials_256(const double* __restrict__ partials, int num_blocks, double* sums) {
+    __shared__ double slice_sum[8][NACC];
+    const int slice = threadIdx.x >> 5, a = threadIdx.x & 31;
+    if (a < NACC) {
+        double s = 0.0;
+#pragma unroll 4
+        for (int b = slice; b < num_blocks; b += 8) s += __ldcg(partials + (size_t)b * NACC + a);
+        slice_sum[slice][a] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NACC) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += slice_sum[k][threadIdx.x];
+        sums[threadIdx.x] = s;
+    }
+}
+
+// The serial tail of an ICP iteration (thread 0): Gauss-Newton guards, 6x6 solve, stop test, pose update.
+__device__ __forceinline__ void icp_solve_and_update(FrameResult* fr, const double* sums, float threshold_delta) {
+    const int it = fr->iters;
+    fr->iters = it + 1;
+    // optimization.py:323-327: |r| < 1e-7 -> warning, x stays 0, residuals r^2; then delta = 0 breaks the loop
+    if (sqrt(sums[28]) < 1e-7) {
+        fr->losses[it] = (float)sums[28];
+        fr->status = PLS_W_TINY_RESIDUAL;
+        fr->done = 1;
+        return;
+    }
+    double dx[6];
+    const double det = solve6(sums, dx);
+    if (!(fabs(det) >= 1e-7)) {  // optimization.py:334-336
+        fr->status = PLS_E_SINGULAR;
+        fr->done = 1;
+        return;
+    }
+    fr->losses[it] = (float)sums[27];
+    float delta[6];
+    float n2 = 0.f;
+    for (int i = 0; i < 6; ++i) {
+        delta[i] = (float)dx[i];
+        n2 += delta[i] * delta[i];
+    }
+    if (sqrtf(n2) < threshold_delta) {  // icp_odometry.py:292-293: the last delta is not applied
+        fr->done = 1;
+        return;
+    }
+    float dT[16], Tn[16], prm[6];
+    build_pose(delta, dT);
+    mat4_mul(dT, fr->T, Tn);
+    from_pose(Tn, prm);          // icp_odometry.py:296
+    build_pose(prm, fr->T);      // icp_odometry.py:297
+    for (int i = 0; i < 6; ++i) fr->params[i] = prm[i];
+}
+
+// Called by every block of a 256-thread correspondence kernel after it stored its partial row: the block
+// that arrives last (ticket in fr->pad) sums all rows in the fixed order and runs the solve -- one launch
+// and one dependent-launch gap less per ICP iteration than a separate step kernel.
+__device__ __forceinline__ void icp_finish_in_last_block(FrameResult* fr, const double* __restrict__ partials,
+                                                         float threshold_delta) {
+    __shared__ int s_last;
+    __shared__ double s_sums[NACC];
+    __threadfence();  // this block's partial row is visible before its ticket
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int ticket = atomicAdd(&fr->pad, 1);
+        s_last = ticket == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    sum_partials_256(partials, (int)gridDim.x, s_sums);
+    __syncthreads();
+    if (threadIdx.x < NACC) fr->last_sums[threadIdx.x] = s_sums[threadIdx.x];
+    if (threadIdx.x != 0) return;
+    fr->pad = 0;
+    icp_solve_and_update(fr, s_sums, threshold_delta);
+}
+
+}  // namespace pls

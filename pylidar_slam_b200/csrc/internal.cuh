@@ -102,6 +102,7 @@ struct KdMap {
     DBuf nodes;             // 64-byte BVH nodes
     DBuf parent, visit;     // build-time parents (internal then leaves), arrival counters
     DBuf bbox;              // 6 ordered-int words
+    bool bbox_clean = false; // the header kernel of the last build left the box empty
     DBuf inv_order;         // sorted position of each stored point (for out_idx)
     DBuf grid_hdr;          // KdGridHeader (quantisation + cell levels)
     DBuf cells;             // cell hash tables of all levels
@@ -311,7 +312,10 @@ void kdmap_update(pls_context* ctx, const float* rel_pose_host, const float* pts
 void kdmap_update_packed(pls_context* ctx, const float* rel_pose_host, const float4* fresh_dev, int64_t num_new,
                          bool has_new);
 // one fused ICP iteration over ctx->queries; returns the number of partial rows written
-int kdmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int num_ranks);
+// first: iteration 0 of a frame (no previous matches); fuse_threshold >= 0: finish the iteration (sum + solve + pose
+// update) in the last block of the reduction kernel when the variant supports it (*solved tells).
+int kdmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int num_ranks, bool first, float fuse_threshold,
+                        bool* solved);
 // pack [n,3] rows without NaN into float4 (stable); count -> *count_dev (u32)
 void pack_valid_rows(pls_context* ctx, const float* pts_dev, int64_t n, float4* out, uint32_t* count_dev);
 // pack the non-null pixels (any channel != 0) of a [3,H,W] map into float4, row-major order

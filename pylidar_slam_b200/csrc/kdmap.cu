@@ -17,8 +17,9 @@
 
 #include "gn_device.cuh"
 #include "internal.cuh"
+#include "icp_device.cuh"
 #include "kdmap_device.cuh"
-#include "kdmap_warp.cuh"
+#include "kdmap_group.cuh"
 #include "pose_device.cuh"
 
 namespace pls {
@@ -124,16 +125,17 @@ __device__ __forceinline__ uint64_t spread3(uint64_t x) {
     return x;
 }
 
-// Quantisation of the map: 256 Morton units per metre (3.9 mm) when the map extent allows it (<= 255 m),
-// else the 16-bit range is stretched over the extent.  Level-0 cells are 2^b0 units with a side in
+// Quantisation of the map: 256 Morton units per metre (3.9 mm) when the map extent allows it (<= 32 m),
+// else the KD_COORD_BITS-bit range is stretched over the extent (13 bits per axis = 39-bit keys = five 8-bit
+// sort passes; the unit stays far below the cell side, and points sharing a unit are ordered by index).  Level-0 cells are 2^b0 units with a side in
 // [KD_CELL_TARGET, 2 KD_CELL_TARGET).
-__global__ void kd_grid_header_kernel(const int* __restrict__ bbox, KdGridHeader* __restrict__ hdr, float cell_target) {
+__global__ void kd_grid_header_kernel(int* __restrict__ bbox, KdGridHeader* __restrict__ hdr, float cell_target) {
     if (threadIdx.x != 0) return;
     const float mnx = ordered_to_float(bbox[0]), mny = ordered_to_float(bbox[1]), mnz = ordered_to_float(bbox[2]);
     const float ex = ordered_to_float(bbox[3]) - mnx, ey = ordered_to_float(bbox[4]) - mny,
                 ez = ordered_to_float(bbox[5]) - mnz;
     const float ext = fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-6f));
-    const float scale = fminf(256.0f, 65535.0f / ext);
+    const float scale = fminf(256.0f, (float)KD_COORD_MAX / ext);
     int b0 = 0;
     while (b0 < 12 && (float)(1 << b0) < cell_target * scale) ++b0;
     hdr->mn[0] = mnx; hdr->mn[1] = mny; hdr->mn[2] = mnz;
@@ -141,6 +143,9 @@ __global__ void kd_grid_header_kernel(const int* __restrict__ bbox, KdGridHeader
     hdr->b0 = b0;
     hdr->cell0 = (float)(1 << b0) / scale;
     for (int l = 0; l < KD_LEVELS; ++l) hdr->overflow[l] = 0;
+    // leave the box empty for the next update (saves that update an init launch)
+    bbox[0] = bbox[1] = bbox[2] = 0x7fffffff;
+    bbox[3] = bbox[4] = bbox[5] = (int)0x80000000;
 }
 
 __global__ void kd_morton_kernel(const float4* __restrict__ pts, int64_t n, const KdGridHeader* __restrict__ hdr,
@@ -149,9 +154,9 @@ __global__ void kd_morton_kernel(const float4* __restrict__ pts, int64_t n, cons
     const float scale = hdr->scale;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float4 p = pts[i];
-        uint32_t qx = (uint32_t)fminf(fmaxf((p.x - mnx) * scale, 0.f), 65535.f);
-        uint32_t qy = (uint32_t)fminf(fmaxf((p.y - mny) * scale, 0.f), 65535.f);
-        uint32_t qz = (uint32_t)fminf(fmaxf((p.z - mnz) * scale, 0.f), 65535.f);
+        uint32_t qx = (uint32_t)fminf(fmaxf((p.x - mnx) * scale, 0.f), (float)KD_COORD_MAX);
+        uint32_t qy = (uint32_t)fminf(fmaxf((p.y - mny) * scale, 0.f), (float)KD_COORD_MAX);
+        uint32_t qz = (uint32_t)fminf(fmaxf((p.z - mnz) * scale, 0.f), (float)KD_COORD_MAX);
         keys[i] = spread3(qx) | (spread3(qy) << 1) | (spread3(qz) << 2);
         vals[i] = (uint32_t)i;
     }
@@ -289,8 +294,10 @@ __global__ void kd_boxes_kernel(const float4* __restrict__ sorted, int n, const 
             const int4 pr = ranges[cur];
             if (pr.z - pr.x + 1 <= KD_LEAF) continue;  // inside a treelet: nothing to do
         }
+        bool wrote = false;  // a thread arriving from a treelet has published nothing yet: no fence needed
         while (cur >= 0) {
-            __threadfence();
+            if (wrote) __threadfence();
+            wrote = true;
             if (atomicAdd(&visit[cur], 1) == 0) break;  // first arrival: the sibling subtree is not done
             const int4 rg = ranges[cur];
             float lmn[3], lmx[3], rmn[3], rmx[3];
@@ -370,42 +377,77 @@ __global__ void kd_export_kernel(const float4* __restrict__ pts, int64_t n, floa
     }
 }
 
-constexpr int KD_WARP_THREADS = 256;
+constexpr int KD_GROUP_THREADS = 128;
 
-// One ICP iteration on the kd map, ONE WARP PER QUERY (see kdmap_warp.cuh): transform, exact 1-NN, lazily
-// cached 10-NN normal, point-to-plane residual / J = [n, p x n] / robust weight.  The 30 normal-equation
-// accumulators are distributed over the lanes (lane a owns accumulator a: its term is v[ia] * v[ib] with
-// v = (wJ_0..5, w r, r, 1)), so the epilogue is one shared-memory pass instead of 30 shuffle trees.
-__global__ void __launch_bounds__(KD_WARP_THREADS)
-kd_icp_warp_kernel(KdIndex ix, const float4* __restrict__ queries, const uint32_t* __restrict__ nq_dev, int64_t q_begin,
-                   int64_t q_stride, const FrameResult* __restrict__ fr, int scheme, float sigma,
-                   int* __restrict__ nn_prev, double* __restrict__ partials) {
+// The same ICP iteration as kd_icp_iter_kernel, split in three launches so that the two searches can run
+// with G lanes per query (kdmap_group.cuh) at full residency and the reduction stays thread-per-query:
+//   kd_nn_group_kernel      p = T p0, exact 1-NN -> nn_prev[qi]
+//   kd_normals_group_kernel lazily cached 10-NN normal of every matched map point that has none yet
+//   kd_residual_kernel      r, J = [n, p x n], robust weight, the 30 fp64 accumulators -> block partials
+template <int G>
+__global__ void __launch_bounds__(KD_GROUP_THREADS, 8)
+kd_nn_group_kernel(KdIndex ix, const float4* __restrict__ queries, const uint32_t* __restrict__ nq_dev, int64_t q_begin,
+                   int64_t q_stride, const FrameResult* __restrict__ fr, int* __restrict__ nn_prev, int first) {
     if (fr->done) return;
     __shared__ float sT[12];
-    __shared__ double red[KD_WARP_THREADS / 32][32];
     if (threadIdx.x < 12) sT[threadIdx.x] = fr->T[threadIdx.x];
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // operand selectors of this lane's accumulator
-    int ia = 8, ib = 8;
-    if (lane < 21) {
-        int k = 0;
-        for (int a = 0; a < 6; ++a)
-            for (int b = a; b < 6; ++b) {
-                if (k == lane) { ia = a; ib = b; }
-                ++k;
-            }
-    } else if (lane < 27) {
-        ia = lane - 21; ib = 6;
-    } else if (lane == 27) {
-        ia = 6; ib = 6;
-    } else if (lane == 28) {
-        ia = 7; ib = 7;
-    }
+    const LaneGroup<G> lg;
     const int64_t nq = (int64_t)*nq_dev;
-    double acc = 0.0;
-    const int64_t warps_total = (int64_t)gridDim.x * (KD_WARP_THREADS / 32);
-    for (int64_t s = (int64_t)blockIdx.x * (KD_WARP_THREADS / 32) + warp;; s += warps_total) {
+    const int64_t groups_total = (int64_t)gridDim.x * (KD_GROUP_THREADS / G);
+    for (int64_t s = ((int64_t)blockIdx.x * KD_GROUP_THREADS + threadIdx.x) / G;; s += groups_total) {
+        const int64_t qi = q_begin + s * q_stride;
+        if (qi >= nq) break;
+        const float4 p0 = queries[qi];
+        const float px = p0.x * sT[0] + p0.y * sT[1] + p0.z * sT[2] + sT[3];
+        const float py = p0.x * sT[4] + p0.y * sT[5] + p0.z * sT[6] + sT[7];
+        const float pz = p0.x * sT[8] + p0.y * sT[9] + p0.z * sT[10] + sT[11];
+        const int hint = (lg.sub == 0 && !first) ? nn_prev[qi] : -1;
+        const int pos = group_nearest<G>(ix, lg, px, py, pz, hint);
+        if (lg.sub == 0) nn_prev[qi] = pos;
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(KD_GROUP_THREADS)
+kd_normals_group_kernel(KdIndex ix, int k_normals, const uint32_t* __restrict__ nq_dev, int64_t q_begin, int64_t q_stride,
+                        const FrameResult* __restrict__ fr, const int* __restrict__ nn_prev) {
+    if (fr->done) return;
+    const LaneGroup<G> lg;
+    const int64_t nq = (int64_t)*nq_dev;
+    const int64_t groups_total = (int64_t)gridDim.x * (KD_GROUP_THREADS / G);
+    for (int64_t s = ((int64_t)blockIdx.x * KD_GROUP_THREADS + threadIdx.x) / G;; s += groups_total) {
+        const int64_t qi = q_begin + s * q_stride;
+        if (qi >= nq) break;
+        const int pos = nn_prev[qi];
+        // one lane decides for the group (another group may publish the same normal concurrently)
+        const float valid = lg.bcast(lg.sub == 0 ? __ldcg(ix.normals + pos).w : 0.f);
+        if (valid != 0.f) continue;
+        float nn[3];
+        if (k_normals == 10) {
+            group_point_normal_k10<G>(ix, lg, pos, nn);
+        } else if (lg.sub == 0) {
+            kd_point_normal(ix, pos, k_normals, nn);
+        }
+        if (lg.sub == 0) __stcg(ix.normals + pos, make_float4(nn[0], nn[1], nn[2], 1.f));
+    }
+}
+
+constexpr int KD_RES_THREADS = 256;
+
+__global__ void __launch_bounds__(KD_RES_THREADS)
+kd_residual_kernel(KdIndex ix, const float4* __restrict__ queries, const uint32_t* __restrict__ nq_dev, int64_t q_begin,
+                   int64_t q_stride, FrameResult* fr, int scheme, float sigma,
+                   const int* __restrict__ nn_prev, double* __restrict__ partials, float fuse_threshold) {
+    if (fr->done) return;
+    __shared__ float sT[12];
+    if (threadIdx.x < 12) sT[threadIdx.x] = fr->T[threadIdx.x];
+    __syncthreads();
+    const int64_t nq = (int64_t)*nq_dev;
+    double acc[NACC];
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;; s += (int64_t)gridDim.x * blockDim.x) {
         const int64_t qi = q_begin + s * q_stride;
         if (qi >= nq) break;
         const float4 p0 = queries[qi];
@@ -413,41 +455,40 @@ kd_icp_warp_kernel(KdIndex ix, const float4* __restrict__ queries, const uint32_
         p[0] = p0.x * sT[0] + p0.y * sT[1] + p0.z * sT[2] + sT[3];
         p[1] = p0.x * sT[4] + p0.y * sT[5] + p0.z * sT[6] + sT[7];
         p[2] = p0.x * sT[8] + p0.y * sT[9] + p0.z * sT[10] + sT[11];
-        const int pos = warp_nearest(ix, p[0], p[1], p[2], nn_prev[qi]);
-        if (lane == 0) nn_prev[qi] = pos;
+        const int pos = nn_prev[qi];
         const float4 qq = __ldg(ix.sorted + pos);
+        const float4 nv = __ldcg(ix.normals + pos);
         float q[3] = {qq.x, qq.y, qq.z};
-        float nn[3];
-        const float4 cached = __ldcg(ix.normals + pos);
-        if (cached.w == 0.f) {
-            warp_point_normal_k10(ix, pos, nn);
-            if (lane == 0) __stcg(ix.normals + pos, make_float4(nn[0], nn[1], nn[2], 1.f));
-        } else {
-            nn[0] = cached.x; nn[1] = cached.y; nn[2] = cached.z;
-        }
+        float nn[3] = {nv.x, nv.y, nv.z};
         float J[6];
         const float r = p2plane_residual_jacobian_identity(p, q, nn, J);
         const float w = ls_weight<float>(scheme, sigma, r, p, q);
-        const float wr = r * w;
-        // v_m lives in lane m (m < 9); the lane's term is v[ia] * v[ib]
-        double v = 1.0;
-#pragma unroll
-        for (int m = 0; m < 6; ++m)
-            if (lane == m) v = (double)(J[m] * w);
-        if (lane == 6) v = (double)wr;
-        if (lane == 7) v = (double)r;
-        const double va = __shfl_sync(FULL, v, ia);
-        const double vb = __shfl_sync(FULL, v, ib);
-        acc += va * vb;
+        accumulate_normal_equations<float>(acc, J, w, r * w, r);
     }
-    red[warp][lane] = acc;
-    __syncthreads();
-    if (threadIdx.x < NACC) {
-        double sum = 0.0;
-#pragma unroll
-        for (int wq = 0; wq < KD_WARP_THREADS / 32; ++wq) sum += red[wq][threadIdx.x];
-        partials[(size_t)blockIdx.x * NACC + threadIdx.x] = sum;
-    }
+    block_reduce_store<KD_RES_THREADS>(acc, partials + (size_t)blockIdx.x * NACC);
+    if (fuse_threshold >= 0.f) icp_finish_in_last_block(fr, partials, fuse_threshold);
+}
+
+template <int G>
+int launch_group_iteration(pls_context* ctx, const KdIndex& ix, int64_t mine, const uint32_t* nq_dev, int rank, int num_ranks,
+                           bool first, float fuse_threshold) {
+    cudaStream_t st = ctx->stream;
+    const int gblocks = grid_for(mine * G, KD_GROUP_THREADS, 16 * kNumSMs);
+    int* nn_prev = ctx->nn_prev.as<int>();
+    FrameResult* fr = frame_result_dev(ctx);
+    kd_nn_group_kernel<G><<<gblocks, KD_GROUP_THREADS, 0, st>>>(ix, ctx->query_ptr, nq_dev, (int64_t)rank,
+                                                                (int64_t)num_ranks, fr, nn_prev, first ? 1 : 0);
+    PLS_CHECK_LAUNCH();
+    kd_normals_group_kernel<G><<<gblocks, KD_GROUP_THREADS, 0, st>>>(ix, ctx->cfg.num_neighbors_normals, nq_dev,
+                                                                     (int64_t)rank, (int64_t)num_ranks, fr, nn_prev);
+    PLS_CHECK_LAUNCH();
+    const int blocks = grid_for(mine, KD_RES_THREADS, 8 * kNumSMs);
+    ctx->partials.reserve((size_t)blocks * NACC * sizeof(double), st);
+    kd_residual_kernel<<<blocks, KD_RES_THREADS, 0, st>>>(ix, ctx->query_ptr, nq_dev, (int64_t)rank, (int64_t)num_ranks, fr,
+                                                          ctx->cfg.scheme, ctx->cfg.sigma, nn_prev,
+                                                          ctx->partials.as<double>(), fuse_threshold);
+    PLS_CHECK_LAUNCH();
+    return blocks;
 }
 
 KdIndex make_index(pls_context* ctx) {
@@ -488,12 +529,13 @@ void build_index(pls_context* ctx) {
     static const float cell_target = getenv("PLS_KD_CELL") ? (float)atof(getenv("PLS_KD_CELL")) : KD_CELL_TARGET;
     kd_grid_header_kernel<<<1, 32, 0, st>>>(kd.bbox.as<int>(), kd.grid_hdr.as<KdGridHeader>(), cell_target);
     PLS_CHECK_LAUNCH();
+    kd.bbox_clean = true;
     kd_morton_kernel<<<grid_for(M, 256, 8 * kNumSMs), 256, 0, st>>>(pts, M, kd.grid_hdr.as<KdGridHeader>(),
                                                                      kd.morton.as<uint64_t>(), kd.order.as<uint32_t>());
     PLS_CHECK_LAUNCH();
     uint64_t* sk;
     uint32_t* sv;
-    radix_sort_pairs(ctx, kd.morton.as<uint64_t>(), kd.order.as<uint32_t>(), M, 6, &sk, &sv);
+    radix_sort_pairs(ctx, kd.morton.as<uint64_t>(), kd.order.as<uint32_t>(), M, (3 * KD_COORD_BITS + 7) / 8, &sk, &sv);
     kd_gather_kernel<<<grid_for(M, 256, 8 * kNumSMs), 256, 0, st>>>(pts, sv, M, kd.sorted.as<float4>(),
                                                                      kd.inv_order.as<uint32_t>());
     PLS_CHECK_LAUNCH();
@@ -541,6 +583,7 @@ void kdmap_reset(pls_context* ctx) {
     ctx->kd.frame_counts.clear();
     ctx->kd.indexed = 0;
     ctx->kd.valid = false;
+    ctx->kd.bbox_clean = false;
 }
 
 void pack_valid_rows(pls_context* ctx, const float* pts_dev, int64_t n, float4* out, uint32_t* count_dev) {
@@ -615,8 +658,11 @@ void kdmap_update_packed(pls_context* ctx, const float* rel_pose_host, const flo
     const int dst = kd.cur ^ 1;
     kd.store[dst].reserve((size_t)(total > 0 ? total : 1) * sizeof(float4), st);
     kd.bbox.reserve(8 * sizeof(int), st);
-    kd_bbox_init_kernel<<<1, 32, 0, st>>>(kd.bbox.as<int>());
-    PLS_CHECK_LAUNCH();
+    if (!kd.bbox_clean) {
+        kd_bbox_init_kernel<<<1, 32, 0, st>>>(kd.bbox.as<int>());
+        PLS_CHECK_LAUNCH();
+    }
+    kd.bbox_clean = false;
     if (total > 0) {
         kd_move_append_kernel<<<grid_for(total, 256, 8 * kNumSMs), 256, 0, st>>>(
             kd.store[kd.cur].as<float4>(), skip, kept, X, fresh_dev, nullptr, num_new, kd.store[dst].as<float4>(),
@@ -664,23 +710,23 @@ void kdmap_update(pls_context* ctx, const float* rel_pose_host, const float* pts
 
 // One fused ICP iteration over the device-resident queries (float4 in ctx->queries, count in
 // SC_QUERY_COUNT); writes block partials to ctx->partials and returns the block count.
-int kdmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int num_ranks) {
+int kdmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int num_ranks, bool first, float fuse_threshold,
+                        bool* solved) {
     PLS_REQUIRE(ctx->kd.valid, "kd map: search before any update");
+    *solved = false;
     const int64_t mine = (query_bound + num_ranks - 1) / num_ranks;
     const uint32_t* nq_dev = reinterpret_cast<const uint32_t*>(&frame_result_dev(ctx)->counts[1]);
     // credited per executed iteration by the caller (the launch is a no-op once ICP converged)
     ProfileScope ps(ctx, 0, 0.0, false);
-    static const bool use_warp = getenv("PLS_KD_WARP") != nullptr;
-    if (use_warp && ctx->cfg.num_neighbors_normals == 10) {
-        const int wpb = KD_WARP_THREADS / 32;
-        const int blocks = grid_for(mine, wpb, 8 * kNumSMs);
-        ctx->partials.reserve((size_t)blocks * NACC * sizeof(double), ctx->stream);
-        kd_icp_warp_kernel<<<blocks, KD_WARP_THREADS, 0, ctx->stream>>>(
-            make_index(ctx), ctx->query_ptr, nq_dev, (int64_t)rank, (int64_t)num_ranks, frame_result_dev(ctx),
-            ctx->cfg.scheme, ctx->cfg.sigma, ctx->nn_prev.as<int>(), ctx->partials.as<double>());
-        PLS_CHECK_LAUNCH();
-        return blocks;
+    // lanes per query of the split search kernels (0 = the fused thread-per-query kernel)
+    static const int group = getenv("PLS_KD_GROUP") ? atoi(getenv("PLS_KD_GROUP")) : 4;
+    if (group == 2 || group == 4 || group == 8) {
+        *solved = fuse_threshold >= 0.f;
+        if (group == 2) return launch_group_iteration<2>(ctx, make_index(ctx), mine, nq_dev, rank, num_ranks, first, fuse_threshold);
+        if (group == 4) return launch_group_iteration<4>(ctx, make_index(ctx), mine, nq_dev, rank, num_ranks, first, fuse_threshold);
+        return launch_group_iteration<8>(ctx, make_index(ctx), mine, nq_dev, rank, num_ranks, first, fuse_threshold);
     }
+    if (first) PLS_CUDA(cudaMemsetAsync(ctx->nn_prev.p, 0xff, (size_t)query_bound * sizeof(int), ctx->stream));
     const int blocks = grid_for(mine, KD_ITER_THREADS, 8 * kNumSMs);
     ctx->partials.reserve((size_t)blocks * NACC * sizeof(double), ctx->stream);
     kd_icp_iter_kernel<<<blocks, KD_ITER_THREADS, 0, ctx->stream>>>(

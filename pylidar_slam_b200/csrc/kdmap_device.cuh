@@ -43,6 +43,8 @@ __device__ __forceinline__ float dist2_point(float x, float y, float z, const fl
 // squared distance is below (cell - margin)^2, because every point that close lies inside the 27-block;
 // otherwise the next coarser level is tried and finally the BVH.
 constexpr int KD_LEVELS = 1;
+constexpr int KD_COORD_BITS = 13;                      // Morton bits per axis
+constexpr int KD_COORD_MAX = (1 << KD_COORD_BITS) - 1;
 constexpr float KD_CELL_TARGET = 0.16f;   // default level-0 cell side in [0.16, 0.32) m (PLS_KD_CELL overrides)
 constexpr float KD_CELL_MARGIN = 2e-3f;   // quantisation slack, metres
 
@@ -115,7 +117,7 @@ __device__ __forceinline__ float kd_grid_scan(const KdIndex& ix, int level, floa
     const float fx = (x - g->mn[0]) * g->scale, fy = (y - g->mn[1]) * g->scale, fz = (z - g->mn[2]) * g->scale;
     // the same truncating quantisation as kd_morton_kernel for in-range points; floor for the rest
     const int cx = ((int)floorf(fx)) >> b, cy = ((int)floorf(fy)) >> b, cz = ((int)floorf(fz)) >> b;
-    const int cmax = 65535 >> b;
+    const int cmax = KD_COORD_MAX >> b;
     const uint4* __restrict__ table = ix.table[level];
     const uint32_t mask = ix.mask[level];
     uint64_t sx[3];
@@ -168,14 +170,17 @@ __device__ __forceinline__ float kd_grid_scan(const KdIndex& ix, int level, floa
             }
         }
     }
+    // one candidate per iteration and a single visit site: the lanes of a warp stay converged while they have
+    // candidates left (the earlier "advance range / continue" form let them drift out of phase: ncu showed
+    // ~4 active lanes on the visit body)
+    int total = 0;
+    for (int r = 0; r < nr; ++r) total += re[r] - rs[r] + 1;
     int j = 0, i = 0, end = -1;
-    while (true) {
+    for (int t = 0; t < total; ++t) {
         if (i > end) {
-            if (j == nr) break;
             i = rs[j];
             end = re[j];
             ++j;
-            continue;
         }
         visit(i, dist2_point(x, y, z, __ldg(ix.sorted + i)));
         ++i;
@@ -369,22 +374,33 @@ struct KBest {
         for (int j = 0; j < K; ++j) { d[j] = FLT_MAX; i[j] = -1; }
     }
     __device__ __forceinline__ bool full() const { return i[K - 1] >= 0; }
+    __device__ __forceinline__ void bubble() {
+#pragma unroll
+        for (int j = K - 1; j > 0; --j) {
+            const bool sw = d[j] < d[j - 1];
+            const float td = sw ? d[j - 1] : d[j];
+            const int ti = sw ? i[j - 1] : i[j];
+            d[j - 1] = sw ? d[j] : d[j - 1];
+            i[j - 1] = sw ? i[j] : i[j - 1];
+            d[j] = td;
+            i[j] = ti;
+        }
+    }
     // strict: a candidate equal to the current K-th distance does not displace it
     __device__ __forceinline__ void insert(float dn, int in) {
         if (dn < d[K - 1]) {
             d[K - 1] = dn;
             i[K - 1] = in;
-#pragma unroll
-            for (int j = K - 1; j > 0; --j) {
-                const bool sw = d[j] < d[j - 1];
-                const float td = sw ? d[j - 1] : d[j];
-                const int ti = sw ? i[j - 1] : i[j];
-                d[j - 1] = sw ? d[j] : d[j - 1];
-                i[j - 1] = sw ? i[j] : i[j - 1];
-                d[j] = td;
-                i[j] = ti;
-            }
+            bubble();
         }
+    }
+    // the same result without a branch: for scans where nearly every candidate enters the list (a divergent
+    // insert ran with ~4 of 32 lanes active and was 37 % of the normals kernel's instructions)
+    __device__ __forceinline__ void insert_uniform(float dn, int in) {
+        const bool take = dn < d[K - 1];
+        d[K - 1] = take ? dn : d[K - 1];
+        i[K - 1] = take ? in : i[K - 1];
+        bubble();
     }
 };
 
@@ -532,21 +548,20 @@ __device__ __forceinline__ void kd_point_normal_k10(const KdIndex& ix, int pos, 
     bool exact = false;
     kd_stat(ix, 6);
     if (ix.M > KD_LEAF) {
-        const float r2 = kd_grid_scan(ix, 0, c.x, c.y, c.z, [&](int i, float dd) { L.insert(dd, i); });
+        const float r2 = kd_grid_scan(ix, 0, c.x, c.y, c.z, [&](int i, float dd) { L.insert_uniform(dd, i); });
         exact = r2 > 0.f && L.full() && L.d[K - 1] <= r2;
         if (exact) kd_stat(ix, 7);
     }
     if (!exact) {
         kd_stat(ix, 10);
         float bound = L.full() ? L.d[K - 1] : FLT_MAX;
-        if (ix.M > 2 * K + 2) {
-            // the K-th smallest distance among the point's 2K+3 neighbours in Morton order (contiguous loads)
-            // is an upper bound of its K-NN radius: the BVH walk below starts pruned even in sparse regions
-            KBest<K> S;
-            S.reset();
-            const int lo = min(max(pos - (K + 1), 0), ix.M - (2 * K + 3));
-            for (int i = lo; i < lo + 2 * K + 3; ++i) S.insert(dist2_point(c.x, c.y, c.z, __ldg(ix.sorted + i)), i);
-            bound = fminf(bound, S.d[K - 1]);
+        if (!L.full() && ix.M >= K) {
+            // fewer than K points in the whole block (a sparse region): the farthest of K consecutive points
+            // in Morton order bounds the K-NN radius, so the BVH walk below starts pruned
+            const int lo = min(max(pos - K / 2, 0), ix.M - K);
+            float far = 0.f;
+            for (int i = lo; i < lo + K; ++i) far = fmaxf(far, dist2_point(c.x, c.y, c.z, __ldg(ix.sorted + i)));
+            bound = far;
         }
         kd_knn_bounded<K>(ix, c.x, c.y, c.z, bound, L);
     }

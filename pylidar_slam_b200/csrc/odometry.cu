@@ -8,6 +8,7 @@
 #include <stdlib.h>
 
 #include "internal.cuh"
+#include "icp_device.cuh"
 #include "pose_device.cuh"
 
 namespace pls {
@@ -32,23 +33,11 @@ __global__ void frame_begin_kernel(FrameResult* fr, const float* T0 /*16, device
         fr->iters = 0;
         fr->status = 0;
         fr->done = 0;
+        fr->pad = 0;  // last-block ticket of the fused correspondence+solve kernels
     }
     if (t < NACC) fr->last_sums[t] = 0.0;
 }
 
-
-// Deterministic parallel sum of the block partial rows: warp w owns accumulators w, w+8, ...; its lanes
-// stride over the rows and a fixed shuffle tree combines them (same order every run).
-__device__ __forceinline__ void sum_partials_256(const double* __restrict__ partials, int num_blocks, double* sums) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int a = warp; a < NACC; a += 8) {
-        double s = 0.0;
-        for (int b = lane; b < num_blocks; b += 32) s += partials[(size_t)b * NACC + a];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-        if (lane == 0) sums[a] = s;
-    }
-}
 
 __global__ void __launch_bounds__(256) reduce_partials_kernel(FrameResult* fr, const double* __restrict__ partials,
                                                               int num_blocks) {
@@ -57,43 +46,6 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(FrameResult* fr, c
     sum_partials_256(partials, num_blocks, sums);
     __syncthreads();
     if (threadIdx.x < NACC) fr->last_sums[threadIdx.x] = sums[threadIdx.x];
-}
-
-// The serial tail of an ICP iteration (thread 0): Gauss-Newton guards, 6x6 solve, stop test, pose update.
-__device__ __forceinline__ void icp_solve_and_update(FrameResult* fr, const double* sums, float threshold_delta) {
-    const int it = fr->iters;
-    fr->iters = it + 1;
-    // optimization.py:323-327: |r| < 1e-7 -> warning, x stays 0, residuals r^2; then delta = 0 breaks the loop
-    if (sqrt(sums[28]) < 1e-7) {
-        fr->losses[it] = (float)sums[28];
-        fr->status = PLS_W_TINY_RESIDUAL;
-        fr->done = 1;
-        return;
-    }
-    double dx[6];
-    const double det = solve6(sums, dx);
-    if (!(fabs(det) >= 1e-7)) {  // optimization.py:334-336
-        fr->status = PLS_E_SINGULAR;
-        fr->done = 1;
-        return;
-    }
-    fr->losses[it] = (float)sums[27];
-    float delta[6];
-    float n2 = 0.f;
-    for (int i = 0; i < 6; ++i) {
-        delta[i] = (float)dx[i];
-        n2 += delta[i] * delta[i];
-    }
-    if (sqrtf(n2) < threshold_delta) {  // icp_odometry.py:292-293: the last delta is not applied
-        fr->done = 1;
-        return;
-    }
-    float dT[16], Tn[16], prm[6];
-    build_pose(delta, dT);
-    mat4_mul(dT, fr->T, Tn);
-    from_pose(Tn, prm);          // icp_odometry.py:296
-    build_pose(prm, fr->T);      // icp_odometry.py:297
-    for (int i = 0; i < 6; ++i) fr->params[i] = prm[i];
 }
 
 // K7: normal-equation solve + ICP bookkeeping (256 threads).  num_blocks == 0: last_sums already holds
@@ -216,9 +168,12 @@ int enqueue_icp_iterations(pls_context* ctx, int64_t query_bound, int first, int
     int last_blocks = 0;
     for (int it = first; it < last; ++it) {
         int blocks;
-        if (ctx->cfg.local_map_type == PLS_MAP_KDTREE) blocks = kdmap_icp_iteration(ctx, query_bound, rank, size);
+        bool solved = false;  // the kd kernels finish the iteration themselves on a single GPU
+        if (ctx->cfg.local_map_type == PLS_MAP_KDTREE)
+            blocks = kdmap_icp_iteration(ctx, query_bound, rank, size, it == 0, size == 1 ? ctx->cfg.threshold_delta_pose : -1.f, &solved);
         else blocks = projmap_icp_iteration(ctx, query_bound, rank, size);
         last_blocks = blocks;
+        if (solved) continue;
         if (size > 1 && comm_is_p2p(ctx)) {
             icp_step_p2p_kernel<<<1, 256, 0, st>>>(fr, ctx->partials.as<double>(), blocks, ctx->cfg.threshold_delta_pose,
                                                    (P2PSlot* const*)comm_p2p_peers(ctx), size, rank, comm_p2p_next_seq(ctx));
@@ -239,7 +194,7 @@ int enqueue_icp_iterations(pls_context* ctx, int64_t query_bound, int first, int
 
 // The ICP loop (icp_odometry.py:248-299) over ctx->query_ptr / counts[1]: iterations are enqueued without
 // host syncs and turn into no-ops once the device-side `done` flag latches.  To avoid paying for
-// max_num_alignments launches when ICP converges in 2-3, only `previous frame's count + 2` iterations are
+// max_num_alignments launches when ICP converges in 2-3, only `previous frame's count + 1` iterations are
 // enqueued up front; the rare frame that needs more continues after the result fetch (same arithmetic,
 // one extra sync).  Returns the block count of the correspondence kernel.
 int run_icp(pls_context* ctx, const float* T0_dev, int64_t query_bound) {
@@ -249,11 +204,10 @@ int run_icp(pls_context* ctx, const float* T0_dev, int64_t query_bound) {
     PLS_CHECK_LAUNCH();
     if (query_bound < 1) query_bound = 1;
     ctx->pm.zbuf_clean = false;  // tmp[3] may have been used by the frame's own projection
-    ctx->nn_prev.reserve((size_t)query_bound * sizeof(int), st);
-    PLS_CUDA(cudaMemsetAsync(ctx->nn_prev.p, 0xff, (size_t)query_bound * sizeof(int), st));
+    ctx->nn_prev.reserve((size_t)query_bound * sizeof(int), st);  // previous matches: ignored by iteration 0
     const int max_it = ctx->cfg.max_num_alignments;
     static const bool all_upfront = getenv("PLS_ICP_UPFRONT_ALL") != nullptr;
-    int upfront = (ctx->last_icp_iters > 0 && !all_upfront) ? ctx->last_icp_iters + 2 : max_it;
+    int upfront = (ctx->last_icp_iters > 0 && !all_upfront) ? ctx->last_icp_iters + 1 : max_it;
     if (upfront > max_it) upfront = max_it;
     int blocks = enqueue_icp_iterations(ctx, query_bound, 0, upfront);
     int enq = upfront;

@@ -97,39 +97,43 @@ __host__ __device__ inline void rigid_inverse(const float* M, float* out) {
     out[12] = 0; out[13] = 0; out[14] = 0; out[15] = 1;
 }
 
-// Solves H dx = -g for the symmetric 6x6 system given the 21 upper-triangle entries and g,
-// Gaussian elimination with partial pivoting in double; returns det(H).
+// Solves H dx = -g for the symmetric positive semi-definite 6x6 system given the 21 upper-triangle entries
+// and g; returns det(H).  Gaussian elimination WITHOUT pivoting (stable for SPD matrices), fully unrolled so
+// that the matrix lives in registers: this runs on one thread between two correspondence launches, where a
+// local-memory, dynamically indexed pivoting version cost microseconds of pure latency.  A zero pivot
+// (rank-deficient H) turns det into 0 or NaN, which the callers' |det| >= 1e-7 guard rejects.
 __host__ __device__ inline double solve6(const double* sums /*21 upper + 6*/, double* dx) {
     double A[6][7];
-    int k = 0;
-    for (int i = 0; i < 6; ++i)
-        for (int j = i; j < 6; ++j) {
-            A[i][j] = sums[k];
-            A[j][i] = sums[k];
-            ++k;
-        }
+    {
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = i; j < 6; ++j) {
+                A[i][j] = sums[k];
+                A[j][i] = sums[k];
+                ++k;
+            }
+    }
+#pragma unroll
     for (int i = 0; i < 6; ++i) A[i][6] = -sums[21 + i];
     double det = 1.0;
+#pragma unroll
     for (int c = 0; c < 6; ++c) {
-        int piv = c;
-        double best = fabs(A[c][c]);
-        for (int r = c + 1; r < 6; ++r)
-            if (fabs(A[r][c]) > best) { best = fabs(A[r][c]); piv = r; }
-        if (best == 0.0) { for (int i = 0; i < 6; ++i) dx[i] = 0.0; return 0.0; }
-        if (piv != c) {
-            for (int j = 0; j < 7; ++j) { double t = A[c][j]; A[c][j] = A[piv][j]; A[piv][j] = t; }
-            det = -det;
-        }
-        det *= A[c][c];
-        double inv = 1.0 / A[c][c];
+        const double piv = A[c][c];
+        det *= piv;
+        const double inv = 1.0 / piv;
+#pragma unroll
         for (int r = c + 1; r < 6; ++r) {
-            double f = A[r][c] * inv;
-            if (f != 0.0)
-                for (int j = c; j < 7; ++j) A[r][j] -= f * A[c][j];
+            const double f = A[r][c] * inv;
+#pragma unroll
+            for (int j = c + 1; j < 7; ++j) A[r][j] -= f * A[c][j];
         }
     }
+#pragma unroll
     for (int i = 5; i >= 0; --i) {
         double s = A[i][6];
+#pragma unroll
         for (int j = i + 1; j < 6; ++j) s -= A[i][j] * dx[j];
         dx[i] = s / A[i][i];
     }

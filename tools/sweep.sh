@@ -1,8 +1,7 @@
 #!/bin/bash
-# development helper: sweep kd search variants with the quick bench pass
-for cell in 0.16 0.32 0.64; do
-  for warp in "" 1; do
-    if [ -n "$warp" ]; then export PLS_KD_WARP=1; else unset PLS_KD_WARP; fi
-    PLS_KD_CELL=$cell python bench.py --quick --steps 30 --warmup 24 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('cell $cell warp [$warp] ms/frame', round(d['ms_per_step'],4))"
+# development helper: sweep kd search variants with the quick bench pass (device-resident frames only)
+for g in 0 2 4 8; do
+  for cell in 0.16 0.32; do
+    PLS_KD_GROUP=$g PLS_KD_CELL=$cell python bench.py --quick --steps 40 --warmup 24 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('group $g cell $cell ms/frame', round(d['ms_per_step'],4), 'launches', d['gpu_launches'])"
   done
 done
