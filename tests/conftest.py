@@ -44,6 +44,44 @@ def golden_icp_full():
     return np.load(os.path.join(GOLDEN, "icp_full.npz"))
 
 
+@pytest.fixture(scope="session")
+def golden_next():
+    return np.load(os.path.join(GOLDEN, "next_rows.npz"))
+
+
+def dist_tol(pose):
+    """Tolerance [m] of a de-skewed frame against the reference's.  A float64 pose is orthonormal to 1e-16 and
+    the closed-form interpolation agrees with scipy's quaternion Slerp to a few ulp of the coordinates (1e-11
+    at 200 m).  The rotation block of a float32 pose is only orthonormal to 6e-8: how the interpolation treats
+    that defect is scipy-version dependent (1.18 projects onto the nearest rotation by SVD, the releases of the
+    reference's era do not), so only float32 resolution of the pose is meaningful there."""
+    return 1e-11 if np.asarray(pose).dtype == np.float64 else 1e-6
+
+
+def check_voxel_stats(out, g, name):
+    """Voxelization outputs against the reference goldens: integer outputs bit-exact; means / scatter
+    matrices to the rounding of the reference's own accumulation (it sums in the cloud's dtype, sequentially,
+    in numba's unstable argsort order -- pointcloud.py:99-131)."""
+    for key in ("voxel_hashes", "voxel_coordinates", "voxel_sizes", "voxel_indices"):
+        assert np.array_equal(np.asarray(out[key]), g[f"vox_{name}_{key}"]), (name, key)
+    means, covs = np.asarray(out["voxel_means"]), np.asarray(out["voxel_covariances"])
+    rm, rc = g[f"vox_{name}_voxel_means"], g[f"vox_{name}_voxel_covariances"]
+    assert means.dtype == rm.dtype and covs.dtype == rc.dtype, (name, means.dtype, covs.dtype)
+    assert means.shape == rm.shape and covs.shape == rc.shape, (name, means.shape, covs.shape)
+    n = np.maximum(g[f"vox_{name}_voxel_sizes"].astype(np.float64), 1.0)
+    eps = float(np.finfo(rm.dtype).eps)
+    scale = float(np.abs(g[f"vox_{name}_pc"]).max())
+    # mean: sequential sum of n terms <= scale; scatter: n terms (x - mean)(x - mean)^T whose factors carry
+    # an absolute rounding error eps * scale each, plus the accumulation error of the sum itself
+    tol_m = 4.0 * eps * scale * n
+    assert (np.abs(means.astype(np.float64) - rm).max(axis=1) <= tol_m).all(), (name, "means")
+    trace = np.maximum(np.einsum("vii->v", rc.astype(np.float64)), 0.0)
+    ext = np.sqrt(trace / n)
+    tol_c = 8.0 * eps * n * (ext * scale + trace) + 1e-300
+    err_c = np.abs(covs.astype(np.float64) - rc).reshape(len(n), -1).max(axis=1)
+    assert (err_c <= tol_c).all(), (name, "covs", float((err_c / tol_c).max()))
+
+
 def pose_errors(T, T_ref):
     """(relative translation error, rotation geodesic angle [rad]) of a 4x4 pose vs a reference."""
     T = np.asarray(T, dtype=np.float64).reshape(4, 4)
