@@ -204,6 +204,32 @@ PLS_API int pls_process_frame_grid_sample(pls_context* ctx, const float* raw_poi
                                   int layout, const float* init_pose, float* out_pose,
                                   float* out_params, int* out_has_pose, double* out_info);
 
+/* ---- the rows either side of the path -----------------------------------
+ * Distortion.filter (slam/preprocessing.py:148-191): de-skew of a frame with the estimated relative motion.
+ * xyz [n,3] float32|float64; timestamps [n] float32|float64 (alpha is formed in their dtype, like numpy does);
+ * rel_pose [16] float32|float64 (the data_dict's init_rpose); out [n,3] FLOAT64 = Slerp(I -> R)(alpha_i) p_i +
+ * alpha_i t.  Constant timestamps give alpha = 0; a NaN timestamp makes every output NaN (np.max/np.min). */
+PLS_API int pls_distort(pls_context* ctx, const void* xyz, int xyz_is_f64, const void* timestamps, int ts_is_f64,
+                int64_t n, const void* rel_pose, int pose_is_f64, double* out);
+/* Voxelization.filter (slam/preprocessing.py:71-97) = voxelise + voxel_hashing + voxel_normal_distribution
+ * (slam/common/pointcloud.py:54-79,40-51,83-167).  coords_out [n,3] / hashes_out [n] as pls_voxel_hash (nullable);
+ * per distinct hash, in ascending hash order: sizes_out [V] int64, means_out [V,3], covs_out [V,3,3] = the scatter
+ * matrix sum (x - mean)(x - mean)^T (not divided by the count), both in the dtype of the input; ids_out [n] int64 =
+ * voxel rank of every point.  Per-voxel outputs need capacity n rows; *out_count = V. */
+PLS_API int pls_voxel_statistics(pls_context* ctx, const void* xyz, int is_f64, int64_t n, double voxel,
+                         int64_t* coords_out, int64_t* hashes_out, int64_t* sizes_out, void* means_out,
+                         void* covs_out, int64_t* ids_out, int64_t* out_count);
+/* GaussNewtonPointToPointAlignment.align (slam/odometry/alignment.py:144-189) -> GaussNewton.compute
+ * (optimization.py:296-344) with PointToPointCost closures (optimization.py:458-541): r = |R p + t - q| and the
+ * reference's Jacobian as written, J[k] = (dT/dx_k p~) . (R p + t - q).  Arguments as pls_align_p2plane. */
+PLS_API int pls_align_p2point(pls_context* ctx, const void* ref, const void* tgt, int64_t n, int is_f64, int scheme,
+                      double sigma, int max_iters, double norm_stop, const void* x0, void* out_dT, void* out_x,
+                      void* out_loss);
+/* weighted_procrustes, numpy path (slam/common/registration.py:15-76): rigid T (float64 [16]) with
+ * T * tgt ~ ref.  tgt / ref [n,3] and weights [n] (nullable) share one dtype; the weights only enter the centroids. */
+PLS_API int pls_weighted_procrustes(pls_context* ctx, const void* tgt, const void* ref, const void* weights, int64_t n,
+                            int is_f64, double* out_T);
+
 /* ---- multi-GPU: per-iteration allreduce of the normal-equation accumulators ---------
  * (no reference counterpart: SURVEY.md section 8e).  Every rank holds the whole local map
  * (kd) or its band of image rows (projective) and a shard of the queries; after

@@ -5,12 +5,14 @@ RigidAlignment, Filter) over hand-written sm_100a CUDA behind a C ABI (include/p
 Importing the package does not need a GPU; creating a context does (no CPU fallback).
 """
 from . import _lib  # noqa: F401
-from .common import (Pose, SphericalProjector, compute_neighbors, compute_normal_map, grid_sample,  # noqa: F401
-                     voxel_hashing, voxelise)
+from .common import (Pose, SphericalProjector, compute_neighbors, compute_normal_map, distort_frame,  # noqa: F401
+                     grid_sample, voxel_hashing, voxel_normal_distribution, voxel_statistics, voxelise,
+                     weighted_procrustes)
 from .odometry import (LOCAL_MAP, ODOMETRY, RIGID_ALIGNMENT, GaussNewtonPointToPlaneAlignment,  # noqa: F401
-                       GaussNewtonPointToPlaneConfig, ICPFrameToModel, ICPFrameToModelConfig, KdTreeLocalMap,
+                       GaussNewtonPointToPlaneConfig, GaussNewtonPointToPointAlignment, GNPointToPointConfig, ICPFrameToModel, ICPFrameToModelConfig, KdTreeLocalMap,
                        KdTreeLocalMapConfig, LocalMap, OdometryAlgorithm, ProjectiveLocalMap,
                        ProjectiveLocalMapConfig)
-from .preprocessing import FILTER, GridSample, GridSampleConfig, Preprocessing, PreprocessingConfig, ToTensor  # noqa: F401
+from .preprocessing import (FILTER, Distortion, DistortionConfig, GridSample, GridSampleConfig, Preprocessing,  # noqa: F401
+                            PreprocessingConfig, ToTensor, ToTensorConfig, Voxelization, VoxelizationConfig)
 
 __version__ = "0.1.0"

@@ -98,6 +98,84 @@ def grid_sample(pointcloud, voxel_size: float, ctx=None):
     return out[:count.value], idx[:count.value]
 
 
+def _is64(x) -> bool:
+    return x.dtype == (np.float64 if isinstance(x, np.ndarray) else torch.float64)
+
+
+def voxel_statistics(pointcloud, voxel_size: float, ctx=None):
+    """voxelise + voxel_hashing + voxel_normal_distribution in one pass over the sorted hashes
+    (pointcloud.py:54-79,40-51,83-167): returns `(coords [n,3], hashes [n], sizes [V], means [V,3], covs [V,3,3],
+    voxel_indices [n])`, voxels in ascending-hash order, covs = the un-normalised scatter matrices."""
+    ctx = ctx or default_context()
+    check_tensor(pointcloud, [-1, 3])
+    is64 = _is64(pointcloud)
+    pc = np.ascontiguousarray(pointcloud) if isinstance(pointcloud, np.ndarray) else pointcloud.contiguous()
+    if not is64:
+        pc = _as_f32(pc)
+    n = pc.shape[0]
+    assert_debug(n > 0, "cannot voxelise an empty point cloud")
+    fdt = np.float64 if is64 else np.float32
+    coords, hashes = _empty_like_kind(pc, (n, 3), np.int64), _empty_like_kind(pc, (n,), np.int64)
+    sizes, ids = _empty_like_kind(pc, (n,), np.int64), _empty_like_kind(pc, (n,), np.int64)
+    means, covs = _empty_like_kind(pc, (n, 3), fdt), _empty_like_kind(pc, (n, 3, 3), fdt)
+    count = C.c_int64(0)
+    ctx.call("pls_voxel_statistics", _lib.ptr(pc), int(is64), n, float(voxel_size), _lib.ptr(coords), _lib.ptr(hashes),
+             _lib.ptr(sizes), _lib.ptr(means), _lib.ptr(covs), _lib.ptr(ids), C.byref(count))
+    V = count.value
+    return coords, hashes, sizes[:V], means[:V], covs[:V], ids
+
+
+def voxel_normal_distribution(pointcloud, voxel_size: float, ctx=None):
+    """`(voxel_sizes, means, covs, voxel_ids)` of voxel_normal_distribution (pointcloud.py:154-167).  The reference
+    takes precomputed hashes; here they come from the same pass, so the argument is the voxel size."""
+    _, _, sizes, means, covs, ids = voxel_statistics(pointcloud, voxel_size, ctx=ctx)
+    return sizes, means, covs, ids
+
+
+def distort_frame(pointcloud, timestamps, relative_pose, ctx=None):
+    """The arithmetic of Distortion.filter (preprocessing.py:171-191): `Slerp(I -> R)(alpha) p + alpha t` with
+    `alpha = (t - min t) / (max t - min t)`; float64 `[n,3]` out."""
+    ctx = ctx or default_context()
+    check_tensor(pointcloud, [-1, 3])
+    n = pointcloud.shape[0]
+    check_tensor(timestamps, [n])
+    check_tensor(relative_pose, [4, 4])
+    is_np = isinstance(pointcloud, np.ndarray)
+    pc64 = _is64(pointcloud)
+    pc = (np.ascontiguousarray(pointcloud) if is_np else pointcloud.contiguous()) if pc64 else _as_f32(pointcloud)
+    ts64 = _is64(timestamps)
+    ts = (np.ascontiguousarray(timestamps) if isinstance(timestamps, np.ndarray) else timestamps.contiguous()) if ts64 \
+        else _as_f32(timestamps)
+    pose = np.asarray(relative_pose.detach().cpu().numpy() if isinstance(relative_pose, torch.Tensor) else relative_pose)
+    pose64 = pose.dtype == np.float64
+    pose = np.ascontiguousarray(pose, dtype=np.float64 if pose64 else np.float32)
+    out = _empty_like_kind(pc, (n, 3), np.float64)
+    ctx.call("pls_distort", _lib.ptr(pc), int(pc64), _lib.ptr(ts), int(ts64), n, _lib.ptr(pose), int(pose64), _lib.ptr(out))
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# slam/common/registration.py
+# ------------------------------------------------------------------------------------------
+def weighted_procrustes(pc_target, pc_reference, weights=None, ctx=None):
+    """Rigid transform (float64 `[4,4]` numpy) with `T * target ~ reference` (registration.py:15-76, numpy path:
+    `[n,3]` clouds, optional `[n,1]` weights that only enter the centroids)."""
+    ctx = ctx or default_context()
+    check_tensor(pc_target, [-1, 3])
+    check_tensor(pc_reference, [*pc_target.shape])
+    is64 = _is64(pc_target)
+    conv = (lambda a: (np.ascontiguousarray(a, dtype=np.float64) if isinstance(a, np.ndarray) else a.to(torch.float64).contiguous())) \
+        if is64 else _as_f32
+    tgt, ref = conv(pc_target), conv(pc_reference)
+    w = None
+    if weights is not None:
+        w = conv(weights.reshape(-1))
+        check_tensor(w, [tgt.shape[0]])
+    out = np.empty((4, 4), dtype=np.float64)
+    ctx.call("pls_weighted_procrustes", _lib.ptr(tgt), _lib.ptr(ref), _lib.ptr(w), tgt.shape[0], int(is64), _lib.ptr(out))
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 # slam/common/projection.py
 # ------------------------------------------------------------------------------------------

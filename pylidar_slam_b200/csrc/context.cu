@@ -228,6 +228,7 @@ int pls_destroy(pls_context* ctx) {
     for (auto& b : ctx->stage_in) b.release();
     for (auto& b : ctx->stage_out) b.release();
     for (auto& b : ctx->tmp) b.release();
+    for (auto& b : ctx->next_buf) b.release();
     ctx->pinned.release();
     ctx->scalars.release();
     ctx->sort.keys_alt.release(); ctx->sort.vals_alt.release(); ctx->sort.hist.release();

@@ -1,4 +1,5 @@
-// K6/K7 -- point-to-plane Gauss-Newton alignment on given correspondences.
+// K6/K7 -- point-to-plane (and, behind the same registry, point-to-point) Gauss-Newton alignment on given
+// correspondences.
 //
 //   gn_accumulate_kernel : residual r = n.(R(x) p + t(x) - q), Jacobian row
 //                          J = [n, (dR/de_k p).n], robust weight w, and the reduction of the
@@ -13,7 +14,9 @@
 // Replaces PointToPlaneCost.get_residual_fun / get_residual_jac_fun
 // (slam/common/optimization.py:356-435), _WLSScheme.weights + the seven cost functions
 // (:45-50,61-226), GaussNewton.compute (:296-344) and GaussNewtonPointToPlaneAlignment.align
-// (slam/odometry/alignment.py:91-127).
+// (slam/odometry/alignment.py:91-127).  COST_POINT swaps in PointToPointCost's closures (optimization.py:458-541)
+// for GaussNewtonPointToPointAlignment.align (alignment.py:144-189); everything after the residual/Jacobian row is
+// shared.
 #include "gn_device.cuh"
 #include "internal.cuh"
 #include "pose_device.cuh"
@@ -35,8 +38,9 @@ struct GnState {
 };
 
 constexpr int GN_THREADS = 256;
+enum { COST_PLANE = 0, COST_POINT = 1 };
 
-template <typename T>
+template <typename T, int COST>
 __global__ void __launch_bounds__(GN_THREADS)
 gn_accumulate_kernel(const T* __restrict__ ref, const T* __restrict__ tgt, const T* __restrict__ nrm, int64_t n,
                      const GnState<T>* __restrict__ state, int scheme, T sigma, T* __restrict__ loss_out,
@@ -59,9 +63,14 @@ gn_accumulate_kernel(const T* __restrict__ ref, const T* __restrict__ tgt, const
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         T p[3] = {tgt[3 * i], tgt[3 * i + 1], tgt[3 * i + 2]};
         T q[3] = {ref[3 * i], ref[3 * i + 1], ref[3 * i + 2]};
-        T nn[3] = {nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]};
         T J[6];
-        T r = p2plane_residual_jacobian<T>(p, q, nn, sR, st, sdR, J);
+        T r;
+        if constexpr (COST == COST_PLANE) {
+            T nn[3] = {nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]};
+            r = p2plane_residual_jacobian<T>(p, q, nn, sR, st, sdR, J);
+        } else {
+            r = p2point_residual_jacobian<T>(p, q, sR, st, sdR, J);
+        }
         T w = ls_weight<T>(scheme, sigma, r, p, q);
         T wr = r * w;
         if (loss_out) loss_out[i] = wr * wr;
@@ -114,7 +123,7 @@ __global__ void gn_solve_kernel(GnState<T>* state, const double* __restrict__ pa
     if (state->dx_norm < (double)norm_stop) state->done = 1;
 }
 
-template <typename T>
+template <typename T, int COST>
 void align_impl(pls_context* ctx, const void* ref, const void* tgt, const void* nrm, int64_t n, int scheme,
                 double sigma, int max_iters, double norm_stop, const void* x0, void* out_dT, void* out_x,
                 void* out_loss, int* status_out) {
@@ -122,7 +131,7 @@ void align_impl(pls_context* ctx, const void* ref, const void* tgt, const void* 
     const size_t pts_bytes = (size_t)n * 3 * sizeof(T);
     const T* d_ref = (const T*)to_device(ctx, ref, pts_bytes, ctx->stage_in[0]);
     const T* d_tgt = (const T*)to_device(ctx, tgt, pts_bytes, ctx->stage_in[1]);
-    const T* d_nrm = (const T*)to_device(ctx, nrm, pts_bytes, ctx->stage_in[2]);
+    const T* d_nrm = COST == COST_PLANE ? (const T*)to_device(ctx, nrm, pts_bytes, ctx->stage_in[2]) : nullptr;
     OutArg o_loss = out_arg(ctx, out_loss, (size_t)n * sizeof(T), ctx->stage_out[0]);
 
     ctx->tmp[0].reserve(sizeof(GnState<T>), st);
@@ -143,8 +152,8 @@ void align_impl(pls_context* ctx, const void* ref, const void* tgt, const void* 
     int iters = max_iters < 1 ? 1 : max_iters;
     for (int it = 0; it < iters; ++it) {
         {
-            ProfileScope ps(ctx, 5, (double)n * 9 * sizeof(T) + NACC * 8.0);
-            gn_accumulate_kernel<T><<<blocks, GN_THREADS, 0, st>>>(d_ref, d_tgt, d_nrm, n, d_state, scheme, (T)sigma,
+            ProfileScope ps(ctx, 5, (double)n * (COST == COST_PLANE ? 9 : 6) * sizeof(T) + NACC * 8.0);
+            gn_accumulate_kernel<T, COST><<<blocks, GN_THREADS, 0, st>>>(d_ref, d_tgt, d_nrm, n, d_state, scheme, (T)sigma,
                                                                   (T*)o_loss.dev, ctx->partials.as<double>());
             PLS_CHECK_LAUNCH();
         }
@@ -188,9 +197,27 @@ int pls_align_p2plane(pls_context* ctx, const void* ref, const void* tgt, const 
     PLS_REQUIRE(ref && tgt && nrm && n > 0, "pls_align_p2plane: ref/tgt/nrm must be [n,3] with n > 0");
     PLS_REQUIRE(scheme >= 0 && scheme <= PLS_SCHEME_CAUCHY, "pls_align_p2plane: unknown weighting scheme");
     if (is_f64)
-        align_impl<double>(ctx, ref, tgt, nrm, n, scheme, sigma, max_iters, norm_stop, x0, out_dT, out_x, out_loss, &status);
+        align_impl<double, COST_PLANE>(ctx, ref, tgt, nrm, n, scheme, sigma, max_iters, norm_stop, x0, out_dT, out_x, out_loss, &status);
     else
-        align_impl<float>(ctx, ref, tgt, nrm, n, scheme, sigma, max_iters, norm_stop, x0, out_dT, out_x, out_loss, &status);
+        align_impl<float, COST_PLANE>(ctx, ref, tgt, nrm, n, scheme, sigma, max_iters, norm_stop, x0, out_dT, out_x, out_loss, &status);
+    if (status == PLS_E_SINGULAR) throw pls::Error{PLS_E_SINGULAR, "Invalid Jacobian in Gauss Newton minimization"};
+    if (status == PLS_W_TINY_RESIDUAL) {
+        ctx->err = "The residual norm is lower than threshold 1e-7";
+        return PLS_W_TINY_RESIDUAL;
+    }
+    PLS_API_END(ctx)
+}
+
+int pls_align_p2point(pls_context* ctx, const void* ref, const void* tgt, int64_t n, int is_f64, int scheme, double sigma,
+                      int max_iters, double norm_stop, const void* x0, void* out_dT, void* out_x, void* out_loss) {
+    int status = PLS_OK;
+    PLS_API_BEGIN(ctx)
+    PLS_REQUIRE(ref && tgt && n > 0, "pls_align_p2point: ref/tgt must be [n,3] with n > 0");
+    PLS_REQUIRE(scheme >= 0 && scheme <= PLS_SCHEME_CAUCHY, "pls_align_p2point: unknown weighting scheme");
+    if (is_f64)
+        align_impl<double, COST_POINT>(ctx, ref, tgt, nullptr, n, scheme, sigma, max_iters, norm_stop, x0, out_dT, out_x, out_loss, &status);
+    else
+        align_impl<float, COST_POINT>(ctx, ref, tgt, nullptr, n, scheme, sigma, max_iters, norm_stop, x0, out_dT, out_x, out_loss, &status);
     if (status == PLS_E_SINGULAR) throw pls::Error{PLS_E_SINGULAR, "Invalid Jacobian in Gauss Newton minimization"};
     if (status == PLS_W_TINY_RESIDUAL) {
         ctx->err = "The residual norm is lower than threshold 1e-7";

@@ -12,7 +12,7 @@ constexpr int NACC_DEV = 30;
 
 // r = n . (R p + t - q);  J = [n, (dR_k p) . n]   (slam/common/optimization.py:381-394,424-433)
 template <typename T>
-__device__ __forceinline__ T p2plane_residual_jacobian(const T* p, const T* q, const T* n, const T* R, const T* t,
+__host__ __device__ __forceinline__ T p2plane_residual_jacobian(const T* p, const T* q, const T* n, const T* R, const T* t,
                                                        const T* dR, T* J) {
     T tp0 = p[0] * R[0] + p[1] * R[1] + p[2] * R[2] + t[0];
     T tp1 = p[0] * R[3] + p[1] * R[4] + p[2] * R[5] + t[1];
@@ -45,9 +45,32 @@ __device__ __forceinline__ float p2plane_residual_jacobian_identity(const float*
     return r;
 }
 
+// Point-to-point cost (slam/common/optimization.py:458-541): r = |d|, d = R p + t - q, and the Jacobian AS THE
+// REFERENCE WRITES IT (:485-501): J[k] = (dT/dx_k p~) . d = [d, (dR_k p) . d] -- that is r * dr/dx, the gradient of
+// r^2 / 2, not dr/dx.  Restated faithfully: the drop-in must return what the reference returns.
+template <typename T>
+__host__ __device__ __forceinline__ T p2point_residual_jacobian(const T* p, const T* q, const T* R, const T* t, const T* dR,
+                                                       T* J) {
+    T d0 = p[0] * R[0] + p[1] * R[1] + p[2] * R[2] + t[0] - q[0];
+    T d1 = p[0] * R[3] + p[1] * R[4] + p[2] * R[5] + t[1] - q[1];
+    T d2 = p[0] * R[6] + p[1] * R[7] + p[2] * R[8] + t[2] - q[2];
+    J[0] = d0;
+    J[1] = d1;
+    J[2] = d2;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const T* D = dR + 9 * k;
+        T v0 = D[0] * p[0] + D[1] * p[1] + D[2] * p[2];
+        T v1 = D[3] * p[0] + D[4] * p[1] + D[5] * p[2];
+        T v2 = D[6] * p[0] + D[7] * p[1] + D[8] * p[2];
+        J[3 + k] = v0 * d0 + v1 * d1 + v2 * d2;
+    }
+    return sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+}
+
 // w = sqrt(cost(r)) / max(|r|, 1e-4)   (optimization.py:45-50 and the cost functions :61-208)
 template <typename T>
-__device__ __forceinline__ T ls_weight(int scheme, T sigma, T r, const T* p, const T* q) {
+__host__ __device__ __forceinline__ T ls_weight(int scheme, T sigma, T r, const T* p, const T* q) {
     if (scheme == PLS_SCHEME_DEFAULT || scheme == PLS_SCHEME_LEAST_SQUARE) return (T)1;
     T a = fabs(r);
     T cost;

@@ -59,6 +59,63 @@ __global__ void gather_samples_kernel(const T* __restrict__ xyz, const uint32_t*
     }
 }
 
+// ---- voxel statistics (Voxelization filter) ---------------------------------------------------------------
+// After the same hash + stable sort as the subsample: rank of every run of equal hashes = voxel id
+// (pointcloud.py:99-150 walks the sorted hashes the same way), scattered back to the points' original order.
+__global__ void voxel_ids_kernel(const uint32_t* __restrict__ vals, const uint8_t* __restrict__ flags,
+                                 const uint32_t* __restrict__ pos, int64_t n, long long* __restrict__ ids_out,
+                                 uint32_t* __restrict__ starts) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t id = pos[i] + flags[i] - 1u;  // pos = number of run heads before i
+        ids_out[vals[i]] = (long long)id;
+        if (flags[i]) starts[id] = (uint32_t)i;
+    }
+}
+
+// One warp per voxel: lanes stride over the voxel's points (gathered through the sorted index), float64 sums,
+// fixed-order shuffle reduction (deterministic); two sweeps -- mean, then the scatter matrix
+// sum (x - mean)(x - mean)^T, which the reference does NOT divide by the count (pointcloud.py:126-131).
+template <typename T>
+__global__ void __launch_bounds__(256)
+voxel_stats_kernel(const T* __restrict__ xyz, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ starts,
+                   const uint32_t* __restrict__ count_dev, int64_t n, long long* __restrict__ sizes,
+                   T* __restrict__ means, T* __restrict__ covs) {
+    const uint32_t V = *count_dev;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < V; v += warps) {
+        const uint32_t b = starts[v];
+        const uint32_t e = (v + 1 < V) ? starts[v + 1] : (uint32_t)n;
+        double sx = 0.0, sy = 0.0, sz = 0.0;
+        for (uint32_t j = b + lane; j < e; j += 32) {
+            const size_t src = vals[j];
+            sx += (double)xyz[3 * src];
+            sy += (double)xyz[3 * src + 1];
+            sz += (double)xyz[3 * src + 2];
+        }
+        sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+        const double cnt = (double)(e - b);
+        const double mx = sx / cnt, my = sy / cnt, mz = sz / cnt;
+        double cxx = 0.0, cxy = 0.0, cxz = 0.0, cyy = 0.0, cyz = 0.0, czz = 0.0;
+        for (uint32_t j = b + lane; j < e; j += 32) {
+            const size_t src = vals[j];
+            const double dx = (double)xyz[3 * src] - mx, dy = (double)xyz[3 * src + 1] - my, dz = (double)xyz[3 * src + 2] - mz;
+            cxx += dx * dx; cxy += dx * dy; cxz += dx * dz;
+            cyy += dy * dy; cyz += dy * dz; czz += dz * dz;
+        }
+        cxx = warp_sum(cxx); cxy = warp_sum(cxy); cxz = warp_sum(cxz);
+        cyy = warp_sum(cyy); cyz = warp_sum(cyz); czz = warp_sum(czz);
+        if (lane == 0) {
+            sizes[v] = (long long)(e - b);
+            means[3 * (size_t)v] = (T)mx; means[3 * (size_t)v + 1] = (T)my; means[3 * (size_t)v + 2] = (T)mz;
+            T* c = covs + 9 * (size_t)v;
+            c[0] = (T)cxx; c[1] = (T)cxy; c[2] = (T)cxz;
+            c[3] = (T)cxy; c[4] = (T)cyy; c[5] = (T)cyz;
+            c[6] = (T)cxz; c[7] = (T)cyz; c[8] = (T)czz;
+        }
+    }
+}
+
 inline int grid_for(int64_t n, int threads = 256) {
     int64_t b = (n + threads - 1) / threads;
     int64_t cap = 8 * kNumSMs;
@@ -89,6 +146,35 @@ void grid_sample_device(pls_context* ctx, const T* xyz_dev, int64_t n, double vo
     exclusive_scan_flags(ctx, ctx->tmp[1].as<uint8_t>(), n, ctx->tmp[2].as<uint32_t>(), scalar_u32(ctx, SC_GS_COUNT));
     gather_samples_kernel<T><<<grid_for(n), 256, 0, st>>>(xyz_dev, sv, ctx->tmp[1].as<uint8_t>(),
                                                           ctx->tmp[2].as<uint32_t>(), n, out_xyz_dev, out_idx_dev);
+    PLS_CHECK_LAUNCH();
+}
+
+// Voxelization.filter (preprocessing.py:71-97): coordinates, hashes and the per-voxel normal distribution.
+template <typename T>
+void voxel_statistics_device(pls_context* ctx, const T* xyz_dev, int64_t n, double voxel, long long* coords_dev,
+                             long long* hashes_dev, long long* sizes_dev, T* means_dev, T* covs_dev, long long* ids_dev) {
+    cudaStream_t st = ctx->stream;
+    ctx->gs_keys.reserve((size_t)n * sizeof(uint64_t), st);
+    ctx->gs_vals.reserve((size_t)n * sizeof(uint32_t), st);
+    ctx->next_buf[1].reserve((size_t)n, st);                    // run-head flags
+    ctx->next_buf[2].reserve((size_t)n * sizeof(uint32_t), st); // heads before i
+    ctx->next_buf[3].reserve((size_t)n * sizeof(uint32_t), st); // first sorted position of every voxel
+    voxel_hash_kernel<T><<<grid_for(n), 256, 0, st>>>(xyz_dev, n, voxel, coords_dev, hashes_dev, ctx->gs_keys.as<uint64_t>(),
+                                                      ctx->gs_vals.as<uint32_t>());
+    PLS_CHECK_LAUNCH();
+    uint64_t* sk;
+    uint32_t* sv;
+    radix_sort_pairs(ctx, ctx->gs_keys.as<uint64_t>(), ctx->gs_vals.as<uint32_t>(), n, 8, &sk, &sv);
+    uint8_t* flags = ctx->next_buf[1].as<uint8_t>();
+    uint32_t* pos = ctx->next_buf[2].as<uint32_t>();
+    uint32_t* starts = ctx->next_buf[3].as<uint32_t>();
+    head_flags_kernel<<<grid_for(n), 256, 0, st>>>(sk, n, flags);
+    PLS_CHECK_LAUNCH();
+    exclusive_scan_flags(ctx, flags, n, pos, scalar_u32(ctx, SC_GS_COUNT));
+    voxel_ids_kernel<<<grid_for(n), 256, 0, st>>>(sv, flags, pos, n, ids_dev, starts);
+    PLS_CHECK_LAUNCH();
+    voxel_stats_kernel<T><<<grid_for(n * 32), 256, 0, st>>>(xyz_dev, sv, starts, scalar_u32(ctx, SC_GS_COUNT), n, sizes_dev,
+                                                           means_dev, covs_dev);
     PLS_CHECK_LAUNCH();
 }
 
@@ -140,6 +226,41 @@ int pls_grid_sample(pls_context* ctx, const void* xyz, int is_f64, int64_t n, do
     *out_count = count;
     finish_out(ctx, ox, (size_t)count * 3 * esz);
     finish_out(ctx, oi, (size_t)count * sizeof(int64_t));
+    PLS_CUDA(cudaStreamSynchronize(ctx->stream));
+    PLS_API_END(ctx)
+}
+
+int pls_voxel_statistics(pls_context* ctx, const void* xyz, int is_f64, int64_t n, double voxel, int64_t* coords_out,
+                         int64_t* hashes_out, int64_t* sizes_out, void* means_out, void* covs_out, int64_t* ids_out,
+                         int64_t* out_count) {
+    PLS_API_BEGIN(ctx)
+    PLS_REQUIRE(xyz && sizes_out && means_out && covs_out && ids_out && out_count && n > 0 && voxel > 0.0,
+                "pls_voxel_statistics: bad arguments");
+    PLS_REQUIRE(n < (1ll << 31), "pls_voxel_statistics: too many points");
+    const size_t esz = is_f64 ? sizeof(double) : sizeof(float);
+    const void* d_xyz = to_device(ctx, xyz, (size_t)n * 3 * esz, ctx->stage_in[0]);
+    OutArg oc = out_arg(ctx, coords_out, (size_t)n * 3 * sizeof(int64_t), ctx->stage_out[0]);
+    OutArg oh = out_arg(ctx, hashes_out, (size_t)n * sizeof(int64_t), ctx->stage_out[1]);
+    OutArg os = out_arg(ctx, sizes_out, (size_t)n * sizeof(int64_t), ctx->stage_out[2]);
+    OutArg om = out_arg(ctx, means_out, (size_t)n * 3 * esz, ctx->stage_out[3]);
+    OutArg ov = out_arg(ctx, covs_out, (size_t)n * 9 * esz, ctx->stage_out[4]);
+    OutArg oi = out_arg(ctx, ids_out, (size_t)n * sizeof(int64_t), ctx->stage_out[5]);
+    if (is_f64)
+        voxel_statistics_device<double>(ctx, (const double*)d_xyz, n, voxel, (long long*)oc.dev, (long long*)oh.dev,
+                                        (long long*)os.dev, (double*)om.dev, (double*)ov.dev, (long long*)oi.dev);
+    else
+        voxel_statistics_device<float>(ctx, (const float*)d_xyz, n, voxel, (long long*)oc.dev, (long long*)oh.dev,
+                                       (long long*)os.dev, (float*)om.dev, (float*)ov.dev, (long long*)oi.dev);
+    uint32_t count = 0;
+    PLS_CUDA(cudaMemcpyAsync(&count, scalar_u32(ctx, SC_GS_COUNT), sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PLS_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out_count = count;
+    finish_out(ctx, oc);
+    finish_out(ctx, oh);
+    finish_out(ctx, os, (size_t)count * sizeof(int64_t));
+    finish_out(ctx, om, (size_t)count * 3 * esz);
+    finish_out(ctx, ov, (size_t)count * 9 * esz);
+    finish_out(ctx, oi);
     PLS_CUDA(cudaStreamSynchronize(ctx->stream));
     PLS_API_END(ctx)
 }

@@ -165,6 +165,9 @@ struct pls_context {
 
     // generic scratch
     pls::DBuf tmp[8];
+    // scratch of the stateless filters / alignments either side of the path (filters.cu, registration.cu, voxel
+    // statistics): kept apart from tmp[] so that they never alias buffers of an in-flight frame
+    pls::DBuf next_buf[8];
 
     // odometry state (icp_odometry.py:100-121)
     pls::KdMap kd;

@@ -313,9 +313,67 @@ class GaussNewtonPointToPlaneAlignment(RigidAlignment):
         return dT, x, loss
 
 
+@dataclass
+class GNPointToPointConfig(RigidAlignmentConfig):
+    """slam/odometry/alignment.py:131-141"""
+    mode: str = "point_to_point_gn"
+    num_gn_iters: int = 1
+    initialize_with_svd: bool = False
+    gauss_newton_config: Dict[str, Any] = field(default_factory=lambda: dict(max_iters=1))
+
+
+class GaussNewtonPointToPointAlignment(RigidAlignment):
+    """GaussNewtonPointToPointAlignment.align (alignment.py:144-189) -> pls_align_p2point.
+
+    Faithful to the reference, including its Jacobian (optimization.py:485-501 is r * dr/dx, see gn_device.cuh).
+    `initialize_with_svd=True` is rejected: the reference's torch weighted_procrustes builds its output with
+    `.repeat(b, 4, 4)` (registration.py:58-59), a [b,16,16] tensor that its own from_pose_matrix shape check then
+    refuses -- there is no reference behaviour to reproduce; `weighted_procrustes` (numpy path) is offered
+    stand-alone in pylidar_slam_b200.common."""
+
+    def __init__(self, config: GNPointToPointConfig, ctx: Optional[_lib.Context] = None, **kwargs):
+        super().__init__(config, **kwargs)
+        self.gn = _gn_settings(config.gauss_newton_config)
+        self._ctx = ctx
+
+    @property
+    def ctx(self):
+        from .common import default_context
+        return self._ctx or default_context()
+
+    def align(self, ref_points, tgt_points, initial_estimate=None, mask=None, **kwargs):
+        assert_debug(not self.config.initialize_with_svd,
+                     "initialize_with_svd fails inside the reference itself (registration.py:58-59 builds a [b,16,16] "
+                     "tensor); use pylidar_slam_b200.common.weighted_procrustes and pass it as initial_estimate")
+        assert_debug(mask is None, "masks are not on the hot path")
+        check_tensor(tgt_points, [1, -1, 3])
+        n = tgt_points.shape[1]
+        check_tensor(ref_points, [1, n, 3])
+        is_np = isinstance(tgt_points, np.ndarray)
+        is64 = (tgt_points.dtype == (np.float64 if is_np else torch.float64))
+        dt_np, dt_t = (np.float64, torch.float64) if is64 else (np.float32, torch.float32)
+        conv = (lambda a: np.ascontiguousarray(a, dtype=dt_np)) if is_np else (lambda a: a.to(dt_t).contiguous())
+        ref, tgt = conv(ref_points), conv(tgt_points)
+        x0 = None
+        if initial_estimate is not None:
+            x0 = conv(initial_estimate)
+            if x0.ndim == 3:
+                check_tensor(x0, [1, 4, 4])
+                assert_debug(not is64, "pose-matrix initial estimates are float32")
+                x0 = self.pose.from_pose_matrix(x0)
+            x0 = conv(x0.reshape(6))
+        mk = (lambda s: np.empty(s, dtype=dt_np)) if is_np else (lambda s: torch.empty(s, dtype=dt_t, device=tgt.device))
+        dT, x, loss = mk((1, 4, 4)), mk((1, 6)), mk((1, n))
+        self.ctx.call("pls_align_p2point", _lib.ptr(ref), _lib.ptr(tgt), n, int(is64), _lib.SCHEMES[self.gn["scheme"]],
+                      self.gn["sigma"], self.gn["max_iters"], self.gn["norm_stop"], _lib.ptr(x0), _lib.ptr(dT), _lib.ptr(x),
+                      _lib.ptr(loss))
+        return dT, x, loss
+
+
 class RIGID_ALIGNMENT(ObjectLoaderEnum, Enum):
     """slam/odometry/alignment.py:200-208"""
     point_to_plane_gauss_newton = (GaussNewtonPointToPlaneAlignment, GaussNewtonPointToPlaneConfig)
+    point_to_point_gauss_newton = (GaussNewtonPointToPointAlignment, GNPointToPointConfig)
 
     @classmethod
     def type_name(cls):
@@ -420,6 +478,10 @@ class ICPFrameToModel(OdometryAlgorithm):
         assert_debug(lm.get("type") in LOCAL_MAP.__members__, f"Unknown type `{lm.get('type')}`")
         assert_debug(al.get("mode", "point_to_plane_gauss_newton") in RIGID_ALIGNMENT.__members__,
                      f"Unknown mode `{al.get('mode')}`")
+        # the reference's ICP loop calls align(neigh, tgt, normals) (icp_odometry.py:285-288): with the point-to-point
+        # alignment the normals land in `initial_estimate` and its shape check raises -- same error type here
+        assert_debug(al.get("mode", "point_to_plane_gauss_newton") == "point_to_plane_gauss_newton",
+                     "ICPFrameToModel needs the point-to-plane alignment (the reference's loop cannot drive point_to_point)")
         gn = _gn_settings(al.get("gauss_newton_config", dict(max_iters=1)))
         is_kd = lm["type"] == "kdtree_local_map"
         self.ctx = _lib.Context(

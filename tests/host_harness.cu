@@ -1,0 +1,137 @@
+// TEST INFRASTRUCTURE ONLY -- host harness around the __host__ __device__ math headers of the CUDA library.
+//
+// The kernels of filters.cu / registration.cu / gn.cu keep their per-element arithmetic in host/device inline
+// functions (filters_device.cuh, registration_device.cuh, gn_device.cuh, pose_device.cuh).  This file wraps that
+// arithmetic in plain host loops behind a tiny C ABI so that tests/test_host_math.py can check -- on a machine
+// WITHOUT a GPU -- the very code the kernels execute against the goldens of the unmodified reference.  It is not
+// part of the product and is never linked into libplslam_b200.so; only the reduction ORDER differs from the
+// kernels (sequential here; warp-shuffle / block partials there), both accumulate in float64.
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../pylidar_slam_b200/csrc/filters_device.cuh"
+#include "../pylidar_slam_b200/csrc/gn_device.cuh"
+#include "../pylidar_slam_b200/csrc/pose_device.cuh"
+#include "../pylidar_slam_b200/csrc/registration_device.cuh"
+
+using namespace pls;
+
+namespace {
+
+template <typename TP, typename TS>
+void distort_host(const TP* pc, const TS* ts, int64_t n, const DistortParams& prm, double* out) {
+    // ts_minmax_kernel + the prologue of distort_kernel
+    double mn = INFINITY, mx = -INFINITY;
+    bool bad = false;
+    for (int64_t i = 0; i < n; ++i) {
+        const double t = (double)ts[i];
+        if (t != t) bad = true;
+        mn = fmin(mn, t);
+        mx = fmax(mx, t);
+    }
+    const TS tmin = (TS)mn, den = (TS)mx - (TS)mn;
+    const int mode = bad ? 2 : (den == (TS)0 ? 1 : 0);
+    for (int64_t i = 0; i < n; ++i) {
+        const TS t = ts[i];
+        TS a;
+        if (mode == 0) a = (t - tmin) / den;
+        else if (mode == 1) a = t * (TS)0;
+        else a = (TS)NAN;
+        distort_point<TS>(a, prm, (double)pc[3 * i], (double)pc[3 * i + 1], (double)pc[3 * i + 2], out[3 * i],
+                          out[3 * i + 1], out[3 * i + 2]);
+    }
+}
+
+// host replica of accumulate_normal_equations (device-only in gn_device.cuh because of its unrolled registers)
+template <typename T>
+void accumulate_host(double* acc, const T* J, T w, T wr, T r) {
+    double wj[6];
+    for (int a = 0; a < 6; ++a) wj[a] = (double)(J[a] * w);
+    int k = 0;
+    for (int a = 0; a < 6; ++a)
+        for (int b = a; b < 6; ++b) acc[k++] += wj[a] * wj[b];
+    for (int a = 0; a < 6; ++a) acc[21 + a] += wj[a] * (double)wr;
+    acc[27] += (double)wr * (double)wr;
+    acc[28] += (double)r * (double)r;
+    acc[29] += 1.0;
+}
+
+// gn_accumulate_kernel + gn_solve_kernel, sequentially
+template <typename T>
+int align_host(int cost, const T* ref, const T* tgt, const T* nrm, int64_t n, int scheme, T sigma, int max_iters,
+               T norm_stop, const T* x0, T* out_x, T* out_dT, T* out_loss) {
+    T x[6] = {0, 0, 0, 0, 0, 0};
+    if (x0) memcpy(x, x0, sizeof(x));
+    int status = 0;
+    build_pose(x, out_dT);
+    for (int it = 0; it < (max_iters < 1 ? 1 : max_iters); ++it) {
+        T M[16], R[9], t[3], dR[27];
+        build_pose(x, M);
+        R[0] = M[0]; R[1] = M[1]; R[2] = M[2]; R[3] = M[4]; R[4] = M[5]; R[5] = M[6]; R[6] = M[8]; R[7] = M[9]; R[8] = M[10];
+        t[0] = M[3]; t[1] = M[7]; t[2] = M[11];
+        euler_jacobian(x + 3, dR);
+        double acc[30];
+        for (int a = 0; a < 30; ++a) acc[a] = 0.0;
+        for (int64_t i = 0; i < n; ++i) {
+            const T* p = tgt + 3 * i;
+            const T* q = ref + 3 * i;
+            T J[6];
+            T r = cost == 0 ? p2plane_residual_jacobian<T>(p, q, nrm + 3 * i, R, t, dR, J)
+                            : p2point_residual_jacobian<T>(p, q, R, t, dR, J);
+            T w = ls_weight<T>(scheme, sigma, r, p, q);
+            T wr = r * w;
+            if (out_loss) out_loss[i] = wr * wr;
+            accumulate_host<T>(acc, J, w, wr, r);
+        }
+        if (sqrt(acc[28]) < 1e-7) { status = PLS_W_TINY_RESIDUAL; build_pose(x, out_dT); break; }
+        double dx[6];
+        const double det = solve6(acc, dx);
+        if (!(fabs(det) >= 1e-7)) { status = PLS_E_SINGULAR; break; }
+        double nrm2 = 0.0;
+        for (int i = 0; i < 6; ++i) {
+            const T d = (T)dx[i];
+            x[i] = x[i] + d;
+            nrm2 += (double)d * (double)d;
+        }
+        build_pose(x, out_dT);
+        if (sqrt(nrm2) < (double)norm_stop) break;
+    }
+    memcpy(out_x, x, sizeof(x));
+    return status;
+}
+
+}  // namespace
+
+extern "C" {
+
+void hh_distort(const void* pc, int pc_is_f64, const void* ts, int ts_is_f64, int64_t n, const double* pose16,
+                int pose_is_f64, double* out) {
+    DistortParams prm;
+    const double R[9] = {pose16[0], pose16[1], pose16[2], pose16[4], pose16[5], pose16[6], pose16[8], pose16[9], pose16[10]};
+    rotation_vector(R, prm.axis, &prm.angle);
+    prm.t[0] = pose16[3]; prm.t[1] = pose16[7]; prm.t[2] = pose16[11];
+    prm.tr_f32 = (!ts_is_f64 && !pose_is_f64) ? 1 : 0;
+    if (pc_is_f64) {
+        if (ts_is_f64) distort_host<double, double>((const double*)pc, (const double*)ts, n, prm, out);
+        else distort_host<double, float>((const double*)pc, (const float*)ts, n, prm, out);
+    } else {
+        if (ts_is_f64) distort_host<float, double>((const float*)pc, (const double*)ts, n, prm, out);
+        else distort_host<float, float>((const float*)pc, (const float*)ts, n, prm, out);
+    }
+}
+
+void hh_rotation_vector(const double* R9, double* axis3, double* angle) { rotation_vector(R9, axis3, angle); }
+
+void hh_kabsch(const double* C9, const double* mu6, double* T16) { kabsch_from_cross(C9, mu6, T16); }
+
+int hh_align(int cost, int is_f64, const void* ref, const void* tgt, const void* nrm, int64_t n, int scheme, double sigma,
+             int max_iters, double norm_stop, const void* x0, void* out_x, void* out_dT, void* out_loss) {
+    if (is_f64)
+        return align_host<double>(cost, (const double*)ref, (const double*)tgt, (const double*)nrm, n, scheme, sigma, max_iters,
+                                  norm_stop, (const double*)x0, (double*)out_x, (double*)out_dT, (double*)out_loss);
+    return align_host<float>(cost, (const float*)ref, (const float*)tgt, (const float*)nrm, n, scheme, (float)sigma, max_iters,
+                             (float)norm_stop, (const float*)x0, (float*)out_x, (float*)out_dT, (float*)out_loss);
+}
+
+}  // extern "C"

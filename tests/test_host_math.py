@@ -1,0 +1,153 @@
+"""The per-element arithmetic of the new kernels, run on the CPU.
+
+filters.cu / registration.cu / gn.cu keep their math in __host__ __device__ headers; tests/host_harness.cu wraps
+those headers in host loops (nvcc, host code only, no GPU needed).  Checked here against the goldens of the
+unmodified reference, so that the device code is pinned even on a box without a GPU; the `-m gpu` tests then only
+have to confirm the launch plumbing and the parallel reductions."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import dist_tol
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SCHEMES = {"default": 0, "least_square": 1, "huber": 2, "exp": 3, "neighborhood": 4, "geman_mcclure": 5,
+           "square_geman_mcclure": 6, "cauchy": 7}
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+
+@pytest.fixture(scope="module")
+def hh():
+    if not os.path.exists(NVCC):
+        pytest.skip("nvcc not available")
+    out_dir = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "host_harness.so")
+    src = os.path.join(ROOT, "tests", "host_harness.cu")
+    deps = [src] + [os.path.join(ROOT, "pylidar_slam_b200", "csrc", f) for f in
+                    ("filters_device.cuh", "registration_device.cuh", "gn_device.cuh", "pose_device.cuh")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call([NVCC, "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+                               "-o", so, src])
+    lib = C.CDLL(so)
+    lib.hh_align.restype = C.c_int
+    return lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def test_distort_point_math_matches_reference(hh, golden_next):
+    g = golden_next
+    for name in ["f64", "f32", "mixed", "const", "big", "pc64"]:
+        pc, ts, pose = (np.ascontiguousarray(g[f"dist_{name}_{k}"]) for k in ("pc", "ts", "pose"))
+        out = np.empty((pc.shape[0], 3), np.float64)
+        pose64 = np.ascontiguousarray(pose.astype(np.float64))
+        hh.hh_distort(_p(pc), int(pc.dtype == np.float64), _p(ts), int(ts.dtype == np.float64), C.c_int64(pc.shape[0]),
+                      _p(pose64), int(pose.dtype == np.float64), _p(out))
+        err = np.abs(out - g[f"dist_{name}_out"]).max()
+        assert err <= dist_tol(pose), (name, err)
+
+
+def test_distort_nan_timestamp_poisons_everything(hh, golden_next):
+    g = golden_next
+    pc, ts, pose = (np.ascontiguousarray(g[f"dist_f64_{k}"]) for k in ("pc", "ts", "pose"))
+    ts = ts.copy()
+    ts[17] = np.nan
+    out = np.zeros((pc.shape[0], 3), np.float64)
+    hh.hh_distort(_p(pc), 0, _p(ts), 1, C.c_int64(pc.shape[0]), _p(pose), 1, _p(out))
+    assert np.isnan(out).all()  # np.max / np.min propagate the NaN into every alpha (preprocessing.py:180-182)
+
+
+def test_rotation_vector_branches(hh):
+    from scipy.spatial.transform import Rotation
+    rng = np.random.RandomState(3)
+    for angle in [0.0, 1e-12, 1e-9, 1e-5, 0.3, 2.0, np.pi - 1e-5, np.pi - 1e-10, np.pi]:
+        axis = rng.randn(3)
+        axis /= np.linalg.norm(axis)
+        R = np.ascontiguousarray(Rotation.from_rotvec(axis * angle).as_matrix())
+        ax, an = np.zeros(3), C.c_double(0)
+        hh.hh_rotation_vector(_p(R), _p(ax), C.byref(an))
+        back = Rotation.from_rotvec(ax * an.value).as_matrix()
+        assert np.abs(back - R).max() <= 1e-7 if angle > 3.1 else np.abs(back - R).max() <= 1e-12, angle
+
+
+def test_kabsch_tail_matches_reference(hh, golden_next):
+    g = golden_next
+
+    def run(pt, pr, w=None):
+        w = np.ones((pt.shape[0], 1)) if w is None else w
+        aw = w / w.sum()
+        mu_t, mu_r = (pt * aw).sum(0), (pr * aw).sum(0)
+        Cm = np.ascontiguousarray((pr - mu_r).T @ (pt - mu_t))
+        mu = np.ascontiguousarray(np.concatenate([mu_t, mu_r]))
+        T = np.zeros(16)
+        hh.hh_kabsch(_p(Cm), _p(mu), _p(T))
+        return T.reshape(4, 4)
+
+    pt, pr = g["proc_tgt"], g["proc_ref"]
+    assert np.abs(run(pt, pr) - g["proc_T"]).max() <= 1e-12
+    assert np.abs(run(pt, pr, g["proc_w"]) - g["proc_T_w"]).max() <= 1e-12
+    Tm = run(pt, g["proc_ref_mirror"])
+    assert np.abs(Tm - g["proc_T_mirror"]).max() <= 1e-12 and np.linalg.det(Tm[:3, :3]) > 0.999
+    assert np.abs(run(g["proc_planar_tgt"], g["proc_planar_ref"]) - g["proc_T_planar"]).max() <= 1e-9
+    # random rotations incl. near-degenerate spectra
+    rng = np.random.RandomState(0)
+    from scipy.spatial.transform import Rotation
+    for scale in ([1, 1, 1], [5, 1, 0.01], [3, 3, 1], [1, 1e-4, 1e-4]):
+        p = rng.randn(200, 3) * np.array(scale)
+        R = Rotation.random(random_state=rng.randint(1 << 30)).as_matrix()
+        t = rng.randn(3)
+        T = run(p, p @ R.T + t)
+        tol = 1e-9 if min(scale) >= 0.01 else 1e-5
+        assert np.abs(T[:3, :3] - R).max() <= tol and np.abs(T[:3, 3] - t).max() <= tol * 10, scale
+
+
+def _align(hh, cost, ref, tgt, nrm, scheme, sigma, max_iters, norm_stop, x0=None):
+    dt = ref.dtype
+    n = ref.shape[0]
+    x, dT, loss = np.zeros(6, dt), np.zeros(16, dt), np.zeros(n, dt)
+    st = hh.hh_align(cost, int(dt == np.float64), _p(np.ascontiguousarray(ref)), _p(np.ascontiguousarray(tgt)),
+                     _p(None if nrm is None else np.ascontiguousarray(nrm)), C.c_int64(n), SCHEMES[scheme], C.c_double(sigma),
+                     max_iters, C.c_double(norm_stop), _p(None if x0 is None else np.ascontiguousarray(x0.astype(dt))),
+                     _p(x), _p(dT), _p(loss))
+    return st, x, dT.reshape(4, 4), loss
+
+
+@pytest.mark.parametrize("scheme", [s for s in SCHEMES if s != "least_square"])
+def test_p2point_device_math_matches_reference(hh, golden_next, scheme):
+    g = golden_next
+    st, x, dT, loss = _align(hh, 1, g["p2p_ref"], g["p2p_tgt"], None, scheme, 0.3, 1, 1e-3)
+    assert st == 0
+    rx = g[f"p2p_{scheme}_x"]
+    assert np.abs(x - rx).max() <= 2e-5 * max(1.0, np.abs(rx).max())
+    assert np.abs(dT - g[f"p2p_{scheme}_dT"]).max() <= 2e-5
+    rl = g[f"p2p_{scheme}_loss"]
+    assert np.abs(loss - rl).max() <= 1e-5 * max(1.0, np.abs(rl).max())
+
+
+def test_p2point_device_math_x0_multi_f64(hh, golden_next):
+    g = golden_next
+    ref, tgt = g["p2p_ref"], g["p2p_tgt"]
+    st, x, dT, loss = _align(hh, 1, ref, tgt, None, "geman_mcclure", 0.3, 4, 1e-9, x0=g["p2p_multi_x0"])
+    assert st == 0 and np.abs(x - g["p2p_multi_x"]).max() <= 2e-3  # see tests/test_next_rows_oracle.py
+    st, x, dT, loss = _align(hh, 1, ref, tgt, None, "huber", 0.3, 1, 1e-3, x0=g["p2p_multi_x0"])
+    assert np.abs(x - g["p2p_mat_x"]).max() <= 2e-5 * max(1.0, np.abs(g["p2p_mat_x"]).max())
+    st, x, dT, loss = _align(hh, 1, ref.astype(np.float64), tgt.astype(np.float64), None, "default", 0.5, 6, 1e-12)
+    assert st == 0
+    assert np.abs(x - g["p2p_f64_x"]).max() <= 1e-9 and np.abs(dT - g["p2p_f64_dT"]).max() <= 1e-9
+    assert np.abs(loss - g["p2p_f64_loss"]).max() <= 1e-9
+
+
+def test_p2plane_device_math_matches_reference(hh, golden_helpers):
+    """Same harness on the hot path's own alignment: the goldens of a11-a15."""
+    g = golden_helpers
+    for scheme in ["default", "huber", "geman_mcclure", "cauchy"]:
+        st, x, dT, loss = _align(hh, 0, g["gn_ref"], g["gn_tgt"], g["gn_nrm"], scheme, 0.3, 1, 1e-3)
+        assert st == 0
+        assert np.abs(x - g[f"gn_{scheme}_delta"]).max() <= 2e-6, scheme
+        assert np.abs(loss - g[f"gn_{scheme}_loss"]).max() <= 1e-5 * max(1.0, np.abs(g[f"gn_{scheme}_loss"]).max())

@@ -1,0 +1,177 @@
+"""Development helper (NOT part of the product, never imported by it): runs the bodies of tests/test_gpu_next_rows.py on
+a machine without a GPU by standing a CPU fake in for the four new C-ABI entry points (and the few old ones those
+tests touch).  The fake follows include/plslam_b200.h argument by argument and computes with the CPU oracle / the host
+harness, so it checks the Python mirrors' plumbing and the tests' own logic (shapes, dtypes, tolerances, error
+paths) before GPU minutes are spent.  It proves nothing about the kernels -- tests/test_host_math.py and the `-m gpu`
+run do that.
+
+    python tools/dryrun_next_rows.py
+"""
+import ctypes as C
+import os
+import sys
+import traceback
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle import icp_oracle as orc  # noqa: E402
+from oracle import next_rows_oracle as nxt  # noqa: E402
+from pylidar_slam_b200 import _lib  # noqa: E402
+
+SCHEME_NAMES = {v: k for k, v in _lib.SCHEMES.items()}
+
+
+def arr(addr, shape, dtype):
+    if addr is None:
+        return None
+    if hasattr(addr, "value"):
+        addr = addr.value
+    n = int(np.prod(shape))
+    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(int(addr))
+    return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+
+class FakeContext:
+    def __init__(self, **kwargs):
+        self.kwargs = kwargs
+
+    def close(self):
+        pass
+
+    def call(self, name, *a):
+        return getattr(self, name)(*a)
+
+    def pls_distort(self, xyz, x64, ts, t64, n, pose, p64, out):
+        pc = arr(xyz, (n, 3), np.float64 if x64 else np.float32)
+        t = arr(ts, (n,), np.float64 if t64 else np.float32)
+        P = arr(pose, (4, 4), np.float64 if p64 else np.float32)
+        arr(out, (n, 3), np.float64)[:] = nxt.distort(pc, t, P)
+
+    def pls_voxel_statistics(self, xyz, is64, n, voxel, coords, hashes, sizes, means, covs, ids, count):
+        dt = np.float64 if is64 else np.float32
+        r = nxt.voxelization(arr(xyz, (n, 3), dt), voxel)
+        V = len(r["voxel_sizes"])
+        if coords:
+            arr(coords, (n, 3), np.int64)[:] = r["voxel_coordinates"]
+        if hashes:
+            arr(hashes, (n,), np.int64)[:] = r["voxel_hashes"]
+        arr(sizes, (n,), np.int64)[:V] = r["voxel_sizes"]
+        arr(means, (n, 3), dt)[:V] = r["voxel_means"]
+        arr(covs, (n, 3, 3), dt)[:V] = r["voxel_covariances"]
+        arr(ids, (n,), np.int64)[:] = r["voxel_indices"]
+        count._obj.value = V
+
+    def pls_voxel_hash(self, xyz, is64, n, voxel, coords, hashes):
+        c = orc.voxel_coords(arr(xyz, (n, 3), np.float64 if is64 else np.float32), voxel)
+        if coords:
+            arr(coords, (n, 3), np.int64)[:] = c
+        if hashes:
+            arr(hashes, (n,), np.int64)[:] = orc.voxel_hashes(c)
+
+    def pls_grid_sample(self, xyz, is64, n, voxel, out, idx, count):
+        dt = np.float64 if is64 else np.float32
+        s, i = orc.grid_sample(arr(xyz, (n, 3), dt), voxel)
+        arr(out, (n, 3), dt)[:len(i)] = s
+        if idx:
+            arr(idx, (n,), np.int64)[:len(i)] = i
+        count._obj.value = len(i)
+
+    def pls_align_p2point(self, ref, tgt, n, is64, scheme, sigma, max_iters, norm_stop, x0, dT, x, loss):
+        dt = np.float64 if is64 else np.float32
+        r, t = (torch.from_numpy(arr(p, (1, n, 3), dt).copy()) for p in (ref, tgt))
+        x0t = None if not x0 else torch.from_numpy(arr(x0, (1, 6), dt).copy())
+        try:
+            dTo, xo, lo, status = nxt.align_p2point(r, t, SCHEME_NAMES[scheme], sigma, max_iters, norm_stop, x0t)
+        except orc.SingularHessian:
+            return _lib.check(None, _lib.PLS_E_SINGULAR)
+        arr(dT, (4, 4), dt)[:] = dTo[0].numpy()
+        arr(x, (6,), dt)[:] = xo[0].numpy()
+        arr(loss, (n,), dt)[:] = lo[0].numpy()
+        if status == "tiny_residual":
+            import logging
+            logging.warning("The residual norm is lower than threshold 1e-7. ")
+
+    def pls_weighted_procrustes(self, tgt, ref, w, n, is64, out):
+        dt = np.float64 if is64 else np.float32
+        ww = None if not w else arr(w, (n, 1), dt)
+        arr(out, (4, 4), np.float64)[:] = nxt.weighted_procrustes(arr(tgt, (n, 3), dt), arr(ref, (n, 3), dt), ww)
+
+    def pls_build_pose_matrix(self, params, batch, out):
+        arr(out, (batch, 4, 4), np.float32)[:] = orc.build_pose_matrix(torch.from_numpy(arr(params, (batch, 6), np.float32).copy())).numpy()
+
+    def pls_from_pose_matrix(self, mats, batch, out):
+        arr(out, (batch, 6), np.float32)[:] = orc.from_pose_matrix(torch.from_numpy(arr(mats, (batch, 4, 4), np.float32).copy())).numpy()
+
+
+def main():
+    import pylidar_slam_b200 as b200
+    from pylidar_slam_b200 import common
+    _lib.Context = FakeContext
+    common._default_ctx = FakeContext()
+    torch.Tensor.cuda = lambda self, *a, **k: self  # device-tensor legs degrade to CPU tensors
+    import conftest
+    import test_gpu_next_rows as T
+    g = np.load(os.path.join(ROOT, "tests", "golden", "next_rows.npz"))
+    from pylidar_slam_b200 import synthetic as syn
+
+    class Caplog:
+        records = []
+
+        def at_level(self, lvl):
+            import contextlib
+            import logging
+            cap = self
+
+            class H(logging.Handler):
+                def emit(self, record):
+                    record.message = record.getMessage()
+                    cap.records.append(record)
+
+            @contextlib.contextmanager
+            def cm():
+                h = H()
+                logging.getLogger().addHandler(h)
+                try:
+                    yield
+                finally:
+                    logging.getLogger().removeHandler(h)
+            return cm()
+
+    runs = []
+    for name in T.DIST_CASES:
+        runs.append((f"distortion_golden[{name}]", lambda name=name: T.test_distortion_golden(b200, g, name)))
+    runs += [("distortion_inactive", lambda: T.test_distortion_inactive_paths_return_the_input(b200, g)),
+             ("distortion_full_64", lambda: T.test_distortion_full_size_vs_oracle_and_properties(b200, nxt, syn, 64, 2048)),
+             ("distortion_nan_single", lambda: T.test_distortion_nan_and_single_point(b200, g)),
+             ("chain", lambda: T.test_shipped_chain_distortion_grid_sample_to_tensor(b200, g))]
+    for name in T.VOX_CASES:
+        runs.append((f"vox_golden[{name}]", lambda name=name: T.test_voxelization_golden(b200, g, name)))
+    runs += [("vox_nostats_errors", lambda: T.test_voxelization_without_statistics_and_errors(b200, g))]
+    for n, v in [(131072, 0.2), (2049, 0.05), (200000, 25.0)]:
+        runs.append((f"vox_full[{n}]", lambda n=n, v=v: T.test_voxelization_full_size_vs_oracle_and_properties(b200, nxt, syn, n, v)))
+    runs += [("vox_device", lambda: T.test_voxelization_device_tensor(b200, nxt))]
+    for s in T.SCHEMES:
+        runs.append((f"p2p_step[{s}]", lambda s=s: T.test_p2point_step_golden(b200, g, s)))
+    runs += [("p2p_x0_multi", lambda: T.test_p2point_initial_estimates_multi_iter_f64_and_device(b200, g)),
+             ("p2p_large_errors", lambda: T.test_p2point_large_vs_oracle_and_error_behaviour(b200, nxt, Caplog())),
+             ("procrustes_golden", lambda: T.test_procrustes_golden(b200, g)),
+             ("procrustes_scan", lambda: T.test_procrustes_scan_size_round_trip(b200, nxt, syn))]
+    bad = 0
+    for name, fn in runs:
+        try:
+            fn()
+            print("ok  ", name)
+        except Exception as e:
+            bad += 1
+            print("FAIL", name, type(e).__name__, str(e)[:300])
+            traceback.print_exc(limit=4)
+    print("dry run:", len(runs) - bad, "ok,", bad, "failed (is_cuda asserts are expected to fail here)")
+
+
+if __name__ == "__main__":
+    main()
