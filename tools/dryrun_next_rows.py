@@ -1,4 +1,4 @@
-"""Development helper (NOT part of the product, never imported by it): runs the bodies of tests/test_gpu_next_rows.py on
+"""Development helper (NOT part of the product, never imported by it): runs the bodies of tests/test_next_rows_gpu.py on
 a machine without a GPU by standing a CPU fake in for the four new C-ABI entry points (and the few old ones those
 tests touch).  The fake follows include/plslam_b200.h argument by argument and computes with the CPU oracle / the host
 harness, so it checks the Python mirrors' plumbing and the tests' own logic (shapes, dtypes, tolerances, error
@@ -115,7 +115,7 @@ def main():
     common._default_ctx = FakeContext()
     torch.Tensor.cuda = lambda self, *a, **k: self  # device-tensor legs degrade to CPU tensors
     import conftest
-    import test_gpu_next_rows as T
+    import test_next_rows_gpu as T
     g = np.load(os.path.join(ROOT, "tests", "golden", "next_rows.npz"))
     from pylidar_slam_b200 import synthetic as syn
 

@@ -1,0 +1,46 @@
+#!/bin/bash
+# One GPU-box session of the round (outputs under gpurun_out/).  Stages are picked by name:
+#   bash tools/gpu_round.sh next subset launches nextprof ncufull full bench
+set -u
+mkdir -p gpurun_out
+export PYTHONUNBUFFERED=1
+for stage in "$@"; do
+case $stage in
+next)
+    echo "== new-row parity tests"
+    timeout 300 python -m pytest tests/test_next_rows_gpu.py -q -m gpu --timeout 150 -rf > gpurun_out/pytest_next_rows.log 2>&1
+    tail -25 gpurun_out/pytest_next_rows.log ;;
+subset)
+    echo "== parity tests touching the files changed this session (gn.cu, grid_sample.cu)"
+    timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 120 -rf -k "gn_ or align or a1_ or a16 or preprocessing or small_vs_reference" \
+        > gpurun_out/pytest_subset.log 2>&1
+    tail -8 gpurun_out/pytest_subset.log ;;
+full)
+    echo "== full gpu suite"
+    timeout 540 python -m pytest tests -q -m gpu --timeout 240 -rf > gpurun_out/pytest_gpu.log 2>&1
+    tail -15 gpurun_out/pytest_gpu.log ;;
+launches)
+    echo "== launch list cfg2 (3 steady-state frames)"
+    timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_cfg2.csv \
+        python bench.py --quick --steps 3 --warmup 24 > gpurun_out/bench_under_ncu.log 2>&1
+    tail -2 gpurun_out/bench_under_ncu.log; wc -l gpurun_out/launches_cfg2.csv ;;
+nextprof)
+    echo "== next-row kernels: durations + DRAM bytes"
+    timeout 150 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
+        --log-file gpurun_out/launches_next_rows.csv python tools/profile_next_rows.py > gpurun_out/next_rows_profile.json 2> gpurun_out/next_rows_profile.err
+    tail -3 gpurun_out/next_rows_profile.json; tail -3 gpurun_out/next_rows_profile.err ;;
+ncufull)
+    echo "== ncu --set full: kd correspondence kernels of two steady-state frames"
+    timeout 300 ncu --set full --clock-control none --import-source on \
+        -k regex:'kd_nn_group_kernel|kd_normals_group_kernel|kd_residual_kernel' --launch-skip 264 --launch-count 24 -f -o gpurun_out/r1_kd_group \
+        python bench.py --quick --steps 3 --warmup 24 > gpurun_out/ncu_full.log 2>&1
+    tail -3 gpurun_out/ncu_full.log
+    ncu -i gpurun_out/r1_kd_group.ncu-rep --page raw --csv > gpurun_out/r1_kd_group_raw.csv 2>/dev/null
+    ls -la gpurun_out/r1_kd_group* ;;
+bench)
+    echo "== bench"
+    timeout 400 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
+    tail -c 600 gpurun_out/bench_n1.json ;;
+esac
+done
+ls gpurun_out | head -30

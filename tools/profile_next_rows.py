@@ -1,0 +1,41 @@
+"""Runs the four kernels either side of the hot path once each at the BASELINE scan sizes on device-resident inputs
+(meant to run under `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum`), and prints
+the algorithmic bytes per launch so that achieved GB/s can be set against the HBM roofline."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import pylidar_slam_b200 as b200  # noqa: E402
+from pylidar_slam_b200 import synthetic as syn  # noqa: E402
+
+out = {}
+for H, W in ((64, 2048), (128, 4096)):
+    pc = syn.scan(3, H, W)
+    n = pc.shape[0]
+    az = np.arctan2(pc[:, 1].astype(np.float64), pc[:, 0].astype(np.float64))
+    ts = 1.6e9 + 0.1 * ((az + np.pi) / (2 * np.pi))
+    pose = syn.gt_relative_pose(3)
+    d_pc, d_ts = torch.from_numpy(pc).cuda(), torch.from_numpy(ts).cuda()
+    for rep in range(2):
+        d = b200.distort_frame(d_pc, d_ts, pose)
+        stats = b200.voxel_statistics(d_pc, 0.2)
+    V = int(stats[2].shape[0])
+    moved = torch.from_numpy((pc.astype(np.float64) @ pose[:3, :3].T + pose[:3, 3]).astype(np.float32)).cuda()
+    al = b200.RIGID_ALIGNMENT.load(dict(mode="point_to_point_gauss_newton", gauss_newton_config=dict(scheme="huber", sigma=0.3, max_iters=1)))
+    for rep in range(2):
+        al.align(moved.unsqueeze(0), d_pc.unsqueeze(0))
+        T = b200.weighted_procrustes(d_pc, moved)
+    out[f"{H}x{W}"] = {
+        "points": n, "voxels": V,
+        "distort_kernel_bytes": n * (12 + 8 + 24), "ts_minmax_kernel_bytes": n * 8,
+        "voxel_stats_kernel_bytes": n * (4 + 12) * 2 + V * (4 + 8 + 12 + 36),
+        "gn_accumulate_kernel_p2point_bytes": n * (24 + 4) + 240,
+        "procrustes_moments_kernel_bytes": n * 24, "procrustes_cross_kernel_bytes": n * 24,
+        "procrustes_residual_max": float(np.abs(T - pose).max()),
+    }
+torch.cuda.synchronize()
+print(json.dumps(out))
