@@ -13,9 +13,10 @@ sigma 0.3, <= 10 alignments, constant-velocity initialisation), on a seeded synt
 * `e2e`    : frames/s through the reference-shaped Python API (Preprocessing[GridSample, ToTensor]
              -> ICPFrameToModel.process_next_frame) from PINNED HOST buffers, host<->device copies
              inside the timed region.
-* roofline : the kd correspondence+reduction kernel (kd_icp_iter_kernel), CUDA-event timed inside
-             the library during the timed frames (a second pass over the same frames, so the event
-             records do not perturb `value`).
+* roofline : the kd correspondence+reduction kernels of one ICP iteration (kd_nn_group_kernel<4> +
+             kd_normals_group_kernel<4> + kd_residual_kernel, which also runs the fused solve), CUDA-event
+             timed inside the library during the timed frames (a second pass over the same frames, so the
+             event records do not perturb `value`).
 * cpu_baseline / --impl reference: the CPU oracle port of the reference path (oracle/) on the host
              cores, on a bounded sample of the same stream.
 """
@@ -330,7 +331,8 @@ def b200_arm(args):
                 "ms_per_step": 1e3 * t_e / K_},
         "gpu_launches": int(launches),
         "clocks": clock_info,
-        "roofline": {"bound": "hbm", "kernel": "kd_icp_iter_kernel (exact 1-NN + lazy 10-NN normals + point-to-plane reduction)",
+        "roofline": {"bound": "hbm", "kernel": "kd_nn_group_kernel<4> + kd_normals_group_kernel<4> + kd_residual_kernel: one ICP iteration "
+                               "(exact 1-NN, lazy 10-NN normals, point-to-plane reduction + fused solve)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic,
                      "launches": int(nn_launches), "avg_us": 1e3 * nn_ms / max(nn_launches, 1),

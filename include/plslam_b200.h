@@ -68,7 +68,11 @@ enum { PLS_MAP_KDTREE = 0, PLS_MAP_PROJECTIVE = 1 };
 enum {
     PLS_INPUT_NDARRAY = 0,    /* np.ndarray [N,3]: queries = the raw points              */
     PLS_INPUT_TENSOR = 1,     /* torch [N,3]: queries = non-null pixels of its vertex map */
-    PLS_INPUT_VERTEX_MAP = 2  /* torch [1,3,H,W]: used as the vertex map directly         */
+    PLS_INPUT_VERTEX_MAP = 2, /* torch [1,3,H,W]: used as the vertex map directly         */
+    /* float64 clouds (e.g. the output of the Distortion filter): the reference projects them in float64 and
+     * rounds the vertex map / the points to float32 afterwards (icp_odometry.py:331-352); `data` is double [n,3] */
+    PLS_INPUT_NDARRAY_F64 = 3,
+    PLS_INPUT_TENSOR_F64 = 4
 };
 
 /* Configuration = SphericalProjector (projection.py:439-450) + ICPFrameToModelConfig
@@ -190,12 +194,12 @@ PLS_API int pls_odometry_init(pls_context* ctx);
 PLS_API int pls_register_frame(pls_context* ctx, const float* points, int64_t n, const float* T0,
                        float* out_T, float* out_params, float* out_losses, int* out_iters);
 /* ICPFrameToModel.do_process_next_frame (icp_odometry.py:157-246): `data` is [n,3] points
- * (PLS_INPUT_NDARRAY / PLS_INPUT_TENSOR) or a [3,H,W] vertex map (PLS_INPUT_VERTEX_MAP, n
- * ignored).  init_pose [16] or NULL (identity).  On frame 0 the map is initialised and
+ * (PLS_INPUT_NDARRAY / PLS_INPUT_TENSOR: float; the _F64 variants: double) or a float [3,H,W] vertex map
+ * (PLS_INPUT_VERTEX_MAP, n ignored).  init_pose [16] or NULL (identity).  On frame 0 the map is initialised and
  * *out_has_pose = 0 (the reference writes no "odometry_pose" then).  out_info (optional,
  * 12 doubles): iterations, final loss, queries used, map points, grid samples, NaN rows dropped,
  * status, key-frame inserted, first non-null pixel x/y/z (vertex-map layout), 0. */
-PLS_API int pls_process_frame(pls_context* ctx, const float* data, int layout, int64_t n,
+PLS_API int pls_process_frame(pls_context* ctx, const void* data, int layout, int64_t n,
                       const float* init_pose, float* out_pose, float* out_params,
                       int* out_has_pose, double* out_info);
 /* Fused preprocessing + odometry for the shipped pipeline (grid_sample.yaml): GridSample

@@ -16,7 +16,7 @@ PLS_OK, PLS_E_INVALID, PLS_E_CUDA, PLS_E_SINGULAR, PLS_W_TINY_RESIDUAL, PLS_E_ST
 SCHEMES = {"default": 0, "least_square": 1, "huber": 2, "exp": 3, "neighborhood": 4, "geman_mcclure": 5,
            "square_geman_mcclure": 6, "cauchy": 7}
 MAP_KDTREE, MAP_PROJECTIVE = 0, 1
-INPUT_NDARRAY, INPUT_TENSOR, INPUT_VERTEX_MAP = 0, 1, 2
+INPUT_NDARRAY, INPUT_TENSOR, INPUT_VERTEX_MAP, INPUT_NDARRAY_F64, INPUT_TENSOR_F64 = 0, 1, 2, 3, 4
 
 
 class PlsConfig(C.Structure):

@@ -298,6 +298,10 @@ __device__ __forceinline__ float ordered_to_float(int i) {
 // projection.cu
 void launch_projection(pls_context* ctx, const float* xyz, const float* channels, int batch, int64_t n,
                        int C, int H, int W, float up, float down, float* out, unsigned long long* zbuf);
+// float64 cloud [n,3] -> float32 vertex map [3,H,W]: pixel math, range comparison and validity in float64, values
+// rounded to float32 at the end (what the reference does with a float64 input, icp_odometry.py:331-352)
+void launch_projection_f64(pls_context* ctx, const double* xyz, int64_t n, int H, int W, float up, float down, float* out,
+                           unsigned long long* zbuf);
 // normal_map.cu
 void launch_normal_map(pls_context* ctx, const float* vmap, int batch, int H, int W, int ksize, float* out);
 // gn.cu
@@ -321,6 +325,7 @@ int kdmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int num
                         bool* solved);
 // pack [n,3] rows without NaN into float4 (stable); count -> *count_dev (u32)
 void pack_valid_rows(pls_context* ctx, const float* pts_dev, int64_t n, float4* out, uint32_t* count_dev);
+void pack_valid_rows_f64(pls_context* ctx, const double* pts_dev, int64_t n, float4* out, uint32_t* count_dev);
 // pack the non-null pixels (any channel != 0) of a [3,H,W] map into float4, row-major order
 void pack_nonnull_pixels(pls_context* ctx, const float* vmap_dev, int64_t hw, float4* out, uint32_t* count_dev);
 // grid_sample.cu

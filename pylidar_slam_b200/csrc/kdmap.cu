@@ -90,16 +90,20 @@ kd_move_append_kernel(const float4* __restrict__ src, int64_t skip, int64_t kept
 }
 
 // [n,3] raw points -> float4, dropping rows containing NaN (utils.py:169-184); flags only.
-__global__ void kd_valid_rows_kernel(const float* __restrict__ pts, int64_t n, uint8_t* __restrict__ flags) {
+// T = double: the reference rounds a float64 cloud to float32 first (`_tgt_pc = pc_data.to(torch.float32)`,
+// icp_odometry.py:352) and removes NaN rows afterwards; NaN survives the rounding, so the order does not matter.
+template <typename T>
+__global__ void kd_valid_rows_kernel(const T* __restrict__ pts, int64_t n, uint8_t* __restrict__ flags) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        float x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+        T x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
         flags[i] = (x == x && y == y && z == z) ? 1 : 0;
     }
 }
-__global__ void kd_pack_rows_kernel(const float* __restrict__ pts, int64_t n, const uint8_t* __restrict__ flags,
+template <typename T>
+__global__ void kd_pack_rows_kernel(const T* __restrict__ pts, int64_t n, const uint8_t* __restrict__ flags,
                                     const uint32_t* __restrict__ pos, float4* __restrict__ out) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        if (flags[i]) out[pos[i]] = make_float4(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], 0.f);
+        if (flags[i]) out[pos[i]] = make_float4((float)pts[3 * i], (float)pts[3 * i + 1], (float)pts[3 * i + 2], 0.f);
 }
 // vertex map [3,H,W] -> pixels with |p| > 0.01 and no NaN (local_map.py:320-328)
 __global__ void kd_valid_pixels_kernel(const float* __restrict__ vmap, int64_t hw, uint8_t* __restrict__ flags) {
@@ -586,7 +590,8 @@ void kdmap_reset(pls_context* ctx) {
     ctx->kd.bbox_clean = false;
 }
 
-void pack_valid_rows(pls_context* ctx, const float* pts_dev, int64_t n, float4* out, uint32_t* count_dev) {
+template <typename T>
+static void pack_valid_rows_impl(pls_context* ctx, const T* pts_dev, int64_t n, float4* out, uint32_t* count_dev) {
     cudaStream_t st = ctx->stream;
     if (n <= 0) {
         PLS_CUDA(cudaMemsetAsync(count_dev, 0, sizeof(uint32_t), st));
@@ -595,11 +600,18 @@ void pack_valid_rows(pls_context* ctx, const float* pts_dev, int64_t n, float4* 
     ctx->tmp[1].reserve((size_t)n, st);
     ctx->tmp[2].reserve((size_t)n * sizeof(uint32_t), st);
     const int g = grid_for(n, 256, 8 * kNumSMs);
-    kd_valid_rows_kernel<<<g, 256, 0, st>>>(pts_dev, n, ctx->tmp[1].as<uint8_t>());
+    kd_valid_rows_kernel<T><<<g, 256, 0, st>>>(pts_dev, n, ctx->tmp[1].as<uint8_t>());
     PLS_CHECK_LAUNCH();
     exclusive_scan_flags(ctx, ctx->tmp[1].as<uint8_t>(), n, ctx->tmp[2].as<uint32_t>(), count_dev);
-    kd_pack_rows_kernel<<<g, 256, 0, st>>>(pts_dev, n, ctx->tmp[1].as<uint8_t>(), ctx->tmp[2].as<uint32_t>(), out);
+    kd_pack_rows_kernel<T><<<g, 256, 0, st>>>(pts_dev, n, ctx->tmp[1].as<uint8_t>(), ctx->tmp[2].as<uint32_t>(), out);
     PLS_CHECK_LAUNCH();
+}
+
+void pack_valid_rows(pls_context* ctx, const float* pts_dev, int64_t n, float4* out, uint32_t* count_dev) {
+    pack_valid_rows_impl<float>(ctx, pts_dev, n, out, count_dev);
+}
+void pack_valid_rows_f64(pls_context* ctx, const double* pts_dev, int64_t n, float4* out, uint32_t* count_dev) {
+    pack_valid_rows_impl<double>(ctx, pts_dev, n, out, count_dev);
 }
 
 namespace {

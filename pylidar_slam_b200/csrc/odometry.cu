@@ -265,9 +265,16 @@ bool keyframe_decision(pls_context* ctx, const float* T) {
     return insert;
 }
 
-void process_frame_device(pls_context* ctx, const float* data_dev, int layout, int64_t n, const float* init_pose,
+void process_frame_device(pls_context* ctx, const void* data_void, int layout, int64_t n, const float* init_pose,
                           float* out_pose, float* out_params, int* out_has_pose, double* out_info) {
     cudaStream_t st = ctx->stream;
+    // float64 point layouts: same flow, the cloud is rounded to float32 for the queries / map insertion while the frame's
+    // own vertex map is projected in float64 (icp_odometry.py:331-352)
+    const bool is64 = layout == PLS_INPUT_NDARRAY_F64 || layout == PLS_INPUT_TENSOR_F64;
+    if (layout == PLS_INPUT_NDARRAY_F64) layout = PLS_INPUT_NDARRAY;
+    if (layout == PLS_INPUT_TENSOR_F64) layout = PLS_INPUT_TENSOR;
+    const float* data_dev = is64 ? nullptr : (const float*)data_void;
+    const double* data64 = is64 ? (const double*)data_void : nullptr;
     const int H = ctx->cfg.height, W = ctx->cfg.width;
     const int64_t hw = (int64_t)H * W;
     const bool kd = ctx->cfg.local_map_type == PLS_MAP_KDTREE;
@@ -296,15 +303,20 @@ void process_frame_device(pls_context* ctx, const float* data_dev, int layout, i
     } else {
         PLS_REQUIRE(n > 0, "process_frame: empty point cloud");
         frame_pts.reserve((size_t)n * sizeof(float4), st);
-        pack_valid_rows(ctx, data_dev, n, frame_pts.as<float4>(), count_slot(ctx, 2));
+        if (is64) pack_valid_rows_f64(ctx, data64, n, frame_pts.as<float4>(), count_slot(ctx, 2));
+        else pack_valid_rows(ctx, data_dev, n, frame_pts.as<float4>(), count_slot(ctx, 2));
         pts_bound = n;
         // the vertex map of the points is needed on frame 0 (map initialisation), as the query
         // source when _sample_pointcloud is False, and by the projective map's update
         if (first || !ctx->sample_pointcloud || !kd) {
             ctx->tmp[3].reserve((size_t)hw * sizeof(unsigned long long), st);
-            launch_projection(ctx, data_dev, nullptr, 1, n, 3, H, W, ctx->cfg.up_fov_deg, ctx->cfg.down_fov_deg,
-                              frame_vmap.as<float>(), ctx->tmp[3].as<unsigned long long>());
-            }
+            if (is64)
+                launch_projection_f64(ctx, data64, n, H, W, ctx->cfg.up_fov_deg, ctx->cfg.down_fov_deg, frame_vmap.as<float>(),
+                                      ctx->tmp[3].as<unsigned long long>());
+            else
+                launch_projection(ctx, data_dev, nullptr, 1, n, 3, H, W, ctx->cfg.up_fov_deg, ctx->cfg.down_fov_deg,
+                                  frame_vmap.as<float>(), ctx->tmp[3].as<unsigned long long>());
+        }
     }
 
     float eye[16];
@@ -463,15 +475,16 @@ int pls_register_frame(pls_context* ctx, const float* points, int64_t n, const f
     PLS_API_END(ctx)
 }
 
-int pls_process_frame(pls_context* ctx, const float* data, int layout, int64_t n, const float* init_pose,
+int pls_process_frame(pls_context* ctx, const void* data, int layout, int64_t n, const float* init_pose,
                       float* out_pose, float* out_params, int* out_has_pose, double* out_info) {
     PLS_API_BEGIN(ctx)
     PLS_REQUIRE(data, "pls_process_frame: null data");
-    PLS_REQUIRE(layout >= PLS_INPUT_NDARRAY && layout <= PLS_INPUT_VERTEX_MAP, "pls_process_frame: unknown layout");
+    PLS_REQUIRE(layout >= PLS_INPUT_NDARRAY && layout <= PLS_INPUT_TENSOR_F64, "pls_process_frame: unknown layout");
     PLS_REQUIRE(ctx->cfg.gn_max_iters == 1, "fused ICP path supports gauss_newton_config.max_iters == 1");
+    const bool is64 = layout == PLS_INPUT_NDARRAY_F64 || layout == PLS_INPUT_TENSOR_F64;
     const size_t bytes = layout == PLS_INPUT_VERTEX_MAP ? (size_t)3 * ctx->cfg.height * ctx->cfg.width * sizeof(float)
-                                                        : (size_t)n * 3 * sizeof(float);
-    const float* d = (const float*)to_device(ctx, data, bytes, ctx->stage_in[0]);
+                                                        : (size_t)n * 3 * (is64 ? sizeof(double) : sizeof(float));
+    const void* d = to_device(ctx, data, bytes, ctx->stage_in[0]);
     process_frame_device(ctx, d, layout, n, init_pose, out_pose, out_params, out_has_pose, out_info);
     PLS_API_END(ctx)
 }

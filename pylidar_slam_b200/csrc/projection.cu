@@ -58,6 +58,66 @@ __global__ void resolve_kernel(const unsigned long long* __restrict__ zbuf, cons
     }
 }
 
+// ---- float64 clouds ----------------------------------------------------------------------------------------------
+// With a float64 `input_data` / `numpy_pc` (what the de-skew filter produces) the reference runs the whole projection in
+// float64 -- pixel coordinates, rounding, the range the z-buffer sorts by -- and only rounds the finished vertex map to
+// float32 (icp_odometry.py:331-352).  Same arithmetic here; a 64-bit range leaves no room for the point index in the
+// atomic word, so the winner is found in two passes: the smallest range per pixel, then the lowest index having it.
+struct ProjConst64 {
+    int H, W;
+    double Hf, Wf, abs_down, fov;
+};
+
+__device__ __forceinline__ bool project_to_pixel_f64(double x, double y, double z, const ProjConst64& pc, int& pix, double& r) {
+    const double kPi = 3.141592653589793;  // np.pi
+    r = sqrt(x * x + y * y + z * z);
+    const bool null = (r == 0.0);
+    const double rr = null ? 0.001 : r;
+    const double theta = -atan2(y, x);
+    const double phi = asin(z / rr);
+    double c = 0.5 * (theta / kPi + 1.0);
+    double rw = 1.0 - (phi + pc.abs_down) / pc.fov;
+    c = c * pc.Wf;
+    rw = rw * pc.Hf;
+    const double pr = rint(null ? -1.0 : rw), pcn = rint(null ? -1.0 : c);
+    const bool ok = (pr >= 0.0) && (pr <= (double)(pc.H - 1)) && (pcn >= 0.0) && (pcn <= (double)(pc.W - 1)) && (r > 0.0);
+    if (!ok) return false;
+    pix = (int)pr * pc.W + (int)pcn;
+    return true;
+}
+
+__global__ void zbuf_range_f64_kernel(const double* __restrict__ xyz, int64_t n, ProjConst64 pc,
+                                      unsigned long long* __restrict__ zrange) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int pix;
+        double r;
+        if (project_to_pixel_f64(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], pc, pix, r))
+            atomicMin(&zrange[pix], (unsigned long long)__double_as_longlong(r));  // r > 0: bit order == value order
+    }
+}
+
+__global__ void zbuf_index_f64_kernel(const double* __restrict__ xyz, int64_t n, ProjConst64 pc,
+                                      const unsigned long long* __restrict__ zrange, unsigned int* __restrict__ zindex) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int pix;
+        double r;
+        if (project_to_pixel_f64(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], pc, pix, r) &&
+            (unsigned long long)__double_as_longlong(r) == zrange[pix])
+            atomicMin(&zindex[pix], (unsigned int)i);
+    }
+}
+
+__global__ void resolve_f64_kernel(const unsigned int* __restrict__ zindex, const double* __restrict__ xyz, int64_t hw,
+                                   float* __restrict__ out) {
+    for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < hw; pix += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned int i = zindex[pix];
+        const bool empty = (i == 0xffffffffu);
+        out[pix] = empty ? 0.f : (float)xyz[3 * (size_t)i];
+        out[hw + pix] = empty ? 0.f : (float)xyz[3 * (size_t)i + 1];
+        out[2 * hw + pix] = empty ? 0.f : (float)xyz[3 * (size_t)i + 2];
+    }
+}
+
 inline int grid_for(int64_t n, int threads = 256) {
     int64_t b = (n + threads - 1) / threads;
     int64_t cap = 16 * kNumSMs;
@@ -91,6 +151,34 @@ void launch_projection(pls_context* ctx, const float* xyz, const float* channels
         PLS_CHECK_LAUNCH();
     }
     resolve_kernel<<<grid_for((int64_t)batch * hw), 256, 0, st>>>(zbuf, channels ? channels : xyz, batch, n, C, hw, out);
+    PLS_CHECK_LAUNCH();
+}
+
+void launch_projection_f64(pls_context* ctx, const double* xyz, int64_t n, int H, int W, float up, float down, float* out,
+                           unsigned long long* zbuf) {
+    cudaStream_t st = ctx->stream;
+    const int64_t hw = (int64_t)H * W;
+    PLS_REQUIRE(n < 0xffffffffll, "projection: at most 2^32 - 1 points per cloud");
+    ProjConst64 pc;
+    pc.H = H;
+    pc.W = W;
+    pc.Hf = (double)H;
+    pc.Wf = (double)W;
+    // fov_up = up / 180.0 * np.pi etc. in Python floats (projection.py:47-49)
+    pc.abs_down = fabs((double)down / 180.0 * 3.141592653589793);
+    pc.fov = pc.abs_down + fabs((double)up / 180.0 * 3.141592653589793);
+    // zbuf holds hw 64-bit range words; the 32-bit winner indices live in the scratch of the stateless filters
+    ctx->next_buf[7].reserve((size_t)hw * sizeof(unsigned int), st);
+    unsigned int* zindex = ctx->next_buf[7].as<unsigned int>();
+    PLS_CUDA(cudaMemsetAsync(zbuf, 0xff, (size_t)hw * sizeof(unsigned long long), st));
+    PLS_CUDA(cudaMemsetAsync(zindex, 0xff, (size_t)hw * sizeof(unsigned int), st));
+    if (n > 0) {
+        zbuf_range_f64_kernel<<<grid_for(n), 256, 0, st>>>(xyz, n, pc, zbuf);
+        PLS_CHECK_LAUNCH();
+        zbuf_index_f64_kernel<<<grid_for(n), 256, 0, st>>>(xyz, n, pc, zbuf, zindex);
+        PLS_CHECK_LAUNCH();
+    }
+    resolve_f64_kernel<<<grid_for(hw), 256, 0, st>>>(zindex, xyz, hw, out);
     PLS_CHECK_LAUNCH();
 }
 

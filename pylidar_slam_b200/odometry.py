@@ -514,8 +514,11 @@ class ICPFrameToModel(OdometryAlgorithm):
     def _interpret(self, data):
         """_read_input's three layouts (icp_odometry.py:319-358)."""
         H, W = self.projector.height, self.projector.width
+        # float64 clouds keep their precision up to the projection, like the reference (icp_odometry.py:331-352)
         if isinstance(data, np.ndarray):
             check_tensor(data, [-1, 3])
+            if data.dtype == np.float64:
+                return _lib.INPUT_NDARRAY_F64, np.ascontiguousarray(data), data.shape[0]
             return _lib.INPUT_NDARRAY, np.ascontiguousarray(data, dtype=np.float32), data.shape[0]
         if isinstance(data, torch.Tensor):
             if data.dim() in (3, 4):
@@ -525,6 +528,8 @@ class ICPFrameToModel(OdometryAlgorithm):
                 return _lib.INPUT_VERTEX_MAP, vm.to(torch.float32).contiguous(), 0
             assert_debug(data.dim() == 2)
             check_tensor(data, [-1, 3])
+            if data.dtype == torch.float64:
+                return _lib.INPUT_TENSOR_F64, data.contiguous(), data.shape[0]
             return _lib.INPUT_TENSOR, data.to(torch.float32).contiguous(), data.shape[0]
         raise RuntimeError(f"Could not interpret the data: {data} as a pointcloud tensor")
 
@@ -553,6 +558,7 @@ class ICPFrameToModel(OdometryAlgorithm):
             tgt_np_pc = self.last_info[8:11].astype(np.float32).reshape(1, 3)  # icp_odometry.py:342-358 quirk
         else:
             tgt_np_pc = data if isinstance(data, np.ndarray) else data.detach().cpu().numpy()
+            tgt_np_pc = tgt_np_pc.astype(np.float32, copy=False)  # _tgt_pc is float32 (icp_odometry.py:352)
             if self.last_info[5] > 0:
                 tgt_np_pc = tgt_np_pc[~np.isnan(tgt_np_pc).any(axis=1)]
         data_dict[self.pointcloud_key()] = tgt_np_pc

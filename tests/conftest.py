@@ -49,6 +49,20 @@ def golden_next():
     return np.load(os.path.join(GOLDEN, "next_rows.npz"))
 
 
+@pytest.fixture(scope="session")
+def golden_chain():
+    return np.load(os.path.join(GOLDEN, "chain_icp.npz"))
+
+
+def chain_timestamps(points, seed):
+    """Per-point acquisition times of the synthetic spinning LiDAR (same formula as tests/golden/make_golden_*.py)."""
+    az = np.arctan2(points[:, 1].astype(np.float64), points[:, 0].astype(np.float64))
+    return 1.6e9 + 0.1 * ((az + np.pi) / (2 * np.pi)) + np.random.RandomState(seed).uniform(0, 1e-4, points.shape[0])
+
+
+CHAIN_CASES = [("tensor", "input_data", 8, 1e-4), ("tensor_fixed6", "input_data", 6, 0.0), ("ndarray_fixed6", "numpy_pc", 6, 0.0)]
+
+
 def dist_tol(pose):
     """Tolerance [m] of a de-skewed frame against the reference's.  A float64 pose is orthonormal to 1e-16 and
     the closed-form interpolation agrees with scipy's quaternion Slerp to a few ulp of the coordinates (1e-11

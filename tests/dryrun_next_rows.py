@@ -5,7 +5,7 @@ harness, so it checks the Python mirrors' plumbing and the tests' own logic (sha
 paths) before GPU minutes are spent.  It proves nothing about the kernels -- tests/test_host_math.py and the `-m gpu`
 run do that.
 
-    python tools/dryrun_next_rows.py
+    python tests/dryrun_next_rows.py
 """
 import ctypes as C
 import os
@@ -17,7 +17,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))  # conftest helpers
 
 from oracle import icp_oracle as orc  # noqa: E402
 from oracle import next_rows_oracle as nxt  # noqa: E402

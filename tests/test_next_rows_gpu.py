@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import check_voxel_stats, dist_tol
+from conftest import CHAIN_CASES, chain_timestamps, check_pose_sequence, check_voxel_stats, dist_tol
 
 pytestmark = pytest.mark.gpu
 
@@ -129,43 +129,70 @@ def test_shipped_chain_distortion_grid_sample_to_tensor(b200, golden_next):
     assert dd["input_data"].dtype == torch.float64 and tuple(dd["input_data"].shape) == g["chain_sample"].shape
 
 
-def test_odometry_on_the_deskewed_chain_matches_oracle(b200, orc, nxt, syn):
-    """The whole shipped pipeline: distortion -> grid_sample -> to_tensor -> ICPFrameToModel (kd map), frame by frame
-    against the CPU oracle fed with the oracle's own de-skew; the scans are static-world, so the de-skew is a
-    consistent perturbation both sides must reproduce identically (poses: 1e-4 rel. translation / 1e-5 rad)."""
-    from conftest import pose_errors
-    H, W, frames = 32, 512, 6
-    proj = b200.SphericalProjector(height=H, width=W, up_fov=3.0, down_fov=-24.0)
+@pytest.mark.parametrize("case", CHAIN_CASES, ids=[c[0] for c in CHAIN_CASES])
+def test_whole_shipped_chain_vs_reference_golden(b200, syn, golden_chain, case):
+    """The whole shipped pipeline -- Distortion -> GridSample(0.4) -> ToTensor -> ICPFrameToModel (kd map) -- against
+    the poses of the unmodified reference (tests/golden/chain_icp.npz).  The de-skewed samples are float64: the frame's
+    vertex map is projected in float64 like the reference's (PLS_INPUT_TENSOR_F64 / _NDARRAY_F64).  Poses: 1e-4
+    relative translation / 1e-5 rad, stop-rule aware for the yaml threshold, strict for the fixed-iteration runs."""
+    name, key, iters, thr = case
+    H, W = 32, 512
     cfg = b200.ICPFrameToModelConfig(
         local_map=b200.KdTreeLocalMapConfig(local_map_size=4),
         alignment=b200.GaussNewtonPointToPlaneConfig(gauss_newton_config=dict(scheme="geman_mcclure", sigma=0.3, max_iters=1)),
-        max_num_alignments=6, threshold_delta_pose=0.0, data_key="input_data")
-    algo = b200.ICPFrameToModel(cfg, projector=proj, device="cuda:0")
+        max_num_alignments=iters, threshold_delta_pose=thr, data_key=key)
+    algo = b200.ICPFrameToModel(cfg, projector=b200.SphericalProjector(height=H, width=W, up_fov=3.0, down_fov=-24.0),
+                                device="cuda:0")
     algo.init()
     pre = b200.Preprocessing(b200.PreprocessingConfig(filters={
         "1": dict(filter_name="distortion", output_key="distorted"),
         "2": dict(filter_name="grid_sample", voxel_size=0.4, pointcloud_key="distorted"),
         "3": dict(filter_name="to_tensor", keys=dict(sample_points="input_data"))}))
-    ref = orc.ICPFrameToModelOracle(orc.ICPConfig(max_num_alignments=6, threshold_delta_pose=0.0, data_key="input_data",
-                                                  local_map="kdtree", local_map_size=4, scheme="geman_mcclure", sigma=0.3),
-                                    orc.Projector(H, W))
-    prev_a = prev_b = None
-    for k in range(frames):
+    prev, poses, its = None, [], []
+    for k in range(7):
         pc = syn.scan(k, H, W)
-        ts = _timestamps(pc, k)
-        da = {"numpy_pc": pc, "numpy_pc_timestamps": ts, "init_rpose": prev_a}
-        pre.forward(da)
-        algo.process_next_frame(da)
-        d = pc if prev_b is None else nxt.distort(pc, ts, prev_b)
-        s, _ = orc.grid_sample(d, 0.4)
-        db = {"input_data": torch.from_numpy(s), "init_rpose": prev_b}
-        ref.process_next_frame(db)
+        dd = {"numpy_pc": pc, "numpy_pc_timestamps": chain_timestamps(pc, k), "init_rpose": prev}
+        pre.forward(dd)
+        if k >= 2:
+            assert dd["sample_points"].dtype == np.float64 and dd["input_data"].dtype == torch.float64
+        if key == "numpy_pc":
+            dd["numpy_pc"] = dd["sample_points"]
+        algo.process_next_frame(dd)
         if k == 0:
-            assert "odometry_pose" not in da
+            assert "odometry_pose" not in dd
             continue
-        dt, ang = pose_errors(da["odometry_pose"], db["odometry_pose"])
-        assert dt <= 1e-4 and ang <= 1e-5, (k, dt, ang)
-        prev_a, prev_b = da["odometry_pose"].astype(np.float64), db["odometry_pose"].astype(np.float64)
+        assert dd["odometry_pose"].dtype == np.float32 and dd["odometry_pc"].dtype == np.float64  # the "distorted" frame
+        poses.append(dd["odometry_pose"].copy())
+        its.append(int(algo.last_info[0]))
+        prev = dd["odometry_pose"].astype(np.float64)
+    check_pose_sequence(np.stack(poses), its, golden_chain[f"{name}_poses"], golden_chain[f"{name}_losses"],
+                        threshold_delta_pose=max(thr, 1e-12), name=name)
+
+
+def test_float64_cloud_projection_matches_oracle(b200, orc, syn):
+    """A float64 `input_data` tensor / `numpy_pc` array keeps float64 up to the vertex map (icp_odometry.py:331-352):
+    first-frame map initialisation from a float64 cloud equals the oracle's float64 projection rounded to float32."""
+    H, W = 32, 512
+    pc = syn.scan(2, H, W).astype(np.float64) * (1.0 + 1e-9)  # not representable in float32
+    vm_ref = orc.Projector(H, W).build_projection_map(torch.from_numpy(pc).unsqueeze(0)).to(torch.float32)[0].numpy()
+    for key, data in (("input_data", torch.from_numpy(pc)), ("numpy_pc", pc), ("input_data", torch.from_numpy(pc).cuda())):
+        cfg = b200.ICPFrameToModelConfig(local_map=b200.KdTreeLocalMapConfig(local_map_size=4), max_num_alignments=4, data_key=key,
+                                         alignment=b200.GaussNewtonPointToPlaneConfig())
+        algo = b200.ICPFrameToModel(cfg, projector=b200.SphericalProjector(height=H, width=W, up_fov=3.0, down_fov=-24.0),
+                                    device="cuda:0")
+        algo.init()
+        algo.process_next_frame({key: data})
+        # frame 0 inserts the pixels of the vertex map with |p| > 0.01 (local_map.py:320-328), row-major
+        pts = vm_ref.reshape(3, -1).T
+        pts = pts[np.linalg.norm(pts, axis=1) > 0.01]
+        from pylidar_slam_b200 import _lib
+        import ctypes as C
+        m = C.c_int64(0)
+        algo.ctx.call("pls_kdmap_size", C.byref(m))
+        got = np.zeros((m.value, 3), np.float32)
+        algo.ctx.call("pls_kdmap_points", _lib.ptr(got))
+        assert got.shape == pts.shape, (key, got.shape, pts.shape)
+        np.testing.assert_array_equal(got, pts)
 
 
 # ------------------------------------------------------------------------------------------ Voxelization

@@ -6,7 +6,7 @@ import torch
 
 from oracle import icp_oracle as orc
 from oracle import next_rows_oracle as nxt
-from conftest import check_voxel_stats, dist_tol
+from conftest import CHAIN_CASES, chain_timestamps, check_pose_sequence, check_voxel_stats, dist_tol
 
 SCHEMES = ["default", "huber", "exp", "neighborhood", "geman_mcclure", "square_geman_mcclure", "cauchy"]
 DIST_CASES = ["f64", "f32", "mixed", "const", "big", "pc64"]
@@ -92,3 +92,29 @@ def test_procrustes_matches_reference(golden_next):
     Tm = nxt.weighted_procrustes(pt, g["proc_ref_mirror"])
     assert np.abs(Tm - g["proc_T_mirror"]).max() <= 1e-12 and np.linalg.det(Tm[:3, :3]) > 0.999
     assert np.abs(nxt.weighted_procrustes(g["proc_planar_tgt"], g["proc_planar_ref"]) - g["proc_T_planar"]).max() <= 1e-9
+
+
+@pytest.mark.parametrize("case", CHAIN_CASES, ids=[c[0] for c in CHAIN_CASES])
+def test_whole_shipped_chain_oracle_vs_reference(golden_chain, case):
+    """Distortion -> GridSample(0.4) -> ToTensor -> ICP (kd map) against the reference's poses.  The de-skewed
+    samples are float64, so this also pins the oracle's float64 projection (icp_odometry.py:331-352)."""
+    from pylidar_slam_b200 import synthetic as syn
+    name, key, iters, thr = case
+    H, W = 32, 512
+    algo = orc.ICPFrameToModelOracle(orc.ICPConfig(max_num_alignments=iters, threshold_delta_pose=thr, data_key=key,
+                                                   local_map="kdtree", local_map_size=4, scheme="geman_mcclure", sigma=0.3),
+                                     orc.Projector(H, W))
+    prev, poses = None, []
+    for k in range(7):
+        pc = syn.scan(k, H, W)
+        d = pc if prev is None else nxt.distort(pc, chain_timestamps(pc, k), prev)
+        s, _ = orc.grid_sample(d, 0.4)
+        assert s.dtype == (np.float32 if prev is None else np.float64)
+        dd = {"init_rpose": prev, key: (torch.from_numpy(s) if key == "input_data" else s)}
+        algo.process_next_frame(dd)
+        if "odometry_pose" in dd:
+            poses.append(dd["odometry_pose"].copy())
+            prev = dd["odometry_pose"].astype(np.float64)
+    its = [len(l) for l in algo.losses]
+    check_pose_sequence(np.stack(poses), its, golden_chain[f"{name}_poses"], golden_chain[f"{name}_losses"],
+                        threshold_delta_pose=max(thr, 1e-12), name=name)

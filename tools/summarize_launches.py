@@ -1,6 +1,9 @@
 """Summarises an `ncu --metrics gpu__time_duration.sum[,dram__bytes_*] --csv` launch list: per kernel name the launch
 count, total / average duration, share of the total kernel time and (when the DRAM counters were collected) the
-DRAM bytes per launch.  usage: python tools/summarize_launches.py launches.csv [frames]"""
+DRAM bytes per launch.
+usage: python tools/summarize_launches.py launches.csv [frames] [--last-frames N --marker KERNEL]
+  --last-frames N --marker K : keep only the launches from N occurrences of kernel K before the end, backed up to
+                               the preceding voxel_hash_kernel (the start of that frame's preprocessing)"""
 import csv
 import re
 import sys
@@ -9,12 +12,27 @@ from collections import defaultdict
 
 def main():
     path = sys.argv[1]
-    frames = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
+    frames = float(sys.argv[2]) if len(sys.argv) > 2 and not sys.argv[2].startswith("--") else 1.0
+    last = int(sys.argv[sys.argv.index("--last-frames") + 1]) if "--last-frames" in sys.argv else 0
+    marker = sys.argv[sys.argv.index("--marker") + 1] if "--marker" in sys.argv else "frame_begin_kernel"
     rows = []
     with open(path, newline="") as fh:
         lines = [ln for ln in fh if ln.startswith('"')]
     for r in csv.DictReader(lines):
         rows.append(r)
+    if last:
+        ids = []
+        for r in rows:
+            if r["ID"] not in ids:
+                ids.append(r["ID"])
+        first_row = {i: next(r for r in rows if r["ID"] == i) for i in ids}
+        marks = [i for i in ids if marker in first_row[i]["Kernel Name"]]
+        start = ids.index(marks[-last])
+        while start > 0 and "voxel_hash_kernel" not in first_row[ids[start]]["Kernel Name"]:
+            start -= 1
+        keep = set(ids[start:])
+        rows = [r for r in rows if r["ID"] in keep]
+        frames = float(last)
     per = defaultdict(lambda: defaultdict(float))
     count = defaultdict(int)
     for r in rows:
