@@ -234,6 +234,18 @@ PLS_API int pls_align_p2point(pls_context* ctx, const void* ref, const void* tgt
 PLS_API int pls_weighted_procrustes(pls_context* ctx, const void* tgt, const void* ref, const void* weights, int64_t n,
                             int is_f64, double* out_T);
 
+/* _PointToPlaneLossModule.point_to_plane_loss (slam/training/loss_modules.py:51-104), forward AND backward: the
+ * unsupervised point-to-plane training loss of a batch of (target, reference) vertex-map pairs and its gradient with
+ * respect to the predicted poses, as the reference's autograd computes it (values flow through the z-buffer scatter to
+ * every point written to a pixel; rounded pixel coordinates carry no gradient).  vm_target / vm_reference /
+ * nm_reference [B,3,H,W]; pose_mats [B,16] or NULL (then built from pose_params [B,6], Euler xyz); up/down fov of the
+ * projector; scheme / sigma = least_square_scheme.  out_loss [1] = mean_b(sum C(|r|)^2 / sum mask); optional
+ * out_loss_per_batch [B], out_grad_mats [B,16] (d loss / d pose matrix, last row 0), out_grad_params [B,6]. */
+PLS_API int pls_p2plane_loss(pls_context* ctx, const float* vm_target, const float* vm_reference,
+                     const float* nm_reference, const float* pose_mats, const float* pose_params, int batch,
+                     int height, int width, float up_fov_deg, float down_fov_deg, int scheme, float sigma,
+                     float* out_loss, float* out_loss_per_batch, float* out_grad_mats, float* out_grad_params);
+
 /* ---- multi-GPU: per-iteration allreduce of the normal-equation accumulators ---------
  * (no reference counterpart: SURVEY.md section 8e).  Every rank holds the whole local map
  * (kd) or its band of image rows (projective) and a shard of the queries; after

@@ -178,3 +178,86 @@ def weighted_procrustes(pc_target: np.ndarray, pc_reference: np.ndarray, weights
     T[:3, :3] = U @ S @ Vt
     T[:3, 3] = mu_r.astype(np.float64).reshape(3) - T[:3, :3] @ mu_t.astype(np.float64).reshape(3)
     return T
+
+
+# --------------------------------------------------------------------------------------
+# _PointToPlaneLossModule.point_to_plane_loss      slam/training/loss_modules.py:51-104
+#   (the other caller of the projection / normal-map helpers)
+# --------------------------------------------------------------------------------------
+def _cost_and_slope(scheme: str, sigma: float, a: np.ndarray, d2: np.ndarray):
+    """C(a) of _LS_SCHEME[scheme].cost (optimization.py:61-208) and dC/da, float64; `d2` = |p' - q|^2 feeds the
+    neighbourhood weights.  Returns (C, dC/da, dC/d(d2))."""
+    zero = np.zeros_like(a)
+    if scheme in ("default", "least_square"):
+        return a * a, 2 * a, zero
+    if scheme == "huber":
+        quad = a < sigma
+        return np.where(quad, a * a, 2 * sigma * a - sigma ** 2), np.where(quad, 2 * a, 2 * sigma), zero
+    if scheme == "exp":
+        e = np.exp(-a * a / sigma ** 2)
+        return a * a * e, 2 * a * e * (1 - a * a / sigma ** 2), zero
+    if scheme == "neighborhood":
+        w = np.exp(-d2 / sigma ** 2)
+        return a * a * w, 2 * a * w, -a * a * w / sigma ** 2
+    if scheme == "geman_mcclure":
+        return sigma * a * a / (sigma + a * a), 2 * sigma ** 2 * a / (sigma + a * a) ** 2, zero
+    if scheme == "square_geman_mcclure":
+        return a * a * (sigma / (sigma + a * a)) ** 2, 2 * a * sigma ** 2 * (sigma - a * a) / (sigma + a * a) ** 3, zero
+    if scheme == "cauchy":
+        return np.log(1 + (a / sigma) ** 2), 2 * a / (sigma ** 2 + a * a), zero
+    raise AssertionError(f"unknown scheme {scheme}")
+
+
+def p2plane_training_loss(vm_target: torch.Tensor, vm_reference: torch.Tensor, nm_reference: torch.Tensor,
+                          pose_mats: torch.Tensor, projector: "orc.Projector", scheme="geman_mcclure", sigma=0.5):
+    """loss = mean_b( sum_pix C(|r|)^2 / sum_pix mask ) with r = n . (q - p'), p' the transformed target point that wins
+    pixel `pix` of the re-projected target map (loss_modules.py:76-104), and its ANALYTIC gradient with respect to the
+    top three rows of the pose matrices (the reference gets it from autograd: values flow through the scatter -- to
+    every point written to a pixel, not only the surviving one -- the rounded pixel coordinates carry none).  float32 where the reference's rounding decides something (transform,
+    projection, masks), float64 for the sums.  Returns (loss, per-batch losses [B], grad [B,4,4])."""
+    B, _, H, W = vm_target.shape
+    pts = vm_target.permute(0, 2, 3, 1).reshape(B, H * W, 3)
+    alive = (pts.norm(dim=2, keepdim=True) != 0.0)
+    moved = orc.apply_transformation(pts, pose_mats) * alive
+    index = torch.arange(H * W, dtype=torch.float32).reshape(1, -1, 1).expand(B, -1, -1)
+    vm_t = projector.build_projection_map(moved, channels=torch.cat([moved, index + 1.0], dim=2), height=H, width=W)
+    pt = vm_t[:, :3].permute(0, 2, 3, 1).reshape(B, H * W, 3).numpy().astype(np.float64)
+    win = vm_t[:, 3].reshape(B, H * W).numpy().astype(np.int64) - 1  # -1 = empty pixel
+    q = vm_reference.permute(0, 2, 3, 1).reshape(B, H * W, 3).numpy()
+    n = nm_reference.permute(0, 2, 3, 1).reshape(B, H * W, 3).numpy()
+    mask = (np.linalg.norm(n, axis=-1) != 0) & (np.linalg.norm(q, axis=-1) != 0) & (np.linalg.norm(pt.astype(np.float32), axis=-1) != 0)
+    q, n = q.astype(np.float64), n.astype(np.float64)
+    r = ((q - pt) * n).sum(-1)
+    a = np.abs(r) * mask
+    d2 = ((pt - q) ** 2).sum(-1)
+    Cv, dCa, dCd2 = _cost_and_slope(scheme, sigma, a, d2)
+    M = mask.sum(1).astype(np.float64)
+    per_batch = (Cv * Cv).sum(1) / M
+    # d(C^2)/dp' = 2 C (dC/da * sign(r) * (-n) + dC/d(d2) * 2 (p' - q)), masked
+    g = (2 * Cv * (dCa * np.sign(r) * mask))[..., None] * (-n) + (2 * Cv * dCd2 * mask)[..., None] * 2 * (pt - q)
+    g = g / (M[:, None, None] * B)
+    # Backward of the z-buffer scatter `image[b, :, row, col] = values[b, order, :]` (projection.py:415): autograd's
+    # index_put backward hands EVERY scattered point the gradient of the pixel it was written to, including the
+    # points a closer one overwrote -- so all points landing in a pixel contribute g[pixel], each with its own
+    # coordinates in dL/dR.  Restated as is: the gradient must be the reference's.
+    row, col = projector.pixels(moved, H, W)
+    prow, pcol = row.round(), col.round()
+    landed = ((prow >= 0.0) & (prow <= H - 1) & (pcol >= 0.0) & (pcol <= W - 1) & (moved.norm(dim=2) > 0.0)).numpy()
+    pix = (prow.long() * W + pcol.long()).numpy()
+    src = pts.numpy().astype(np.float64)
+    grad = np.zeros((B, 4, 4))
+    for b in range(B):
+        gp = g[b][pix[b][landed[b]]]            # gradient of the pixel each landed point was written to
+        grad[b, :3, 3] = gp.sum(0)
+        grad[b, :3, :3] = gp.T @ src[b][landed[b]]
+    return float(per_batch.mean()), per_batch, grad
+
+
+def pose_matrix_grad_to_params(params: np.ndarray, grad_mats: np.ndarray) -> np.ndarray:
+    """Chain rule through Pose.build_pose_matrix (pose.py:120-144, rotation.py:166-184): [B,4,4] -> [B,6]."""
+    dR = orc.euler_jacobian(torch.from_numpy(np.asarray(params, np.float64)[:, 3:])).numpy()  # [B,3,3,3]
+    out = np.zeros((params.shape[0], 6))
+    out[:, :3] = grad_mats[:, :3, 3]
+    for k in range(3):
+        out[:, 3 + k] = (grad_mats[:, :3, :3] * dR[:, k]).sum((1, 2))
+    return out

@@ -15,4 +15,6 @@ from .odometry import (LOCAL_MAP, ODOMETRY, RIGID_ALIGNMENT, GaussNewtonPointToP
 from .preprocessing import (FILTER, Distortion, DistortionConfig, GridSample, GridSampleConfig, Preprocessing,  # noqa: F401
                             PreprocessingConfig, ToTensor, ToTensorConfig, Voxelization, VoxelizationConfig)
 
+from .training import LossConfig, PointToPlaneLossConfig, _PointToPlaneLossModule  # noqa: F401
+
 __version__ = "0.1.0"

@@ -126,19 +126,6 @@ inline int grid_for(int64_t n, int threads = 256) {
 
 }  // namespace
 
-ProjConst make_proj_const(int H, int W, float up_deg, float down_deg) {
-    ProjConst pc;
-    pc.H = H;
-    pc.W = W;
-    double up = (double)up_deg / 180.0 * 3.141592653589793;
-    double down = (double)down_deg / 180.0 * 3.141592653589793;
-    pc.abs_down = (float)fabs(down);
-    pc.fov = (float)(fabs(down) + fabs(up));
-    pc.Wf = (float)W;
-    pc.Hf = (float)H;
-    return pc;
-}
-
 void launch_projection(pls_context* ctx, const float* xyz, const float* channels, int batch, int64_t n, int C, int H,
                        int W, float up, float down, float* out, unsigned long long* zbuf) {
     cudaStream_t st = ctx->stream;

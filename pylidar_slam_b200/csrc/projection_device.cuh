@@ -2,6 +2,7 @@
 // reference's operation order.
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 
 namespace pls {
 
@@ -12,11 +13,22 @@ struct ProjConst {
     float fov;       // |fov_down| + |fov_up|
 };
 
-ProjConst make_proj_const(int H, int W, float up_deg, float down_deg);
+inline ProjConst make_proj_const(int H, int W, float up_deg, float down_deg) {
+    ProjConst pc;
+    pc.H = H;
+    pc.W = W;
+    double up = (double)up_deg / 180.0 * 3.141592653589793;
+    double down = (double)down_deg / 180.0 * 3.141592653589793;
+    pc.abs_down = (float)fabs(down);
+    pc.fov = (float)(fabs(down) + fabs(up));
+    pc.Wf = (float)W;
+    pc.Hf = (float)H;
+    return pc;
+}
 
 #ifdef __CUDACC__
 // Float pixel coordinates as torch__spherical_projection returns them: (-1,-1) for the null point.
-__device__ __forceinline__ void project_point(float x, float y, float z, const ProjConst& pc, float& row, float& col,
+__host__ __device__ __forceinline__ void project_point(float x, float y, float z, const ProjConst& pc, float& row, float& col,
                                               float& r_out) {
     const float kPi = 3.14159274101257324f;  // float(np.pi)
     float r = sqrtf(x * x + y * y + z * z);
@@ -34,7 +46,7 @@ __device__ __forceinline__ void project_point(float x, float y, float z, const P
 }
 
 // Rounded pixel index + validity (projection.py:393-401,408).  False for NaN / null / out of image.
-__device__ __forceinline__ bool project_to_pixel(float x, float y, float z, const ProjConst& pc, int& pix, float& r) {
+__host__ __device__ __forceinline__ bool project_to_pixel(float x, float y, float z, const ProjConst& pc, int& pix, float& r) {
     float row, col;
     project_point(x, y, z, pc, row, col, r);
     float pr = rintf(row), pcn = rintf(col);

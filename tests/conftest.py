@@ -54,6 +54,11 @@ def golden_chain():
     return np.load(os.path.join(GOLDEN, "chain_icp.npz"))
 
 
+@pytest.fixture(scope="session")
+def golden_loss():
+    return np.load(os.path.join(GOLDEN, "p2plane_loss.npz"))
+
+
 def chain_timestamps(points, seed):
     """Per-point acquisition times of the synthetic spinning LiDAR (same formula as tests/golden/make_golden_*.py)."""
     az = np.arctan2(points[:, 1].astype(np.float64), points[:, 0].astype(np.float64))

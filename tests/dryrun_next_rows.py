@@ -101,6 +101,24 @@ class FakeContext:
         ww = None if not w else arr(w, (n, 1), dt)
         arr(out, (4, 4), np.float64)[:] = nxt.weighted_procrustes(arr(tgt, (n, 3), dt), arr(ref, (n, 3), dt), ww)
 
+    def pls_p2plane_loss(self, vt, vr, nr, mats, params, B, H, W, up, down, scheme, sigma, loss, pb, gm, gp):
+        maps = [torch.from_numpy(arr(p, (B, 3, H, W), np.float32).copy()) for p in (vt, vr, nr)]
+        if mats:
+            M = torch.from_numpy(arr(mats, (B, 4, 4), np.float32).copy())
+        else:
+            M = orc.build_pose_matrix(torch.from_numpy(arr(params, (B, 6), np.float32).copy()))
+        lo, per_batch, g = nxt.p2plane_training_loss(maps[0], maps[1], maps[2], M, orc.Projector(H, W, up, down), SCHEME_NAMES[scheme], sigma)
+        arr(loss, (1,), np.float32)[:] = lo
+        if pb:
+            arr(pb, (B,), np.float32)[:] = per_batch
+        if gm:
+            arr(gm, (B, 4, 4), np.float32)[:] = g
+        if gp:
+            arr(gp, (B, 6), np.float32)[:] = nxt.pose_matrix_grad_to_params(arr(params, (B, 6), np.float32), g)
+
+    def pls_normal_map(self, vmap, B, H, W, ksize, out):
+        arr(out, (B, 3, H, W), np.float32)[:] = orc.normal_map(torch.from_numpy(arr(vmap, (B, 3, H, W), np.float32).copy()), ksize).numpy()
+
     def pls_build_pose_matrix(self, params, batch, out):
         arr(out, (batch, 4, 4), np.float32)[:] = orc.build_pose_matrix(torch.from_numpy(arr(params, (batch, 6), np.float32).copy())).numpy()
 
@@ -161,12 +179,19 @@ def main():
              ("p2p_large_errors", lambda: T.test_p2point_large_vs_oracle_and_error_behaviour(b200, nxt, Caplog())),
              ("procrustes_golden", lambda: T.test_procrustes_golden(b200, g)),
              ("procrustes_scan", lambda: T.test_procrustes_scan_size_round_trip(b200, nxt, syn))]
+    gl = np.load(os.path.join(ROOT, "tests", "golden", "p2plane_loss.npz"))
+    from pylidar_slam_b200 import training
+    training._require_cuda = lambda t: None
+    for sch in T.SCHEMES:
+        runs.append((f"loss_golden[{sch}]", lambda sch=sch: T.test_training_loss_and_gradients_golden(b200, gl, sch)))
+    runs += [("loss_normals_shapes", lambda: T.test_training_loss_computes_missing_normal_maps_and_checks_shapes(b200, gl)),
+             ("loss_scan_size", lambda: T.test_training_loss_scan_size_vs_oracle(b200, nxt, orc, syn))]
     bad = 0
     for name, fn in runs:
         try:
             fn()
             print("ok  ", name)
-        except Exception as e:
+        except BaseException as e:
             bad += 1
             print("FAIL", name, type(e).__name__, str(e)[:300])
             traceback.print_exc(limit=4)

@@ -13,7 +13,9 @@
 #include "../pylidar_slam_b200/csrc/filters_device.cuh"
 #include "../pylidar_slam_b200/csrc/gn_device.cuh"
 #include "../pylidar_slam_b200/csrc/pose_device.cuh"
+#include "../pylidar_slam_b200/csrc/projection_device.cuh"
 #include "../pylidar_slam_b200/csrc/registration_device.cuh"
+#include "../pylidar_slam_b200/csrc/training_device.cuh"
 
 using namespace pls;
 
@@ -132,6 +134,88 @@ int hh_align(int cost, int is_f64, const void* ref, const void* tgt, const void*
                                   norm_stop, (const double*)x0, (double*)out_x, (double*)out_dT, (double*)out_loss);
     return align_host<float>(cost, (const float*)ref, (const float*)tgt, (const float*)nrm, n, scheme, (float)sigma, max_iters,
                              (float)norm_stop, (const float*)x0, (float*)out_x, (float*)out_dT, (float*)out_loss);
+}
+
+// loss_zbuf_kernel + loss_accumulate_kernel + loss_finalize_kernel of training.cu, sequentially (same per-point code)
+void hh_p2plane_loss(const float* vt, const float* vr, const float* nr, const float* mats, const float* params, int B, int H,
+                     int W, float up, float down, int scheme, float sigma, float* out_loss, float* out_pb, float* out_gm,
+                     float* out_gp) {
+    const int64_t hw = (int64_t)H * W;
+    const ProjConst pc = make_proj_const(H, W, up, down);
+    unsigned long long* zbuf = new unsigned long long[(size_t)B * hw];
+    double total = 0.0;
+    for (int b = 0; b < B; ++b) {
+        float Mb[16];
+        if (mats) memcpy(Mb, mats + 16 * b, sizeof(Mb));
+        else build_pose(params + 6 * b, Mb);
+        const float* vm = vt + 3 * hw * b;
+        auto moved = [&](int64_t i, float* p, float* pm) {
+            p[0] = vm[i]; p[1] = vm[hw + i]; p[2] = vm[2 * hw + i];
+            if (p[0] == 0.f && p[1] == 0.f && p[2] == 0.f) return false;
+            pm[0] = p[0] * Mb[0] + p[1] * Mb[1] + p[2] * Mb[2] + Mb[3];
+            pm[1] = p[0] * Mb[4] + p[1] * Mb[5] + p[2] * Mb[6] + Mb[7];
+            pm[2] = p[0] * Mb[8] + p[1] * Mb[9] + p[2] * Mb[10] + Mb[11];
+            return true;
+        };
+        unsigned long long* zb = zbuf + hw * b;
+        for (int64_t i = 0; i < hw; ++i) zb[i] = ~0ull;
+        for (int64_t i = 0; i < hw; ++i) {
+            float p[3], pm[3], r;
+            int pix;
+            if (!moved(i, p, pm) || !project_to_pixel(pm[0], pm[1], pm[2], pc, pix, r)) continue;
+            unsigned int bits;
+            memcpy(&bits, &r, 4);
+            const unsigned long long key = ((unsigned long long)bits << 32) | (unsigned long long)(uint32_t)i;
+            if (key < zb[pix]) zb[pix] = key;
+        }
+        double row[16];
+        for (int a = 0; a < 16; ++a) row[a] = 0.0;
+        for (int64_t i = 0; i < hw; ++i) {
+            float p[3], pm[3], r;
+            int pix;
+            if (!moved(i, p, pm) || !project_to_pixel(pm[0], pm[1], pm[2], pc, pix, r)) continue;
+            const uint32_t win = (uint32_t)(zb[pix] & 0xffffffffull);
+            float pw[3] = {pm[0], pm[1], pm[2]};
+            if (win != (uint32_t)i) {
+                float pj[3];
+                moved((int64_t)win, pj, pw);
+            }
+            const float q[3] = {vr[3 * hw * b + pix], vr[3 * hw * b + hw + pix], vr[3 * hw * b + 2 * hw + pix]};
+            const float n[3] = {nr[3 * hw * b + pix], nr[3 * hw * b + hw + pix], nr[3 * hw * b + 2 * hw + pix]};
+            double mask, c2, g[3];
+            loss_pixel_terms(scheme, (double)sigma, pw, q, n, mask, c2, g);
+            if (win == (uint32_t)i) { row[0] += c2; row[1] += mask; }
+            for (int a = 0; a < 3; ++a) {
+                row[2 + a] += g[a];
+                for (int c = 0; c < 3; ++c) row[5 + 3 * a + c] += g[a] * (double)p[c];
+            }
+        }
+        const double Mc = row[1], lb = row[0] / Mc, sc = 1.0 / (Mc * (double)B);
+        total += lb;
+        if (out_pb) out_pb[b] = (float)lb;
+        double G[12];
+        for (int a = 0; a < 3; ++a) {
+            for (int c = 0; c < 3; ++c) G[4 * a + c] = row[5 + 3 * a + c] * sc;
+            G[4 * a + 3] = row[2 + a] * sc;
+        }
+        if (out_gm) {
+            for (int k = 0; k < 12; ++k) out_gm[16 * b + k] = (float)G[k];
+            for (int k = 12; k < 16; ++k) out_gm[16 * b + k] = 0.f;
+        }
+        if (out_gp && params) {
+            float dR[27];
+            euler_jacobian(params + 6 * b + 3, dR);
+            for (int a = 0; a < 3; ++a) out_gp[6 * b + a] = (float)G[4 * a + 3];
+            for (int k = 0; k < 3; ++k) {
+                double s2 = 0.0;
+                for (int a = 0; a < 3; ++a)
+                    for (int c = 0; c < 3; ++c) s2 += G[4 * a + c] * (double)dR[9 * k + 3 * a + c];
+                out_gp[6 * b + 3 + k] = (float)s2;
+            }
+        }
+    }
+    *out_loss = (float)(total / (double)B);
+    delete[] zbuf;
 }
 
 }  // extern "C"

@@ -28,7 +28,8 @@ def hh():
     so = os.path.join(out_dir, "host_harness.so")
     src = os.path.join(ROOT, "tests", "host_harness.cu")
     deps = [src] + [os.path.join(ROOT, "pylidar_slam_b200", "csrc", f) for f in
-                    ("filters_device.cuh", "registration_device.cuh", "gn_device.cuh", "pose_device.cuh")]
+                    ("filters_device.cuh", "registration_device.cuh", "gn_device.cuh", "pose_device.cuh",
+                     "projection_device.cuh", "training_device.cuh")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call([NVCC, "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
                                "-o", so, src])
@@ -151,3 +152,25 @@ def test_p2plane_device_math_matches_reference(hh, golden_helpers):
         assert st == 0
         assert np.abs(x - g[f"gn_{scheme}_delta"]).max() <= 2e-6, scheme
         assert np.abs(loss - g[f"gn_{scheme}_loss"]).max() <= 1e-5 * max(1.0, np.abs(g[f"gn_{scheme}_loss"]).max())
+
+
+@pytest.mark.parametrize("scheme", list(SCHEMES))
+def test_training_loss_device_math_matches_reference_autograd(hh, golden_loss, scheme):
+    """loss_modules.py:51-132: the kernel's per-point code (zbuf, pixel terms, index_put-style gradient routing, chain
+    rule to the Euler parameters) against the loss and the autograd gradients of the unmodified reference."""
+    if scheme == "least_square":
+        pytest.skip("alias of default")
+    g = golden_loss
+    vm, nm, x = g["vertex_map"], g["normal_map"], np.ascontiguousarray(g["pose_params"])
+    B, _, _, H, W = vm.shape
+    vt, vr, nr = (np.ascontiguousarray(a) for a in (vm[:, 1], vm[:, 0], nm[:, 0]))
+    loss, pb = np.zeros(1, np.float32), np.zeros(B, np.float32)
+    gm, gp = np.zeros((B, 4, 4), np.float32), np.zeros((B, 6), np.float32)
+    hh.hh_p2plane_loss(_p(vt), _p(vr), _p(nr), None, _p(x), B, H, W, C.c_float(3.0), C.c_float(-24.0), SCHEMES[scheme],
+                       C.c_float(0.5), _p(loss), _p(pb), _p(gm), _p(gp))
+    ref = float(g[f"{scheme}_loss"])
+    assert abs(float(loss[0]) - ref) <= 2e-5 * abs(ref), (scheme, loss, ref)
+    assert abs(float(pb.mean()) - ref) <= 2e-5 * abs(ref)
+    rp, rm = g[f"{scheme}_grad_params"], g[f"{scheme}_grad_matrix"]
+    assert np.abs(gp - rp).max() <= 2e-4 * np.abs(rp).max(), (scheme, np.abs(gp - rp).max() / np.abs(rp).max())
+    assert np.abs(gm - rm).max() <= 2e-4 * np.abs(rm).max(), (scheme, np.abs(gm - rm).max() / np.abs(rm).max())

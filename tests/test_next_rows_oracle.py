@@ -118,3 +118,22 @@ def test_whole_shipped_chain_oracle_vs_reference(golden_chain, case):
     its = [len(l) for l in algo.losses]
     check_pose_sequence(np.stack(poses), its, golden_chain[f"{name}_poses"], golden_chain[f"{name}_losses"],
                         threshold_delta_pose=max(thr, 1e-12), name=name)
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_training_loss_and_analytic_gradient_match_reference_autograd(golden_loss, scheme):
+    """loss_modules.py:51-132: the oracle's analytic gradient against the reference's autograd (float32)."""
+    g = golden_loss
+    vm, nm, x = torch.from_numpy(g["vertex_map"]), torch.from_numpy(g["normal_map"]), g["pose_params"]
+    mats = orc.build_pose_matrix(torch.from_numpy(x))
+    loss, per_batch, grad = nxt.p2plane_training_loss(vm[:, 1], vm[:, 0], nm[:, 0], mats, orc.Projector(16, 256), scheme, 0.5)
+    ref = float(g[f"{scheme}_loss"])
+    assert abs(loss - ref) <= 2e-5 * abs(ref), (scheme, loss, ref)
+    assert abs(float(g[f"{scheme}_loss_matrix"]) - ref) <= 1e-6 * abs(ref)
+    gm = g[f"{scheme}_grad_matrix"].astype(np.float64)
+    scale = np.abs(gm).max()
+    assert np.abs(grad[:, :3] - gm[:, :3]).max() <= 2e-4 * scale, (scheme, np.abs(grad[:, :3] - gm[:, :3]).max() / scale)
+    assert np.abs(gm[:, 3]).max() == 0.0
+    gp = nxt.pose_matrix_grad_to_params(x, grad)
+    rp = g[f"{scheme}_grad_params"].astype(np.float64)
+    assert np.abs(gp - rp).max() <= 2e-4 * np.abs(rp).max(), (scheme, np.abs(gp - rp).max() / np.abs(rp).max())
