@@ -483,8 +483,22 @@ int launch_group_iteration(pls_context* ctx, const KdIndex& ix, int64_t mine, co
     kd_nn_group_kernel<G><<<gblocks, KD_GROUP_THREADS, 0, st>>>(ix, ctx->query_ptr, nq_dev, (int64_t)rank,
                                                                 (int64_t)num_ranks, fr, nn_prev, first ? 1 : 0);
     PLS_CHECK_LAUNCH();
-    kd_normals_group_kernel<G><<<gblocks, KD_GROUP_THREADS, 0, st>>>(ix, ctx->cfg.num_neighbors_normals, nq_dev,
-                                                                     (int64_t)rank, (int64_t)num_ranks, fr, nn_prev);
+    // lanes per pending normal (default = the search's G; PLS_KD_NGROUP=2|4|8 decouples the two for A/B runs: later
+    // iterations only compute a few hundred new normals, where a wider group shortens the straggler chains)
+    static const int ngroup = getenv("PLS_KD_NGROUP") ? atoi(getenv("PLS_KD_NGROUP")) : G;
+    if (ngroup == 8 && G != 8) {
+        kd_normals_group_kernel<8><<<grid_for(mine * 8, KD_GROUP_THREADS, 16 * kNumSMs), KD_GROUP_THREADS, 0, st>>>(
+            ix, ctx->cfg.num_neighbors_normals, nq_dev, (int64_t)rank, (int64_t)num_ranks, fr, nn_prev);
+    } else if (ngroup == 2 && G != 2) {
+        kd_normals_group_kernel<2><<<grid_for(mine * 2, KD_GROUP_THREADS, 16 * kNumSMs), KD_GROUP_THREADS, 0, st>>>(
+            ix, ctx->cfg.num_neighbors_normals, nq_dev, (int64_t)rank, (int64_t)num_ranks, fr, nn_prev);
+    } else if (ngroup == 4 && G != 4) {
+        kd_normals_group_kernel<4><<<grid_for(mine * 4, KD_GROUP_THREADS, 16 * kNumSMs), KD_GROUP_THREADS, 0, st>>>(
+            ix, ctx->cfg.num_neighbors_normals, nq_dev, (int64_t)rank, (int64_t)num_ranks, fr, nn_prev);
+    } else {
+        kd_normals_group_kernel<G><<<gblocks, KD_GROUP_THREADS, 0, st>>>(ix, ctx->cfg.num_neighbors_normals, nq_dev,
+                                                                         (int64_t)rank, (int64_t)num_ranks, fr, nn_prev);
+    }
     PLS_CHECK_LAUNCH();
     const int blocks = grid_for(mine, KD_RES_THREADS, 8 * kNumSMs);
     ctx->partials.reserve((size_t)blocks * NACC * sizeof(double), st);

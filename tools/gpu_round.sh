@@ -37,6 +37,18 @@ ncufull)
     tail -3 gpurun_out/ncu_full.log
     ncu -i gpurun_out/r1_kd_group.ncu-rep --page raw --csv > gpurun_out/r1_kd_group_raw.csv 2>/dev/null
     ls -la gpurun_out/r1_kd_group* ;;
+final)
+    echo "== full gpu suite, new tests first"
+    timeout 450 python -m pytest tests/test_next_rows_gpu.py tests/test_gpu_parity.py tests/test_multi_gpu.py -q -m gpu --timeout 200 -rf \
+        --durations=8 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
+    tail -30 gpurun_out/pytest_gpu.log ;;
+ab)
+    echo "== A/B: lanes per pending normal (device-resident frames only)"
+    for ng in 4 8; do
+        PLS_KD_NGROUP=$ng timeout 90 python bench.py --quick --steps 40 --warmup 24 2>/dev/null | tail -1 | \
+            python -c "import json,sys; d=json.loads(sys.stdin.read()); print('ngroup $ng ms/frame', round(d['ms_per_step'],4), 'iters', d['iters_mean'])" \
+            | tee -a gpurun_out/ab_ngroup.log
+    done ;;
 bench)
     echo "== bench"
     timeout 400 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
