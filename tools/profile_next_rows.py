@@ -42,5 +42,17 @@ for H, W in ((64, 2048), (128, 4096)):
         "procrustes_moments_kernel_bytes": n * 24, "procrustes_cross_kernel_bytes": n * 24,
         "procrustes_residual_max": float(np.abs(T[:3, :3] - Rg).max()),
     }
+# training loss, batch of 4 pairs of 64x2048 vertex maps
+H, W, B = 64, 2048, 4
+pairs = np.stack([np.stack([syn.vertex_map_from_scan(syn.scan(k, H, W), H, W)[0], syn.vertex_map_from_scan(syn.scan(k + 1, H, W), H, W)[0]])
+                  for k in range(B)]).astype(np.float32)
+vm = torch.from_numpy(pairs).cuda()
+mod = b200._PointToPlaneLossModule(b200.PointToPlaneLossConfig(), b200.SphericalProjector(height=H, width=W, up_fov=3.0, down_fov=-24.0))
+x = torch.tensor([[0.8, 0.0, 0.0, 0.0, 0.0, 0.01]] * B, device="cuda", requires_grad=True)
+for rep in range(2):
+    loss, dd = mod({"vertex_map": vm, "pose_params": x})
+    loss.backward()
+out["training_loss"] = {"batch": B, "pixels": H * W, "loss": float(loss.detach()),
+                        "loss_zbuf_kernel_bytes": B * H * W * (12 + 8), "loss_accumulate_kernel_bytes": B * H * W * (12 + 8 + 12 + 24)}
 torch.cuda.synchronize()
 print(json.dumps(out))
