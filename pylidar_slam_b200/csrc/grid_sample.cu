@@ -4,7 +4,10 @@
 //                       and hash = 73856093 x + 19349669 y + 83492791 z in signed 64-bit
 //                       (slam/common/pointcloud.py:13-23,40-79).  Also emits the sort key
 //                       (hash with the sign bit flipped -> unsigned order == signed order).
-//   radix sort        : stable, so equal hashes keep ascending point index.
+//   radix sort        : stable, so equal hashes keep ascending point index.  The hashes of a LiDAR frame span ~2^38
+//                       (|voxel coordinate| <~ 1000), so the sort runs on 40-bit biased keys -- 5 passes instead of the
+//                       8 a raw int64 needs; a hash outside [-2^39, 2^39) stamps an overflow word and the caller,
+//                       which reads the sample count back anyway, repeats the call on full 64-bit keys.
 //   head flags + scan : first element of each run of equal hashes == np.unique(...,
 //                       return_index=True)'s first occurrence (pointcloud.py:177,193).
 //   gather            : sample_points / sample_indices in ascending-hash order.
@@ -16,10 +19,13 @@ namespace {
 
 constexpr long long HX = 73856093ll, HY = 19349669ll, HZ = 83492791ll;
 
+constexpr int GS_COMPACT_BITS = 40;
+
 template <typename T>
 __global__ void voxel_hash_kernel(const T* __restrict__ xyz, int64_t n, double voxel, long long* __restrict__ coords,
                                   long long* __restrict__ hashes, uint64_t* __restrict__ keys,
-                                  uint32_t* __restrict__ vals) {
+                                  uint32_t* __restrict__ vals, uint32_t* __restrict__ overflow = nullptr,
+                                  uint32_t stamp = 0) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double x = (double)xyz[3 * i], y = (double)xyz[3 * i + 1], z = (double)xyz[3 * i + 2];
         long long cx = __double2ll_rn(x / voxel);
@@ -33,7 +39,13 @@ __global__ void voxel_hash_kernel(const T* __restrict__ xyz, int64_t n, double v
         }
         if (hashes) hashes[i] = h;
         if (keys) {
-            keys[i] = (uint64_t)h ^ 0x8000000000000000ull;
+            if (overflow) {  // compact keys: h + 2^39 in 40 bits keeps the signed order
+                const uint64_t hb = (uint64_t)h + (1ull << (GS_COMPACT_BITS - 1));  // modular: no signed overflow
+                if (hb >> GS_COMPACT_BITS) *overflow = stamp;
+                keys[i] = hb & ((1ull << GS_COMPACT_BITS) - 1ull);
+            } else {
+                keys[i] = (uint64_t)h ^ 0x8000000000000000ull;
+            }
             vals[i] = (uint32_t)i;
         }
     }
@@ -128,19 +140,26 @@ inline int grid_for(int64_t n, int threads = 256) {
 // the sample count lands in the device scalar SC_GS_COUNT.
 template <typename T>
 void grid_sample_device(pls_context* ctx, const T* xyz_dev, int64_t n, double voxel, T* out_xyz_dev,
-                        long long* out_idx_dev) {
+                        long long* out_idx_dev, bool compact) {
     cudaStream_t st = ctx->stream;
+    static const bool full_keys = getenv("PLS_GS_FULLKEYS") != nullptr;  // A/B: always sort the raw 64-bit hashes
+    if (full_keys) compact = false;
     ProfileScope ps(ctx, 4, (double)n * 3 * sizeof(T));
     ctx->gs_keys.reserve((size_t)n * sizeof(uint64_t), st);
     ctx->gs_vals.reserve((size_t)n * sizeof(uint32_t), st);
     ctx->tmp[1].reserve((size_t)n, st);                    // head flags
     ctx->tmp[2].reserve((size_t)n * sizeof(uint32_t), st); // positions
+    if (compact) {
+        ctx->gs_seq += 1;
+        if (ctx->gs_seq == 0) ctx->gs_seq = 1;
+    }
     voxel_hash_kernel<T><<<grid_for(n), 256, 0, st>>>(xyz_dev, n, voxel, nullptr, nullptr, ctx->gs_keys.as<uint64_t>(),
-                                                      ctx->gs_vals.as<uint32_t>());
+                                                      ctx->gs_vals.as<uint32_t>(),
+                                                      compact ? scalar_u32(ctx, SC_GS_OVERFLOW) : nullptr, ctx->gs_seq);
     PLS_CHECK_LAUNCH();
     uint64_t* sk;
     uint32_t* sv;
-    radix_sort_pairs(ctx, ctx->gs_keys.as<uint64_t>(), ctx->gs_vals.as<uint32_t>(), n, 8, &sk, &sv);
+    radix_sort_pairs(ctx, ctx->gs_keys.as<uint64_t>(), ctx->gs_vals.as<uint32_t>(), n, compact ? GS_COMPACT_BITS / 8 : 8, &sk, &sv);
     head_flags_kernel<<<grid_for(n), 256, 0, st>>>(sk, n, ctx->tmp[1].as<uint8_t>());
     PLS_CHECK_LAUNCH();
     exclusive_scan_flags(ctx, ctx->tmp[1].as<uint8_t>(), n, ctx->tmp[2].as<uint32_t>(), scalar_u32(ctx, SC_GS_COUNT));
@@ -178,8 +197,17 @@ void voxel_statistics_device(pls_context* ctx, const T* xyz_dev, int64_t n, doub
     PLS_CHECK_LAUNCH();
 }
 
-template void grid_sample_device<float>(pls_context*, const float*, int64_t, double, float*, long long*);
-template void grid_sample_device<double>(pls_context*, const double*, int64_t, double, double*, long long*);
+template void grid_sample_device<float>(pls_context*, const float*, int64_t, double, float*, long long*, bool);
+template void grid_sample_device<double>(pls_context*, const double*, int64_t, double, double*, long long*, bool);
+
+uint32_t grid_sample_read_count(pls_context* ctx, bool* overflowed) {
+    uint32_t words[8];
+    static_assert(SC_GS_COUNT == 0 && SC_GS_OVERFLOW == 7, "one 32-byte copy covers the count and the overflow stamp");
+    PLS_CUDA(cudaMemcpyAsync(words, scalar_u32(ctx, SC_GS_COUNT), sizeof(words), cudaMemcpyDeviceToHost, ctx->stream));
+    PLS_CUDA(cudaStreamSynchronize(ctx->stream));
+    *overflowed = ctx->gs_seq != 0 && words[SC_GS_OVERFLOW] == ctx->gs_seq;
+    return words[SC_GS_COUNT];
+}
 
 }  // namespace pls
 
@@ -216,13 +244,17 @@ int pls_grid_sample(pls_context* ctx, const void* xyz, int is_f64, int64_t n, do
     const void* d_xyz = to_device(ctx, xyz, (size_t)n * 3 * esz, ctx->stage_in[0]);
     OutArg ox = out_arg(ctx, out_xyz, (size_t)n * 3 * esz, ctx->stage_out[0]);
     OutArg oi = out_arg(ctx, out_idx, (size_t)n * sizeof(int64_t), ctx->stage_out[1]);
-    if (is_f64)
-        grid_sample_device<double>(ctx, (const double*)d_xyz, n, voxel, (double*)ox.dev, (long long*)oi.dev);
-    else
-        grid_sample_device<float>(ctx, (const float*)d_xyz, n, voxel, (float*)ox.dev, (long long*)oi.dev);
     uint32_t count = 0;
-    PLS_CUDA(cudaMemcpyAsync(&count, scalar_u32(ctx, SC_GS_COUNT), sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    PLS_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const bool compact = attempt == 0;
+        if (is_f64)
+            grid_sample_device<double>(ctx, (const double*)d_xyz, n, voxel, (double*)ox.dev, (long long*)oi.dev, compact);
+        else
+            grid_sample_device<float>(ctx, (const float*)d_xyz, n, voxel, (float*)ox.dev, (long long*)oi.dev, compact);
+        bool overflowed = false;
+        count = grid_sample_read_count(ctx, &overflowed);
+        if (!(compact && overflowed)) break;  // hashes beyond 40 bits: once more on the raw 64-bit keys
+    }
     *out_count = count;
     finish_out(ctx, ox, (size_t)count * 3 * esz);
     finish_out(ctx, oi, (size_t)count * sizeof(int64_t));

@@ -184,6 +184,7 @@ struct pls_context {
     pls::DBuf nn_prev;                  // previous-iteration match per query
     pls::DBuf partials;                 // [blocks][NACC] doubles
     pls::DBuf gs_keys, gs_vals, gs_out_xyz, gs_out_idx;
+    uint32_t gs_seq = 0;                // stamp of the last compact-key grid sample (overflow detection)
     int64_t last_query_count = 0;
 
     pls::Comm* comm = nullptr;
@@ -211,7 +212,7 @@ namespace pls {
 
 // device scalar slots (u32) living behind the FrameResult in ctx->scalars
 enum { SC_GS_COUNT = 0, SC_QUERY_COUNT = 1, SC_NAN_COUNT = 2, SC_INSERT_COUNT = 3, SC_PROJ_NC = 4,
-       SC_TMP0 = 5, SC_TMP1 = 6, SC_NUM = 16 };
+       SC_TMP0 = 5, SC_TMP1 = 6, SC_GS_OVERFLOW = 7, SC_NUM = 16 };
 
 // ---- pointer classification + staging ---------------------------------------------------
 bool is_device_ptr(const void* p);
@@ -329,9 +330,16 @@ void pack_valid_rows_f64(pls_context* ctx, const double* pts_dev, int64_t n, flo
 // pack the non-null pixels (any channel != 0) of a [3,H,W] map into float4, row-major order
 void pack_nonnull_pixels(pls_context* ctx, const float* vmap_dev, int64_t hw, float4* out, uint32_t* count_dev);
 // grid_sample.cu
+// compact = true sorts on 40-bit keys (5 radix passes instead of 8): exact whenever every hash lies in [-2^39, 2^39),
+// i.e. voxel coordinates up to ~3 000 000 in magnitude; otherwise the kernel stamps `gs_seq` into the device scalar
+// SC_GS_OVERFLOW and the caller -- which reads the sample count back anyway -- repeats the call with compact = false
+// (grid_sample_overflowed() tells).
 template <typename T>
 void grid_sample_device(pls_context* ctx, const T* xyz_dev, int64_t n, double voxel, T* out_xyz_dev,
-                        long long* out_idx_dev);
+                        long long* out_idx_dev, bool compact = true);
+// Reads SC_GS_COUNT (and the overflow stamp) back: one 32-byte copy + one stream sync.  Returns the sample count;
+// *overflowed tells whether the last compact grid sample has to be repeated with full keys.
+uint32_t grid_sample_read_count(pls_context* ctx, bool* overflowed);
 // projmap.cu
 void projmap_reset(pls_context* ctx);
 void projmap_update(pls_context* ctx, const float* rel_pose_host, const float* vmap_dev);

@@ -498,11 +498,15 @@ int pls_process_frame_grid_sample(pls_context* ctx, const float* raw_points, int
     PLS_REQUIRE(ctx->cfg.gn_max_iters == 1, "fused ICP path supports gauss_newton_config.max_iters == 1");
     const float* d = (const float*)to_device(ctx, raw_points, (size_t)n * 3 * sizeof(float), ctx->stage_in[0]);
     ctx->gs_out_xyz.reserve((size_t)n * 3 * sizeof(float), ctx->stream);
-    grid_sample_device<float>(ctx, d, n, voxel, ctx->gs_out_xyz.as<float>(), nullptr);
-    // the sample count is needed on the host to size the point-layout frame: one small sync
+    // the sample count is needed on the host to size the point-layout frame: one small sync (it also carries the
+    // overflow stamp of the 40-bit sort keys; a frame whose hashes exceed them is re-sampled on the raw keys)
     uint32_t S = 0;
-    PLS_CUDA(cudaMemcpyAsync(&S, scalar_u32(ctx, SC_GS_COUNT), sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    PLS_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        grid_sample_device<float>(ctx, d, n, voxel, ctx->gs_out_xyz.as<float>(), nullptr, attempt == 0);
+        bool overflowed = false;
+        S = grid_sample_read_count(ctx, &overflowed);
+        if (!(attempt == 0 && overflowed)) break;
+    }
     process_frame_device(ctx, ctx->gs_out_xyz.as<float>(), layout, (int64_t)S, init_pose, out_pose, out_params,
                          out_has_pose, out_info);
     if (out_info) out_info[4] = (double)S;

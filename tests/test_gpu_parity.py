@@ -637,3 +637,35 @@ def test_odometry_reinit_is_clean(b200, syn):
     b = _drive(algo, fr, 4)
     np.testing.assert_array_equal(a, b)
     assert algo.get_relative_poses().shape == (4, 4, 4)
+
+
+def test_a1_grid_sample_hashes_beyond_the_compact_sort_keys(b200, orc, syn):
+    """The subsample sorts on 40-bit biased keys (5 radix passes); hashes outside [-2^39, 2^39) -- voxel coordinates
+    beyond ~3e6 -- are detected on the device and the call is repeated on the raw 64-bit keys.  Bit-exact either way,
+    through pls_grid_sample and through the fused pls_process_frame_grid_sample."""
+    import ctypes as C
+    from pylidar_slam_b200 import _lib
+    rng = np.random.RandomState(12)
+    base = (rng.randn(50000, 3) * np.array([30.0, 30.0, 3.0])).astype(np.float32)
+    for offset, voxel in ((0.0, 0.3), (4.0e5, 0.3), (-2.5e6, 0.5), (3.0e4, 0.001)):
+        pts = (base + np.float32(offset)).astype(np.float32)
+        h = orc.voxel_hashes(orc.voxel_coords(pts, voxel))
+        if offset != 0.0:
+            assert np.abs(h).max() >= 2 ** 39, "this case is meant to overflow the compact keys"
+        s_ref, i_ref = orc.grid_sample(pts, voxel)
+        s, i = b200.grid_sample(pts, voxel)
+        np.testing.assert_array_equal(i, i_ref)
+        np.testing.assert_array_equal(s, s_ref)
+    # mixed: a frame whose hashes straddle the 40-bit range, then a regular one on the same context
+    pts = np.concatenate([base[:1000], base[1000:2000] + np.float32(1e6)]).astype(np.float32)
+    for cloud in (pts, base):
+        s_ref, i_ref = orc.grid_sample(cloud, 0.3)
+        s, i = b200.grid_sample(cloud, 0.3)
+        np.testing.assert_array_equal(i, i_ref)
+    # fused path: frame 0 only initialises the map; info[4] = number of samples
+    far = (syn.scan(0, 32, 512) + np.float32(5.0e5)).astype(np.float32)
+    algo = _make(b200, "kdtree", 32, 512, "input_data", 4, lm_size=4)
+    pose, params, info, has = np.zeros((4, 4), np.float32), np.zeros(6, np.float32), np.zeros(12), C.c_int(0)
+    algo.ctx.call("pls_process_frame_grid_sample", _lib.ptr(far), far.shape[0], 0.3, _lib.INPUT_TENSOR, None, _lib.ptr(pose),
+                  _lib.ptr(params), C.byref(has), _lib.ptr(info))
+    assert has.value == 0 and int(info[4]) == orc.grid_sample(far, 0.3)[1].shape[0]

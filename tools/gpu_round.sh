@@ -49,6 +49,14 @@ ab)
             python -c "import json,sys; d=json.loads(sys.stdin.read()); print('ngroup $ng ms/frame', round(d['ms_per_step'],4), 'iters', d['iters_mean'])" \
             | tee -a gpurun_out/ab_ngroup.log
     done ;;
+abkeys)
+    echo "== A/B: 40-bit compact sort keys in the grid sample vs raw 64-bit keys (device-resident frames only)"
+    for rep in 1 2; do
+        timeout 90 python bench.py --quick --steps 40 --warmup 24 2>/dev/null | tail -1 | \
+            python -c "import json,sys; d=json.loads(sys.stdin.read()); print('compact keys ms/frame', round(d['ms_per_step'],4), 'launches', d['gpu_launches'])" | tee -a gpurun_out/ab_keys.log
+        PLS_GS_FULLKEYS=1 timeout 90 python bench.py --quick --steps 40 --warmup 24 2>/dev/null | tail -1 | \
+            python -c "import json,sys; d=json.loads(sys.stdin.read()); print('full keys    ms/frame', round(d['ms_per_step'],4), 'launches', d['gpu_launches'])" | tee -a gpurun_out/ab_keys.log
+    done ;;
 bench)
     echo "== bench"
     timeout 400 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
