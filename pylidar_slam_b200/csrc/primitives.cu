@@ -307,6 +307,7 @@ void radix_sort_pairs(pls_context* ctx, uint64_t* keys, uint32_t* vals, int64_t 
         sort_pass_kernel<<<(unsigned)tiles, SORT_THREADS, 0, st>>>(
             kin, vin, kout, vout, n, 8 * p, s.hist.as<uint32_t>() + p * RADIX,
             s.status.as<uint32_t>() + (size_t)p * tiles * RADIX, counters + p);
+        PLS_CHECK_LAUNCH();
         uint64_t* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;
     }
