@@ -5,7 +5,6 @@ plumbing: `_P2PlaneLossFn` hands the gradient the kernel already computed back t
 
 Gradients follow the reference's autograd exactly, including index_put's backward through the z-buffer scatter (every
 point written to a pixel receives that pixel's gradient, not only the survivor)."""
-import ctypes as C  # noqa: F401
 from dataclasses import dataclass, field
 from typing import Any, Dict, Optional
 
