@@ -3,7 +3,8 @@ a machine without a GPU by standing a CPU fake in for the four new C-ABI entry p
 tests touch).  The fake follows include/plslam_b200.h argument by argument and computes with the CPU oracle / the host
 harness, so it checks the Python mirrors' plumbing and the tests' own logic (shapes, dtypes, tolerances, error
 paths) before GPU minutes are spent.  It proves nothing about the kernels -- tests/test_host_math.py and the `-m gpu`
-run do that.
+run do that.  `FakeContext` is also what tests/test_host_logic_cpu.py patches in (per test, via monkeypatch) to check
+the Python mirrors' host logic in the CPU suite.
 
     python tests/dryrun_next_rows.py
 """
