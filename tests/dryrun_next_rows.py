@@ -120,6 +120,42 @@ class FakeContext:
     def pls_normal_map(self, vmap, B, H, W, ksize, out):
         arr(out, (B, 3, H, W), np.float32)[:] = orc.normal_map(torch.from_numpy(arr(vmap, (B, 3, H, W), np.float32).copy()), ksize).numpy()
 
+    # ---- the odometry entry points (host logic of the ICPFrameToModel mirror) -- the oracle's ICP behind the C ABI
+    def pls_odometry_init(self):
+        k = self.kwargs
+        names = {v: n for n, v in _lib.SCHEMES.items()}
+        cfg = orc.ICPConfig(max_num_alignments=k["max_num_alignments"], threshold_delta_pose=k["threshold_delta_pose"],
+                            threshold_trans=k["threshold_trans"], threshold_rot=k["threshold_rot"], data_key="data",
+                            local_map="kdtree" if k["local_map_type"] == _lib.MAP_KDTREE else "projective",
+                            local_map_size=k["local_map_size"], num_neighbors_normals=k["num_neighbors_normals"],
+                            normals_kernel_size=k["normals_kernel_size"], scheme=names[k["scheme"]], sigma=k["sigma"])
+        self.algo = orc.ICPFrameToModelOracle(cfg, orc.Projector(k["height"], k["width"], k["up_fov_deg"], k["down_fov_deg"]))
+
+    def pls_process_frame(self, data, layout, n, init, out_pose, out_params, has_pose, info):
+        H, W = self.kwargs["height"], self.kwargs["width"]
+        f64 = layout in (_lib.INPUT_NDARRAY_F64, _lib.INPUT_TENSOR_F64)
+        if layout == _lib.INPUT_VERTEX_MAP:
+            x = torch.from_numpy(arr(data, (1, 3, H, W), np.float32).copy())
+        else:
+            a = arr(data, (n, 3), np.float64 if f64 else np.float32).copy()
+            x = a if layout in (_lib.INPUT_NDARRAY, _lib.INPUT_NDARRAY_F64) else torch.from_numpy(a)
+        dd = {"data": x, "init_rpose": None if not init else arr(init, (4, 4), np.float32).astype(np.float64)}
+        nan_rows = 0 if layout == _lib.INPUT_VERTEX_MAP else int(np.isnan(np.asarray(x, dtype=np.float64)).any(axis=1).sum())
+        self.algo.process_next_frame(dd)
+        out = arr(info, (12,), np.float64)
+        out[:] = 0.0
+        out[5] = nan_rows
+        if "odometry_pose" not in dd:
+            has_pose._obj.value = 0
+            return
+        has_pose._obj.value = 1
+        T = dd["odometry_pose"].astype(np.float32)
+        arr(out_pose, (4, 4), np.float32)[:] = T
+        arr(out_params, (6,), np.float32)[:] = orc.from_pose_matrix(torch.from_numpy(T).unsqueeze(0))[0].numpy()
+        out[0] = len(self.algo.losses[-1])
+        if layout == _lib.INPUT_VERTEX_MAP:
+            out[8:11] = self.algo.pc.reshape(-1, 3)[0].numpy()
+
     def pls_build_pose_matrix(self, params, batch, out):
         arr(out, (batch, 4, 4), np.float32)[:] = orc.build_pose_matrix(torch.from_numpy(arr(params, (batch, 6), np.float32).copy())).numpy()
 

@@ -84,6 +84,74 @@ def test_training_loss_module_and_autograd_hand_off(b200, golden_loss, scheme):
     T.test_training_loss_and_gradients_golden(b200, golden_loss, scheme)
 
 
+KD_CASES = [("kd_ndarray", "ndarray", "numpy_pc", 0.4, 7), ("kd_tensor", "tensor", "input_data", 0.4, 7),
+            ("kd_vmap", "vertex_map", "vertex_map", None, 4)]
+
+
+@pytest.mark.parametrize("case", KD_CASES, ids=[c[0] for c in KD_CASES])
+def test_icp_frame_to_model_mirror_host_logic(b200, golden_icp_small, case):
+    """ICPFrameToModel mirror (icp_odometry.py:157-246): the three input layouts, frame 0 writes nothing, data_dict keys
+    and dtypes, relative / absolute pose bookkeeping -- against the reference's poses (the arithmetic behind the fake C
+    ABI is the oracle's, so the poses themselves restate tests/test_oracle_vs_golden.py)."""
+    from conftest import pose_errors
+    name, layout, key, voxel, nf = case
+    H, W = 32, 512
+    cfg = b200.ICPFrameToModelConfig(
+        local_map=b200.KdTreeLocalMapConfig(local_map_size=4),
+        alignment=b200.GaussNewtonPointToPlaneConfig(gauss_newton_config=dict(scheme="geman_mcclure", sigma=0.3, max_iters=1)),
+        max_num_alignments=8, data_key=key)
+    algo = b200.ICPFrameToModel(cfg, projector=b200.SphericalProjector(height=H, width=W, up_fov=3.0, down_fov=-24.0), device="cuda:0")
+    algo.init()
+    prev, poses = None, []
+    for k in range(nf):
+        pc = syn.scan(k, H, W)
+        if layout == "vertex_map":
+            dd = {"vertex_map": torch.from_numpy(syn.vertex_map_from_scan(pc, H, W))}
+        else:
+            s, _ = orc.grid_sample(pc, voxel)
+            dd = {"numpy_pc": s} if layout == "ndarray" else {"input_data": torch.from_numpy(s)}
+        dd["init_rpose"] = prev
+        algo.process_next_frame(dd)
+        if k == 0:
+            assert "odometry_pose" not in dd and "odometry_pc" not in dd
+            continue
+        assert dd["odometry_pose"].dtype == np.float32 and dd["odometry_pose"].shape == (4, 4)
+        assert dd["odometry_pc"].dtype == np.float32 and dd["odometry_pc"].shape[1] == 3
+        poses.append(dd["odometry_pose"].copy())
+        prev = dd["odometry_pose"].astype(np.float64)
+    ref = golden_icp_small[f"{name}_poses"]
+    assert len(poses) == len(ref)
+    for T_, Tr in zip(poses, ref):
+        dt, ang = pose_errors(T_, Tr)
+        assert dt <= 1e-4 and ang <= 1e-5, (name, dt, ang)
+    rel = algo.get_relative_poses()
+    assert rel.shape == (nf, 4, 4) and np.array_equal(rel[0], np.eye(4, dtype=np.float32))
+    assert len(algo.absolute_poses) == nf
+    absolute = np.eye(4)
+    for T_ in poses:
+        absolute = absolute @ T_.astype(np.float64)
+    assert np.abs(algo.absolute_poses[-1] - absolute).max() <= 1e-4  # Euler re-normalised float64 product
+    with pytest.raises(AssertionError):
+        algo.process_next_frame({"other_key": pc})
+    with pytest.raises(AssertionError):
+        algo.process_next_frame({key: np.zeros((5, 4), np.float32) if layout != "vertex_map" else torch.zeros(1, 3, 8, 8)})
+
+
+def test_icp_mirror_float64_layouts_are_announced(b200):
+    """float64 clouds must reach the C ABI as the _F64 layouts (float64 projection), float32 ones as before."""
+    from pylidar_slam_b200 import _lib
+    cfg = b200.ICPFrameToModelConfig(local_map=b200.KdTreeLocalMapConfig(), data_key="input_data",
+                                     alignment=b200.GaussNewtonPointToPlaneConfig())
+    algo = b200.ICPFrameToModel(cfg, projector=b200.SphericalProjector(height=16, width=64, up_fov=3.0, down_fov=-24.0), device="cuda:0")
+    pts = np.random.RandomState(0).randn(10, 3)
+    assert algo._interpret(pts)[0] == _lib.INPUT_NDARRAY_F64 and algo._interpret(pts)[1].dtype == np.float64
+    assert algo._interpret(pts.astype(np.float32))[0] == _lib.INPUT_NDARRAY
+    assert algo._interpret(torch.from_numpy(pts))[0] == _lib.INPUT_TENSOR_F64
+    assert algo._interpret(torch.from_numpy(pts).float())[0] == _lib.INPUT_TENSOR
+    assert algo._interpret(torch.zeros(1, 3, 16, 64, dtype=torch.float64))[0] == _lib.INPUT_VERTEX_MAP
+    assert algo._interpret(torch.zeros(1, 3, 16, 64, dtype=torch.float64))[1].dtype == torch.float32
+
+
 def test_registries_expose_the_reference_names(b200):
     assert set(b200.FILTER.__members__) == {"distortion", "voxelization", "grid_sample", "to_tensor"}
     assert set(b200.RIGID_ALIGNMENT.__members__) == {"point_to_plane_gauss_newton", "point_to_point_gauss_newton"}
