@@ -382,6 +382,7 @@ __global__ void kd_export_kernel(const float4* __restrict__ pts, int64_t n, floa
 }
 
 constexpr int KD_GROUP_THREADS = 128;
+constexpr int KD_NGROUP_LATER_DEFAULT = 0;  // 0 = same group width in every iteration; 32 = a warp per pending normal later
 
 // The same ICP iteration as kd_icp_iter_kernel, split in three launches so that the two searches can run
 // with G lanes per query (kdmap_group.cuh) at full residency and the reduction stays thread-per-query:
@@ -486,7 +487,16 @@ int launch_group_iteration(pls_context* ctx, const KdIndex& ix, int64_t mine, co
     // lanes per pending normal (default = the search's G; PLS_KD_NGROUP=2|4|8 decouples the two for A/B runs: later
     // iterations only compute a few hundred new normals, where a wider group shortens the straggler chains)
     static const int ngroup = getenv("PLS_KD_NGROUP") ? atoi(getenv("PLS_KD_NGROUP")) : G;
-    if (ngroup == 8 && G != 8) {
+    // Iterations >= 2 of a frame only meet a few hundred new matches: the kernel is then a tail of a few groups
+    // walking long dependent 10-NN chains while the grid has drained (profiles/r1_kd_traffic.json: 7-9 of 32 lanes
+    // active, 33-83 us).  PLS_KD_NGROUP_LATER=32 hands every pending normal of those iterations a full warp (one of
+    // the 27 cells per lane); the first iteration, where all ~32 k matches need a normal and throughput matters,
+    // keeps the narrow groups.
+    static const int later = getenv("PLS_KD_NGROUP_LATER") ? atoi(getenv("PLS_KD_NGROUP_LATER")) : KD_NGROUP_LATER_DEFAULT;
+    if (!first && later == 32) {
+        kd_normals_group_kernel<32><<<grid_for(mine * 32, KD_GROUP_THREADS, 16 * kNumSMs), KD_GROUP_THREADS, 0, st>>>(
+            ix, ctx->cfg.num_neighbors_normals, nq_dev, (int64_t)rank, (int64_t)num_ranks, fr, nn_prev);
+    } else if (ngroup == 8 && G != 8) {
         kd_normals_group_kernel<8><<<grid_for(mine * 8, KD_GROUP_THREADS, 16 * kNumSMs), KD_GROUP_THREADS, 0, st>>>(
             ix, ctx->cfg.num_neighbors_normals, nq_dev, (int64_t)rank, (int64_t)num_ranks, fr, nn_prev);
     } else if (ngroup == 2 && G != 2) {

@@ -57,6 +57,18 @@ abkeys)
         PLS_GS_FULLKEYS=1 timeout 90 python bench.py --quick --steps 40 --warmup 24 2>/dev/null | tail -1 | \
             python -c "import json,sys; d=json.loads(sys.stdin.read()); print('full keys    ms/frame', round(d['ms_per_step'],4), 'launches', d['gpu_launches'])" | tee -a gpurun_out/ab_keys.log
     done ;;
+later)
+    echo "== warp-per-pending-normal in iterations >= 2 (PLS_KD_NGROUP_LATER=32): parity under the toggle, then A/B"
+    PLS_KD_NGROUP_LATER=32 timeout 60 python -m pytest tests/test_gpu_parity.py tests/test_next_rows_gpu.py -q -m gpu --timeout 50 -p no:cacheprovider \
+        -k "icp_kd_small or icp_cfg2 or nan_rows or reinit or whole_shipped_chain" > gpurun_out/pytest_later32.log 2>&1
+    tail -4 gpurun_out/pytest_later32.log
+    for rep in 1 2; do
+        for later in 0 32; do
+            PLS_KD_NGROUP_LATER=$later timeout 40 python bench.py --quick --steps 40 --warmup 24 2>/dev/null | tail -1 | \
+                python -c "import json,sys; d=json.loads(sys.stdin.read()); print('later $later ms/frame', round(d['ms_per_step'],4), 'iters', d['iters_mean'])" \
+                | tee -a gpurun_out/ab_later.log
+        done
+    done ;;
 bench)
     echo "== bench"
     timeout 400 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
