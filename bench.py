@@ -173,6 +173,8 @@ def b200_arm(args):
     stream = torch.cuda.Stream(device=dev)
     projector = b200.SphericalProjector(height=H, width=W, up_fov=3.0, down_fov=-24.0)
 
+    comm_used = [args.comm]  # init_comm reports a fall-back from p2p to nccl
+
     def make_algo():
         cfg = b200.ICPFrameToModelConfig(
             local_map=b200.KdTreeLocalMapConfig(local_map_size=LM_SIZE),
@@ -182,7 +184,7 @@ def b200_arm(args):
         algo.init()
         if world > 1:
             from pylidar_slam_b200.distributed import init_comm
-            init_comm(algo.ctx, dist, rank, world, dev, mode=args.comm)
+            comm_used[0] = init_comm(algo.ctx, dist, rank, world, dev, mode=args.comm)
         return algo
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -253,7 +255,7 @@ def b200_arm(args):
             ms_dev = float(t[0])
             dist.destroy_process_group()
         if rank == 0:
-            print(json.dumps({"quick": True, "n_gpus": world, "comm": args.comm if world > 1 else None,
+            print(json.dumps({"quick": True, "n_gpus": world, "comm": comm_used[0] if world > 1 else None,
                               "ms_per_step": ms_dev / K_, "gpu_launches": launches, **stats}))
         return
     ms_dev_flushed, _, _, _, _ = device_pass(flush_each_step=True)
@@ -325,7 +327,7 @@ def b200_arm(args):
                          "value_l2_flushed_every_step re-measures with a 256 MiB flush INSIDE the bracket before every frame",
                    "value_l2_flushed_every_step": K_ / (ms_dev_flushed / 1e3),
                    "parallelism": "1 GPU" if world == 1 else f"queries sharded over {world} GPUs, map replicated, "
-                                                             f"one 30-double all-reduce per ICP iteration ({args.comm})",
+                                                             f"one 30-double all-reduce per ICP iteration ({comm_used[0]})",
                    **stats},
         "e2e": {"value": K_ / t_e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d / K_), "d2h_bytes_per_step": int(d2h / K_),
                 "ms_per_step": 1e3 * t_e / K_},

@@ -38,22 +38,48 @@ def broadcast_unique_id(make_id, dist, rank: int, device=None) -> bytes:
     return bytes(uid.cpu().tolist())
 
 
-def init_comm(ctx, dist, rank: int, world: int, device, mode: str = "p2p") -> None:
-    """Connects `ctx` to its peer ranks (collective over all ranks).
+def _all_agree(dist, ok: bool, device) -> bool:
+    """True iff `ok` on EVERY rank (one tiny MIN all-reduce): ranks must leave a failed attempt together."""
+    import torch
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return bool(int(flag.cpu()[0]) == 1)
+
+
+def init_comm(ctx, dist, rank: int, world: int, device, mode: str = "p2p") -> str:
+    """Connects `ctx` to its peer ranks (collective over all ranks) and returns the mode in use.
 
     mode "p2p" : one-shot all-reduce over NVLink peer memory fused into the solve kernel (CUDA IPC handles
-                 all-gathered with torch.distributed); mode "nccl": ncclAllReduce on the library's stream."""
+                 all-gathered with torch.distributed); mode "nccl": ncclAllReduce on the library's stream.
+    If any rank cannot export or map the IPC handles (IPC disabled in a container, no peer access between two
+    GPUs), ALL ranks agree on it and fall back to the NCCL mode together instead of hanging or crashing."""
     if mode == "p2p":
+        import logging
+
         import torch
         buf = (C.c_ubyte * 64)()
-        ctx.call("pls_comm_p2p_handle", world, buf)
-        mine = torch.tensor(list(buf), dtype=torch.uint8, device=device)
-        gathered = [torch.zeros(64, dtype=torch.uint8, device=device) for _ in range(world)]
-        dist.all_gather(gathered, mine)
-        raw = b"".join(bytes(t.cpu().tolist()) for t in gathered)
-        ctx.call("pls_comm_p2p_init", world, rank, raw)
-        dist.barrier()
-        return
+        err = None
+        try:
+            ctx.call("pls_comm_p2p_handle", world, buf)
+        except Exception as e:  # noqa: BLE001  (the failure is reported below, by every rank)
+            err = e
+        if _all_agree(dist, err is None, device):
+            mine = torch.tensor(list(buf), dtype=torch.uint8, device=device)
+            gathered = [torch.zeros(64, dtype=torch.uint8, device=device) for _ in range(world)]
+            dist.all_gather(gathered, mine)
+            raw = b"".join(bytes(t.cpu().tolist()) for t in gathered)
+            try:
+                ctx.call("pls_comm_p2p_init", world, rank, raw)
+            except Exception as e:  # noqa: BLE001
+                err = e
+            if _all_agree(dist, err is None, device):
+                dist.barrier()
+                return "p2p"
+            if err is None:
+                ctx.call("pls_comm_destroy")  # this rank mapped its peers, another one could not
+        if rank == 0 or err is not None:
+            logging.warning("plslam_b200: peer-to-peer exchange unavailable (%s); all ranks use the NCCL all-reduce",
+                            err if err is not None else "a peer rank failed")
     nccl_path = find_nccl().encode()
 
     def make_id():
@@ -64,3 +90,4 @@ def init_comm(ctx, dist, rank: int, world: int, device, mode: str = "p2p") -> No
 
     raw = broadcast_unique_id(make_id, dist, rank, device)
     ctx.call("pls_comm_init", world, rank, raw, nccl_path)
+    return "nccl"

@@ -72,3 +72,59 @@ def test_sharded_reduction_equals_unsharded_gloo_world2():
     out = mgr.dict()
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     assert out[0] and out[1]
+
+
+class _FakeCommCtx:
+    """Stands in for a pls context in the rendezvous tests: records the calls, fails where told to."""
+
+    def __init__(self, fail_at=None):
+        self.fail_at, self.calls = fail_at, []
+
+        class _Lib:
+            @staticmethod
+            def pls_comm_unique_id(path, buf):
+                for i in range(128):
+                    buf[i] = i
+                return 0
+        self.lib = _Lib()
+
+    def call(self, name, *args):
+        self.calls.append(name)
+        if name == self.fail_at:
+            raise RuntimeError(f"{name}: simulated failure")
+        if name == "pls_comm_p2p_handle":
+            for i in range(64):
+                args[1][i] = (i + 1) % 256
+        return 0
+
+
+def _comm_worker(rank, world, port, scenario, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pylidar_slam_b200.distributed import init_comm
+    fail = {"ok": None, "handle_fails_on_1": "pls_comm_p2p_handle" if rank == 1 else None,
+            "map_fails_on_0": "pls_comm_p2p_init" if rank == 0 else None}[scenario]
+    ctx = _FakeCommCtx(fail)
+    mode = init_comm(ctx, dist, rank, world, torch.device("cpu"), mode="p2p")
+    out[rank] = (mode, list(ctx.calls))
+    dist.destroy_process_group()
+
+
+def test_p2p_rendezvous_falls_back_to_nccl_on_every_rank_together():
+    """init_comm: if ANY rank cannot export or map the CUDA-IPC handles, all ranks agree (MIN all-reduce) and take the
+    NCCL mode together; a rank that had already mapped its peers releases them first."""
+    for scenario, want in (("ok", "p2p"), ("handle_fails_on_1", "nccl"), ("map_fails_on_0", "nccl")):
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+        s.close()
+        out = mp.Manager().dict()
+        mp.spawn(_comm_worker, args=(2, port, scenario, out), nprocs=2, join=True)
+        assert out[0][0] == out[1][0] == want, (scenario, dict(out))
+        if want == "nccl":
+            assert out[0][1][-1] == out[1][1][-1] == "pls_comm_init"
+        if scenario == "map_fails_on_0":
+            assert "pls_comm_destroy" in out[1][1] and "pls_comm_destroy" not in out[0][1]
+        if scenario == "handle_fails_on_1":
+            assert "pls_comm_p2p_init" not in out[0][1] and "pls_comm_p2p_init" not in out[1][1]
