@@ -109,8 +109,8 @@ def ptr(x):
     if x is None:
         return None
     if isinstance(x, np.ndarray):
-        assert x.flags["C_CONTIGUOUS"], "arrays passed to the C ABI must be C-contiguous"
-        return x.ctypes.data
+        assert x.flags.c_contiguous, "arrays passed to the C ABI must be C-contiguous"
+        return x.__array_interface__["data"][0]  # same address as x.ctypes.data without building a ctypes object
     if hasattr(x, "data_ptr"):
         assert x.is_contiguous(), "tensors passed to the C ABI must be contiguous"
         return x.data_ptr()

@@ -285,13 +285,13 @@ class Pose:
 
 
 def euler_pose_matrix_f64(params: np.ndarray) -> np.ndarray:
-    """float64 host build_pose_matrix for the absolute-pose bookkeeping (icp_odometry.py:200-202)."""
+    """float64 host build_pose_matrix for the absolute-pose bookkeeping (icp_odometry.py:200-202):
+    R = Rz(ez) Ry(ey) Rx(ex) written out (this runs once per frame on the host; scalar math beats numpy's
+    small-matrix overheads by 10x)."""
+    import math
     tx, ty, tz, ex, ey, ez = [float(v) for v in params]
-    cx, sx, cy, sy, cz, sz = np.cos(ex), np.sin(ex), np.cos(ey), np.sin(ey), np.cos(ez), np.sin(ez)
-    rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
-    ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
-    rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
-    T = np.eye(4)
-    T[:3, :3] = rz @ ry @ rx
-    T[:3, 3] = [tx, ty, tz]
-    return T
+    cx, sx, cy, sy, cz, sz = math.cos(ex), math.sin(ex), math.cos(ey), math.sin(ey), math.cos(ez), math.sin(ez)
+    return np.array([[cz * cy, cz * sy * sx - sz * cx, cz * sy * cx + sz * sx, tx],
+                     [sz * cy, sz * sy * sx + cz * cx, sz * sy * cx - cz * sx, ty],
+                     [-sy, cy * sx, cy * cx, tz],
+                     [0.0, 0.0, 0.0, 1.0]], dtype=np.float64)
