@@ -1,159 +1,141 @@
-"""Mirror of the Distortion / Voxelization / GridSample / ToTensor filters and the Preprocessing chain the shipped
-`config/slam/preprocessing/{grid_sample,voxelization}.yaml` build (slam/preprocessing.py:43-291)."""
-from dataclasses import dataclass
+"""Filters that run before the odometry, GPU-backed, behind the reference's own plug-in surface.
+
+The reference builds its preprocessing chain from `config/slam/preprocessing/{grid_sample,voxelization,none}.yaml`:
+a dict of filter configs keyed by order, each naming a `filter_name` that is looked up in the `FILTER` enum
+(slam/preprocessing.py:230-291).  The surface kept here is exactly that -- filter names, config field names and
+defaults, `data_dict` keys and dtypes -- so either yaml runs unchanged; the work itself happens in the CUDA library:
+
+    distortion    Distortion.filter    slam/preprocessing.py:148-191   -> pls_distort
+    voxelization  Voxelization.filter  slam/preprocessing.py:71-97     -> pls_voxel_statistics / pls_voxel_hash
+    grid_sample   GridSample.filter    slam/preprocessing.py:213-226   -> pls_grid_sample
+    to_tensor     ToTensor.filter      slam/preprocessing.py:112-126   (host: numpy -> torch, renaming)
+"""
+import dataclasses
 from enum import Enum
 from typing import Any, Dict, Optional
 
 import numpy as np
 import torch
 
-from .common import assert_debug, check_tensor, distort_frame, grid_sample, voxel_statistics
+from .common import assert_debug, check_tensor, distort_frame, grid_sample, voxel_hashing, voxel_statistics, voxelise
 from .odometry import MISSING, _cfg_to_dict
 
 
-@dataclass
-class FilterConfig:
-    filter_name: str = MISSING
+def _config_class(name: str, doc: str, base=None, **fields):
+    """A config dataclass with the given `field=default` pairs (the hydra-visible surface of a filter)."""
+    spec = [(k, Any if (v is None or v == MISSING) else type(v), dataclasses.field(default=v)) for k, v in fields.items()]
+    cls = dataclasses.make_dataclass(name, spec, bases=(base,) if base else ())
+    cls.__doc__ = doc
+    return cls
+
+
+FilterConfig = _config_class("FilterConfig", "slam/preprocessing.py:24-28", filter_name=MISSING)
+
+VoxelizationConfig = _config_class(
+    "VoxelizationConfig", "slam/preprocessing.py:43-60", FilterConfig,
+    filter_name="voxelization", input_channel="numpy_pc", voxel_covariances_key="voxel_covariances",
+    voxel_means_key="voxel_means", voxel_size_key="voxel_sizes", voxel_indices_key="voxel_indices",
+    voxel_hashes_key="voxel_hashes", voxel_coordinates_key="voxel_coordinates", with_normal_distribution=True, voxel_size=0.2)
+
+DistortionConfig = _config_class(
+    "DistortionConfig", "slam/preprocessing.py:129-141 (pose_key = Initialization.initial_pose_key())", FilterConfig,
+    filter_name="distortion", pointcloud_key="numpy_pc", timestamps_key="numpy_pc_timestamps", pose_key="init_rpose",
+    output_key="input_data", force=False, activate=True)
+
+GridSampleConfig = _config_class(
+    "GridSampleConfig", "slam/preprocessing.py:195-204", FilterConfig,
+    filter_name="grid_sample", voxel_size=0.3, pointcloud_key="numpy_pc", output_indices_key="sample_indices",
+    output_sample_key="sample_points")
+
+ToTensorConfig = _config_class(
+    "ToTensorConfig", "slam/preprocessing.py:100-106", FilterConfig, filter_name="to_tensor", device="cpu", keys=MISSING)
 
 
 class Filter:
-    def __init__(self, config: FilterConfig, **kwargs):
+    """A step of the chain: reads and extends the frame's `data_dict` in place (slam/preprocessing.py:31-40)."""
+
+    def __init__(self, config, ctx=None, **kwargs):
         self.config = config
+        self.ctx = ctx  # the CUDA context to run on (None: the package's default context on cuda:0)
 
     def filter(self, data_dict: dict):
         raise NotImplementedError("")
 
-
-@dataclass
-class VoxelizationConfig(FilterConfig):
-    """slam/preprocessing.py:43-60"""
-    filter_name: str = "voxelization"
-    input_channel: str = "numpy_pc"
-    voxel_covariances_key: str = "voxel_covariances"
-    voxel_means_key: str = "voxel_means"
-    voxel_size_key: str = "voxel_sizes"
-    voxel_indices_key: str = "voxel_indices"
-    voxel_hashes_key: str = "voxel_hashes"
-    voxel_coordinates_key: str = "voxel_coordinates"
-    with_normal_distribution: bool = True
-    voxel_size: float = 0.2
+    @staticmethod
+    def _host_cloud(data_dict: dict, key: str, what: str) -> np.ndarray:
+        """The `[n,3]` numpy cloud stored under `key`; the reference's filters accept nothing else."""
+        cloud = data_dict[key]
+        assert_debug(isinstance(cloud, np.ndarray), what)
+        check_tensor(cloud, [-1, 3])
+        return cloud
 
 
 class Voxelization(Filter):
-    """Voxelization.filter (preprocessing.py:71-97): voxel coordinates, hashes and -- optionally -- every voxel's
-    point count, mean and scatter matrix, in one GPU pass (hash, stable radix sort, segmented warp reductions)."""
-
-    def __init__(self, config: VoxelizationConfig, ctx=None, **kwargs):
-        super().__init__(config)
-        self.ctx = ctx
+    """Voxel coordinates and hashes of every point and -- unless `with_normal_distribution` is off -- each voxel's
+    point count, mean and scatter matrix plus every point's voxel rank: one hash + stable radix sort + segmented
+    warp reduction on the GPU."""
 
     def filter(self, data_dict: dict):
-        cfg = self.config
-        assert_debug(cfg.input_channel in data_dict,
-                     f"The input channel {cfg.input_channel} was not in the input channel")
-        pointcloud = data_dict[cfg.input_channel]
-        assert_debug(isinstance(pointcloud, np.ndarray))
-        check_tensor(pointcloud, [-1, 3])
-        if not cfg.with_normal_distribution:
-            from .common import voxelise, voxel_hashing
-            data_dict[cfg.voxel_hashes_key] = voxel_hashing(pointcloud, cfg.voxel_size, ctx=self.ctx)
-            data_dict[cfg.voxel_coordinates_key] = voxelise(pointcloud, cfg.voxel_size, ctx=self.ctx)
-            return
-        coords, hashes, sizes, means, covs, ids = voxel_statistics(pointcloud, cfg.voxel_size, ctx=self.ctx)
-        data_dict[cfg.voxel_hashes_key] = hashes
-        data_dict[cfg.voxel_coordinates_key] = coords
-        data_dict[cfg.voxel_means_key] = means
-        data_dict[cfg.voxel_covariances_key] = covs
-        data_dict[cfg.voxel_size_key] = sizes
-        data_dict[cfg.voxel_indices_key] = ids
-
-
-@dataclass
-class DistortionConfig(FilterConfig):
-    """slam/preprocessing.py:129-141"""
-    filter_name: str = "distortion"
-    pointcloud_key: str = "numpy_pc"
-    timestamps_key: str = "numpy_pc_timestamps"
-    pose_key: str = "init_rpose"  # Initialization.initial_pose_key()
-    output_key: str = "input_data"
-    force: bool = False
-    activate: bool = True
+        c = self.config
+        assert_debug(c.input_channel in data_dict, f"The input channel {c.input_channel} was not in the input channel")
+        cloud = self._host_cloud(data_dict, c.input_channel, "voxelization needs a numpy point cloud")
+        if c.with_normal_distribution:
+            coords, hashes, sizes, means, covs, ranks = voxel_statistics(cloud, c.voxel_size, ctx=self.ctx)
+            data_dict.update({c.voxel_means_key: means, c.voxel_covariances_key: covs, c.voxel_size_key: sizes,
+                              c.voxel_indices_key: ranks})
+        else:
+            coords, hashes = voxelise(cloud, c.voxel_size, ctx=self.ctx), voxel_hashing(cloud, c.voxel_size, ctx=self.ctx)
+        data_dict[c.voxel_hashes_key] = hashes
+        data_dict[c.voxel_coordinates_key] = coords
 
 
 class Distortion(Filter):
-    """Distortion.filter (preprocessing.py:148-191): de-skew the frame with the initial motion estimate."""
-
-    def __init__(self, config: DistortionConfig, ctx=None, **kwargs):
-        super().__init__(config)
-        self.ctx = ctx
+    """De-skews the frame with the initial motion estimate: every point is moved by the fraction of the relative pose
+    that corresponds to its acquisition time.  Without timestamps, without a pose, or when deactivated, the input array
+    itself is passed on (same object, as in the reference)."""
 
     def filter(self, data_dict: dict):
-        cfg = self.config
-        pc = data_dict[cfg.pointcloud_key]
-        assert_debug(isinstance(pc, np.ndarray), "Cannot Distort a non numpy frame")
-        check_tensor(pc, [-1, 3])
-        no_distortion = not cfg.activate or (cfg.timestamps_key not in data_dict)
-        no_distortion = no_distortion or (data_dict[cfg.pose_key] is None if cfg.pose_key in data_dict else False)
-        if no_distortion:
-            data_dict[cfg.output_key] = pc
+        c = self.config
+        cloud = self._host_cloud(data_dict, c.pointcloud_key, "Cannot Distort a non numpy frame")
+        pose_is_none = c.pose_key in data_dict and data_dict[c.pose_key] is None
+        if not c.activate or c.timestamps_key not in data_dict or pose_is_none:
+            data_dict[c.output_key] = cloud
             return
-        rpose = data_dict[cfg.pose_key]
+        rpose = data_dict[c.pose_key]  # a missing key raises KeyError, like the reference
         check_tensor(rpose, [4, 4])
-        timestamps = data_dict[cfg.timestamps_key]
-        assert_debug(isinstance(timestamps, np.ndarray))
-        timestamps = timestamps.reshape(-1)
-        check_tensor(timestamps, [pc.shape[0]])
-        data_dict[cfg.output_key] = distort_frame(pc, timestamps, rpose, ctx=self.ctx)
-
-
-@dataclass
-class GridSampleConfig(FilterConfig):
-    filter_name: str = "grid_sample"
-    voxel_size: float = 0.3
-    pointcloud_key: str = "numpy_pc"
-    output_indices_key: str = "sample_indices"
-    output_sample_key: str = "sample_points"
+        stamps = data_dict[c.timestamps_key]
+        assert_debug(isinstance(stamps, np.ndarray))
+        stamps = stamps.reshape(-1)
+        check_tensor(stamps, [cloud.shape[0]])
+        data_dict[c.output_key] = distort_frame(cloud, stamps, rpose, ctx=self.ctx)
 
 
 class GridSample(Filter):
-    """GridSample.filter (preprocessing.py:213-226): one point per voxel hash, on the GPU (K1)."""
-
-    def __init__(self, config: GridSampleConfig, ctx=None, **kwargs):
-        super().__init__(config)
-        self.ctx = ctx
+    """Keeps one point per voxel (the first one met, voxels in ascending hash order) and its index."""
 
     def filter(self, data_dict: dict):
-        pc = data_dict[self.config.pointcloud_key]
-        assert_debug(isinstance(pc, np.ndarray), "Cannot Distort a non numpy frame")
-        check_tensor(pc, [-1, 3])
-        sample, indices = grid_sample(pc, self.config.voxel_size, ctx=self.ctx)
-        data_dict[self.config.output_sample_key] = sample
-        data_dict[self.config.output_indices_key] = indices
-
-
-@dataclass
-class ToTensorConfig(FilterConfig):
-    filter_name: str = "to_tensor"
-    device: str = "cpu"
-    keys: Any = MISSING
+        c = self.config
+        cloud = self._host_cloud(data_dict, c.pointcloud_key, "Cannot Distort a non numpy frame")
+        data_dict[c.output_sample_key], data_dict[c.output_indices_key] = grid_sample(cloud, c.voxel_size, ctx=self.ctx)
 
 
 class ToTensor(Filter):
-    """ToTensor.filter (preprocessing.py:112-126)."""
+    """Renames numpy entries of the dict into torch tensors on `device` (host-side glue, no kernel)."""
 
-    def __init__(self, config: ToTensorConfig, device: str = "cpu", **kwargs):
-        super().__init__(config)
+    def __init__(self, config, device: str = "cpu", **kwargs):
+        super().__init__(config, **kwargs)
         self.device = torch.device(device)
 
     def filter(self, data_dict: dict):
-        for old_key, new_key in _cfg_to_dict(self.config.keys).items():
-            assert_debug(old_key in data_dict)
-            np_array = data_dict[old_key]
-            assert_debug(isinstance(np_array, np.ndarray))
-            data_dict[new_key] = torch.from_numpy(np_array).to(self.device)
+        for source, target in _cfg_to_dict(self.config.keys).items():
+            assert_debug(source in data_dict)
+            value = data_dict[source]
+            assert_debug(isinstance(value, np.ndarray))
+            data_dict[target] = torch.from_numpy(value).to(self.device)
 
 
 class FILTER(Enum):
+    """The registry the yaml's `filter_name` indexes (slam/preprocessing.py:230-253)."""
     distortion = (Distortion, DistortionConfig)
     voxelization = (Voxelization, VoxelizationConfig)
     grid_sample = (GridSample, GridSampleConfig)
@@ -161,29 +143,28 @@ class FILTER(Enum):
 
     @staticmethod
     def load(config, **kwargs) -> Filter:
-        d = _cfg_to_dict(config)
-        assert_debug("filter_name" in d)
-        assert_debug(d["filter_name"] in FILTER.__members__, f"filter {d['filter_name']} is not on the B200 hot path")
-        _class, _config = FILTER[d["filter_name"]].value
-        return _class(_config(**d), **kwargs)
+        entries = _cfg_to_dict(config)
+        assert_debug("filter_name" in entries)
+        name = entries["filter_name"]
+        assert_debug(name in FILTER.__members__, f"filter {name} is not on the B200 hot path")
+        impl, config_cls = FILTER[name].value
+        return impl(config_cls(**entries), **kwargs)
 
 
-@dataclass
+@dataclasses.dataclass
 class PreprocessingConfig:
+    """slam/preprocessing.py:257-260: `filters` maps an ordering key to one filter config."""
     filters: Optional[Dict[str, Any]] = None
 
 
 class Preprocessing:
-    """Preprocessing (preprocessing.py:268-291): filters applied in sorted-key order."""
+    """The chain itself (slam/preprocessing.py:268-291): filters instantiated once, applied in sorted-key order."""
 
     def __init__(self, preprocessing_config: PreprocessingConfig, **kwargs):
         self.config = preprocessing_config
-        self.filters = []
-        filters_config = _cfg_to_dict(self.config).get("filters")
-        if filters_config is not None:
-            for key in sorted(filters_config.keys()):
-                self.filters.append(FILTER.load(filters_config[key], **kwargs))
+        chain = _cfg_to_dict(self.config).get("filters") or {}
+        self.filters = [FILTER.load(chain[key], **kwargs) for key in sorted(chain)]
 
     def forward(self, data_dict: dict):
-        for _filter in self.filters:
-            _filter.filter(data_dict)
+        for step in self.filters:
+            step.filter(data_dict)
