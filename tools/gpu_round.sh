@@ -69,6 +69,20 @@ later)
                 | tee -a gpurun_out/ab_later.log
         done
     done ;;
+mgpu)
+    # needs `gpurun --gpus N`: sharded == single-GPU poses for both maps and both exchange modes, then the quick bench
+    # at 2 .. N ranks with the peer-to-peer and the NCCL exchange
+    NG=$(python -c "import torch; print(torch.cuda.device_count())")
+    echo "== multi-GPU on $NG GPUs"
+    timeout 600 python -m pytest tests/test_multi_gpu.py -q -m gpu --timeout 300 -rf > gpurun_out/pytest_mgpu.log 2>&1
+    tail -5 gpurun_out/pytest_mgpu.log
+    for n in 2 4 8; do
+        [ "$n" -le "$NG" ] || continue
+        for comm in p2p nccl; do
+            timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29541 \
+                bench.py --gpus $n --quick --steps 40 --warmup 24 --comm $comm 2>/dev/null | tail -1 | tee -a gpurun_out/mgpu_quick.log
+        done
+    done ;;
 bench)
     echo "== bench"
     timeout 400 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
