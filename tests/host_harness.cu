@@ -136,6 +136,10 @@ int hh_align(int cost, int is_f64, const void* ref, const void* tgt, const void*
                              (float)norm_stop, (const float*)x0, (float*)out_x, (float*)out_dT, (float*)out_loss);
 }
 
+void hh_loss_pixel(int scheme, double sigma, const float* pw, const float* q, const float* n, double* out5 /*mask, c2, g[3]*/) {
+    loss_pixel_terms(scheme, sigma, pw, q, n, out5[0], out5[1], out5 + 2);
+}
+
 // loss_zbuf_kernel + loss_accumulate_kernel + loss_finalize_kernel of training.cu, sequentially (same per-point code)
 void hh_p2plane_loss(const float* vt, const float* vr, const float* nr, const float* mats, const float* params, int B, int H,
                      int W, float up, float down, int scheme, float sigma, float* out_loss, float* out_pb, float* out_gm,

@@ -174,3 +174,67 @@ def test_training_loss_device_math_matches_reference_autograd(hh, golden_loss, s
     rp, rm = g[f"{scheme}_grad_params"], g[f"{scheme}_grad_matrix"]
     assert np.abs(gp - rp).max() <= 2e-4 * np.abs(rp).max(), (scheme, np.abs(gp - rp).max() / np.abs(rp).max())
     assert np.abs(gm - rm).max() <= 2e-4 * np.abs(rm).max(), (scheme, np.abs(gm - rm).max() / np.abs(rm).max())
+
+
+@pytest.mark.parametrize("scheme", [s for s in SCHEMES if s != "least_square"])
+def test_loss_pixel_gradient_matches_finite_differences(hh, scheme):
+    """d(C(|r|)^2)/d(p') of training_device.cuh against central differences of the same function's value, for every
+    weighting scheme (incl. the neighbourhood scheme's extra term through |p' - q|^2) -- independent of any reference."""
+    rng = np.random.RandomState(SCHEMES[scheme])
+    worst = 0.0
+    for _ in range(200):
+        q = rng.randn(3).astype(np.float32) * 5
+        n = rng.randn(3).astype(np.float32)
+        n /= np.linalg.norm(n)
+        pw = (q + rng.randn(3) * rng.choice([0.02, 0.3, 1.5])).astype(np.float32)
+        out = np.zeros(5)
+        hh.hh_loss_pixel(SCHEMES[scheme], C.c_double(0.5), _p(pw), _p(q), _p(n), _p(out))
+        assert out[0] == 1.0
+        g = out[2:5].copy()
+        r = float(np.dot(n.astype(np.float64), q.astype(np.float64) - pw.astype(np.float64)))
+        if scheme == "huber" and abs(abs(r) - 0.5) < 1e-2:
+            continue  # the kink of the Huber cost
+        fd = np.zeros(3)
+        # float32 inputs: step on the float32 grid, large enough for a clean central difference
+        for k in range(3):
+            h = np.float32(1e-4)
+            a, b = pw.copy(), pw.copy()
+            a[k] += h
+            b[k] -= h
+            oa, ob = np.zeros(5), np.zeros(5)
+            hh.hh_loss_pixel(SCHEMES[scheme], C.c_double(0.5), _p(a), _p(q), _p(n), _p(oa))
+            hh.hh_loss_pixel(SCHEMES[scheme], C.c_double(0.5), _p(b), _p(q), _p(n), _p(ob))
+            fd[k] = (oa[1] - ob[1]) / (float(a[k]) - float(b[k]))
+        scale = max(np.abs(g).max(), np.abs(fd).max(), 1e-12)
+        if abs(r) < 5e-3:
+            continue  # |r| changes sign inside the stencil
+        worst = max(worst, np.abs(g - fd).max() / scale)
+    assert worst <= 5e-3, (scheme, worst)
+    # masked pixels contribute nothing
+    zero = np.zeros(3, np.float32)
+    for args in ((zero, q, n), (pw, zero, n), (pw, q, zero)):
+        out = np.ones(5)
+        hh.hh_loss_pixel(SCHEMES[scheme], C.c_double(0.5), _p(args[0]), _p(args[1]), _p(args[2]), _p(out))
+        assert not out.any()
+
+
+def test_kabsch_properties_on_random_problems(hh):
+    """kabsch_from_cross: always a proper rotation, agrees with numpy's SVD solution (U diag(1,1,det) V^T), on
+    well-conditioned, near-planar and reflected problems."""
+    rng = np.random.RandomState(7)
+    for trial in range(300):
+        scale = rng.choice([1.0, 1e-3, 1e3]) * np.array([1.0, rng.uniform(0.05, 1.0), rng.choice([1.0, 0.2, 1e-3])])
+        A = rng.randn(50, 3) * scale
+        Bm = rng.randn(50, 3) * scale if trial % 5 == 0 else A @ np.linalg.qr(rng.randn(3, 3))[0].T + 1e-3 * scale.max() * rng.randn(50, 3)
+        mu_t, mu_r = A.mean(0), Bm.mean(0)
+        Cm = np.ascontiguousarray((Bm - mu_r).T @ (A - mu_t))
+        T = np.zeros(16)
+        hh.hh_kabsch(_p(Cm), _p(np.ascontiguousarray(np.concatenate([mu_t, mu_r]))), _p(T))
+        R = T.reshape(4, 4)[:3, :3]
+        assert abs(np.linalg.det(R) - 1.0) <= 1e-9 and np.abs(R @ R.T - np.eye(3)).max() <= 1e-9
+        U, S, Vt = np.linalg.svd(Cm)
+        D = np.diag([1.0, 1.0, np.sign(np.linalg.det(U) * np.linalg.det(Vt))])
+        if S[1] > 1e-6 * S[0] and (S[1] - S[2]) > 1e-6 * S[0] and (S[0] - S[1]) > 1e-6 * S[0]:  # unique solution
+            assert np.abs(R - U @ D @ Vt).max() <= 1e-6, (trial, S)
+        # the objective trace(R^T C) is never worse than the SVD solution's
+        assert np.trace(R.T @ Cm) >= np.trace((U @ D @ Vt).T @ Cm) - 1e-9 * max(S[0], 1e-300)
