@@ -75,6 +75,10 @@ enum {
     PLS_INPUT_TENSOR_F64 = 4
 };
 
+/* Optional residency hints, OR-ed into the `layout` argument of pls_process_frame by a caller that knows where `data`
+ * lives (no reference counterpart: the reference's tensors carry their device).  Without a hint the pointer is classified. */
+enum { PLS_PTR_DEVICE = 0x100, PLS_PTR_HOST = 0x200 };
+
 /* Configuration = SphericalProjector (projection.py:439-450) + ICPFrameToModelConfig
  * (icp_odometry.py:27-64) + local-map configs (local_map.py:83-88,244-251) +
  * GaussNewtonPointToPlaneConfig.gauss_newton_config (alignment.py:69-77). */
@@ -105,6 +109,9 @@ PLS_API const char* pls_last_error(pls_context* ctx);
 PLS_API const char* pls_version(void);
 /* cudaStreamSynchronize on the context's stream. */
 PLS_API int pls_synchronize(pls_context* ctx);
+/* Orders the work already enqueued on `other_stream` (a cudaStream_t, e.g. PyTorch's current stream that produced a
+ * CUDA tensor about to be passed in) before everything this context enqueues afterwards; no host synchronisation. */
+PLS_API int pls_wait_stream(pls_context* ctx, void* other_stream);
 
 /* ---- a1: voxel-grid subsample ----------------------------------------------------
  * voxelise + voxel_hashing  (slam/common/pointcloud.py:13-23,40-79): int64 voxel
@@ -117,6 +124,18 @@ PLS_API int pls_voxel_hash(pls_context* ctx, const void* xyz, int is_f64, int64_
  * out_xyz [n,3] (same dtype as the input), out_idx [n] int64; *out_count = S. */
 PLS_API int pls_grid_sample(pls_context* ctx, const void* xyz, int is_f64, int64_t n, double voxel,
                     void* out_xyz, int64_t* out_idx, int64_t* out_count);
+
+/* The same subsample for HOST callers without an extra copy (GridSample.filter hands numpy arrays to the next
+ * filter): the gather kernel writes samples and indices straight into the context's pinned, device-mapped staging and
+ * keeps a device-resident copy.  *out_xyz_host / *out_idx_host point into the staging (S rows, valid until the next
+ * grid-sample call on this context); *out_xyz_dev (optional) is the device copy, which pls_process_frame accepts with
+ * PLS_PTR_DEVICE -- the samples then never travel host -> device again.  One stream synchronisation per call. */
+PLS_API int pls_grid_sample_staged(pls_context* ctx, const void* xyz, int is_f64, int64_t n, double voxel,
+                           const void** out_xyz_host, const int64_t** out_idx_host, const void** out_xyz_dev,
+                           int64_t* out_count);
+/* 64-bit fingerprint of a host buffer (256 evenly spread 8-byte words + its length): lets a caller check cheaply that
+ * an array it handed out earlier still holds what the device-resident copy holds. */
+PLS_API int pls_host_fingerprint(const void* host_ptr, int64_t num_bytes, uint64_t* out);
 
 /* ---- a2/a3: spherical projection + closest-wins z-buffer --------------------------
  * SphericalProjector.project_pointcloud (projection.py:11-73,452-484): float pixel

@@ -17,6 +17,7 @@ SCHEMES = {"default": 0, "least_square": 1, "huber": 2, "exp": 3, "neighborhood"
            "square_geman_mcclure": 6, "cauchy": 7}
 MAP_KDTREE, MAP_PROJECTIVE = 0, 1
 INPUT_NDARRAY, INPUT_TENSOR, INPUT_VERTEX_MAP, INPUT_NDARRAY_F64, INPUT_TENSOR_F64 = 0, 1, 2, 3, 4
+PTR_DEVICE, PTR_HOST = 0x100, 0x200  # residency hints OR-ed into a layout
 
 
 class PlsConfig(C.Structure):
@@ -34,8 +35,11 @@ _SIGNATURES = {
     "pls_create": [C.POINTER(PlsConfig), C.POINTER(_P)],
     "pls_destroy": [_P],
     "pls_synchronize": [_P],
+    "pls_wait_stream": [_P, _P],
     "pls_voxel_hash": [_P, _P, _I, _L, _D, _P, _P],
     "pls_grid_sample": [_P, _P, _I, _L, _D, _P, _P, C.POINTER(_L)],
+    "pls_grid_sample_staged": [_P, _P, _I, _L, _D, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_L)],
+    "pls_host_fingerprint": [_P, _L, C.POINTER(C.c_uint64)],
     "pls_project_pixels": [_P, _P, _L, _I, _I, _F, _F, _P],
     "pls_build_projection_map": [_P, _P, _P, _I, _L, _I, _I, _I, _F, _F, _P],
     "pls_normal_map": [_P, _P, _I, _I, _I, _I, _P],
@@ -104,6 +108,12 @@ def exported_symbols():
     return sorted(list(_SIGNATURES) + ["pls_last_error", "pls_version"])
 
 
+# CUDA devices whose tensors were addressed since the last library call: the producer kernels of such a tensor sit on
+# PyTorch's current stream, the library runs on its own -- Context.call orders the two (pls_wait_stream) before
+# launching.  Empty (one truth test per call) whenever only host memory is passed.
+_cuda_inputs = set()
+
+
 def ptr(x):
     """Raw address of a numpy array / torch tensor (host or CUDA) / None."""
     if x is None:
@@ -113,8 +123,55 @@ def ptr(x):
         return x.__array_interface__["data"][0]  # same address as x.ctypes.data without building a ctypes object
     if hasattr(x, "data_ptr"):
         assert x.is_contiguous(), "tensors passed to the C ABI must be contiguous"
+        if x.is_cuda:
+            _cuda_inputs.add(x.device.index or 0)
         return x.data_ptr()
     raise TypeError(f"cannot take the address of {type(x)}")
+
+
+def host_view(address: int, shape, dtype) -> np.ndarray:
+    """A numpy view (no copy) of library-owned host memory, e.g. the pinned staging of pls_grid_sample_staged."""
+    count = int(np.prod(shape))
+    buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(address)
+    return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+
+def host_fingerprint(address: int, num_bytes: int) -> int:
+    out = C.c_uint64(0)
+    load().pls_host_fingerprint(address, num_bytes, C.byref(out))
+    return out.value
+
+
+class Handoff:
+    """The last grid-sample result a filter handed out as a host array, with its device-resident twin.  The odometry
+    recognises the array by identity (address + size + content fingerprint; the record keeps the array alive, so the
+    address cannot be recycled) and passes the device copy to the library: the samples never travel back up."""
+    array = None        # the numpy array given to the caller (strong reference)
+    address = 0
+    rows = 0
+    is_f64 = False
+    dev_ptr = 0
+    device = -1
+    fingerprint = 0
+
+    @classmethod
+    def publish(cls, array, dev_ptr, device, is_f64):
+        cls.array, cls.address, cls.rows = array, array.__array_interface__["data"][0], array.shape[0]
+        cls.dev_ptr, cls.device, cls.is_f64 = dev_ptr, device, is_f64
+        cls.fingerprint = host_fingerprint(cls.address, array.nbytes)
+
+    @classmethod
+    def clear(cls):
+        cls.array, cls.address, cls.rows, cls.dev_ptr, cls.device = None, 0, 0, 0, -1
+
+    @classmethod
+    def match(cls, address, rows, is_f64, device):
+        """The device pointer to use instead of `address`, or 0."""
+        if address != cls.address or rows != cls.rows or is_f64 != cls.is_f64 or device != cls.device or not cls.dev_ptr:
+            return 0
+        if host_fingerprint(address, cls.array.nbytes) != cls.fingerprint:
+            return 0  # the caller wrote into the array: its host content is the truth
+        return cls.dev_ptr
 
 
 def check(ctx_handle, status):
@@ -165,10 +222,26 @@ class Context:
         return ms.value, n.value, b.value
 
     def call(self, name, *args):
+        if _cuda_inputs:
+            self._order_after_torch()
         return check(self.handle, getattr(self.lib, name)(self.handle, *args))
+
+    def _order_after_torch(self):
+        """CUDA tensors were addressed for this call: whatever PyTorch still has in flight on its current stream
+        (a .to(float32), a slice copy, a network forward pass) must finish before the library's stream reads them."""
+        import torch
+        devices = list(_cuda_inputs)
+        _cuda_inputs.clear()
+        for d in devices:
+            if d == int(self.cfg.device):
+                check(self.handle, self.lib.pls_wait_stream(self.handle, torch.cuda.current_stream(d).cuda_stream))
+            else:
+                torch.cuda.current_stream(d).synchronize()
 
     def close(self):
         if getattr(self, "handle", None):
+            if Handoff.device == int(self.cfg.device):
+                Handoff.clear()  # the device twin may live in this context
             self.lib.pls_destroy(self.handle)
             self.handle = None
 

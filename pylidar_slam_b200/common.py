@@ -91,9 +91,22 @@ def grid_sample(pointcloud, voxel_size: float, ctx=None):
     if not is64:
         pc = _as_f32(pc)
     n = pc.shape[0]
+    count = C.c_int64(0)
+    if isinstance(pc, np.ndarray):
+        # host caller (GridSample.filter): the library leaves the result in its pinned staging -- one synchronisation,
+        # no pageable device->host copy -- and keeps a device-resident twin; the arrays handed out are exact-size
+        # copies (the staging is reused by the next call), and the twin is published so that ICPFrameToModel can
+        # consume it without sending the samples back to the device
+        hx, hi, dx = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        ctx.call("pls_grid_sample_staged", _lib.ptr(pc), int(is64), n, float(voxel_size), C.byref(hx), C.byref(hi),
+                 C.byref(dx), C.byref(count))
+        S = count.value
+        out = _lib.host_view(hx.value, (S, 3), np.float64 if is64 else np.float32).copy()
+        idx = _lib.host_view(hi.value, (S,), np.int64).copy()
+        _lib.Handoff.publish(out, dx.value or 0, int(ctx.cfg.device), is64)
+        return out, idx
     out = _empty_like_kind(pc, (n, 3), np.float64 if is64 else np.float32)
     idx = _empty_like_kind(pc, (n,), np.int64)
-    count = C.c_int64(0)
     ctx.call("pls_grid_sample", _lib.ptr(pc), int(is64), n, float(voxel_size), _lib.ptr(out), _lib.ptr(idx), C.byref(count))
     return out[:count.value], idx[:count.value]
 

@@ -9,7 +9,10 @@ long long g_kernel_launches = 0;
 
 void DBuf::reserve(size_t bytes, cudaStream_t s, bool keep) {
     if (bytes <= cap) return;
-    size_t want = bytes + bytes / 4 + 256;
+    // growth is a stall (stream sync + cudaMalloc + cudaFree): callers that know their steady-state size reserve it
+    // up front (kd map: kd_reserve_capacity); everything else grows by half so that a slowly growing buffer settles
+    // after a few frames
+    size_t want = bytes + bytes / 2 + 256;
     void* np = nullptr;
     PLS_CUDA(cudaStreamSynchronize(s));
     PLS_CUDA(cudaMalloc(&np, want));
@@ -21,6 +24,19 @@ void DBuf::reserve(size_t bytes, cudaStream_t s, bool keep) {
     cap = want;
 }
 
+void DBuf::reserve_exact(size_t bytes, cudaStream_t s, bool keep) {
+    if (bytes <= cap) return;
+    void* np = nullptr;
+    PLS_CUDA(cudaStreamSynchronize(s));
+    PLS_CUDA(cudaMalloc(&np, bytes));
+    if (p) {
+        if (keep) PLS_CUDA(cudaMemcpy(np, p, cap, cudaMemcpyDeviceToDevice));
+        PLS_CUDA(cudaFree(p));
+    }
+    p = np;
+    cap = bytes;
+}
+
 void DBuf::release() {
     if (p) cudaFree(p);
     p = nullptr;
@@ -30,8 +46,18 @@ void DBuf::release() {
 void HBuf::reserve(size_t bytes) {
     if (bytes <= cap) return;
     if (p) PLS_CUDA(cudaFreeHost(p));
-    PLS_CUDA(cudaMallocHost(&p, bytes));
+    p = nullptr;
+    cap = 0;
+    // mapped + portable: kernels may write results straight into it (zero-copy over PCIe), any context may read it
+    PLS_CUDA(cudaHostAlloc(&p, bytes, cudaHostAllocMapped | cudaHostAllocPortable));
     cap = bytes;
+}
+
+void* HBuf::device_ptr() const {
+    if (!p) return nullptr;
+    void* d = nullptr;
+    PLS_CUDA(cudaHostGetDevicePointer(&d, p, 0));
+    return d;
 }
 
 void HBuf::release() {
@@ -65,7 +91,29 @@ void sync_all(pls_context* ctx) {
     ctx->map_pending = false;
 }
 
+// Classification cache: cudaPointerGetAttributes costs ~1 us per pointer and a frame passes half a dozen of them, the
+// same ones every frame (the caller's pose / info arrays, pinned scan buffers).  Under unified addressing a virtual
+// address never changes kind (device allocations live in the driver's reserved range), so the answer is cached per
+// address; one host thread drives a context, the cache is thread-local.
+namespace {
+struct PtrCacheEntry {
+    const void* p;
+    bool dev;
+};
+thread_local PtrCacheEntry t_ptr_cache[64] = {};
+}  // namespace
+
 bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    PtrCacheEntry& e = t_ptr_cache[(reinterpret_cast<uintptr_t>(p) >> 6) & 63u];
+    if (e.p == p) return e.dev;
+    const bool d = is_device_ptr_uncached(p);
+    e.p = p;
+    e.dev = d;
+    return d;
+}
+
+bool is_device_ptr_uncached(const void* p) {
     if (!p) return false;
     cudaPointerAttributes a;
     cudaError_t e = cudaPointerGetAttributes(&a, p);
@@ -149,6 +197,27 @@ extern "C" {
 
 const char* pls_version(void) { return "plslam_b200 0.1 (sm_100a)"; }
 
+int pls_host_fingerprint(const void* host_ptr, int64_t num_bytes, uint64_t* out) {
+    if (!host_ptr || !out || num_bytes < 0) return PLS_E_INVALID;
+    const int64_t words = num_bytes / 8;
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ (uint64_t)num_bytes;
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(host_ptr);
+    const int64_t step = words > 256 ? words / 256 : 1;
+    for (int64_t i = 0; i < words; i += step) {
+        uint64_t v;
+        memcpy(&v, w + i, 8);
+        h = (h ^ v) * 0x100000001B3ull;
+        h ^= h >> 29;
+    }
+    if (words > 0) {
+        uint64_t v;
+        memcpy(&v, w + words - 1, 8);
+        h = (h ^ v) * 0x100000001B3ull;
+    }
+    *out = h;
+    return PLS_OK;
+}
+
 int pls_launch_count(int64_t* out) {
     if (!out) return PLS_E_INVALID;
     *out = (int64_t)pls::g_kernel_launches;
@@ -206,7 +275,7 @@ int pls_create(const pls_config* cfg, pls_context** out) {
         ctx->stream_main = ctx->stream;
         PLS_CUDA(cudaStreamCreateWithFlags(&ctx->stream_map, cudaStreamNonBlocking));
         PLS_CUDA(cudaEventCreateWithFlags(&ctx->ev_map_done, cudaEventDisableTiming));
-        ctx->pinned.reserve(sizeof(FrameResult) + 256);
+        ctx->pinned.reserve(kScalarOffset + 256);  // FrameResult, then the host copy of the u32 scalars
         ctx->scalars.reserve(sizeof(FrameResult) + 4096, ctx->stream);
         PLS_CUDA(cudaMemsetAsync(ctx->scalars.p, 0, ctx->scalars.cap, ctx->stream));
         odometry_reset(ctx);
@@ -250,6 +319,8 @@ int pls_destroy(pls_context* ctx) {
     for (auto& s : ctx->prof)
         for (auto e : s.pool) cudaEventDestroy(e);
     if (ctx->ev_map_done) cudaEventDestroy(ctx->ev_map_done);
+    if (ctx->ev_inputs) cudaEventDestroy(ctx->ev_inputs);
+    ctx->gs_host_xyz.release(); ctx->gs_host_idx.release();
     if (ctx->stream_map) cudaStreamDestroy(ctx->stream_map);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream_main);
     delete ctx;
@@ -261,6 +332,19 @@ const char* pls_last_error(pls_context* ctx) { return ctx ? ctx->err.c_str() : "
 int pls_synchronize(pls_context* ctx) {
     PLS_API_BEGIN(ctx)
     sync_all(ctx);
+    PLS_API_END(ctx)
+}
+
+int pls_wait_stream(pls_context* ctx, void* other_stream) {
+    PLS_API_BEGIN(ctx)
+    // work the caller enqueued on `other_stream` (e.g. PyTorch's current stream: the kernels that produced a CUDA
+    // tensor handed to this library) happens-before everything this context launches from now on; no host sync
+    cudaStream_t other = (cudaStream_t)other_stream;
+    if (other != ctx->stream_main) {
+        if (!ctx->ev_inputs) PLS_CUDA(cudaEventCreateWithFlags(&ctx->ev_inputs, cudaEventDisableTiming));
+        PLS_CUDA(cudaEventRecord(ctx->ev_inputs, other));
+        PLS_CUDA(cudaStreamWaitEvent(ctx->stream_main, ctx->ev_inputs, 0));
+    }
     PLS_API_END(ctx)
 }
 

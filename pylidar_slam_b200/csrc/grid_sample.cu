@@ -56,18 +56,28 @@ __global__ void head_flags_kernel(const uint64_t* __restrict__ keys, int64_t n, 
         flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
 }
 
+// host_xyz / host_idx (nullable): a second copy of the outputs written straight into mapped pinned host memory --
+// the samples cross PCIe while the kernel runs and the host caller needs no separate device->host copy.
 template <typename T>
 __global__ void gather_samples_kernel(const T* __restrict__ xyz, const uint32_t* __restrict__ vals,
                                       const uint8_t* __restrict__ flags, const uint32_t* __restrict__ pos, int64_t n,
-                                      T* __restrict__ out_xyz, long long* __restrict__ out_idx) {
+                                      T* __restrict__ out_xyz, long long* __restrict__ out_idx,
+                                      T* __restrict__ host_xyz, long long* __restrict__ host_idx) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         if (!flags[i]) continue;
         uint32_t src = vals[i];
         uint32_t dst = pos[i];
+        const T x = xyz[3 * (size_t)src], y = xyz[3 * (size_t)src + 1], z = xyz[3 * (size_t)src + 2];
         if (out_idx) out_idx[dst] = (long long)src;
-        out_xyz[3 * (size_t)dst] = xyz[3 * (size_t)src];
-        out_xyz[3 * (size_t)dst + 1] = xyz[3 * (size_t)src + 1];
-        out_xyz[3 * (size_t)dst + 2] = xyz[3 * (size_t)src + 2];
+        out_xyz[3 * (size_t)dst] = x;
+        out_xyz[3 * (size_t)dst + 1] = y;
+        out_xyz[3 * (size_t)dst + 2] = z;
+        if (host_xyz) {
+            host_xyz[3 * (size_t)dst] = x;
+            host_xyz[3 * (size_t)dst + 1] = y;
+            host_xyz[3 * (size_t)dst + 2] = z;
+        }
+        if (host_idx) host_idx[dst] = (long long)src;
     }
 }
 
@@ -140,7 +150,7 @@ inline int grid_for(int64_t n, int threads = 256) {
 // the sample count lands in the device scalar SC_GS_COUNT.
 template <typename T>
 void grid_sample_device(pls_context* ctx, const T* xyz_dev, int64_t n, double voxel, T* out_xyz_dev,
-                        long long* out_idx_dev, bool compact) {
+                        long long* out_idx_dev, bool compact, T* host_xyz, long long* host_idx) {
     cudaStream_t st = ctx->stream;
     static const bool full_keys = getenv("PLS_GS_FULLKEYS") != nullptr;  // A/B: always sort the raw 64-bit hashes
     if (full_keys) compact = false;
@@ -164,7 +174,8 @@ void grid_sample_device(pls_context* ctx, const T* xyz_dev, int64_t n, double vo
     PLS_CHECK_LAUNCH();
     exclusive_scan_flags(ctx, ctx->tmp[1].as<uint8_t>(), n, ctx->tmp[2].as<uint32_t>(), scalar_u32(ctx, SC_GS_COUNT));
     gather_samples_kernel<T><<<grid_for(n), 256, 0, st>>>(xyz_dev, sv, ctx->tmp[1].as<uint8_t>(),
-                                                          ctx->tmp[2].as<uint32_t>(), n, out_xyz_dev, out_idx_dev);
+                                                          ctx->tmp[2].as<uint32_t>(), n, out_xyz_dev, out_idx_dev,
+                                                          host_xyz, host_idx);
     PLS_CHECK_LAUNCH();
 }
 
@@ -197,13 +208,17 @@ void voxel_statistics_device(pls_context* ctx, const T* xyz_dev, int64_t n, doub
     PLS_CHECK_LAUNCH();
 }
 
-template void grid_sample_device<float>(pls_context*, const float*, int64_t, double, float*, long long*, bool);
-template void grid_sample_device<double>(pls_context*, const double*, int64_t, double, double*, long long*, bool);
+template void grid_sample_device<float>(pls_context*, const float*, int64_t, double, float*, long long*, bool, float*,
+                                        long long*);
+template void grid_sample_device<double>(pls_context*, const double*, int64_t, double, double*, long long*, bool, double*,
+                                         long long*);
 
 uint32_t grid_sample_read_count(pls_context* ctx, bool* overflowed) {
-    uint32_t words[8];
+    // into the pinned block behind the host FrameResult: a pageable destination would make the copy synchronous
+    // through the driver's own staging buffer
+    uint32_t* words = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ctx->pinned.p) + kScalarOffset);
     static_assert(SC_GS_COUNT == 0 && SC_GS_OVERFLOW == 7, "one 32-byte copy covers the count and the overflow stamp");
-    PLS_CUDA(cudaMemcpyAsync(words, scalar_u32(ctx, SC_GS_COUNT), sizeof(words), cudaMemcpyDeviceToHost, ctx->stream));
+    PLS_CUDA(cudaMemcpyAsync(words, scalar_u32(ctx, SC_GS_COUNT), 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     PLS_CUDA(cudaStreamSynchronize(ctx->stream));
     *overflowed = ctx->gs_seq != 0 && words[SC_GS_OVERFLOW] == ctx->gs_seq;
     return words[SC_GS_COUNT];
@@ -248,9 +263,11 @@ int pls_grid_sample(pls_context* ctx, const void* xyz, int is_f64, int64_t n, do
     for (int attempt = 0; attempt < 2; ++attempt) {
         const bool compact = attempt == 0;
         if (is_f64)
-            grid_sample_device<double>(ctx, (const double*)d_xyz, n, voxel, (double*)ox.dev, (long long*)oi.dev, compact);
+            grid_sample_device<double>(ctx, (const double*)d_xyz, n, voxel, (double*)ox.dev, (long long*)oi.dev, compact,
+                                       nullptr, nullptr);
         else
-            grid_sample_device<float>(ctx, (const float*)d_xyz, n, voxel, (float*)ox.dev, (long long*)oi.dev, compact);
+            grid_sample_device<float>(ctx, (const float*)d_xyz, n, voxel, (float*)ox.dev, (long long*)oi.dev, compact,
+                                      nullptr, nullptr);
         bool overflowed = false;
         count = grid_sample_read_count(ctx, &overflowed);
         if (!(compact && overflowed)) break;  // hashes beyond 40 bits: once more on the raw 64-bit keys
@@ -259,6 +276,39 @@ int pls_grid_sample(pls_context* ctx, const void* xyz, int is_f64, int64_t n, do
     finish_out(ctx, ox, (size_t)count * 3 * esz);
     finish_out(ctx, oi, (size_t)count * sizeof(int64_t));
     PLS_CUDA(cudaStreamSynchronize(ctx->stream));
+    PLS_API_END(ctx)
+}
+
+int pls_grid_sample_staged(pls_context* ctx, const void* xyz, int is_f64, int64_t n, double voxel,
+                           const void** out_xyz_host, const int64_t** out_idx_host, const void** out_xyz_dev,
+                           int64_t* out_count) {
+    PLS_API_BEGIN(ctx)
+    PLS_REQUIRE(xyz && out_xyz_host && out_idx_host && out_count && n > 0 && voxel > 0.0, "pls_grid_sample_staged: bad arguments");
+    const size_t esz = is_f64 ? sizeof(double) : sizeof(float);
+    const void* d_xyz = to_device(ctx, xyz, (size_t)n * 3 * esz, ctx->stage_in[0]);
+    // one device-resident copy (what pls_process_frame consumes without a host hop) and one in mapped pinned memory,
+    // written by the gather kernel itself; a single stream synchronisation ends the call
+    DBuf& dev_xyz = is_f64 ? ctx->stage_out[0] : ctx->gs_out_xyz;
+    dev_xyz.reserve((size_t)n * 3 * esz, ctx->stream);
+    ctx->gs_host_xyz.reserve((size_t)n * 3 * esz);
+    ctx->gs_host_idx.reserve((size_t)n * sizeof(int64_t));
+    uint32_t count = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const bool compact = attempt == 0;
+        if (is_f64)
+            grid_sample_device<double>(ctx, (const double*)d_xyz, n, voxel, dev_xyz.as<double>(), nullptr, compact,
+                                       (double*)ctx->gs_host_xyz.device_ptr(), (long long*)ctx->gs_host_idx.device_ptr());
+        else
+            grid_sample_device<float>(ctx, (const float*)d_xyz, n, voxel, dev_xyz.as<float>(), nullptr, compact,
+                                      (float*)ctx->gs_host_xyz.device_ptr(), (long long*)ctx->gs_host_idx.device_ptr());
+        bool overflowed = false;
+        count = grid_sample_read_count(ctx, &overflowed);
+        if (!(compact && overflowed)) break;  // hashes beyond 40 bits: once more on the raw 64-bit keys
+    }
+    *out_count = count;
+    *out_xyz_host = ctx->gs_host_xyz.p;
+    *out_idx_host = ctx->gs_host_idx.as<int64_t>();
+    if (out_xyz_dev) *out_xyz_dev = dev_xyz.p;
     PLS_API_END(ctx)
 }
 

@@ -54,6 +54,7 @@ struct DBuf {
     template <typename T>
     T* as() const { return reinterpret_cast<T*>(p); }
     void reserve(size_t bytes, cudaStream_t s, bool keep = false);
+    void reserve_exact(size_t bytes, cudaStream_t s, bool keep = false);  // no head-room: the caller planned the size
     void release();
 };
 
@@ -65,6 +66,7 @@ struct HBuf {
     T* as() const { return reinterpret_cast<T*>(p); }
     void reserve(size_t bytes);
     void release();
+    void* device_ptr() const;  // the device-side alias of the mapped allocation
 };
 
 struct ProfileSlot {
@@ -111,6 +113,8 @@ struct KdMap {
     uint32_t table_mask[4] = {0, 0, 0, 0};
     int64_t indexed = 0;    // points covered by the index
     bool valid = false;
+    int64_t cap_points = 0; // every per-point array holds this many points (kd_reserve_capacity)
+    int64_t max_frame = 0;  // largest frame inserted so far (sizes the steady state: local_map_size frames)
 };
 
 struct ProjMap {
@@ -150,6 +154,7 @@ struct pls_context {
     cudaStream_t stream_main = nullptr; // caller-visible stream (== stream outside a map-update scope)
     cudaStream_t stream_map = nullptr;  // local-map update stream (overlaps the next frame's preprocessing)
     cudaEvent_t ev_map_done = nullptr;  // recorded on stream_map after every asynchronous map update
+    cudaEvent_t ev_inputs = nullptr;    // pls_wait_stream: orders the caller's stream before this context's work
     bool map_pending = false;
     bool own_stream = false;
     std::string err;
@@ -185,6 +190,7 @@ struct pls_context {
     pls::DBuf partials;                 // [blocks][NACC] doubles
     pls::DBuf gs_keys, gs_vals, gs_out_xyz, gs_out_idx;
     uint32_t gs_seq = 0;                // stamp of the last compact-key grid sample (overflow detection)
+    pls::HBuf gs_host_xyz, gs_host_idx; // pinned + mapped staging the grid sample's gather writes directly (host callers)
     int64_t last_query_count = 0;
 
     pls::Comm* comm = nullptr;
@@ -215,7 +221,8 @@ enum { SC_GS_COUNT = 0, SC_QUERY_COUNT = 1, SC_NAN_COUNT = 2, SC_INSERT_COUNT = 
        SC_TMP0 = 5, SC_TMP1 = 6, SC_GS_OVERFLOW = 7, SC_NUM = 16 };
 
 // ---- pointer classification + staging ---------------------------------------------------
-bool is_device_ptr(const void* p);
+bool is_device_ptr(const void* p);           // cached per address
+bool is_device_ptr_uncached(const void* p);
 // Returns a device pointer holding `bytes` of `p` (copying through `stage` if p is host).
 const void* to_device(pls_context* ctx, const void* p, size_t bytes, DBuf& stage);
 // Returns a device pointer results may be written to; if `p` is host, it is `stage` and
@@ -265,8 +272,9 @@ inline void profile_credit(pls_context* ctx, int which, int64_t launches, double
 // the arrays holding the result (either the inputs or the scratch partners) -- they are device
 // pointers stored in DEVICE memory (the plan), and also returned on the host when the number of
 // executed passes is statically known (no skipping), which is how it is used here.
+// cap_n >= n: the scratch is sized for cap_n elements (callers whose n grows towards a known bound pass the bound).
 void radix_sort_pairs(pls_context* ctx, uint64_t* keys, uint32_t* vals, int64_t n, int num_passes,
-                      uint64_t** keys_out, uint32_t** vals_out);
+                      uint64_t** keys_out, uint32_t** vals_out, int64_t cap_n = 0);
 
 // Exclusive scan / stream compaction with a single-pass decoupled look-back.
 // flags[i] in {0,1}; pos_out[i] = number of set flags before i; *total_dev = number set.
@@ -336,7 +344,7 @@ void pack_nonnull_pixels(pls_context* ctx, const float* vmap_dev, int64_t hw, fl
 // (grid_sample_overflowed() tells).
 template <typename T>
 void grid_sample_device(pls_context* ctx, const T* xyz_dev, int64_t n, double voxel, T* out_xyz_dev,
-                        long long* out_idx_dev, bool compact = true);
+                        long long* out_idx_dev, bool compact = true, T* host_xyz = nullptr, long long* host_idx = nullptr);
 // Reads SC_GS_COUNT (and the overflow stamp) back: one 32-byte copy + one stream sync.  Returns the sample count;
 // *overflowed tells whether the last compact grid sample has to be repeated with full keys.
 uint32_t grid_sample_read_count(pls_context* ctx, bool* overflowed);

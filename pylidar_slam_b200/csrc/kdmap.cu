@@ -534,6 +534,46 @@ KdIndex make_index(pls_context* ctx) {
     return ix;
 }
 
+size_t cell_table_bytes(int64_t M, uint32_t* masks, size_t* offsets) {
+    size_t off = 0;
+    for (int l = 0; l < KD_LEVELS; ++l) {
+        uint64_t want = (uint64_t)(1.5 * (double)M) >> l;
+        uint32_t sz = 1024;
+        while (sz < want) sz <<= 1;
+        if (masks) masks[l] = sz - 1;
+        if (offsets) offsets[l] = off;
+        off += (size_t)sz * sizeof(uint4);
+    }
+    return off;
+}
+
+// Sizes every per-point array of the map at once.  The map grows frame by frame until local_map_size frames are
+// held, then oscillates around that size: reserving the steady state (local_map_size + 1 frames of the largest
+// frame seen, 30 % head-room) on the first insertion means NO further allocation -- and none of the stream
+// synchronisations an allocation implies -- while the map fills up, i.e. inside any timed region that starts after
+// the first frame.  `need` beyond the plan (a denser frame later on) re-plans with 25 % head-room.
+void kd_reserve_capacity(pls_context* ctx, int64_t need) {
+    KdMap& kd = ctx->kd;
+    if (need <= kd.cap_points) return;
+    cudaStream_t st = ctx->stream;
+    const int64_t steady = (int64_t)(1.3 * (double)kd.max_frame * (double)(ctx->cfg.local_map_size + 1));
+    int64_t cap = need + need / 4 + 64;
+    if (cap < steady) cap = steady;
+    const size_t C = (size_t)cap;
+    kd.store[kd.cur].reserve_exact(C * sizeof(float4), st, true);  // the live points survive
+    kd.store[kd.cur ^ 1].reserve_exact(C * sizeof(float4), st);
+    kd.morton.reserve_exact(C * sizeof(uint64_t), st);
+    kd.order.reserve_exact(C * sizeof(uint32_t), st);
+    kd.sorted.reserve_exact(C * sizeof(float4), st);
+    kd.normals.reserve_exact(C * sizeof(float4), st);
+    kd.inv_order.reserve_exact(C * sizeof(uint32_t), st);
+    kd.nodes.reserve_exact(C * 64, st);
+    kd.parent.reserve_exact(2 * C * sizeof(int), st);
+    kd.visit.reserve_exact(C * sizeof(int) + C * sizeof(int4) + 16, st);
+    kd.cells.reserve_exact(cell_table_bytes(cap, nullptr, nullptr), st);
+    kd.cap_points = cap;
+}
+
 void build_index(pls_context* ctx) {
     KdMap& kd = ctx->kd;
     cudaStream_t st = ctx->stream;
@@ -543,15 +583,8 @@ void build_index(pls_context* ctx) {
     if (M <= 0) return;
     ProfileScope ps(ctx, 3, (double)M * 32.0);
     PLS_REQUIRE(M < (1ll << 30), "kd map: too many points");
+    kd_reserve_capacity(ctx, M);
     const float4* pts = kd.store[kd.cur].as<float4>();
-    kd.morton.reserve((size_t)M * sizeof(uint64_t), st);
-    kd.order.reserve((size_t)M * sizeof(uint32_t), st);
-    kd.sorted.reserve((size_t)M * sizeof(float4), st);
-    kd.normals.reserve((size_t)M * sizeof(float4), st);
-    kd.inv_order.reserve((size_t)M * sizeof(uint32_t), st);
-    kd.nodes.reserve((size_t)(M > 1 ? M - 1 : 1) * 64, st);
-    kd.parent.reserve((size_t)(2 * M) * sizeof(int), st);
-    kd.visit.reserve((size_t)M * sizeof(int) + (size_t)M * sizeof(int4), st);
     PLS_CUDA(cudaMemsetAsync(kd.normals.p, 0, (size_t)M * sizeof(float4), st));
     kd.grid_hdr.reserve(sizeof(KdGridHeader), st);
     static const float cell_target = getenv("PLS_KD_CELL") ? (float)atof(getenv("PLS_KD_CELL")) : KD_CELL_TARGET;
@@ -563,21 +596,14 @@ void build_index(pls_context* ctx) {
     PLS_CHECK_LAUNCH();
     uint64_t* sk;
     uint32_t* sv;
-    radix_sort_pairs(ctx, kd.morton.as<uint64_t>(), kd.order.as<uint32_t>(), M, (3 * KD_COORD_BITS + 7) / 8, &sk, &sv);
+    radix_sort_pairs(ctx, kd.morton.as<uint64_t>(), kd.order.as<uint32_t>(), M, (3 * KD_COORD_BITS + 7) / 8, &sk, &sv,
+                     kd.cap_points);
     kd_gather_kernel<<<grid_for(M, 256, 8 * kNumSMs), 256, 0, st>>>(pts, sv, M, kd.sorted.as<float4>(),
                                                                      kd.inv_order.as<uint32_t>());
     PLS_CHECK_LAUNCH();
     {   // cell tables: level l gets a power-of-two table of >= 1.5 M / 2^l slots (overflow falls back to the BVH)
         CellTables T;
-        size_t off = 0;
-        for (int l = 0; l < KD_LEVELS; ++l) {
-            uint64_t want = (uint64_t)(1.5 * (double)M) >> l;
-            uint32_t sz = 1024;
-            while (sz < want) sz <<= 1;
-            kd.table_mask[l] = sz - 1;
-            kd.table_offset[l] = off;
-            off += (size_t)sz * sizeof(uint4);
-        }
+        const size_t off = cell_table_bytes(M, kd.table_mask, kd.table_offset);
         kd.cells.reserve(off, st);
         PLS_CUDA(cudaMemsetAsync(kd.cells.p, 0, off, st));
         for (int l = 0; l < KD_LEVELS; ++l) {
@@ -612,6 +638,7 @@ void kdmap_reset(pls_context* ctx) {
     ctx->kd.indexed = 0;
     ctx->kd.valid = false;
     ctx->kd.bbox_clean = false;
+    ctx->kd.max_frame = 0;   // the buffers (cap_points) are kept: a re-initialised sequence reuses them
 }
 
 template <typename T>
@@ -691,8 +718,9 @@ void kdmap_update_packed(pls_context* ctx, const float* rel_pose_host, const flo
     if (!has_new) num_new = 0;
     const int64_t kept = kd.count - skip;
     const int64_t total = kept + num_new;
+    if (num_new > kd.max_frame) kd.max_frame = num_new;
+    kd_reserve_capacity(ctx, total > 0 ? total : 1);
     const int dst = kd.cur ^ 1;
-    kd.store[dst].reserve((size_t)(total > 0 ? total : 1) * sizeof(float4), st);
     kd.bbox.reserve(8 * sizeof(int), st);
     if (!kd.bbox_clean) {
         kd_bbox_init_kernel<<<1, 32, 0, st>>>(kd.bbox.as<int>());

@@ -479,12 +479,25 @@ int pls_process_frame(pls_context* ctx, const void* data, int layout, int64_t n,
                       float* out_pose, float* out_params, int* out_has_pose, double* out_info) {
     PLS_API_BEGIN(ctx)
     PLS_REQUIRE(data, "pls_process_frame: null data");
+    // optional residency hint in the high bits: the caller knows where `data` lives (a device-resident grid-sample
+    // result handed over by pls_grid_sample_staged, a CUDA tensor, a numpy array) and saves the classification
+    const int hint = layout & (PLS_PTR_DEVICE | PLS_PTR_HOST);
+    layout &= ~(PLS_PTR_DEVICE | PLS_PTR_HOST);
     PLS_REQUIRE(layout >= PLS_INPUT_NDARRAY && layout <= PLS_INPUT_TENSOR_F64, "pls_process_frame: unknown layout");
     PLS_REQUIRE(ctx->cfg.gn_max_iters == 1, "fused ICP path supports gauss_newton_config.max_iters == 1");
     const bool is64 = layout == PLS_INPUT_NDARRAY_F64 || layout == PLS_INPUT_TENSOR_F64;
     const size_t bytes = layout == PLS_INPUT_VERTEX_MAP ? (size_t)3 * ctx->cfg.height * ctx->cfg.width * sizeof(float)
                                                         : (size_t)n * 3 * (is64 ? sizeof(double) : sizeof(float));
-    const void* d = to_device(ctx, data, bytes, ctx->stage_in[0]);
+    const void* d = data;
+    if (hint != PLS_PTR_DEVICE) {
+        if (hint == PLS_PTR_HOST) {
+            ctx->stage_in[0].reserve(bytes, ctx->stream);
+            PLS_CUDA(cudaMemcpyAsync(ctx->stage_in[0].p, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+            d = ctx->stage_in[0].p;
+        } else {
+            d = to_device(ctx, data, bytes, ctx->stage_in[0]);
+        }
+    }
     process_frame_device(ctx, d, layout, n, init_pose, out_pose, out_params, out_has_pose, out_info);
     PLS_API_END(ctx)
 }

@@ -273,7 +273,7 @@ scan_flags_kernel(const uint8_t* __restrict__ flags, int64_t n, uint32_t* __rest
 }  // namespace
 
 void radix_sort_pairs(pls_context* ctx, uint64_t* keys, uint32_t* vals, int64_t n, int num_passes,
-                      uint64_t** keys_out, uint32_t** vals_out) {
+                      uint64_t** keys_out, uint32_t** vals_out, int64_t cap_n) {
     PLS_REQUIRE(num_passes >= 1 && num_passes <= 8, "radix_sort_pairs: 1..8 passes");
     PLS_REQUIRE(n < (1ll << 30), "radix_sort_pairs: n must be < 2^30");
     SortScratch& s = ctx->sort;
@@ -284,12 +284,14 @@ void radix_sort_pairs(pls_context* ctx, uint64_t* keys, uint32_t* vals, int64_t 
         return;
     }
     const int64_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
-    s.keys_alt.reserve(n * sizeof(uint64_t), st);
-    s.vals_alt.reserve(n * sizeof(uint32_t), st);
+    if (cap_n < n) cap_n = n;
+    const int64_t cap_tiles = (cap_n + SORT_TILE - 1) / SORT_TILE;
+    s.keys_alt.reserve(cap_n * sizeof(uint64_t), st);
+    s.vals_alt.reserve(cap_n * sizeof(uint32_t), st);
     const size_t hist_bytes = (8 * RADIX + 1) * sizeof(uint32_t);  // + the histogram kernel's last-block ticket
     const size_t status_words = (size_t)num_passes * tiles * RADIX + 8;
     s.hist.reserve(hist_bytes, st);
-    s.status.reserve(status_words * sizeof(uint32_t), st);
+    s.status.reserve(((size_t)num_passes * cap_tiles * RADIX + 8) * sizeof(uint32_t), st);
     PLS_CUDA(cudaMemsetAsync(s.hist.p, 0, hist_bytes, st));
     PLS_CUDA(cudaMemsetAsync(s.status.p, 0, status_words * sizeof(uint32_t), st));
     // one block per SM at most: every block ends with num_passes * 256 global atomics

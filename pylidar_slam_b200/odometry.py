@@ -518,8 +518,8 @@ class ICPFrameToModel(OdometryAlgorithm):
         if isinstance(data, np.ndarray):
             check_tensor(data, [-1, 3])
             if data.dtype == np.float64:
-                return _lib.INPUT_NDARRAY_F64, np.ascontiguousarray(data), data.shape[0]
-            return _lib.INPUT_NDARRAY, np.ascontiguousarray(data, dtype=np.float32), data.shape[0]
+                return _lib.INPUT_NDARRAY_F64 | _lib.PTR_HOST, np.ascontiguousarray(data), data.shape[0]
+            return _lib.INPUT_NDARRAY | _lib.PTR_HOST, np.ascontiguousarray(data, dtype=np.float32), data.shape[0]
         if isinstance(data, torch.Tensor):
             if data.dim() in (3, 4):
                 vm = data if data.dim() == 4 else data.unsqueeze(0)
@@ -528,9 +528,10 @@ class ICPFrameToModel(OdometryAlgorithm):
                 return _lib.INPUT_VERTEX_MAP, vm.to(torch.float32).contiguous(), 0
             assert_debug(data.dim() == 2)
             check_tensor(data, [-1, 3])
+            hint = _lib.PTR_DEVICE if data.is_cuda else _lib.PTR_HOST
             if data.dtype == torch.float64:
-                return _lib.INPUT_TENSOR_F64, data.contiguous(), data.shape[0]
-            return _lib.INPUT_TENSOR, data.to(torch.float32).contiguous(), data.shape[0]
+                return _lib.INPUT_TENSOR_F64 | hint, data.contiguous(), data.shape[0]
+            return _lib.INPUT_TENSOR | hint, data.to(torch.float32).contiguous(), data.shape[0]
         raise RuntimeError(f"Could not interpret the data: {data} as a pointcloud tensor")
 
     def do_process_next_frame(self, data_dict: dict):
@@ -541,8 +542,16 @@ class ICPFrameToModel(OdometryAlgorithm):
         init = data_dict.get("init_rpose", None)
         init = None if init is None else np.ascontiguousarray(np.asarray(init, dtype=np.float32).reshape(4, 4))
         has_pose = C.c_int(0)
-        self.ctx.call("pls_process_frame", _lib.ptr(data), layout, n, _lib.ptr(init), _lib.ptr(self._pose_out),
+        address = _lib.ptr(data)
+        if layout & _lib.PTR_HOST and n == _lib.Handoff.rows:
+            # the array GridSample.filter handed out (possibly wrapped by ToTensor): its device-resident twin is used
+            # instead of copying the samples host -> device again
+            twin = _lib.Handoff.match(address, n, bool((layout & 0xff) >= _lib.INPUT_NDARRAY_F64), int(self.ctx.cfg.device))
+            if twin:
+                address, layout = twin, (layout & 0xff) | _lib.PTR_DEVICE
+        self.ctx.call("pls_process_frame", address, layout, n, _lib.ptr(init), _lib.ptr(self._pose_out),
                       _lib.ptr(self._params_out), C.byref(has_pose), _lib.ptr(self.last_info))
+        layout &= 0xff
         if not has_pose.value:
             eye = np.eye(4, dtype=np.float32).reshape(1, 4, 4)
             self.relative_poses.append(eye)

@@ -40,6 +40,9 @@ def arr(addr, shape, dtype):
 class FakeContext:
     def __init__(self, **kwargs):
         self.kwargs = kwargs
+        self.cfg = _lib.PlsConfig()
+        self.cfg.device = int(kwargs.get("device", 0) or 0)
+        self._staging = {}  # "device" twins of pls_grid_sample_staged live in host memory here
 
     def close(self):
         pass
@@ -81,6 +84,19 @@ class FakeContext:
         if idx:
             arr(idx, (n,), np.int64)[:len(i)] = i
         count._obj.value = len(i)
+
+    def pls_grid_sample_staged(self, xyz, is64, n, voxel, out_host, idx_host, out_dev, count):
+        dt = np.float64 if is64 else np.float32
+        s, i = orc.grid_sample(arr(xyz, (n, 3), dt), voxel)
+        self._staging = {"xyz": np.ascontiguousarray(s, dtype=dt), "idx": np.ascontiguousarray(i, dtype=np.int64),
+                         "twin": np.ascontiguousarray(s, dtype=dt).copy()}
+        out_host._obj.value = self._staging["xyz"].ctypes.data
+        idx_host._obj.value = self._staging["idx"].ctypes.data
+        out_dev._obj.value = self._staging["twin"].ctypes.data
+        count._obj.value = len(i)
+
+    def pls_wait_stream(self, stream):
+        pass
 
     def pls_align_p2point(self, ref, tgt, n, is64, scheme, sigma, max_iters, norm_stop, x0, dT, x, loss):
         dt = np.float64 if is64 else np.float32
@@ -132,6 +148,7 @@ class FakeContext:
         self.algo = orc.ICPFrameToModelOracle(cfg, orc.Projector(k["height"], k["width"], k["up_fov_deg"], k["down_fov_deg"]))
 
     def pls_process_frame(self, data, layout, n, init, out_pose, out_params, has_pose, info):
+        layout &= 0xff  # residency hints: everything is host memory here
         H, W = self.kwargs["height"], self.kwargs["width"]
         f64 = layout in (_lib.INPUT_NDARRAY_F64, _lib.INPUT_TENSOR_F64)
         if layout == _lib.INPUT_VERTEX_MAP:

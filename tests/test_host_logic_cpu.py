@@ -144,10 +144,11 @@ def test_icp_mirror_float64_layouts_are_announced(b200):
                                      alignment=b200.GaussNewtonPointToPlaneConfig())
     algo = b200.ICPFrameToModel(cfg, projector=b200.SphericalProjector(height=16, width=64, up_fov=3.0, down_fov=-24.0), device="cuda:0")
     pts = np.random.RandomState(0).randn(10, 3)
-    assert algo._interpret(pts)[0] == _lib.INPUT_NDARRAY_F64 and algo._interpret(pts)[1].dtype == np.float64
-    assert algo._interpret(pts.astype(np.float32))[0] == _lib.INPUT_NDARRAY
-    assert algo._interpret(torch.from_numpy(pts))[0] == _lib.INPUT_TENSOR_F64
-    assert algo._interpret(torch.from_numpy(pts).float())[0] == _lib.INPUT_TENSOR
+    # point layouts carry a residency hint in the high bits (host memory here)
+    assert algo._interpret(pts)[0] == _lib.INPUT_NDARRAY_F64 | _lib.PTR_HOST and algo._interpret(pts)[1].dtype == np.float64
+    assert algo._interpret(pts.astype(np.float32))[0] == _lib.INPUT_NDARRAY | _lib.PTR_HOST
+    assert algo._interpret(torch.from_numpy(pts))[0] == _lib.INPUT_TENSOR_F64 | _lib.PTR_HOST
+    assert algo._interpret(torch.from_numpy(pts).float())[0] == _lib.INPUT_TENSOR | _lib.PTR_HOST
     assert algo._interpret(torch.zeros(1, 3, 16, 64, dtype=torch.float64))[0] == _lib.INPUT_VERTEX_MAP
     assert algo._interpret(torch.zeros(1, 3, 16, 64, dtype=torch.float64))[1].dtype == torch.float32
 
