@@ -307,8 +307,8 @@ int pls_destroy(pls_context* ctx) {
     ctx->scan.status.release();
     for (auto& b : ctx->kd.store) b.release();
     ctx->kd.morton.release(); ctx->kd.order.release(); ctx->kd.sorted.release(); ctx->kd.normals.release();
-    ctx->kd.nodes.release(); ctx->kd.parent.release(); ctx->kd.visit.release(); ctx->kd.bbox.release();
-    ctx->kd.inv_order.release(); ctx->kd.grid_hdr.release(); ctx->kd.cells.release();
+    ctx->kd.bbox.release(); ctx->kd.grid_hdr.release(); ctx->kd.cells.release(); ctx->kd.stats.release();
+    ctx->kd_worklist.release();
     ctx->pm.vmaps.release(); ctx->pm.nmaps.release(); ctx->pm.poses.release();
     ctx->pm.model_v.release(); ctx->pm.model_n.release(); ctx->pm.zbuf.release();
     for (auto& b : ctx->frame_vmap_buf) b.release();

@@ -90,7 +90,7 @@ struct ScanScratch {
     DBuf status;  // look-back words + tile counter + total
 };
 
-// ---- LBVH over the kd local map -------------------------------------------------------------
+// ---- the kd local map: point storage + the cell-pyramid search index (kdmap_device.cuh) ---------------------
 struct KdMap {
     // insertion-ordered storage, float4 (x,y,z,unused); ping-pong for the per-frame move
     DBuf store[2];
@@ -98,19 +98,17 @@ struct KdMap {
     int64_t count = 0;                // points in store[cur]
     std::deque<int64_t> frame_counts; // per inserted frame
     // search index
-    DBuf morton, order;     // u64 keys, u32 original index (sorted)
-    DBuf sorted;            // float4 (x,y,z, bitcast original index), Morton order
-    DBuf normals;           // float4 (nx,ny,nz, flag) in Morton order, cleared per rebuild
-    DBuf nodes;             // 64-byte BVH nodes
-    DBuf parent, visit;     // build-time parents (internal then leaves), arrival counters
+    DBuf morton, order;     // u64 cell keys, u32 original index (sorted)
+    DBuf sorted;            // float4 (x,y,z, bitcast original index), level-0 cell order
+    DBuf normals;           // float4 (nx,ny,nz, state word) in sorted order; states carry the build generation
     DBuf bbox;              // 6 ordered-int words
     bool bbox_clean = false; // the header kernel of the last build left the box empty
-    DBuf inv_order;         // sorted position of each stored point (for out_idx)
     DBuf grid_hdr;          // KdGridHeader (quantisation + cell levels)
-    DBuf cells;             // cell hash tables of all levels
+    DBuf cells;             // cell hash tables of all levels (generation-stamped entries, never cleared)
     DBuf stats;             // optional debug counters (PLS_KD_STATS=1)
-    size_t table_offset[4] = {0, 0, 0, 0};
-    uint32_t table_mask[4] = {0, 0, 0, 0};
+    size_t table_offset[16] = {};
+    uint32_t table_mask[16] = {};
+    uint32_t gen = 0;       // generation of the current index build (0 = never built)
     int64_t indexed = 0;    // points covered by the index
     bool valid = false;
     int64_t cap_points = 0; // every per-point array holds this many points (kd_reserve_capacity)
@@ -187,6 +185,7 @@ struct pls_context {
     pls::DBuf queries;                  // float4 queries P0 (owned storage)
     const float4* query_ptr = nullptr;  // the queries of the current frame (may alias frame_pts)
     pls::DBuf nn_prev;                  // previous-iteration match per query
+    pls::DBuf kd_worklist;              // map points whose normal the current iteration has to compute
     pls::DBuf partials;                 // [blocks][NACC] doubles
     pls::DBuf gs_keys, gs_vals, gs_out_xyz, gs_out_idx;
     uint32_t gs_seq = 0;                // stamp of the last compact-key grid sample (overflow detection)
@@ -218,7 +217,8 @@ namespace pls {
 
 // device scalar slots (u32) living behind the FrameResult in ctx->scalars
 enum { SC_GS_COUNT = 0, SC_QUERY_COUNT = 1, SC_NAN_COUNT = 2, SC_INSERT_COUNT = 3, SC_PROJ_NC = 4,
-       SC_TMP0 = 5, SC_TMP1 = 6, SC_GS_OVERFLOW = 7, SC_NUM = 16 };
+       SC_WL0 = 5, SC_WL1 = 6,  // pending-normal worklist counters, one per iteration parity (kdmap.cu)
+       SC_GS_OVERFLOW = 7, SC_NUM = 16 };
 
 // ---- pointer classification + staging ---------------------------------------------------
 bool is_device_ptr(const void* p);           // cached per address
@@ -327,10 +327,10 @@ void kdmap_update(pls_context* ctx, const float* rel_pose_host, const float* pts
 // insertion of already packed float4 points (nullable) whose count the host knows
 void kdmap_update_packed(pls_context* ctx, const float* rel_pose_host, const float4* fresh_dev, int64_t num_new,
                          bool has_new);
-// one fused ICP iteration over ctx->queries; returns the number of partial rows written
-// first: iteration 0 of a frame (no previous matches); fuse_threshold >= 0: finish the iteration (sum + solve + pose
-// update) in the last block of the reduction kernel when the variant supports it (*solved tells).
-int kdmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int num_ranks, bool first, float fuse_threshold,
+// ICP iteration `it` of the frame over ctx->query_ptr; returns the number of partial rows written
+// it == 0: no previous matches; fuse_threshold >= 0: finish the iteration (sum + solve + pose update) in the last
+// block of the reduction kernel (*solved tells).
+int kdmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int num_ranks, int it, float fuse_threshold,
                         bool* solved);
 // pack [n,3] rows without NaN into float4 (stable); count -> *count_dev (u32)
 void pack_valid_rows(pls_context* ctx, const float* pts_dev, int64_t n, float4* out, uint32_t* count_dev);

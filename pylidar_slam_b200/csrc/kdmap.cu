@@ -1,25 +1,22 @@
 // K5/K8 -- the kd local map on the GPU (replaces KdTreeLocalMap, slam/odometry/local_map.py:254-427).
 //
-// Per update (local_map.py:302-369): the whole map is moved by inverse(relative_pose) in float32,
-// the new frame's points are appended, the oldest frame is dropped beyond local_map_size, the
-// search index is rebuilt and the normal cache cleared -- exactly the reference's life cycle,
-// with the pykdtree build replaced by an LBVH build:
+// Per update (local_map.py:302-369): the whole map is moved by inverse(relative_pose) in float32, the new frame's
+// points are appended, the oldest frame is dropped beyond local_map_size, the search index is rebuilt and the normal
+// cache invalidated -- exactly the reference's life cycle, with the pykdtree build replaced by a cell-pyramid build:
 //   kd_move_append_kernel   move + append + bounding box (block reduce, ordered-int atomics)
-//   kd_morton_kernel        48-bit Morton keys (16 bits/axis, cubic cells)
-//   radix sort (6 passes)   primitives.cu
-//   kd_gather_kernel        Morton-ordered float4 copy of the points
-//   kd_hierarchy_kernel     Karras 2012 radix-tree topology, one thread per internal node
-//   kd_boxes_kernel         bottom-up child boxes, second arrival at a node does the work
-// Search (local_map.py:372-422): kd_search_kernel (fine-grained API) and kd_icp_iter_kernel
-// (one launch per ICP iteration: transform, exact 1-NN, lazy 10-NN normals, point-to-plane
-// residual/Jacobian/weight and the block-reduced normal equations).
+//   kd_grid_header_kernel   quantisation of the new bounding box
+//   kd_cell_key_kernel      Morton id of every point's level-0 cell
+//   radix sort (4 passes)   primitives.cu (stable: insertion order inside a cell)
+//   kd_finalize_kernel      sorted float4 copy + the hashed cell tables of all levels
+// Tables and cached normals carry the build's generation number: nothing is cleared between frames.
+// Search (local_map.py:372-422): whole warps per query, see kdmap_device.cuh; one ICP iteration = three launches
+// (kd_nn_warp_kernel, kd_normals_warp_kernel, kd_residual_kernel which also runs the solve in its last block).
 #include <stdlib.h>
 
 #include "gn_device.cuh"
 #include "internal.cuh"
 #include "icp_device.cuh"
 #include "kdmap_device.cuh"
-#include "kdmap_group.cuh"
 #include "pose_device.cuh"
 
 namespace pls {
@@ -119,20 +116,11 @@ __global__ void kd_pack_pixels_kernel(const float* __restrict__ vmap, int64_t hw
         if (flags[i]) out[pos[i]] = make_float4(vmap[i], vmap[hw + i], vmap[2 * hw + i], 0.f);
 }
 
-__device__ __forceinline__ uint64_t spread3(uint64_t x) {
-    x &= 0x1fffffull;
-    x = (x | x << 32) & 0x1f00000000ffffull;
-    x = (x | x << 16) & 0x1f0000ff0000ffull;
-    x = (x | x << 8) & 0x100f00f00f00f00full;
-    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
-    x = (x | x << 2) & 0x1249249249249249ull;
-    return x;
-}
-
-// Quantisation of the map: 256 Morton units per metre (3.9 mm) when the map extent allows it (<= 32 m),
-// else the KD_COORD_BITS-bit range is stretched over the extent (13 bits per axis = 39-bit keys = five 8-bit
-// sort passes; the unit stays far below the cell side, and points sharing a unit are ordered by index).  Level-0 cells are 2^b0 units with a side in
-// [KD_CELL_TARGET, 2 KD_CELL_TARGET).
+// Quantisation of the map: 256 units per metre (3.9 mm) when the map extent allows it (<= 32 m), else the
+// KD_COORD_BITS-bit range is stretched over the extent.  Level-0 cells are 2^b0 units with a side in
+// [cell_target, 2 cell_target) -- but never fewer than KD_MIN_B0 bits are dropped, so that a level-0 cell id
+// (13 - b0 bits per axis, Morton-interleaved) fits 30 bits and the sort needs four 8-bit passes whatever the extent
+// (maps wider than ~160 m simply get coarser cells).
 __global__ void kd_grid_header_kernel(int* __restrict__ bbox, KdGridHeader* __restrict__ hdr, float cell_target) {
     if (threadIdx.x != 0) return;
     const float mnx = ordered_to_float(bbox[0]), mny = ordered_to_float(bbox[1]), mnz = ordered_to_float(bbox[2]);
@@ -140,238 +128,95 @@ __global__ void kd_grid_header_kernel(int* __restrict__ bbox, KdGridHeader* __re
                 ez = ordered_to_float(bbox[5]) - mnz;
     const float ext = fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-6f));
     const float scale = fminf(256.0f, (float)KD_COORD_MAX / ext);
-    int b0 = 0;
+    int b0 = KD_MIN_B0;
     while (b0 < 12 && (float)(1 << b0) < cell_target * scale) ++b0;
     hdr->mn[0] = mnx; hdr->mn[1] = mny; hdr->mn[2] = mnz;
     hdr->scale = scale;
     hdr->b0 = b0;
     hdr->cell0 = (float)(1 << b0) / scale;
-    for (int l = 0; l < KD_LEVELS; ++l) hdr->overflow[l] = 0;
+    hdr->top = KD_COORD_BITS - b0;
+    for (int l = 0; l < KD_MAX_LEVELS; ++l) hdr->overflow[l] = 0;
     // leave the box empty for the next update (saves that update an init launch)
     bbox[0] = bbox[1] = bbox[2] = 0x7fffffff;
     bbox[3] = bbox[4] = bbox[5] = (int)0x80000000;
 }
 
-__global__ void kd_morton_kernel(const float4* __restrict__ pts, int64_t n, const KdGridHeader* __restrict__ hdr,
-                                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+// Sort key of a map point = the Morton id of its level-0 cell (<= 30 bits); the order inside a cell is the
+// insertion order (stable sort), nothing finer is needed: every level's cell is a prefix of this id.
+__global__ void kd_cell_key_kernel(const float4* __restrict__ pts, int64_t n, const KdGridHeader* __restrict__ hdr,
+                                   uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     const float mnx = hdr->mn[0], mny = hdr->mn[1], mnz = hdr->mn[2];
     const float scale = hdr->scale;
+    const int b0 = hdr->b0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        float4 p = pts[i];
-        uint32_t qx = (uint32_t)fminf(fmaxf((p.x - mnx) * scale, 0.f), (float)KD_COORD_MAX);
-        uint32_t qy = (uint32_t)fminf(fmaxf((p.y - mny) * scale, 0.f), (float)KD_COORD_MAX);
-        uint32_t qz = (uint32_t)fminf(fmaxf((p.z - mnz) * scale, 0.f), (float)KD_COORD_MAX);
-        keys[i] = spread3(qx) | (spread3(qy) << 1) | (spread3(qz) << 2);
+        const float4 p = pts[i];
+        const uint32_t qx = (uint32_t)fminf(fmaxf((p.x - mnx) * scale, 0.f), (float)KD_COORD_MAX);
+        const uint32_t qy = (uint32_t)fminf(fmaxf((p.y - mny) * scale, 0.f), (float)KD_COORD_MAX);
+        const uint32_t qz = (uint32_t)fminf(fmaxf((p.z - mnz) * scale, 0.f), (float)KD_COORD_MAX);
+        keys[i] = (uint64_t)kd_cell_id(qx >> b0, qy >> b0, qz >> b0);
         vals[i] = (uint32_t)i;
     }
 }
 
-// Cell tables of all levels in one pass over the sorted keys: thread i is the head of a cell run at
-// level l if its prefix differs from key[i-1]'s, the tail if it differs from key[i+1]'s; heads store
-// `start`, tails store `end` into the slot they find-or-claim (64-bit CAS on the id words).
 struct CellTables {
-    uint4* table[KD_LEVELS];
-    uint32_t mask[KD_LEVELS];
+    uint4* table[KD_MAX_LEVELS];
+    uint32_t mask[KD_MAX_LEVELS];
 };
 
-__device__ __forceinline__ int cell_slot(uint4* table, uint32_t mask, uint64_t id) {
+// Finds or claims the slot of cell `id` in this generation's table.  Slots of older generations are free.
+__device__ __forceinline__ int cell_claim(uint4* table, uint32_t mask, uint32_t id, uint32_t gen) {
+    const unsigned long long want = (unsigned long long)id | ((unsigned long long)gen << 32);
     uint32_t h = kd_hash(id) & mask;
-    const unsigned long long want = id + 1;
     for (int probe = 0; probe < 64; ++probe) {
         unsigned long long* word = reinterpret_cast<unsigned long long*>(&table[h]);
-        const unsigned long long old = atomicCAS(word, 0ull, want);
-        if (old == 0ull || old == want) return (int)h;
+        unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(word);
+        while (true) {
+            if (old == want) return (int)h;
+            if ((uint32_t)(old >> 32) == gen) break;  // another cell of this generation lives here
+            const unsigned long long prev = atomicCAS(word, old, want);
+            if (prev == old) return (int)h;
+            old = prev;
+        }
         h = (h + 1) & mask;
     }
     return -1;
 }
 
-__global__ void kd_cells_kernel(const uint64_t* __restrict__ keys, int64_t n, CellTables T, KdGridHeader* hdr) {
-    const int b0 = hdr->b0;
+// One pass over the sorted order finishes the index: the Morton-ordered float4 copy of the points and the cell
+// tables of ALL levels -- element i is the head of a level-l cell run if its id prefix differs from element i-1's,
+// i.e. for every level up to (highest differing bit) / 3, and the tail likewise against element i+1; heads store
+// `first`, tails store `last` into the slot they find-or-claim.
+__global__ void __launch_bounds__(256)
+kd_finalize_kernel(const float4* __restrict__ pts, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ order,
+                   int64_t n, CellTables T, KdGridHeader* hdr, uint32_t gen, float4* __restrict__ sorted) {
+    const int top = hdr->top;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const uint64_t k = keys[i];
-        const uint64_t kp = i > 0 ? keys[i - 1] : ~0ull;
-        const uint64_t kn = i + 1 < n ? keys[i + 1] : ~0ull;
-#pragma unroll
-        for (int l = 0; l < KD_LEVELS; ++l) {
-            const int sh = 3 * (b0 + l);
-            const uint64_t id = k >> sh;
-            const bool head = (i == 0) || ((kp >> sh) != id);
-            const bool tail = (i + 1 == n) || ((kn >> sh) != id);
-            if (head || tail) {
-                const int slot = cell_slot(T.table[l], T.mask[l], id);
-                if (slot < 0) {
-                    hdr->overflow[l] = 1;
-                } else {
-                    if (head) T.table[l][slot].z = (uint32_t)i;
-                    if (tail) T.table[l][slot].w = (uint32_t)i;
-                }
-            }
-        }
-    }
-}
-
-__global__ void kd_gather_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ order, int64_t n,
-                                 float4* __restrict__ sorted, uint32_t* __restrict__ inv_order) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        uint32_t src = order[i];
+        const uint32_t src = order[i];
         float4 p = pts[src];
         p.w = __uint_as_float(src);
         sorted[i] = p;
-        inv_order[src] = (uint32_t)i;
-    }
-}
-
-__device__ __forceinline__ int delta_fn(const uint64_t* __restrict__ keys, int n, int i, int j) {
-    if (j < 0 || j >= n) return -1;
-    uint64_t a = keys[i], b = keys[j];
-    if (a == b) return 64 + __clz(i ^ j);
-    return __clzll((long long)(a ^ b));
-}
-
-// Karras 2012: internal node i in [0, n-2]
-__global__ void kd_hierarchy_kernel(const uint64_t* __restrict__ keys, int n, int4* __restrict__ ranges,
-                                    int* __restrict__ parent /* [n-1 internal][n leaves] */) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n - 1; i += gridDim.x * blockDim.x) {
-        const int d = (delta_fn(keys, n, i, i + 1) - delta_fn(keys, n, i, i - 1)) >= 0 ? 1 : -1;
-        const int dmin = delta_fn(keys, n, i, i - d);
-        int lmax = 2;
-        while (delta_fn(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
-        int l = 0;
-        for (int t = lmax >> 1; t >= 1; t >>= 1)
-            if (delta_fn(keys, n, i, i + (l + t) * d) > dmin) l += t;
-        const int j = i + l * d;
-        const int dnode = delta_fn(keys, n, i, j);
-        int s = 0;
-        int t = l;
-        do {
-            t = (t + 1) >> 1;
-            if (delta_fn(keys, n, i, i + (s + t) * d) > dnode) s += t;
-        } while (t > 1);
-        const int gamma = i + s * d + min(d, 0);
-        const int first = min(i, j), last = max(i, j);
-        ranges[i] = make_int4(first, gamma, last, 0);
-        if (first == gamma) parent[(n - 1) + gamma] = i; else parent[gamma] = i;
-        if (last == gamma + 1) parent[(n - 1) + gamma + 1] = i; else parent[gamma + 1] = i;
-        if (i == 0) parent[0] = -1;
-    }
-}
-
-// Box of a child of a "big" node: a treelet (<= KD_LEAF points, scanned directly) or a completed big node.
-__device__ __forceinline__ void child_box(const float4* __restrict__ sorted, const float4* nodes, int lo, int hi,
-                                          int internal_id, float* mn, float* mx) {
-    if (hi - lo + 1 <= KD_LEAF) {
-        float4 p = sorted[lo];
-        mn[0] = mx[0] = p.x; mn[1] = mx[1] = p.y; mn[2] = mx[2] = p.z;
-        for (int i = lo + 1; i <= hi; ++i) {
-            p = sorted[i];
-            mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
-            mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+        const uint32_t k = (uint32_t)keys[i];
+        // number of levels (from 0) at which this element starts / ends a run
+        int nh = top + 1, nt = top + 1;
+        if (i > 0) {
+            const uint32_t d = k ^ (uint32_t)keys[i - 1];
+            nh = d ? min((31 - __clz((int)d)) / 3 + 1, top + 1) : 0;
         }
-    } else {
-        const float4 a = __ldcg(nodes + 4 * (size_t)internal_id);
-        const float4 b = __ldcg(nodes + 4 * (size_t)internal_id + 1);
-        const float4 c = __ldcg(nodes + 4 * (size_t)internal_id + 2);
-        mn[0] = fminf(a.x, b.z); mn[1] = fminf(a.y, b.w); mn[2] = fminf(a.z, c.x);
-        mx[0] = fmaxf(a.w, c.y); mx[1] = fmaxf(b.x, c.z); mx[2] = fmaxf(b.y, c.w);
-    }
-}
-
-// Bottom-up child boxes of the BIG nodes (> KD_LEAF points).  Subtrees of <= KD_LEAF points ("treelets")
-// are never descended by the search (they are scanned linearly), so the pass starts at the treelet roots:
-// thread t < n-1 is internal node t, thread t >= n-1 is point leaf t-(n-1); a thread whose node is small
-// while its parent is big "arrives" at the parent; the second arrival at a node computes its child boxes
-// and continues upward.  Chains are ~log2(KD_LEAF) levels shorter than a per-point pass.
-__global__ void kd_boxes_kernel(const float4* __restrict__ sorted, int n, const int4* __restrict__ ranges,
-                                const int* __restrict__ parent, int* __restrict__ visit, float4* nodes) {
-    const int total = 2 * n - 1;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-        int cur;
-        if (t < n - 1) {
-            const int4 rg = ranges[t];
-            if (rg.z - rg.x + 1 > KD_LEAF || t == 0) continue;  // big node (completed by its children) or root
-            cur = parent[t];
-        } else {
-            cur = parent[t];  // point leaf
+        if (i + 1 < n) {
+            const uint32_t d = k ^ (uint32_t)keys[i + 1];
+            nt = d ? min((31 - __clz((int)d)) / 3 + 1, top + 1) : 0;
         }
-        {
-            const int4 pr = ranges[cur];
-            if (pr.z - pr.x + 1 <= KD_LEAF) continue;  // inside a treelet: nothing to do
-        }
-        bool wrote = false;  // a thread arriving from a treelet has published nothing yet: no fence needed
-        while (cur >= 0) {
-            if (wrote) __threadfence();
-            wrote = true;
-            if (atomicAdd(&visit[cur], 1) == 0) break;  // first arrival: the sibling subtree is not done
-            const int4 rg = ranges[cur];
-            float lmn[3], lmx[3], rmn[3], rmx[3];
-            child_box(sorted, nodes, rg.x, rg.y, rg.y, lmn, lmx);
-            child_box(sorted, nodes, rg.y + 1, rg.z, rg.y + 1, rmn, rmx);
-            float4* o = nodes + 4 * (size_t)cur;
-            __stcg(o + 0, make_float4(lmn[0], lmn[1], lmn[2], lmx[0]));
-            __stcg(o + 1, make_float4(lmx[1], lmx[2], rmn[0], rmn[1]));
-            __stcg(o + 2, make_float4(rmn[2], rmx[0], rmx[1], rmx[2]));
-            __stcg(o + 3, make_float4(__int_as_float(rg.x), __int_as_float(rg.y), __int_as_float(rg.z), 0.f));
-            cur = parent[cur];
+        const int nl = max(nh, nt);
+        for (int l = 0; l < nl; ++l) {
+            const int slot = cell_claim(T.table[l], T.mask[l], k >> (3 * l), gen);
+            if (slot < 0) {
+                hdr->overflow[l] = 1;
+            } else {
+                if (l < nh) T.table[l][slot].z = (uint32_t)i;
+                if (l < nt) T.table[l][slot].w = (uint32_t)i;
+            }
         }
     }
-}
-
-// Fine-grained search: queries [n,3] -> neighbour points, normals, insertion indices.
-__global__ void __launch_bounds__(128)
-kd_search_kernel(KdIndex ix, int k_normals, const float* __restrict__ queries, int64_t n, float* __restrict__ out_nb,
-                 float* __restrict__ out_nrm, long long* __restrict__ out_idx) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        float x = queries[3 * i], y = queries[3 * i + 1], z = queries[3 * i + 2];
-        int pos = kd_nearest_fast(ix, x, y, z, -1, nullptr);
-        float4 q = __ldg(ix.sorted + pos);
-        out_nb[3 * i] = q.x; out_nb[3 * i + 1] = q.y; out_nb[3 * i + 2] = q.z;
-        if (out_idx) out_idx[i] = (long long)__float_as_uint(q.w);
-        if (out_nrm) {
-            float nn[3];
-            kd_cached_normal(ix, pos, k_normals, nn);
-            out_nrm[3 * i] = nn[0]; out_nrm[3 * i + 1] = nn[1]; out_nrm[3 * i + 2] = nn[2];
-        }
-    }
-}
-
-constexpr int KD_ITER_THREADS = 128;
-
-// One ICP iteration on the kd map (icp_odometry.py:275-284 + alignment.py:91-127 at x0 = 0):
-//   p = T p0; q = NN(p); n = normal(q); r = n.(p - q); J = [n, p x n]; w; reduce.
-__global__ void __launch_bounds__(KD_ITER_THREADS)
-kd_icp_iter_kernel(KdIndex ix, int k_normals, const float4* __restrict__ queries, const uint32_t* __restrict__ nq_dev,
-                   int64_t q_begin, int64_t q_stride, const FrameResult* __restrict__ fr, int scheme, float sigma,
-                   int* __restrict__ nn_prev, double* __restrict__ partials) {
-    if (fr->done) return;
-    __shared__ float sT[12];
-    if (threadIdx.x < 12) sT[threadIdx.x] = fr->T[threadIdx.x];
-    __syncthreads();
-    const int64_t nq = (int64_t)*nq_dev;
-    double acc[NACC];
-#pragma unroll
-    for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
-    // q_begin/q_stride shard the queries across ranks (multi-GPU): rank r takes r, r+R, ...
-    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;; s += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t qi = q_begin + s * q_stride;
-        if (qi >= nq) break;
-        const float4 p0 = queries[qi];
-        float p[3];
-        p[0] = p0.x * sT[0] + p0.y * sT[1] + p0.z * sT[2] + sT[3];
-        p[1] = p0.x * sT[4] + p0.y * sT[5] + p0.z * sT[6] + sT[7];
-        p[2] = p0.x * sT[8] + p0.y * sT[9] + p0.z * sT[10] + sT[11];
-        const int pos = kd_nearest_fast(ix, p[0], p[1], p[2], nn_prev[qi], nullptr);
-        nn_prev[qi] = pos;
-        const float4 qq = __ldg(ix.sorted + pos);
-        float q[3] = {qq.x, qq.y, qq.z};
-        float nn[3];
-        kd_cached_normal(ix, pos, k_normals, nn);
-        float J[6];
-        float r = p2plane_residual_jacobian_identity(p, q, nn, J);
-        float w = ls_weight<float>(scheme, sigma, r, p, q);
-        accumulate_normal_equations<float>(acc, J, w, r * w, r);
-    }
-    block_reduce_store<KD_ITER_THREADS>(acc, partials + (size_t)blockIdx.x * NACC);
 }
 
 __global__ void kd_export_kernel(const float4* __restrict__ pts, int64_t n, float* __restrict__ out) {
@@ -381,60 +226,103 @@ __global__ void kd_export_kernel(const float4* __restrict__ pts, int64_t n, floa
     }
 }
 
-constexpr int KD_GROUP_THREADS = 128;
-constexpr int KD_NGROUP_LATER_DEFAULT = 0;  // 0 = same group width in every iteration; 32 = a warp per pending normal later
+// ---- one ICP iteration on the kd map (icp_odometry.py:275-284 + alignment.py:91-127 at x0 = 0) -----------------------
+//   p = T p0; q = NN(p); n = normal(q); r = n.(p - q); J = [n, p x n]; w; reduce        -- three launches:
+//   kd_nn_warp_kernel       a warp per query: transform, exact 1-NN (kdmap_device.cuh) -> match[qi]; the first warp to
+//                           match a map point whose normal is not cached claims it (CAS on the state word) and
+//                           queues it (block-aggregated append: one global atomic per block)
+//   kd_normals_warp_kernel  a warp per queued map point: exact (k+1)-NN, second moments; the eigen-solves are deferred
+//                           and run lane-parallel (each lane one point) so that no warp idles behind a serial solve
+//   kd_residual_kernel      a thread per query: r, J, robust weight, the 30 fp64 accumulators -> block partials; the
+//                           last block sums them in fixed order and runs the solve / stop test / pose update
+constexpr int KD_THREADS = 256;
+constexpr int KD_WARPS = KD_THREADS / 32;
+constexpr int KD_QPW_MAX = 8;   // queries per warp of the search kernel (bounds the block's claim list)
 
-// The same ICP iteration as kd_icp_iter_kernel, split in three launches so that the two searches can run
-// with G lanes per query (kdmap_group.cuh) at full residency and the reduction stays thread-per-query:
-//   kd_nn_group_kernel      p = T p0, exact 1-NN -> nn_prev[qi]
-//   kd_normals_group_kernel lazily cached 10-NN normal of every matched map point that has none yet
-//   kd_residual_kernel      r, J = [n, p x n], robust weight, the 30 fp64 accumulators -> block partials
-template <int G>
-__global__ void __launch_bounds__(KD_GROUP_THREADS, 8)
-kd_nn_group_kernel(KdIndex ix, const float4* __restrict__ queries, const uint32_t* __restrict__ nq_dev, int64_t q_begin,
-                   int64_t q_stride, const FrameResult* __restrict__ fr, int* __restrict__ nn_prev, int first) {
-    if (fr->done) return;
+__global__ void __launch_bounds__(KD_THREADS)
+kd_nn_warp_kernel(KdIndex ix, const float4* __restrict__ queries, const uint32_t* __restrict__ nq_dev, int64_t q_begin,
+                  int64_t q_stride, int qpw, const float* __restrict__ T, const int* __restrict__ done,
+                  int* __restrict__ match, int use_hint, int* __restrict__ worklist, uint32_t* wl_count, int parity) {
+    if (done && *done) return;
     __shared__ float sT[12];
-    if (threadIdx.x < 12) sT[threadIdx.x] = fr->T[threadIdx.x];
+    __shared__ int s_list[KD_WARPS * KD_QPW_MAX];
+    __shared__ int s_n, s_base;
+    if (threadIdx.x < 12) sT[threadIdx.x] = T[threadIdx.x];
+    if (threadIdx.x == 0) {
+        s_n = 0;
+        if (blockIdx.x == 0) wl_count[parity ^ 1] = 0;  // the other slot: consumed by the previous iteration, used by the next
+    }
     __syncthreads();
-    const LaneGroup<G> lg;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const KdGridLocal g = kd_load_grid(ix);
     const int64_t nq = (int64_t)*nq_dev;
-    const int64_t groups_total = (int64_t)gridDim.x * (KD_GROUP_THREADS / G);
-    for (int64_t s = ((int64_t)blockIdx.x * KD_GROUP_THREADS + threadIdx.x) / G;; s += groups_total) {
+    const int64_t total_warps = (int64_t)gridDim.x * KD_WARPS;
+    const uint32_t claimed = kd_normal_claimed(ix.gen), valid = kd_normal_valid(ix.gen);
+    for (int k = 0; k < qpw; ++k) {
+        const int64_t s = (int64_t)blockIdx.x * KD_WARPS + warp + (int64_t)k * total_warps;
         const int64_t qi = q_begin + s * q_stride;
         if (qi >= nq) break;
         const float4 p0 = queries[qi];
         const float px = p0.x * sT[0] + p0.y * sT[1] + p0.z * sT[2] + sT[3];
         const float py = p0.x * sT[4] + p0.y * sT[5] + p0.z * sT[6] + sT[7];
         const float pz = p0.x * sT[8] + p0.y * sT[9] + p0.z * sT[10] + sT[11];
-        const int hint = (lg.sub == 0 && !first) ? nn_prev[qi] : -1;
-        const int pos = group_nearest<G>(ix, lg, px, py, pz, hint);
-        if (lg.sub == 0) nn_prev[qi] = pos;
+        const int hint = use_hint ? match[qi] : -1;
+        const int pos = warp_nearest(ix, g, px, py, pz, hint, lane);
+        if (lane == 0) {
+            match[qi] = pos;
+            if (pos >= 0 && worklist) {
+                uint32_t* w = reinterpret_cast<uint32_t*>(&ix.normals[pos].w);
+                const uint32_t cur = __ldcg(w);
+                if (cur != valid && cur != claimed && atomicCAS(w, cur, claimed) == cur) s_list[atomicAdd(&s_n, 1)] = pos;
+            }
+        }
     }
+    __syncthreads();
+    const int n = s_n;
+    if (n == 0) return;
+    if (threadIdx.x == 0) s_base = (int)atomicAdd(&wl_count[parity], (uint32_t)n);
+    __syncthreads();
+    if (threadIdx.x < n) worklist[s_base + threadIdx.x] = s_list[threadIdx.x];
 }
 
-template <int G>
-__global__ void __launch_bounds__(KD_GROUP_THREADS)
-kd_normals_group_kernel(KdIndex ix, int k_normals, const uint32_t* __restrict__ nq_dev, int64_t q_begin, int64_t q_stride,
-                        const FrameResult* __restrict__ fr, const int* __restrict__ nn_prev) {
-    if (fr->done) return;
-    const LaneGroup<G> lg;
-    const int64_t nq = (int64_t)*nq_dev;
-    const int64_t groups_total = (int64_t)gridDim.x * (KD_GROUP_THREADS / G);
-    for (int64_t s = ((int64_t)blockIdx.x * KD_GROUP_THREADS + threadIdx.x) / G;; s += groups_total) {
-        const int64_t qi = q_begin + s * q_stride;
-        if (qi >= nq) break;
-        const int pos = nn_prev[qi];
-        // one lane decides for the group (another group may publish the same normal concurrently)
-        const float valid = lg.bcast(lg.sub == 0 ? __ldcg(ix.normals + pos).w : 0.f);
-        if (valid != 0.f) continue;
-        float nn[3];
-        if (k_normals == 10) {
-            group_point_normal_k10<G>(ix, lg, pos, nn);
-        } else if (lg.sub == 0) {
-            kd_point_normal(ix, pos, k_normals, nn);
+__global__ void __launch_bounds__(KD_THREADS)
+kd_normals_warp_kernel(KdIndex ix, int k_normals, const int* __restrict__ worklist, const uint32_t* __restrict__ wl_count,
+                       const int* __restrict__ done) {
+    if (done && *done) return;
+    const int n = (int)*wl_count;
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * KD_WARPS + (threadIdx.x >> 5);
+    const int total_warps = gridDim.x * KD_WARPS;
+    if (warp_global >= n) return;
+    const KdGridLocal g = kd_load_grid(ix);
+    const float valid = __uint_as_float(kd_normal_valid(ix.gen));
+    float mycov[6];
+    int mypos = -1, held = 0;
+    for (int e = warp_global; e < n; e += total_warps) {
+        const int pos = worklist[e];
+        const float4 c = __ldg(ix.sorted + pos);
+        float nd;
+        int ni;
+        const int found = warp_knn(ix, g, c.x, c.y, c.z, k_normals + 1, lane, nd, ni);
+        float cov[6];
+        warp_second_moments(ix, c, k_normals, found, ni, lane, cov);
+        if (lane == held) {
+#pragma unroll
+            for (int a = 0; a < 6; ++a) mycov[a] = cov[a];
+            mypos = pos;
         }
-        if (lg.sub == 0) __stcg(ix.normals + pos, make_float4(nn[0], nn[1], nn[2], 1.f));
+        if (++held == 32) {  // 32 moments collected: every lane solves its own
+            float nn[3];
+            smallest_eigenvector(mycov, nn);
+            __stcg(ix.normals + mypos, make_float4(nn[0], nn[1], nn[2], valid));
+            held = 0;
+            mypos = -1;
+        }
+    }
+    if (mypos >= 0) {
+        float nn[3];
+        smallest_eigenvector(mycov, nn);
+        __stcg(ix.normals + mypos, make_float4(nn[0], nn[1], nn[2], valid));
     }
 }
 
@@ -443,7 +331,7 @@ constexpr int KD_RES_THREADS = 256;
 __global__ void __launch_bounds__(KD_RES_THREADS)
 kd_residual_kernel(KdIndex ix, const float4* __restrict__ queries, const uint32_t* __restrict__ nq_dev, int64_t q_begin,
                    int64_t q_stride, FrameResult* fr, int scheme, float sigma,
-                   const int* __restrict__ nn_prev, double* __restrict__ partials, float fuse_threshold) {
+                   const int* __restrict__ match, double* __restrict__ partials, float fuse_threshold) {
     if (fr->done) return;
     __shared__ float sT[12];
     if (threadIdx.x < 12) sT[threadIdx.x] = fr->T[threadIdx.x];
@@ -460,7 +348,8 @@ kd_residual_kernel(KdIndex ix, const float4* __restrict__ queries, const uint32_
         p[0] = p0.x * sT[0] + p0.y * sT[1] + p0.z * sT[2] + sT[3];
         p[1] = p0.x * sT[4] + p0.y * sT[5] + p0.z * sT[6] + sT[7];
         p[2] = p0.x * sT[8] + p0.y * sT[9] + p0.z * sT[10] + sT[11];
-        const int pos = nn_prev[qi];
+        const int pos = match[qi];
+        if (pos < 0) continue;
         const float4 qq = __ldg(ix.sorted + pos);
         const float4 nv = __ldcg(ix.normals + pos);
         float q[3] = {qq.x, qq.y, qq.z};
@@ -474,71 +363,35 @@ kd_residual_kernel(KdIndex ix, const float4* __restrict__ queries, const uint32_
     if (fuse_threshold >= 0.f) icp_finish_in_last_block(fr, partials, fuse_threshold);
 }
 
-template <int G>
-int launch_group_iteration(pls_context* ctx, const KdIndex& ix, int64_t mine, const uint32_t* nq_dev, int rank, int num_ranks,
-                           bool first, float fuse_threshold) {
-    cudaStream_t st = ctx->stream;
-    const int gblocks = grid_for(mine * G, KD_GROUP_THREADS, 16 * kNumSMs);
-    int* nn_prev = ctx->nn_prev.as<int>();
-    FrameResult* fr = frame_result_dev(ctx);
-    kd_nn_group_kernel<G><<<gblocks, KD_GROUP_THREADS, 0, st>>>(ix, ctx->query_ptr, nq_dev, (int64_t)rank,
-                                                                (int64_t)num_ranks, fr, nn_prev, first ? 1 : 0);
-    PLS_CHECK_LAUNCH();
-    // lanes per pending normal (default = the search's G; PLS_KD_NGROUP=2|4|8 decouples the two for A/B runs: later
-    // iterations only compute a few hundred new normals, where a wider group shortens the straggler chains)
-    static const int ngroup = getenv("PLS_KD_NGROUP") ? atoi(getenv("PLS_KD_NGROUP")) : G;
-    // Iterations >= 2 of a frame only meet a few hundred new matches: the kernel is then a tail of a few groups
-    // walking long dependent 10-NN chains while the grid has drained (profiles/r1_kd_traffic.json: 7-9 of 32 lanes
-    // active, 33-83 us).  PLS_KD_NGROUP_LATER=32 hands every pending normal of those iterations a full warp (one of
-    // the 27 cells per lane); the first iteration, where all ~32 k matches need a normal and throughput matters,
-    // keeps the narrow groups.
-    static const int later = getenv("PLS_KD_NGROUP_LATER") ? atoi(getenv("PLS_KD_NGROUP_LATER")) : KD_NGROUP_LATER_DEFAULT;
-    if (!first && later == 32) {
-        kd_normals_group_kernel<32><<<grid_for(mine * 32, KD_GROUP_THREADS, 16 * kNumSMs), KD_GROUP_THREADS, 0, st>>>(
-            ix, ctx->cfg.num_neighbors_normals, nq_dev, (int64_t)rank, (int64_t)num_ranks, fr, nn_prev);
-    } else if (ngroup == 8 && G != 8) {
-        kd_normals_group_kernel<8><<<grid_for(mine * 8, KD_GROUP_THREADS, 16 * kNumSMs), KD_GROUP_THREADS, 0, st>>>(
-            ix, ctx->cfg.num_neighbors_normals, nq_dev, (int64_t)rank, (int64_t)num_ranks, fr, nn_prev);
-    } else if (ngroup == 2 && G != 2) {
-        kd_normals_group_kernel<2><<<grid_for(mine * 2, KD_GROUP_THREADS, 16 * kNumSMs), KD_GROUP_THREADS, 0, st>>>(
-            ix, ctx->cfg.num_neighbors_normals, nq_dev, (int64_t)rank, (int64_t)num_ranks, fr, nn_prev);
-    } else if (ngroup == 4 && G != 4) {
-        kd_normals_group_kernel<4><<<grid_for(mine * 4, KD_GROUP_THREADS, 16 * kNumSMs), KD_GROUP_THREADS, 0, st>>>(
-            ix, ctx->cfg.num_neighbors_normals, nq_dev, (int64_t)rank, (int64_t)num_ranks, fr, nn_prev);
-    } else {
-        kd_normals_group_kernel<G><<<gblocks, KD_GROUP_THREADS, 0, st>>>(ix, ctx->cfg.num_neighbors_normals, nq_dev,
-                                                                         (int64_t)rank, (int64_t)num_ranks, fr, nn_prev);
-    }
-    PLS_CHECK_LAUNCH();
-    const int blocks = grid_for(mine, KD_RES_THREADS, 8 * kNumSMs);
-    ctx->partials.reserve((size_t)blocks * NACC * sizeof(double), st);
-    kd_residual_kernel<<<blocks, KD_RES_THREADS, 0, st>>>(ix, ctx->query_ptr, nq_dev, (int64_t)rank, (int64_t)num_ranks, fr,
-                                                          ctx->cfg.scheme, ctx->cfg.sigma, nn_prev,
-                                                          ctx->partials.as<double>(), fuse_threshold);
-    PLS_CHECK_LAUNCH();
-    return blocks;
+// Fine-grained API: [n,3] rows -> float4 queries (no row is dropped: outputs stay aligned with the inputs)
+__global__ void kd_rows_to_float4_kernel(const float* __restrict__ rows, int64_t n, float4* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = make_float4(rows[3 * i], rows[3 * i + 1], rows[3 * i + 2], 0.f);
 }
 
-KdIndex make_index(pls_context* ctx) {
-    KdIndex ix;
-    ix.sorted = ctx->kd.sorted.as<float4>();
-    ix.nodes = ctx->kd.nodes.as<float4>();
-    ix.normals = ctx->kd.normals.as<float4>();
-    ix.M = (int)ctx->kd.indexed;
-    ix.grid = ctx->kd.grid_hdr.as<KdGridHeader>();
-    for (int l = 0; l < KD_LEVELS; ++l) {
-        ix.table[l] = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(ctx->kd.cells.p) + ctx->kd.table_offset[l]);
-        ix.mask[l] = ctx->kd.table_mask[l];
+__global__ void kd_search_export_kernel(KdIndex ix, const int* __restrict__ match, int64_t n, float* __restrict__ out_nb,
+                                        float* __restrict__ out_nrm, long long* __restrict__ out_idx) {
+    const float nan = __int_as_float(0x7fc00000);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int pos = match[i];
+        float4 q = make_float4(nan, nan, nan, 0.f), nv = make_float4(nan, nan, nan, 0.f);
+        long long idx = -1;
+        if (pos >= 0) {
+            q = __ldg(ix.sorted + pos);
+            idx = (long long)__float_as_uint(q.w);
+            if (out_nrm) nv = __ldcg(ix.normals + pos);
+        }
+        out_nb[3 * i] = q.x; out_nb[3 * i + 1] = q.y; out_nb[3 * i + 2] = q.z;
+        if (out_idx) out_idx[i] = idx;
+        if (out_nrm) { out_nrm[3 * i] = nv.x; out_nrm[3 * i + 1] = nv.y; out_nrm[3 * i + 2] = nv.z; }
     }
-    ix.stats = ctx->kd.stats.p ? ctx->kd.stats.as<unsigned long long>() : nullptr;
-    return ix;
 }
 
 size_t cell_table_bytes(int64_t M, uint32_t* masks, size_t* offsets) {
     size_t off = 0;
-    for (int l = 0; l < KD_LEVELS; ++l) {
+    for (int l = 0; l < KD_MAX_LEVELS; ++l) {
         uint64_t want = (uint64_t)(1.5 * (double)M) >> l;
-        uint32_t sz = 1024;
+        uint32_t sz = 64;
         while (sz < want) sz <<= 1;
         if (masks) masks[l] = sz - 1;
         if (offsets) offsets[l] = off;
@@ -552,11 +405,14 @@ size_t cell_table_bytes(int64_t M, uint32_t* masks, size_t* offsets) {
 // frame seen, 30 % head-room) on the first insertion means NO further allocation -- and none of the stream
 // synchronisations an allocation implies -- while the map fills up, i.e. inside any timed region that starts after
 // the first frame.  `need` beyond the plan (a denser frame later on) re-plans with 25 % head-room.
+// Tables and normal states are generation-stamped and never cleared per build, so fresh memory is zeroed here once
+// (generation 0 is never used).
 void kd_reserve_capacity(pls_context* ctx, int64_t need) {
     KdMap& kd = ctx->kd;
     if (need <= kd.cap_points) return;
     cudaStream_t st = ctx->stream;
-    const int64_t steady = (int64_t)(1.3 * (double)kd.max_frame * (double)(ctx->cfg.local_map_size + 1));
+    int64_t steady = (int64_t)(1.3 * (double)kd.max_frame * (double)(ctx->cfg.local_map_size + 1));
+    if (steady > need + (8ll << 20)) steady = need + (8ll << 20);  // a multi-million-point insertion plans 8 M ahead at most
     int64_t cap = need + need / 4 + 64;
     if (cap < steady) cap = steady;
     const size_t C = (size_t)cap;
@@ -566,14 +422,30 @@ void kd_reserve_capacity(pls_context* ctx, int64_t need) {
     kd.order.reserve_exact(C * sizeof(uint32_t), st);
     kd.sorted.reserve_exact(C * sizeof(float4), st);
     kd.normals.reserve_exact(C * sizeof(float4), st);
-    kd.inv_order.reserve_exact(C * sizeof(uint32_t), st);
-    kd.nodes.reserve_exact(C * 64, st);
-    kd.parent.reserve_exact(2 * C * sizeof(int), st);
-    kd.visit.reserve_exact(C * sizeof(int) + C * sizeof(int4) + 16, st);
-    kd.cells.reserve_exact(cell_table_bytes(cap, nullptr, nullptr), st);
+    const size_t table_bytes = cell_table_bytes(cap, nullptr, nullptr);
+    kd.cells.reserve_exact(table_bytes, st);
+    PLS_CUDA(cudaMemsetAsync(kd.normals.p, 0, C * sizeof(float4), st));
+    PLS_CUDA(cudaMemsetAsync(kd.cells.p, 0, table_bytes, st));
     kd.cap_points = cap;
 }
 
+KdIndex make_index(pls_context* ctx) {
+    KdIndex ix;
+    ix.sorted = ctx->kd.sorted.as<float4>();
+    ix.normals = ctx->kd.normals.as<float4>();
+    ix.M = (int)ctx->kd.indexed;
+    ix.gen = ctx->kd.gen;
+    ix.grid = ctx->kd.grid_hdr.as<KdGridHeader>();
+    for (int l = 0; l < KD_MAX_LEVELS; ++l) {
+        ix.table[l] = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(ctx->kd.cells.p) + ctx->kd.table_offset[l]);
+        ix.mask[l] = ctx->kd.table_mask[l];
+    }
+    ix.stats = ctx->kd.stats.p ? ctx->kd.stats.as<unsigned long long>() : nullptr;
+    return ix;
+}
+
+// The per-frame index build (stands in for the KDTree rebuild of local_map.py:365-369): header, cell keys, four
+// radix passes, one finishing pass.  Nothing is cleared: tables and normal states carry the build's generation.
 void build_index(pls_context* ctx) {
     KdMap& kd = ctx->kd;
     cudaStream_t st = ctx->stream;
@@ -584,45 +456,34 @@ void build_index(pls_context* ctx) {
     ProfileScope ps(ctx, 3, (double)M * 32.0);
     PLS_REQUIRE(M < (1ll << 30), "kd map: too many points");
     kd_reserve_capacity(ctx, M);
+    kd.gen += 1;
+    if (kd.gen >= 0x7ffffff0u) {  // state words are 2 gen (+1): restart the generations on clean memory
+        PLS_CUDA(cudaMemsetAsync(kd.normals.p, 0, kd.normals.cap, st));
+        PLS_CUDA(cudaMemsetAsync(kd.cells.p, 0, kd.cells.cap, st));
+        kd.gen = 1;
+    }
     const float4* pts = kd.store[kd.cur].as<float4>();
-    PLS_CUDA(cudaMemsetAsync(kd.normals.p, 0, (size_t)M * sizeof(float4), st));
     kd.grid_hdr.reserve(sizeof(KdGridHeader), st);
     static const float cell_target = getenv("PLS_KD_CELL") ? (float)atof(getenv("PLS_KD_CELL")) : KD_CELL_TARGET;
     kd_grid_header_kernel<<<1, 32, 0, st>>>(kd.bbox.as<int>(), kd.grid_hdr.as<KdGridHeader>(), cell_target);
     PLS_CHECK_LAUNCH();
     kd.bbox_clean = true;
-    kd_morton_kernel<<<grid_for(M, 256, 8 * kNumSMs), 256, 0, st>>>(pts, M, kd.grid_hdr.as<KdGridHeader>(),
-                                                                     kd.morton.as<uint64_t>(), kd.order.as<uint32_t>());
+    kd_cell_key_kernel<<<grid_for(M, 256, 8 * kNumSMs), 256, 0, st>>>(pts, M, kd.grid_hdr.as<KdGridHeader>(),
+                                                                       kd.morton.as<uint64_t>(), kd.order.as<uint32_t>());
     PLS_CHECK_LAUNCH();
     uint64_t* sk;
     uint32_t* sv;
-    radix_sort_pairs(ctx, kd.morton.as<uint64_t>(), kd.order.as<uint32_t>(), M, (3 * KD_COORD_BITS + 7) / 8, &sk, &sv,
-                     kd.cap_points);
-    kd_gather_kernel<<<grid_for(M, 256, 8 * kNumSMs), 256, 0, st>>>(pts, sv, M, kd.sorted.as<float4>(),
-                                                                     kd.inv_order.as<uint32_t>());
+    radix_sort_pairs(ctx, kd.morton.as<uint64_t>(), kd.order.as<uint32_t>(), M, 4, &sk, &sv, kd.cap_points);
+    // table geometry follows the capacity, not M: it only changes when the buffers are re-planned
+    cell_table_bytes(kd.cap_points, kd.table_mask, kd.table_offset);
+    CellTables T;
+    for (int l = 0; l < KD_MAX_LEVELS; ++l) {
+        T.table[l] = reinterpret_cast<uint4*>(reinterpret_cast<char*>(kd.cells.p) + kd.table_offset[l]);
+        T.mask[l] = kd.table_mask[l];
+    }
+    kd_finalize_kernel<<<grid_for(M, 256, 8 * kNumSMs), 256, 0, st>>>(pts, sk, sv, M, T, kd.grid_hdr.as<KdGridHeader>(),
+                                                                       kd.gen, kd.sorted.as<float4>());
     PLS_CHECK_LAUNCH();
-    {   // cell tables: level l gets a power-of-two table of >= 1.5 M / 2^l slots (overflow falls back to the BVH)
-        CellTables T;
-        const size_t off = cell_table_bytes(M, kd.table_mask, kd.table_offset);
-        kd.cells.reserve(off, st);
-        PLS_CUDA(cudaMemsetAsync(kd.cells.p, 0, off, st));
-        for (int l = 0; l < KD_LEVELS; ++l) {
-            T.table[l] = reinterpret_cast<uint4*>(reinterpret_cast<char*>(kd.cells.p) + kd.table_offset[l]);
-            T.mask[l] = kd.table_mask[l];
-        }
-        kd_cells_kernel<<<grid_for(M, 256, 8 * kNumSMs), 256, 0, st>>>(sk, M, T, kd.grid_hdr.as<KdGridHeader>());
-        PLS_CHECK_LAUNCH();
-    }
-    if (M > 1) {
-        int* visit = kd.visit.as<int>();
-        int4* ranges = reinterpret_cast<int4*>(reinterpret_cast<char*>(kd.visit.p) + (((size_t)M * sizeof(int) + 15) / 16) * 16);
-        PLS_CUDA(cudaMemsetAsync(visit, 0, (size_t)M * sizeof(int), st));
-        kd_hierarchy_kernel<<<grid_for(M - 1, 128, 1 << 20), 128, 0, st>>>(sk, (int)M, ranges, kd.parent.as<int>());
-        PLS_CHECK_LAUNCH();
-        kd_boxes_kernel<<<grid_for(2 * M, 128, 1 << 20), 128, 0, st>>>(kd.sorted.as<float4>(), (int)M, ranges,
-                                                                        kd.parent.as<int>(), visit, kd.nodes.as<float4>());
-        PLS_CHECK_LAUNCH();
-    }
 }
 
 }  // namespace
@@ -638,7 +499,8 @@ void kdmap_reset(pls_context* ctx) {
     ctx->kd.indexed = 0;
     ctx->kd.valid = false;
     ctx->kd.bbox_clean = false;
-    ctx->kd.max_frame = 0;   // the buffers (cap_points) are kept: a re-initialised sequence reuses them
+    ctx->kd.max_frame = 0;   // the buffers (cap_points) and the generation counter are kept: a re-initialised
+                             // sequence reuses them
 }
 
 template <typename T>
@@ -772,31 +634,60 @@ void kdmap_update(pls_context* ctx, const float* rel_pose_host, const float* pts
     kdmap_update_packed(ctx, rel_pose_host, ctx->tmp[4].as<float4>(), num_new, has_new);
 }
 
-// One fused ICP iteration over the device-resident queries (float4 in ctx->queries, count in
-// SC_QUERY_COUNT); writes block partials to ctx->partials and returns the block count.
-int kdmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int num_ranks, bool first, float fuse_threshold,
+// Launch geometry of the search kernel: `qpw` queries per warp, chosen so that the grid is about one resident wave.
+static int nn_queries_per_warp(int64_t mine) {
+    static const int forced = getenv("PLS_KD_QPW") ? atoi(getenv("PLS_KD_QPW")) : 0;
+    if (forced >= 1 && forced <= KD_QPW_MAX) return forced;
+    const int64_t resident_warps = (int64_t)kNumSMs * 32;  // 64 registers per thread
+    int qpw = (int)((mine + resident_warps - 1) / resident_warps);
+    return qpw < 1 ? 1 : (qpw > KD_QPW_MAX ? KD_QPW_MAX : qpw);
+}
+
+static void launch_search(pls_context* ctx, const KdIndex& ix, const float4* queries, const uint32_t* nq_dev, int64_t mine,
+                          int rank, int num_ranks, const float* T, const int* done, int* match, bool use_hint, bool normals,
+                          int parity) {
+    cudaStream_t st = ctx->stream;
+    const int qpw = nn_queries_per_warp(mine);
+    const int64_t per_block = (int64_t)KD_WARPS * qpw;
+    const int blocks = (int)((mine + per_block - 1) / per_block);
+    ctx->kd_worklist.reserve((size_t)(mine + 64) * sizeof(int), st);
+    uint32_t* wl_count = scalar_u32(ctx, SC_WL0);
+    kd_nn_warp_kernel<<<blocks, KD_THREADS, 0, st>>>(ix, queries, nq_dev, (int64_t)rank, (int64_t)num_ranks, qpw, T, done, match,
+                                                     use_hint ? 1 : 0, normals ? ctx->kd_worklist.as<int>() : nullptr, wl_count,
+                                                     parity);
+    PLS_CHECK_LAUNCH();
+    if (normals) {
+        // a warp per queued point; with ~one resident wave of warps a frame's first iteration (every match new) gives
+        // each warp a handful of points, later iterations leave most warps without work (they exit at once)
+        int nblocks = (int)((mine + KD_WARPS - 1) / KD_WARPS);
+        if (nblocks > 4 * kNumSMs) nblocks = 4 * kNumSMs;
+        kd_normals_warp_kernel<<<nblocks, KD_THREADS, 0, st>>>(ix, ctx->cfg.num_neighbors_normals, ctx->kd_worklist.as<int>(),
+                                                               wl_count + parity, done);
+        PLS_CHECK_LAUNCH();
+    }
+}
+
+// One ICP iteration over the device-resident queries (float4 in ctx->query_ptr, count in the FrameResult); writes
+// block partials to ctx->partials and returns the block count.
+int kdmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int num_ranks, int it, float fuse_threshold,
                         bool* solved) {
     PLS_REQUIRE(ctx->kd.valid, "kd map: search before any update");
-    *solved = false;
+    cudaStream_t st = ctx->stream;
     const int64_t mine = (query_bound + num_ranks - 1) / num_ranks;
-    const uint32_t* nq_dev = reinterpret_cast<const uint32_t*>(&frame_result_dev(ctx)->counts[1]);
+    FrameResult* fr = frame_result_dev(ctx);
+    const uint32_t* nq_dev = reinterpret_cast<const uint32_t*>(&fr->counts[1]);
     // credited per executed iteration by the caller (the launch is a no-op once ICP converged)
     ProfileScope ps(ctx, 0, 0.0, false);
-    // lanes per query of the split search kernels (0 = the fused thread-per-query kernel)
-    static const int group = getenv("PLS_KD_GROUP") ? atoi(getenv("PLS_KD_GROUP")) : 4;
-    if (group == 2 || group == 4 || group == 8) {
-        *solved = fuse_threshold >= 0.f;
-        if (group == 2) return launch_group_iteration<2>(ctx, make_index(ctx), mine, nq_dev, rank, num_ranks, first, fuse_threshold);
-        if (group == 4) return launch_group_iteration<4>(ctx, make_index(ctx), mine, nq_dev, rank, num_ranks, first, fuse_threshold);
-        return launch_group_iteration<8>(ctx, make_index(ctx), mine, nq_dev, rank, num_ranks, first, fuse_threshold);
-    }
-    if (first) PLS_CUDA(cudaMemsetAsync(ctx->nn_prev.p, 0xff, (size_t)query_bound * sizeof(int), ctx->stream));
-    const int blocks = grid_for(mine, KD_ITER_THREADS, 8 * kNumSMs);
-    ctx->partials.reserve((size_t)blocks * NACC * sizeof(double), ctx->stream);
-    kd_icp_iter_kernel<<<blocks, KD_ITER_THREADS, 0, ctx->stream>>>(
-        make_index(ctx), ctx->cfg.num_neighbors_normals, ctx->query_ptr, nq_dev, (int64_t)rank, (int64_t)num_ranks,
-        frame_result_dev(ctx), ctx->cfg.scheme, ctx->cfg.sigma, ctx->nn_prev.as<int>(), ctx->partials.as<double>());
+    const KdIndex ix = make_index(ctx);
+    launch_search(ctx, ix, ctx->query_ptr, nq_dev, mine, rank, num_ranks, fr->T, &fr->done, ctx->nn_prev.as<int>(), it > 0, true,
+                  it & 1);
+    const int blocks = grid_for(mine, KD_RES_THREADS, 8 * kNumSMs);
+    ctx->partials.reserve((size_t)blocks * NACC * sizeof(double), st);
+    kd_residual_kernel<<<blocks, KD_RES_THREADS, 0, st>>>(ix, ctx->query_ptr, nq_dev, (int64_t)rank, (int64_t)num_ranks, fr,
+                                                          ctx->cfg.scheme, ctx->cfg.sigma, ctx->nn_prev.as<int>(),
+                                                          ctx->partials.as<double>(), fuse_threshold);
     PLS_CHECK_LAUNCH();
+    *solved = fuse_threshold >= 0.f;
     return blocks;
 }
 
@@ -878,8 +769,24 @@ int pls_kdmap_nn_search(pls_context* ctx, const float* queries, int64_t n, float
     OutArg onb = out_arg(ctx, out_neighbors, (size_t)n * 3 * sizeof(float), ctx->stage_out[0]);
     OutArg onr = out_arg(ctx, out_normals, (size_t)n * 3 * sizeof(float), ctx->stage_out[1]);
     OutArg oix = out_arg(ctx, out_idx, (size_t)n * sizeof(int64_t), ctx->stage_out[2]);
-    kd_search_kernel<<<grid_for(n, 128, 8 * kNumSMs), 128, 0, ctx->stream>>>(
-        make_index(ctx), ctx->cfg.num_neighbors_normals, d, n, (float*)onb.dev, (float*)onr.dev, (long long*)oix.dev);
+    // the same warp-cooperative kernels as the ICP loop, with an identity transform and no previous matches
+    cudaStream_t st = ctx->stream;
+    ctx->queries.reserve((size_t)n * sizeof(float4), st);
+    ctx->nn_prev.reserve((size_t)n * sizeof(int), st);
+    ctx->tmp[6].reserve(16 * sizeof(float) + 16, st);
+    static const float eye12[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    PLS_CUDA(cudaMemcpyAsync(ctx->tmp[6].p, eye12, sizeof(eye12), cudaMemcpyHostToDevice, st));
+    uint32_t* nq = scalar_u32(ctx, SC_QUERY_COUNT);
+    const uint32_t nq_host[3] = {(uint32_t)n, 0u, 0u};
+    PLS_CUDA(cudaMemcpyAsync(nq, nq_host, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    PLS_CUDA(cudaMemsetAsync(scalar_u32(ctx, SC_WL0), 0, 2 * sizeof(uint32_t), st));
+    kd_rows_to_float4_kernel<<<grid_for(n, 256, 8 * kNumSMs), 256, 0, st>>>(d, n, ctx->queries.as<float4>());
+    PLS_CHECK_LAUNCH();
+    const KdIndex ix = make_index(ctx);
+    launch_search(ctx, ix, ctx->queries.as<float4>(), nq, n, 0, 1, ctx->tmp[6].as<float>(), nullptr, ctx->nn_prev.as<int>(), false,
+                  out_normals != nullptr, 0);
+    kd_search_export_kernel<<<grid_for(n, 256, 8 * kNumSMs), 256, 0, st>>>(ix, ctx->nn_prev.as<int>(), n, (float*)onb.dev,
+                                                                            (float*)onr.dev, (long long*)oix.dev);
     PLS_CHECK_LAUNCH();
     finish_out(ctx, onb);
     finish_out(ctx, onr);

@@ -1,15 +1,24 @@
-// Exact nearest-neighbour search over the kd local map: a linear BVH (Karras 2012) over the
-// Morton-sorted map points, traversed with a per-thread stack.  Device side only.
+// Exact nearest-neighbour search over the kd local map (replaces the pykdtree queries of
+// slam/odometry/local_map.py:385,405): a pyramid of hashed cell tables over ONE array of map points sorted by
+// the Morton code of their level-0 cell, searched by WHOLE WARPS.  Device side only.
 //
-// Index layout (all in HBM, L2-resident for the BASELINE map sizes):
-//   sorted[M]   float4  map points in Morton order; .w = bit-cast insertion index
-//   nodes[M-1]  64 B    internal node i covers sorted[first..last], split after `gamma`:
-//                       left child = [first..gamma], right child = [gamma+1..last]; the node
-//                       stores BOTH child boxes, so one 64-byte fetch decides both descents.
-//                       Child ids are implicit (Karras): internal(left) = gamma,
-//                       internal(right) = gamma + 1.  Ranges of <= LEAF points are scanned
-//                       linearly (contiguous float4 loads) instead of being descended.
-//   normals[M]  float4  lazily computed unit normal of each map point, .w = 1 once valid
+// Index layout (HBM; L2-resident at the BASELINE map sizes):
+//   sorted[M]   float4  map points ordered by level-0 cell id (insertion order inside a cell); .w = bit-cast
+//                       insertion index
+//   normals[M]  float4  lazily computed unit normal of each map point; .w carries a state word:
+//                       2 gen = claimed (queued for computation), 2 gen + 1 = valid, anything else = stale
+//   table[l]    uint4   open-addressing hash table of level l: {cell id, gen, first, last}.  A level-l cell is the
+//                       Morton prefix id0 >> 3 l (cube of side cell0 * 2^l) and owns a CONTIGUOUS range of `sorted`,
+//                       so one sorted array serves every level.  Entries of older generations count as empty: no
+//                       table is ever cleared.  Level `top` is a single cell holding the whole map.
+//
+// Search.  A warp owns a query.  Lanes 0..26 each probe one cell of the 3x3x3 block around the query (27 independent
+// table loads = one L2 round trip); the candidate ranges are flattened with a warp scan and read 32 at a time, lane t
+// taking candidate t -- consecutive lanes read consecutive float4 of a range, so a round is a handful of full 128-byte
+// lines instead of 32 scattered sectors (the thread-per-cell scans of round 1 spent their time in L1 wavefronts).
+// Every point closer than (cell side - margin) lies inside the block, so a best (or k-th best) distance below that is
+// exact; otherwise the next coarser level is scanned (cells pruned by their box distance), up to the level that holds
+// everything.  No tree, no stack, no divergent descent.
 #pragma once
 #include <cuda_runtime.h>
 #include <float.h>
@@ -17,455 +26,297 @@
 
 namespace pls {
 
-#ifndef PLS_KD_LEAF
-#define PLS_KD_LEAF 8
-#endif
-constexpr int KD_LEAF = PLS_KD_LEAF;  // treelet size: subtrees of <= KD_LEAF points are scanned linearly
-constexpr int KD_STACK = 96;
-constexpr int KD_KMAX = 32;  // k + 1 <= 32
-
-struct BvhNode {
-    float lmin[3], lmax[3], rmin[3], rmax[3];
-    int first, gamma, last, pad;
-};
-static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
-
-__device__ __forceinline__ float dist2_point(float x, float y, float z, const float4& p) {
-    float dx = x - p.x, dy = y - p.y, dz = z - p.z;
-    return dx * dx + dy * dy + dz * dz;
-}
-
-// Multi-level cell tables over the SAME Morton-sorted array: at level l a cell is the key prefix
-// key >> 3 (b0 + l) (cubic cell of side cell0 * 2^l metres) and owns a contiguous range of `sorted`.
-// Open-addressing hash tables (linear probing) map cell id -> [start, end].  A query probes the 27
-// cells around it (independent loads) and scans their ranges (contiguous float4 reads): memory-level
-// parallelism instead of the BVH's dependent node chain.  The result is exact whenever the k-th best
-// squared distance is below (cell - margin)^2, because every point that close lies inside the 27-block;
-// otherwise the next coarser level is tried and finally the BVH.
-constexpr int KD_LEVELS = 1;
-constexpr int KD_COORD_BITS = 13;                      // Morton bits per axis
+constexpr int KD_COORD_BITS = 13;                       // quantisation bits per axis
 constexpr int KD_COORD_MAX = (1 << KD_COORD_BITS) - 1;
+constexpr int KD_MIN_B0 = 3;                            // level-0 cell ids then fit 30 bits (4 radix passes)
+constexpr int KD_MAX_LEVELS = KD_COORD_BITS - KD_MIN_B0 + 1;  // levels 0 .. top, top <= 10
 constexpr float KD_CELL_TARGET = 0.16f;   // default level-0 cell side in [0.16, 0.32) m (PLS_KD_CELL overrides)
 constexpr float KD_CELL_MARGIN = 2e-3f;   // quantisation slack, metres
+constexpr int KD_KMAX = 32;               // k + 1 <= 32
+constexpr unsigned FULL = 0xffffffffu;
 
 struct KdGridHeader {
     float mn[3];
-    float scale;      // Morton units per metre
+    float scale;      // quantisation units per metre
     int b0;           // bits dropped per axis at level 0
     float cell0;      // level-0 cell side, metres
-    int overflow[KD_LEVELS];
+    int top;          // coarsest level = KD_COORD_BITS - b0 (one cell)
+    int overflow[KD_MAX_LEVELS];
 };
 
 struct KdIndex {
     const float4* sorted;
-    const float4* nodes;  // 4 float4 per node
     float4* normals;
     int M;
+    uint32_t gen;                      // generation of this build (tables, normal states)
     const KdGridHeader* grid;
-    const uint4* table[KD_LEVELS];  // {id+1 lo, id+1 hi, start, end}
-    uint32_t mask[KD_LEVELS];
-    unsigned long long* stats;      // optional debug counters (PLS_KD_STATS=1), else null
+    const uint4* table[KD_MAX_LEVELS];
+    uint32_t mask[KD_MAX_LEVELS];
+    unsigned long long* stats;         // optional debug counters (PLS_KD_STATS=1), else null
 };
-// stats slots: 0 nn queries, 1 nn exact@L0, 2 nn exact@L1, 3 nn exact@L2, 4 nn bvh, 5 nn candidates,
-//              6 knn queries, 7 knn exact@L0, 8 @L1, 9 @L2, 10 knn bvh, 11 knn candidates
+// stats slots: 0 nn queries, 1 nn exact at level 0, 2 nn needing coarser levels, 3 nn candidates,
+//              4 knn queries, 5 knn exact at level 0, 6 knn needing coarser levels, 7 knn candidates
 __device__ __forceinline__ void kd_stat(const KdIndex& ix, int slot, unsigned long long v = 1ull) {
     if (ix.stats) atomicAdd(ix.stats + slot, v);
 }
 
-__device__ __forceinline__ uint64_t kd_spread3(uint64_t x) {
-    x &= 0x1fffffull;
-    x = (x | x << 32) & 0x1f00000000ffffull;
-    x = (x | x << 16) & 0x1f0000ff0000ffull;
-    x = (x | x << 8) & 0x100f00f00f00f00full;
-    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
-    x = (x | x << 2) & 0x1249249249249249ull;
+__device__ __forceinline__ uint32_t kd_spread10(uint32_t x) {  // 10 bits -> every third bit
+    x &= 0x3ffu;
+    x = (x | (x << 16)) & 0x030000ffu;
+    x = (x | (x << 8)) & 0x0300f00fu;
+    x = (x | (x << 4)) & 0x030c30c3u;
+    x = (x | (x << 2)) & 0x09249249u;
     return x;
 }
-__device__ __forceinline__ uint32_t kd_hash(uint64_t id) {
-    uint64_t h = id * 0x9E3779B97F4A7C15ull;
-    return (uint32_t)(h >> 32);
+__device__ __forceinline__ uint32_t kd_cell_id(uint32_t cx, uint32_t cy, uint32_t cz) {
+    return kd_spread10(cx) | (kd_spread10(cy) << 1) | (kd_spread10(cz) << 2);
 }
+__device__ __forceinline__ uint32_t kd_hash(uint32_t id) { return (id * 0x9E3779B1u) ^ (id >> 15); }
 
-// Looks up cell `id` at one level; returns false if the cell is empty.
-__device__ __forceinline__ bool kd_cell_lookup(const uint4* __restrict__ table, uint32_t mask, uint64_t id, int& start,
-                                               int& end) {
-    const uint32_t lo = (uint32_t)(id + 1), hi = (uint32_t)((id + 1) >> 32);
-    uint32_t h = kd_hash(id) & mask;
-    for (int probe = 0; probe < 64; ++probe) {
-        const uint4 e = __ldg(table + h);
-        if (e.x == lo && e.y == hi) {
-            start = (int)e.z;
-            end = (int)e.w;
-            return true;
-        }
-        if (e.x == 0u && e.y == 0u) return false;
-        h = (h + 1) & mask;
-    }
-    return false;
-}
-
-// Grid search of one level.  Calls visit(i, d2) for every point of the 27-block; returns the squared
-// exactness radius (cell - margin)^2 of that level, or -1 if the level is unusable.
-// Phase 1 probes the 27 cells (nine independent table loads per z-slab) and records the non-empty ranges;
-// phase 2 walks the lane's ranges in ONE flattened loop, so a warp runs max_lane(sum of counts)
-// iterations instead of sum_cells(max_lane(count)) -- the nested form diverged ~7x.
-template <typename Visit>
-__device__ __forceinline__ float kd_grid_scan(const KdIndex& ix, int level, float x, float y, float z, Visit visit) {
-    const KdGridHeader* g = ix.grid;
-    if (g->overflow[level]) return -1.f;
-    const int b = g->b0 + level;
-    const float fx = (x - g->mn[0]) * g->scale, fy = (y - g->mn[1]) * g->scale, fz = (z - g->mn[2]) * g->scale;
-    // the same truncating quantisation as kd_morton_kernel for in-range points; floor for the rest
-    const int cx = ((int)floorf(fx)) >> b, cy = ((int)floorf(fy)) >> b, cz = ((int)floorf(fz)) >> b;
-    const int cmax = KD_COORD_MAX >> b;
-    const uint4* __restrict__ table = ix.table[level];
-    const uint32_t mask = ix.mask[level];
-    uint64_t sx[3];
-    bool okx[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        const int xx = cx + d - 1;
-        okx[d] = xx >= 0 && xx <= cmax;
-        sx[d] = okx[d] ? kd_spread3((uint64_t)xx) : 0ull;
-    }
-    int rs[27], re[27];
-    int nr = 0;
-#pragma unroll 1
-    for (int dz = -1; dz <= 1; ++dz) {
-        const int zz = cz + dz;
-        if (zz < 0 || zz > cmax) continue;
-        const uint64_t kz = kd_spread3((uint64_t)zz) << 2;
-        uint64_t id[9];
-        uint32_t hh[9];
-        uint4 ent[9];
-        bool ok[9];
-#pragma unroll
-        for (int j = 0; j < 9; ++j) {
-            const int yy = cy + j / 3 - 1;
-            ok[j] = okx[j % 3] && yy >= 0 && yy <= cmax;
-            id[j] = kz | (kd_spread3((uint64_t)(ok[j] ? yy : 0)) << 1) | sx[j % 3];
-            hh[j] = kd_hash(id[j]) & mask;
-        }
-#pragma unroll
-        for (int j = 0; j < 9; ++j) ent[j] = ok[j] ? __ldg(table + hh[j]) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-        for (int j = 0; j < 9; ++j) {
-            if (!ok[j]) continue;
-            const uint32_t lo = (uint32_t)(id[j] + 1), hi = (uint32_t)((id[j] + 1) >> 32);
-            uint4 e = ent[j];
-            bool hit = e.x == lo && e.y == hi;
-            if (!hit && (e.x | e.y) != 0u) {  // collision: keep probing
-                uint32_t h = hh[j];
-                for (int probe = 0; probe < 64 && !hit; ++probe) {
-                    h = (h + 1) & mask;
-                    e = __ldg(table + h);
-                    hit = e.x == lo && e.y == hi;
-                    if ((e.x | e.y) == 0u) break;
-                }
-            }
-            if (hit) {
-                rs[nr] = (int)e.z;
-                re[nr] = (int)e.w;
-                ++nr;
-            }
-        }
-    }
-    // one candidate per iteration and a single visit site: the lanes of a warp stay converged while they have
-    // candidates left (the earlier "advance range / continue" form let them drift out of phase: ncu showed
-    // ~4 active lanes on the visit body)
-    int total = 0;
-    for (int r = 0; r < nr; ++r) total += re[r] - rs[r] + 1;
-    int j = 0, i = 0, end = -1;
-    for (int t = 0; t < total; ++t) {
-        if (i > end) {
-            i = rs[j];
-            end = re[j];
-            ++j;
-        }
-        visit(i, dist2_point(x, y, z, __ldg(ix.sorted + i)));
-        ++i;
-    }
-    const float cell = g->cell0 * (float)(1 << level) - KD_CELL_MARGIN;
-    return cell > 0.f ? cell * cell : -1.f;
-}
-
-__device__ __forceinline__ float dist2_box(float x, float y, float z, float mnx, float mny, float mnz, float mxx,
-                                           float mxy, float mxz) {
-    float dx = fmaxf(fmaxf(mnx - x, x - mxx), 0.f);
-    float dy = fmaxf(fmaxf(mny - y, y - mxy), 0.f);
-    float dz = fmaxf(fmaxf(mnz - z, z - mxz), 0.f);
+__device__ __forceinline__ float dist2_point(float x, float y, float z, const float4& p) {
+    const float dx = x - p.x, dy = y - p.y, dz = z - p.z;
     return dx * dx + dy * dy + dz * dz;
 }
 
-// Exact 1-NN.  `hint` (a sorted position or -1) only seeds the pruning bound.
-__device__ __forceinline__ int kd_nearest(const KdIndex& ix, float x, float y, float z, int hint, float* best_out) {
+// The grid header in registers (warp-uniform values).
+struct KdGridLocal {
+    float mnx, mny, mnz, scale, inv_scale;
+    int b0, top;
+};
+__device__ __forceinline__ KdGridLocal kd_load_grid(const KdIndex& ix) {
+    KdGridLocal g;
+    g.mnx = __ldg(&ix.grid->mn[0]); g.mny = __ldg(&ix.grid->mn[1]); g.mnz = __ldg(&ix.grid->mn[2]);
+    g.scale = __ldg(&ix.grid->scale);
+    g.inv_scale = 1.f / g.scale;
+    g.b0 = __ldg(&ix.grid->b0);
+    g.top = __ldg(&ix.grid->top);
+    return g;
+}
+
+// The cell of the 3x3x3 block (at `level`, around the query) owned by this lane: its point range [start, start+count)
+// or count = 0 (lanes >= 27, cells outside the grid, empty cells, cells whose box is farther than sqrt(prune2)).
+// Returns the squared exactness radius of the block (FLT_MAX at the top level: the block then holds every point).
+// A query outside the grid is clamped to the border cell: all points lie on one side of it along that axis, so the
+// block still holds everything within one cell side.
+__device__ __forceinline__ float warp_probe_block(const KdIndex& ix, const KdGridLocal& g, int level, float x, float y,
+                                                  float z, float prune2, int lane, int& start, int& count) {
+    start = 0;
+    count = 0;
+    const int b = g.b0 + level;
+    const int cmax = KD_COORD_MAX >> b;
+    const float side_u = (float)(1 << b);                      // cell side in quantisation units
+    const float fx = fminf(fmaxf((x - g.mnx) * g.scale, -1.0e6f), 1.0e6f);
+    const float fy = fminf(fmaxf((y - g.mny) * g.scale, -1.0e6f), 1.0e6f);
+    const float fz = fminf(fmaxf((z - g.mnz) * g.scale, -1.0e6f), 1.0e6f);
+    const int cx = min(max(((int)floorf(fx)) >> b, 0), cmax);
+    const int cy = min(max(((int)floorf(fy)) >> b, 0), cmax);
+    const int cz = min(max(((int)floorf(fz)) >> b, 0), cmax);
+    if (lane < 27) {
+        const int dz = lane / 9, rem = lane - dz * 9, dy = rem / 3, dx = rem - dy * 3;
+        const int xx = cx + dx - 1, yy = cy + dy - 1, zz = cz + dz - 1;
+        bool ok = xx >= 0 && xx <= cmax && yy >= 0 && yy <= cmax && zz >= 0 && zz <= cmax && !__ldg(&ix.grid->overflow[level]);
+        if (ok && prune2 < FLT_MAX) {
+            // metres from the query to the cell's box, shrunk by the quantisation slack (conservative)
+            const float lox = ((float)xx * side_u - fx), hix = (fx - (float)(xx + 1) * side_u);
+            const float loy = ((float)yy * side_u - fy), hiy = (fy - (float)(yy + 1) * side_u);
+            const float loz = ((float)zz * side_u - fz), hiz = (fz - (float)(zz + 1) * side_u);
+            const float ax = fmaxf(fmaxf(lox, hix) * g.inv_scale - KD_CELL_MARGIN, 0.f);
+            const float ay = fmaxf(fmaxf(loy, hiy) * g.inv_scale - KD_CELL_MARGIN, 0.f);
+            const float az = fmaxf(fmaxf(loz, hiz) * g.inv_scale - KD_CELL_MARGIN, 0.f);
+            ok = (ax * ax + ay * ay + az * az) <= prune2;
+        }
+        if (ok) {
+            const uint32_t id = kd_cell_id((uint32_t)xx, (uint32_t)yy, (uint32_t)zz) ;
+            const uint4* __restrict__ table = ix.table[level];
+            const uint32_t mask = ix.mask[level];
+            uint32_t h = kd_hash(id) & mask;
+            for (int probe = 0; probe < 64; ++probe) {
+                const uint4 e = __ldg(table + h);
+                if (e.y != ix.gen) break;              // empty (or stale generation): the cell holds no point
+                if (e.x == id) {
+                    start = (int)e.z;
+                    count = (int)e.w - (int)e.z + 1;
+                    break;
+                }
+                h = (h + 1) & mask;
+            }
+        }
+    }
+    if (level >= g.top) return FLT_MAX;
+    if (__ldg(&ix.grid->overflow[level])) return -1.f;  // this level's table was too small: nothing scanned, nothing proven
+    const float cell = side_u * g.inv_scale - KD_CELL_MARGIN;
+    return cell > 0.f ? cell * cell : -1.f;
+}
+
+// Flattened walk over the block's candidates: calls visit(active, d2, index) once per round on every lane
+// (active = this lane holds a candidate), 32 candidates per round, lane t taking the t-th point of the
+// concatenated ranges.  Returns the number of candidates.
+template <typename Visit>
+__device__ __forceinline__ int warp_scan_block(const KdIndex& ix, float x, float y, float z, int start, int count, int lane,
+                                               Visit visit) {
+    int incl = count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    const int adj = start - (incl - count);  // index = adj(owner) + t
+    for (int base = 0; base < total; base += 32) {
+        const int t = base + lane;
+        const bool active = t < total;
+        const int tt = active ? t : total - 1;
+        // owner cell = number of lanes whose inclusive prefix is <= t (prefixes are non-decreasing)
+        int c = 0;
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) {
+            const int v = __shfl_sync(FULL, incl, c + s - 1);
+            if (v <= tt) c += s;
+        }
+        const int idx = __shfl_sync(FULL, adj, c) + tt;
+        const float4 p = __ldg(ix.sorted + idx);
+        visit(active, dist2_point(x, y, z, p), idx);
+    }
+    return total;
+}
+
+// arg-min of (d, i) over the warp (ties: smaller index); the result lands in every lane
+__device__ __forceinline__ void warp_argmin(float& d, int& i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(FULL, d, o);
+        const int oi = __shfl_xor_sync(FULL, i, o);
+        if (od < d || (od == d && (unsigned)oi < (unsigned)i)) {
+            d = od;
+            i = oi;
+        }
+    }
+}
+
+// Exact 1-NN of (x, y, z) by the whole warp; every lane returns the same sorted position (-1 if the map is empty).
+// `hint` (a sorted position or -1, warp-uniform) only seeds the pruning bound.
+__device__ __forceinline__ int warp_nearest(const KdIndex& ix, const KdGridLocal& g, float x, float y, float z, int hint,
+                                            int lane) {
     float best = FLT_MAX;
     int best_i = -1;
     if (hint >= 0 && hint < ix.M) {
         best = dist2_point(x, y, z, __ldg(ix.sorted + hint));
         best_i = hint;
     }
-    if (ix.M <= KD_LEAF) {
-        for (int i = 0; i < ix.M; ++i) {
-            float d = dist2_point(x, y, z, __ldg(ix.sorted + i));
-            if (d < best) { best = d; best_i = i; }
+    if (lane == 0) kd_stat(ix, 0);
+    for (int level = 0; level <= g.top; ++level) {
+        int start, count;
+        const float r2 = warp_probe_block(ix, g, level, x, y, z, best, lane, start, count);
+        const int cand = warp_scan_block(ix, x, y, z, start, count, lane, [&](bool active, float d, int i) {
+            if (active && (d < best || (d == best && (unsigned)i < (unsigned)best_i))) {
+                best = d;
+                best_i = i;
+            }
+        });
+        warp_argmin(best, best_i);
+        if (ix.stats && lane == 0) {
+            kd_stat(ix, 3, (unsigned long long)cand);
+            if (level == 0) kd_stat(ix, (best_i >= 0 && best <= r2) ? 1 : 2);
         }
-        if (best_out) *best_out = best;
-        return best_i;
+        if (best_i >= 0 && best <= r2) break;
     }
-    int stack_n[KD_STACK];
-    float stack_d[KD_STACK];
-    int sp = 0;
-    int node = 0;
-    while (true) {
-        const float4 a = __ldg(ix.nodes + 4 * (size_t)node);
-        const float4 b = __ldg(ix.nodes + 4 * (size_t)node + 1);
-        const float4 c = __ldg(ix.nodes + 4 * (size_t)node + 2);
-        const float4 dd = __ldg(ix.nodes + 4 * (size_t)node + 3);
-        const int first = __float_as_int(dd.x), gamma = __float_as_int(dd.y), last = __float_as_int(dd.z);
-        float dl = dist2_box(x, y, z, a.x, a.y, a.z, a.w, b.x, b.y);
-        float dr = dist2_box(x, y, z, b.z, b.w, c.x, c.y, c.z, c.w);
-        const bool lleaf = (gamma - first + 1) <= KD_LEAF;
-        const bool rleaf = (last - gamma) <= KD_LEAF;
-        if (lleaf && dl < best) {
-            for (int i = first; i <= gamma; ++i) {
-                float d = dist2_point(x, y, z, __ldg(ix.sorted + i));
-                if (d < best) { best = d; best_i = i; }
-            }
-        }
-        if (rleaf && dr < best) {
-            for (int i = gamma + 1; i <= last; ++i) {
-                float d = dist2_point(x, y, z, __ldg(ix.sorted + i));
-                if (d < best) { best = d; best_i = i; }
-            }
-        }
-        const bool cl = !lleaf && dl < best;
-        const bool cr = !rleaf && dr < best;
-        if (cl && cr) {
-            if (dl <= dr) {
-                if (sp < KD_STACK) { stack_n[sp] = gamma + 1; stack_d[sp] = dr; ++sp; }
-                node = gamma;
-            } else {
-                if (sp < KD_STACK) { stack_n[sp] = gamma; stack_d[sp] = dl; ++sp; }
-                node = gamma + 1;
-            }
-            continue;
-        }
-        if (cl) { node = gamma; continue; }
-        if (cr) { node = gamma + 1; continue; }
-        // pop
-        bool found = false;
-        while (sp > 0) {
-            --sp;
-            if (stack_d[sp] < best) { node = stack_n[sp]; found = true; break; }
-        }
-        if (!found) break;
-    }
-    if (best_out) *best_out = best;
     return best_i;
 }
 
-// Exact 1-NN, grid first: levels 0..KD_LEVELS-1, then the BVH seeded with the best candidate so far.
-__device__ __forceinline__ int kd_nearest_fast(const KdIndex& ix, float x, float y, float z, int hint, int* used_bvh) {
-    float best = FLT_MAX;
-    int best_i = -1;
-    if (hint >= 0 && hint < ix.M) {
-        best = dist2_point(x, y, z, __ldg(ix.sorted + hint));
-        best_i = hint;
-    }
-    kd_stat(ix, 0);
-    if (ix.M > KD_LEAF) {
-        for (int level = 0; level < KD_LEVELS; ++level) {
-            int cand = 0;
-            const float r2 = kd_grid_scan(ix, level, x, y, z, [&](int i, float d) {
-                ++cand;
-                if (d < best) { best = d; best_i = i; }
-            });
-            kd_stat(ix, 5, cand);
-            if (r2 > 0.f && best <= r2) { kd_stat(ix, 1 + level); return best_i; }
-        }
-    }
-    kd_stat(ix, 4);
-    if (used_bvh) *used_bvh = 1;
-    return kd_nearest(ix, x, y, z, best_i, nullptr);
-}
-
-// Sorted insertion into an ascending (d, i) list of capacity k.
-__device__ __forceinline__ void knn_insert(float* d, int* idx, int k, int& count, float dn, int in) {
-    if (count == k && dn >= d[k - 1]) return;
-    int pos = count < k ? count : k - 1;
-    while (pos > 0 && d[pos - 1] > dn) {
-        d[pos] = d[pos - 1];
-        idx[pos] = idx[pos - 1];
-        --pos;
-    }
-    d[pos] = dn;
-    idx[pos] = in;
-    if (count < k) ++count;
-}
-
-// Exact k-NN (k <= KD_KMAX): fills d[]/idx[] ascending, returns the number found (min(k, M)).
-// `count` entries of d[]/idx[] may already hold candidates (seeds): they bound the search from the start.
-__device__ __forceinline__ int kd_knn(const KdIndex& ix, float x, float y, float z, int k, float* d, int* idx,
-                                      int count = 0) {
-    if (ix.M <= KD_LEAF) {
-        for (int i = 0; i < ix.M; ++i) knn_insert(d, idx, k, count, dist2_point(x, y, z, __ldg(ix.sorted + i)), i);
-        return count;
-    }
-    int stack_n[KD_STACK];
-    float stack_d[KD_STACK];
-    int sp = 0;
-    int node = 0;
-    while (true) {
-        const float4 a = __ldg(ix.nodes + 4 * (size_t)node);
-        const float4 b = __ldg(ix.nodes + 4 * (size_t)node + 1);
-        const float4 c = __ldg(ix.nodes + 4 * (size_t)node + 2);
-        const float4 dd = __ldg(ix.nodes + 4 * (size_t)node + 3);
-        const int first = __float_as_int(dd.x), gamma = __float_as_int(dd.y), last = __float_as_int(dd.z);
-        float dl = dist2_box(x, y, z, a.x, a.y, a.z, a.w, b.x, b.y);
-        float dr = dist2_box(x, y, z, b.z, b.w, c.x, c.y, c.z, c.w);
-        const bool lleaf = (gamma - first + 1) <= KD_LEAF;
-        const bool rleaf = (last - gamma) <= KD_LEAF;
-        float worst = count < k ? FLT_MAX : d[k - 1];
-        if (lleaf && dl < worst) {
-            for (int i = first; i <= gamma; ++i)
-                knn_insert(d, idx, k, count, dist2_point(x, y, z, __ldg(ix.sorted + i)), i);
-            worst = count < k ? FLT_MAX : d[k - 1];
-        }
-        if (rleaf && dr < worst) {
-            for (int i = gamma + 1; i <= last; ++i)
-                knn_insert(d, idx, k, count, dist2_point(x, y, z, __ldg(ix.sorted + i)), i);
-            worst = count < k ? FLT_MAX : d[k - 1];
-        }
-        const bool cl = !lleaf && dl < worst;
-        const bool cr = !rleaf && dr < worst;
-        if (cl && cr) {
-            if (dl <= dr) {
-                if (sp < KD_STACK) { stack_n[sp] = gamma + 1; stack_d[sp] = dr; ++sp; }
-                node = gamma;
-            } else {
-                if (sp < KD_STACK) { stack_n[sp] = gamma; stack_d[sp] = dl; ++sp; }
-                node = gamma + 1;
-            }
-            continue;
-        }
-        if (cl) { node = gamma; continue; }
-        if (cr) { node = gamma + 1; continue; }
-        bool found = false;
-        while (sp > 0) {
-            --sp;
-            float w2 = count < k ? FLT_MAX : d[k - 1];
-            if (stack_d[sp] < w2) { node = stack_n[sp]; found = true; break; }
-        }
-        if (!found) break;
-    }
-    return count;
-}
-
-// Register-resident ascending list of the K best (distance, index) pairs: fully unrolled, branch-free
-// bubble insertion -- no local memory, no per-lane loops (the local-memory insertion sort ran with ~2.5
-// active lanes per instruction and dominated the first version of the correspondence kernel).
-template <int K>
-struct KBest {
-    float d[K];
-    int i[K];
-    __device__ __forceinline__ void reset() {
+// Exact K-NN (K <= 32, warp-uniform) of (x, y, z): on return lane r < found holds the r-th nearest point
+// (out_d, out_i), ascending by (distance, index); returns the number found (min(K, M)).
+//
+// Selection.  The candidates of a block are taken in chunks of 32 * R (R register slots per lane); K rounds of
+// {lane-local minimum, warp arg-min, the winner retires its slot} extract the K smallest of the chunk plus the K kept
+// from the previous chunk (re-entered through one carry slot per lane).  A 27-cell block of the BASELINE maps holds
+// 100-200 points: one chunk.
+constexpr int KD_KNN_SLOTS = 8;
+__device__ __forceinline__ int warp_knn(const KdIndex& ix, const KdGridLocal& g, float x, float y, float z, int K, int lane,
+                                        float& out_d, int& out_i) {
+    constexpr int R = KD_KNN_SLOTS;
+    float keep_d = FLT_MAX;   // lane r: r-th best so far (carry between chunks / the result)
+    int keep_i = -1;
+    int found = 0;
+    if (lane == 0) kd_stat(ix, 4);
+    float bound = FLT_MAX;    // K-th distance of the previous (finer) level: an upper bound for this one
+    for (int level = 0; level <= g.top; ++level) {
+        int start, count;
+        const float r2 = warp_probe_block(ix, g, level, x, y, z, bound, lane, start, count);
+        // flatten the ranges (as warp_scan_block, but chunked into register slots)
+        int incl = count;
 #pragma unroll
-        for (int j = 0; j < K; ++j) { d[j] = FLT_MAX; i[j] = -1; }
-    }
-    __device__ __forceinline__ bool full() const { return i[K - 1] >= 0; }
-    __device__ __forceinline__ void bubble() {
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(FULL, incl, 31);
+        const int adj = start - (incl - count);
+        if (ix.stats && lane == 0) kd_stat(ix, 7, (unsigned long long)total);
+        keep_d = FLT_MAX;     // this level's block is a superset of the previous one: select afresh
+        keep_i = -1;
+        for (int chunk = 0; chunk < total || chunk == 0; chunk += 32 * R) {
+            float sd[R + 1];
+            int si[R + 1];
 #pragma unroll
-        for (int j = K - 1; j > 0; --j) {
-            const bool sw = d[j] < d[j - 1];
-            const float td = sw ? d[j - 1] : d[j];
-            const int ti = sw ? i[j - 1] : i[j];
-            d[j - 1] = sw ? d[j] : d[j - 1];
-            i[j - 1] = sw ? i[j] : i[j - 1];
-            d[j] = td;
-            i[j] = ti;
-        }
-    }
-    // strict: a candidate equal to the current K-th distance does not displace it
-    __device__ __forceinline__ void insert(float dn, int in) {
-        if (dn < d[K - 1]) {
-            d[K - 1] = dn;
-            i[K - 1] = in;
-            bubble();
-        }
-    }
-    // the same result without a branch: for scans where nearly every candidate enters the list (a divergent
-    // insert ran with ~4 of 32 lanes active and was 37 % of the normals kernel's instructions)
-    __device__ __forceinline__ void insert_uniform(float dn, int in) {
-        const bool take = dn < d[K - 1];
-        d[K - 1] = take ? dn : d[K - 1];
-        i[K - 1] = take ? in : i[K - 1];
-        bubble();
-    }
-};
-
-// Exact K-NN over the BVH into a fresh list, pruned from the start by `bound2` (an upper bound of the
-// K-th squared distance, inclusive; FLT_MAX if none).  Every point is visited at most once.
-template <int K>
-__device__ __forceinline__ void kd_knn_bounded(const KdIndex& ix, float x, float y, float z, float bound2, KBest<K>& L) {
-    L.reset();
-    if (ix.M <= KD_LEAF) {
-        for (int i = 0; i < ix.M; ++i) L.insert(dist2_point(x, y, z, __ldg(ix.sorted + i)), i);
-        return;
-    }
-    // until the list is full, the bound (nudged up one ulp so that equality passes the strict tests) prunes
-    const float open_bound = bound2 < FLT_MAX ? __int_as_float(__float_as_int(bound2) + 1) : FLT_MAX;
-    int stack_n[KD_STACK];
-    float stack_d[KD_STACK];
-    int sp = 0;
-    int node = 0;
-    while (true) {
-        const float4 a = __ldg(ix.nodes + 4 * (size_t)node);
-        const float4 b = __ldg(ix.nodes + 4 * (size_t)node + 1);
-        const float4 c = __ldg(ix.nodes + 4 * (size_t)node + 2);
-        const float4 dd = __ldg(ix.nodes + 4 * (size_t)node + 3);
-        const int first = __float_as_int(dd.x), gamma = __float_as_int(dd.y), last = __float_as_int(dd.z);
-        const float dl = dist2_box(x, y, z, a.x, a.y, a.z, a.w, b.x, b.y);
-        const float dr = dist2_box(x, y, z, b.z, b.w, c.x, c.y, c.z, c.w);
-        const bool lleaf = (gamma - first + 1) <= KD_LEAF;
-        const bool rleaf = (last - gamma) <= KD_LEAF;
-        float worst = L.full() ? L.d[K - 1] : open_bound;
-        if (lleaf && dl < worst) {
-            for (int i = first; i <= gamma; ++i) {
-                const float dp = dist2_point(x, y, z, __ldg(ix.sorted + i));
-                if (dp < open_bound) L.insert(dp, i);
+            for (int s = 0; s < R; ++s) {
+                const int t = chunk + s * 32 + lane;
+                const bool active = t < total;
+                const int tt = active ? t : (total > 0 ? total - 1 : 0);
+                int c = 0;
+#pragma unroll
+                for (int st = 16; st >= 1; st >>= 1) {
+                    const int v = __shfl_sync(FULL, incl, c + st - 1);
+                    if (v <= tt) c += st;
+                }
+                const int idx = __shfl_sync(FULL, adj, c) + tt;
+                float d = FLT_MAX;
+                if (active) d = dist2_point(x, y, z, __ldg(ix.sorted + idx));
+                sd[s] = d;
+                si[s] = active ? idx : -1;
             }
-            worst = L.full() ? L.d[K - 1] : open_bound;
-        }
-        if (rleaf && dr < worst) {
-            for (int i = gamma + 1; i <= last; ++i) {
-                const float dp = dist2_point(x, y, z, __ldg(ix.sorted + i));
-                if (dp < open_bound) L.insert(dp, i);
+            sd[R] = keep_d;   // the K kept so far compete again
+            si[R] = keep_i;
+            float nd = FLT_MAX;
+            int ni = -1;
+            for (int r = 0; r < K; ++r) {
+                float ld = sd[0];
+                int li = si[0];
+#pragma unroll
+                for (int s = 1; s <= R; ++s) {
+                    const bool lt = sd[s] < ld || (sd[s] == ld && (unsigned)si[s] < (unsigned)li);
+                    ld = lt ? sd[s] : ld;
+                    li = lt ? si[s] : li;
+                }
+                float wd = ld;
+                int wi = li;
+                warp_argmin(wd, wi);
+                if (wi < 0) break;  // nothing left
+                if (li == wi) {     // indices are unique: exactly one lane retires its slot
+#pragma unroll
+                    for (int s = 0; s <= R; ++s) {
+                        const bool hit = si[s] == wi;
+                        sd[s] = hit ? FLT_MAX : sd[s];
+                        si[s] = hit ? -1 : si[s];
+                    }
+                }
+                if (lane == r) {
+                    nd = wd;
+                    ni = wi;
+                }
             }
-            worst = L.full() ? L.d[K - 1] : open_bound;
+            keep_d = nd;
+            keep_i = ni;
         }
-        const bool cl = !lleaf && dl < worst;
-        const bool cr = !rleaf && dr < worst;
-        if (cl && cr) {
-            if (dl <= dr) {
-                if (sp < KD_STACK) { stack_n[sp] = gamma + 1; stack_d[sp] = dr; ++sp; }
-                node = gamma;
-            } else {
-                if (sp < KD_STACK) { stack_n[sp] = gamma; stack_d[sp] = dl; ++sp; }
-                node = gamma + 1;
-            }
-            continue;
-        }
-        if (cl) { node = gamma; continue; }
-        if (cr) { node = gamma + 1; continue; }
-        bool found = false;
-        while (sp > 0) {
-            --sp;
-            const float w2 = L.full() ? L.d[K - 1] : open_bound;
-            if (stack_d[sp] < w2) { node = stack_n[sp]; found = true; break; }
-        }
-        if (!found) break;
+        found = __popc(__ballot_sync(FULL, keep_i >= 0));
+        const float kth = __shfl_sync(FULL, keep_d, K - 1);
+        const bool exact = (found == K && kth <= r2) || level >= g.top;
+        if (ix.stats && lane == 0 && level == 0) kd_stat(ix, exact ? 5 : 6);
+        if (exact) break;
+        if (found == K) bound = kth;
     }
+    out_d = keep_d;
+    out_i = keep_i;
+    return found;
 }
 
 // Eigenvector of the smallest eigenvalue of a symmetric 3x3 matrix (cyclic Jacobi, fp64).
@@ -515,90 +366,36 @@ __device__ __forceinline__ void smallest_eigenvector(const float* c /*xx,xy,xz,y
     n[2] = (float)(nz * inv);
 }
 
-// Second moments about the point itself of its k nearest OTHER map points (entry 0 of the (k+1)-NN list is
-// the point itself), float32 sequential sums in ascending-distance order, then the smallest-eigenvalue
-// direction (slam/odometry/local_map.py:397-422).
-template <typename GetIdx>
-__device__ __forceinline__ void kd_normal_from_neighbours(const KdIndex& ix, const float4& c, int k, int found,
-                                                          GetIdx get_idx, float* n) {
+// Second moments about map point c of its k nearest OTHER map points (entry 0 of the (k+1)-NN list is the point
+// itself): float32 sums taken sequentially in ascending-distance order and divided by k, as numpy's
+// `.mean(axis=1)` forms them (slam/odometry/local_map.py:411-413).  Lane j holds neighbour j (nb_i); every lane
+// returns the same six moments.
+__device__ __forceinline__ void warp_second_moments(const KdIndex& ix, const float4& c, int k, int found, int nb_i, int lane,
+                                                    float* cov) {
+    float dx = 0.f, dy = 0.f, dz = 0.f;
+    if (lane >= 1 && lane < found) {
+        const float4 q = __ldg(ix.sorted + nb_i);
+        dx = __fsub_rn(q.x, c.x);
+        dy = __fsub_rn(q.y, c.y);
+        dz = __fsub_rn(q.z, c.z);
+    }
     float sxx = 0.f, sxy = 0.f, sxz = 0.f, syy = 0.f, syz = 0.f, szz = 0.f;
     for (int j = 1; j < found; ++j) {
-        const float4 q = __ldg(ix.sorted + get_idx(j));
-        float dx = __fsub_rn(q.x, c.x), dy = __fsub_rn(q.y, c.y), dz = __fsub_rn(q.z, c.z);
-        sxx = __fadd_rn(sxx, __fmul_rn(dx, dx));
-        sxy = __fadd_rn(sxy, __fmul_rn(dx, dy));
-        sxz = __fadd_rn(sxz, __fmul_rn(dx, dz));
-        syy = __fadd_rn(syy, __fmul_rn(dy, dy));
-        syz = __fadd_rn(syz, __fmul_rn(dy, dz));
-        szz = __fadd_rn(szz, __fmul_rn(dz, dz));
+        const float bx = __shfl_sync(FULL, dx, j), by = __shfl_sync(FULL, dy, j), bz = __shfl_sync(FULL, dz, j);
+        sxx = __fadd_rn(sxx, __fmul_rn(bx, bx));
+        sxy = __fadd_rn(sxy, __fmul_rn(bx, by));
+        sxz = __fadd_rn(sxz, __fmul_rn(bx, bz));
+        syy = __fadd_rn(syy, __fmul_rn(by, by));
+        syz = __fadd_rn(syz, __fmul_rn(by, bz));
+        szz = __fadd_rn(szz, __fmul_rn(bz, bz));
     }
     const float kk = (float)k;
-    float cov[6] = {__fdiv_rn(sxx, kk), __fdiv_rn(sxy, kk), __fdiv_rn(sxz, kk),
-                    __fdiv_rn(syy, kk), __fdiv_rn(syz, kk), __fdiv_rn(szz, kk)};
-    smallest_eigenvector(cov, n);
+    cov[0] = __fdiv_rn(sxx, kk); cov[1] = __fdiv_rn(sxy, kk); cov[2] = __fdiv_rn(sxz, kk);
+    cov[3] = __fdiv_rn(syy, kk); cov[4] = __fdiv_rn(syz, kk); cov[5] = __fdiv_rn(szz, kk);
 }
 
-// Fast path for the default k = 10: grid block into a register list; if that is not provably exact, a fresh
-// BVH pass bounded by the grid's K-th distance.
-__device__ __forceinline__ void kd_point_normal_k10(const KdIndex& ix, int pos, float* n) {
-    constexpr int K = 11;
-    const float4 c = __ldg(ix.sorted + pos);
-    KBest<K> L;
-    L.reset();
-    bool exact = false;
-    kd_stat(ix, 6);
-    if (ix.M > KD_LEAF) {
-        const float r2 = kd_grid_scan(ix, 0, c.x, c.y, c.z, [&](int i, float dd) { L.insert_uniform(dd, i); });
-        exact = r2 > 0.f && L.full() && L.d[K - 1] <= r2;
-        if (exact) kd_stat(ix, 7);
-    }
-    if (!exact) {
-        kd_stat(ix, 10);
-        float bound = L.full() ? L.d[K - 1] : FLT_MAX;
-        if (!L.full() && ix.M >= K) {
-            // fewer than K points in the whole block (a sparse region): the farthest of K consecutive points
-            // in Morton order bounds the K-NN radius, so the BVH walk below starts pruned
-            const int lo = min(max(pos - K / 2, 0), ix.M - K);
-            float far = 0.f;
-            for (int i = lo; i < lo + K; ++i) far = fmaxf(far, dist2_point(c.x, c.y, c.z, __ldg(ix.sorted + i)));
-            bound = far;
-        }
-        kd_knn_bounded<K>(ix, c.x, c.y, c.z, bound, L);
-    }
-    int found = 0;
-#pragma unroll
-    for (int j = 0; j < K; ++j) found += (L.i[j] >= 0) ? 1 : 0;
-    // copy the indices out through a small switch-free accessor (keeps the list in registers)
-    int idx[K];
-#pragma unroll
-    for (int j = 0; j < K; ++j) idx[j] = L.i[j];
-    kd_normal_from_neighbours(ix, c, 10, found, [&](int j) { return idx[j]; }, n);
-}
-
-// Generic k (3..31): local-memory list over the BVH.
-__device__ __forceinline__ void kd_point_normal(const KdIndex& ix, int pos, int k, float* n) {
-    if (k == 10) {
-        kd_point_normal_k10(ix, pos, n);
-        return;
-    }
-    const float4 c = __ldg(ix.sorted + pos);
-    float d[KD_KMAX];
-    int idx[KD_KMAX];
-    const int found = kd_knn(ix, c.x, c.y, c.z, k + 1, d, idx);
-    kd_normal_from_neighbours(ix, c, k, found, [&](int j) { return idx[j]; }, n);
-}
-
-// Cached normal of map point `pos`; computes and publishes it on first use.  The 16-byte
-// store carries normal and valid flag together, so a concurrent reader sees either the old
-// (flag 0) or the complete new value; concurrent writers store identical bits.
-__device__ __forceinline__ void kd_cached_normal(const KdIndex& ix, int pos, int k, float* n) {
-    float4 v = __ldcg(ix.normals + pos);
-    if (v.w == 0.f) {
-        kd_point_normal(ix, pos, k, n);
-        __stcg(ix.normals + pos, make_float4(n[0], n[1], n[2], 1.f));
-    } else {
-        n[0] = v.x; n[1] = v.y; n[2] = v.z;
-    }
-}
+// State words of the normal cache.
+__device__ __forceinline__ uint32_t kd_normal_claimed(uint32_t gen) { return 2u * gen; }
+__device__ __forceinline__ uint32_t kd_normal_valid(uint32_t gen) { return 2u * gen + 1u; }
 
 }  // namespace pls

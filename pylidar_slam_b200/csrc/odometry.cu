@@ -24,8 +24,10 @@ unsigned long long comm_p2p_next_seq(pls_context* ctx);
 
 namespace {
 
-__global__ void frame_begin_kernel(FrameResult* fr, const float* T0 /*16, device or null*/, int max_iters) {
+__global__ void frame_begin_kernel(FrameResult* fr, const float* T0 /*16, device or null*/, int max_iters,
+                                   uint32_t* worklist_counts /*2*/) {
     int t = threadIdx.x;
+    if (t < 2) worklist_counts[t] = 0;
     if (t < 16) fr->T[t] = T0 ? T0[t] : ((t % 5 == 0) ? 1.f : 0.f);
     if (t < 6) fr->params[t] = 0.f;
     if (t < kMaxAlign) fr->losses[t] = __int_as_float(0x7fc00000);
@@ -170,7 +172,7 @@ int enqueue_icp_iterations(pls_context* ctx, int64_t query_bound, int first, int
         int blocks;
         bool solved = false;  // the kd kernels finish the iteration themselves on a single GPU
         if (ctx->cfg.local_map_type == PLS_MAP_KDTREE)
-            blocks = kdmap_icp_iteration(ctx, query_bound, rank, size, it == 0, size == 1 ? ctx->cfg.threshold_delta_pose : -1.f, &solved);
+            blocks = kdmap_icp_iteration(ctx, query_bound, rank, size, it, size == 1 ? ctx->cfg.threshold_delta_pose : -1.f, &solved);
         else blocks = projmap_icp_iteration(ctx, query_bound, rank, size);
         last_blocks = blocks;
         if (solved) continue;
@@ -200,7 +202,7 @@ int enqueue_icp_iterations(pls_context* ctx, int64_t query_bound, int first, int
 int run_icp(pls_context* ctx, const float* T0_dev, int64_t query_bound) {
     cudaStream_t st = ctx->stream;
     FrameResult* fr = frame_result_dev(ctx);
-    frame_begin_kernel<<<1, kMaxAlign, 0, st>>>(fr, T0_dev, ctx->cfg.max_num_alignments);
+    frame_begin_kernel<<<1, kMaxAlign, 0, st>>>(fr, T0_dev, ctx->cfg.max_num_alignments, scalar_u32(ctx, SC_WL0));
     PLS_CHECK_LAUNCH();
     if (query_bound < 1) query_bound = 1;
     ctx->pm.zbuf_clean = false;  // tmp[3] may have been used by the frame's own projection

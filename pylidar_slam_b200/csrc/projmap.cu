@@ -802,7 +802,7 @@ int pls_projmap_nn_search(pls_context* ctx, const float* queries, int64_t n, flo
     const float* d = (const float*)to_device(ctx, queries, (size_t)n * 3 * sizeof(float), ctx->stage_in[0]);
     // queries as float4 (no NaN filtering here: the reference passes them through unchanged)
     ctx->queries.reserve((size_t)n * sizeof(float4), st);
-    uint32_t* cnt = scalar_u32(ctx, SC_TMP0);
+    uint32_t* cnt = scalar_u32(ctx, SC_NAN_COUNT);
     pack_valid_rows(ctx, d, n, ctx->queries.as<float4>(), cnt);
     ctx->tmp[3].reserve((size_t)hw * sizeof(unsigned long long), st);
     unsigned long long* zbuf = ctx->tmp[3].as<unsigned long long>();
