@@ -117,8 +117,8 @@ __global__ void kd_pack_pixels_kernel(const float* __restrict__ vmap, int64_t hw
 }
 
 // Quantisation of the map: 256 units per metre (3.9 mm) when the map extent allows it (<= 32 m), else the
-// KD_COORD_BITS-bit range is stretched over the extent.  Level-0 cells are 2^b0 units with a side in
-// [cell_target, 2 cell_target) -- but never fewer than KD_MIN_B0 bits are dropped, so that a level-0 cell id
+// KD_COORD_BITS-bit range is stretched over the extent.  Level-0 cells are 2^b0 units, the power of two nearest
+// the target side -- but never fewer than KD_MIN_B0 bits are dropped, so that a level-0 cell id
 // (13 - b0 bits per axis, Morton-interleaved) fits 30 bits and the sort needs four 8-bit passes whatever the extent
 // (maps wider than ~160 m simply get coarser cells).
 __global__ void kd_grid_header_kernel(int* __restrict__ bbox, KdGridHeader* __restrict__ hdr, float cell_target) {
@@ -128,8 +128,9 @@ __global__ void kd_grid_header_kernel(int* __restrict__ bbox, KdGridHeader* __re
                 ez = ordered_to_float(bbox[5]) - mnz;
     const float ext = fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-6f));
     const float scale = fminf(256.0f, (float)KD_COORD_MAX / ext);
+    // the power of two nearest (in ratio) to the target side: cell0 in [target / sqrt 2, target * sqrt 2)
     int b0 = KD_MIN_B0;
-    while (b0 < 12 && (float)(1 << b0) < cell_target * scale) ++b0;
+    while (b0 < 12 && (float)(1 << b0) * 1.41421356f < cell_target * scale) ++b0;
     hdr->mn[0] = mnx; hdr->mn[1] = mny; hdr->mn[2] = mnz;
     hdr->scale = scale;
     hdr->b0 = b0;
@@ -239,17 +240,23 @@ constexpr int KD_THREADS = 256;
 constexpr int KD_WARPS = KD_THREADS / 32;
 constexpr int KD_QPW_MAX = 8;   // queries per warp of the search kernel (bounds the block's claim list)
 
+// counters of the search kernels (u64, behind the u32 scalar slots): candidates tested by the 1-NN searches, by the
+// k-NN searches, normals computed -- the inputs of SURVEY 8d's algorithmic-bytes formulas
+enum { KDC_NN_CAND = 0, KDC_KNN_CAND = 1, KDC_NORMALS = 2 };
+
 __global__ void __launch_bounds__(KD_THREADS)
 kd_nn_warp_kernel(KdIndex ix, const float4* __restrict__ queries, const uint32_t* __restrict__ nq_dev, int64_t q_begin,
                   int64_t q_stride, int qpw, const float* __restrict__ T, const int* __restrict__ done,
-                  int* __restrict__ match, int use_hint, int* __restrict__ worklist, uint32_t* wl_count, int parity) {
+                  int* __restrict__ match, int use_hint, int* __restrict__ worklist, uint32_t* wl_count, int parity,
+                  unsigned long long* __restrict__ counters) {
     if (done && *done) return;
     __shared__ float sT[12];
     __shared__ int s_list[KD_WARPS * KD_QPW_MAX];
-    __shared__ int s_n, s_base;
+    __shared__ int s_n, s_base, s_cand;
     if (threadIdx.x < 12) sT[threadIdx.x] = T[threadIdx.x];
     if (threadIdx.x == 0) {
         s_n = 0;
+        s_cand = 0;
         if (blockIdx.x == 0) wl_count[parity ^ 1] = 0;  // the other slot: consumed by the previous iteration, used by the next
     }
     __syncthreads();
@@ -257,37 +264,57 @@ kd_nn_warp_kernel(KdIndex ix, const float4* __restrict__ queries, const uint32_t
     const KdGridLocal g = kd_load_grid(ix);
     const int64_t nq = (int64_t)*nq_dev;
     const int64_t total_warps = (int64_t)gridDim.x * KD_WARPS;
-    const uint32_t claimed = kd_normal_claimed(ix.gen), valid = kd_normal_valid(ix.gen);
-    for (int k = 0; k < qpw; ++k) {
-        const int64_t s = (int64_t)blockIdx.x * KD_WARPS + warp + (int64_t)k * total_warps;
-        const int64_t qi = q_begin + s * q_stride;
-        if (qi >= nq) break;
-        const float4 p0 = queries[qi];
+    const int64_t s0 = (int64_t)blockIdx.x * KD_WARPS + warp;
+    int my_pos = -1;  // lane k: the match of this warp's k-th query (claims are made by all lanes at once, afterwards)
+    int cand = 0;
+    int64_t qi = q_begin + s0 * q_stride;
+    float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    int hint = -1;
+    if (qi < nq) {
+        p0 = queries[qi];
+        if (use_hint) hint = match[qi];
+    }
+    for (int k = 0; k < qpw && qi < nq; ++k) {
+        // the next query's data is fetched while this one is searched
+        const int64_t qn = q_begin + (s0 + (int64_t)(k + 1) * total_warps) * q_stride;
+        float4 pn = p0;
+        int hn = -1;
+        if (k + 1 < qpw && qn < nq) {
+            pn = queries[qn];
+            if (use_hint) hn = match[qn];
+        }
         const float px = p0.x * sT[0] + p0.y * sT[1] + p0.z * sT[2] + sT[3];
         const float py = p0.x * sT[4] + p0.y * sT[5] + p0.z * sT[6] + sT[7];
         const float pz = p0.x * sT[8] + p0.y * sT[9] + p0.z * sT[10] + sT[11];
-        const int hint = use_hint ? match[qi] : -1;
-        const int pos = warp_nearest(ix, g, px, py, pz, hint, lane);
-        if (lane == 0) {
-            match[qi] = pos;
-            if (pos >= 0 && worklist) {
-                uint32_t* w = reinterpret_cast<uint32_t*>(&ix.normals[pos].w);
-                const uint32_t cur = __ldcg(w);
-                if (cur != valid && cur != claimed && atomicCAS(w, cur, claimed) == cur) s_list[atomicAdd(&s_n, 1)] = pos;
-            }
-        }
+        const int pos = warp_nearest(ix, g, px, py, pz, hint, lane, &cand);
+        if (lane == 0) match[qi] = pos;
+        if (lane == k) my_pos = pos;
+        qi = qn;
+        p0 = pn;
+        hint = hn;
     }
+    if (worklist && my_pos >= 0) {
+        // the first warp to match a map point whose normal is not cached claims it and queues it
+        const uint32_t claimed = kd_normal_claimed(ix.gen), valid = kd_normal_valid(ix.gen);
+        uint32_t* w = reinterpret_cast<uint32_t*>(&ix.normals[my_pos].w);
+        const uint32_t cur = __ldcg(w);
+        if (cur != valid && cur != claimed && atomicCAS(w, cur, claimed) == cur) s_list[atomicAdd(&s_n, 1)] = my_pos;
+    }
+    if (lane == 0 && cand) atomicAdd(&s_cand, cand);
     __syncthreads();
     const int n = s_n;
+    if (threadIdx.x == 0) {
+        if (n) s_base = (int)atomicAdd(&wl_count[parity], (uint32_t)n);
+        if (counters && s_cand) atomicAdd(counters + KDC_NN_CAND, (unsigned long long)s_cand);
+    }
     if (n == 0) return;
-    if (threadIdx.x == 0) s_base = (int)atomicAdd(&wl_count[parity], (uint32_t)n);
     __syncthreads();
     if (threadIdx.x < n) worklist[s_base + threadIdx.x] = s_list[threadIdx.x];
 }
 
 __global__ void __launch_bounds__(KD_THREADS)
 kd_normals_warp_kernel(KdIndex ix, int k_normals, const int* __restrict__ worklist, const uint32_t* __restrict__ wl_count,
-                       const int* __restrict__ done) {
+                       const int* __restrict__ done, unsigned long long* __restrict__ counters) {
     if (done && *done) return;
     const int n = (int)*wl_count;
     const int lane = threadIdx.x & 31;
@@ -297,13 +324,22 @@ kd_normals_warp_kernel(KdIndex ix, int k_normals, const int* __restrict__ workli
     const KdGridLocal g = kd_load_grid(ix);
     const float valid = __uint_as_float(kd_normal_valid(ix.gen));
     float mycov[6];
-    int mypos = -1, held = 0;
-    for (int e = warp_global; e < n; e += total_warps) {
-        const int pos = worklist[e];
-        const float4 c = __ldg(ix.sorted + pos);
+    int mypos = -1, held = 0, cand = 0, done_here = 0;
+    int e = warp_global;
+    int pos = worklist[e];
+    float4 c = __ldg(ix.sorted + pos);
+    while (true) {
+        // the next point is fetched while this one is searched
+        const int en = e + total_warps;
+        int posn = 0;
+        float4 cn = c;
+        if (en < n) {
+            posn = worklist[en];
+            cn = __ldg(ix.sorted + posn);
+        }
         float nd;
         int ni;
-        const int found = warp_knn(ix, g, c.x, c.y, c.z, k_normals + 1, lane, nd, ni);
+        const int found = warp_knn(ix, g, c.x, c.y, c.z, k_normals + 1, lane, nd, ni, &cand);
         float cov[6];
         warp_second_moments(ix, c, k_normals, found, ni, lane, cov);
         if (lane == held) {
@@ -311,6 +347,7 @@ kd_normals_warp_kernel(KdIndex ix, int k_normals, const int* __restrict__ workli
             for (int a = 0; a < 6; ++a) mycov[a] = cov[a];
             mypos = pos;
         }
+        ++done_here;
         if (++held == 32) {  // 32 moments collected: every lane solves its own
             float nn[3];
             smallest_eigenvector(mycov, nn);
@@ -318,11 +355,19 @@ kd_normals_warp_kernel(KdIndex ix, int k_normals, const int* __restrict__ workli
             held = 0;
             mypos = -1;
         }
+        if (en >= n) break;
+        e = en;
+        pos = posn;
+        c = cn;
     }
     if (mypos >= 0) {
         float nn[3];
         smallest_eigenvector(mycov, nn);
         __stcg(ix.normals + mypos, make_float4(nn[0], nn[1], nn[2], valid));
+    }
+    if (counters && lane == 0) {
+        atomicAdd(counters + KDC_KNN_CAND, (unsigned long long)cand);
+        atomicAdd(counters + KDC_NORMALS, (unsigned long long)done_here);
     }
 }
 
@@ -634,13 +679,27 @@ void kdmap_update(pls_context* ctx, const float* rel_pose_host, const float* pts
     kdmap_update_packed(ctx, rel_pose_host, ctx->tmp[4].as<float4>(), num_new, has_new);
 }
 
-// Launch geometry of the search kernel: `qpw` queries per warp, chosen so that the grid is about one resident wave.
+// Launch geometry of the search kernels: about ONE resident wave of warps (a second, partial wave would wait for the
+// first to drain), each warp looping over its share.
+static int resident_blocks(const void* kernel) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, KD_THREADS, 0) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 2;
+    }
+    return per_sm * kNumSMs;
+}
+
 static int nn_queries_per_warp(int64_t mine) {
     static const int forced = getenv("PLS_KD_QPW") ? atoi(getenv("PLS_KD_QPW")) : 0;
     if (forced >= 1 && forced <= KD_QPW_MAX) return forced;
-    const int64_t resident_warps = (int64_t)kNumSMs * 32;  // 64 registers per thread
+    static const int64_t resident_warps = (int64_t)resident_blocks((const void*)kd_nn_warp_kernel) * KD_WARPS;
     int qpw = (int)((mine + resident_warps - 1) / resident_warps);
     return qpw < 1 ? 1 : (qpw > KD_QPW_MAX ? KD_QPW_MAX : qpw);
+}
+
+static unsigned long long* kd_counters(pls_context* ctx) {
+    return reinterpret_cast<unsigned long long*>(scalar_u32(ctx, SC_KD_COUNTERS));
 }
 
 static void launch_search(pls_context* ctx, const KdIndex& ix, const float4* queries, const uint32_t* nq_dev, int64_t mine,
@@ -654,15 +713,16 @@ static void launch_search(pls_context* ctx, const KdIndex& ix, const float4* que
     uint32_t* wl_count = scalar_u32(ctx, SC_WL0);
     kd_nn_warp_kernel<<<blocks, KD_THREADS, 0, st>>>(ix, queries, nq_dev, (int64_t)rank, (int64_t)num_ranks, qpw, T, done, match,
                                                      use_hint ? 1 : 0, normals ? ctx->kd_worklist.as<int>() : nullptr, wl_count,
-                                                     parity);
+                                                     parity, kd_counters(ctx));
     PLS_CHECK_LAUNCH();
     if (normals) {
-        // a warp per queued point; with ~one resident wave of warps a frame's first iteration (every match new) gives
-        // each warp a handful of points, later iterations leave most warps without work (they exit at once)
+        // a warp per queued point: a frame's first iteration (every match is new) gives each warp a handful of points,
+        // later iterations leave most warps without work (they exit at once)
+        static const int resident = resident_blocks((const void*)kd_normals_warp_kernel);
         int nblocks = (int)((mine + KD_WARPS - 1) / KD_WARPS);
-        if (nblocks > 4 * kNumSMs) nblocks = 4 * kNumSMs;
+        if (nblocks > resident) nblocks = resident;
         kd_normals_warp_kernel<<<nblocks, KD_THREADS, 0, st>>>(ix, ctx->cfg.num_neighbors_normals, ctx->kd_worklist.as<int>(),
-                                                               wl_count + parity, done);
+                                                               wl_count + parity, done, kd_counters(ctx));
         PLS_CHECK_LAUNCH();
     }
 }

@@ -94,14 +94,18 @@ __device__ __forceinline__ KdGridLocal kd_load_grid(const KdIndex& ix) {
 }
 
 // The cell of the 3x3x3 block (at `level`, around the query) owned by this lane: its point range [start, start+count)
-// or count = 0 (lanes >= 27, cells outside the grid, empty cells, cells whose box is farther than sqrt(prune2)).
-// Returns the squared exactness radius of the block (FLT_MAX at the top level: the block then holds every point).
-// A query outside the grid is clamped to the border cell: all points lie on one side of it along that axis, so the
-// block still holds everything within one cell side.
+// or count = 0 (lanes >= 27, cells outside the grid, empty cells).  `box2` receives the squared distance from the
+// query to the cell's box, shrunk by the quantisation slack (a lower bound for every point binned into it): the caller
+// drops cells farther than its current best.  The probe itself does not depend on any bound, so it can be in flight
+// together with the load of the previous match.
+// Returns the squared exactness radius of the block (FLT_MAX at the top level: the block then holds every point;
+// negative if the level is unusable).  A query outside the grid is clamped to the border cell: all points lie on one
+// side of it along that axis, so the block still holds everything within one cell side.
 __device__ __forceinline__ float warp_probe_block(const KdIndex& ix, const KdGridLocal& g, int level, float x, float y,
-                                                  float z, float prune2, int lane, int& start, int& count) {
+                                                  float z, int lane, int& start, int& count, float& box2) {
     start = 0;
     count = 0;
+    box2 = FLT_MAX;
     const int b = g.b0 + level;
     const int cmax = KD_COORD_MAX >> b;
     const float side_u = (float)(1 << b);                      // cell side in quantisation units
@@ -111,27 +115,25 @@ __device__ __forceinline__ float warp_probe_block(const KdIndex& ix, const KdGri
     const int cx = min(max(((int)floorf(fx)) >> b, 0), cmax);
     const int cy = min(max(((int)floorf(fy)) >> b, 0), cmax);
     const int cz = min(max(((int)floorf(fz)) >> b, 0), cmax);
-    if (lane < 27) {
+    const bool usable = level >= g.top || !__ldg(&ix.grid->overflow[level]);
+    if (lane < 27 && usable) {
         const int dz = lane / 9, rem = lane - dz * 9, dy = rem / 3, dx = rem - dy * 3;
         const int xx = cx + dx - 1, yy = cy + dy - 1, zz = cz + dz - 1;
-        bool ok = xx >= 0 && xx <= cmax && yy >= 0 && yy <= cmax && zz >= 0 && zz <= cmax && !__ldg(&ix.grid->overflow[level]);
-        if (ok && prune2 < FLT_MAX) {
-            // metres from the query to the cell's box, shrunk by the quantisation slack (conservative)
+        if (xx >= 0 && xx <= cmax && yy >= 0 && yy <= cmax && zz >= 0 && zz <= cmax) {
+            const uint32_t id = kd_cell_id((uint32_t)xx, (uint32_t)yy, (uint32_t)zz);
+            const uint4* __restrict__ table = ix.table[level];
+            const uint32_t mask = ix.mask[level];
+            uint32_t h = kd_hash(id) & mask;
+            uint4 e = __ldg(table + h);
+            // box distance while the probe is in flight
             const float lox = ((float)xx * side_u - fx), hix = (fx - (float)(xx + 1) * side_u);
             const float loy = ((float)yy * side_u - fy), hiy = (fy - (float)(yy + 1) * side_u);
             const float loz = ((float)zz * side_u - fz), hiz = (fz - (float)(zz + 1) * side_u);
             const float ax = fmaxf(fmaxf(lox, hix) * g.inv_scale - KD_CELL_MARGIN, 0.f);
             const float ay = fmaxf(fmaxf(loy, hiy) * g.inv_scale - KD_CELL_MARGIN, 0.f);
             const float az = fmaxf(fmaxf(loz, hiz) * g.inv_scale - KD_CELL_MARGIN, 0.f);
-            ok = (ax * ax + ay * ay + az * az) <= prune2;
-        }
-        if (ok) {
-            const uint32_t id = kd_cell_id((uint32_t)xx, (uint32_t)yy, (uint32_t)zz) ;
-            const uint4* __restrict__ table = ix.table[level];
-            const uint32_t mask = ix.mask[level];
-            uint32_t h = kd_hash(id) & mask;
+            box2 = ax * ax + ay * ay + az * az;
             for (int probe = 0; probe < 64; ++probe) {
-                const uint4 e = __ldg(table + h);
                 if (e.y != ix.gen) break;              // empty (or stale generation): the cell holds no point
                 if (e.x == id) {
                     start = (int)e.z;
@@ -139,83 +141,92 @@ __device__ __forceinline__ float warp_probe_block(const KdIndex& ix, const KdGri
                     break;
                 }
                 h = (h + 1) & mask;
+                e = __ldg(table + h);
             }
         }
     }
     if (level >= g.top) return FLT_MAX;
-    if (__ldg(&ix.grid->overflow[level])) return -1.f;  // this level's table was too small: nothing scanned, nothing proven
+    if (!usable) return -1.f;  // this level's table was too small: nothing scanned, nothing proven
     const float cell = side_u * g.inv_scale - KD_CELL_MARGIN;
     return cell > 0.f ? cell * cell : -1.f;
 }
 
-// Flattened walk over the block's candidates: calls visit(active, d2, index) once per round on every lane
-// (active = this lane holds a candidate), 32 candidates per round, lane t taking the t-th point of the
-// concatenated ranges.  Returns the number of candidates.
-template <typename Visit>
-__device__ __forceinline__ int warp_scan_block(const KdIndex& ix, float x, float y, float z, int start, int count, int lane,
-                                               Visit visit) {
-    int incl = count;
+// arg-min of (d, i) over the warp with two REDUX instructions (d >= 0, so the float's bit pattern orders like its
+// value; ties: smaller index).  The result lands in every lane; (FLT_MAX, -1) if no lane holds a candidate.
+__device__ __forceinline__ void warp_argmin(float& d, int& i) {
+    const unsigned bits = __float_as_uint(d);
+    const unsigned m = __reduce_min_sync(FULL, bits);
+    const unsigned wi = __reduce_min_sync(FULL, bits == m ? (unsigned)i : 0xffffffffu);
+    d = __uint_as_float(m);
+    i = (int)wi;
+}
+
+// Inclusive warp scan of the per-lane range sizes; returns the total.
+__device__ __forceinline__ int warp_scan_counts(int count, int lane, int& incl) {
+    incl = count;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int v = __shfl_up_sync(FULL, incl, o);
         if (lane >= o) incl += v;
     }
-    const int total = __shfl_sync(FULL, incl, 31);
-    const int adj = start - (incl - count);  // index = adj(owner) + t
-    for (int base = 0; base < total; base += 32) {
-        const int t = base + lane;
-        const bool active = t < total;
-        const int tt = active ? t : total - 1;
-        // owner cell = number of lanes whose inclusive prefix is <= t (prefixes are non-decreasing)
-        int c = 0;
-#pragma unroll
-        for (int s = 16; s >= 1; s >>= 1) {
-            const int v = __shfl_sync(FULL, incl, c + s - 1);
-            if (v <= tt) c += s;
-        }
-        const int idx = __shfl_sync(FULL, adj, c) + tt;
-        const float4 p = __ldg(ix.sorted + idx);
-        visit(active, dist2_point(x, y, z, p), idx);
-    }
-    return total;
+    return __shfl_sync(FULL, incl, 31);
 }
 
-// arg-min of (d, i) over the warp (ties: smaller index); the result lands in every lane
-__device__ __forceinline__ void warp_argmin(float& d, int& i) {
+// Index (into `sorted`) of the t-th candidate of the concatenated ranges: the owner cell is the number of lanes whose
+// inclusive prefix is <= t (the prefixes are non-decreasing), found by a 5-step search over lane registers.
+__device__ __forceinline__ int warp_candidate(int incl, int adj /* = start - exclusive prefix */, int t) {
+    int c = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float od = __shfl_xor_sync(FULL, d, o);
-        const int oi = __shfl_xor_sync(FULL, i, o);
-        if (od < d || (od == d && (unsigned)oi < (unsigned)i)) {
-            d = od;
-            i = oi;
-        }
+    for (int s = 16; s >= 1; s >>= 1) {
+        const int v = __shfl_sync(FULL, incl, c + s - 1);
+        if (v <= t) c += s;
     }
+    return __shfl_sync(FULL, adj, c) + t;
 }
 
 // Exact 1-NN of (x, y, z) by the whole warp; every lane returns the same sorted position (-1 if the map is empty).
-// `hint` (a sorted position or -1, warp-uniform) only seeds the pruning bound.
+// `hint` (a sorted position or -1, warp-uniform) only seeds the pruning bound; its load overlaps the level-0 probes.
+// *cand_out (optional) accumulates the number of candidates tested.
 __device__ __forceinline__ int warp_nearest(const KdIndex& ix, const KdGridLocal& g, float x, float y, float z, int hint,
-                                            int lane) {
+                                            int lane, int* cand_out) {
     float best = FLT_MAX;
     int best_i = -1;
-    if (hint >= 0 && hint < ix.M) {
-        best = dist2_point(x, y, z, __ldg(ix.sorted + hint));
-        best_i = hint;
-    }
+    float4 hp = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool has_hint = hint >= 0 && hint < ix.M;
+    if (has_hint) hp = __ldg(ix.sorted + hint);
     if (lane == 0) kd_stat(ix, 0);
     for (int level = 0; level <= g.top; ++level) {
         int start, count;
-        const float r2 = warp_probe_block(ix, g, level, x, y, z, best, lane, start, count);
-        const int cand = warp_scan_block(ix, x, y, z, start, count, lane, [&](bool active, float d, int i) {
-            if (active && (d < best || (d == best && (unsigned)i < (unsigned)best_i))) {
-                best = d;
-                best_i = i;
+        float box2;
+        const float r2 = warp_probe_block(ix, g, level, x, y, z, lane, start, count, box2);
+        if (level == 0 && has_hint) {
+            best = dist2_point(x, y, z, hp);
+            best_i = hint;
+        }
+        if (box2 > best) count = 0;  // nothing in that cell can beat (or tie) the bound
+        int incl;
+        const int total = warp_scan_counts(count, lane, incl);
+        const int adj = start - (incl - count);
+        float ld = best;
+        int li = best_i;
+        for (int base = 0; base < total; base += 32) {
+            const int t = base + lane;
+            const bool active = t < total;
+            const int idx = warp_candidate(incl, adj, active ? t : total - 1);
+            if (active) {
+                const float d = dist2_point(x, y, z, __ldg(ix.sorted + idx));
+                if (d < ld || (d == ld && (unsigned)idx < (unsigned)li)) {
+                    ld = d;
+                    li = idx;
+                }
             }
-        });
-        warp_argmin(best, best_i);
+        }
+        warp_argmin(ld, li);
+        best = ld;
+        best_i = li;
+        if (cand_out) *cand_out += total;
         if (ix.stats && lane == 0) {
-            kd_stat(ix, 3, (unsigned long long)cand);
+            kd_stat(ix, 3, (unsigned long long)total);
             if (level == 0) kd_stat(ix, (best_i >= 0 && best <= r2) ? 1 : 2);
         }
         if (best_i >= 0 && best <= r2) break;
@@ -223,89 +234,95 @@ __device__ __forceinline__ int warp_nearest(const KdIndex& ix, const KdGridLocal
     return best_i;
 }
 
+// One chunk of the K-NN selection: R fresh candidates per lane (t = chunk + s * 32 + lane) plus the lane's entry of the
+// list kept so far compete; on return lane r < K holds the r-th smallest of them.
+//   * every lane sorts its R + 1 entries ascending (a small compare-exchange network, no communication);
+//   * K rounds: the warp's minimum over the lane heads (two REDUX), the owner pops its head (a register shift).
+template <int R>
+__device__ __forceinline__ void knn_select_chunk(const KdIndex& ix, float x, float y, float z, int K, int lane, int incl, int adj,
+                                                 int total, int chunk, float& keep_d, int& keep_i) {
+    float sd[R + 1];
+    int si[R + 1];
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+        const int t = chunk + s * 32 + lane;
+        const bool active = t < total;
+        const int idx = warp_candidate(incl, adj, active ? t : total - 1);
+        sd[s] = active ? dist2_point(x, y, z, __ldg(ix.sorted + idx)) : FLT_MAX;
+        si[s] = active ? idx : -1;
+    }
+    sd[R] = keep_d;
+    si[R] = keep_i;
+    // insertion network: after pass p the first p + 2 entries are ordered
+#pragma unroll
+    for (int p = 1; p <= R; ++p) {
+#pragma unroll
+        for (int q = p; q >= 1; --q) {
+            const bool sw = sd[q] < sd[q - 1] || (sd[q] == sd[q - 1] && (unsigned)si[q] < (unsigned)si[q - 1]);
+            const float td = sw ? sd[q - 1] : sd[q];
+            const int ti = sw ? si[q - 1] : si[q];
+            sd[q - 1] = sw ? sd[q] : sd[q - 1];
+            si[q - 1] = sw ? si[q] : si[q - 1];
+            sd[q] = td;
+            si[q] = ti;
+        }
+    }
+    float nd = FLT_MAX;
+    int ni = -1;
+    for (int r = 0; r < K; ++r) {
+        float wd = sd[0];
+        int wi = si[0];
+        const int mine = wi;
+        warp_argmin(wd, wi);
+        if (wi < 0) break;  // nothing left anywhere
+        if (mine == wi) {   // indices are unique: exactly one lane pops
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                sd[s] = sd[s + 1];
+                si[s] = si[s + 1];
+            }
+            sd[R] = FLT_MAX;
+            si[R] = -1;
+        }
+        if (lane == r) {
+            nd = wd;
+            ni = wi;
+        }
+    }
+    keep_d = nd;
+    keep_i = ni;
+}
+
 // Exact K-NN (K <= 32, warp-uniform) of (x, y, z): on return lane r < found holds the r-th nearest point
 // (out_d, out_i), ascending by (distance, index); returns the number found (min(K, M)).
-//
-// Selection.  The candidates of a block are taken in chunks of 32 * R (R register slots per lane); K rounds of
-// {lane-local minimum, warp arg-min, the winner retires its slot} extract the K smallest of the chunk plus the K kept
-// from the previous chunk (re-entered through one carry slot per lane).  A 27-cell block of the BASELINE maps holds
-// 100-200 points: one chunk.
-constexpr int KD_KNN_SLOTS = 8;
+// The candidates of a block are taken in chunks of 32 * R, R = 2, 4 or 8 register slots per lane by block size
+// (a 27-cell block of the BASELINE maps holds 30-80 points: one chunk of R = 2 or 4).
 __device__ __forceinline__ int warp_knn(const KdIndex& ix, const KdGridLocal& g, float x, float y, float z, int K, int lane,
-                                        float& out_d, int& out_i) {
-    constexpr int R = KD_KNN_SLOTS;
-    float keep_d = FLT_MAX;   // lane r: r-th best so far (carry between chunks / the result)
+                                        float& out_d, int& out_i, int* cand_out) {
+    float keep_d = FLT_MAX;   // lane r: r-th best so far (carried between chunks / the result)
     int keep_i = -1;
     int found = 0;
     if (lane == 0) kd_stat(ix, 4);
     float bound = FLT_MAX;    // K-th distance of the previous (finer) level: an upper bound for this one
     for (int level = 0; level <= g.top; ++level) {
         int start, count;
-        const float r2 = warp_probe_block(ix, g, level, x, y, z, bound, lane, start, count);
-        // flatten the ranges (as warp_scan_block, but chunked into register slots)
-        int incl = count;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += v;
-        }
-        const int total = __shfl_sync(FULL, incl, 31);
+        float box2;
+        const float r2 = warp_probe_block(ix, g, level, x, y, z, lane, start, count, box2);
+        if (box2 > bound) count = 0;
+        int incl;
+        const int total = warp_scan_counts(count, lane, incl);
         const int adj = start - (incl - count);
+        if (cand_out) *cand_out += total;
         if (ix.stats && lane == 0) kd_stat(ix, 7, (unsigned long long)total);
         keep_d = FLT_MAX;     // this level's block is a superset of the previous one: select afresh
         keep_i = -1;
-        for (int chunk = 0; chunk < total || chunk == 0; chunk += 32 * R) {
-            float sd[R + 1];
-            int si[R + 1];
-#pragma unroll
-            for (int s = 0; s < R; ++s) {
-                const int t = chunk + s * 32 + lane;
-                const bool active = t < total;
-                const int tt = active ? t : (total > 0 ? total - 1 : 0);
-                int c = 0;
-#pragma unroll
-                for (int st = 16; st >= 1; st >>= 1) {
-                    const int v = __shfl_sync(FULL, incl, c + st - 1);
-                    if (v <= tt) c += st;
-                }
-                const int idx = __shfl_sync(FULL, adj, c) + tt;
-                float d = FLT_MAX;
-                if (active) d = dist2_point(x, y, z, __ldg(ix.sorted + idx));
-                sd[s] = d;
-                si[s] = active ? idx : -1;
-            }
-            sd[R] = keep_d;   // the K kept so far compete again
-            si[R] = keep_i;
-            float nd = FLT_MAX;
-            int ni = -1;
-            for (int r = 0; r < K; ++r) {
-                float ld = sd[0];
-                int li = si[0];
-#pragma unroll
-                for (int s = 1; s <= R; ++s) {
-                    const bool lt = sd[s] < ld || (sd[s] == ld && (unsigned)si[s] < (unsigned)li);
-                    ld = lt ? sd[s] : ld;
-                    li = lt ? si[s] : li;
-                }
-                float wd = ld;
-                int wi = li;
-                warp_argmin(wd, wi);
-                if (wi < 0) break;  // nothing left
-                if (li == wi) {     // indices are unique: exactly one lane retires its slot
-#pragma unroll
-                    for (int s = 0; s <= R; ++s) {
-                        const bool hit = si[s] == wi;
-                        sd[s] = hit ? FLT_MAX : sd[s];
-                        si[s] = hit ? -1 : si[s];
-                    }
-                }
-                if (lane == r) {
-                    nd = wd;
-                    ni = wi;
-                }
-            }
-            keep_d = nd;
-            keep_i = ni;
+        if (total <= 64) {
+            knn_select_chunk<2>(ix, x, y, z, K, lane, incl, adj, total, 0, keep_d, keep_i);
+        } else if (total <= 128) {
+            knn_select_chunk<4>(ix, x, y, z, K, lane, incl, adj, total, 0, keep_d, keep_i);
+        } else {
+            for (int chunk = 0; chunk < total; chunk += 256)
+                knn_select_chunk<8>(ix, x, y, z, K, lane, incl, adj, total, chunk, keep_d, keep_i);
         }
         found = __popc(__ballot_sync(FULL, keep_i >= 0));
         const float kth = __shfl_sync(FULL, keep_d, K - 1);

@@ -28,6 +28,7 @@ __global__ void frame_begin_kernel(FrameResult* fr, const float* T0 /*16, device
                                    uint32_t* worklist_counts /*2*/) {
     int t = threadIdx.x;
     if (t < 2) worklist_counts[t] = 0;
+    if (t >= 3 && t < 11) worklist_counts[t] = 0;  // SC_KD_COUNTERS: the kd search counters of this frame
     if (t < 16) fr->T[t] = T0 ? T0[t] : ((t % 5 == 0) ? 1.f : 0.f);
     if (t < 6) fr->params[t] = 0.f;
     if (t < kMaxAlign) fr->losses[t] = __int_as_float(0x7fc00000);
@@ -227,16 +228,27 @@ int run_icp(pls_context* ctx, const float* T0_dev, int64_t query_bound) {
 }
 
 void fetch_result(pls_context* ctx) {
-    PLS_CUDA(cudaMemcpyAsync(ctx->pinned.p, ctx->scalars.p, sizeof(FrameResult), cudaMemcpyDeviceToHost, ctx->stream));
+    // the FrameResult and the u32 / u64 scalar slots behind it in one copy
+    PLS_CUDA(cudaMemcpyAsync(ctx->pinned.p, ctx->scalars.p, kScalarOffset + SC_NUM * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                             ctx->stream));
     PLS_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
-// Algorithmic bytes of one executed correspondence+reduction launch (DESIGN.md "K5/K6"):
-// kd map: per query 16 B query + 4+4 B previous-match read/write + 16 B matched point + 16 B normal;
-// plus one 30-double partial row per block.
+// Algorithmic bytes of the frame's executed ICP iterations, by SURVEY.md 8d's formulas.
+// kd map:  K5a exact 1-NN    per query 12 B (query) + 27 * 8 B (cell-range lookups) + 4 B (match), plus 16 B per
+//                            candidate actually tested (counted by the kernel);
+//          K5b/c normals     per computed normal 16 B (point) + 16 B (normal written), plus 16 B per candidate tested;
+//          K6 reduction      per correspondence 36 B, plus one 30-double partial row per block.
+// (bench.py also reports the lower bound SURVEY names: 44 B per query + 16 B per touched map point.)
 void credit_icp_profile(pls_context* ctx, const FrameResult* h, int blocks) {
     if (ctx->cfg.local_map_type == PLS_MAP_KDTREE) {
-        profile_credit(ctx, 0, h->iters, (double)h->iters * ((double)h->counts[1] * 56.0 + (double)blocks * NACC * 8.0));
+        const unsigned long long* kc = reinterpret_cast<const unsigned long long*>(
+            reinterpret_cast<const char*>(h) + kScalarOffset + SC_KD_COUNTERS * sizeof(uint32_t));
+        const double iters = (double)h->iters, nq = (double)h->counts[1];
+        const double bytes = iters * nq * (12.0 + 27.0 * 8.0 + 4.0) + 16.0 * (double)kc[0]      // K5a
+                             + 32.0 * (double)kc[2] + 16.0 * (double)kc[1]                      // K5b/c
+                             + iters * (nq * 36.0 + (double)blocks * NACC * 8.0);               // K6
+        profile_credit(ctx, 0, h->iters, bytes);
     } else {
         // projective map: HW*12*(K+1) (target + K candidate vertex maps, each read once)
         // + N_c*12 (winner normals) + one partial row per block
