@@ -220,7 +220,8 @@ enum { SC_GS_COUNT = 0, SC_QUERY_COUNT = 1, SC_NAN_COUNT = 2, SC_INSERT_COUNT = 
        SC_WL0 = 5, SC_WL1 = 6,  // pending-normal worklist counters, one per iteration parity (kdmap.cu)
        SC_GS_OVERFLOW = 7,
        SC_KD_COUNTERS = 8,      // four u64 counters of the kd search kernels (slots 8..15)
-       SC_NUM = 16 };
+       SC_KD_LISTS = 16,        // per-iteration work-list counters of the kd search (kdmap.cu: KDL_*), 8 words
+       SC_NUM = 32 };
 
 // ---- pointer classification + staging ---------------------------------------------------
 bool is_device_ptr(const void* p);           // cached per address

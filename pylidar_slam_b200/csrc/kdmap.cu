@@ -229,89 +229,184 @@ __global__ void kd_export_kernel(const float4* __restrict__ pts, int64_t n, floa
 
 // ---- one ICP iteration on the kd map (icp_odometry.py:275-284 + alignment.py:91-127 at x0 = 0) -----------------------
 //   p = T p0; q = NN(p); n = normal(q); r = n.(p - q); J = [n, p x n]; w; reduce        -- three launches:
-//   kd_nn_warp_kernel       a warp per query: transform, exact 1-NN (kdmap_device.cuh) -> match[qi]; the first warp to
-//                           match a map point whose normal is not cached claims it (CAS on the state word) and
-//                           queues it (block-aggregated append: one global atomic per block)
-//   kd_normals_warp_kernel  a warp per queued map point: exact (k+1)-NN, second moments; the eigen-solves are deferred
-//                           and run lane-parallel (each lane one point) so that no warp idles behind a serial solve
+//   kd_nn_thread_kernel / kd_nn_warp_kernel            transform, exact 1-NN -> match[qi]: a thread per query proves
+//                           the easy ones inside the 3x3x3 level-0 block, a warp per remaining query searches the
+//                           pyramid; the first to match a map point whose normal is not cached claims it (CAS on the
+//                           state word) and queues it (block- / warp-aggregated appends)
+//   kd_normals_thread_kernel / kd_normals_warp_kernel  exact (k+1)-NN of every queued map point, second moments,
+//                           eigen-solve: a thread per point inside the 5x5x5 block, a warp per remaining point
 //   kd_residual_kernel      a thread per query: r, J, robust weight, the 30 fp64 accumulators -> block partials; the
 //                           last block sums them in fixed order and runs the solve / stop test / pose update
 constexpr int KD_THREADS = 256;
 constexpr int KD_WARPS = KD_THREADS / 32;
-constexpr int KD_QPW_MAX = 8;   // queries per warp of the search kernel (bounds the block's claim list)
 
 // counters of the search kernels (u64, behind the u32 scalar slots): candidates tested by the 1-NN searches, by the
 // k-NN searches, normals computed -- the inputs of SURVEY 8d's algorithmic-bytes formulas
 enum { KDC_NN_CAND = 0, KDC_KNN_CAND = 1, KDC_NORMALS = 2 };
+// per-iteration work-list counters (u32 words at SC_KD_LISTS), one pair per list, indexed by the iteration's parity:
+// the first kernel of iteration `it` zeroes the words of parity (it + 1) & 1 -- consumed by the previous iteration,
+// filled by the next -- so no list is ever reset by a separate launch
+enum { KDL_PENDING = 0, KDL_HARD_NN = 2, KDL_HARD_KNN = 4, KDL_WORDS = 6 };
 
+// Appends this block's entries (collected in shared memory by any of its threads) to a global list: one atomic per block.
+__device__ __forceinline__ void block_flush_list(const int* s_list, int n, int* __restrict__ list, uint32_t* count, int* s_base) {
+    if (n == 0) return;  // block-uniform
+    if (threadIdx.x == 0) *s_base = (int)atomicAdd(count, (uint32_t)n);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) list[*s_base + i] = s_list[i];
+}
+
+// Claims the normal of map point `pos` for computation if it is neither cached nor already claimed.
+__device__ __forceinline__ bool claim_normal(const KdIndex& ix, int pos) {
+    const uint32_t claimed = kd_normal_claimed(ix.gen), valid = kd_normal_valid(ix.gen);
+    uint32_t* w = reinterpret_cast<uint32_t*>(&ix.normals[pos].w);
+    const uint32_t cur = __ldcg(w);
+    return cur != valid && cur != claimed && atomicCAS(w, cur, claimed) == cur;
+}
+
+// 1-NN, fast path: a thread per query (thread_nearest).  Proven matches claim their normal; unproven ones are queued
+// for the warp-cooperative search (their best candidate so far is left in match[] as its bound).
 __global__ void __launch_bounds__(KD_THREADS)
-kd_nn_warp_kernel(KdIndex ix, const float4* __restrict__ queries, const uint32_t* __restrict__ nq_dev, int64_t q_begin,
-                  int64_t q_stride, int qpw, const float* __restrict__ T, const int* __restrict__ done,
-                  int* __restrict__ match, int use_hint, int* __restrict__ worklist, uint32_t* wl_count, int parity,
-                  unsigned long long* __restrict__ counters) {
+kd_nn_thread_kernel(KdIndex ix, const float4* __restrict__ queries, const uint32_t* __restrict__ nq_dev, int64_t q_begin,
+                    int64_t q_stride, const float* __restrict__ T, const int* __restrict__ done, int* __restrict__ match,
+                    int use_hint, int want_normals, int* __restrict__ pending, int* __restrict__ hard, uint32_t* lists,
+                    int parity, unsigned long long* __restrict__ counters) {
     if (done && *done) return;
     __shared__ float sT[12];
-    __shared__ int s_list[KD_WARPS * KD_QPW_MAX];
-    __shared__ int s_n, s_base, s_cand;
+    __shared__ int s_pending[KD_THREADS], s_hard[KD_THREADS];
+    __shared__ int s_np, s_nh, s_cand, s_base;
     if (threadIdx.x < 12) sT[threadIdx.x] = T[threadIdx.x];
     if (threadIdx.x == 0) {
-        s_n = 0;
+        s_np = 0;
+        s_nh = 0;
         s_cand = 0;
-        if (blockIdx.x == 0) wl_count[parity ^ 1] = 0;  // the other slot: consumed by the previous iteration, used by the next
+        if (blockIdx.x == 0)
+            for (int l = 0; l < KDL_WORDS; l += 2) lists[l + (parity ^ 1)] = 0;
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const KdGridLocal g = kd_load_grid(ix);
     const int64_t nq = (int64_t)*nq_dev;
-    const int64_t total_warps = (int64_t)gridDim.x * KD_WARPS;
-    const int64_t s0 = (int64_t)blockIdx.x * KD_WARPS + warp;
-    int my_pos = -1;  // lane k: the match of this warp's k-th query (claims are made by all lanes at once, afterwards)
+    const int64_t qi = q_begin + ((int64_t)blockIdx.x * KD_THREADS + threadIdx.x) * q_stride;
     int cand = 0;
-    int64_t qi = q_begin + s0 * q_stride;
-    float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f);
-    int hint = -1;
     if (qi < nq) {
-        p0 = queries[qi];
-        if (use_hint) hint = match[qi];
-    }
-    for (int k = 0; k < qpw && qi < nq; ++k) {
-        // the next query's data is fetched while this one is searched
-        const int64_t qn = q_begin + (s0 + (int64_t)(k + 1) * total_warps) * q_stride;
-        float4 pn = p0;
-        int hn = -1;
-        if (k + 1 < qpw && qn < nq) {
-            pn = queries[qn];
-            if (use_hint) hn = match[qn];
-        }
+        const KdGridLocal g = kd_load_grid(ix);
+        const float4 p0 = queries[qi];
         const float px = p0.x * sT[0] + p0.y * sT[1] + p0.z * sT[2] + sT[3];
         const float py = p0.x * sT[4] + p0.y * sT[5] + p0.z * sT[6] + sT[7];
         const float pz = p0.x * sT[8] + p0.y * sT[9] + p0.z * sT[10] + sT[11];
-        const int pos = warp_nearest(ix, g, px, py, pz, hint, lane, &cand);
-        if (lane == 0) match[qi] = pos;
-        if (lane == k) my_pos = pos;
-        qi = qn;
-        p0 = pn;
-        hint = hn;
+        bool exact;
+        const int pos = thread_nearest(ix, g, px, py, pz, use_hint ? match[qi] : -1, exact, cand);
+        match[qi] = pos;
+        if (!exact) s_hard[atomicAdd(&s_nh, 1)] = (int)qi;
+        else if (want_normals && claim_normal(ix, pos)) s_pending[atomicAdd(&s_np, 1)] = pos;
     }
-    if (worklist && my_pos >= 0) {
-        // the first warp to match a map point whose normal is not cached claims it and queues it
-        const uint32_t claimed = kd_normal_claimed(ix.gen), valid = kd_normal_valid(ix.gen);
-        uint32_t* w = reinterpret_cast<uint32_t*>(&ix.normals[my_pos].w);
-        const uint32_t cur = __ldcg(w);
-        if (cur != valid && cur != claimed && atomicCAS(w, cur, claimed) == cur) s_list[atomicAdd(&s_n, 1)] = my_pos;
-    }
-    if (lane == 0 && cand) atomicAdd(&s_cand, cand);
+    // candidates tested: warp sum, then one shared atomic per warp
+    cand = __reduce_add_sync(FULL, cand);
+    if ((threadIdx.x & 31) == 0 && cand) atomicAdd(&s_cand, cand);
     __syncthreads();
-    const int n = s_n;
-    if (threadIdx.x == 0) {
-        if (n) s_base = (int)atomicAdd(&wl_count[parity], (uint32_t)n);
-        if (counters && s_cand) atomicAdd(counters + KDC_NN_CAND, (unsigned long long)s_cand);
-    }
-    if (n == 0) return;
+    if (threadIdx.x == 0 && counters && s_cand) atomicAdd(counters + KDC_NN_CAND, (unsigned long long)s_cand);
+    block_flush_list(s_hard, s_nh, hard, lists + KDL_HARD_NN + parity, &s_base);
     __syncthreads();
-    if (threadIdx.x < n) worklist[s_base + threadIdx.x] = s_list[threadIdx.x];
+    block_flush_list(s_pending, s_np, pending, lists + KDL_PENDING + parity, &s_base);
 }
 
+// 1-NN, exact path for the queued queries: a warp per query searches the cell pyramid (warp_nearest), seeded with the
+// fast path's candidate.  Claims are made by all lanes at once after a warp's queries are done.
+__global__ void __launch_bounds__(KD_THREADS)
+kd_nn_warp_kernel(KdIndex ix, const float4* __restrict__ queries, const int* __restrict__ hard, const uint32_t* __restrict__ hard_count,
+                  const float* __restrict__ T, const int* __restrict__ done, int* __restrict__ match, int want_normals,
+                  int* __restrict__ pending, uint32_t* pending_count, unsigned long long* __restrict__ counters) {
+    if (done && *done) return;
+    const int n = (int)*hard_count;
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * KD_WARPS + (threadIdx.x >> 5);
+    const int total_warps = gridDim.x * KD_WARPS;
+    if (warp_global >= n) return;
+    float t[12];
+#pragma unroll
+    for (int a = 0; a < 12; ++a) t[a] = T[a];
+    const KdGridLocal g = kd_load_grid(ix);
+    int my_pos = -1, held = 0, cand = 0;
+    auto flush_claims = [&]() {
+        const bool mine = want_normals && my_pos >= 0 && claim_normal(ix, my_pos);
+        const unsigned m = __ballot_sync(FULL, mine);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = (int)atomicAdd(pending_count, (uint32_t)__popc(m));
+            base = __shfl_sync(FULL, base, 0);
+            if (mine) pending[base + __popc(m & ((1u << lane) - 1u))] = my_pos;
+        }
+        my_pos = -1;
+        held = 0;
+    };
+    for (int s = warp_global; s < n; s += total_warps) {
+        const int qi = hard[s];
+        const float4 p0 = queries[qi];
+        const float px = p0.x * t[0] + p0.y * t[1] + p0.z * t[2] + t[3];
+        const float py = p0.x * t[4] + p0.y * t[5] + p0.z * t[6] + t[7];
+        const float pz = p0.x * t[8] + p0.y * t[9] + p0.z * t[10] + t[11];
+        const int pos = warp_nearest(ix, g, px, py, pz, match[qi], lane, &cand);
+        if (lane == 0) match[qi] = pos;
+        if (lane == held) my_pos = pos;
+        if (++held == 32) flush_claims();
+    }
+    flush_claims();
+    if (counters && lane == 0 && cand) atomicAdd(counters + KDC_NN_CAND, (unsigned long long)cand);
+}
+
+// Normals, fast path: a thread per queued map point (thread_knn: 3x3x3 block, then the pruned 5x5x5 shell), second
+// moments and the eigen-solve -- 32 independent points per warp.  Points whose K-th neighbour cannot be proven inside
+// the 5x5x5 block are queued for the warp-cooperative search.
+__global__ void __launch_bounds__(KD_THREADS)
+kd_normals_thread_kernel(KdIndex ix, const int* __restrict__ pending, const uint32_t* __restrict__ pending_count,
+                         const int* __restrict__ done, int* __restrict__ hard, uint32_t* hard_count,
+                         unsigned long long* __restrict__ counters) {
+    if (done && *done) return;
+    __shared__ int s_hard[KD_THREADS];
+    __shared__ int s_nh, s_cand, s_done, s_base;
+    const int n = (int)*pending_count;
+    if ((int)(blockIdx.x * KD_THREADS) >= n) return;
+    if (threadIdx.x == 0) {
+        s_nh = 0;
+        s_cand = 0;
+        s_done = 0;
+    }
+    __syncthreads();
+    const int e = blockIdx.x * KD_THREADS + threadIdx.x;
+    int cand = 0, solved = 0;
+    if (e < n) {
+        const KdGridLocal g = kd_load_grid(ix);
+        const int pos = pending[e];
+        const float4 c = __ldg(ix.sorted + pos);
+        KBest<11> L;
+        bool exact;
+        thread_knn<11>(ix, g, c.x, c.y, c.z, L, exact, cand);
+        if (exact) {
+            float cov[6], nn[3];
+            thread_moments<11>(ix, c, L, cov);
+            smallest_eigenvector(cov, nn);
+            __stcg(ix.normals + pos, make_float4(nn[0], nn[1], nn[2], __uint_as_float(kd_normal_valid(ix.gen))));
+            solved = 1;
+        } else {
+            s_hard[atomicAdd(&s_nh, 1)] = pos;
+        }
+    }
+    cand = __reduce_add_sync(FULL, cand);
+    solved = __reduce_add_sync(FULL, solved);
+    if ((threadIdx.x & 31) == 0) {
+        if (cand) atomicAdd(&s_cand, cand);
+        if (solved) atomicAdd(&s_done, solved);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && counters) {
+        if (s_cand) atomicAdd(counters + KDC_KNN_CAND, (unsigned long long)s_cand);
+        if (s_done) atomicAdd(counters + KDC_NORMALS, (unsigned long long)s_done);
+    }
+    block_flush_list(s_hard, s_nh, hard, hard_count, &s_base);
+}
+
+// Normals, exact path for the queued points (or for every pending point when k != 10): a warp per point, exact
+// (k+1)-NN over the cell pyramid (warp_knn), second moments; the eigen-solves are deferred and run lane-parallel
+// (each lane one point) so that no warp idles behind a serial solve.
 __global__ void __launch_bounds__(KD_THREADS)
 kd_normals_warp_kernel(KdIndex ix, int k_normals, const int* __restrict__ worklist, const uint32_t* __restrict__ wl_count,
                        const int* __restrict__ done, unsigned long long* __restrict__ counters) {
@@ -690,41 +785,48 @@ static int resident_blocks(const void* kernel) {
     return per_sm * kNumSMs;
 }
 
-static int nn_queries_per_warp(int64_t mine) {
-    static const int forced = getenv("PLS_KD_QPW") ? atoi(getenv("PLS_KD_QPW")) : 0;
-    if (forced >= 1 && forced <= KD_QPW_MAX) return forced;
-    static const int64_t resident_warps = (int64_t)resident_blocks((const void*)kd_nn_warp_kernel) * KD_WARPS;
-    int qpw = (int)((mine + resident_warps - 1) / resident_warps);
-    return qpw < 1 ? 1 : (qpw > KD_QPW_MAX ? KD_QPW_MAX : qpw);
-}
-
 static unsigned long long* kd_counters(pls_context* ctx) {
     return reinterpret_cast<unsigned long long*>(scalar_u32(ctx, SC_KD_COUNTERS));
 }
 
+// The search of one ICP iteration (or of one fine-grained API call): thread-per-query fast paths over compacted work
+// lists, each followed by its warp-cooperative exact path for the queries it could not prove.
 static void launch_search(pls_context* ctx, const KdIndex& ix, const float4* queries, const uint32_t* nq_dev, int64_t mine,
                           int rank, int num_ranks, const float* T, const int* done, int* match, bool use_hint, bool normals,
                           int parity) {
     cudaStream_t st = ctx->stream;
-    const int qpw = nn_queries_per_warp(mine);
-    const int64_t per_block = (int64_t)KD_WARPS * qpw;
-    const int blocks = (int)((mine + per_block - 1) / per_block);
-    ctx->kd_worklist.reserve((size_t)(mine + 64) * sizeof(int), st);
-    uint32_t* wl_count = scalar_u32(ctx, SC_WL0);
-    kd_nn_warp_kernel<<<blocks, KD_THREADS, 0, st>>>(ix, queries, nq_dev, (int64_t)rank, (int64_t)num_ranks, qpw, T, done, match,
-                                                     use_hint ? 1 : 0, normals ? ctx->kd_worklist.as<int>() : nullptr, wl_count,
-                                                     parity, kd_counters(ctx));
+    const size_t slots = (size_t)mine + 64;
+    ctx->kd_worklist.reserve(3 * slots * sizeof(int), st);
+    int* pending = ctx->kd_worklist.as<int>();
+    int* hard_nn = pending + slots;
+    int* hard_knn = hard_nn + slots;
+    uint32_t* lists = scalar_u32(ctx, SC_KD_LISTS);
+    unsigned long long* counters = kd_counters(ctx);
+    const int tblocks = (int)((mine + KD_THREADS - 1) / KD_THREADS);
+    static const int resident_nn = resident_blocks((const void*)kd_nn_warp_kernel);
+    static const int resident_kn = resident_blocks((const void*)kd_normals_warp_kernel);
+    int wblocks = (int)((mine + KD_WARPS - 1) / KD_WARPS);
+    kd_nn_thread_kernel<<<tblocks, KD_THREADS, 0, st>>>(ix, queries, nq_dev, (int64_t)rank, (int64_t)num_ranks, T, done, match,
+                                                        use_hint ? 1 : 0, normals ? 1 : 0, pending, hard_nn, lists, parity, counters);
     PLS_CHECK_LAUNCH();
-    if (normals) {
-        // a warp per queued point: a frame's first iteration (every match is new) gives each warp a handful of points,
-        // later iterations leave most warps without work (they exit at once)
-        static const int resident = resident_blocks((const void*)kd_normals_warp_kernel);
-        int nblocks = (int)((mine + KD_WARPS - 1) / KD_WARPS);
-        if (nblocks > resident) nblocks = resident;
-        kd_normals_warp_kernel<<<nblocks, KD_THREADS, 0, st>>>(ix, ctx->cfg.num_neighbors_normals, ctx->kd_worklist.as<int>(),
-                                                               wl_count + parity, done, kd_counters(ctx));
+    kd_nn_warp_kernel<<<wblocks < resident_nn ? wblocks : resident_nn, KD_THREADS, 0, st>>>(
+        ix, queries, hard_nn, lists + KDL_HARD_NN + parity, T, done, match, normals ? 1 : 0, pending, lists + KDL_PENDING + parity,
+        counters);
+    PLS_CHECK_LAUNCH();
+    if (!normals) return;
+    const int k = ctx->cfg.num_neighbors_normals;
+    const int* exact_list = pending;
+    const uint32_t* exact_count = lists + KDL_PENDING + parity;
+    if (k == 10) {
+        kd_normals_thread_kernel<<<tblocks, KD_THREADS, 0, st>>>(ix, pending, lists + KDL_PENDING + parity, done, hard_knn,
+                                                                 lists + KDL_HARD_KNN + parity, counters);
         PLS_CHECK_LAUNCH();
+        exact_list = hard_knn;
+        exact_count = lists + KDL_HARD_KNN + parity;
     }
+    kd_normals_warp_kernel<<<wblocks < resident_kn ? wblocks : resident_kn, KD_THREADS, 0, st>>>(ix, k, exact_list, exact_count, done,
+                                                                                                 counters);
+    PLS_CHECK_LAUNCH();
 }
 
 // One ICP iteration over the device-resident queries (float4 in ctx->query_ptr, count in the FrameResult); writes
@@ -839,7 +941,7 @@ int pls_kdmap_nn_search(pls_context* ctx, const float* queries, int64_t n, float
     uint32_t* nq = scalar_u32(ctx, SC_QUERY_COUNT);
     const uint32_t nq_host[3] = {(uint32_t)n, 0u, 0u};
     PLS_CUDA(cudaMemcpyAsync(nq, nq_host, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    PLS_CUDA(cudaMemsetAsync(scalar_u32(ctx, SC_WL0), 0, 2 * sizeof(uint32_t), st));
+    PLS_CUDA(cudaMemsetAsync(scalar_u32(ctx, SC_KD_LISTS), 0, 8 * sizeof(uint32_t), st));
     kd_rows_to_float4_kernel<<<grid_for(n, 256, 8 * kNumSMs), 256, 0, st>>>(d, n, ctx->queries.as<float4>());
     PLS_CHECK_LAUNCH();
     const KdIndex ix = make_index(ctx);

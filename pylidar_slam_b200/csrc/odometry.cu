@@ -27,8 +27,7 @@ namespace {
 __global__ void frame_begin_kernel(FrameResult* fr, const float* T0 /*16, device or null*/, int max_iters,
                                    uint32_t* worklist_counts /*2*/) {
     int t = threadIdx.x;
-    if (t < 2) worklist_counts[t] = 0;
-    if (t >= 3 && t < 11) worklist_counts[t] = 0;  // SC_KD_COUNTERS: the kd search counters of this frame
+    if (t < 16) worklist_counts[t] = 0;  // SC_KD_COUNTERS + SC_KD_LISTS: the kd search's counters and work lists
     if (t < 16) fr->T[t] = T0 ? T0[t] : ((t % 5 == 0) ? 1.f : 0.f);
     if (t < 6) fr->params[t] = 0.f;
     if (t < kMaxAlign) fr->losses[t] = __int_as_float(0x7fc00000);
@@ -203,7 +202,7 @@ int enqueue_icp_iterations(pls_context* ctx, int64_t query_bound, int first, int
 int run_icp(pls_context* ctx, const float* T0_dev, int64_t query_bound) {
     cudaStream_t st = ctx->stream;
     FrameResult* fr = frame_result_dev(ctx);
-    frame_begin_kernel<<<1, kMaxAlign, 0, st>>>(fr, T0_dev, ctx->cfg.max_num_alignments, scalar_u32(ctx, SC_WL0));
+    frame_begin_kernel<<<1, kMaxAlign, 0, st>>>(fr, T0_dev, ctx->cfg.max_num_alignments, scalar_u32(ctx, SC_KD_COUNTERS));
     PLS_CHECK_LAUNCH();
     if (query_bound < 1) query_bound = 1;
     ctx->pm.zbuf_clean = false;  // tmp[3] may have been used by the frame's own projection

@@ -34,6 +34,29 @@ launches)
         python bench.py --quick --steps 3 --warmup 24 > gpurun_out/${TAG}_bench_under_ncu.log 2>&1
     python tools/summarize_launches.py gpurun_out/${TAG}_launches_cfg2.csv 3 > gpurun_out/${TAG}_launches_cfg2_summary.txt 2>&1
     head -40 gpurun_out/${TAG}_launches_cfg2_summary.txt ;;
+ncukd)
+    timeout 300 ncu --set full --clock-control none --import-source on -k regex:'kd_nn_warp_kernel|kd_normals_warp_kernel|kd_residual_kernel' \
+        --launch-skip ${SKIP:-240} --launch-count ${COUNT:-9} -f -o gpurun_out/${TAG}_kd python bench.py --quick --steps 3 --warmup 24 > gpurun_out/${TAG}_ncu_kd.log 2>&1
+    tail -2 gpurun_out/${TAG}_ncu_kd.log
+    ncu -i gpurun_out/${TAG}_kd.ncu-rep --page raw --csv > gpurun_out/${TAG}_kd_raw.csv 2>/dev/null
+    ls -la gpurun_out/${TAG}_kd* ;;
+kdtimes)
+    timeout 200 ncu --metrics gpu__time_duration.sum,sm__cycles_active.avg,smsp__inst_executed.sum --clock-control none -k regex:'kd_|frame_begin' \
+        --launch-skip ${SKIP:-400} --launch-count ${COUNT:-60} --csv --log-file gpurun_out/${TAG}_kdtimes.csv \
+        python bench.py --quick --steps 4 --warmup 24 > gpurun_out/${TAG}_kdtimes.log 2>&1
+    python - <<PY
+import csv
+lines=[l for l in open("gpurun_out/${TAG}_kdtimes.csv") if l.startswith('"')]
+rows=list(csv.DictReader(lines))
+by={}
+for r in rows:
+    by.setdefault(r["ID"],{"name":r["Kernel Name"].split("(")[0].split("::")[-1]})[r["Metric Name"]]=r["Metric Value"]
+for i,v in list(by.items())[:60]:
+    print(v["name"][:28].ljust(28), "us", float(v.get("gpu__time_duration.sum","0").replace(",",""))/1e3, "cyc", v.get("sm__cycles_active.avg"), "inst", v.get("smsp__inst_executed.sum"))
+PY
+    ;;
+stats)
+    PLS_KD_STATS=1 timeout 120 python tools/quick_time.py 30 tensor 2>&1 | tail -6 | tee gpurun_out/${TAG}_kd_stats.log ;;
 quick)
     for rep in 1 2; do
         timeout 120 python bench.py --quick --steps 40 --warmup 24 2>/dev/null | tail -1 | tee -a gpurun_out/${TAG}_quick.log

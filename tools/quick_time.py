@@ -38,5 +38,5 @@ st = (ctypes.c_ulonglong * 16)()
 algo.ctx.call("pls_kdmap_stats", st)
 st = list(st)
 if st[0]:
-    print(f"nn: {st[0]} queries, exact L0/L1/L2 = {st[1]/st[0]:.3f}/{st[2]/st[0]:.3f}/{st[3]/st[0]:.3f}, bvh {st[4]/st[0]:.4f}, cand/query {st[5]/st[0]:.1f}")
-    print(f"knn: {st[6]} queries, exact L0/L1/L2 = {st[7]/max(st[6],1):.3f}/{st[8]/max(st[6],1):.3f}/{st[9]/max(st[6],1):.3f}, bvh {st[10]/max(st[6],1):.4f}, cand/query {st[11]/max(st[6],1):.1f}")
+    print(f"nn: {st[0]} queries, exact at level 0 {st[1]/st[0]:.4f}, coarser levels {st[2]/st[0]:.4f}, cand/query {st[3]/st[0]:.1f}")
+    print(f"knn: {st[4]} queries, exact at level 0 {st[5]/max(st[4],1):.4f}, coarser levels {st[6]/max(st[4],1):.4f}, cand/query {st[7]/max(st[4],1):.1f}")
