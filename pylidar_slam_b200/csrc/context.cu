@@ -305,6 +305,7 @@ int pls_destroy(pls_context* ctx) {
     ctx->sort_map.keys_alt.release(); ctx->sort_map.vals_alt.release(); ctx->sort_map.hist.release();
     ctx->sort_map.status.release(); ctx->sort_map.plan.release();
     ctx->scan.status.release();
+    ctx->sel[0].status.release(); ctx->sel[1].status.release(); ctx->input_zbuf.release();
     for (auto& b : ctx->kd.store) b.release();
     ctx->kd.morton.release(); ctx->kd.order.release(); ctx->kd.sorted.release(); ctx->kd.normals.release();
     ctx->kd.bbox.release(); ctx->kd.grid_hdr.release(); ctx->kd.cells.release(); ctx->kd.stats.release();

@@ -12,6 +12,7 @@
 //                       return_index=True)'s first occurrence (pointcloud.py:177,193).
 //   gather            : sample_points / sample_indices in ascending-hash order.
 #include "internal.cuh"
+#include "select_device.cuh"
 
 namespace pls {
 
@@ -80,6 +81,35 @@ __global__ void gather_samples_kernel(const T* __restrict__ xyz, const uint32_t*
         if (host_idx) host_idx[dst] = (long long)src;
     }
 }
+
+// Run heads of the sorted keys -> samples, in ONE selection pass (select_device.cuh): element i is kept iff its key
+// differs from its predecessor's; the kept element's original index is vals[i].
+template <typename T>
+struct GridSampleSelect {
+    const uint64_t* keys;
+    const uint32_t* vals;
+    const T* xyz;
+    T* out_xyz;
+    long long* out_idx;
+    T* host_xyz;
+    long long* host_idx;
+    struct State {};
+    __device__ __forceinline__ uint32_t flags(int64_t i, State&) const { return (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u; }
+    __device__ __forceinline__ void emit(int64_t i, int, uint32_t dst, const State&) const {
+        const uint32_t src = vals[i];
+        const T x = xyz[3 * (size_t)src], y = xyz[3 * (size_t)src + 1], z = xyz[3 * (size_t)src + 2];
+        if (out_idx) out_idx[dst] = (long long)src;
+        out_xyz[3 * (size_t)dst] = x;
+        out_xyz[3 * (size_t)dst + 1] = y;
+        out_xyz[3 * (size_t)dst + 2] = z;
+        if (host_xyz) {
+            host_xyz[3 * (size_t)dst] = x;
+            host_xyz[3 * (size_t)dst + 1] = y;
+            host_xyz[3 * (size_t)dst + 2] = z;
+        }
+        if (host_idx) host_idx[dst] = (long long)src;
+    }
+};
 
 // ---- voxel statistics (Voxelization filter) ---------------------------------------------------------------
 // After the same hash + stable sort as the subsample: rank of every run of equal hashes = voxel id
@@ -170,6 +200,12 @@ void grid_sample_device(pls_context* ctx, const T* xyz_dev, int64_t n, double vo
     uint64_t* sk;
     uint32_t* sv;
     radix_sort_pairs(ctx, ctx->gs_keys.as<uint64_t>(), ctx->gs_vals.as<uint32_t>(), n, compact ? GS_COMPACT_BITS / 8 : 8, &sk, &sv);
+    if (n <= SEL_MAX_N) {
+        GridSampleSelect<T> op{sk, sv, xyz_dev, out_xyz_dev, out_idx_dev, host_xyz, host_idx};
+        select_launch(ctx, op, n, nullptr, scalar_u32(ctx, SC_GS_COUNT), nullptr);
+        return;
+    }
+    // clouds beyond the single-wave selection: flags, scan, gather
     head_flags_kernel<<<grid_for(n), 256, 0, st>>>(sk, n, ctx->tmp[1].as<uint8_t>());
     PLS_CHECK_LAUNCH();
     exclusive_scan_flags(ctx, ctx->tmp[1].as<uint8_t>(), n, ctx->tmp[2].as<uint32_t>(), scalar_u32(ctx, SC_GS_COUNT));

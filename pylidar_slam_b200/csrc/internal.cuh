@@ -16,7 +16,7 @@ namespace pls {
 constexpr int kNumSMs = 148;  // B200
 constexpr int NACC = 30;      // 21 JtJ upper + 6 Jtr + sum (w r)^2 + sum r^2 + count
 constexpr int kMaxAlign = 128;
-constexpr int kProfileSlots = 6;
+constexpr int kProfileSlots = 16;  // 0-5: kernel families of the bench line; 6-15: single kernels (development)
 constexpr size_t kScalarOffset = 2048;  // FrameResult first, then u32 scalar slots
 
 struct Error {
@@ -88,6 +88,12 @@ struct SortScratch {
 
 struct ScanScratch {
     DBuf status;  // look-back words + tile counter + total
+};
+
+// select_device.cuh: epoch-tagged look-back words of the single-pass selection (one scratch per stream)
+struct SelectScratch {
+    DBuf status;
+    uint32_t epoch = 0;
 };
 
 // ---- the kd local map: point storage + the cell-pyramid search index (kdmap_device.cuh) ---------------------
@@ -165,6 +171,9 @@ struct pls_context {
     pls::SortScratch sort;
     pls::SortScratch sort_map;          // radix-sort scratch of the map-update stream
     pls::ScanScratch scan;
+    pls::SelectScratch sel[2];          // [0] main stream, [1] map-update stream
+    pls::DBuf input_zbuf;               // z-buffer of the frame-input stage (kept all-empty between frames by its consumers)
+    bool input_zbuf_clean = false;
 
     // generic scratch
     pls::DBuf tmp[8];
@@ -314,6 +323,10 @@ void launch_projection(pls_context* ctx, const float* xyz, const float* channels
 // rounded to float32 at the end (what the reference does with a float64 input, icp_odometry.py:331-352)
 void launch_projection_f64(pls_context* ctx, const double* xyz, int64_t n, int H, int W, float up, float down, float* out,
                            unsigned long long* zbuf);
+// z-buffer pass only (no resolve): one 64-bit atomicMin of (range bits << 32 | point index) per point; n_dev (nullable)
+// is a device-side point count overriding n.  The buffer must hold ~0 in every pixel beforehand.
+void launch_zbuf_points(pls_context* ctx, const float* xyz, int64_t n, const uint32_t* n_dev, int H, int W, float up, float down,
+                        unsigned long long* zbuf);
 // normal_map.cu
 void launch_normal_map(pls_context* ctx, const float* vmap, int batch, int H, int W, int ksize, float* out);
 // gn.cu

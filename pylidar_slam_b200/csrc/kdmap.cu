@@ -264,6 +264,23 @@ __device__ __forceinline__ bool claim_normal(const KdIndex& ix, int pos) {
     return cur != valid && cur != claimed && atomicCAS(w, cur, claimed) == cur;
 }
 
+// Development switch (PLS_KD_FAST=0): every query goes to the warp-cooperative path.
+__global__ void kd_all_hard_kernel(const uint32_t* __restrict__ nq_dev, int64_t q_begin, int64_t q_stride, const int* __restrict__ done,
+                                   int* __restrict__ match, int keep_match, int* __restrict__ hard, uint32_t* lists, int parity) {
+    if (done && *done) return;
+    const int64_t nq = (int64_t)*nq_dev;
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s == 0)
+        for (int l = 0; l < KDL_WORDS; l += 2) lists[l + (parity ^ 1)] = 0;
+    const int64_t qi = q_begin + s * q_stride;
+    if (qi < nq) {
+        hard[s] = (int)qi;
+        if (!keep_match) match[qi] = -1;
+    }
+    const int64_t mine = nq > q_begin ? (nq - q_begin + q_stride - 1) / q_stride : 0;
+    if (s == 0) lists[KDL_HARD_NN + parity] = (uint32_t)mine;
+}
+
 // 1-NN, fast path: a thread per query (thread_nearest).  Proven matches claim their normal; unproven ones are queued
 // for the warp-cooperative search (their best candidate so far is left in match[] as its bound).
 __global__ void __launch_bounds__(KD_THREADS)
@@ -806,24 +823,39 @@ static void launch_search(pls_context* ctx, const KdIndex& ix, const float4* que
     static const int resident_nn = resident_blocks((const void*)kd_nn_warp_kernel);
     static const int resident_kn = resident_blocks((const void*)kd_normals_warp_kernel);
     int wblocks = (int)((mine + KD_WARPS - 1) / KD_WARPS);
-    kd_nn_thread_kernel<<<tblocks, KD_THREADS, 0, st>>>(ix, queries, nq_dev, (int64_t)rank, (int64_t)num_ranks, T, done, match,
-                                                        use_hint ? 1 : 0, normals ? 1 : 0, pending, hard_nn, lists, parity, counters);
-    PLS_CHECK_LAUNCH();
-    kd_nn_warp_kernel<<<wblocks < resident_nn ? wblocks : resident_nn, KD_THREADS, 0, st>>>(
-        ix, queries, hard_nn, lists + KDL_HARD_NN + parity, T, done, match, normals ? 1 : 0, pending, lists + KDL_PENDING + parity,
-        counters);
-    PLS_CHECK_LAUNCH();
+    static const int fast = getenv("PLS_KD_FAST") ? atoi(getenv("PLS_KD_FAST")) : 3;  // bit 0: 1-NN fast path, bit 1: k-NN fast path
+    {
+        ProfileScope p6(ctx, 6, 0.0);
+        if (fast & 1) {
+            kd_nn_thread_kernel<<<tblocks, KD_THREADS, 0, st>>>(ix, queries, nq_dev, (int64_t)rank, (int64_t)num_ranks, T, done, match,
+                                                                use_hint ? 1 : 0, normals ? 1 : 0, pending, hard_nn, lists, parity,
+                                                                counters);
+        } else {
+            kd_all_hard_kernel<<<tblocks, KD_THREADS, 0, st>>>(nq_dev, (int64_t)rank, (int64_t)num_ranks, done, match, use_hint ? 1 : 0,
+                                                               hard_nn, lists, parity);
+        }
+        PLS_CHECK_LAUNCH();
+    }
+    {
+        ProfileScope p7(ctx, 7, 0.0);
+        kd_nn_warp_kernel<<<wblocks < resident_nn ? wblocks : resident_nn, KD_THREADS, 0, st>>>(
+            ix, queries, hard_nn, lists + KDL_HARD_NN + parity, T, done, match, normals ? 1 : 0, pending, lists + KDL_PENDING + parity,
+            counters);
+        PLS_CHECK_LAUNCH();
+    }
     if (!normals) return;
     const int k = ctx->cfg.num_neighbors_normals;
     const int* exact_list = pending;
     const uint32_t* exact_count = lists + KDL_PENDING + parity;
-    if (k == 10) {
+    if (k == 10 && (fast & 2)) {
+        ProfileScope p8(ctx, 8, 0.0);
         kd_normals_thread_kernel<<<tblocks, KD_THREADS, 0, st>>>(ix, pending, lists + KDL_PENDING + parity, done, hard_knn,
                                                                  lists + KDL_HARD_KNN + parity, counters);
         PLS_CHECK_LAUNCH();
         exact_list = hard_knn;
         exact_count = lists + KDL_HARD_KNN + parity;
     }
+    ProfileScope p9(ctx, 9, 0.0);
     kd_normals_warp_kernel<<<wblocks < resident_kn ? wblocks : resident_kn, KD_THREADS, 0, st>>>(ix, k, exact_list, exact_count, done,
                                                                                                  counters);
     PLS_CHECK_LAUNCH();
@@ -845,6 +877,7 @@ int kdmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int num
                   it & 1);
     const int blocks = grid_for(mine, KD_RES_THREADS, 8 * kNumSMs);
     ctx->partials.reserve((size_t)blocks * NACC * sizeof(double), st);
+    ProfileScope p10(ctx, 10, 0.0);
     kd_residual_kernel<<<blocks, KD_RES_THREADS, 0, st>>>(ix, ctx->query_ptr, nq_dev, (int64_t)rank, (int64_t)num_ranks, fr,
                                                           ctx->cfg.scheme, ctx->cfg.sigma, ctx->nn_prev.as<int>(),
                                                           ctx->partials.as<double>(), fuse_threshold);

@@ -10,6 +10,8 @@
 #include "internal.cuh"
 #include "icp_device.cuh"
 #include "pose_device.cuh"
+#include "projection_device.cuh"
+#include "select_device.cuh"
 
 namespace pls {
 
@@ -153,6 +155,52 @@ __global__ void first_point_kernel(const float4* __restrict__ packed, const uint
         *out_count = c > 0 ? 1u : 0u;
     }
 }
+
+// _read_input + sample_points of a float32 point layout on the kd map after frame 0, in one selection pass over the
+// input rows (select_device.cuh): the NaN-free rows (utils.py:169-184) are packed as float4 -- the points the map
+// update inserts -- and, when the queries are the non-null pixels of the cloud's vertex map (icp_odometry.py:303-305),
+// the rows that won their pixel of the z-buffer (closest point, lowest index on ties: projection.py:393-415) are packed
+// as the queries.  The vertex map itself is never materialised: its non-null pixels ARE the winners.  (The queries come
+// out in input order rather than pixel order; the reduction over them is order-independent up to fp64 rounding.)
+// Each winner also resets its pixel, which leaves the z-buffer empty for the next frame.
+struct FrameInputSelect {
+    const float* pts;
+    ProjConst pc;
+    unsigned long long* zbuf;   // null: no query selection (queries = the valid rows)
+    float4* frame_pts;
+    float4* queries;
+    struct State {
+        float x, y, z;
+        int pix;
+    };
+    __device__ __forceinline__ uint32_t flags(int64_t i, State& s) const {
+        s.x = pts[3 * i];
+        s.y = pts[3 * i + 1];
+        s.z = pts[3 * i + 2];
+        s.pix = -1;
+        const bool valid = s.x == s.x && s.y == s.y && s.z == s.z;
+        if (!valid) return 0u;
+        uint32_t f = 1u;
+        if (zbuf) {
+            int pix;
+            float r;
+            if (project_to_pixel(s.x, s.y, s.z, pc, pix, r) &&
+                zbuf[pix] == (((unsigned long long)__float_as_uint(r) << 32) | (unsigned long long)(uint32_t)i)) {
+                s.pix = pix;
+                f |= 2u;
+            }
+        }
+        return f;
+    }
+    __device__ __forceinline__ void emit(int64_t, int which, uint32_t pos, const State& s) const {
+        if (which == 0) {
+            frame_pts[pos] = make_float4(s.x, s.y, s.z, 0.f);
+        } else {
+            queries[pos] = make_float4(s.x, s.y, s.z, 0.f);
+            zbuf[s.pix] = ~0ull;
+        }
+    }
+};
 
 inline int grid_for(int64_t n, int threads = 256) {
     int64_t b = (n + threads - 1) / threads;
@@ -303,6 +351,7 @@ void process_frame_device(pls_context* ctx, const void* data_void, int layout, i
     // ---- _read_input (icp_odometry.py:319-358)
     frame_vmap.reserve((size_t)3 * hw * sizeof(float), st);
     int64_t pts_bound = 0;
+    bool fused_input = false;
     if (layout == PLS_INPUT_VERTEX_MAP) {
         scrub_vertex_map_kernel<<<grid_for(hw), 256, 0, st>>>(data_dev, hw, frame_vmap.as<float>());
         PLS_CHECK_LAUNCH();
@@ -316,12 +365,39 @@ void process_frame_device(pls_context* ctx, const void* data_void, int layout, i
     } else {
         PLS_REQUIRE(n > 0, "process_frame: empty point cloud");
         frame_pts.reserve((size_t)n * sizeof(float4), st);
-        if (is64) pack_valid_rows_f64(ctx, data64, n, frame_pts.as<float4>(), count_slot(ctx, 2));
-        else pack_valid_rows(ctx, data_dev, n, frame_pts.as<float4>(), count_slot(ctx, 2));
         pts_bound = n;
+        // the shipped pipelines (float32 points, kd map, any frame but the first): one z-buffer pass and one selection
+        fused_input = !is64 && kd && !first && n <= SEL_MAX_N && n < (1ll << 32);
+        if (fused_input) {
+            const bool pixel_queries = !ctx->sample_pointcloud;
+            FrameInputSelect op;
+            op.pts = data_dev;
+            op.pc = make_proj_const(H, W, ctx->cfg.up_fov_deg, ctx->cfg.down_fov_deg);
+            op.zbuf = nullptr;
+            op.frame_pts = frame_pts.as<float4>();
+            op.queries = nullptr;
+            if (pixel_queries) {
+                if (ctx->input_zbuf.cap < (size_t)hw * sizeof(unsigned long long)) ctx->input_zbuf_clean = false;
+                ctx->input_zbuf.reserve((size_t)hw * sizeof(unsigned long long), st);
+                if (!ctx->input_zbuf_clean)
+                    PLS_CUDA(cudaMemsetAsync(ctx->input_zbuf.p, 0xff, (size_t)hw * sizeof(unsigned long long), st));
+                ctx->input_zbuf_clean = false;  // dirty until the selection below (whose winners reset their pixels) is enqueued
+                ctx->queries.reserve((size_t)(n < hw ? n : hw) * sizeof(float4), st);
+                launch_zbuf_points(ctx, data_dev, n, nullptr, H, W, ctx->cfg.up_fov_deg, ctx->cfg.down_fov_deg,
+                                   ctx->input_zbuf.as<unsigned long long>());
+                op.zbuf = ctx->input_zbuf.as<unsigned long long>();
+                op.queries = ctx->queries.as<float4>();
+            }
+            select_launch(ctx, op, n, nullptr, count_slot(ctx, 2), pixel_queries ? count_slot(ctx, 1) : nullptr);
+            if (pixel_queries) ctx->input_zbuf_clean = true;
+        } else if (is64) {
+            pack_valid_rows_f64(ctx, data64, n, frame_pts.as<float4>(), count_slot(ctx, 2));
+        } else {
+            pack_valid_rows(ctx, data_dev, n, frame_pts.as<float4>(), count_slot(ctx, 2));
+        }
         // the vertex map of the points is needed on frame 0 (map initialisation), as the query
         // source when _sample_pointcloud is False, and by the projective map's update
-        if (first || !ctx->sample_pointcloud || !kd) {
+        if (!fused_input && (first || !ctx->sample_pointcloud || !kd)) {
             ctx->tmp[3].reserve((size_t)hw * sizeof(unsigned long long), st);
             if (is64)
                 launch_projection_f64(ctx, data64, n, H, W, ctx->cfg.up_fov_deg, ctx->cfg.down_fov_deg, frame_vmap.as<float>(),
@@ -364,6 +440,9 @@ void process_frame_device(pls_context* ctx, const void* data_void, int layout, i
     } else if (layout == PLS_INPUT_VERTEX_MAP) {
         ctx->query_ptr = ctx->tmp[5].as<float4>();
         query_bound = hw;
+    } else if (fused_input) {
+        ctx->query_ptr = ctx->queries.as<float4>();  // selected together with the valid rows above
+        query_bound = n < hw ? n : hw;
     } else {
         ctx->queries.reserve((size_t)hw * sizeof(float4), st);
         pack_nonnull_pixels(ctx, frame_vmap.as<float>(), hw, ctx->queries.as<float4>(), count_slot(ctx, 1));

@@ -42,6 +42,17 @@ __global__ void zbuf_kernel(const float* __restrict__ xyz, int batch, int64_t n,
     }
 }
 
+__global__ void zbuf_points_kernel(const float* __restrict__ xyz, int64_t n, const uint32_t* __restrict__ n_dev, ProjConst pc,
+                                   unsigned long long* __restrict__ zbuf) {
+    if (n_dev) n = min(n, (int64_t)*n_dev);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int pix;
+        float r;
+        if (project_to_pixel(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], pc, pix, r))
+            atomicMin(&zbuf[pix], ((unsigned long long)__float_as_uint(r) << 32) | (unsigned long long)(uint32_t)i);
+    }
+}
+
 __global__ void resolve_kernel(const unsigned long long* __restrict__ zbuf, const float* __restrict__ values,
                                int batch, int64_t n, int C, int64_t hw, float* __restrict__ out) {
     const int64_t total = (int64_t)batch * hw;
@@ -138,6 +149,13 @@ void launch_projection(pls_context* ctx, const float* xyz, const float* channels
         PLS_CHECK_LAUNCH();
     }
     resolve_kernel<<<grid_for((int64_t)batch * hw), 256, 0, st>>>(zbuf, channels ? channels : xyz, batch, n, C, hw, out);
+    PLS_CHECK_LAUNCH();
+}
+
+void launch_zbuf_points(pls_context* ctx, const float* xyz, int64_t n, const uint32_t* n_dev, int H, int W, float up, float down,
+                        unsigned long long* zbuf) {
+    PLS_REQUIRE(n > 0 && n < (1ll << 32), "projection: 1 .. 2^32 points per cloud");
+    zbuf_points_kernel<<<grid_for(n), 256, 0, ctx->stream>>>(xyz, n, n_dev, make_proj_const(H, W, up, down), zbuf);
     PLS_CHECK_LAUNCH();
 }
 
