@@ -309,7 +309,7 @@ int pls_destroy(pls_context* ctx) {
     for (auto& b : ctx->kd.store) b.release();
     ctx->kd.morton.release(); ctx->kd.order.release(); ctx->kd.sorted.release(); ctx->kd.normals.release();
     ctx->kd.bbox.release(); ctx->kd.grid_hdr.release(); ctx->kd.cells.release(); ctx->kd.stats.release();
-    ctx->kd_worklist.release();
+    ctx->kd_worklist.release(); ctx->kd_nn_state.release();
     ctx->pm.vmaps.release(); ctx->pm.nmaps.release(); ctx->pm.poses.release();
     ctx->pm.model_v.release(); ctx->pm.model_n.release(); ctx->pm.zbuf.release();
     for (auto& b : ctx->frame_vmap_buf) b.release();

@@ -194,7 +194,8 @@ struct pls_context {
     pls::DBuf queries;                  // float4 queries P0 (owned storage)
     const float4* query_ptr = nullptr;  // the queries of the current frame (may alias frame_pts)
     pls::DBuf nn_prev;                  // previous-iteration match per query
-    pls::DBuf kd_worklist;              // map points whose normal the current iteration has to compute
+    pls::DBuf kd_worklist;              // map points whose normal the current iteration has to compute; queued queries
+    pls::DBuf kd_nn_state;              // per query: position at its last full search + runner-up bound (float4)
     pls::DBuf partials;                 // [blocks][NACC] doubles
     pls::DBuf gs_keys, gs_vals, gs_out_xyz, gs_out_idx;
     uint32_t gs_seq = 0;                // stamp of the last compact-key grid sample (overflow detection)

@@ -229,12 +229,12 @@ __global__ void kd_export_kernel(const float4* __restrict__ pts, int64_t n, floa
 
 // ---- one ICP iteration on the kd map (icp_odometry.py:275-284 + alignment.py:91-127 at x0 = 0) -----------------------
 //   p = T p0; q = NN(p); n = normal(q); r = n.(p - q); J = [n, p x n]; w; reduce        -- three launches:
-//   kd_nn_thread_kernel / kd_nn_warp_kernel            transform, exact 1-NN -> match[qi]: a thread per query proves
-//                           the easy ones inside the 3x3x3 level-0 block, a warp per remaining query searches the
-//                           pyramid; the first to match a map point whose normal is not cached claims it (CAS on the
-//                           state word) and queues it (block- / warp-aggregated appends)
-//   kd_normals_thread_kernel / kd_normals_warp_kernel  exact (k+1)-NN of every queued map point, second moments,
-//                           eigen-solve: a thread per point inside the 5x5x5 block, a warp per remaining point
+//   kd_nn_verify_kernel     (iterations after a frame's first) a thread per query proves that its previous match is
+//                           still the nearest neighbour; the unproven ones are queued
+//   kd_nn_warp_kernel       transform, exact 1-NN -> match[qi] for every query (first iteration) or the queued ones: a
+//                           warp per query over the cell pyramid; the first to match a map point whose normal is not
+//                           cached claims it (CAS on the state word) and queues it (warp-aggregated appends)
+//   kd_normals_warp_kernel  exact (k+1)-NN of every queued map point, second moments, lane-parallel eigen-solves
 //   kd_residual_kernel      a thread per query: r, J, robust weight, the 30 fp64 accumulators -> block partials; the
 //                           last block sums them in fixed order and runs the solve / stop test / pose update
 constexpr int KD_THREADS = 256;
@@ -246,7 +246,7 @@ enum { KDC_NN_CAND = 0, KDC_KNN_CAND = 1, KDC_NORMALS = 2 };
 // per-iteration work-list counters (u32 words at SC_KD_LISTS), one pair per list, indexed by the iteration's parity:
 // the first kernel of iteration `it` zeroes the words of parity (it + 1) & 1 -- consumed by the previous iteration,
 // filled by the next -- so no list is ever reset by a separate launch
-enum { KDL_PENDING = 0, KDL_HARD_NN = 2, KDL_HARD_KNN = 4, KDL_WORDS = 6 };
+enum { KDL_PENDING = 0, KDL_HARD_NN = 2, KDL_WORDS = 4 };
 
 // Appends this block's entries (collected in shared memory by any of its threads) to a global list: one atomic per block.
 __device__ __forceinline__ void block_flush_list(const int* s_list, int n, int* __restrict__ list, uint32_t* count, int* s_base) {
@@ -264,76 +264,66 @@ __device__ __forceinline__ bool claim_normal(const KdIndex& ix, int pos) {
     return cur != valid && cur != claimed && atomicCAS(w, cur, claimed) == cur;
 }
 
-// Development switch (PLS_KD_FAST=0): every query goes to the warp-cooperative path.
-__global__ void kd_all_hard_kernel(const uint32_t* __restrict__ nq_dev, int64_t q_begin, int64_t q_stride, const int* __restrict__ done,
-                                   int* __restrict__ match, int keep_match, int* __restrict__ hard, uint32_t* lists, int parity) {
-    if (done && *done) return;
-    const int64_t nq = (int64_t)*nq_dev;
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s == 0)
-        for (int l = 0; l < KDL_WORDS; l += 2) lists[l + (parity ^ 1)] = 0;
-    const int64_t qi = q_begin + s * q_stride;
-    if (qi < nq) {
-        hard[s] = (int)qi;
-        if (!keep_match) match[qi] = -1;
-    }
-    const int64_t mine = nq > q_begin ? (nq - q_begin + q_stride - 1) / q_stride : 0;
-    if (s == 0) lists[KDL_HARD_NN + parity] = (uint32_t)mine;
-}
-
-// 1-NN, fast path: a thread per query (thread_nearest).  Proven matches claim their normal; unproven ones are queued
-// for the warp-cooperative search (their best candidate so far is left in match[] as its bound).
+// 1-NN of ICP iterations after a frame's first: VERIFY instead of searching.  The full search stored, per query, where
+// the query stood (its transformed position) and a lower bound of the distance to every map point other than its match.
+// If the query has moved by eps since then and its match is now at distance d, every other point is still at least
+// (bound - eps) away, so d + eps < bound proves the match unchanged -- one point load and a dozen flops per query.
+// The few queries that cannot be proven are queued for the full search.
 __global__ void __launch_bounds__(KD_THREADS)
-kd_nn_thread_kernel(KdIndex ix, const float4* __restrict__ queries, const uint32_t* __restrict__ nq_dev, int64_t q_begin,
-                    int64_t q_stride, const float* __restrict__ T, const int* __restrict__ done, int* __restrict__ match,
-                    int use_hint, int want_normals, int* __restrict__ pending, int* __restrict__ hard, uint32_t* lists,
-                    int parity, unsigned long long* __restrict__ counters) {
+kd_nn_verify_kernel(KdIndex ix, const float4* __restrict__ queries, const uint32_t* __restrict__ nq_dev, int64_t q_begin,
+                    int64_t q_stride, const float* __restrict__ T, const int* __restrict__ done, const int* __restrict__ match,
+                    const float4* __restrict__ nn_state, int* __restrict__ hard, uint32_t* lists, int parity) {
     if (done && *done) return;
     __shared__ float sT[12];
-    __shared__ int s_pending[KD_THREADS], s_hard[KD_THREADS];
-    __shared__ int s_np, s_nh, s_cand, s_base;
+    __shared__ int s_hard[KD_THREADS];
+    __shared__ int s_nh, s_base;
     if (threadIdx.x < 12) sT[threadIdx.x] = T[threadIdx.x];
     if (threadIdx.x == 0) {
-        s_np = 0;
         s_nh = 0;
-        s_cand = 0;
         if (blockIdx.x == 0)
             for (int l = 0; l < KDL_WORDS; l += 2) lists[l + (parity ^ 1)] = 0;
     }
     __syncthreads();
     const int64_t nq = (int64_t)*nq_dev;
     const int64_t qi = q_begin + ((int64_t)blockIdx.x * KD_THREADS + threadIdx.x) * q_stride;
-    int cand = 0;
     if (qi < nq) {
-        const KdGridLocal g = kd_load_grid(ix);
         const float4 p0 = queries[qi];
         const float px = p0.x * sT[0] + p0.y * sT[1] + p0.z * sT[2] + sT[3];
         const float py = p0.x * sT[4] + p0.y * sT[5] + p0.z * sT[6] + sT[7];
         const float pz = p0.x * sT[8] + p0.y * sT[9] + p0.z * sT[10] + sT[11];
-        bool exact;
-        const int pos = thread_nearest(ix, g, px, py, pz, use_hint ? match[qi] : -1, exact, cand);
-        match[qi] = pos;
-        if (!exact) s_hard[atomicAdd(&s_nh, 1)] = (int)qi;
-        else if (want_normals && claim_normal(ix, pos)) s_pending[atomicAdd(&s_np, 1)] = pos;
+        const int pos = match[qi];
+        bool proven = false;
+        if (pos >= 0) {
+            const float4 s = nn_state[qi];
+            const float d = sqrtf(dist2_point(px, py, pz, __ldg(ix.sorted + pos)));
+            const float eps = sqrtf(dist2_point(px, py, pz, s));
+            proven = (d + eps) * 1.00001f + 1e-6f < sqrtf(s.w);
+        }
+        if (!proven) s_hard[atomicAdd(&s_nh, 1)] = (int)qi;
     }
-    // candidates tested: warp sum, then one shared atomic per warp
-    cand = __reduce_add_sync(FULL, cand);
-    if ((threadIdx.x & 31) == 0 && cand) atomicAdd(&s_cand, cand);
     __syncthreads();
-    if (threadIdx.x == 0 && counters && s_cand) atomicAdd(counters + KDC_NN_CAND, (unsigned long long)s_cand);
     block_flush_list(s_hard, s_nh, hard, lists + KDL_HARD_NN + parity, &s_base);
-    __syncthreads();
-    block_flush_list(s_pending, s_np, pending, lists + KDL_PENDING + parity, &s_base);
 }
 
-// 1-NN, exact path for the queued queries: a warp per query searches the cell pyramid (warp_nearest), seeded with the
-// fast path's candidate.  Claims are made by all lanes at once after a warp's queries are done.
+// 1-NN, full search: a warp per query over the cell pyramid (warp_nearest).  hard == nullptr: every query of this
+// rank's shard (a frame's first iteration); else the queued ones, seeded with their previous match.  The first warp to
+// match a map point whose normal is not cached claims it (CAS on the state word) and queues it; claims are made by all
+// lanes at once after 32 queries.  Each query's position and runner-up bound are kept for the later iterations' checks.
 __global__ void __launch_bounds__(KD_THREADS)
-kd_nn_warp_kernel(KdIndex ix, const float4* __restrict__ queries, const int* __restrict__ hard, const uint32_t* __restrict__ hard_count,
-                  const float* __restrict__ T, const int* __restrict__ done, int* __restrict__ match, int want_normals,
-                  int* __restrict__ pending, uint32_t* pending_count, unsigned long long* __restrict__ counters) {
+kd_nn_warp_kernel(KdIndex ix, const float4* __restrict__ queries, const uint32_t* __restrict__ nq_dev, int64_t q_begin,
+                  int64_t q_stride, const int* __restrict__ hard, uint32_t* lists, int parity, const float* __restrict__ T,
+                  const int* __restrict__ done, int* __restrict__ match, float4* __restrict__ nn_state, int want_normals,
+                  int* __restrict__ pending, unsigned long long* __restrict__ counters) {
     if (done && *done) return;
-    const int n = (int)*hard_count;
+    int n;
+    if (hard) {
+        n = (int)lists[KDL_HARD_NN + parity];
+    } else {
+        const int64_t nq = (int64_t)*nq_dev;
+        n = nq > q_begin ? (int)((nq - q_begin + q_stride - 1) / q_stride) : 0;
+        if (blockIdx.x == 0 && threadIdx.x == 0)  // first kernel of the iteration: recycle the other parity's lists
+            for (int l = 0; l < KDL_WORDS; l += 2) lists[l + (parity ^ 1)] = 0;
+    }
     const int lane = threadIdx.x & 31;
     const int warp_global = blockIdx.x * KD_WARPS + (threadIdx.x >> 5);
     const int total_warps = gridDim.x * KD_WARPS;
@@ -342,6 +332,7 @@ kd_nn_warp_kernel(KdIndex ix, const float4* __restrict__ queries, const int* __r
 #pragma unroll
     for (int a = 0; a < 12; ++a) t[a] = T[a];
     const KdGridLocal g = kd_load_grid(ix);
+    uint32_t* pending_count = lists + KDL_PENDING + parity;
     int my_pos = -1, held = 0, cand = 0;
     auto flush_claims = [&]() {
         const bool mine = want_normals && my_pos >= 0 && claim_normal(ix, my_pos);
@@ -355,75 +346,44 @@ kd_nn_warp_kernel(KdIndex ix, const float4* __restrict__ queries, const int* __r
         my_pos = -1;
         held = 0;
     };
-    for (int s = warp_global; s < n; s += total_warps) {
-        const int qi = hard[s];
-        const float4 p0 = queries[qi];
+    // the next query's data is fetched while this one is searched
+    int s = warp_global;
+    int64_t qi = hard ? (int64_t)hard[s] : q_begin + (int64_t)s * q_stride;
+    float4 p0 = queries[qi];
+    int hint = hard ? match[qi] : -1;
+    while (true) {
+        const int sn = s + total_warps;
+        int64_t qn = qi;
+        float4 pn = p0;
+        int hn = -1;
+        if (sn < n) {
+            qn = hard ? (int64_t)hard[sn] : q_begin + (int64_t)sn * q_stride;
+            pn = queries[qn];
+            if (hard) hn = match[qn];
+        }
         const float px = p0.x * t[0] + p0.y * t[1] + p0.z * t[2] + t[3];
         const float py = p0.x * t[4] + p0.y * t[5] + p0.z * t[6] + t[7];
         const float pz = p0.x * t[8] + p0.y * t[9] + p0.z * t[10] + t[11];
-        const int pos = warp_nearest(ix, g, px, py, pz, match[qi], lane, &cand);
-        if (lane == 0) match[qi] = pos;
+        float second;
+        const int pos = warp_nearest(ix, g, px, py, pz, hint, lane, &cand, &second);
+        if (lane == 0) {
+            match[qi] = pos;
+            if (nn_state) nn_state[qi] = make_float4(px, py, pz, second);
+        }
         if (lane == held) my_pos = pos;
         if (++held == 32) flush_claims();
+        if (sn >= n) break;
+        s = sn;
+        qi = qn;
+        p0 = pn;
+        hint = hn;
     }
     flush_claims();
     if (counters && lane == 0 && cand) atomicAdd(counters + KDC_NN_CAND, (unsigned long long)cand);
 }
 
-// Normals, fast path: a thread per queued map point (thread_knn: 3x3x3 block, then the pruned 5x5x5 shell), second
-// moments and the eigen-solve -- 32 independent points per warp.  Points whose K-th neighbour cannot be proven inside
-// the 5x5x5 block are queued for the warp-cooperative search.
-__global__ void __launch_bounds__(KD_THREADS)
-kd_normals_thread_kernel(KdIndex ix, const int* __restrict__ pending, const uint32_t* __restrict__ pending_count,
-                         const int* __restrict__ done, int* __restrict__ hard, uint32_t* hard_count,
-                         unsigned long long* __restrict__ counters) {
-    if (done && *done) return;
-    __shared__ int s_hard[KD_THREADS];
-    __shared__ int s_nh, s_cand, s_done, s_base;
-    const int n = (int)*pending_count;
-    if ((int)(blockIdx.x * KD_THREADS) >= n) return;
-    if (threadIdx.x == 0) {
-        s_nh = 0;
-        s_cand = 0;
-        s_done = 0;
-    }
-    __syncthreads();
-    const int e = blockIdx.x * KD_THREADS + threadIdx.x;
-    int cand = 0, solved = 0;
-    if (e < n) {
-        const KdGridLocal g = kd_load_grid(ix);
-        const int pos = pending[e];
-        const float4 c = __ldg(ix.sorted + pos);
-        KBest<11> L;
-        bool exact;
-        thread_knn<11>(ix, g, c.x, c.y, c.z, L, exact, cand);
-        if (exact) {
-            float cov[6], nn[3];
-            thread_moments<11>(ix, c, L, cov);
-            smallest_eigenvector(cov, nn);
-            __stcg(ix.normals + pos, make_float4(nn[0], nn[1], nn[2], __uint_as_float(kd_normal_valid(ix.gen))));
-            solved = 1;
-        } else {
-            s_hard[atomicAdd(&s_nh, 1)] = pos;
-        }
-    }
-    cand = __reduce_add_sync(FULL, cand);
-    solved = __reduce_add_sync(FULL, solved);
-    if ((threadIdx.x & 31) == 0) {
-        if (cand) atomicAdd(&s_cand, cand);
-        if (solved) atomicAdd(&s_done, solved);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && counters) {
-        if (s_cand) atomicAdd(counters + KDC_KNN_CAND, (unsigned long long)s_cand);
-        if (s_done) atomicAdd(counters + KDC_NORMALS, (unsigned long long)s_done);
-    }
-    block_flush_list(s_hard, s_nh, hard, hard_count, &s_base);
-}
-
-// Normals, exact path for the queued points (or for every pending point when k != 10): a warp per point, exact
-// (k+1)-NN over the cell pyramid (warp_knn), second moments; the eigen-solves are deferred and run lane-parallel
-// (each lane one point) so that no warp idles behind a serial solve.
+// Normals: a warp per queued map point, exact (k+1)-NN over the cell pyramid (warp_knn), second moments; the
+// eigen-solves are deferred and run lane-parallel (each lane one point) so that no warp idles behind a serial solve.
 __global__ void __launch_bounds__(KD_THREADS)
 kd_normals_warp_kernel(KdIndex ix, int k_normals, const int* __restrict__ worklist, const uint32_t* __restrict__ wl_count,
                        const int* __restrict__ done, unsigned long long* __restrict__ counters) {
@@ -806,58 +766,41 @@ static unsigned long long* kd_counters(pls_context* ctx) {
     return reinterpret_cast<unsigned long long*>(scalar_u32(ctx, SC_KD_COUNTERS));
 }
 
-// The search of one ICP iteration (or of one fine-grained API call): thread-per-query fast paths over compacted work
-// lists, each followed by its warp-cooperative exact path for the queries it could not prove.
+// The search of one ICP iteration (or of one fine-grained API call).  first: every query is searched; later iterations
+// first verify the previous matches and search only the unproven ones.
 static void launch_search(pls_context* ctx, const KdIndex& ix, const float4* queries, const uint32_t* nq_dev, int64_t mine,
-                          int rank, int num_ranks, const float* T, const int* done, int* match, bool use_hint, bool normals,
+                          int rank, int num_ranks, const float* T, const int* done, int* match, bool first, bool normals,
                           int parity) {
     cudaStream_t st = ctx->stream;
     const size_t slots = (size_t)mine + 64;
-    ctx->kd_worklist.reserve(3 * slots * sizeof(int), st);
+    ctx->kd_worklist.reserve(2 * slots * sizeof(int), st);
+    ctx->kd_nn_state.reserve(slots * (size_t)num_ranks * sizeof(float4), st);  // indexed by query, not by shard slot
     int* pending = ctx->kd_worklist.as<int>();
     int* hard_nn = pending + slots;
-    int* hard_knn = hard_nn + slots;
+    float4* nn_state = ctx->kd_nn_state.as<float4>();
     uint32_t* lists = scalar_u32(ctx, SC_KD_LISTS);
     unsigned long long* counters = kd_counters(ctx);
     const int tblocks = (int)((mine + KD_THREADS - 1) / KD_THREADS);
     static const int resident_nn = resident_blocks((const void*)kd_nn_warp_kernel);
     static const int resident_kn = resident_blocks((const void*)kd_normals_warp_kernel);
-    int wblocks = (int)((mine + KD_WARPS - 1) / KD_WARPS);
-    static const int fast = getenv("PLS_KD_FAST") ? atoi(getenv("PLS_KD_FAST")) : 3;  // bit 0: 1-NN fast path, bit 1: k-NN fast path
-    {
+    const int wblocks = (int)((mine + KD_WARPS - 1) / KD_WARPS);
+    if (!first) {
         ProfileScope p6(ctx, 6, 0.0);
-        if (fast & 1) {
-            kd_nn_thread_kernel<<<tblocks, KD_THREADS, 0, st>>>(ix, queries, nq_dev, (int64_t)rank, (int64_t)num_ranks, T, done, match,
-                                                                use_hint ? 1 : 0, normals ? 1 : 0, pending, hard_nn, lists, parity,
-                                                                counters);
-        } else {
-            kd_all_hard_kernel<<<tblocks, KD_THREADS, 0, st>>>(nq_dev, (int64_t)rank, (int64_t)num_ranks, done, match, use_hint ? 1 : 0,
-                                                               hard_nn, lists, parity);
-        }
+        kd_nn_verify_kernel<<<tblocks, KD_THREADS, 0, st>>>(ix, queries, nq_dev, (int64_t)rank, (int64_t)num_ranks, T, done, match,
+                                                            nn_state, hard_nn, lists, parity);
         PLS_CHECK_LAUNCH();
     }
     {
         ProfileScope p7(ctx, 7, 0.0);
         kd_nn_warp_kernel<<<wblocks < resident_nn ? wblocks : resident_nn, KD_THREADS, 0, st>>>(
-            ix, queries, hard_nn, lists + KDL_HARD_NN + parity, T, done, match, normals ? 1 : 0, pending, lists + KDL_PENDING + parity,
-            counters);
+            ix, queries, nq_dev, (int64_t)rank, (int64_t)num_ranks, first ? nullptr : hard_nn, lists, parity, T, done, match, nn_state,
+            normals ? 1 : 0, pending, counters);
         PLS_CHECK_LAUNCH();
     }
     if (!normals) return;
-    const int k = ctx->cfg.num_neighbors_normals;
-    const int* exact_list = pending;
-    const uint32_t* exact_count = lists + KDL_PENDING + parity;
-    if (k == 10 && (fast & 2)) {
-        ProfileScope p8(ctx, 8, 0.0);
-        kd_normals_thread_kernel<<<tblocks, KD_THREADS, 0, st>>>(ix, pending, lists + KDL_PENDING + parity, done, hard_knn,
-                                                                 lists + KDL_HARD_KNN + parity, counters);
-        PLS_CHECK_LAUNCH();
-        exact_list = hard_knn;
-        exact_count = lists + KDL_HARD_KNN + parity;
-    }
     ProfileScope p9(ctx, 9, 0.0);
-    kd_normals_warp_kernel<<<wblocks < resident_kn ? wblocks : resident_kn, KD_THREADS, 0, st>>>(ix, k, exact_list, exact_count, done,
-                                                                                                 counters);
+    kd_normals_warp_kernel<<<wblocks < resident_kn ? wblocks : resident_kn, KD_THREADS, 0, st>>>(
+        ix, ctx->cfg.num_neighbors_normals, pending, lists + KDL_PENDING + parity, done, counters);
     PLS_CHECK_LAUNCH();
 }
 
@@ -873,7 +816,7 @@ int kdmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int num
     // credited per executed iteration by the caller (the launch is a no-op once ICP converged)
     ProfileScope ps(ctx, 0, 0.0, false);
     const KdIndex ix = make_index(ctx);
-    launch_search(ctx, ix, ctx->query_ptr, nq_dev, mine, rank, num_ranks, fr->T, &fr->done, ctx->nn_prev.as<int>(), it > 0, true,
+    launch_search(ctx, ix, ctx->query_ptr, nq_dev, mine, rank, num_ranks, fr->T, &fr->done, ctx->nn_prev.as<int>(), it == 0, true,
                   it & 1);
     const int blocks = grid_for(mine, KD_RES_THREADS, 8 * kNumSMs);
     ctx->partials.reserve((size_t)blocks * NACC * sizeof(double), st);
@@ -978,7 +921,7 @@ int pls_kdmap_nn_search(pls_context* ctx, const float* queries, int64_t n, float
     kd_rows_to_float4_kernel<<<grid_for(n, 256, 8 * kNumSMs), 256, 0, st>>>(d, n, ctx->queries.as<float4>());
     PLS_CHECK_LAUNCH();
     const KdIndex ix = make_index(ctx);
-    launch_search(ctx, ix, ctx->queries.as<float4>(), nq, n, 0, 1, ctx->tmp[6].as<float>(), nullptr, ctx->nn_prev.as<int>(), false,
+    launch_search(ctx, ix, ctx->queries.as<float4>(), nq, n, 0, 1, ctx->tmp[6].as<float>(), nullptr, ctx->nn_prev.as<int>(), true,
                   out_normals != nullptr, 0);
     kd_search_export_kernel<<<grid_for(n, 256, 8 * kNumSMs), 256, 0, st>>>(ix, ctx->nn_prev.as<int>(), n, (float*)onb.dev,
                                                                             (float*)onr.dev, (long long*)oix.dev);

@@ -187,9 +187,13 @@ __device__ __forceinline__ int warp_candidate(int incl, int adj /* = start - exc
 // Exact 1-NN of (x, y, z) by the whole warp; every lane returns the same sorted position (-1 if the map is empty).
 // `hint` (a sorted position or -1, warp-uniform) only seeds the pruning bound; its load overlaps the level-0 probes.
 // *cand_out (optional) accumulates the number of candidates tested.
+// *second_out receives a lower bound of the squared distance from the query to every map point OTHER than the winner
+// (the runner-up inside the scanned block, the boxes of the cells that were pruned, the block's exactness radius):
+// as long as the query moves by less than the gap between the two, the winner stays the nearest neighbour -- the next
+// ICP iterations verify that instead of searching again (kd_nn_verify_kernel).
 __device__ __forceinline__ int warp_nearest(const KdIndex& ix, const KdGridLocal& g, float x, float y, float z, int hint,
-                                            int lane, int* cand_out) {
-    float best = FLT_MAX;
+                                            int lane, int* cand_out, float* second_out) {
+    float best = FLT_MAX, second = FLT_MAX;
     int best_i = -1;
     float4 hp = make_float4(0.f, 0.f, 0.f, 0.f);
     const bool has_hint = hint >= 0 && hint < ix.M;
@@ -203,7 +207,11 @@ __device__ __forceinline__ int warp_nearest(const KdIndex& ix, const KdGridLocal
             best = dist2_point(x, y, z, hp);
             best_i = hint;
         }
-        if (box2 > best) count = 0;  // nothing in that cell can beat (or tie) the bound
+        float l2 = FLT_MAX;          // this lane's bound for points other than its own best
+        if (box2 > best) {           // nothing in that cell can beat (or tie) the bound ...
+            if (count > 0) l2 = box2;  // ... but its points may be the runner-up
+            count = 0;
+        }
         int incl;
         const int total = warp_scan_counts(count, lane, incl);
         const int adj = start - (incl - count);
@@ -216,14 +224,22 @@ __device__ __forceinline__ int warp_nearest(const KdIndex& ix, const KdGridLocal
             if (active) {
                 const float d = dist2_point(x, y, z, __ldg(ix.sorted + idx));
                 if (d < ld || (d == ld && (unsigned)idx < (unsigned)li)) {
+                    l2 = fminf(l2, ld);
                     ld = d;
                     li = idx;
+                } else if (idx != li) {
+                    l2 = fminf(l2, d);
                 }
             }
         }
-        warp_argmin(ld, li);
-        best = ld;
-        best_i = li;
+        float wd = ld;
+        int wi = li;
+        warp_argmin(wd, wi);
+        if (li != wi) l2 = fminf(l2, ld);  // this lane's best lost: it is a runner-up candidate
+        second = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(l2)));
+        if (r2 >= 0.f) second = fminf(second, r2);  // anything outside the block is at least that far
+        best = wd;
+        best_i = wi;
         if (cand_out) *cand_out += total;
         if (ix.stats && lane == 0) {
             kd_stat(ix, 3, (unsigned long long)total);
@@ -231,6 +247,7 @@ __device__ __forceinline__ int warp_nearest(const KdIndex& ix, const KdGridLocal
         }
         if (best_i >= 0 && best <= r2) break;
     }
+    if (second_out) *second_out = second;
     return best_i;
 }
 
@@ -334,235 +351,6 @@ __device__ __forceinline__ int warp_knn(const KdIndex& ix, const KdGridLocal& g,
     out_d = keep_d;
     out_i = keep_i;
     return found;
-}
-
-// ---- thread-per-query fast paths ------------------------------------------------------------------------------------
-// Most queries are easy: their neighbour(s) lie well inside the 3x3x3 (or 5x5x5) level-0 block.  For those a single
-// thread is the cheapest executor -- no replicated bookkeeping, 32 independent searches per warp in flight -- as long as
-// every lane of the warp has the same kind of work: the kernels run these paths over COMPACTED work lists and hand the
-// few queries they cannot prove exact to the warp-cooperative pyramid search above.
-
-// A query's place in the level-0 grid: its (clamped) cell and the conservative squared distances (m^2, shrunk by the
-// quantisation slack) from the query to the cell columns at offsets -2..+2 per axis.
-struct KdCellFrame {
-    int cx, cy, cz, cmax;
-    float ax2[5], ay2[5], az2[5];
-};
-__device__ __forceinline__ void kd_axis_dist2(float f, int c, float side_u, float inv_scale, float* a2) {
-    // offset o < 0: the column ends at (c + o + 1) * side; o > 0: it starts at (c + o) * side; o = 0: inside (0 is conservative)
-#pragma unroll
-    for (int o = -2; o <= 2; ++o) {
-        float d = 0.f;
-        if (o < 0) d = (f - (float)(c + o + 1) * side_u) * inv_scale - KD_CELL_MARGIN;
-        if (o > 0) d = ((float)(c + o) * side_u - f) * inv_scale - KD_CELL_MARGIN;
-        d = fmaxf(d, 0.f);
-        a2[o + 2] = d * d;
-    }
-}
-__device__ __forceinline__ KdCellFrame kd_cell_frame(const KdGridLocal& g, float x, float y, float z) {
-    KdCellFrame f;
-    const int b = g.b0;
-    f.cmax = KD_COORD_MAX >> b;
-    const float side_u = (float)(1 << b);
-    const float fx = fminf(fmaxf((x - g.mnx) * g.scale, -1.0e6f), 1.0e6f);
-    const float fy = fminf(fmaxf((y - g.mny) * g.scale, -1.0e6f), 1.0e6f);
-    const float fz = fminf(fmaxf((z - g.mnz) * g.scale, -1.0e6f), 1.0e6f);
-    f.cx = min(max(((int)floorf(fx)) >> b, 0), f.cmax);
-    f.cy = min(max(((int)floorf(fy)) >> b, 0), f.cmax);
-    f.cz = min(max(((int)floorf(fz)) >> b, 0), f.cmax);
-    kd_axis_dist2(fx, f.cx, side_u, g.inv_scale, f.ax2);
-    kd_axis_dist2(fy, f.cy, side_u, g.inv_scale, f.ay2);
-    kd_axis_dist2(fz, f.cz, side_u, g.inv_scale, f.az2);
-    return f;
-}
-
-// Level-0 table lookup of cell (xx, yy, zz) (in range); false if the cell holds no point.
-__device__ __forceinline__ bool kd_lookup0(const KdIndex& ix, int xx, int yy, int zz, int& start, int& end) {
-    const uint32_t id = kd_cell_id((uint32_t)xx, (uint32_t)yy, (uint32_t)zz);
-    const uint4* __restrict__ table = ix.table[0];
-    const uint32_t mask = ix.mask[0];
-    uint32_t h = kd_hash(id) & mask;
-    for (int probe = 0; probe < 64; ++probe) {
-        const uint4 e = __ldg(table + h);
-        if (e.y != ix.gen) return false;
-        if (e.x == id) {
-            start = (int)e.z;
-            end = (int)e.w;
-            return true;
-        }
-        h = (h + 1) & mask;
-    }
-    return false;
-}
-
-// Exact 1-NN by ONE thread when it can be proven inside the 3x3x3 level-0 block: the previous match (hint) and the
-// query's own cell give a bound, then only ring cells whose box is within the bound are probed (typically none to
-// two).  Returns the best position found; `exact` tells whether it is proven (else the caller queues the query for
-// the warp-cooperative search, which restarts from this bound).
-__device__ __forceinline__ int thread_nearest(const KdIndex& ix, const KdGridLocal& g, float x, float y, float z, int hint,
-                                              bool& exact, int& cand) {
-    float best = FLT_MAX;
-    int best_i = -1;
-    if (hint >= 0 && hint < ix.M) {
-        best = dist2_point(x, y, z, __ldg(ix.sorted + hint));
-        best_i = hint;
-    }
-    const KdCellFrame f = kd_cell_frame(g, x, y, z);
-    int s, e;
-    if (kd_lookup0(ix, f.cx, f.cy, f.cz, s, e)) {
-        cand += e - s + 1;
-        for (int i = s; i <= e; ++i) {
-            const float d = dist2_point(x, y, z, __ldg(ix.sorted + i));
-            if (d < best || (d == best && (unsigned)i < (unsigned)best_i)) { best = d; best_i = i; }
-        }
-    }
-#pragma unroll 1
-    for (int c = 0; c < 27; ++c) {
-        if (c == 13) continue;
-        const int dz = c / 9, rem = c - dz * 9, dy = rem / 3, dx = rem - dy * 3;
-        if (f.ax2[dx + 1] + f.ay2[dy + 1] + f.az2[dz + 1] > best) continue;
-        const int xx = f.cx + dx - 1, yy = f.cy + dy - 1, zz = f.cz + dz - 1;
-        if (xx < 0 || xx > f.cmax || yy < 0 || yy > f.cmax || zz < 0 || zz > f.cmax) continue;
-        if (!kd_lookup0(ix, xx, yy, zz, s, e)) continue;
-        cand += e - s + 1;
-        for (int i = s; i <= e; ++i) {
-            const float d = dist2_point(x, y, z, __ldg(ix.sorted + i));
-            if (d < best || (d == best && (unsigned)i < (unsigned)best_i)) { best = d; best_i = i; }
-        }
-    }
-    const float cell = (float)(1 << g.b0) * g.inv_scale - KD_CELL_MARGIN;
-    exact = best_i >= 0 && cell > 0.f && best <= cell * cell && g.top > 0 && !__ldg(&ix.grid->overflow[0]);
-    return best_i;
-}
-
-// Register-resident ascending list of the K best (distance, index) pairs: fully unrolled, branch-free bubble insertion
-// (no local memory, no per-lane loops).
-template <int K>
-struct KBest {
-    float d[K];
-    int i[K];
-    __device__ __forceinline__ void reset() {
-#pragma unroll
-        for (int j = 0; j < K; ++j) { d[j] = FLT_MAX; i[j] = -1; }
-    }
-    __device__ __forceinline__ bool full() const { return i[K - 1] >= 0; }
-    __device__ __forceinline__ void insert_uniform(float dn, int in) {
-        const bool take = dn < d[K - 1] || (dn == d[K - 1] && (unsigned)in < (unsigned)i[K - 1]);
-        d[K - 1] = take ? dn : d[K - 1];
-        i[K - 1] = take ? in : i[K - 1];
-#pragma unroll
-        for (int j = K - 1; j > 0; --j) {
-            const bool sw = d[j] < d[j - 1] || (d[j] == d[j - 1] && (unsigned)i[j] < (unsigned)i[j - 1]);
-            const float td = sw ? d[j - 1] : d[j];
-            const int ti = sw ? i[j - 1] : i[j];
-            d[j - 1] = sw ? d[j] : d[j - 1];
-            i[j - 1] = sw ? i[j] : i[j - 1];
-            d[j] = td;
-            i[j] = ti;
-        }
-    }
-};
-
-// Exact K-NN by ONE thread when it can be proven inside the 5x5x5 level-0 block.  Phase A scans the 3x3x3 block (nine
-// independent table probes per z-slab, then their point ranges); if the K-th distance found is not yet provably
-// exact, phase B adds the 98 cells of the surrounding shell -- only those whose box lies within the K-th distance so
-// far, usually a handful.  `exact` tells whether the list is proven.
-template <int K>
-__device__ __forceinline__ void thread_knn(const KdIndex& ix, const KdGridLocal& g, float x, float y, float z, KBest<K>& L,
-                                           bool& exact, int& cand) {
-    L.reset();
-    const KdCellFrame f = kd_cell_frame(g, x, y, z);
-    const uint4* __restrict__ table = ix.table[0];
-    const uint32_t mask = ix.mask[0];
-    // Morton-spread coordinates of the three cell columns per axis
-    uint32_t sx[3], sy[3];
-    bool vx[3], vy[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        const int xx = f.cx + d - 1, yy = f.cy + d - 1;
-        vx[d] = xx >= 0 && xx <= f.cmax;
-        vy[d] = yy >= 0 && yy <= f.cmax;
-        sx[d] = vx[d] ? kd_spread10((uint32_t)xx) : 0u;
-        sy[d] = vy[d] ? kd_spread10((uint32_t)yy) << 1 : 0u;
-    }
-#pragma unroll 1
-    for (int dz = -1; dz <= 1; ++dz) {
-        const int zz = f.cz + dz;
-        if (zz < 0 || zz > f.cmax) continue;
-        const uint32_t kz = kd_spread10((uint32_t)zz) << 2;
-        uint32_t id[9], hh[9];
-        uint4 ent[9];
-        bool ok[9];
-#pragma unroll
-        for (int j = 0; j < 9; ++j) {
-            ok[j] = vx[j % 3] && vy[j / 3];
-            id[j] = kz | sy[j / 3] | sx[j % 3];
-            hh[j] = kd_hash(id[j]) & mask;
-        }
-#pragma unroll
-        for (int j = 0; j < 9; ++j) ent[j] = ok[j] ? __ldg(table + hh[j]) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-        for (int j = 0; j < 9; ++j) {
-            if (!ok[j]) continue;
-            uint4 e = ent[j];
-            bool hit = e.y == ix.gen && e.x == id[j];
-            if (!hit && e.y == ix.gen) {  // collision: keep probing
-                uint32_t h = hh[j];
-                for (int probe = 0; probe < 64 && !hit; ++probe) {
-                    h = (h + 1) & mask;
-                    e = __ldg(table + h);
-                    if (e.y != ix.gen) break;
-                    hit = e.x == id[j];
-                }
-            }
-            if (hit) {
-                cand += (int)e.w - (int)e.z + 1;
-                for (int i = (int)e.z; i <= (int)e.w; ++i) L.insert_uniform(dist2_point(x, y, z, __ldg(ix.sorted + i)), i);
-            }
-        }
-    }
-    const float cell0 = (float)(1 << g.b0) * g.inv_scale;
-    const bool usable = g.top > 0 && !__ldg(&ix.grid->overflow[0]);
-    const float ra = cell0 - KD_CELL_MARGIN;
-    exact = usable && L.full() && ra > 0.f && L.d[K - 1] <= ra * ra;
-    if (exact || !usable) return;
-    // phase B: the shell of the 5x5x5 block, pruned by the K-th distance so far
-#pragma unroll 1
-    for (int c = 0; c < 125; ++c) {
-        const int dz = c / 25, rem = c - dz * 25, dy = rem / 5, dx = rem - dy * 5;
-        if (dx >= 1 && dx <= 3 && dy >= 1 && dy <= 3 && dz >= 1 && dz <= 3) continue;  // phase A's block
-        if (f.ax2[dx] + f.ay2[dy] + f.az2[dz] > L.d[K - 1]) continue;
-        const int xx = f.cx + dx - 2, yy = f.cy + dy - 2, zz = f.cz + dz - 2;
-        if (xx < 0 || xx > f.cmax || yy < 0 || yy > f.cmax || zz < 0 || zz > f.cmax) continue;
-        int s, e;
-        if (!kd_lookup0(ix, xx, yy, zz, s, e)) continue;
-        cand += e - s + 1;
-        for (int i = s; i <= e; ++i) L.insert_uniform(dist2_point(x, y, z, __ldg(ix.sorted + i)), i);
-    }
-    const float rb = 2.f * cell0 - KD_CELL_MARGIN;
-    exact = L.full() && L.d[K - 1] <= rb * rb && g.top > 1;
-}
-
-// Second moments about map point c of its k nearest OTHER map points and the normal, by one thread (the list's entry 0
-// is the point itself): float32 sums in ascending-distance order, divided by k (slam/odometry/local_map.py:411-413).
-template <int K>
-__device__ __forceinline__ void thread_moments(const KdIndex& ix, const float4& c, const KBest<K>& L, float* cov) {
-    float sxx = 0.f, sxy = 0.f, sxz = 0.f, syy = 0.f, syz = 0.f, szz = 0.f;
-#pragma unroll
-    for (int j = 1; j < K; ++j) {
-        if (L.i[j] < 0) continue;
-        const float4 q = __ldg(ix.sorted + L.i[j]);
-        const float dx = __fsub_rn(q.x, c.x), dy = __fsub_rn(q.y, c.y), dz = __fsub_rn(q.z, c.z);
-        sxx = __fadd_rn(sxx, __fmul_rn(dx, dx));
-        sxy = __fadd_rn(sxy, __fmul_rn(dx, dy));
-        sxz = __fadd_rn(sxz, __fmul_rn(dx, dz));
-        syy = __fadd_rn(syy, __fmul_rn(dy, dy));
-        syz = __fadd_rn(syz, __fmul_rn(dy, dz));
-        szz = __fadd_rn(szz, __fmul_rn(dz, dz));
-    }
-    const float kk = (float)(K - 1);
-    cov[0] = __fdiv_rn(sxx, kk); cov[1] = __fdiv_rn(sxy, kk); cov[2] = __fdiv_rn(sxz, kk);
-    cov[3] = __fdiv_rn(syy, kk); cov[4] = __fdiv_rn(syz, kk); cov[5] = __fdiv_rn(szz, kk);
 }
 
 // Eigenvector of the smallest eigenvalue of a symmetric 3x3 matrix (cyclic Jacobi, fp64).

@@ -55,6 +55,8 @@ for i,v in list(by.items())[:60]:
     print(v["name"][:28].ljust(28), "us", float(v.get("gpu__time_duration.sum","0").replace(",",""))/1e3, "cyc", v.get("sm__cycles_active.avg"), "inst", v.get("smsp__inst_executed.sum"))
 PY
     ;;
+kdprof)
+    timeout 200 python tools/kd_profile.py 2>&1 | tail -9 | tee -a gpurun_out/${TAG}_kdprof.log ;;
 stats)
     PLS_KD_STATS=1 timeout 120 python tools/quick_time.py 30 tensor 2>&1 | tail -6 | tee gpurun_out/${TAG}_kd_stats.log ;;
 quick)

@@ -11,8 +11,8 @@ H, W, F, WARM = 64, 2048, 44, 24
 scans = [syn.scan(k, H, W) for k in range(F)]
 dev = torch.device("cuda", 0)
 dscans = torch.from_numpy(np.stack(scans)).to(dev)
-names = {0: "icp iteration (all)", 3: "index build", 4: "grid sample", 6: "nn fast/iota", 7: "nn warp", 8: "normals fast", 9: "normals warp", 10: "residual+solve"}
-for slot in (int(a) for a in (sys.argv[1:] or ["0", "3", "4", "6", "7", "8", "9", "10"])):
+names = {0: "icp iteration (all)", 3: "index build", 4: "grid sample", 6: "nn verify", 7: "nn search", 9: "normals", 10: "residual+solve"}
+for slot in (int(a) for a in (sys.argv[1:] or ["0", "3", "4", "6", "7", "9", "10"])):
     cfg = b200.ICPFrameToModelConfig(local_map=b200.KdTreeLocalMapConfig(local_map_size=20),
         alignment=b200.GaussNewtonPointToPlaneConfig(gauss_newton_config=dict(scheme="geman_mcclure", sigma=0.3, max_iters=1)),
         max_num_alignments=10, data_key="input_data")
