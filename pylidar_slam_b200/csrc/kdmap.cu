@@ -116,21 +116,18 @@ __global__ void kd_pack_pixels_kernel(const float* __restrict__ vmap, int64_t hw
         if (flags[i]) out[pos[i]] = make_float4(vmap[i], vmap[hw + i], vmap[2 * hw + i], 0.f);
 }
 
-// Quantisation of the map: 256 units per metre (3.9 mm) when the map extent allows it (<= 32 m), else the
-// KD_COORD_BITS-bit range is stretched over the extent.  Level-0 cells are 2^b0 units, the power of two nearest
-// the target side -- but never fewer than KD_MIN_B0 bits are dropped, so that a level-0 cell id
-// (13 - b0 bits per axis, Morton-interleaved) fits 30 bits and the sort needs four 8-bit passes whatever the extent
-// (maps wider than ~160 m simply get coarser cells).
+// Quantisation of the map.  A level-0 cell is always 2^KD_MIN_B0 = 8 quantisation units, so its id (10 bits per axis,
+// Morton-interleaved) fits 30 bits and the sort needs four 8-bit passes whatever the extent; the unit is chosen so
+// that the cell side equals the target -- or, for maps wider than 1024 cells, so that the 13-bit range just covers the
+// extent (coarser cells).  The coarsest level (top = 10) is a single cell.
 __global__ void kd_grid_header_kernel(int* __restrict__ bbox, KdGridHeader* __restrict__ hdr, float cell_target) {
     if (threadIdx.x != 0) return;
     const float mnx = ordered_to_float(bbox[0]), mny = ordered_to_float(bbox[1]), mnz = ordered_to_float(bbox[2]);
     const float ex = ordered_to_float(bbox[3]) - mnx, ey = ordered_to_float(bbox[4]) - mny,
                 ez = ordered_to_float(bbox[5]) - mnz;
     const float ext = fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-6f));
-    const float scale = fminf(256.0f, (float)KD_COORD_MAX / ext);
-    // the power of two nearest (in ratio) to the target side: cell0 in [target / sqrt 2, target * sqrt 2)
-    int b0 = KD_MIN_B0;
-    while (b0 < 12 && (float)(1 << b0) * 1.41421356f < cell_target * scale) ++b0;
+    const int b0 = KD_MIN_B0;
+    const float scale = fminf((float)(1 << b0) / cell_target, (float)KD_COORD_MAX / ext);
     hdr->mn[0] = mnx; hdr->mn[1] = mny; hdr->mn[2] = mnz;
     hdr->scale = scale;
     hdr->b0 = b0;

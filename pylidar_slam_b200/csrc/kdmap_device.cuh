@@ -24,13 +24,15 @@
 #include <float.h>
 #include <stdint.h>
 
+#include "eigen_device.cuh"
+
 namespace pls {
 
 constexpr int KD_COORD_BITS = 13;                       // quantisation bits per axis
 constexpr int KD_COORD_MAX = (1 << KD_COORD_BITS) - 1;
 constexpr int KD_MIN_B0 = 3;                            // level-0 cell ids then fit 30 bits (4 radix passes)
 constexpr int KD_MAX_LEVELS = KD_COORD_BITS - KD_MIN_B0 + 1;  // levels 0 .. top, top <= 10
-constexpr float KD_CELL_TARGET = 0.16f;   // default level-0 cell side in [0.16, 0.32) m (PLS_KD_CELL overrides)
+constexpr float KD_CELL_TARGET = 0.20f;   // default level-0 cell side, metres (PLS_KD_CELL overrides)
 constexpr float KD_CELL_MARGIN = 2e-3f;   // quantisation slack, metres
 constexpr int KD_KMAX = 32;               // k + 1 <= 32
 constexpr unsigned FULL = 0xffffffffu;
@@ -351,53 +353,6 @@ __device__ __forceinline__ int warp_knn(const KdIndex& ix, const KdGridLocal& g,
     out_d = keep_d;
     out_i = keep_i;
     return found;
-}
-
-// Eigenvector of the smallest eigenvalue of a symmetric 3x3 matrix (cyclic Jacobi, fp64).
-__device__ __forceinline__ void smallest_eigenvector(const float* c /*xx,xy,xz,yy,yz,zz*/, float* n) {
-    double A[3][3] = {{c[0], c[1], c[2]}, {c[1], c[3], c[4]}, {c[2], c[4], c[5]}};
-    double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-    for (int sweep = 0; sweep < 12; ++sweep) {
-        double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
-        double diag = fabs(A[0][0]) + fabs(A[1][1]) + fabs(A[2][2]);
-        if (off <= 1e-18 * diag || off == 0.0) break;
-#pragma unroll
-        for (int pq = 0; pq < 3; ++pq) {
-            const int p = pq == 2 ? 1 : 0;
-            const int q = pq == 0 ? 1 : 2;
-            double apq = A[p][q];
-            if (apq == 0.0) continue;
-            double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
-            double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-            double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                double akp = A[k][p], akq = A[k][q];
-                A[k][p] = cs * akp - sn * akq;
-                A[k][q] = sn * akp + cs * akq;
-            }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                double apk = A[p][k], aqk = A[q][k];
-                A[p][k] = cs * apk - sn * aqk;
-                A[q][k] = sn * apk + cs * aqk;
-            }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                double vkp = V[k][p], vkq = V[k][q];
-                V[k][p] = cs * vkp - sn * vkq;
-                V[k][q] = sn * vkp + cs * vkq;
-            }
-        }
-    }
-    int m = 0;
-    if (A[1][1] < A[m][m]) m = 1;
-    if (A[2][2] < A[m][m]) m = 2;
-    double nx = V[0][m], ny = V[1][m], nz = V[2][m];
-    double inv = 1.0 / sqrt(nx * nx + ny * ny + nz * nz);
-    n[0] = (float)(nx * inv);
-    n[1] = (float)(ny * inv);
-    n[2] = (float)(nz * inv);
 }
 
 // Second moments about map point c of its k nearest OTHER map points (entry 0 of the (k+1)-NN list is the point

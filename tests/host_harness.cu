@@ -10,6 +10,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include "../pylidar_slam_b200/csrc/eigen_device.cuh"
 #include "../pylidar_slam_b200/csrc/filters_device.cuh"
 #include "../pylidar_slam_b200/csrc/gn_device.cuh"
 #include "../pylidar_slam_b200/csrc/pose_device.cuh"
@@ -220,6 +221,18 @@ void hh_p2plane_loss(const float* vt, const float* vr, const float* nr, const fl
     }
     *out_loss = (float)(total / (double)B);
     delete[] zbuf;
+}
+
+// smallest-eigenvalue directions of n symmetric 3x3 matrices (xx,xy,xz,yy,yz,zz): which = 0 the product's solver
+// (closed form with Jacobi fall-back), 1 Jacobi only, 2 closed form only (used[i] = 0 where it declined)
+void hh_smallest_eigenvectors(const float* cov6, int64_t n, int which, float* out3, int* used) {
+    for (int64_t i = 0; i < n; ++i) {
+        bool ok = true;
+        if (which == 0) smallest_eigenvector(cov6 + 6 * i, out3 + 3 * i);
+        else if (which == 1) smallest_eigenvector_jacobi(cov6 + 6 * i, out3 + 3 * i);
+        else ok = smallest_eigenvector_closed_form(cov6 + 6 * i, out3 + 3 * i);
+        if (used) used[i] = ok ? 1 : 0;
+    }
 }
 
 }  // extern "C"

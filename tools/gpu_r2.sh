@@ -57,6 +57,11 @@ PY
     ;;
 kdprof)
     timeout 200 python tools/kd_profile.py 2>&1 | tail -9 | tee -a gpurun_out/${TAG}_kdprof.log ;;
+cellsweep)
+    for cell in ${CELLS:-0.16 0.2 0.25 0.3}; do
+        echo "== PLS_KD_CELL=$cell"
+        PLS_KD_CELL=$cell timeout 200 python tools/kd_profile.py 0 7 9 2>&1 | tail -3 | tee -a gpurun_out/${TAG}_cellsweep.log
+    done ;;
 stats)
     PLS_KD_STATS=1 timeout 120 python tools/quick_time.py 30 tensor 2>&1 | tail -6 | tee gpurun_out/${TAG}_kd_stats.log ;;
 quick)
