@@ -228,11 +228,10 @@ __global__ void kd_export_kernel(const float4* __restrict__ pts, int64_t n, floa
 //   p = T p0; q = NN(p); n = normal(q); r = n.(p - q); J = [n, p x n]; w; reduce        -- three launches:
 //   kd_nn_verify_kernel     (iterations after a frame's first) a thread per query proves that its previous match is
 //                           still the nearest neighbour; the unproven ones are queued
-//   kd_nn_group_kernel      transform, exact 1-NN -> match[qi] for every query (first iteration) or the queued ones:
-//                           eight lanes per query over the cell pyramid; the first to match a map point whose normal
-//                           is not cached claims it (CAS on the state word) and queues it (group-aggregated appends)
-//   kd_normals_group_kernel exact (k+1)-NN of every queued map point (eight lanes per point), second moments,
-//                           lane-parallel eigen-solves
+//   kd_nn_warp_kernel       transform, exact 1-NN -> match[qi] for every query (first iteration) or the queued ones: a
+//                           warp per query over the cell pyramid; the first to match a map point whose normal is not
+//                           cached claims it (CAS on the state word) and queues it (warp-aggregated appends)
+//   kd_normals_warp_kernel  exact (k+1)-NN of every queued map point, second moments, lane-parallel eigen-solves
 //   kd_residual_kernel      a thread per query: r, J, robust weight, the 30 fp64 accumulators -> block partials; the
 //                           last block sums them in fixed order and runs the solve / stop test / pose update
 constexpr int KD_THREADS = 256;
@@ -303,35 +302,16 @@ kd_nn_verify_kernel(KdIndex ix, const float4* __restrict__ queries, const uint32
     block_flush_list(s_hard, s_nh, hard, lists + KDL_HARD_NN + parity, &s_base);
 }
 
-constexpr int KD_G = 8;                         // lanes per query (kdmap_device.cuh: LaneGroup)
-constexpr int KD_GROUPS = KD_THREADS / KD_G;    // searches a block runs side by side
-
-// Queues the map points among a group's last matches whose normal is neither cached nor claimed: the claims are made by
-// all lanes of the group at once, the append is one atomic per group.
-__device__ __forceinline__ void group_flush_claims(const KdIndex& ix, const LaneGroup<KD_G>& lg, int want_normals, int& my_pos,
-                                                   int* __restrict__ pending, uint32_t* pending_count) {
-    const bool mine = want_normals && my_pos >= 0 && claim_normal(ix, my_pos);
-    const unsigned m = __ballot_sync(lg.mask, mine) & lg.mask;
-    if (m) {
-        int base = 0;
-        if (lg.sub == 0) base = (int)atomicAdd(pending_count, (uint32_t)__popc(m));
-        base = lg.bcast(base, 0);
-        if (mine) pending[base + __popc(m & ((1u << lg.lane) - 1u))] = my_pos;
-    }
-    my_pos = -1;
-}
-
-// 1-NN, full search: a lane group per query over the cell pyramid (group_nearest).  hard == nullptr: every query of
-// this rank's shard (a frame's first iteration); else the queued ones, seeded with their previous match.  The first
-// group to match a map point whose normal is not cached claims it (CAS on the state word) and queues it.  Each query's
-// position and runner-up bound are kept for the later iterations' checks.
+// 1-NN, full search: a warp per query over the cell pyramid (warp_nearest).  hard == nullptr: every query of this
+// rank's shard (a frame's first iteration); else the queued ones, seeded with their previous match.  The first warp to
+// match a map point whose normal is not cached claims it (CAS on the state word) and queues it; claims are made by all
+// lanes at once after 32 queries.  Each query's position and runner-up bound are kept for the later iterations' checks.
 __global__ void __launch_bounds__(KD_THREADS)
-kd_nn_group_kernel(KdIndex ix, const float4* __restrict__ queries, const uint32_t* __restrict__ nq_dev, int64_t q_begin,
-                   int64_t q_stride, const int* __restrict__ hard, uint32_t* lists, int parity, const float* __restrict__ T,
-                   const int* __restrict__ done, int* __restrict__ match, float4* __restrict__ nn_state, int want_normals,
-                   int* __restrict__ pending, unsigned long long* __restrict__ counters) {
+kd_nn_warp_kernel(KdIndex ix, const float4* __restrict__ queries, const uint32_t* __restrict__ nq_dev, int64_t q_begin,
+                  int64_t q_stride, const int* __restrict__ hard, uint32_t* lists, int parity, const float* __restrict__ T,
+                  const int* __restrict__ done, int* __restrict__ match, float4* __restrict__ nn_state, int want_normals,
+                  int* __restrict__ pending, unsigned long long* __restrict__ counters) {
     if (done && *done) return;
-    __shared__ int s_list[KD_GROUPS][KD_LIST];
     int n;
     if (hard) {
         n = (int)lists[KDL_HARD_NN + parity];
@@ -341,25 +321,35 @@ kd_nn_group_kernel(KdIndex ix, const float4* __restrict__ queries, const uint32_
         if (blockIdx.x == 0 && threadIdx.x == 0)  // first kernel of the iteration: recycle the other parity's lists
             for (int l = 0; l < KDL_WORDS; l += 2) lists[l + (parity ^ 1)] = 0;
     }
-    const LaneGroup<KD_G> lg;
-    const int group_local = threadIdx.x / KD_G;
-    const int group_global = blockIdx.x * KD_GROUPS + group_local;
-    const int total_groups = gridDim.x * KD_GROUPS;
-    if (group_global >= n) return;
-    int* list = s_list[group_local];
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * KD_WARPS + (threadIdx.x >> 5);
+    const int total_warps = gridDim.x * KD_WARPS;
+    if (warp_global >= n) return;
     float t[12];
 #pragma unroll
     for (int a = 0; a < 12; ++a) t[a] = T[a];
     const KdGridLocal g = kd_load_grid(ix);
     uint32_t* pending_count = lists + KDL_PENDING + parity;
     int my_pos = -1, held = 0, cand = 0;
+    auto flush_claims = [&]() {
+        const bool mine = want_normals && my_pos >= 0 && claim_normal(ix, my_pos);
+        const unsigned m = __ballot_sync(FULL, mine);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = (int)atomicAdd(pending_count, (uint32_t)__popc(m));
+            base = __shfl_sync(FULL, base, 0);
+            if (mine) pending[base + __popc(m & ((1u << lane) - 1u))] = my_pos;
+        }
+        my_pos = -1;
+        held = 0;
+    };
     // the next query's data is fetched while this one is searched
-    int s = group_global;
+    int s = warp_global;
     int64_t qi = hard ? (int64_t)hard[s] : q_begin + (int64_t)s * q_stride;
     float4 p0 = queries[qi];
     int hint = hard ? match[qi] : -1;
     while (true) {
-        const int sn = s + total_groups;
+        const int sn = s + total_warps;
         int64_t qn = qi;
         float4 pn = p0;
         int hn = -1;
@@ -372,69 +362,62 @@ kd_nn_group_kernel(KdIndex ix, const float4* __restrict__ queries, const uint32_
         const float py = p0.x * t[4] + p0.y * t[5] + p0.z * t[6] + t[7];
         const float pz = p0.x * t[8] + p0.y * t[9] + p0.z * t[10] + t[11];
         float second;
-        const int pos = group_nearest<KD_G>(ix, g, lg, px, py, pz, hint, list, &cand, &second);
-        if (lg.sub == 0) {
+        const int pos = warp_nearest(ix, g, px, py, pz, hint, lane, &cand, &second);
+        if (lane == 0) {
             match[qi] = pos;
             if (nn_state) nn_state[qi] = make_float4(px, py, pz, second);
         }
-        if (lg.sub == held) my_pos = pos;
-        if (++held == KD_G) {
-            group_flush_claims(ix, lg, want_normals, my_pos, pending, pending_count);
-            held = 0;
-        }
+        if (lane == held) my_pos = pos;
+        if (++held == 32) flush_claims();
         if (sn >= n) break;
         s = sn;
         qi = qn;
         p0 = pn;
         hint = hn;
     }
-    group_flush_claims(ix, lg, want_normals, my_pos, pending, pending_count);
-    if (counters && lg.sub == 0 && cand) atomicAdd(counters + KDC_NN_CAND, (unsigned long long)cand);
+    flush_claims();
+    if (counters && lane == 0 && cand) atomicAdd(counters + KDC_NN_CAND, (unsigned long long)cand);
 }
 
-// Normals: a lane group per queued map point, exact (k+1)-NN over the cell pyramid (group_knn), second moments; the
-// eigen-solves are deferred until every lane of the group holds a point's moments and then run lane-parallel.
-template <int KEEP>
+// Normals: a warp per queued map point, exact (k+1)-NN over the cell pyramid (warp_knn), second moments; the
+// eigen-solves are deferred and run lane-parallel (each lane one point) so that no warp idles behind a serial solve.
 __global__ void __launch_bounds__(KD_THREADS)
-kd_normals_group_kernel(KdIndex ix, int k_normals, const int* __restrict__ worklist, const uint32_t* __restrict__ wl_count,
-                        const int* __restrict__ done, unsigned long long* __restrict__ counters) {
+kd_normals_warp_kernel(KdIndex ix, int k_normals, const int* __restrict__ worklist, const uint32_t* __restrict__ wl_count,
+                       const int* __restrict__ done, unsigned long long* __restrict__ counters) {
     if (done && *done) return;
-    __shared__ int s_list[KD_GROUPS][KD_LIST];
     const int n = (int)*wl_count;
-    const LaneGroup<KD_G> lg;
-    const int group_local = threadIdx.x / KD_G;
-    const int group_global = blockIdx.x * KD_GROUPS + group_local;
-    const int total_groups = gridDim.x * KD_GROUPS;
-    if (group_global >= n) return;
-    int* list = s_list[group_local];
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * KD_WARPS + (threadIdx.x >> 5);
+    const int total_warps = gridDim.x * KD_WARPS;
+    if (warp_global >= n) return;
     const KdGridLocal g = kd_load_grid(ix);
     const float valid = __uint_as_float(kd_normal_valid(ix.gen));
     float mycov[6];
     int mypos = -1, held = 0, cand = 0, done_here = 0;
-    int e = group_global;
+    int e = warp_global;
     int pos = worklist[e];
     float4 c = __ldg(ix.sorted + pos);
     while (true) {
         // the next point is fetched while this one is searched
-        const int en = e + total_groups;
+        const int en = e + total_warps;
         int posn = 0;
         float4 cn = c;
         if (en < n) {
             posn = worklist[en];
             cn = __ldg(ix.sorted + posn);
         }
-        float nd[KEEP];
-        int ni[KEEP];
-        const int found = group_knn<KD_G, KEEP>(ix, g, lg, c.x, c.y, c.z, k_normals + 1, list, nd, ni, &cand);
+        float nd;
+        int ni;
+        const int found = warp_knn(ix, g, c.x, c.y, c.z, k_normals + 1, lane, nd, ni, &cand);
         float cov[6];
-        group_second_moments<KD_G, KEEP>(ix, lg, c, k_normals, found, ni, cov);
-        if (lg.sub == held) {
+        warp_second_moments(ix, c, k_normals, found, ni, lane, cov);
+        if (lane == held) {
 #pragma unroll
             for (int a = 0; a < 6; ++a) mycov[a] = cov[a];
             mypos = pos;
         }
         ++done_here;
-        if (++held == KD_G) {  // every lane of the group holds one point's moments: each solves its own
+        if (++held == 32) {  // 32 moments collected: every lane solves its own
             float nn[3];
             smallest_eigenvector(mycov, nn);
             __stcg(ix.normals + mypos, make_float4(nn[0], nn[1], nn[2], valid));
@@ -451,7 +434,7 @@ kd_normals_group_kernel(KdIndex ix, int k_normals, const int* __restrict__ workl
         smallest_eigenvector(mycov, nn);
         __stcg(ix.normals + mypos, make_float4(nn[0], nn[1], nn[2], valid));
     }
-    if (counters && lg.sub == 0) {
+    if (counters && lane == 0) {
         atomicAdd(counters + KDC_KNN_CAND, (unsigned long long)cand);
         atomicAdd(counters + KDC_NORMALS, (unsigned long long)done_here);
     }
@@ -795,10 +778,9 @@ static void launch_search(pls_context* ctx, const KdIndex& ix, const float4* que
     uint32_t* lists = scalar_u32(ctx, SC_KD_LISTS);
     unsigned long long* counters = kd_counters(ctx);
     const int tblocks = (int)((mine + KD_THREADS - 1) / KD_THREADS);
-    static const int resident_nn = resident_blocks((const void*)kd_nn_group_kernel);
-    static const int resident_kn2 = resident_blocks((const void*)kd_normals_group_kernel<2>);
-    static const int resident_kn4 = resident_blocks((const void*)kd_normals_group_kernel<4>);
-    const int wblocks = (int)((mine + KD_GROUPS - 1) / KD_GROUPS);
+    static const int resident_nn = resident_blocks((const void*)kd_nn_warp_kernel);
+    static const int resident_kn = resident_blocks((const void*)kd_normals_warp_kernel);
+    const int wblocks = (int)((mine + KD_WARPS - 1) / KD_WARPS);
     if (!first) {
         ProfileScope p6(ctx, 6, 0.0);
         kd_nn_verify_kernel<<<tblocks, KD_THREADS, 0, st>>>(ix, queries, nq_dev, (int64_t)rank, (int64_t)num_ranks, T, done, match,
@@ -807,20 +789,15 @@ static void launch_search(pls_context* ctx, const KdIndex& ix, const float4* que
     }
     {
         ProfileScope p7(ctx, 7, 0.0);
-        kd_nn_group_kernel<<<wblocks < resident_nn ? wblocks : resident_nn, KD_THREADS, 0, st>>>(
+        kd_nn_warp_kernel<<<wblocks < resident_nn ? wblocks : resident_nn, KD_THREADS, 0, st>>>(
             ix, queries, nq_dev, (int64_t)rank, (int64_t)num_ranks, first ? nullptr : hard_nn, lists, parity, T, done, match, nn_state,
             normals ? 1 : 0, pending, counters);
         PLS_CHECK_LAUNCH();
     }
     if (!normals) return;
     ProfileScope p9(ctx, 9, 0.0);
-    const int k = ctx->cfg.num_neighbors_normals;
-    if (k + 1 <= 2 * KD_G)  // the default k = 10: two result slots per lane
-        kd_normals_group_kernel<2><<<wblocks < resident_kn2 ? wblocks : resident_kn2, KD_THREADS, 0, st>>>(
-            ix, k, pending, lists + KDL_PENDING + parity, done, counters);
-    else
-        kd_normals_group_kernel<4><<<wblocks < resident_kn4 ? wblocks : resident_kn4, KD_THREADS, 0, st>>>(
-            ix, k, pending, lists + KDL_PENDING + parity, done, counters);
+    kd_normals_warp_kernel<<<wblocks < resident_kn ? wblocks : resident_kn, KD_THREADS, 0, st>>>(
+        ix, ctx->cfg.num_neighbors_normals, pending, lists + KDL_PENDING + parity, done, counters);
     PLS_CHECK_LAUNCH();
 }
 

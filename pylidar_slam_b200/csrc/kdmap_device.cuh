@@ -12,13 +12,13 @@
 //                       so one sorted array serves every level.  Entries of older generations count as empty: no
 //                       table is ever cleared.  Level `top` is a single cell holding the whole map.
 //
-// Search.  A group of 8 lanes owns a query (four searches per warp).  The lanes share the 27 probes of the 3x3x3 block
-// around the query (independent table loads = one L2 round trip); the candidate ranges are flattened with a group scan,
-// their indices staged in a small shared-memory list and read G at a time, lane t taking candidate t -- the lanes of a
-// group read consecutive float4 of a cell as one segment instead of scattered sectors (the thread-per-cell scans of
-// round 1 spent their time in L1 wavefronts).  Every point closer than (cell side - margin) lies inside the block, so a
-// best (or k-th best) distance below that is exact; otherwise the next coarser level is scanned (cells pruned by their
-// box distance), up to the level that holds everything.  No tree, no stack, no divergent descent.
+// Search.  A warp owns a query.  Lanes 0..26 each probe one cell of the 3x3x3 block around the query (27 independent
+// table loads = one L2 round trip); the candidate ranges are flattened with a warp scan and read 32 at a time, lane t
+// taking candidate t -- consecutive lanes read consecutive float4 of a range, so a round is a handful of full 128-byte
+// lines instead of 32 scattered sectors (the thread-per-cell scans of round 1 spent their time in L1 wavefronts).
+// Every point closer than (cell side - margin) lies inside the block, so a best (or k-th best) distance below that is
+// exact; otherwise the next coarser level is scanned (cells pruned by their box distance), up to the level that holds
+// everything.  No tree, no stack, no divergent descent.
 #pragma once
 #include <cuda_runtime.h>
 #include <float.h>
@@ -95,51 +95,19 @@ __device__ __forceinline__ KdGridLocal kd_load_grid(const KdIndex& ix) {
     return g;
 }
 
-// ---- lane groups ---------------------------------------------------------------------------------------------------
-// G lanes (8 here) share ONE query; a warp runs 32 / G searches side by side.  Everything a search needs across lanes --
-// probing the 27 cells, walking the candidates, the arg-min / selection rounds -- costs the same number of warp
-// instructions whatever G is, so a narrow group divides the per-query instruction count by 32 / G, while the group is
-// still wide enough to read a cell's points as one coalesced segment and to finish a selection in few rounds.
-// (Round 1 used 4 lanes with a private k-best list per lane -- ~70 instructions per candidate; a full warp per query,
-// tried first in round 2, replicates the bookkeeping 32 times for ~25 candidates.)
-template <int G>
-struct LaneGroup {
-    int lane, sub;
-    unsigned mask;
-    __device__ __forceinline__ LaneGroup() {
-        lane = threadIdx.x & 31;
-        sub = lane & (G - 1);
-        mask = G == 32 ? FULL : (((1u << G) - 1u) << (lane - sub));
-    }
-    template <typename T>
-    __device__ __forceinline__ T bcast(T v, int src) const { return __shfl_sync(mask, v, src, G); }
-    __device__ __forceinline__ unsigned min_u32(unsigned v) const { return __reduce_min_sync(mask, v); }
-    // arg-min of (d, i) over the group with two REDUX (d >= 0: the float's bit pattern orders like its value; ties:
-    // smaller index); (FLT_MAX, -1) if no lane holds a candidate
-    __device__ __forceinline__ void argmin(float& d, int& i) const {
-        const unsigned bits = __float_as_uint(d);
-        const unsigned m = min_u32(bits);
-        const unsigned wi = min_u32(bits == m ? (unsigned)i : 0xffffffffu);
-        d = __uint_as_float(m);
-        i = (int)wi;
-    }
-    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
-};
-
-constexpr int KD_LIST = 256;  // candidate indices a group stages in shared memory per window
-
-// The 27 cells of the 3x3x3 block (at `level`, around the query) are dealt to the G lanes, NC = ceil(27 / G) each
-// (cell c = sub + k G): start[k], count[k] = the cell's point range (count 0: outside the grid / empty), box2[k] = the
-// squared distance from the query to the cell's box, shrunk by the quantisation slack (a lower bound for every point
-// binned into it): the caller drops cells farther than its current best.  The probes do not depend on any bound: all
-// table loads of a lane are issued back to back.
+// The cell of the 3x3x3 block (at `level`, around the query) owned by this lane: its point range [start, start+count)
+// or count = 0 (lanes >= 27, cells outside the grid, empty cells).  `box2` receives the squared distance from the
+// query to the cell's box, shrunk by the quantisation slack (a lower bound for every point binned into it): the caller
+// drops cells farther than its current best.  The probe itself does not depend on any bound, so it can be in flight
+// together with the load of the previous match.
 // Returns the squared exactness radius of the block (FLT_MAX at the top level: the block then holds every point;
 // negative if the level is unusable).  A query outside the grid is clamped to the border cell: all points lie on one
 // side of it along that axis, so the block still holds everything within one cell side.
-template <int G>
-__device__ __forceinline__ float group_probe_block(const KdIndex& ix, const KdGridLocal& g, int level, float x, float y, float z,
-                                                   int sub, int* start, int* count, float* box2) {
-    constexpr int NC = (27 + G - 1) / G;
+__device__ __forceinline__ float warp_probe_block(const KdIndex& ix, const KdGridLocal& g, int level, float x, float y,
+                                                  float z, int lane, int& start, int& count, float& box2) {
+    start = 0;
+    count = 0;
+    box2 = FLT_MAX;
     const int b = g.b0 + level;
     const int cmax = KD_COORD_MAX >> b;
     const float side_u = (float)(1 << b);                      // cell side in quantisation units
@@ -150,46 +118,33 @@ __device__ __forceinline__ float group_probe_block(const KdIndex& ix, const KdGr
     const int cy = min(max(((int)floorf(fy)) >> b, 0), cmax);
     const int cz = min(max(((int)floorf(fz)) >> b, 0), cmax);
     const bool usable = level >= g.top || !__ldg(&ix.grid->overflow[level]);
-    const uint4* __restrict__ table = ix.table[level];
-    const uint32_t mask = ix.mask[level];
-    uint32_t id[NC], hh[NC];
-    uint4 ent[NC];
-    bool ok[NC];
-#pragma unroll
-    for (int k = 0; k < NC; ++k) {
-        const int c = sub + k * G;
-        const int dz = c / 9, rem = c - dz * 9, dy = rem / 3, dx = rem - dy * 3;
+    if (lane < 27 && usable) {
+        const int dz = lane / 9, rem = lane - dz * 9, dy = rem / 3, dx = rem - dy * 3;
         const int xx = cx + dx - 1, yy = cy + dy - 1, zz = cz + dz - 1;
-        ok[k] = usable && c < 27 && xx >= 0 && xx <= cmax && yy >= 0 && yy <= cmax && zz >= 0 && zz <= cmax;
-        id[k] = kd_cell_id((uint32_t)xx, (uint32_t)yy, (uint32_t)zz);
-        hh[k] = kd_hash(id[k]) & mask;
-        // metres from the query to the cell's box
-        const float lox = ((float)xx * side_u - fx), hix = (fx - (float)(xx + 1) * side_u);
-        const float loy = ((float)yy * side_u - fy), hiy = (fy - (float)(yy + 1) * side_u);
-        const float loz = ((float)zz * side_u - fz), hiz = (fz - (float)(zz + 1) * side_u);
-        const float ax = fmaxf(fmaxf(lox, hix) * g.inv_scale - KD_CELL_MARGIN, 0.f);
-        const float ay = fmaxf(fmaxf(loy, hiy) * g.inv_scale - KD_CELL_MARGIN, 0.f);
-        const float az = fmaxf(fmaxf(loz, hiz) * g.inv_scale - KD_CELL_MARGIN, 0.f);
-        box2[k] = ok[k] ? ax * ax + ay * ay + az * az : FLT_MAX;
-    }
-#pragma unroll
-    for (int k = 0; k < NC; ++k) ent[k] = ok[k] ? __ldg(table + hh[k]) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-    for (int k = 0; k < NC; ++k) {
-        start[k] = 0;
-        count[k] = 0;
-        if (!ok[k]) continue;
-        uint4 e = ent[k];
-        uint32_t h = hh[k];
-        for (int probe = 0; probe < 64; ++probe) {
-            if (e.y != ix.gen) break;              // empty (or stale generation): the cell holds no point
-            if (e.x == id[k]) {
-                start[k] = (int)e.z;
-                count[k] = (int)e.w - (int)e.z + 1;
-                break;
+        if (xx >= 0 && xx <= cmax && yy >= 0 && yy <= cmax && zz >= 0 && zz <= cmax) {
+            const uint32_t id = kd_cell_id((uint32_t)xx, (uint32_t)yy, (uint32_t)zz);
+            const uint4* __restrict__ table = ix.table[level];
+            const uint32_t mask = ix.mask[level];
+            uint32_t h = kd_hash(id) & mask;
+            uint4 e = __ldg(table + h);
+            // box distance while the probe is in flight
+            const float lox = ((float)xx * side_u - fx), hix = (fx - (float)(xx + 1) * side_u);
+            const float loy = ((float)yy * side_u - fy), hiy = (fy - (float)(yy + 1) * side_u);
+            const float loz = ((float)zz * side_u - fz), hiz = (fz - (float)(zz + 1) * side_u);
+            const float ax = fmaxf(fmaxf(lox, hix) * g.inv_scale - KD_CELL_MARGIN, 0.f);
+            const float ay = fmaxf(fmaxf(loy, hiy) * g.inv_scale - KD_CELL_MARGIN, 0.f);
+            const float az = fmaxf(fmaxf(loz, hiz) * g.inv_scale - KD_CELL_MARGIN, 0.f);
+            box2 = ax * ax + ay * ay + az * az;
+            for (int probe = 0; probe < 64; ++probe) {
+                if (e.y != ix.gen) break;              // empty (or stale generation): the cell holds no point
+                if (e.x == id) {
+                    start = (int)e.z;
+                    count = (int)e.w - (int)e.z + 1;
+                    break;
+                }
+                h = (h + 1) & mask;
+                e = __ldg(table + h);
             }
-            h = (h + 1) & mask;
-            e = __ldg(table + h);
         }
     }
     if (level >= g.top) return FLT_MAX;
@@ -198,83 +153,77 @@ __device__ __forceinline__ float group_probe_block(const KdIndex& ix, const KdGr
     return cell > 0.f ? cell * cell : -1.f;
 }
 
-// The group's candidates as one flat sequence: lane `sub` owns positions [base, base + own) of it.  Returns the total.
-template <int G>
-__device__ __forceinline__ int group_flatten(const LaneGroup<G>& lg, const int* count, int& base) {
-    constexpr int NC = (27 + G - 1) / G;
-    int own = 0;
-#pragma unroll
-    for (int k = 0; k < NC; ++k) own += count[k];
-    int incl = own;
-#pragma unroll
-    for (int o = 1; o < G; o <<= 1) {
-        const int v = __shfl_up_sync(lg.mask, incl, o, G);
-        if (lg.sub >= o) incl += v;
-    }
-    base = incl - own;
-    return lg.bcast(incl, G - 1);
+// arg-min of (d, i) over the warp with two REDUX instructions (d >= 0, so the float's bit pattern orders like its
+// value; ties: smaller index).  The result lands in every lane; (FLT_MAX, -1) if no lane holds a candidate.
+__device__ __forceinline__ void warp_argmin(float& d, int& i) {
+    const unsigned bits = __float_as_uint(d);
+    const unsigned m = __reduce_min_sync(FULL, bits);
+    const unsigned wi = __reduce_min_sync(FULL, bits == m ? (unsigned)i : 0xffffffffu);
+    d = __uint_as_float(m);
+    i = (int)wi;
 }
 
-// Stages the point indices of flat positions [w0, w0 + KD_LIST) in the group's shared-memory list: every lane writes
-// the part of its own cells' ranges that falls into the window; afterwards lane t reads list[t], list[t + G], ... so
-// that the lanes of a group load consecutive float4 of a cell as one segment.
-template <int G>
-__device__ __forceinline__ void group_stage(const LaneGroup<G>& lg, const int* start, const int* count, int base, int w0,
-                                            int* __restrict__ list) {
-    constexpr int NC = (27 + G - 1) / G;
-    lg.sync();  // the previous window has been consumed
-    int p = base;
+// Inclusive warp scan of the per-lane range sizes; returns the total.
+__device__ __forceinline__ int warp_scan_counts(int count, int lane, int& incl) {
+    incl = count;
 #pragma unroll
-    for (int k = 0; k < NC; ++k) {
-        const int lo = max(p, w0), hi = min(p + count[k], w0 + KD_LIST);
-        for (int q = lo; q < hi; ++q) list[q - w0] = start[k] + (q - p);
-        p += count[k];
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
     }
-    lg.sync();
+    return __shfl_sync(FULL, incl, 31);
 }
 
-// Exact 1-NN of (x, y, z) by a lane group; every lane of the group returns the same sorted position (-1 if the map is
-// empty).  `hint` (a sorted position or -1, group-uniform) only seeds the pruning bound; its load overlaps the level-0
-// probes.  *cand_out (optional) accumulates the number of candidates tested.
+// Index (into `sorted`) of the t-th candidate of the concatenated ranges: the owner cell is the number of lanes whose
+// inclusive prefix is <= t (the prefixes are non-decreasing), found by a 5-step search over lane registers.
+__device__ __forceinline__ int warp_candidate(int incl, int adj /* = start - exclusive prefix */, int t) {
+    int c = 0;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const int v = __shfl_sync(FULL, incl, c + s - 1);
+        if (v <= t) c += s;
+    }
+    return __shfl_sync(FULL, adj, c) + t;
+}
+
+// Exact 1-NN of (x, y, z) by the whole warp; every lane returns the same sorted position (-1 if the map is empty).
+// `hint` (a sorted position or -1, warp-uniform) only seeds the pruning bound; its load overlaps the level-0 probes.
+// *cand_out (optional) accumulates the number of candidates tested.
 // *second_out receives a lower bound of the squared distance from the query to every map point OTHER than the winner
 // (the runner-up inside the scanned block, the boxes of the cells that were pruned, the block's exactness radius):
 // as long as the query moves by less than the gap between the two, the winner stays the nearest neighbour -- the next
 // ICP iterations verify that instead of searching again (kd_nn_verify_kernel).
-template <int G>
-__device__ __forceinline__ int group_nearest(const KdIndex& ix, const KdGridLocal& g, const LaneGroup<G>& lg, float x, float y,
-                                             float z, int hint, int* __restrict__ list, int* cand_out, float* second_out) {
-    constexpr int NC = (27 + G - 1) / G;
+__device__ __forceinline__ int warp_nearest(const KdIndex& ix, const KdGridLocal& g, float x, float y, float z, int hint,
+                                            int lane, int* cand_out, float* second_out) {
     float best = FLT_MAX, second = FLT_MAX;
     int best_i = -1;
     float4 hp = make_float4(0.f, 0.f, 0.f, 0.f);
     const bool has_hint = hint >= 0 && hint < ix.M;
     if (has_hint) hp = __ldg(ix.sorted + hint);
-    if (lg.sub == 0) kd_stat(ix, 0);
+    if (lane == 0) kd_stat(ix, 0);
     for (int level = 0; level <= g.top; ++level) {
-        int start[NC], count[NC];
-        float box2[NC];
-        const float r2 = group_probe_block<G>(ix, g, level, x, y, z, lg.sub, start, count, box2);
+        int start, count;
+        float box2;
+        const float r2 = warp_probe_block(ix, g, level, x, y, z, lane, start, count, box2);
         if (level == 0 && has_hint) {
             best = dist2_point(x, y, z, hp);
             best_i = hint;
         }
         float l2 = FLT_MAX;          // this lane's bound for points other than its own best
-#pragma unroll
-        for (int k = 0; k < NC; ++k) {
-            if (box2[k] > best) {    // nothing in that cell can beat (or tie) the bound ...
-                if (count[k] > 0) l2 = fminf(l2, box2[k]);  // ... but its points may be the runner-up
-                count[k] = 0;
-            }
+        if (box2 > best) {           // nothing in that cell can beat (or tie) the bound ...
+            if (count > 0) l2 = box2;  // ... but its points may be the runner-up
+            count = 0;
         }
-        int base;
-        const int total = group_flatten<G>(lg, count, base);
+        int incl;
+        const int total = warp_scan_counts(count, lane, incl);
+        const int adj = start - (incl - count);
         float ld = best;
         int li = best_i;
-        for (int w0 = 0; w0 < total; w0 += KD_LIST) {
-            group_stage<G>(lg, start, count, base, w0, list);
-            const int wn = min(total - w0, KD_LIST);
-            for (int t = lg.sub; t < wn; t += G) {
-                const int idx = list[t];
+        for (int base = 0; base < total; base += 32) {
+            const int t = base + lane;
+            const bool active = t < total;
+            const int idx = warp_candidate(incl, adj, active ? t : total - 1);
+            if (active) {
                 const float d = dist2_point(x, y, z, __ldg(ix.sorted + idx));
                 if (d < ld || (d == ld && (unsigned)idx < (unsigned)li)) {
                     l2 = fminf(l2, ld);
@@ -287,14 +236,14 @@ __device__ __forceinline__ int group_nearest(const KdIndex& ix, const KdGridLoca
         }
         float wd = ld;
         int wi = li;
-        lg.argmin(wd, wi);
+        warp_argmin(wd, wi);
         if (li != wi) l2 = fminf(l2, ld);  // this lane's best lost: it is a runner-up candidate
-        second = __uint_as_float(lg.min_u32(__float_as_uint(l2)));
+        second = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(l2)));
         if (r2 >= 0.f) second = fminf(second, r2);  // anything outside the block is at least that far
         best = wd;
         best_i = wi;
         if (cand_out) *cand_out += total;
-        if (ix.stats && lg.sub == 0) {
+        if (ix.stats && lane == 0) {
             kd_stat(ix, 3, (unsigned long long)total);
             if (level == 0) kd_stat(ix, (best_i >= 0 && best <= r2) ? 1 : 2);
         }
@@ -304,145 +253,124 @@ __device__ __forceinline__ int group_nearest(const KdIndex& ix, const KdGridLoca
     return best_i;
 }
 
-// Exact K-NN (K <= 32, group-uniform) of (x, y, z) by a lane group.  The r-th nearest point (ascending by distance,
-// then index) ends up in lane r % G, slot r / G of (out_d, out_i) (KD_KEEP slots per lane); returns the number found
-// (min(K, M)).
-//
-// Selection.  The candidates of a block are taken in chunks of G * R (R register slots per lane, lane `sub` holding
-// list positions sub, sub + G, ...); K rounds of {lane-local minimum over its slots, group arg-min (two REDUX), the
-// owner retires that slot} extract the K smallest of the chunk plus the K kept so far (which re-enter through the
-// lanes' keep slots).  A 27-cell block of the BASELINE maps holds 30-80 points: one chunk.
-constexpr int KD_KNN_SLOTS = 8;
-// KEEP = result slots per lane: ceil(Kmax / G) for the largest K the instantiation serves.
-template <int G, int KEEP>
-__device__ __forceinline__ int group_knn(const KdIndex& ix, const KdGridLocal& g, const LaneGroup<G>& lg, float x, float y, float z,
-                                         int K, int* __restrict__ list, float* out_d, int* out_i, int* cand_out) {
-    constexpr int NC = (27 + G - 1) / G;
-    constexpr int R = KD_KNN_SLOTS;
-    float keep_d[KEEP];
-    int keep_i[KEEP];
+// One chunk of the K-NN selection: R fresh candidates per lane (t = chunk + s * 32 + lane) plus the lane's entry of the
+// list kept so far compete; on return lane r < K holds the r-th smallest of them.
+//   * every lane sorts its R + 1 entries ascending (a small compare-exchange network, no communication);
+//   * K rounds: the warp's minimum over the lane heads (two REDUX), the owner pops its head (a register shift).
+template <int R>
+__device__ __forceinline__ void knn_select_chunk(const KdIndex& ix, float x, float y, float z, int K, int lane, int incl, int adj,
+                                                 int total, int chunk, float& keep_d, int& keep_i) {
+    float sd[R + 1];
+    int si[R + 1];
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+        const int t = chunk + s * 32 + lane;
+        const bool active = t < total;
+        const int idx = warp_candidate(incl, adj, active ? t : total - 1);
+        sd[s] = active ? dist2_point(x, y, z, __ldg(ix.sorted + idx)) : FLT_MAX;
+        si[s] = active ? idx : -1;
+    }
+    sd[R] = keep_d;
+    si[R] = keep_i;
+    // insertion network: after pass p the first p + 2 entries are ordered
+#pragma unroll
+    for (int p = 1; p <= R; ++p) {
+#pragma unroll
+        for (int q = p; q >= 1; --q) {
+            const bool sw = sd[q] < sd[q - 1] || (sd[q] == sd[q - 1] && (unsigned)si[q] < (unsigned)si[q - 1]);
+            const float td = sw ? sd[q - 1] : sd[q];
+            const int ti = sw ? si[q - 1] : si[q];
+            sd[q - 1] = sw ? sd[q] : sd[q - 1];
+            si[q - 1] = sw ? si[q] : si[q - 1];
+            sd[q] = td;
+            si[q] = ti;
+        }
+    }
+    float nd = FLT_MAX;
+    int ni = -1;
+    for (int r = 0; r < K; ++r) {
+        float wd = sd[0];
+        int wi = si[0];
+        const int mine = wi;
+        warp_argmin(wd, wi);
+        if (wi < 0) break;  // nothing left anywhere
+        if (mine == wi) {   // indices are unique: exactly one lane pops
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                sd[s] = sd[s + 1];
+                si[s] = si[s + 1];
+            }
+            sd[R] = FLT_MAX;
+            si[R] = -1;
+        }
+        if (lane == r) {
+            nd = wd;
+            ni = wi;
+        }
+    }
+    keep_d = nd;
+    keep_i = ni;
+}
+
+// Exact K-NN (K <= 32, warp-uniform) of (x, y, z): on return lane r < found holds the r-th nearest point
+// (out_d, out_i), ascending by (distance, index); returns the number found (min(K, M)).
+// The candidates of a block are taken in chunks of 32 * R, R = 2, 4 or 8 register slots per lane by block size
+// (a 27-cell block of the BASELINE maps holds 30-80 points: one chunk of R = 2 or 4).
+__device__ __forceinline__ int warp_knn(const KdIndex& ix, const KdGridLocal& g, float x, float y, float z, int K, int lane,
+                                        float& out_d, int& out_i, int* cand_out) {
+    float keep_d = FLT_MAX;   // lane r: r-th best so far (carried between chunks / the result)
+    int keep_i = -1;
     int found = 0;
-    if (lg.sub == 0) kd_stat(ix, 4);
+    if (lane == 0) kd_stat(ix, 4);
     float bound = FLT_MAX;    // K-th distance of the previous (finer) level: an upper bound for this one
     for (int level = 0; level <= g.top; ++level) {
-        int start[NC], count[NC];
-        float box2[NC];
-        const float r2 = group_probe_block<G>(ix, g, level, x, y, z, lg.sub, start, count, box2);
-#pragma unroll
-        for (int k = 0; k < NC; ++k)
-            if (box2[k] > bound) count[k] = 0;
-        int base;
-        const int total = group_flatten<G>(lg, count, base);
+        int start, count;
+        float box2;
+        const float r2 = warp_probe_block(ix, g, level, x, y, z, lane, start, count, box2);
+        if (box2 > bound) count = 0;
+        int incl;
+        const int total = warp_scan_counts(count, lane, incl);
+        const int adj = start - (incl - count);
         if (cand_out) *cand_out += total;
-        if (ix.stats && lg.sub == 0) kd_stat(ix, 7, (unsigned long long)total);
-#pragma unroll
-        for (int c = 0; c < KEEP; ++c) {  // this level's block is a superset of the previous one: select afresh
-            keep_d[c] = FLT_MAX;
-            keep_i[c] = -1;
+        if (ix.stats && lane == 0) kd_stat(ix, 7, (unsigned long long)total);
+        keep_d = FLT_MAX;     // this level's block is a superset of the previous one: select afresh
+        keep_i = -1;
+        if (total <= 64) {
+            knn_select_chunk<2>(ix, x, y, z, K, lane, incl, adj, total, 0, keep_d, keep_i);
+        } else if (total <= 128) {
+            knn_select_chunk<4>(ix, x, y, z, K, lane, incl, adj, total, 0, keep_d, keep_i);
+        } else {
+            for (int chunk = 0; chunk < total; chunk += 256)
+                knn_select_chunk<8>(ix, x, y, z, K, lane, incl, adj, total, chunk, keep_d, keep_i);
         }
-        for (int w0 = 0; w0 < total || w0 == 0; w0 += KD_LIST) {
-            group_stage<G>(lg, start, count, base, w0, list);
-            const int wn = min(total - w0, KD_LIST);
-            for (int chunk = 0; chunk < wn || chunk == 0; chunk += G * R) {
-                float sd[R + KEEP];
-                int si[R + KEEP];
-#pragma unroll
-                for (int s = 0; s < R; ++s) {
-                    const int t = chunk + s * G + lg.sub;
-                    const bool active = t < wn;
-                    const int idx = active ? list[t] : -1;
-                    sd[s] = active ? dist2_point(x, y, z, __ldg(ix.sorted + idx)) : FLT_MAX;
-                    si[s] = idx;
-                }
-#pragma unroll
-                for (int c = 0; c < KEEP; ++c) {  // the K kept so far compete again
-                    sd[R + c] = keep_d[c];
-                    si[R + c] = keep_i[c];
-                    keep_d[c] = FLT_MAX;
-                    keep_i[c] = -1;
-                }
-                for (int r = 0; r < K; ++r) {
-                    float ld = sd[0];
-                    int li = si[0];
-#pragma unroll
-                    for (int s = 1; s < R + KEEP; ++s) {
-                        const bool lt = sd[s] < ld || (sd[s] == ld && (unsigned)si[s] < (unsigned)li);
-                        ld = lt ? sd[s] : ld;
-                        li = lt ? si[s] : li;
-                    }
-                    float wd = ld;
-                    int wi = li;
-                    lg.argmin(wd, wi);
-                    if (wi < 0) break;  // nothing left
-                    if (li == wi) {     // indices are unique: exactly one lane retires a slot
-#pragma unroll
-                        for (int s = 0; s < R + KEEP; ++s) {
-                            const bool hit = si[s] == wi;
-                            sd[s] = hit ? FLT_MAX : sd[s];
-                            si[s] = hit ? -1 : si[s];
-                        }
-                    }
-                    if (lg.sub == (r & (G - 1))) {
-#pragma unroll
-                        for (int c = 0; c < KEEP; ++c)
-                            if (c == r / G) {
-                                keep_d[c] = wd;
-                                keep_i[c] = wi;
-                            }
-                    }
-                }
-            }
-        }
-        // found = number of kept entries over the group; K-th distance = entry K - 1
-        int mine = 0;
-#pragma unroll
-        for (int c = 0; c < KEEP; ++c) mine += keep_i[c] >= 0 ? 1 : 0;
-        found = __reduce_add_sync(lg.mask, mine);
-        float kth = FLT_MAX;
-#pragma unroll
-        for (int c = 0; c < KEEP; ++c)
-            if (c == (K - 1) / G) kth = keep_d[c];
-        kth = lg.bcast(kth, (K - 1) & (G - 1));
+        found = __popc(__ballot_sync(FULL, keep_i >= 0));
+        const float kth = __shfl_sync(FULL, keep_d, K - 1);
         const bool exact = (found == K && kth <= r2) || level >= g.top;
-        if (ix.stats && lg.sub == 0 && level == 0) kd_stat(ix, exact ? 5 : 6);
+        if (ix.stats && lane == 0 && level == 0) kd_stat(ix, exact ? 5 : 6);
         if (exact) break;
         if (found == K) bound = kth;
     }
-#pragma unroll
-    for (int c = 0; c < KEEP; ++c) {
-        out_d[c] = keep_d[c];
-        out_i[c] = keep_i[c];
-    }
+    out_d = keep_d;
+    out_i = keep_i;
     return found;
 }
 
 // Second moments about map point c of its k nearest OTHER map points (entry 0 of the (k+1)-NN list is the point
 // itself): float32 sums taken sequentially in ascending-distance order and divided by k, as numpy's
-// `.mean(axis=1)` forms them (slam/odometry/local_map.py:411-413).  Neighbour j lives in lane j % G, slot j / G
-// (group_knn's layout, KEEP slots per lane); every lane of the group returns the same six moments.
-template <int G, int KEEP>
-__device__ __forceinline__ void group_second_moments(const KdIndex& ix, const LaneGroup<G>& lg, const float4& c, int k, int found,
-                                                     const int* nb_i, float* cov) {
-    float dx[KEEP], dy[KEEP], dz[KEEP];
-#pragma unroll
-    for (int s = 0; s < KEEP; ++s) {
-        dx[s] = dy[s] = dz[s] = 0.f;
-        const int j = s * G + lg.sub;
-        if (j >= 1 && j < found && nb_i[s] >= 0) {
-            const float4 q = __ldg(ix.sorted + nb_i[s]);
-            dx[s] = __fsub_rn(q.x, c.x);
-            dy[s] = __fsub_rn(q.y, c.y);
-            dz[s] = __fsub_rn(q.z, c.z);
-        }
+// `.mean(axis=1)` forms them (slam/odometry/local_map.py:411-413).  Lane j holds neighbour j (nb_i); every lane
+// returns the same six moments.
+__device__ __forceinline__ void warp_second_moments(const KdIndex& ix, const float4& c, int k, int found, int nb_i, int lane,
+                                                    float* cov) {
+    float dx = 0.f, dy = 0.f, dz = 0.f;
+    if (lane >= 1 && lane < found) {
+        const float4 q = __ldg(ix.sorted + nb_i);
+        dx = __fsub_rn(q.x, c.x);
+        dy = __fsub_rn(q.y, c.y);
+        dz = __fsub_rn(q.z, c.z);
     }
     float sxx = 0.f, sxy = 0.f, sxz = 0.f, syy = 0.f, syz = 0.f, szz = 0.f;
     for (int j = 1; j < found; ++j) {
-        float vx = 0.f, vy = 0.f, vz = 0.f;
-#pragma unroll
-        for (int s = 0; s < KEEP; ++s)
-            if (s == j / G) { vx = dx[s]; vy = dy[s]; vz = dz[s]; }
-        const int src = j & (G - 1);
-        const float bx = lg.bcast(vx, src), by = lg.bcast(vy, src), bz = lg.bcast(vz, src);
+        const float bx = __shfl_sync(FULL, dx, j), by = __shfl_sync(FULL, dy, j), bz = __shfl_sync(FULL, dz, j);
         sxx = __fadd_rn(sxx, __fmul_rn(bx, bx));
         sxy = __fadd_rn(sxy, __fmul_rn(bx, by));
         sxz = __fadd_rn(sxz, __fmul_rn(bx, bz));
