@@ -5,22 +5,29 @@ One "step" = one frame of the BASELINE config-2 pipeline: GridSample(voxel 0.3) 
 ICPFrameToModel (kd-tree local map of 20 frames, point-to-plane Gauss-Newton, geman_mcclure
 sigma 0.3, <= 10 alignments, constant-velocity initialisation), on a seeded synthetic stream.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--no-extra] [--no-cpu]
 
 * `value`  : frames/s with every raw scan already resident in HBM; one C-ABI call per frame
-             (pls_process_frame_grid_sample) on device pointers; CUDA events on the library's
-             stream; L2 flushed (untimed) between frames.
+             (pls_process_frame_grid_sample) on device pointers; ONE CUDA-event bracket on the library's
+             stream around the K timed frames (closed after both of the library's streams have drained).
 * `e2e`    : frames/s through the reference-shaped Python API (Preprocessing[GridSample, ToTensor]
              -> ICPFrameToModel.process_next_frame) from PINNED HOST buffers, host<->device copies
              inside the timed region.
-* roofline : the kd correspondence+reduction kernels of one ICP iteration (kd_nn_group_kernel<4> +
-             kd_normals_group_kernel<4> + kd_residual_kernel, which also runs the fused solve), CUDA-event
-             timed inside the library during the timed frames (a second pass over the same frames, so the
-             event records do not perturb `value`).
+* roofline : the kd correspondence kernels of the executed ICP iterations (verify / 1-NN search / lazy 10-NN normals /
+             reduction + fused solve), CUDA-event timed inside the library over the timed frames (a second pass, so
+             that the event records do not perturb `value`).  `achieved` uses SURVEY.md 8d's algorithmic bytes with
+             the candidate counts the kernels themselves count; `lower_bound` is the 44 B / query + 16 B / touched
+             map point figure.
+* config.extra_workloads : the HBM-sized configurations of BASELINE.json (cfg3 128x2048 projective, cfg5 128x4096
+             x 20 iterations projective, cfg4 5 M-point kd map x 131 072 queries), each with ms/frame, the CUDA-event
+             time of its dominant kernel, algorithmic bytes and fraction of the measured HBM peak; at N > 1 also
+             sharded over the ranks.
+* config.sharded_vs_single (N > 1): poses of a forced-sharded run against rank 0's private single-GPU context.
 * cpu_baseline / --impl reference: the CPU oracle port of the reference path (oracle/) on the host
              cores, on a bounded sample of the same stream.
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -50,13 +57,25 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+def committed_traffic(name):
+    """DRAM bytes per launch of a kernel family from the ncu capture committed under profiles/ (produced by
+    tools/gpu_r2.sh traffic from the same sources; the file names the commit it was taken at)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        return d.get(name), d.get("commit")
+    except Exception:
+        return None, None
 
-    def __init__(self, index=0):
-        self.index, self.rows, self._p, self._t = index, [], None, None
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (rank 0 only)."""
+
+    def __init__(self, index=0, enabled=True):
+        self.index, self.rows, self._p, self._t, self.enabled = index, [], None, None, enabled
 
     def start(self):
+        if not self.enabled:
+            return
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
@@ -73,6 +92,8 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if not self.enabled:
+            return None
         if self._p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self._p.terminate()
@@ -95,9 +116,19 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_scans(n_frames):
+def make_scans(n_frames, h=H, w=W):
     from pylidar_slam_b200 import synthetic as syn
-    return [syn.scan(k, H, W) for k in range(n_frames)]
+    return [syn.scan(k, h, w) for k in range(n_frames)]
+
+
+def ref_vs_port_note():
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ref_vs_port.json")))
+        return (f"; in the build container ({d['cores']} cores) the unmodified reference runs this stream at "
+                f"{d['reference_ms_per_frame']:.0f} ms/frame and this port at {d['port_ms_per_frame']:.0f} ms/frame "
+                f"(profiles/ref_vs_port.json)")
+    except Exception:
+        return ""
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -129,7 +160,7 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample: the map needs ~20 frames to reach steady state; cap the CPU work at ~60 frames
+    # bounded sample: the map needs ~20 frames to reach steady state; cap the CPU work at ~55 frames
     warmup = min(args.warmup, 24)
     steps = min(args.steps, 30)
     scans = make_scans(warmup + steps)
@@ -143,7 +174,7 @@ def reference_arm(args):
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"frames {warmup}..{warmup + steps - 1} of the same seeded stream after {warmup} warm-up "
                                    f"frames (oracle/icp_oracle.py: torch CPU + scipy cKDTree workers=-1), "
-                                   f"{time.perf_counter() - t0:.1f} s wall"},
+                                   f"{time.perf_counter() - t0:.1f} s wall" + ref_vs_port_note()},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -151,11 +182,20 @@ def reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def pose_errors(Ta, Tb):
+    Ta, Tb = np.asarray(Ta, np.float64), np.asarray(Tb, np.float64)
+    dt = np.linalg.norm(Ta[:3, 3] - Tb[:3, 3]) / max(np.linalg.norm(Tb[:3, 3]), 1e-12)
+    dR = Tb[:3, :3].T @ Ta[:3, :3]
+    ang = np.linalg.norm(0.5 * np.array([dR[2, 1] - dR[1, 2], dR[0, 2] - dR[2, 0], dR[1, 0] - dR[0, 1]]))
+    return float(dt), float(ang)
+
+
 def b200_arm(args):
     import torch
     import torch.distributed as dist
     import pylidar_slam_b200 as b200
     from pylidar_slam_b200 import _lib
+    from pylidar_slam_b200 import synthetic as syn
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -171,20 +211,26 @@ def b200_arm(args):
     scans = make_scans(n_frames)
     n_raw = scans[0].shape[0]
     stream = torch.cuda.Stream(device=dev)
-    projector = b200.SphericalProjector(height=H, width=W, up_fov=3.0, down_fov=-24.0)
+    peak, peak_src = measured_peaks()
 
     comm_used = [args.comm]  # init_comm reports a fall-back from p2p to nccl
 
-    def make_algo():
-        cfg = b200.ICPFrameToModelConfig(
-            local_map=b200.KdTreeLocalMapConfig(local_map_size=LM_SIZE),
-            alignment=b200.GaussNewtonPointToPlaneConfig(gauss_newton_config=dict(scheme=SCHEME, sigma=SIGMA, max_iters=1)),
-            max_num_alignments=MAX_ALIGN, data_key="input_data")
-        algo = b200.ICPFrameToModel(cfg, projector=projector, device=dev, stream=stream.cuda_stream)
-        algo.init()
+    def connect(ctx):
         if world > 1:
             from pylidar_slam_b200.distributed import init_comm
-            comm_used[0] = init_comm(algo.ctx, dist, rank, world, dev, mode=args.comm)
+            comm_used[0] = init_comm(ctx, dist, rank, world, dev, mode=args.comm)
+
+    def make_algo(local_map="kdtree", h=H, w=W, data_key="input_data", max_align=MAX_ALIGN, threshold=1e-4, comm=True):
+        projector = b200.SphericalProjector(height=h, width=w, up_fov=3.0, down_fov=-24.0)
+        lm = b200.KdTreeLocalMapConfig(local_map_size=LM_SIZE) if local_map == "kdtree" else \
+            b200.ProjectiveLocalMapConfig(local_map_size=LM_SIZE)
+        cfg = b200.ICPFrameToModelConfig(
+            local_map=lm, alignment=b200.GaussNewtonPointToPlaneConfig(gauss_newton_config=dict(scheme=SCHEME, sigma=SIGMA, max_iters=1)),
+            max_num_alignments=max_align, threshold_delta_pose=threshold, data_key=data_key)
+        algo = b200.ICPFrameToModel(cfg, projector=projector, device=dev, stream=stream.cuda_stream)
+        algo.init()
+        if comm:
+            connect(algo.ctx)
         return algo
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -197,6 +243,13 @@ def b200_arm(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
+
+    def max_over_ranks(*vals):
+        if world == 1:
+            return vals
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return tuple(float(v) for v in t.cpu())
 
     # ---------------- value: inputs resident in HBM, one C-ABI call per frame
     dev_scans = torch.from_numpy(np.stack(scans)).to(dev)
@@ -212,10 +265,9 @@ def b200_arm(args):
         pose = np.zeros((4, 4), np.float32)
         params = np.zeros(6, np.float32)
         info = np.zeros(12, np.float64)
-        import ctypes as C
         has = C.c_int(0)
         prev = None
-        launches0, iters = 0, []
+        launches0, iters, sharded = 0, [], 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for k in range(n_frames):
             timed = k > W_
@@ -233,6 +285,7 @@ def b200_arm(args):
                      _lib.ptr(prev), _lib.ptr(pose), _lib.ptr(params), C.byref(has), _lib.ptr(info))
             if timed:
                 iters.append(int(info[0]))
+                sharded += int(info[11])
             if has.value:
                 prev = pose.copy()
         ctx.call("pls_synchronize")
@@ -241,28 +294,27 @@ def b200_arm(args):
         launches = ctx.launch_count() - launches0
         total_ms = e0.elapsed_time(e1)
         prof = ctx.profile(profile_slot) if profile_slot is not None else None
-        stats = {"samples": int(info[4]), "queries": int(info[2]), "map_points": int(info[3]), "iters_mean": float(np.mean(iters))}
-        return total_ms, launches, prof, stats, ctx
+        stats = {"samples": int(info[4]), "queries": int(info[2]), "map_points": int(info[3]), "iters_mean": float(np.mean(iters)),
+                 "iters_total": int(np.sum(iters)), "frames_sharded": sharded}
+        return total_ms, launches, prof, stats
 
-    clocks = ClockSampler(local_rank)
+    clocks = ClockSampler(local_rank, enabled=(rank == 0))
     clocks.start()
-    ms_dev, launches, _, stats, _ = device_pass()
+    ms_dev, launches, _, stats = device_pass()
     clock_info = clocks.stop()
     if args.quick:
+        (ms_dev,) = max_over_ranks(ms_dev)
         if world > 1:
-            t = torch.tensor([ms_dev], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_dev = float(t[0])
             dist.destroy_process_group()
         if rank == 0:
             print(json.dumps({"quick": True, "n_gpus": world, "comm": comm_used[0] if world > 1 else None,
                               "ms_per_step": ms_dev / K_, "gpu_launches": launches, **stats}))
         return
-    ms_dev_flushed, _, _, _, _ = device_pass(flush_each_step=True)
+    ms_dev_flushed, _, _, _ = device_pass(flush_each_step=True)
     # roofline passes: same frames with CUDA events around one kernel family inside the library
-    _, _, prof_nn, _, _ = device_pass(profile_slot=0)
-    _, _, prof_idx, _, _ = device_pass(profile_slot=3)
-    _, _, prof_gs, _, _ = device_pass(profile_slot=4)
+    _, _, prof_nn, stats_nn = device_pass(profile_slot=0)
+    _, _, prof_idx, _ = device_pass(profile_slot=3)
+    _, _, prof_gs, _ = device_pass(profile_slot=4)
 
     # ---------------- e2e: reference-shaped Python API from pinned host buffers
     pinned = [torch.from_numpy(s).pin_memory() for s in scans]
@@ -291,31 +343,36 @@ def b200_arm(args):
             prev = dd["odometry_pose"].astype(np.float64)
         if timed:
             S = dd["sample_points"].shape[0]
-            h2d += host_scans[k].nbytes + S * 12 + 64
-            d2h += S * 12 + S * 8 + 8 + 1400  # samples + indices + count + FrameResult
+            h2d += host_scans[k].nbytes + 64                  # the raw scan + the initial pose (the samples stay on the device)
+            d2h += S * 12 + S * 8 + 32 + 2176                 # samples + indices (filter outputs) + count + FrameResult block
     gs_ctx.call("pls_synchronize")
     t_e = time.perf_counter() - t_start
     barrier()
+    del algo
 
-    # ---------------- aggregate over ranks (max of the per-rank time)
-    t_dev = ms_dev / 1e3
+    t_dev, t_e = max_over_ranks(ms_dev / 1e3, t_e)
+
+    # ---------------- N > 1: sharded == single-GPU evidence on the benched stream (forced sharding, fixed iterations)
+    parity = None
     if world > 1:
-        t = torch.tensor([t_dev, t_e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_dev, t_e = float(t[0]), float(t[1])
+        parity = sharded_vs_single(b200, make_algo, syn, dist, dev, rank, world, comm_used)
+
+    # ---------------- the HBM-sized configurations
+    extra = None
+    if not args.no_extra:
+        extra = extra_workloads(b200, _lib, syn, make_algo, stream, dev, rank, world, dist, peak, comm_used, max_over_ranks, barrier)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peak, peak_src = measured_peaks()
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_kd_traffic.json")))["traffic_bytes_per_launch"]
-    except Exception:
-        pass
+    traffic, traffic_commit = committed_traffic("kd_iteration_bytes_per_launch")
     nn_ms, nn_launches, nn_bytes = prof_nn
-    achieved = (nn_bytes / max(nn_launches, 1)) / (nn_ms / max(nn_launches, 1) * 1e-3) / 1e9 if nn_ms > 0 else 0.0
+    per_launch_bytes = nn_bytes / max(nn_launches, 1)
+    avg_us = 1e3 * nn_ms / max(nn_launches, 1)
+    achieved = per_launch_bytes / (avg_us * 1e-6) / 1e9 if nn_ms > 0 else 0.0
+    lower = (stats_nn["queries"] * 44.0 + stats_nn["queries"] * 16.0) / (avg_us * 1e-6) / 1e9 if nn_ms > 0 else 0.0
     frame_ms = ms_dev / K_
     line = {
         "metric": "icp_odometry_frames_per_sec", "value": K_ / t_dev, "unit": "frames/s", "n_gpus": world,
@@ -323,45 +380,197 @@ def b200_arm(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "height": H, "width": W, "voxel": VOXEL,
                    "l2": "L2 flushed once before the timed bracket; every step streams a NEW 1.5 MB scan from HBM while the "
-                         "62 MB local map legitimately stays L2-resident across frames (production behaviour); "
+                         "~60 MB local map legitimately stays L2-resident across frames (production behaviour); "
                          "value_l2_flushed_every_step re-measures with a 256 MiB flush INSIDE the bracket before every frame",
                    "value_l2_flushed_every_step": K_ / (ms_dev_flushed / 1e3),
-                   "parallelism": "1 GPU" if world == 1 else f"queries sharded over {world} GPUs, map replicated, "
-                                                             f"one 30-double all-reduce per ICP iteration ({comm_used[0]})",
-                   **stats},
+                   "parallelism": "1 GPU" if world == 1 else
+                   (f"{world} GPUs, map replicated; a frame's {stats['queries']} queries are below the sharding threshold "
+                    f"(PLS_SHARD_MIN = 24576 per rank), so every rank runs the whole frame and no exchange takes place "
+                    f"(frames sharded in the timed region: {stats['frames_sharded']}); the sharded path is measured on the "
+                    f"HBM-sized configurations under extra_workloads ({comm_used[0]} exchange)"),
+                   **{k: v for k, v in stats.items() if k != "iters_total"}},
         "e2e": {"value": K_ / t_e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d / K_), "d2h_bytes_per_step": int(d2h / K_),
                 "ms_per_step": 1e3 * t_e / K_},
         "gpu_launches": int(launches),
         "clocks": clock_info,
-        "roofline": {"bound": "hbm", "kernel": "kd_nn_group_kernel<4> + kd_normals_group_kernel<4> + kd_residual_kernel: one ICP iteration "
-                               "(exact 1-NN, lazy 10-NN normals, point-to-plane reduction + fused solve)",
+        "roofline": {"bound": "hbm", "kernel": "kd_nn_verify_kernel + kd_nn_group_kernel + kd_normals_group_kernel<2> + kd_residual_kernel: "
+                               "one executed ICP iteration (exact 1-NN, lazy 10-NN normals, point-to-plane reduction + fused solve)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                     "frac": achieved / peak if peak else None, "traffic": traffic,
-                     "launches": int(nn_launches), "avg_us": 1e3 * nn_ms / max(nn_launches, 1),
-                     "algorithmic_bytes_per_launch": nn_bytes / max(nn_launches, 1),
+                     "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source":
+                     f"profiles/r2_traffic.json (ncu dram bytes of the same kernels, commit {traffic_commit})" if traffic else None,
+                     "launches": int(nn_launches), "avg_us": avg_us,
+                     "algorithmic_bytes_per_launch": per_launch_bytes,
+                     "algorithmic_bytes_formula": "SURVEY 8d: per query 12 + 27*8 + 4 B, 16 B per 1-NN candidate tested; per computed "
+                                                  "normal 32 B + 16 B per k-NN candidate tested; 36 B per correspondence + 240 B per "
+                                                  "block (candidates counted by the kernels)",
+                     "lower_bound": {"achieved": lower, "frac": lower / peak if peak else None,
+                                     "note": "44 B per query + 16 B per touched map point: the ~60 MB map is L2-resident, so this "
+                                             "latency-bound family cannot approach the HBM roofline at 32 k queries per frame"},
                      "share_of_step": (nn_ms / K_) / frame_ms},
         "kernels": {"index_build_ms_per_frame": prof_idx[0] / K_, "grid_sample_ms_per_frame": prof_gs[0] / K_,
                     "correspondence_ms_per_frame": nn_ms / K_},
     }
+    if parity is not None:
+        line["config"]["sharded_vs_single"] = parity
+    if extra is not None:
+        line["config"]["extra_workloads"] = extra
     if world == 1 and not args.no_cpu:
         t0 = time.perf_counter()
         nb = min(len(scans), 30)
         fps_cpu, times = run_cpu_port(scans[:nb], min(22, nb - 6), nb - min(22, nb - 6))
         line["cpu_baseline"] = {"value": fps_cpu, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": f"frames {min(22, nb - 6)}..{nb - 1} of the same stream (oracle port: torch CPU + scipy "
-                                          f"cKDTree workers=-1), {time.perf_counter() - t0:.1f} s wall"}
+                                          f"cKDTree workers=-1), {time.perf_counter() - t0:.1f} s wall" + ref_vs_port_note()}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+def sharded_vs_single(b200, make_algo, syn, dist, dev, rank, world, comm_used):
+    """The sharded odometry (PLS_SHARD_MIN forced to 1: the 32 k queries of a frame split over the ranks, one exchange
+    per ICP iteration) against rank 0's private single-GPU context on the first frames of the benched stream, with a
+    fixed iteration count so that the stop rule cannot flip."""
+    import torch
+    frames = 8
+
+    def drive(algo):
+        prev, poses = None, []
+        for k in range(frames):
+            s, _ = b200.grid_sample(syn.scan(k, H, W), VOXEL, ctx=algo.ctx)
+            dd = {"input_data": torch.from_numpy(s), "init_rpose": prev}
+            algo.process_next_frame(dd)
+            if "odometry_pose" in dd:
+                prev = dd["odometry_pose"].astype(np.float64)
+                poses.append(prev)
+        return np.stack(poses), int(algo.last_info[11])
+
+    from pylidar_slam_b200 import _lib
+    _lib.load().pls_set_shard_min(1)
+    sharded, was_sharded = drive(make_algo(max_align=6, threshold=0.0))
+    _lib.load().pls_set_shard_min(-1)
+    gathered = [torch.zeros_like(torch.from_numpy(sharded)).to(dev) for _ in range(world)]
+    dist.all_gather(gathered, torch.from_numpy(sharded).to(dev))
+    out = None
+    if rank == 0:
+        single, _ = drive(make_algo(max_align=6, threshold=0.0, comm=False))
+        identical = all(bool((g.cpu().numpy() == sharded).all()) for g in gathered)
+        errs = [pose_errors(a, b) for a, b in zip(sharded, single)]
+        out = {"frames": frames - 1, "iterations_per_frame": 6, "exchange": comm_used[0], "sharded": bool(was_sharded),
+               "max_rel_dt": max(e[0] for e in errs), "max_dR": max(e[1] for e in errs), "identical_across_ranks": identical}
+    return out
+
+
+def extra_workloads(b200, _lib, syn, make_algo, stream, dev, rank, world, dist, peak, comm_used, max_over_ranks, barrier):
+    """cfg3 / cfg5 (projective map, the HBM-bound correspondence kernel) and cfg4 (5 M-point kd map).  At N > 1 the
+    correspondences are sharded over the ranks (tiles / queries) with one 30-double exchange per ICP iteration."""
+    import torch
+    out = {}
+
+    def timed_frames(algo, frames, warm, slot, feed):
+        ctx = algo.ctx
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        prev, iters, sharded = None, 0, 0
+        for k, data in enumerate(frames):
+            if k == warm:
+                ctx.call("pls_synchronize")
+                barrier()
+                ctx.call("pls_profile_enable", slot, 1)
+                e0.record(stream)
+            dd = feed(data)
+            dd["init_rpose"] = prev
+            algo.process_next_frame(dd)
+            if "odometry_pose" in dd:
+                prev = dd["odometry_pose"].astype(np.float64)
+            if k >= warm:
+                iters += int(algo.last_info[0])
+                sharded += int(algo.last_info[11])
+        ctx.call("pls_synchronize")
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        kms, klaunches, kbytes = ctx.profile(slot)
+        n = len(frames) - warm
+        (ms,) = max_over_ranks(ms)
+        return ms / n, iters / n, kms, klaunches, kbytes, sharded
+
+    # ---- projective configurations: one vertex map per frame, device-resident
+    for name, (h, w, max_align, threshold, timed) in {"cfg3": (128, 2048, 10, 1e-4, 8), "cfg5": (128, 4096, 20, 0.0, 5)}.items():
+        warm = 22
+        vms = [torch.from_numpy(syn.vertex_map_from_scan(syn.scan(k, h, w), h, w)).to(dev) for k in range(warm + timed)]
+        algo = make_algo(local_map="projective", h=h, w=w, data_key="vertex_map", max_align=max_align, threshold=threshold)
+        ms_frame, iters, kms, kl, kb, sharded = timed_frames(algo, vms, warm, 1, lambda vm: {"vertex_map": vm})
+        traffic, tcommit = committed_traffic(f"{name}_proj_bytes_per_launch")
+        us = 1e3 * kms / max(kl, 1)
+        ach = (kb / max(kl, 1)) / (us * 1e-6) / 1e9 if kms > 0 else 0.0
+        out[name] = {"workload": f"{h}x{w} vertex maps, projective local map (20 frames), {max_align} alignments"
+                                 + (" (all executed: threshold_delta_pose = 0)" if threshold == 0.0 else " at most"),
+                     "ms_per_frame": ms_frame, "frames_per_sec": 1e3 / ms_frame, "iterations_per_frame": iters, "timed_frames": timed,
+                     "kernel": "proj_icp_tma_kernel", "kernel_avg_us": us, "kernel_launches": int(kl),
+                     "algorithmic_bytes_per_launch": kb / max(kl, 1), "achieved_gbs": ach, "frac_of_measured_hbm_peak": ach / peak,
+                     "traffic_bytes_per_launch": traffic, "traffic_commit": tcommit,
+                     "ranks": world, "tiles_sharded": bool(sharded), "exchange": comm_used[0] if world > 1 else None,
+                     "kernel_note": "per rank: each rank streams its share of the tiles" if world > 1 else None}
+        del algo, vms
+        torch.cuda.empty_cache()
+
+    # ---- cfg4: 5 M-point kd map, one 64x2048 scan registered against it (fixed 5 iterations)
+    target = 5_000_000
+    frames_needed = (target + H * W - 1) // (H * W)
+    world_pts = []
+    for k in range(frames_needed):
+        P = syn.gt_pose(100 + 3 * k)
+        pc = syn.scan(100 + 3 * k, H, W).astype(np.float64)
+        world_pts.append((pc @ P[:3, :3].T + P[:3, 3]).astype(np.float32))
+    cloud = np.concatenate(world_pts)[:target]
+    algo = make_algo(max_align=5, threshold=0.0, data_key="numpy_pc")
+    ctx = algo.ctx
+    cloud_dev = torch.from_numpy(cloud).to(dev)
+    eye = np.eye(4, dtype=np.float32)
+    ctx.call("pls_kdmap_update_points", _lib.ptr(eye), cloud_dev.data_ptr(), cloud.shape[0])
+    Pq = syn.gt_pose(100 + 3 * (frames_needed // 2))
+    q = ((syn.scan(100 + 3 * (frames_needed // 2), H, W).astype(np.float64) + np.array([0.05, -0.03, 0.01])) @ Pq[:3, :3].T
+         + Pq[:3, 3]).astype(np.float32)
+    q_dev = torch.from_numpy(q).to(dev)
+    T, params, losses, it = np.zeros((4, 4), np.float32), np.zeros(6, np.float32), np.zeros(5, np.float32), C.c_int(0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps, ms_reg = 4, []
+    for r in range(reps + 1):
+        if r == 1:
+            ctx.call("pls_profile_enable", 0, 1)
+        barrier()
+        e0.record(stream)
+        ctx.call("pls_register_frame", q_dev.data_ptr(), q.shape[0], None, _lib.ptr(T), _lib.ptr(params), _lib.ptr(losses), C.byref(it))
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        if r >= 1:
+            ms_reg.append(e0.elapsed_time(e1))
+    kms, kl, kb = ctx.profile(0)
+    (ms4,) = max_over_ranks(float(np.mean(ms_reg)))
+    us = 1e3 * kms / max(kl, 1)
+    ach = (kb / max(kl, 1)) / (us * 1e-6) / 1e9 if kms > 0 else 0.0
+    out["cfg4"] = {"workload": f"{cloud.shape[0]} map points (kd map), one 64x2048 scan ({q.shape[0]} queries) registered with 5 ICP "
+                               f"iterations (threshold_delta_pose = 0)",
+                   "ms_per_registration": ms4, "iterations": int(it.value), "kernel": "kd correspondence family (per executed iteration)",
+                   "kernel_avg_us": us, "kernel_launches": int(kl), "algorithmic_bytes_per_launch": kb / max(kl, 1),
+                   "achieved_gbs": ach, "frac_of_measured_hbm_peak": ach / peak, "ranks": world,
+                   "queries_sharded": bool(ctx_sharded(ctx)), "exchange": comm_used[0] if world > 1 else None}
+    return out
+
+
+def ctx_sharded(ctx):
+    n = C.c_int(0)
+    ctx.lib.pls_last_sharded(ctx.handle, C.byref(n))
+    return n.value
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=24)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip config.extra_workloads (cfg3 / cfg4 / cfg5)")
     ap.add_argument("--quick", action="store_true", help="device-resident pass only (for ncu captures)")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
                     help="N>1 exchange: one-shot NVLink peer-to-peer all-reduce fused into the solve kernel, or NCCL")

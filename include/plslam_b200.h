@@ -217,7 +217,8 @@ PLS_API int pls_register_frame(pls_context* ctx, const float* points, int64_t n,
  * (PLS_INPUT_VERTEX_MAP, n ignored).  init_pose [16] or NULL (identity).  On frame 0 the map is initialised and
  * *out_has_pose = 0 (the reference writes no "odometry_pose" then).  out_info (optional,
  * 12 doubles): iterations, final loss, queries used, map points, grid samples, NaN rows dropped,
- * status, key-frame inserted, first non-null pixel x/y/z (vertex-map layout), 0. */
+ * status, key-frame inserted, first non-null pixel x/y/z (vertex-map layout), 1 if the correspondences were
+ * sharded over the ranks of a multi-GPU communicator (0: every rank ran the whole frame). */
 PLS_API int pls_process_frame(pls_context* ctx, const void* data, int layout, int64_t n,
                       const float* init_pose, float* out_pose, float* out_params,
                       int* out_has_pose, double* out_info);
@@ -281,6 +282,13 @@ PLS_API int pls_comm_unique_id(const char* nccl_library, void* out_id_128_bytes)
 PLS_API int pls_comm_p2p_handle(pls_context* ctx, int num_ranks, void* out_handle_64_bytes);
 PLS_API int pls_comm_p2p_init(pls_context* ctx, int num_ranks, int rank, const void* all_handles /* [num_ranks][64] */);
 PLS_API int pls_comm_destroy(pls_context* ctx);
+/* Sharding threshold: a frame's correspondences are split over the ranks only if every rank gets at least this many work
+ * items (queries of the kd map / pixels of the projective map); below it every rank runs the whole frame itself and no
+ * exchange takes place (identical inputs + deterministic kernels = identical poses).  Default 24576 (environment
+ * variable PLS_SHARD_MIN); a negative value restores the default.  Process-wide; every rank must set the same value. */
+PLS_API int pls_set_shard_min(int64_t work_items_per_rank);
+/* 1 if the last ICP of this context split its correspondences over the ranks, else 0. */
+PLS_API int pls_last_sharded(pls_context* ctx, int* out);
 
 /* ---- measurement ---------------------------------------------------------------------
  * CUDA-event timing of one kernel family inside the library's own launches.

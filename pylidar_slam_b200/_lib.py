@@ -72,6 +72,8 @@ _SIGNATURES = {
     "pls_comm_p2p_handle": [_P, _I, _P],
     "pls_comm_p2p_init": [_P, _I, _I, _P],
     "pls_comm_destroy": [_P],
+    "pls_set_shard_min": [_L],
+    "pls_last_sharded": [_P, C.POINTER(_I)],
     "pls_launch_count": [C.POINTER(_L)],
     "pls_profile_enable": [_P, _I, _I],
     "pls_profile_read": [_P, _I, C.POINTER(_D), C.POINTER(_L), C.POINTER(_D), _I],

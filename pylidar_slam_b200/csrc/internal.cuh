@@ -186,6 +186,7 @@ struct pls_context {
     pls::ProjMap pm;
     int frame_index = 0;
     int last_icp_iters = 0;             // iterations the previous frame's ICP executed (sizes the up-front enqueue)
+    bool last_sharded = false;          // the last ICP actually split its correspondences over the ranks
     int sample_pointcloud = 0;          // _sample_pointcloud
     float delta_since_update[16];       // _delta_since_map_update
     pls::DBuf frame_vmap_buf[2];        // [3][H][W] of the current frame (double-buffered: the previous one may

@@ -26,6 +26,12 @@ unsigned long long comm_p2p_next_seq(pls_context* ctx);
 
 namespace {
 
+int64_t g_shard_min_override = -1;  // pls_set_shard_min
+int64_t shard_min_default() {
+    static const int64_t v = getenv("PLS_SHARD_MIN") ? atoll(getenv("PLS_SHARD_MIN")) : 24576;
+    return v;
+}
+
 __global__ void frame_begin_kernel(FrameResult* fr, const float* T0 /*16, device or null*/, int max_iters,
                                    uint32_t* worklist_counts /*2*/) {
     int t = threadIdx.x;
@@ -214,7 +220,20 @@ uint32_t* count_slot(pls_context* ctx, int i) { return reinterpret_cast<uint32_t
 int enqueue_icp_iterations(pls_context* ctx, int64_t query_bound, int first, int last) {
     cudaStream_t st = ctx->stream;
     FrameResult* fr = frame_result_dev(ctx);
-    const int rank = comm_rank(ctx), size = comm_size(ctx);
+    int rank = comm_rank(ctx), size = comm_size(ctx);
+    // Sharding pays only when a rank's share of the correspondences outweighs the exchange it buys: below
+    // PLS_SHARD_MIN work items (queries / pixels) per rank every rank runs the whole iteration itself -- same inputs,
+    // same deterministic kernels, hence the same bits on every rank, and no exchange at all.  (The bound is a host
+    // value every rank computes alike, so the ranks always take the same branch.)
+    const int64_t shard_min = g_shard_min_override >= 0 ? g_shard_min_override : shard_min_default();
+    if (size > 1) {
+        const int64_t work = ctx->cfg.local_map_type == PLS_MAP_KDTREE ? query_bound : (int64_t)ctx->cfg.height * ctx->cfg.width;
+        if (work / size < shard_min) {
+            rank = 0;
+            size = 1;
+        }
+    }
+    ctx->last_sharded = size > 1;
     int last_blocks = 0;
     for (int it = first; it < last; ++it) {
         int blocks;
@@ -494,7 +513,7 @@ void process_frame_device(pls_context* ctx, const void* data_void, int layout, i
         out_info[6] = (double)h->status;
         out_info[7] = insert ? 1.0 : 0.0;
         out_info[8] = h->first_pt[0]; out_info[9] = h->first_pt[1]; out_info[10] = h->first_pt[2];
-        out_info[11] = 0.0;
+        out_info[11] = ctx->last_sharded ? 1.0 : 0.0;  // the correspondences were split over the ranks
     }
 }
 
@@ -520,6 +539,18 @@ int pls_map_init(pls_context* ctx) {
     sync_all(ctx);
     kdmap_reset(ctx);
     projmap_reset(ctx);
+    PLS_API_END(ctx)
+}
+
+int pls_set_shard_min(int64_t work_items_per_rank) {
+    g_shard_min_override = work_items_per_rank;
+    return PLS_OK;
+}
+
+int pls_last_sharded(pls_context* ctx, int* out) {
+    PLS_API_BEGIN(ctx)
+    PLS_REQUIRE(out, "pls_last_sharded: null output");
+    *out = ctx->last_sharded ? 1 : 0;
     PLS_API_END(ctx)
 }
 
