@@ -57,12 +57,22 @@ struct Comm {
     void* xchg = nullptr;            // this rank's exchange buffer [2][size] slots (written by the peers)
     std::vector<void*> peer_ptrs;    // every rank's exchange buffer mapped into this process (own = xchg)
     void* peer_table_dev = nullptr;  // device copy of peer_ptrs
-    unsigned long long seq = 0;
+    unsigned long long* seq_dev = nullptr;  // number of exchanges this rank has EXECUTED (device side: a launch that finds
+                                            // the frame converged does not count) -- the round number of the next one
+    double* allreduce_buf = nullptr;        // NCCL mode: the sums in flight (kept apart from the FrameResult)
 };
 
 bool comm_is_p2p(pls_context* ctx) { return ctx->comm && ctx->comm->p2p; }
 void* comm_p2p_peers(pls_context* ctx) { return ctx->comm->peer_table_dev; }
-unsigned long long comm_p2p_next_seq(pls_context* ctx) { return ++ctx->comm->seq; }
+unsigned long long* comm_p2p_seq(pls_context* ctx) { return ctx->comm->seq_dev; }
+double* comm_allreduce_buffer(pls_context* ctx) {
+    Comm* c = ctx->comm;
+    if (!c->allreduce_buf) {
+        PLS_CUDA(cudaMalloc(&c->allreduce_buf, NACC * sizeof(double)));
+        PLS_CUDA(cudaMemset(c->allreduce_buf, 0, NACC * sizeof(double)));
+    }
+    return c->allreduce_buf;
+}
 
 int comm_rank(pls_context* ctx) { return ctx->comm ? ctx->comm->rank : 0; }
 int comm_size(pls_context* ctx) { return ctx->comm ? ctx->comm->size : 1; }
@@ -81,7 +91,10 @@ void comm_free(pls_context* ctx) {
         for (int r = 0; r < (int)ctx->comm->peer_ptrs.size(); ++r)
             if (r != ctx->comm->rank && ctx->comm->peer_ptrs[r]) cudaIpcCloseMemHandle(ctx->comm->peer_ptrs[r]);
         if (ctx->comm->peer_table_dev) cudaFree(ctx->comm->peer_table_dev);
+        if (ctx->comm->seq_dev) cudaFree(ctx->comm->seq_dev);
+        if (ctx->comm->xchg) cudaFree(ctx->comm->xchg);
     }
+    if (ctx->comm->allreduce_buf) cudaFree(ctx->comm->allreduce_buf);
     if (ctx->comm->comm) ctx->comm->api.CommDestroy(ctx->comm->comm);
     delete ctx->comm;
     ctx->comm = nullptr;
@@ -133,8 +146,8 @@ int pls_comm_init(pls_context* ctx, int num_ranks, int rank, const void* nccl_un
     PLS_API_END(ctx)
 }
 
-// ---- one-shot P2P mode: step 1, every rank allocates its exchange buffer and exports an IPC handle
-static void* g_p2p_pending_xchg = nullptr;  // handed from pls_comm_p2p_handle to pls_comm_p2p_init
+// ---- one-shot P2P mode: step 1, every rank allocates its exchange buffer and exports an IPC handle; the buffer waits
+// in the context (p2p_pending_xchg) for step 2
 
 int pls_comm_p2p_handle(pls_context* ctx, int num_ranks, void* out_handle_64_bytes) {
     PLS_API_BEGIN(ctx)
@@ -147,15 +160,15 @@ int pls_comm_p2p_handle(pls_context* ctx, int num_ranks, void* out_handle_64_byt
     cudaIpcMemHandle_t h;
     PLS_CUDA(cudaIpcGetMemHandle(&h, buf));
     memcpy(out_handle_64_bytes, &h, 64);
-    if (g_p2p_pending_xchg) cudaFree(g_p2p_pending_xchg);
-    g_p2p_pending_xchg = buf;
+    if (ctx->p2p_pending_xchg) cudaFree(ctx->p2p_pending_xchg);
+    ctx->p2p_pending_xchg = buf;
     PLS_API_END(ctx)
 }
 
 // step 2 (after the host program all-gathered the handles): map every peer's buffer
 int pls_comm_p2p_init(pls_context* ctx, int num_ranks, int rank, const void* all_handles) {
     PLS_API_BEGIN(ctx)
-    PLS_REQUIRE(num_ranks >= 2 && rank >= 0 && rank < num_ranks && all_handles && g_p2p_pending_xchg,
+    PLS_REQUIRE(num_ranks >= 2 && rank >= 0 && rank < num_ranks && all_handles && ctx->p2p_pending_xchg,
                 "pls_comm_p2p_init: call pls_comm_p2p_handle first");
     sync_all(ctx);
     comm_free(ctx);
@@ -163,8 +176,8 @@ int pls_comm_p2p_init(pls_context* ctx, int num_ranks, int rank, const void* all
     c->p2p = true;
     c->rank = rank;
     c->size = num_ranks;
-    c->xchg = g_p2p_pending_xchg;
-    g_p2p_pending_xchg = nullptr;
+    c->xchg = ctx->p2p_pending_xchg;
+    ctx->p2p_pending_xchg = nullptr;
     c->peer_ptrs.assign(num_ranks, nullptr);
     for (int r = 0; r < num_ranks; ++r) {
         if (r == rank) {
@@ -176,10 +189,16 @@ int pls_comm_p2p_init(pls_context* ctx, int num_ranks, int rank, const void* all
         cudaError_t e = cudaIpcOpenMemHandle(&c->peer_ptrs[r], h, cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) {
             std::string msg = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e);
+            cudaGetLastError();
+            for (int o = 0; o < r; ++o)  // unmap what was mapped so far, release this rank's own buffer
+                if (o != rank && c->peer_ptrs[o]) cudaIpcCloseMemHandle(c->peer_ptrs[o]);
+            cudaFree(c->xchg);
             delete c;
             throw pls::Error{PLS_E_COMM, msg};
         }
     }
+    PLS_CUDA(cudaMalloc(&c->seq_dev, sizeof(unsigned long long)));
+    PLS_CUDA(cudaMemset(c->seq_dev, 0, sizeof(unsigned long long)));
     PLS_CUDA(cudaMalloc(&c->peer_table_dev, num_ranks * sizeof(void*)));
     PLS_CUDA(cudaMemcpy(c->peer_table_dev, c->peer_ptrs.data(), num_ranks * sizeof(void*), cudaMemcpyHostToDevice));
     ctx->comm = c;

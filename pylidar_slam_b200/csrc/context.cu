@@ -294,6 +294,7 @@ int pls_destroy(pls_context* ctx) {
     cudaStreamSynchronize(ctx->stream_map);
     cudaStreamSynchronize(ctx->stream_main);
     comm_free(ctx);
+    if (ctx->p2p_pending_xchg) cudaFree(ctx->p2p_pending_xchg);
     for (auto& b : ctx->stage_in) b.release();
     for (auto& b : ctx->stage_out) b.release();
     for (auto& b : ctx->tmp) b.release();

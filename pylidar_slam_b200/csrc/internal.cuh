@@ -204,6 +204,7 @@ struct pls_context {
     int64_t last_query_count = 0;
 
     pls::Comm* comm = nullptr;
+    void* p2p_pending_xchg = nullptr;   // exchange buffer exported by pls_comm_p2p_handle, adopted by pls_comm_p2p_init
     pls::ProfileSlot prof[pls::kProfileSlots];
 };
 

@@ -22,7 +22,8 @@ int comm_rank(pls_context* ctx);
 int comm_size(pls_context* ctx);
 bool comm_is_p2p(pls_context* ctx);
 void* comm_p2p_peers(pls_context* ctx);
-unsigned long long comm_p2p_next_seq(pls_context* ctx);
+unsigned long long* comm_p2p_seq(pls_context* ctx);
+double* comm_allreduce_buffer(pls_context* ctx);
 
 namespace {
 
@@ -49,28 +50,29 @@ __global__ void frame_begin_kernel(FrameResult* fr, const float* T0 /*16, device
 }
 
 
-__global__ void __launch_bounds__(256) reduce_partials_kernel(FrameResult* fr, const double* __restrict__ partials,
-                                                              int num_blocks) {
+// NCCL mode, before the all-reduce: this rank's sums go to the exchange buffer `out` (not into the FrameResult: the
+// all-reduce runs in place, and launches enqueued after convergence must leave the frame's result alone).
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const FrameResult* fr, const double* __restrict__ partials,
+                                                              int num_blocks, double* __restrict__ out) {
     if (fr->done) return;
     __shared__ double sums[NACC];
     sum_partials_256(partials, num_blocks, sums);
     __syncthreads();
-    if (threadIdx.x < NACC) fr->last_sums[threadIdx.x] = sums[threadIdx.x];
+    if (threadIdx.x < NACC) out[threadIdx.x] = sums[threadIdx.x];
 }
 
-// K7: normal-equation solve + ICP bookkeeping (256 threads).  num_blocks == 0: last_sums already holds
-// the (all-reduced) sums.
+// K7: normal-equation solve + ICP bookkeeping (256 threads).  num_blocks == 0: `reduced` holds the (all-reduced) sums.
 __global__ void __launch_bounds__(256) icp_step_kernel(FrameResult* fr, const double* __restrict__ partials,
-                                                       int num_blocks, float threshold_delta) {
+                                                       int num_blocks, const double* __restrict__ reduced, float threshold_delta) {
     if (fr->done) return;
     __shared__ double sums[NACC];
     if (num_blocks > 0) {
         sum_partials_256(partials, num_blocks, sums);
     } else if (threadIdx.x < NACC) {
-        sums[threadIdx.x] = fr->last_sums[threadIdx.x];
+        sums[threadIdx.x] = reduced[threadIdx.x];
     }
     __syncthreads();
-    if (num_blocks > 0 && threadIdx.x < NACC) fr->last_sums[threadIdx.x] = sums[threadIdx.x];
+    if (threadIdx.x < NACC) fr->last_sums[threadIdx.x] = sums[threadIdx.x];
     if (threadIdx.x != 0) return;
     icp_solve_and_update(fr, sums, threshold_delta);
 }
@@ -91,13 +93,18 @@ struct P2PSlot {
 static_assert(sizeof(P2PSlot) == 256, "P2PSlot must match comm.cu's kP2PSlotBytes");
 __global__ void __launch_bounds__(256)
 icp_step_p2p_kernel(FrameResult* fr, const double* __restrict__ partials, int num_blocks, float threshold_delta,
-                    P2PSlot* const* __restrict__ peers, int world, int rank, unsigned long long seq) {
+                    P2PSlot* const* __restrict__ peers, int world, int rank, unsigned long long* seq_counter) {
     if (fr->done) return;
     __shared__ double sums[NACC];
     __shared__ int timed_out;
-    if (threadIdx.x == 0) timed_out = 0;
+    __shared__ unsigned long long s_seq;
+    if (threadIdx.x == 0) {
+        timed_out = 0;
+        s_seq = ++(*seq_counter);  // this exchange's round
+    }
     sum_partials_256(partials, num_blocks, sums);
     __syncthreads();
+    const unsigned long long seq = s_seq;
     const int parity = (int)(seq & 1ull);
     if (threadIdx.x < NACC)
         for (int r = 0; r < world; ++r) peers[r][parity * world + rank].sums[threadIdx.x] = sums[threadIdx.x];
@@ -245,17 +252,20 @@ int enqueue_icp_iterations(pls_context* ctx, int64_t query_bound, int first, int
         if (solved) continue;
         if (size > 1 && comm_is_p2p(ctx)) {
             icp_step_p2p_kernel<<<1, 256, 0, st>>>(fr, ctx->partials.as<double>(), blocks, ctx->cfg.threshold_delta_pose,
-                                                   (P2PSlot* const*)comm_p2p_peers(ctx), size, rank, comm_p2p_next_seq(ctx));
+                                                   (P2PSlot* const*)comm_p2p_peers(ctx), size, rank, comm_p2p_seq(ctx));
             PLS_CHECK_LAUNCH();
             continue;
         }
+        const double* reduced = nullptr;
         if (size > 1) {
-            reduce_partials_kernel<<<1, 256, 0, st>>>(fr, ctx->partials.as<double>(), blocks);
+            double* buf = comm_allreduce_buffer(ctx);
+            reduce_partials_kernel<<<1, 256, 0, st>>>(fr, ctx->partials.as<double>(), blocks, buf);
             PLS_CHECK_LAUNCH();
-            comm_allreduce_sums(ctx, fr->last_sums);
+            comm_allreduce_sums(ctx, buf);
+            reduced = buf;
             blocks = 0;
         }
-        icp_step_kernel<<<1, 256, 0, st>>>(fr, ctx->partials.as<double>(), blocks, ctx->cfg.threshold_delta_pose);
+        icp_step_kernel<<<1, 256, 0, st>>>(fr, ctx->partials.as<double>(), blocks, reduced, ctx->cfg.threshold_delta_pose);
         PLS_CHECK_LAUNCH();
     }
     return last_blocks;

@@ -237,6 +237,37 @@ __global__ void query_resolve_kernel(unsigned long long* __restrict__ zbuf, cons
     }
 }
 
+// sqrtf(a) < sqrtf(b) for a, b >= 0 (b may be +inf), WITHOUT the square roots in the common case.  The reference takes the
+// arg-min over distances (torch.norm, then torch.min keeps the first minimum: geometry.py:424-428), and two different
+// squared distances can share one correctly rounded root -- but only if they lie within 2^-22 of each other (the
+// pre-image of a float under sqrt is at most that wide, relatively).  Outside that band the squares decide; inside it
+// (about one comparison in a million) both roots are taken.
+__device__ __forceinline__ bool dist_less(float a2, float b2) {
+    if (!(a2 < b2)) return false;
+    if (a2 < b2 * 0.99999952f) return true;  // 1 - 2^-21
+    return sqrtf(a2) < sqrtf(b2);
+}
+
+// acc += [ (wJ)(wJ)^T upper, (wJ)(wr), (wr)^2, r^2, 1 ] in float32: a thread of the tile-streaming kernel meets a
+// handful of pixels only (tiles / CTAs), their sum goes to float64 before the block reduction -- each partial sum
+// carries ~1e-7 relative rounding, the half-million-term totals stay far more accurate than the reference's float32
+// sgemm while the accumulators cost 30 registers instead of 60
+__device__ __forceinline__ void accumulate_normal_equations_f32(float* acc, const float* J, float w, float wr, float r) {
+    float wj[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) wj[a] = J[a] * w;
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = a; b < 6; ++b) acc[k++] += wj[a] * wj[b];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) acc[21 + a] += wj[a] * wr;
+    acc[27] += wr * wr;
+    acc[28] += r * r;
+    acc[29] += 1.0f;
+}
+
 // argmin over the K candidates at one pixel; returns false if none is valid
 __device__ __forceinline__ bool pixel_argmin(const float* __restrict__ model_v, const float4* __restrict__ model_n, int K,
                                              int kcap, int64_t pix, const float* p, float* q, float* n) {
@@ -366,9 +397,9 @@ proj_icp_tma_kernel(const float* __restrict__ model_v, const float4* __restrict_
             if (t < tile_end) issue(t, s);
         }
     }
-    double acc[NACC];
+    float acc[NACC];
 #pragma unroll
-    for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
+    for (int a = 0; a < NACC; ++a) acc[a] = 0.f;
     bool pend = false;
     float pp[3] = {0.f, 0.f, 0.f}, pq[3] = {0.f, 0.f, 0.f}, pn[3] = {0.f, 0.f, 0.f};
     int it = 0;
@@ -393,32 +424,29 @@ proj_icp_tma_kernel(const float* __restrict__ model_v, const float4* __restrict_
         const bool has = tp.w != 0.f;
         if (has) {
             const float* st = stage_base + (size_t)s * stage_floats + threadIdx.x;
-            float best = __int_as_float(0x7f800000);
+            float best2 = __int_as_float(0x7f800000);  // squared distance of the best candidate so far
 #pragma unroll 4
             for (int k = 0; k < ktma; ++k) {
                 const float x = st[(3 * k) * PT_TILE], y = st[(3 * k + 1) * PT_TILE], z = st[(3 * k + 2) * PT_TILE];
-                if (fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) > 0.f) {
-                    const float dx = p[0] - x, dy = p[1] - y, dz = p[2] - z;
-                    const float d = sqrtf(dx * dx + dy * dy + dz * dz);
-                    if (d < best) {  // torch.min keeps the first minimum
-                        best = d;
-                        kbest = k;
-                        q[0] = x; q[1] = y; q[2] = z;
-                    }
+                const float dx = p[0] - x, dy = p[1] - y, dz = p[2] - z;
+                const float d2 = dx * dx + dy * dy + dz * dz;
+                // torch.min keeps the first minimum; null candidates (all channels 0) do not compete
+                if (fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) > 0.f && dist_less(d2, best2)) {
+                    best2 = d2;
+                    kbest = k;
+                    q[0] = x; q[1] = y; q[2] = z;
                 }
             }
 #pragma unroll
             for (int j = 0; j < KDIRECT_MAX; ++j) {
                 if (j < K - ktma) {
                     const float x = dv[3 * j], y = dv[3 * j + 1], z = dv[3 * j + 2];
-                    if (fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) > 0.f) {
-                        const float dx = p[0] - x, dy = p[1] - y, dz = p[2] - z;
-                        const float d = sqrtf(dx * dx + dy * dy + dz * dz);
-                        if (d < best) {
-                            best = d;
-                            kbest = ktma + j;
-                            q[0] = x; q[1] = y; q[2] = z;
-                        }
+                    const float dx = p[0] - x, dy = p[1] - y, dz = p[2] - z;
+                    const float d2 = dx * dx + dy * dy + dz * dz;
+                    if (fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) > 0.f && dist_less(d2, best2)) {
+                        best2 = d2;
+                        kbest = ktma + j;
+                        q[0] = x; q[1] = y; q[2] = z;
                     }
                 }
             }
@@ -435,7 +463,7 @@ proj_icp_tma_kernel(const float* __restrict__ model_v, const float4* __restrict_
             float J[6];
             const float r = p2plane_residual_jacobian_identity(pp, pq, pn, J);
             const float w = ls_weight<float>(scheme, sigma, r, pp, pq);
-            accumulate_normal_equations<float>(acc, J, w, r * w, r);
+            accumulate_normal_equations_f32(acc, J, w, r * w, r);
         }
         // ... then issue THIS tile's winner-normal gather straight into the pending registers (no copy that
         // would force the load to complete here)
@@ -451,9 +479,12 @@ proj_icp_tma_kernel(const float* __restrict__ model_v, const float4* __restrict_
         float J[6];
         const float r = p2plane_residual_jacobian_identity(pp, pq, pn, J);
         const float w = ls_weight<float>(scheme, sigma, r, pp, pq);
-        accumulate_normal_equations<float>(acc, J, w, r * w, r);
+        accumulate_normal_equations_f32(acc, J, w, r * w, r);
     }
-    block_reduce_store<PT_TILE>(acc, partials + (size_t)blockIdx.x * NACC);
+    double acc64[NACC];
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) acc64[a] = (double)acc[a];
+    block_reduce_store<PT_TILE>(acc64, partials + (size_t)blockIdx.x * NACC);
 }
 
 // per-pixel association for the fine-grained API: flag + (q, n, p)

@@ -62,6 +62,16 @@ cellsweep)
         echo "== PLS_KD_CELL=$cell"
         PLS_KD_CELL=$cell timeout 200 python tools/kd_profile.py 0 7 9 2>&1 | tail -3 | tee -a gpurun_out/${TAG}_cellsweep.log
     done ;;
+projtests)
+    timeout 400 python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 200 -rf -p no:cacheprovider -k "proj or cfg3 or cfg5 or a5 or a6 or neighbors" > gpurun_out/${TAG}_pytest_proj.log 2>&1
+    tail -8 gpurun_out/${TAG}_pytest_proj.log ;;
+projsweep)
+    for kd in ${KDIRECTS:-4 8}; do for stg in ${STAGES:-2 3}; do
+        echo "== PLS_PROJ_KDIRECT=$kd PLS_PROJ_STAGES=$stg"
+        PLS_PROJ_KDIRECT=$kd PLS_PROJ_STAGES=$stg timeout 200 python tools/profile_proj.py 128 4096 26 20 2>&1 | tail -1 | tee -a gpurun_out/${TAG}_projsweep.log
+    done; done ;;
+quicktime)
+    timeout 120 python tools/quick_time.py 40 tensor 2>&1 | tail -4 | tee gpurun_out/${TAG}_quicktime.log ;;
 stats)
     PLS_KD_STATS=1 timeout 120 python tools/quick_time.py 30 tensor 2>&1 | tail -6 | tee gpurun_out/${TAG}_kd_stats.log ;;
 quick)
