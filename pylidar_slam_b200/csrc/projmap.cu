@@ -424,18 +424,22 @@ proj_icp_tma_kernel(const float* __restrict__ model_v, const float4* __restrict_
         const bool has = tp.w != 0.f;
         if (has) {
             const float* st = stage_base + (size_t)s * stage_floats + threadIdx.x;
+            // Branch-free arg-min on squared distances.  `band` records whether any comparison fell inside the
+            // 2^-22 band where the squares cannot decide (dist_less): the pixel is then redone with the roots.
             float best2 = __int_as_float(0x7f800000);  // squared distance of the best candidate so far
+            bool band = false;
 #pragma unroll 4
             for (int k = 0; k < ktma; ++k) {
                 const float x = st[(3 * k) * PT_TILE], y = st[(3 * k + 1) * PT_TILE], z = st[(3 * k + 2) * PT_TILE];
                 const float dx = p[0] - x, dy = p[1] - y, dz = p[2] - z;
                 const float d2 = dx * dx + dy * dy + dz * dz;
                 // torch.min keeps the first minimum; null candidates (all channels 0) do not compete
-                if (fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) > 0.f && dist_less(d2, best2)) {
-                    best2 = d2;
-                    kbest = k;
-                    q[0] = x; q[1] = y; q[2] = z;
-                }
+                const bool live = fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) > 0.f;
+                const bool lt = live && d2 < best2 * 0.99999952f;
+                band |= live && !lt && d2 < best2;
+                best2 = lt ? d2 : best2;
+                kbest = lt ? k : kbest;
+                q[0] = lt ? x : q[0]; q[1] = lt ? y : q[1]; q[2] = lt ? z : q[2];
             }
 #pragma unroll
             for (int j = 0; j < KDIRECT_MAX; ++j) {
@@ -443,10 +447,33 @@ proj_icp_tma_kernel(const float* __restrict__ model_v, const float4* __restrict_
                     const float x = dv[3 * j], y = dv[3 * j + 1], z = dv[3 * j + 2];
                     const float dx = p[0] - x, dy = p[1] - y, dz = p[2] - z;
                     const float d2 = dx * dx + dy * dy + dz * dz;
-                    if (fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) > 0.f && dist_less(d2, best2)) {
-                        best2 = d2;
-                        kbest = ktma + j;
-                        q[0] = x; q[1] = y; q[2] = z;
+                    const bool live = fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) > 0.f;
+                    const bool lt = live && d2 < best2 * 0.99999952f;
+                    band |= live && !lt && d2 < best2;
+                    best2 = lt ? d2 : best2;
+                    kbest = lt ? ktma + j : kbest;
+                    q[0] = lt ? x : q[0]; q[1] = lt ? y : q[1]; q[2] = lt ? z : q[2];
+                }
+            }
+            if (band) {  // about one pixel in 50 000: the reference's arg-min over the roots, first minimum wins
+                float best = __int_as_float(0x7f800000);
+                kbest = -1;
+                for (int k = 0; k < K; ++k) {
+                    float x, y, z;
+                    if (k < ktma) {
+                        x = st[(3 * k) * PT_TILE]; y = st[(3 * k + 1) * PT_TILE]; z = st[(3 * k + 2) * PT_TILE];
+                    } else {
+                        const float* gk = model_v + (size_t)tile * ((size_t)kcap * 3 * PT_TILE) + (size_t)k * 3 * PT_TILE + threadIdx.x;
+                        x = __ldg(gk); y = __ldg(gk + PT_TILE); z = __ldg(gk + 2 * PT_TILE);
+                    }
+                    if (fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) > 0.f) {
+                        const float dx = p[0] - x, dy = p[1] - y, dz = p[2] - z;
+                        const float d = sqrtf(dx * dx + dy * dy + dz * dz);
+                        if (d < best) {
+                            best = d;
+                            kbest = k;
+                            q[0] = x; q[1] = y; q[2] = z;
+                        }
                     }
                 }
             }

@@ -70,6 +70,13 @@ projsweep)
         echo "== PLS_PROJ_KDIRECT=$kd PLS_PROJ_STAGES=$stg"
         PLS_PROJ_KDIRECT=$kd PLS_PROJ_STAGES=$stg timeout 200 python tools/profile_proj.py 128 4096 26 20 2>&1 | tail -1 | tee -a gpurun_out/${TAG}_projsweep.log
     done; done ;;
+ncuproj)
+    timeout 300 ncu --set full --clock-control none --import-source on -k regex:'proj_icp_tma_kernel' \
+        --launch-skip ${SKIP:-400} --launch-count ${COUNT:-2} -f -o gpurun_out/${TAG}_proj python tools/profile_proj.py 128 4096 26 20 > gpurun_out/${TAG}_ncu_proj.log 2>&1
+    tail -2 gpurun_out/${TAG}_ncu_proj.log
+    ncu -i gpurun_out/${TAG}_proj.ncu-rep --page raw --csv > gpurun_out/${TAG}_proj_raw.csv 2>/dev/null
+    ncu -i gpurun_out/${TAG}_proj.ncu-rep --page source --csv > gpurun_out/${TAG}_proj_source.csv 2>/dev/null
+    ls -la gpurun_out/${TAG}_proj* ;;
 quicktime)
     timeout 120 python tools/quick_time.py 40 tensor 2>&1 | tail -4 | tee gpurun_out/${TAG}_quicktime.log ;;
 stats)
