@@ -4,6 +4,8 @@ Everything here needs a GPU (`-m gpu`).  Tolerances are stated per test:
   * float32 image ops: pixel assignment exact up to points within an ulp of a rounding boundary
   * poses: 1e-4 relative translation, 1e-5 rad rotation (BASELINE.json north_star)
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -102,8 +104,21 @@ def test_a3_projection_full_size_vs_oracle(b200, orc, syn, H, W):
     ref = orc.Projector(H, W).build_projection_map(torch.from_numpy(both))[0].numpy()
     out = b200.SphericalProjector(height=H, width=W, up_fov=3.0, down_fov=-24.0).build_projection_map(both)[0]
     assert _pixel_mismatch(out, ref) <= 1e-3
+    # ... and EVERY differing pixel is accounted for: the z-buffer itself is exact integer work; the only float step
+    # before it is the pixel coordinate (atan2 / asin: CUDA's libm and the host's differ by a couple of ulp), so a
+    # pixel may differ only if some input point has a coordinate within 2e-3 px of a rounding boundary there
+    row, col = orc.Projector(H, W).pixels(torch.from_numpy(both))
+    rc = np.stack([row[0].numpy(), col[0].numpy()], axis=1).astype(np.float64)             # float (row, col) per point
+    near = (np.abs(rc - np.floor(rc) - 0.5) < 2e-3).any(axis=1) & np.isfinite(rc).all(axis=1)
+    touched = np.zeros((H, W), bool)
+    for r, c in rc[near]:
+        for rr in (int(np.floor(r)), int(np.ceil(r))):
+            for cc in (int(np.floor(c)), int(np.ceil(c))):
+                if 0 <= rr < H and 0 <= cc < W:
+                    touched[rr, cc] = True
+    differing = np.any(out != ref, axis=0)
+    assert not (differing & ~touched).any(), int((differing & ~touched).sum())
     # closest-wins property, independent of the oracle: every written pixel holds an input point
-    # and no input point projecting to that pixel is closer (checked on a sample of pixels)
     r_out = np.linalg.norm(out, axis=0)
     assert np.all(r_out[r_out > 0] > 0.5)
 
@@ -242,6 +257,40 @@ def test_kd_exact_nn_vs_bruteforce(b200, M, N):
         dmin = dmin ** 2
     d_mine = ((q.astype(np.float64) - res.neighbor_points.astype(np.float64)) ** 2).sum(-1)
     np.testing.assert_allclose(d_mine, dmin, rtol=1e-5, atol=1e-9)
+
+
+def test_a9_normals_per_point_bound(b200, syn):
+    """Every returned normal against an independent float64 computation from the exact 10 nearest map neighbours of
+    the matched point (scipy cKDTree on the same float32 map): |sin angle| <= 2e-5 * lambda_max / gap, gap =
+    lambda_mid - lambda_min of the point's second-moment matrix -- the perturbation bound of an eigenvector for the
+    float32 rounding of the moments (~1e-6 lambda_max, as in the reference).  Only points whose plane direction is
+    provably ill-defined (gap < 1e-3 lambda_max: the reference's own SVD is arbitrary there) are excluded, and they
+    must be rare."""
+    from scipy.spatial import cKDTree
+    H, W = 32, 1024
+    lm = b200.KdTreeLocalMap(b200.KdTreeLocalMapConfig(local_map_size=4))
+    lm.init()
+    for k in range(4):
+        rel = np.eye(4, dtype=np.float32) if k == 0 else syn.gt_relative_pose(k).astype(np.float32)
+        s, _ = b200.grid_sample(syn.scan(k, H, W), 0.3)
+        lm.update(rel[None], new_pc_data=s)
+    m = lm.points()
+    q, _ = b200.grid_sample(syn.scan(4, H, W), 0.3)
+    res = lm.nearest_neighbor_search(q)
+    tree = cKDTree(m.astype(np.float64))
+    _, i1 = tree.query(res.neighbor_points.astype(np.float64))
+    assert np.abs(m[i1] - res.neighbor_points).max() == 0.0              # the matches are map points
+    d11, i11 = tree.query(m[i1].astype(np.float64), k=12)
+    unique_set = d11[:, 11] > d11[:, 10] * (1 + 1e-6)                     # no tie at the 10th neighbour
+    diff = (m[i11[:, 1:11]] - m[i1][:, None, :]).astype(np.float64)
+    C = (diff[:, :, :, None] * diff[:, :, None, :]).mean(axis=1)
+    w, v = np.linalg.eigh(C)
+    gap = (w[:, 1] - w[:, 0]) / np.maximum(w[:, 2], 1e-300)
+    sin = np.linalg.norm(np.cross(res.neighbor_normals.astype(np.float64), v[:, :, 0]), axis=1)
+    ok = unique_set & (gap > 1e-3)
+    assert ok.mean() > 0.97, ok.mean()
+    assert (sin[ok] <= 2e-5 / gap[ok] + 2e-7).all(), float((sin[ok] * gap[ok]).max())
+    assert np.abs(np.linalg.norm(res.neighbor_normals, axis=1) - 1).max() <= 1e-6
 
 
 def test_kd_map_lifecycle_vs_oracle(b200, orc, syn):
@@ -489,18 +538,35 @@ def test_a5_projective_map_lifecycle_vs_oracle(b200, orc, syn):
 PROJ_SMALL = [("proj_vmap", "vertex_map", "vertex_map"), ("proj_ndarray", "ndarray", "numpy_pc")]
 
 
+def measured_sensitivity(case):
+    """Largest pose deviation of the UNMODIFIED reference from itself when the last bit of its input coordinates is
+    perturbed (tests/golden/sensitivity.json, written by tests/golden/sensitivity.py in the build container)."""
+    import json
+    d = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sensitivity.json")))["cases"][case]
+    return d["max_rel_translation"], d["max_rotation_rad"]
+
+
+def relaxed_tolerance(case, wanted):
+    """A translation tolerance above the north star's 1e-4 is admissible only up to 1.5 x what the reference itself
+    moves under 1-ulp input noise in that configuration."""
+    sens_t, _ = measured_sensitivity(case)
+    assert wanted <= max(1e-4, 1.5 * sens_t), (case, wanted, sens_t)
+    return wanted
+
+
 @pytest.mark.parametrize("name,layout,key", PROJ_SMALL)
 def test_icp_projective_small_vs_reference_golden(b200, syn, golden_icp_small, name, layout, key):
     """32x512 projective ICP is numerically ill-conditioned in the REFERENCE itself: its normals come from
     a float32 inverse of the uncentred second-moment matrix and 8 iterations do not converge.  Measured on
-    the CPU oracle: 1-ulp (1.2e-7 relative) noise on the input scans moves its own poses by up to 4.6e-4
-    relative translation within 6 frames (3 seeds).  The translation tolerance here is therefore 6e-4
-    (rotation stays 1e-5); the full-size config-3 test below keeps the strict 1e-4."""
+    the unmodified reference (tests/golden/sensitivity.py -> sensitivity.json): 1-ulp noise on the input scans
+    moves its own poses by up to 2.8e-3 relative translation / 2.6e-5 rad within 6 frames (3 seeds).  The translation
+    tolerance here is 6e-4 -- a fifth of that -- and the rotation stays at 1e-5; the full-size config-3 test below
+    keeps the strict 1e-4."""
     algo = _make(b200, "projective", 32, 512, key, 8, lm_size=4)
     iters = []
     poses = _drive(algo, _frames(syn, b200.grid_sample, layout, 32, 512, None), 7, iters)
     flips, worst = check_pose_sequence(poses, iters, golden_icp_small[f"{name}_poses"], golden_icp_small[f"{name}_losses"],
-                                       name=name, tol_t=6e-4)
+                                       name=name, tol_t=relaxed_tolerance(f"{name}_32x512", 6e-4))
     print(name, "flips", flips, "worst", worst)
 
 
@@ -549,8 +615,9 @@ def test_cfg4_5M_point_map_exact_search(b200):
 def test_cfg5_projective_128x4096_20_iterations(b200, orc, syn):
     """BASELINE config 5 shape: 128x4096 vertex-map input, projective map, 20 alignments forced
     (threshold_delta_pose = 0).  GPU vs the CPU oracle on identical frames.  Tolerance: strict on the first
-    registered frame; 3e-4 relative translation on the second (the reference's float32 normal maps amplify
-    1-ulp input noise to 8e-5 by then, see tests/test_gpu_parity.py::test_icp_projective_small...)."""
+    registered frame; 3e-4 relative translation on the second -- the unmodified reference moves by 3.2e-4 on the
+    first and 1.05e-3 on the second frame under 1-ulp input noise (tests/golden/sensitivity.json,
+    cfg5_proj_128x4096_20it: its float32 normal maps amplify the last bit)."""
     H, W = 128, 4096
     algo = _make(b200, "projective", H, W, "vertex_map", 20, thr=0.0)
     ocfg = orc.ICPConfig(max_num_alignments=20, data_key="vertex_map", local_map="projective", local_map_size=20,
@@ -567,14 +634,18 @@ def test_cfg5_projective_128x4096_20_iterations(b200, orc, syn):
             continue
         assert int(algo.last_info[0]) == 20
         dt, ang = pose_errors(da["odometry_pose"], db["odometry_pose"])
-        assert dt <= (1e-4 if k == 1 else 3e-4) and ang <= 1e-5, (k, dt, ang)
+        assert dt <= (1e-4 if k == 1 else relaxed_tolerance("cfg5_proj_128x4096_20it", 3e-4)) and ang <= 1e-5, (k, dt, ang)
         pa, pb = da["odometry_pose"].astype(np.float64), db["odometry_pose"].astype(np.float64)
 
 
 def test_nan_rows_and_nan_pixels_match_oracle(b200, orc, syn):
     """remove_nan / modify_nan_pmap (utils.py:169-196): NaN rows are dropped from the point layouts, NaN pixels
-    are zeroed in the vertex-map layout; poses follow the oracle fed with the same corrupted inputs."""
+    are zeroed in the vertex-map layout; poses follow the oracle fed with the same corrupted inputs.  Tolerances from the
+    reference's own sensitivity to the last input bit (tests/golden/sensitivity.json): the small kd case (voxel 0.4
+    subsample of a 32x512 scan, 8 fixed iterations) moves by 1.45e-3, the projective one by 1.9e-5 -- 6e-4 and the
+    north star's 1e-4 respectively."""
     H, W = 32, 512
+    tol = {"ndarray": relaxed_tolerance("nan_kd_ndarray_32x512", 6e-4), "vertex_map": 1e-4}
     for layout, key in (("ndarray", "numpy_pc"), ("vertex_map", "vertex_map")):
         lm = "kdtree" if layout == "ndarray" else "projective"
         algo = _make(b200, lm, H, W, key, 8, lm_size=4, thr=0.0)
@@ -598,7 +669,7 @@ def test_nan_rows_and_nan_pixels_match_oracle(b200, orc, syn):
             if k == 0:
                 continue
             dt, ang = pose_errors(da["odometry_pose"], db["odometry_pose"])
-            assert dt <= 6e-4 and ang <= 1e-5, (layout, k, dt, ang)
+            assert dt <= tol[layout] and ang <= 1e-5, (layout, k, dt, ang)
             if layout == "ndarray":
                 assert not np.isnan(da["odometry_pc"]).any()
                 assert da["odometry_pc"].shape == db["odometry_pc"].shape

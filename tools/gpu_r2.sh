@@ -77,6 +77,34 @@ ncuproj)
     ncu -i gpurun_out/${TAG}_proj.ncu-rep --page raw --csv > gpurun_out/${TAG}_proj_raw.csv 2>/dev/null
     ncu -i gpurun_out/${TAG}_proj.ncu-rep --page source --csv > gpurun_out/${TAG}_proj_source.csv 2>/dev/null
     ls -la gpurun_out/${TAG}_proj* ;;
+newtests)
+    timeout 400 python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 200 -rf -p no:cacheprovider -k "a3 or a9 or nan or projective_small or cfg5" > gpurun_out/${TAG}_pytest_new.log 2>&1
+    tail -12 gpurun_out/${TAG}_pytest_new.log ;;
+mgpu)
+    NG=$(python -c "import torch; print(torch.cuda.device_count())")
+    echo "== multi-GPU on $NG GPUs"
+    timeout 900 python -m pytest tests/test_multi_gpu.py -q -m gpu --timeout 400 -rf -s -p no:cacheprovider > gpurun_out/${TAG}_pytest_mgpu.log 2>&1
+    grep -E "mgpu_check|passed|failed|error" gpurun_out/${TAG}_pytest_mgpu.log | tail -12 ;;
+mbench)
+    NG=$(python -c "import torch; print(torch.cuda.device_count())")
+    for n in ${NS:-2}; do
+        [ "$n" -le "$NG" ] || continue
+        for comm in ${COMMS:-p2p}; do
+            timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29541 \
+                bench.py --gpus $n --steps 20 --warmup 5 --comm $comm > gpurun_out/${TAG}_bench_n${n}_${comm}.json 2> gpurun_out/${TAG}_bench_n${n}_${comm}.err
+            python - <<PY
+import json
+try:
+    d = json.loads(open("gpurun_out/${TAG}_bench_n${n}_${comm}.json").read().strip().splitlines()[-1])
+    print("N=$n $comm value", round(d["value"], 1), "e2e", round(d["e2e"]["value"], 1), "parity", d["config"].get("sharded_vs_single"))
+    for k, v in d["config"].get("extra_workloads", {}).items():
+        print("  ", k, {a: (round(b, 4) if isinstance(b, float) else b) for a, b in v.items() if a in ("ms_per_frame", "ms_per_registration", "kernel_avg_us", "frac_of_measured_hbm_peak", "tiles_sharded", "queries_sharded", "exchange")})
+except Exception as e:
+    print("bench N=$n $comm failed", e)
+PY
+            tail -3 gpurun_out/${TAG}_bench_n${n}_${comm}.err
+        done
+    done ;;
 quicktime)
     timeout 120 python tools/quick_time.py 40 tensor 2>&1 | tail -4 | tee gpurun_out/${TAG}_quicktime.log ;;
 stats)
