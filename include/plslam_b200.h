@@ -266,6 +266,22 @@ PLS_API int pls_p2plane_loss(pls_context* ctx, const float* vm_target, const flo
                      int height, int width, float up_fov_deg, float down_fov_deg, int scheme, float sigma,
                      float* out_loss, float* out_loss_per_batch, float* out_grad_mats, float* out_grad_params);
 
+/* ---- the rows either side of the path, rank 4: dataset -> vertex-map ingestion and pose chains --------------------------
+ * KITTIOdometrySequence.correct_scan (slam/dataset/kitti_dataset.py:200-231): the HDL-64 intrinsic correction, every point
+ * rotated by 0.205 degrees about normalise(p x e_z).  scan [n, stride] float32 rows (x, y, z[, reflectance]), stride 3 or 4;
+ * out_xyz [n,3] FLOAT64 (the reference's result dtype).  Points on the vertical axis come out NaN, as in the reference. */
+PLS_API int pls_kitti_correct_scan(pls_context* ctx, const float* scan, int64_t n, int stride, double* out_xyz);
+/* KITTIOdometrySequence.__getitem__ (kitti_dataset.py:233-249): optional rectification, then the spherical projection +
+ * closest-wins z-buffer in float64 (Projector.build_projection_map on the float64 cloud).  out_xyz [n,3] float64 (the
+ * `numpy_pc` entry; may be NULL), out_vertex_map [3,H,W] float64 (the `vertex_map` entry). */
+PLS_API int pls_ingest_scan(pls_context* ctx, const float* scan, int64_t n, int stride, int correct, int height, int width,
+                    float up_fov_deg, float down_fov_deg, double* out_xyz, double* out_vertex_map);
+/* compute_relative_poses (slam/eval/eval_odometry.py:80-83): out[i] = inv(poses[i-1]) @ poses[i], out[0] = poses[0];
+ * poses / out [n,4,4] float32 or float64 (is_f64), computed in that precision. */
+PLS_API int pls_relative_poses(pls_context* ctx, const void* poses, int64_t n, int is_f64, void* out);
+/* compute_absolute_poses (eval_odometry.py:86-96): out[0] = rel[0], out[i+1] = out[i] @ rel[i+1] (sequential product). */
+PLS_API int pls_absolute_poses(pls_context* ctx, const void* relative_poses, int64_t n, int is_f64, void* out);
+
 /* ---- multi-GPU: per-iteration allreduce of the normal-equation accumulators ---------
  * (no reference counterpart: SURVEY.md section 8e).  Every rank holds the whole local map
  * (kd) or its band of image rows (projective) and a shard of the queries; after

@@ -15,6 +15,10 @@ from .odometry import (LOCAL_MAP, ODOMETRY, RIGID_ALIGNMENT, GaussNewtonPointToP
 from .preprocessing import (FILTER, Distortion, DistortionConfig, GridSample, GridSampleConfig, Preprocessing,  # noqa: F401
                             PreprocessingConfig, ToTensor, ToTensorConfig, Voxelization, VoxelizationConfig)
 
+from . import dataset, integration, io  # noqa: F401
+from .dataset import correct_scan, kitti_frame, kitti_read_scan  # noqa: F401
+from .io import (compute_absolute_poses, compute_relative_poses, read_poses_from_disk,  # noqa: F401
+                 write_poses_to_disk)
 from .training import LossConfig, PointToPlaneLossConfig, _PointToPlaneLossModule  # noqa: F401
 
 __version__ = "0.1.0"

@@ -52,6 +52,10 @@ _SIGNATURES = {
     "pls_align_p2point": [_P, _P, _P, _L, _I, _I, _D, _I, _D, _P, _P, _P, _P],
     "pls_weighted_procrustes": [_P, _P, _P, _P, _L, _I, _P],
     "pls_p2plane_loss": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _F, _P, _P, _P, _P],
+    "pls_kitti_correct_scan": [_P, _P, _L, _I, _P],
+    "pls_ingest_scan": [_P, _P, _L, _I, _I, _I, _I, _F, _F, _P, _P],
+    "pls_relative_poses": [_P, _P, _L, _I, _P],
+    "pls_absolute_poses": [_P, _P, _L, _I, _P],
     "pls_map_init": [_P],
     "pls_kdmap_update_points": [_P, _P, _P, _L],
     "pls_kdmap_update_vertex_map": [_P, _P, _P, _I, _I],

@@ -320,7 +320,8 @@ void credit_icp_profile(pls_context* ctx, const FrameResult* h, int blocks) {
     if (ctx->cfg.local_map_type == PLS_MAP_KDTREE) {
         const unsigned long long* kc = reinterpret_cast<const unsigned long long*>(
             reinterpret_cast<const char*>(h) + kScalarOffset + SC_KD_COUNTERS * sizeof(uint32_t));
-        const double iters = (double)h->iters, nq = (double)h->counts[1];
+        // a rank of a sharded frame handles its share of the queries (the counters already are per rank)
+        const double iters = (double)h->iters, nq = (double)h->counts[1] / (ctx->last_sharded ? (double)comm_size(ctx) : 1.0);
         const double bytes = iters * nq * (12.0 + 27.0 * 8.0 + 4.0) + 16.0 * (double)kc[0]      // K5a
                              + 32.0 * (double)kc[2] + 16.0 * (double)kc[1]                      // K5b/c
                              + iters * (nq * 36.0 + (double)blocks * NACC * 8.0);               // K6
@@ -328,8 +329,10 @@ void credit_icp_profile(pls_context* ctx, const FrameResult* h, int blocks) {
     } else {
         // projective map: HW*12*(K+1) (target + K candidate vertex maps, each read once)
         // + N_c*12 (winner normals) + one partial row per block
-        const double hw = (double)ctx->cfg.height * ctx->cfg.width;
-        profile_credit(ctx, 1, h->iters, (double)h->iters * (hw * 12.0 * (ctx->pm.K + 1) + h->last_sums[29] * 12.0 +
+        // a rank of a sharded frame streams its share of the tiles
+        const double share = ctx->last_sharded ? 1.0 / (double)comm_size(ctx) : 1.0;
+        const double hw = (double)ctx->cfg.height * ctx->cfg.width * share;
+        profile_credit(ctx, 1, h->iters, (double)h->iters * (hw * 12.0 * (ctx->pm.K + 1) + h->last_sums[29] * share * 12.0 +
                                                               (double)blocks * NACC * 8.0));
     }
 }

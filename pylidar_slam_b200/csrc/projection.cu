@@ -118,14 +118,15 @@ __global__ void zbuf_index_f64_kernel(const double* __restrict__ xyz, int64_t n,
     }
 }
 
+template <typename TO>
 __global__ void resolve_f64_kernel(const unsigned int* __restrict__ zindex, const double* __restrict__ xyz, int64_t hw,
-                                   float* __restrict__ out) {
+                                   TO* __restrict__ out) {
     for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < hw; pix += (int64_t)gridDim.x * blockDim.x) {
         const unsigned int i = zindex[pix];
         const bool empty = (i == 0xffffffffu);
-        out[pix] = empty ? 0.f : (float)xyz[3 * (size_t)i];
-        out[hw + pix] = empty ? 0.f : (float)xyz[3 * (size_t)i + 1];
-        out[2 * hw + pix] = empty ? 0.f : (float)xyz[3 * (size_t)i + 2];
+        out[pix] = empty ? (TO)0 : (TO)xyz[3 * (size_t)i];
+        out[hw + pix] = empty ? (TO)0 : (TO)xyz[3 * (size_t)i + 1];
+        out[2 * hw + pix] = empty ? (TO)0 : (TO)xyz[3 * (size_t)i + 2];
     }
 }
 
@@ -159,8 +160,9 @@ void launch_zbuf_points(pls_context* ctx, const float* xyz, int64_t n, const uin
     PLS_CHECK_LAUNCH();
 }
 
-void launch_projection_f64(pls_context* ctx, const double* xyz, int64_t n, int H, int W, float up, float down, float* out,
-                           unsigned long long* zbuf) {
+template <typename TO>
+static void launch_projection_f64_impl(pls_context* ctx, const double* xyz, int64_t n, int H, int W, float up, float down, TO* out,
+                                       unsigned long long* zbuf) {
     cudaStream_t st = ctx->stream;
     const int64_t hw = (int64_t)H * W;
     PLS_REQUIRE(n < 0xffffffffll, "projection: at most 2^32 - 1 points per cloud");
@@ -183,8 +185,19 @@ void launch_projection_f64(pls_context* ctx, const double* xyz, int64_t n, int H
         zbuf_index_f64_kernel<<<grid_for(n), 256, 0, st>>>(xyz, n, pc, zbuf, zindex);
         PLS_CHECK_LAUNCH();
     }
-    resolve_f64_kernel<<<grid_for(hw), 256, 0, st>>>(zindex, xyz, hw, out);
+    resolve_f64_kernel<TO><<<grid_for(hw), 256, 0, st>>>(zindex, xyz, hw, out);
     PLS_CHECK_LAUNCH();
+}
+
+void launch_projection_f64(pls_context* ctx, const double* xyz, int64_t n, int H, int W, float up, float down, float* out,
+                           unsigned long long* zbuf) {
+    launch_projection_f64_impl<float>(ctx, xyz, n, H, W, up, down, out, zbuf);
+}
+
+// the float64 vertex map itself (what a float64 cloud gives build_projection_map: the dataset loaders' case)
+void launch_projection_f64_out64(pls_context* ctx, const double* xyz, int64_t n, int H, int W, float up, float down, double* out,
+                                 unsigned long long* zbuf) {
+    launch_projection_f64_impl<double>(ctx, xyz, n, H, W, up, down, out, zbuf);
 }
 
 }  // namespace pls

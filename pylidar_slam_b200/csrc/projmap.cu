@@ -237,16 +237,11 @@ __global__ void query_resolve_kernel(unsigned long long* __restrict__ zbuf, cons
     }
 }
 
-// sqrtf(a) < sqrtf(b) for a, b >= 0 (b may be +inf), WITHOUT the square roots in the common case.  The reference takes the
-// arg-min over distances (torch.norm, then torch.min keeps the first minimum: geometry.py:424-428), and two different
-// squared distances can share one correctly rounded root -- but only if they lie within 2^-22 of each other (the
-// pre-image of a float under sqrt is at most that wide, relatively).  Outside that band the squares decide; inside it
-// (about one comparison in a million) both roots are taken.
-__device__ __forceinline__ bool dist_less(float a2, float b2) {
-    if (!(a2 < b2)) return false;
-    if (a2 < b2 * 0.99999952f) return true;  // 1 - 2^-21
-    return sqrtf(a2) < sqrtf(b2);
-}
+// Arg-min over distances WITHOUT the square roots in the common case.  The reference takes the arg-min over
+// torch.norm (then torch.min keeps the first minimum: geometry.py:424-428), and two different squared distances can share
+// one correctly rounded root -- but only if they lie within 2^-22 of each other (the pre-image of a float under sqrt is at
+// most that wide, relatively).  The tile loop therefore compares squares against best2 * (1 - 2^-21), records whether any
+// comparison fell inside that band, and redoes such a pixel (about one in 50 000) with the roots.
 
 // acc += [ (wJ)(wJ)^T upper, (wJ)(wr), (wr)^2, r^2, 1 ] in float32: a thread of the tile-streaming kernel meets a
 // handful of pixels only (tiles / CTAs), their sum goes to float64 before the block reduction -- each partial sum
@@ -425,7 +420,7 @@ proj_icp_tma_kernel(const float* __restrict__ model_v, const float4* __restrict_
         if (has) {
             const float* st = stage_base + (size_t)s * stage_floats + threadIdx.x;
             // Branch-free arg-min on squared distances.  `band` records whether any comparison fell inside the
-            // 2^-22 band where the squares cannot decide (dist_less): the pixel is then redone with the roots.
+            // 2^-22 band where the squares cannot decide (see above): the pixel is then redone with the roots.
             float best2 = __int_as_float(0x7f800000);  // squared distance of the best candidate so far
             bool band = false;
 #pragma unroll 4

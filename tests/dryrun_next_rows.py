@@ -98,6 +98,29 @@ class FakeContext:
     def pls_wait_stream(self, stream):
         pass
 
+    # ---- rank 4: ingestion and pose chains
+    def pls_kitti_correct_scan(self, scan, n, stride, out):
+        from oracle import io_oracle as ioo
+        arr(out, (n, 3), np.float64)[:] = ioo.kitti_correct_scan(arr(scan, (n, stride), np.float32))
+
+    def pls_ingest_scan(self, scan, n, stride, correct, H, W, up, down, out_xyz, out_vmap):
+        from oracle import io_oracle as ioo
+        s = arr(scan, (n, stride), np.float32)
+        xyz = ioo.kitti_correct_scan(s) if correct else s[:, :3].astype(np.float64)
+        if out_xyz:
+            arr(out_xyz, (n, 3), np.float64)[:] = xyz
+        arr(out_vmap, (3, H, W), np.float64)[:] = ioo.project_f64(xyz, H, W, up, down)
+
+    def pls_relative_poses(self, poses, n, is64, out):
+        from oracle import io_oracle as ioo
+        dt = np.float64 if is64 else np.float32
+        arr(out, (n, 4, 4), dt)[:] = ioo.relative_poses(arr(poses, (n, 4, 4), dt))
+
+    def pls_absolute_poses(self, rel, n, is64, out):
+        from oracle import io_oracle as ioo
+        dt = np.float64 if is64 else np.float32
+        arr(out, (n, 4, 4), dt)[:] = ioo.absolute_poses(arr(rel, (n, 4, 4), dt))
+
     def pls_align_p2point(self, ref, tgt, n, is64, scheme, sigma, max_iters, norm_stop, x0, dT, x, loss):
         dt = np.float64 if is64 else np.float32
         r, t = (torch.from_numpy(arr(p, (1, n, 3), dt).copy()) for p in (ref, tgt))

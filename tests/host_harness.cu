@@ -13,6 +13,7 @@
 #include "../pylidar_slam_b200/csrc/eigen_device.cuh"
 #include "../pylidar_slam_b200/csrc/filters_device.cuh"
 #include "../pylidar_slam_b200/csrc/gn_device.cuh"
+#include "../pylidar_slam_b200/csrc/ingest_device.cuh"
 #include "../pylidar_slam_b200/csrc/pose_device.cuh"
 #include "../pylidar_slam_b200/csrc/projection_device.cuh"
 #include "../pylidar_slam_b200/csrc/registration_device.cuh"
@@ -221,6 +222,24 @@ void hh_p2plane_loss(const float* vt, const float* vr, const float* nr, const fl
     }
     *out_loss = (float)(total / (double)B);
     delete[] zbuf;
+}
+
+// rank 4: kitti_correct_kernel's per-point math and the pose chains (relative_poses_kernel / absolute_poses_kernel)
+void hh_kitti_correct(const float* scan, int64_t n, int stride, double* out) {
+    const double theta = 0.205 * 3.141592653589793 / 180.0;
+    for (int64_t i = 0; i < n; ++i)
+        kitti_correct_point(scan[stride * i], scan[stride * i + 1], scan[stride * i + 2], cos(theta), sin(theta), out + 3 * i);
+}
+
+void hh_pose_chains(const double* poses, int64_t n, double* rel, double* absolute) {
+    for (int64_t i = 0; i < n; ++i) {
+        double prev[16], inv[16];
+        for (int k = 0; k < 16; ++k) prev[k] = i > 0 ? poses[16 * (i - 1) + k] : ((k % 5 == 0) ? 1.0 : 0.0);
+        inverse4<double>(prev, inv);
+        matmul4<double>(inv, poses + 16 * i, rel + 16 * i);
+    }
+    for (int k = 0; k < 16; ++k) absolute[k] = rel[k];
+    for (int64_t i = 1; i < n; ++i) matmul4<double>(absolute + 16 * (i - 1), rel + 16 * i, absolute + 16 * i);
 }
 
 // smallest-eigenvalue directions of n symmetric 3x3 matrices (xx,xy,xz,yy,yz,zz): which = 0 the product's solver

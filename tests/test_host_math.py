@@ -29,7 +29,7 @@ def hh():
     src = os.path.join(ROOT, "tests", "host_harness.cu")
     deps = [src] + [os.path.join(ROOT, "pylidar_slam_b200", "csrc", f) for f in
                     ("filters_device.cuh", "registration_device.cuh", "gn_device.cuh", "pose_device.cuh",
-                     "projection_device.cuh", "training_device.cuh", "eigen_device.cuh")]
+                     "projection_device.cuh", "training_device.cuh", "eigen_device.cuh", "ingest_device.cuh")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call([NVCC, "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
                                "-o", so, src])
@@ -282,3 +282,20 @@ def test_normal_eigen_solvers_agree_with_lapack(hh):
                 assert declined.size == 0 or declined.max() <= 2e-3, (kind, declined.max())
                 if must_use_closed_form:
                     assert used.mean() >= 0.99, (kind, used.mean())
+
+
+def test_ingestion_and_pose_chain_device_math_matches_reference(hh):
+    """kitti_correct_point / inverse4 / matmul4 (ingest_device.cuh) against the goldens of the unmodified reference."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "io_rows.npz"))
+    scan = np.ascontiguousarray(g["kitti_scan"])
+    out = np.empty((scan.shape[0], 3), np.float64)
+    hh.hh_kitti_correct(_p(scan), C.c_int64(scan.shape[0]), 4, _p(out))
+    ref = g["kitti_corrected"]
+    assert np.array_equal(np.isnan(out), np.isnan(ref))
+    ok = ~np.isnan(ref).any(axis=1)
+    assert np.abs(out[ok] - ref[ok]).max() <= 1e-12 * np.abs(ref[ok]).max()
+    P = np.ascontiguousarray(g["rel_f64_in"])
+    rel, absolute = np.empty_like(P), np.empty_like(P)
+    hh.hh_pose_chains(_p(P), C.c_int64(P.shape[0]), _p(rel), _p(absolute))
+    np.testing.assert_allclose(rel, g["rel_f64_out"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(absolute, g["abs_f64_out"], rtol=0, atol=1e-9)
