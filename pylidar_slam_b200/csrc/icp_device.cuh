@@ -31,11 +31,20 @@ __device__ __forceinline__ void sum_partials_256(const double* __restrict__ part
 __device__ __forceinline__ void icp_solve_and_update(FrameResult* fr, const double* sums, float threshold_delta) {
     const int it = fr->iters;
     fr->iters = it + 1;
-    // optimization.py:323-327: |r| < 1e-7 -> warning, x stays 0, residuals r^2; then delta = 0 breaks the loop
+    // optimization.py:323-327: |r| < 1e-7 -> warning, x stays 0, the residuals are r^2.  The ICP loop then sees delta = 0:
+    // it breaks if 0 < threshold_delta_pose (icp_odometry.py:292) and otherwise goes on, the pose unchanged
+    // (delta_pose_matrix = I, so `new_pose_matrix` only passes through the Euler round trip again)
     if (sqrt(sums[28]) < 1e-7) {
         fr->losses[it] = (float)sums[28];
         fr->status = PLS_W_TINY_RESIDUAL;
-        fr->done = 1;
+        if (0.f < threshold_delta) {
+            fr->done = 1;
+        } else {
+            float prm[6];
+            from_pose(fr->T, prm);
+            build_pose(prm, fr->T);
+            for (int i = 0; i < 6; ++i) fr->params[i] = prm[i];
+        }
         return;
     }
     double dx[6];

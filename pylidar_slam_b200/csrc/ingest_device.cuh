@@ -14,7 +14,14 @@ namespace pls {
 __host__ __device__ inline void kitti_correct_point(float x, float y, float z, double c, double s, double* out) {
     // p x (0, 0, 1) = (y, -x, 0), exact in float32
     const float a0 = y, a1 = -x;
-    const float nrm = sqrtf(a0 * a0 + a1 * a1);   // np.linalg.norm over (a0, a1, 0), float32
+    // np.linalg.norm over (a0, a1, 0) in float32: two rounded products, one rounded sum (no fused multiply-add: the
+    // device compiler would contract a0 * a0 + a1 * a1 and move the axis by an ulp)
+#ifdef __CUDA_ARCH__
+    const float nrm = sqrtf(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1)));
+#else
+    const float s0 = a0 * a0, s1 = a1 * a1;
+    const float nrm = sqrtf(s0 + s1);
+#endif
     const float u0 = a0 / nrm, u1 = a1 / nrm;
     const double o00 = (double)(u0 * u0), o01 = (double)(u0 * u1), o11 = (double)(u1 * u1);  // float32 outer product
     const double k = 1.0 - c;

@@ -537,7 +537,8 @@ void odometry_reset(pls_context* ctx) {
     projmap_reset(ctx);
     ctx->frame_index = 0;
     ctx->last_icp_iters = 0;
-    ctx->sample_pointcloud = 0;
+    // _sample_pointcloud is set in the reference's constructor only: ICPFrameToModel.init() keeps it
+    // (icp_odometry.py:105,128-137), so a re-initialised sequence samples like the last frame of the previous one
     for (int i = 0; i < 16; ++i) ctx->delta_since_update[i] = (i % 5 == 0) ? 1.f : 0.f;
 }
 

@@ -491,12 +491,22 @@ class ICPFrameToModel(OdometryAlgorithm):
             local_map_size=int(lm.get("local_map_size", 20)),
             num_neighbors_normals=int(lm.get("num_neighbors_normals", 10)),
             normals_kernel_size=int(lm.get("normals_kernel_size", 5)),
-            scheme=_lib.SCHEMES[gn["scheme"]], sigma=gn["sigma"], gn_max_iters=gn["max_iters"],
+            scheme=_lib.SCHEMES[gn["scheme"]], sigma=gn["sigma"], gn_max_iters=1,
             gn_norm_stop=gn["norm_stop"], max_num_alignments=int(self.config.max_num_alignments),
             threshold_delta_pose=float(self.config.threshold_delta_pose),
             threshold_trans=float(self.config.threshold_trans), threshold_rot=float(self.config.threshold_rot),
             device=dev.index or 0, stream=stream)
         self.gn_max_iters = self.config.max_num_alignments
+        # The fused C-ABI path runs ONE Gauss-Newton step per ICP iteration (the shipped configuration,
+        # alignment.py:77).  gauss_newton_config.max_iters > 1 (alignment.py:69-77,110-127: several re-linearised steps on
+        # the same correspondences) takes the reference-shaped loop below, built from the fine-grained GPU plug-ins.
+        self._fine_grained = gn["max_iters"] > 1
+        if self._fine_grained:
+            self.ctx.cfg.gn_max_iters = 1  # the context's own fused entry points stay usable (register_new_frame)
+            self.local_map = LOCAL_MAP.load(self.config.local_map, projector=projector, ctx=self.ctx)
+            self.rigid_alignment = RIGID_ALIGNMENT.load(self.config.alignment, ctx=self.ctx)
+            self._pose_ops = Pose("euler", ctx=self.ctx)
+            self._delta_since_map_update = torch.eye(4, dtype=torch.float32)
         self.relative_poses: list = []
         self.absolute_poses: list = []
         self._iter = 0
@@ -510,6 +520,10 @@ class ICPFrameToModel(OdometryAlgorithm):
         self.absolute_poses = []
         self._iter = 0
         self.ctx.call("pls_odometry_init")
+        if self._fine_grained:
+            self.local_map.init()
+            self._delta_since_map_update = torch.eye(4, dtype=torch.float32)
+            self._sample_pointcloud = False
 
     def _interpret(self, data):
         """_read_input's three layouts (icp_odometry.py:319-358)."""
@@ -534,10 +548,88 @@ class ICPFrameToModel(OdometryAlgorithm):
             return _lib.INPUT_TENSOR | hint, data.to(torch.float32).contiguous(), data.shape[0]
         raise RuntimeError(f"Could not interpret the data: {data} as a pointcloud tensor")
 
+    # -- the reference-shaped loop over the fine-grained plug-ins (icp_odometry.py:157-380), for configurations the fused
+    #    path does not cover: the NN search, the normals, every Gauss-Newton step and the map update are the same CUDA
+    #    kernels, the loop itself runs here (one host round trip per ICP iteration, like the reference)
+    def _process_fine_grained(self, data_dict: dict):
+        dev = self.device
+        data = data_dict[self.config.data_key]
+        if isinstance(data, np.ndarray):                                   # _read_input, icp_odometry.py:319-358
+            check_tensor(data, [-1, 3])
+            self._sample_pointcloud = True
+            pc = torch.from_numpy(data).to(dev).unsqueeze(0)
+            vmap = self.projector.build_projection_map(pc.to(torch.float32))
+        elif isinstance(data, torch.Tensor):
+            if data.dim() in (3, 4):
+                vmap = data.to(dev) if data.dim() == 4 else data.to(dev).unsqueeze(0)
+                assert_debug(vmap.shape[0] == 1, "Unexpected batched data format.")
+                check_tensor(vmap, [1, 3, -1, -1])
+                pc = vmap.permute(0, 2, 3, 1).reshape(1, -1, 3)
+                pc = pc[:, (pc[0] != 0).any(dim=-1)][:, :1]   # the reference keeps the first non-null pixel only (:342-358)
+            else:
+                assert_debug(data.dim() == 2)
+                pc = data.to(dev).unsqueeze(0)
+                vmap = self.projector.build_projection_map(pc.to(torch.float32))
+        else:
+            raise RuntimeError(f"Could not interpret the data: {data} as a pointcloud tensor")
+        vmap = vmap.to(torch.float32)
+        vmap = torch.where(torch.isnan(vmap).any(dim=1, keepdim=True), torch.zeros_like(vmap), vmap)   # modify_nan_pmap
+        pc = pc.to(torch.float32)
+        pc = pc[:, ~torch.isnan(pc[0]).any(dim=-1)]                                                    # remove_nan
+        if self._iter == 0:
+            eye = torch.eye(4, dtype=torch.float32).unsqueeze(0)
+            self.local_map.update(eye, new_vertex_map=vmap)
+            self.relative_poses.append(eye.numpy())
+            self.absolute_poses.append(np.eye(4, dtype=np.float64))
+            self._iter += 1
+            return
+        init = data_dict.get("init_rpose", None)
+        T = torch.eye(4, dtype=torch.float32, device=dev).unsqueeze(0) if init is None else \
+            torch.from_numpy(np.asarray(init, dtype=np.float32).reshape(1, 4, 4)).to(dev)
+        if self._sample_pointcloud:                                       # sample_points, icp_odometry.py:301-308
+            points = pc[0]
+        else:
+            flat = vmap[0].permute(1, 2, 0).reshape(-1, 3)
+            points = flat[flat.norm(dim=-1) > 0.0]
+        params = torch.zeros(1, 6, dtype=torch.float32, device=dev)
+        self.last_losses = []
+        for _ in range(self.config.max_num_alignments):                   # register_new_frame, icp_odometry.py:274-297
+            moved = points @ T[0, :3, :3].T + T[0, :3, 3]
+            res = self.local_map.nearest_neighbor_search(moved)
+            dT, delta, residuals = self.rigid_alignment.align(res.neighbor_points, res.new_target_points, res.neighbor_normals)
+            self.last_losses.append(float(residuals.sum()))
+            if float(torch.as_tensor(delta).norm()) < self.config.threshold_delta_pose:
+                break
+            params = self._pose_ops.from_pose_matrix(torch.as_tensor(dT).to(dev) @ T)
+            T = self._pose_ops.build_pose_matrix(params)
+        self.last_info[0] = len(self.last_losses)
+        T_host = T.detach().cpu()
+        new_delta = self._delta_since_map_update @ T_host[0]              # __update_map, icp_odometry.py:360-380
+        dp = self._pose_ops.from_pose_matrix(new_delta.unsqueeze(0))
+        dp = torch.as_tensor(dp).cpu()
+        if float(dp[0, :3].norm()) > self.config.threshold_trans or float(dp[0, 3:].norm()) * 180 / np.pi > self.config.threshold_rot:
+            self.local_map.update(T_host, new_vertex_map=vmap, new_pc_data=pc[0])
+            self._delta_since_map_update = torch.eye(4, dtype=torch.float32)
+        else:
+            self.local_map.update(T_host)
+            self._delta_since_map_update = new_delta
+        T_np = T_host.numpy().reshape(4, 4).astype(np.float32)
+        self.relative_poses.append(T_np.reshape(1, 4, 4))
+        self.absolute_poses.append(self.absolute_poses[-1].dot(euler_pose_matrix_f64(torch.as_tensor(params).cpu().numpy().reshape(6))))
+        if "distorted" in data_dict:
+            tgt_np_pc = data_dict["distorted"]
+        else:
+            tgt_np_pc = pc[0].detach().cpu().numpy()
+        data_dict[self.pointcloud_key()] = tgt_np_pc
+        data_dict[self.relative_pose_key()] = T_np
+        self._iter += 1
+
     def do_process_next_frame(self, data_dict: dict):
         assert_debug(self.config.data_key in data_dict,
                      f"Could not find the key `{self.config.data_key}` in the input dictionary.\n"
                      f"With keys : {data_dict.keys()}). Set the parameter `slam.odometry.data_key` to the desired key")
+        if self._fine_grained:
+            return self._process_fine_grained(data_dict)
         layout, data, n = self._interpret(data_dict[self.config.data_key])
         init = data_dict.get("init_rpose", None)
         init = None if init is None else np.ascontiguousarray(np.asarray(init, dtype=np.float32).reshape(4, 4))
@@ -552,6 +644,10 @@ class ICPFrameToModel(OdometryAlgorithm):
         self.ctx.call("pls_process_frame", address, layout, n, _lib.ptr(init), _lib.ptr(self._pose_out),
                       _lib.ptr(self._params_out), C.byref(has_pose), _lib.ptr(self.last_info))
         layout &= 0xff
+        if int(self.last_info[6]) == _lib.PLS_W_TINY_RESIDUAL:   # GaussNewton.compute's warning (optimization.py:323-327)
+            import logging
+            logging.warning("The residual norm is lower than threshold 1e-7. "
+                            "This would lead to invalid jacobian. We prefer Stopping ICP")
         if not has_pose.value:
             eye = np.eye(4, dtype=np.float32).reshape(1, 4, 4)
             self.relative_poses.append(eye)

@@ -573,6 +573,31 @@ def test_icp_projective_small_vs_reference_golden(b200, syn, golden_icp_small, n
     print(name, "flips", flips, "worst", worst)
 
 
+@pytest.mark.parametrize("name,lm,key", [("kd_gn3", "kdtree", "numpy_pc"), ("proj_gn2", "projective", "vertex_map")])
+def test_icp_with_several_gauss_newton_steps_vs_reference_golden(b200, syn, name, lm, key):
+    """gauss_newton_config.max_iters > 1 (alignment.py:69-77,110-127: several re-linearised Gauss-Newton steps on the same
+    correspondences per ICP iteration) takes the reference-shaped loop over the fine-grained GPU plug-ins; poses against the
+    unmodified reference (tests/golden/make_golden_gn.py), 5 alignments per frame, no stop rule."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "icp_gn.npz"))
+    H, W = 32, 512
+    lmc = b200.KdTreeLocalMapConfig(local_map_size=4) if lm == "kdtree" else b200.ProjectiveLocalMapConfig(local_map_size=4)
+    cfg = b200.ICPFrameToModelConfig(
+        local_map=lmc, alignment=b200.GaussNewtonPointToPlaneConfig(gauss_newton_config=dict(
+            scheme="geman_mcclure", sigma=0.3, max_iters=int(g[f"{name}_gn_iters"]), norm_stop_criterion=1e-9)),
+        max_num_alignments=5, data_key=key, threshold_delta_pose=0.0)
+    algo = b200.ICPFrameToModel(cfg, projector=b200.SphericalProjector(height=H, width=W, up_fov=3.0, down_fov=-24.0),
+                                pose=b200.Pose("euler"), device="cuda:0")
+    algo.init()
+    layout = "ndarray" if key == "numpy_pc" else "vertex_map"
+    poses = _drive(algo, _frames(syn, b200.grid_sample, layout, H, W, 0.4 if layout == "ndarray" else None), 6)
+    ref = g[f"{name}_poses"]
+    assert len(poses) == len(ref)
+    tol_t = 1e-4 if lm == "kdtree" else relaxed_tolerance("proj_vmap_32x512", 6e-4)
+    for k, (T, Tr) in enumerate(zip(poses, ref)):
+        dt, ang = pose_errors(T, Tr)
+        assert dt <= tol_t and ang <= 1e-5, (name, k, dt, ang)
+
+
 def test_icp_cfg3_projective_full_size_vs_reference_golden(b200, syn, golden_icp_full):
     """BASELINE config 3 (128x2048 vertex-map input, projective map K<=20, normals kernel 5)."""
     ref = golden_icp_full["cfg3_proj_poses"]

@@ -27,7 +27,7 @@ except Exception as e:
 PY
     tail -3 gpurun_out/${TAG}_bench.err ;;
 benchlong)
-    timeout 300 python bench.py --no-cpu > gpurun_out/${TAG}_bench_default.json 2> gpurun_out/${TAG}_bench_default.err
+    timeout 400 python bench.py > gpurun_out/${TAG}_bench_default.json 2> gpurun_out/${TAG}_bench_default.err
     tail -c 1500 gpurun_out/${TAG}_bench_default.json; tail -3 gpurun_out/${TAG}_bench_default.err ;;
 launches)
     timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches_cfg2.csv \
@@ -105,6 +105,8 @@ PY
             tail -3 gpurun_out/${TAG}_bench_n${n}_${comm}.err
         done
     done ;;
+e2ebreak)
+    timeout 120 python tools/e2e_breakdown.py 2>&1 | tail -8 | tee gpurun_out/${TAG}_e2e_breakdown.log ;;
 quicktime)
     timeout 120 python tools/quick_time.py 40 tensor 2>&1 | tail -4 | tee gpurun_out/${TAG}_quicktime.log ;;
 stats)
