@@ -129,10 +129,16 @@ PLS_API int pls_grid_sample(pls_context* ctx, const void* xyz, int is_f64, int64
  * filter): the gather kernel writes samples and indices straight into the context's pinned, device-mapped staging and
  * keeps a device-resident copy.  *out_xyz_host / *out_idx_host point into the staging (S rows, valid until the next
  * grid-sample call on this context); *out_xyz_dev (optional) is the device copy, which pls_process_frame accepts with
- * PLS_PTR_DEVICE -- the samples then never travel host -> device again.  One stream synchronisation per call. */
+ * PLS_PTR_DEVICE -- the samples then never travel host -> device again.  One stream synchronisation per call.
+ * Caller-owned staging: when *out_xyz_host and *out_idx_host are non-NULL ON ENTRY they name pinned, device-mapped
+ * buffers from pls_pinned_alloc with room for n rows each, and the kernel writes there instead -- the caller (the
+ * GridSample filter) then hands those very buffers on as arrays, no host-side copy at all. */
 PLS_API int pls_grid_sample_staged(pls_context* ctx, const void* xyz, int is_f64, int64_t n, double voxel,
                            const void** out_xyz_host, const int64_t** out_idx_host, const void** out_xyz_dev,
                            int64_t* out_count);
+/* Page-locked, device-mapped host memory for results a kernel writes straight into (see pls_grid_sample_staged). */
+PLS_API int pls_pinned_alloc(int64_t num_bytes, void** out_ptr);
+PLS_API int pls_pinned_free(void* ptr);
 /* 64-bit fingerprint of a host buffer (256 evenly spread 8-byte words + its length): lets a caller check cheaply that
  * an array it handed out earlier still holds what the device-resident copy holds. */
 PLS_API int pls_host_fingerprint(const void* host_ptr, int64_t num_bytes, uint64_t* out);

@@ -40,6 +40,8 @@ _SIGNATURES = {
     "pls_grid_sample": [_P, _P, _I, _L, _D, _P, _P, C.POINTER(_L)],
     "pls_grid_sample_staged": [_P, _P, _I, _L, _D, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_L)],
     "pls_host_fingerprint": [_P, _L, C.POINTER(C.c_uint64)],
+    "pls_pinned_alloc": [_L, C.POINTER(_P)],
+    "pls_pinned_free": [_P],
     "pls_project_pixels": [_P, _P, _L, _I, _I, _F, _F, _P],
     "pls_build_projection_map": [_P, _P, _P, _I, _L, _I, _I, _I, _F, _F, _P],
     "pls_normal_map": [_P, _P, _I, _I, _I, _I, _P],
@@ -124,7 +126,7 @@ def ptr(x):
     """Raw address of a numpy array / torch tensor (host or CUDA) / None."""
     if x is None:
         return None
-    if isinstance(x, np.ndarray):
+    if type(x) is np.ndarray or isinstance(x, np.ndarray):
         assert x.flags.c_contiguous, "arrays passed to the C ABI must be C-contiguous"
         return x.__array_interface__["data"][0]  # same address as x.ctypes.data without building a ctypes object
     if hasattr(x, "data_ptr"):
@@ -137,9 +139,43 @@ def ptr(x):
 
 def host_view(address: int, shape, dtype) -> np.ndarray:
     """A numpy view (no copy) of library-owned host memory, e.g. the pinned staging of pls_grid_sample_staged."""
-    count = int(np.prod(shape))
+    count = 1
+    for extent in shape:
+        count *= int(extent)
     buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(address)
     return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+
+class PinnedPool:
+    """Page-locked, device-mapped byte buffers that become the arrays a filter hands out: the kernel writes the result
+    over PCIe straight into the memory the caller receives (no staging copy, no page faults on fresh pages).  Every
+    array handed out is a view of its buffer, so the buffer's reference count says when nothing refers to it any more
+    (pool entry + getrefcount's own argument = 2) and it can take the next frame.  A caller that keeps every frame's
+    arrays simply exhausts the pool (`limit` buffers) and gets ordinary pageable copies from then on."""
+    limit = 12
+    buffers: list = []
+
+    @classmethod
+    def take(cls, num_bytes: int):
+        """A free buffer of at least num_bytes (uint8 array over pinned memory), or None when the pool is exhausted."""
+        import sys
+        pool = cls.buffers
+        for i in range(len(pool)):          # by index: a loop variable would itself hold a reference
+            if sys.getrefcount(pool[i]) == 2 and pool[i].nbytes >= num_bytes:
+                return pool[i]
+        if len(pool) >= cls.limit:
+            small = [i for i in range(len(pool)) if sys.getrefcount(pool[i]) == 2 and pool[i].nbytes < num_bytes]
+            if not small:
+                return None
+            del pool[small[0]]              # its finalizer returns the pinned memory
+        lib, p = load(), _P()
+        if lib.pls_pinned_alloc(num_bytes, C.byref(p)) != PLS_OK:
+            return None
+        buf = np.frombuffer((C.c_char * num_bytes).from_address(p.value), dtype=np.uint8)
+        import weakref
+        weakref.finalize(buf, lib.pls_pinned_free, p.value)
+        cls.buffers.append(buf)
+        return buf
 
 
 def host_fingerprint(address: int, num_bytes: int) -> int:

@@ -32,9 +32,15 @@ def assert_debug(condition: bool, message: str = ""):
 
 def check_tensor(tensor, sizes: list):
     """slam/common/utils.py:54-74 (shape check; -1 matches any size)."""
-    shape = list(tensor.shape)
-    ok = len(shape) == len(sizes) and all(s == -1 or s == t for s, t in zip(sizes, shape))
-    assert_debug(ok, f"[BAD TENSOR SHAPE] Wrong tensor shape got {tuple(tensor.shape)} expected {sizes}")
+    shape = tensor.shape
+    ok = len(shape) == len(sizes)
+    if ok:
+        for s, t in zip(sizes, shape):   # a plain loop: this runs several times per frame
+            if s != -1 and s != t:
+                ok = False
+                break
+    if not ok:
+        raise AssertionError(f"[BAD TENSOR SHAPE] Wrong tensor shape got {tuple(tensor.shape)} expected {sizes}")
 
 
 def _as_f32(x):
@@ -93,16 +99,29 @@ def grid_sample(pointcloud, voxel_size: float, ctx=None):
     n = pc.shape[0]
     count = C.c_int64(0)
     if isinstance(pc, np.ndarray):
-        # host caller (GridSample.filter): the library leaves the result in its pinned staging -- one synchronisation,
-        # no pageable device->host copy -- and keeps a device-resident twin; the arrays handed out are exact-size
-        # copies (the staging is reused by the next call), and the twin is published so that ICPFrameToModel can
-        # consume it without sending the samples back to the device
-        hx, hi, dx = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        ctx.call("pls_grid_sample_staged", _lib.ptr(pc), int(is64), n, float(voxel_size), C.byref(hx), C.byref(hi),
-                 C.byref(dx), C.byref(count))
-        S = count.value
-        out = _lib.host_view(hx.value, (S, 3), np.float64 if is64 else np.float32).copy()
-        idx = _lib.host_view(hi.value, (S,), np.int64).copy()
+        # host caller (GridSample.filter): the gather kernel writes the result into pinned host memory -- one
+        # synchronisation, no pageable device->host copy -- and the library keeps a device-resident twin, which is
+        # published so that ICPFrameToModel can consume it without sending the samples back to the device
+        fdt = np.dtype(np.float64 if is64 else np.float32)
+        xyz_buf, idx_buf = _lib.PinnedPool.take(n * 3 * fdt.itemsize), _lib.PinnedPool.take(n * 8)
+        dx = C.c_void_p()
+        if xyz_buf is not None and idx_buf is not None:
+            # the kernel writes into pinned buffers of the pool; the arrays handed out are views of them (zero copies)
+            hx, hi = C.c_void_p(_lib.ptr(xyz_buf)), C.c_void_p(_lib.ptr(idx_buf))
+            ctx.call("pls_grid_sample_staged", _lib.ptr(pc), int(is64), n, float(voxel_size), C.byref(hx), C.byref(hi),
+                     C.byref(dx), C.byref(count))
+            S = count.value
+            out = xyz_buf[:S * 3 * fdt.itemsize].view(fdt).reshape(S, 3)
+            idx = idx_buf[:S * 8].view(np.int64)
+        else:
+            # pool exhausted (the caller keeps many frames alive): the library's own staging, copied out
+            del xyz_buf, idx_buf
+            hx, hi = C.c_void_p(), C.c_void_p()
+            ctx.call("pls_grid_sample_staged", _lib.ptr(pc), int(is64), n, float(voxel_size), C.byref(hx), C.byref(hi),
+                     C.byref(dx), C.byref(count))
+            S = count.value
+            out = _lib.host_view(hx.value, (S, 3), fdt).copy()
+            idx = _lib.host_view(hi.value, (S,), np.int64).copy()
         _lib.Handoff.publish(out, dx.value or 0, int(ctx.cfg.device), is64)
         return out, idx
     out = _empty_like_kind(pc, (n, 3), np.float64 if is64 else np.float32)

@@ -326,26 +326,59 @@ int pls_grid_sample_staged(pls_context* ctx, const void* xyz, int is_f64, int64_
     // written by the gather kernel itself; a single stream synchronisation ends the call
     DBuf& dev_xyz = is_f64 ? ctx->stage_out[0] : ctx->gs_out_xyz;
     dev_xyz.reserve((size_t)n * 3 * esz, ctx->stream);
-    ctx->gs_host_xyz.reserve((size_t)n * 3 * esz);
-    ctx->gs_host_idx.reserve((size_t)n * sizeof(int64_t));
+    void* host_xyz = const_cast<void*>(*out_xyz_host);
+    int64_t* host_idx = const_cast<int64_t*>(*out_idx_host);
+    void *map_xyz = nullptr, *map_idx = nullptr;  // the device-side aliases the gather kernel writes through
+    if (host_xyz && host_idx) {
+        PLS_REQUIRE(cudaHostGetDevicePointer(&map_xyz, host_xyz, 0) == cudaSuccess &&
+                        cudaHostGetDevicePointer(&map_idx, host_idx, 0) == cudaSuccess,
+                    "pls_grid_sample_staged: caller-owned staging must come from pls_pinned_alloc");
+    } else {
+        ctx->gs_host_xyz.reserve((size_t)n * 3 * esz);
+        ctx->gs_host_idx.reserve((size_t)n * sizeof(int64_t));
+        host_xyz = ctx->gs_host_xyz.p;
+        host_idx = ctx->gs_host_idx.as<int64_t>();
+        map_xyz = ctx->gs_host_xyz.device_ptr();
+        map_idx = ctx->gs_host_idx.device_ptr();
+    }
     uint32_t count = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
         const bool compact = attempt == 0;
         if (is_f64)
             grid_sample_device<double>(ctx, (const double*)d_xyz, n, voxel, dev_xyz.as<double>(), nullptr, compact,
-                                       (double*)ctx->gs_host_xyz.device_ptr(), (long long*)ctx->gs_host_idx.device_ptr());
+                                       (double*)map_xyz, (long long*)map_idx);
         else
             grid_sample_device<float>(ctx, (const float*)d_xyz, n, voxel, dev_xyz.as<float>(), nullptr, compact,
-                                      (float*)ctx->gs_host_xyz.device_ptr(), (long long*)ctx->gs_host_idx.device_ptr());
+                                      (float*)map_xyz, (long long*)map_idx);
         bool overflowed = false;
         count = grid_sample_read_count(ctx, &overflowed);
         if (!(compact && overflowed)) break;  // hashes beyond 40 bits: once more on the raw 64-bit keys
     }
     *out_count = count;
-    *out_xyz_host = ctx->gs_host_xyz.p;
-    *out_idx_host = ctx->gs_host_idx.as<int64_t>();
+    *out_xyz_host = host_xyz;
+    *out_idx_host = host_idx;
     if (out_xyz_dev) *out_xyz_dev = dev_xyz.p;
     PLS_API_END(ctx)
+}
+
+int pls_pinned_alloc(int64_t num_bytes, void** out_ptr) {
+    if (!out_ptr || num_bytes <= 0) return PLS_E_INVALID;
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, (size_t)num_bytes, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return PLS_E_CUDA;
+    }
+    *out_ptr = p;
+    return PLS_OK;
+}
+
+int pls_pinned_free(void* ptr) {
+    if (!ptr) return PLS_OK;
+    if (cudaFreeHost(ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return PLS_E_CUDA;
+    }
+    return PLS_OK;
 }
 
 int pls_voxel_statistics(pls_context* ctx, const void* xyz, int is_f64, int64_t n, double voxel, int64_t* coords_out,

@@ -342,6 +342,24 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// L2 eviction-priority policies (the fixed encodings of createpolicy.fractional.L2::evict_last / evict_first, fraction 1)
+constexpr unsigned long long L2_EVICT_LAST = 0x14F0000000000000ull, L2_EVICT_FIRST = 0x12F0000000000000ull;
+__device__ __forceinline__ void bulk_copy_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, unsigned long long policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ float ldg_f32_hint(const float* p, unsigned long long policy) {
+    float v;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ float4 ldg_f4_hint(const float4* p, unsigned long long policy) {
+    float4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(policy));
+    return v;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -358,7 +376,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __global__ void __launch_bounds__(PT_TILE)
 proj_icp_tma_kernel(const float* __restrict__ model_v, const float4* __restrict__ model_n, int K, int kcap,
                     const float4* __restrict__ tgt, const FrameResult* __restrict__ fr, int64_t tile_begin, int64_t tile_end, int scheme, float sigma,
-                    int stages, int ktma, double* __restrict__ partials) {
+                    int stages, int ktma, int64_t resident_end, double* __restrict__ partials) {
     if (fr->done) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[PT_STAGES];
@@ -382,8 +400,12 @@ proj_icp_tma_kernel(const float* __restrict__ model_v, const float4* __restrict_
         mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
         // the tile's K*3 candidate rows are contiguous in the tile-interleaved layout: one bulk copy; a second
         // one brings the tile of the (z-buffered, already transformed) target vertex map
+        // the same model is streamed once per ICP iteration: the tiles below `resident_end` ask L2 to keep them
+        // (evict-last) and are served from L2 from the second iteration on; the rest passes through (evict-first)
+        // without pushing them out
         float* dst = stage_base + (size_t)s * stage_floats;
-        bulk_copy_g2s(dst, model_v + (size_t)tile * ((size_t)kcap * 3 * PT_TILE), model_bytes, &full_bar[s]);
+        bulk_copy_g2s_hint(dst, model_v + (size_t)tile * ((size_t)kcap * 3 * PT_TILE), model_bytes, &full_bar[s],
+                           tile < resident_end ? L2_EVICT_LAST : L2_EVICT_FIRST);
         bulk_copy_g2s(dst + (size_t)rows * PT_TILE, tgt + tile * PT_TILE, PT_TILE * sizeof(float4), &full_bar[s]);
     };
     if (threadIdx.x == 0) {
@@ -406,9 +428,10 @@ proj_icp_tma_kernel(const float* __restrict__ model_v, const float4* __restrict_
         float dv[3 * KDIRECT_MAX];
         {
             const float* g = model_v + (size_t)tile * ((size_t)kcap * 3 * PT_TILE) + (size_t)ktma * 3 * PT_TILE + threadIdx.x;
+            const unsigned long long policy = tile < resident_end ? L2_EVICT_LAST : L2_EVICT_FIRST;
 #pragma unroll
             for (int j = 0; j < 3 * KDIRECT_MAX; ++j)
-                dv[j] = (j < (K - ktma) * 3) ? __ldg(g + (size_t)j * PT_TILE) : 0.f;
+                dv[j] = (j < (K - ktma) * 3) ? ldg_f32_hint(g + (size_t)j * PT_TILE, policy) : 0.f;
         }
         mbar_wait(&full_bar[s], parity);
         bool matched = false;
@@ -491,7 +514,7 @@ proj_icp_tma_kernel(const float* __restrict__ model_v, const float4* __restrict_
         // would force the load to complete here)
         pend = matched;
         if (matched) {
-            const float4 mn = model_n[normal_off(pix, kbest, kcap)];
+            const float4 mn = ldg_f4_hint(model_n + normal_off(pix, kbest, kcap), L2_EVICT_FIRST);  // one 16-byte gather, no reuse
             pn[0] = mn.x; pn[1] = mn.y; pn[2] = mn.z;
 #pragma unroll
             for (int c = 0; c < 3; ++c) { pp[c] = p[c]; pq[c] = q[c]; }
@@ -734,10 +757,14 @@ int projmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int n
         ctx->tmp[7].reserve((size_t)hw * sizeof(float4), st);
         query_resolve_kernel<<<grid_for(hw, 256), 256, 0, st>>>(zbuf, ctx->query_ptr, fr->T, &fr->done, hw, ctx->tmp[7].as<float4>());
         PLS_CHECK_LAUNCH();
+        // how much of this rank's share of the model asks to stay in the 126 MB L2 between iterations
+        static const int resident_mb = getenv("PLS_PROJ_RESIDENT_MB") ? atoi(getenv("PLS_PROJ_RESIDENT_MB")) : 56;
+        const int64_t tile_bytes = (int64_t)ctx->cfg.local_map_size * 3 * PT_TILE * sizeof(float);
+        const int64_t resident_end = tile_begin + ((int64_t)resident_mb << 20) / tile_bytes;
         ProfileScope ps(ctx, 1, 0.0, false);
         proj_icp_tma_kernel<<<blocks, PT_TILE, smem, st>>>(pm.model_v.as<float>(), pm.model_n.as<float4>(), K,
                                                            ctx->cfg.local_map_size, ctx->tmp[7].as<float4>(), fr, tile_begin,
-                                                           tile_end, ctx->cfg.scheme, ctx->cfg.sigma, stages, ktma,
+                                                           tile_end, ctx->cfg.scheme, ctx->cfg.sigma, stages, ktma, resident_end,
                                                            ctx->partials.as<double>());
         PLS_CHECK_LAUNCH();
         pm.zbuf_clean = true;

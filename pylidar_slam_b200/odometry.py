@@ -513,6 +513,10 @@ class ICPFrameToModel(OdometryAlgorithm):
         self.last_info = np.zeros(12, dtype=np.float64)
         self._pose_out = np.zeros((4, 4), dtype=np.float32)
         self._params_out = np.zeros(6, dtype=np.float32)
+        # per-frame call arguments that never change: addresses of the persistent output arrays, the has-pose cell
+        self._has_pose = C.c_int(0)
+        self._out_args = (_lib.ptr(self._pose_out), _lib.ptr(self._params_out), C.byref(self._has_pose),
+                          _lib.ptr(self.last_info))
 
     def init(self):
         super().init()
@@ -545,7 +549,9 @@ class ICPFrameToModel(OdometryAlgorithm):
             hint = _lib.PTR_DEVICE if data.is_cuda else _lib.PTR_HOST
             if data.dtype == torch.float64:
                 return _lib.INPUT_TENSOR_F64 | hint, data.contiguous(), data.shape[0]
-            return _lib.INPUT_TENSOR | hint, data.to(torch.float32).contiguous(), data.shape[0]
+            if data.dtype != torch.float32 or not data.is_contiguous():
+                data = data.to(torch.float32).contiguous()
+            return _lib.INPUT_TENSOR | hint, data, data.shape[0]
         raise RuntimeError(f"Could not interpret the data: {data} as a pointcloud tensor")
 
     # -- the reference-shaped loop over the fine-grained plug-ins (icp_odometry.py:157-380), for configurations the fused
@@ -633,7 +639,7 @@ class ICPFrameToModel(OdometryAlgorithm):
         layout, data, n = self._interpret(data_dict[self.config.data_key])
         init = data_dict.get("init_rpose", None)
         init = None if init is None else np.ascontiguousarray(np.asarray(init, dtype=np.float32).reshape(4, 4))
-        has_pose = C.c_int(0)
+        has_pose = self._has_pose
         address = _lib.ptr(data)
         if layout & _lib.PTR_HOST and n == _lib.Handoff.rows:
             # the array GridSample.filter handed out (possibly wrapped by ToTensor): its device-resident twin is used
@@ -641,8 +647,7 @@ class ICPFrameToModel(OdometryAlgorithm):
             twin = _lib.Handoff.match(address, n, bool((layout & 0xff) >= _lib.INPUT_NDARRAY_F64), int(self.ctx.cfg.device))
             if twin:
                 address, layout = twin, (layout & 0xff) | _lib.PTR_DEVICE
-        self.ctx.call("pls_process_frame", address, layout, n, _lib.ptr(init), _lib.ptr(self._pose_out),
-                      _lib.ptr(self._params_out), C.byref(has_pose), _lib.ptr(self.last_info))
+        self.ctx.call("pls_process_frame", address, layout, n, _lib.ptr(init), *self._out_args)
         layout &= 0xff
         if int(self.last_info[6]) == _lib.PLS_W_TINY_RESIDUAL:   # GaussNewton.compute's warning (optimization.py:323-327)
             import logging
@@ -662,7 +667,8 @@ class ICPFrameToModel(OdometryAlgorithm):
         elif layout == _lib.INPUT_VERTEX_MAP:
             tgt_np_pc = self.last_info[8:11].astype(np.float32).reshape(1, 3)  # icp_odometry.py:342-358 quirk
         else:
-            tgt_np_pc = data if isinstance(data, np.ndarray) else data.detach().cpu().numpy()
+            tgt_np_pc = data if isinstance(data, np.ndarray) else \
+                (data.detach().cpu().numpy() if data.is_cuda or data.requires_grad else data.numpy())
             tgt_np_pc = tgt_np_pc.astype(np.float32, copy=False)  # _tgt_pc is float32 (icp_odometry.py:352)
             if self.last_info[5] > 0:
                 tgt_np_pc = tgt_np_pc[~np.isnan(tgt_np_pc).any(axis=1)]

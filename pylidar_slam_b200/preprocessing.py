@@ -125,13 +125,16 @@ class ToTensor(Filter):
     def __init__(self, config, device: str = "cpu", **kwargs):
         super().__init__(config, **kwargs)
         self.device = torch.device(device)
+        self._keys = tuple(_cfg_to_dict(self.config.keys).items())
+        self._on_host = self.device.type == "cpu"
 
     def filter(self, data_dict: dict):
-        for source, target in _cfg_to_dict(self.config.keys).items():
+        for source, target in self._keys:
             assert_debug(source in data_dict)
             value = data_dict[source]
             assert_debug(isinstance(value, np.ndarray))
-            data_dict[target] = torch.from_numpy(value).to(self.device)
+            tensor = torch.from_numpy(value)
+            data_dict[target] = tensor if self._on_host else tensor.to(self.device)
 
 
 class FILTER(Enum):

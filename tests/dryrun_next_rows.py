@@ -90,8 +90,12 @@ class FakeContext:
         s, i = orc.grid_sample(arr(xyz, (n, 3), dt), voxel)
         self._staging = {"xyz": np.ascontiguousarray(s, dtype=dt), "idx": np.ascontiguousarray(i, dtype=np.int64),
                          "twin": np.ascontiguousarray(s, dtype=dt).copy()}
-        out_host._obj.value = self._staging["xyz"].ctypes.data
-        idx_host._obj.value = self._staging["idx"].ctypes.data
+        if out_host._obj.value and idx_host._obj.value:   # caller-owned staging (pls_pinned_alloc buffers)
+            arr(out_host._obj.value, (len(i), 3), dt)[:] = self._staging["xyz"]
+            arr(idx_host._obj.value, (len(i),), np.int64)[:] = self._staging["idx"]
+        else:
+            out_host._obj.value = self._staging["xyz"].ctypes.data
+            idx_host._obj.value = self._staging["idx"].ctypes.data
         out_dev._obj.value = self._staging["twin"].ctypes.data
         count._obj.value = len(i)
 

@@ -173,3 +173,71 @@ def test_the_fake_backend_does_not_leak():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             _lib.Context()
+
+
+def test_handoff_twin_is_matched_by_identity_and_dropped_after_a_write(b200):
+    """GridSample hands out a host array and publishes its device-resident twin; the odometry may substitute the twin
+    only for that very array with unchanged content (odometry.do_process_next_frame)."""
+    from pylidar_slam_b200 import _lib
+    pts = syn.scan(0, 16, 256).astype(np.float32)
+    ctx = dry.FakeContext()
+    samples, _ = b200.grid_sample(pts, 0.3, ctx=ctx)
+    H = _lib.Handoff
+    assert H.array is samples and H.rows == samples.shape[0] and H.dev_ptr
+    addr = _lib.ptr(torch.from_numpy(samples))            # what ToTensor produces shares the address
+    dev = int(ctx.cfg.device)
+    assert H.match(addr, samples.shape[0], False, dev) == H.dev_ptr
+    assert H.match(addr, samples.shape[0], True, dev) == 0                    # other dtype
+    assert H.match(addr, samples.shape[0] - 1, False, dev) == 0               # a slice is another cloud
+    assert H.match(_lib.ptr(samples.copy()), samples.shape[0], False, dev) == 0   # a copy lives elsewhere
+    assert H.match(addr, samples.shape[0], False, dev + 1) == 0               # twin on another device
+    samples[0, 0] += 1.0                                                       # caller edits the array: host content wins
+    assert H.match(addr, samples.shape[0], False, dev) == 0
+    H.clear()
+    assert H.match(addr, samples.shape[0], False, dev) == 0
+
+
+def test_pinned_pool_reuses_a_buffer_only_when_nothing_refers_to_it(monkeypatch):
+    """_lib.PinnedPool: arrays handed out are views of pooled buffers; a buffer takes the next frame only after every
+    view (numpy or torch) is gone; an exhausted pool answers None (the caller then copies into pageable arrays)."""
+    import ctypes as C
+    from pylidar_slam_b200 import _lib
+
+    class Allocator:            # stands in for pls_pinned_alloc / pls_pinned_free (no CUDA on this box)
+        def __init__(self):
+            self.live, self.freed = {}, []
+
+        def pls_pinned_alloc(self, n, ref):
+            block = (C.c_char * n)()
+            self.live[C.addressof(block)] = block
+            ref._obj.value = C.addressof(block)
+            return 0
+
+        def pls_pinned_free(self, p):
+            self.freed.append(p)
+            self.live.pop(p, None)
+            return 0
+
+    alloc = Allocator()
+    monkeypatch.setattr(_lib, "load", lambda: alloc)
+    monkeypatch.setattr(_lib.PinnedPool, "buffers", [])
+    monkeypatch.setattr(_lib.PinnedPool, "limit", 3)
+    take = _lib.PinnedPool.take
+    a = take(120)
+    view = a[:48].view(np.float32).reshape(-1, 3)
+    b = take(120)
+    assert a is not b and len(_lib.PinnedPool.buffers) == 2
+    del a, b
+    assert take(120) is _lib.PinnedPool.buffers[1]          # buffer 0 is still referenced through `view`
+    tensor = torch.from_numpy(view)
+    del view
+    assert take(64) is _lib.PinnedPool.buffers[1]           # ... and now through the tensor
+    del tensor
+    assert take(64) is _lib.PinnedPool.buffers[0]
+    big = take(4096)                                         # too small buffers do not qualify: a third one
+    assert big.nbytes == 4096 and len(_lib.PinnedPool.buffers) == 3
+    held = [take(8), take(8)]
+    assert held[0] is not held[1] and take(8) is None        # limit reached, everything referenced
+    del held
+    bigger = take(8192)                                      # limit reached: a free smaller buffer makes room
+    assert bigger is not None and len(_lib.PinnedPool.buffers) == 3 and len(alloc.freed) == 1

@@ -55,6 +55,11 @@ for i,v in list(by.items())[:60]:
     print(v["name"][:28].ljust(28), "us", float(v.get("gpu__time_duration.sum","0").replace(",",""))/1e3, "cyc", v.get("sm__cycles_active.avg"), "inst", v.get("smsp__inst_executed.sum"))
 PY
     ;;
+shellab)
+    for rep in 1 2; do for sh in 1 0; do
+        echo "== PLS_KD_SHELL=$sh"
+        PLS_KD_SHELL=$sh timeout 200 python tools/kd_profile.py 0 7 9 2>&1 | tail -3 | tee -a gpurun_out/${TAG}_shellab.log
+    done; done ;;
 kdprof)
     timeout 200 python tools/kd_profile.py 2>&1 | tail -9 | tee -a gpurun_out/${TAG}_kdprof.log ;;
 cellsweep)
@@ -70,6 +75,15 @@ projsweep)
         echo "== PLS_PROJ_KDIRECT=$kd PLS_PROJ_STAGES=$stg"
         PLS_PROJ_KDIRECT=$kd PLS_PROJ_STAGES=$stg timeout 200 python tools/profile_proj.py 128 4096 26 20 2>&1 | tail -1 | tee -a gpurun_out/${TAG}_projsweep.log
     done; done ;;
+residentsweep)
+    for mb in ${RESIDENT:-0 32 48 56 64 80 96}; do
+        echo "== PLS_PROJ_RESIDENT_MB=$mb"
+        PLS_PROJ_RESIDENT_MB=$mb timeout 200 python tools/profile_proj.py 128 4096 26 20 2>&1 | tail -1 | tee -a gpurun_out/${TAG}_residentsweep.log
+    done
+    for mb in ${RESIDENT3:-0 32 64}; do
+        echo "== cfg3 PLS_PROJ_RESIDENT_MB=$mb"
+        PLS_PROJ_RESIDENT_MB=$mb timeout 200 python tools/profile_proj.py 128 2048 26 10 2>&1 | tail -1 | tee -a gpurun_out/${TAG}_residentsweep.log
+    done ;;
 ncuproj)
     timeout 300 ncu --set full --clock-control none --import-source on -k regex:'proj_icp_tma_kernel' \
         --launch-skip ${SKIP:-400} --launch-count ${COUNT:-2} -f -o gpurun_out/${TAG}_proj python tools/profile_proj.py 128 4096 26 20 > gpurun_out/${TAG}_ncu_proj.log 2>&1
