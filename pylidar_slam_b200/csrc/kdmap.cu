@@ -555,8 +555,6 @@ KdIndex make_index(pls_context* ctx) {
         ix.mask[l] = ctx->kd.table_mask[l];
     }
     ix.stats = ctx->kd.stats.p ? ctx->kd.stats.as<unsigned long long>() : nullptr;
-    static const int shell = [] { const char* e = getenv("PLS_KD_SHELL"); return e ? atoi(e) : 1; }();
-    ix.shell = shell;
     return ix;
 }
 

@@ -55,11 +55,9 @@ struct KdIndex {
     const uint4* table[KD_MAX_LEVELS];
     uint32_t mask[KD_MAX_LEVELS];
     unsigned long long* stats;         // optional debug counters (PLS_KD_STATS=1), else null
-    int shell;                         // second-ring fallback on (default; PLS_KD_SHELL=0 for A/B runs)
 };
 // stats slots: 0 nn queries, 1 nn exact at level 0, 2 nn needing coarser levels, 3 nn candidates,
-//              4 knn queries, 5 knn exact at level 0, 6 knn needing coarser levels, 7 knn candidates,
-//              8 nn settled by the level-0 shell, 9 knn settled by the level-0 shell
+//              4 knn queries, 5 knn exact at level 0, 6 knn needing coarser levels, 7 knn candidates
 __device__ __forceinline__ void kd_stat(const KdIndex& ix, int slot, unsigned long long v = 1ull) {
     if (ix.stats) atomicAdd(ix.stats + slot, v);
 }
@@ -163,96 +161,6 @@ __device__ __forceinline__ float warp_probe_block(const KdIndex& ix, const KdGri
 }
 
 
-// One hashed-table lookup of cell `id` at `level`: its point range, or count = 0.
-__device__ __forceinline__ void kd_lookup_cell(const KdIndex& ix, int level, uint32_t id, int& start, int& count) {
-    const uint4* __restrict__ table = ix.table[level];
-    const uint32_t mask = ix.mask[level];
-    uint32_t h = kd_hash(id) & mask;
-    uint4 e = __ldg(table + h);
-    for (int probe = 0; probe < 64; ++probe) {
-        if (e.y != ix.gen) break;
-        if (e.x == id) {
-            start = (int)e.z;
-            count = (int)e.w - (int)e.z + 1;
-            break;
-        }
-        h = (h + 1) & mask;
-        e = __ldg(table + h);
-    }
-}
-
-// Second ring.  When the 3x3x3 block could not settle a search -- the (k-th) best distance found reaches past the
-// block -- the points that can still matter lie in the level-0 cells of the surrounding 5x5x5 block whose box is
-// within that distance of the query: usually a handful of the 98 shell cells (a sphere poking through one or two faces
-// of the core), most of them empty on a surface scan.  Four rounds of 32 lanes enumerate the shell; only cells within
-// `bound2` are looked up; the non-empty ones are compacted so that lane j ends up holding the j-th of them.
-// Returns their number (0..32), or -1 if there are more than 32 (the caller falls back to the next level).
-// *pruned2 = the smallest box distance among the shell cells that were NOT looked up (FLT_MAX if none): no point of
-// those cells is closer than that.
-__device__ __forceinline__ int warp_probe_shell(const KdIndex& ix, const KdGridLocal& g, float x, float y, float z,
-                                                float bound2, int lane, int& start, int& count, float& pruned2) {
-    start = 0;
-    count = 0;
-    const int b = g.b0;
-    const int cmax = KD_COORD_MAX >> b;
-    const float side_u = (float)(1 << b);
-    const float fx = fminf(fmaxf((x - g.mnx) * g.scale, -1.0e6f), 1.0e6f);
-    const float fy = fminf(fmaxf((y - g.mny) * g.scale, -1.0e6f), 1.0e6f);
-    const float fz = fminf(fmaxf((z - g.mnz) * g.scale, -1.0e6f), 1.0e6f);
-    const int cx = min(max(((int)floorf(fx)) >> b, 0), cmax);
-    const int cy = min(max(((int)floorf(fy)) >> b, 0), cmax);
-    const int cz = min(max(((int)floorf(fz)) >> b, 0), cmax);
-    float skipped = FLT_MAX;
-    int n = 0;
-    for (int round = 0; round < 4; ++round) {
-        const int c = round * 32 + lane;  // cells 0..124 of the 5x5x5 block
-        int s = 0, cnt = 0;
-        if (c < 125) {
-            const int dz = c / 25, rem = c - dz * 25, dy = rem / 5, dx = rem - dy * 5;
-            const int ox = dx - 2, oy = dy - 2, oz = dz - 2;
-            const int xx = cx + ox, yy = cy + oy, zz = cz + oz;
-            const bool shell = max(abs(ox), max(abs(oy), abs(oz))) == 2;
-            if (shell && xx >= 0 && xx <= cmax && yy >= 0 && yy <= cmax && zz >= 0 && zz <= cmax) {
-                const float lox = ((float)xx * side_u - fx), hix = (fx - (float)(xx + 1) * side_u);
-                const float loy = ((float)yy * side_u - fy), hiy = (fy - (float)(yy + 1) * side_u);
-                const float loz = ((float)zz * side_u - fz), hiz = (fz - (float)(zz + 1) * side_u);
-                const float ax = fmaxf(fmaxf(lox, hix) * g.inv_scale - KD_CELL_MARGIN, 0.f);
-                const float ay = fmaxf(fmaxf(loy, hiy) * g.inv_scale - KD_CELL_MARGIN, 0.f);
-                const float az = fmaxf(fmaxf(loz, hiz) * g.inv_scale - KD_CELL_MARGIN, 0.f);
-                const float box2 = ax * ax + ay * ay + az * az;
-                if (box2 <= bound2)
-                    kd_lookup_cell(ix, 0, kd_cell_id((uint32_t)xx, (uint32_t)yy, (uint32_t)zz), s, cnt);
-                else
-                    skipped = fminf(skipped, box2);
-            }
-        }
-        const unsigned m = __ballot_sync(FULL, cnt > 0);
-        const int add = __popc(m);
-        if (add) {
-            if (n + add > 32) return -1;
-            const int want = lane - n;  // lane n + j takes the j-th non-empty cell of this round
-            const bool take = want >= 0 && want < add;
-            const int src = take ? (int)__fns(m, 0, want + 1) : 0;
-            const int gs = __shfl_sync(FULL, s, src), gc = __shfl_sync(FULL, cnt, src);
-            if (take) {
-                start = gs;
-                count = gc;
-            }
-            n += add;
-        }
-    }
-    pruned2 = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(skipped)));
-    return n;
-}
-
-// Squared radius around the query within which the 5x5x5 level-0 block certainly holds every map point
-// (negative if level 0 is unusable).
-__device__ __forceinline__ float kd_shell_radius2(const KdIndex& ix, const KdGridLocal& g) {
-    if (!ix.shell || g.top < 1 || __ldg(&ix.grid->overflow[0])) return -1.f;
-    const float r = 2.f * (float)(1 << g.b0) * g.inv_scale - KD_CELL_MARGIN;
-    return r > 0.f ? r * r : -1.f;
-}
-
 // arg-min of (d, i) over the warp with two REDUX instructions (d >= 0, so the float's bit pattern orders like its
 // value; ties: smaller index).  The result lands in every lane; (FLT_MAX, -1) if no lane holds a candidate.
 __device__ __forceinline__ void warp_argmin(float& d, int& i) {
@@ -348,54 +256,6 @@ __device__ __forceinline__ int warp_nearest(const KdIndex& ix, const KdGridLocal
             if (level == 0) kd_stat(ix, (best_i >= 0 && best <= r2) ? 1 : 2);
         }
         if (best_i >= 0 && best <= r2) break;
-        if (level == 0 && best_i >= 0) {
-            // second ring of level-0 cells instead of a whole coarser block (see warp_probe_shell)
-            const float r5 = kd_shell_radius2(ix, g);
-            if (best <= r5) {
-                int s2, c2;
-                float pruned2;
-                const int cells = warp_probe_shell(ix, g, x, y, z, best, lane, s2, c2, pruned2);
-                if (cells >= 0) {
-                    int incl2;
-                    const int total2 = warp_scan_counts(c2, lane, incl2);
-                    const int adj2 = s2 - (incl2 - c2);
-                    float sd = best, l2s = FLT_MAX;
-                    int si = best_i;
-                    for (int base = 0; base < total2; base += 32) {
-                        const int t = base + lane;
-                        const bool active = t < total2;
-                        const int idx = warp_candidate(incl2, adj2, active ? t : total2 - 1);
-                        if (active) {
-                            const float d = dist2_point(x, y, z, __ldg(ix.sorted + idx));
-                            if (d < sd || (d == sd && (unsigned)idx < (unsigned)si)) {
-                                l2s = fminf(l2s, sd);
-                                sd = d;
-                                si = idx;
-                            } else if (idx != si) {  // (the seed of the bound may itself lie in the shell)
-                                l2s = fminf(l2s, d);
-                            }
-                        }
-                    }
-                    float wd = sd;
-                    int wi = si;
-                    warp_argmin(wd, wi);
-                    if (si != wi) l2s = fminf(l2s, sd);
-                    // runner-up bound: the core's runner-up, everything examined in the shell, the shell cells that
-                    // were skipped, the rim of the 5x5x5 block -- and the core's winner if the shell beat it
-                    float sec = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(l2s)));
-                    sec = fminf(fminf(sec, pruned2), fminf(r5, inner));
-                    second = wi == best_i ? sec : fminf(sec, best);
-                    best = wd;
-                    best_i = wi;
-                    if (cand_out) *cand_out += total2;
-                    if (ix.stats && lane == 0) {
-                        kd_stat(ix, 3, (unsigned long long)total2);
-                        kd_stat(ix, 8);
-                    }
-                    break;
-                }
-            }
-        }
     }
     if (second_out) *second_out = second;
     return best_i;
@@ -497,26 +357,6 @@ __device__ __forceinline__ int warp_knn(const KdIndex& ix, const KdGridLocal& g,
         if (ix.stats && lane == 0 && level == 0) kd_stat(ix, exact ? 5 : 6);
         if (exact) break;
         if (found == K) bound = kth;
-        if (level == 0 && found == K && kth <= kd_shell_radius2(ix, g)) {
-            // the K-th distance reaches past the 3x3x3 block but stays inside the 5x5x5 one: merge the points of the
-            // few shell cells it touches into the list instead of selecting afresh from a coarser block
-            int s2, c2;
-            float pruned2;
-            const int cells = warp_probe_shell(ix, g, x, y, z, kth, lane, s2, c2, pruned2);
-            if (cells >= 0) {
-                int incl2;
-                const int total2 = warp_scan_counts(c2, lane, incl2);
-                const int adj2 = s2 - (incl2 - c2);
-                if (cand_out) *cand_out += total2;
-                if (ix.stats && lane == 0) {
-                    kd_stat(ix, 7, (unsigned long long)total2);
-                    kd_stat(ix, 9);
-                }
-                for (int chunk = 0; chunk < total2; chunk += 64)  // usually one chunk; the list is carried across
-                    knn_select_chunk<2>(ix, x, y, z, K, lane, incl2, adj2, total2, chunk, keep_d, keep_i);
-                break;
-            }
-        }
     }
     out_d = keep_d;
     out_i = keep_i;

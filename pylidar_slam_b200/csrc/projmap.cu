@@ -376,7 +376,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __global__ void __launch_bounds__(PT_TILE)
 proj_icp_tma_kernel(const float* __restrict__ model_v, const float4* __restrict__ model_n, int K, int kcap,
                     const float4* __restrict__ tgt, const FrameResult* __restrict__ fr, int64_t tile_begin, int64_t tile_end, int scheme, float sigma,
-                    int stages, int ktma, int64_t resident_end, double* __restrict__ partials) {
+                    int stages, int ktma, int64_t resident_end, unsigned long long policy_resident,
+                    unsigned long long policy_stream, double* __restrict__ partials) {
     if (fr->done) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[PT_STAGES];
@@ -405,7 +406,7 @@ proj_icp_tma_kernel(const float* __restrict__ model_v, const float4* __restrict_
         // without pushing them out
         float* dst = stage_base + (size_t)s * stage_floats;
         bulk_copy_g2s_hint(dst, model_v + (size_t)tile * ((size_t)kcap * 3 * PT_TILE), model_bytes, &full_bar[s],
-                           tile < resident_end ? L2_EVICT_LAST : L2_EVICT_FIRST);
+                           tile < resident_end ? policy_resident : policy_stream);
         bulk_copy_g2s(dst + (size_t)rows * PT_TILE, tgt + tile * PT_TILE, PT_TILE * sizeof(float4), &full_bar[s]);
     };
     if (threadIdx.x == 0) {
@@ -428,7 +429,7 @@ proj_icp_tma_kernel(const float* __restrict__ model_v, const float4* __restrict_
         float dv[3 * KDIRECT_MAX];
         {
             const float* g = model_v + (size_t)tile * ((size_t)kcap * 3 * PT_TILE) + (size_t)ktma * 3 * PT_TILE + threadIdx.x;
-            const unsigned long long policy = tile < resident_end ? L2_EVICT_LAST : L2_EVICT_FIRST;
+            const unsigned long long policy = tile < resident_end ? policy_resident : policy_stream;
 #pragma unroll
             for (int j = 0; j < 3 * KDIRECT_MAX; ++j)
                 dv[j] = (j < (K - ktma) * 3) ? ldg_f32_hint(g + (size_t)j * PT_TILE, policy) : 0.f;
@@ -514,7 +515,7 @@ proj_icp_tma_kernel(const float* __restrict__ model_v, const float4* __restrict_
         // would force the load to complete here)
         pend = matched;
         if (matched) {
-            const float4 mn = ldg_f4_hint(model_n + normal_off(pix, kbest, kcap), L2_EVICT_FIRST);  // one 16-byte gather, no reuse
+            const float4 mn = ldg_f4_hint(model_n + normal_off(pix, kbest, kcap), policy_stream);  // one 16-byte gather, no reuse
             pn[0] = mn.x; pn[1] = mn.y; pn[2] = mn.z;
 #pragma unroll
             for (int c = 0; c < 3; ++c) { pp[c] = p[c]; pq[c] = q[c]; }
@@ -761,11 +762,13 @@ int projmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int n
         static const int resident_mb = getenv("PLS_PROJ_RESIDENT_MB") ? atoi(getenv("PLS_PROJ_RESIDENT_MB")) : 56;
         const int64_t tile_bytes = (int64_t)ctx->cfg.local_map_size * 3 * PT_TILE * sizeof(float);
         const int64_t resident_end = tile_begin + ((int64_t)resident_mb << 20) / tile_bytes;
+        // (a persisting access-policy window on the stream -- a set-aside part of L2 -- was tried instead of the
+        // per-instruction priorities and lost: 38.5 us vs 33.2 us per launch at cfg5, profiles/r2_proj_l2_residency.md)
         ProfileScope ps(ctx, 1, 0.0, false);
         proj_icp_tma_kernel<<<blocks, PT_TILE, smem, st>>>(pm.model_v.as<float>(), pm.model_n.as<float4>(), K,
                                                            ctx->cfg.local_map_size, ctx->tmp[7].as<float4>(), fr, tile_begin,
                                                            tile_end, ctx->cfg.scheme, ctx->cfg.sigma, stages, ktma, resident_end,
-                                                           ctx->partials.as<double>());
+                                                           L2_EVICT_LAST, L2_EVICT_FIRST, ctx->partials.as<double>());
         PLS_CHECK_LAUNCH();
         pm.zbuf_clean = true;
         return blocks;

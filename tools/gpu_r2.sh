@@ -55,11 +55,6 @@ for i,v in list(by.items())[:60]:
     print(v["name"][:28].ljust(28), "us", float(v.get("gpu__time_duration.sum","0").replace(",",""))/1e3, "cyc", v.get("sm__cycles_active.avg"), "inst", v.get("smsp__inst_executed.sum"))
 PY
     ;;
-shellab)
-    for rep in 1 2; do for sh in 1 0; do
-        echo "== PLS_KD_SHELL=$sh"
-        PLS_KD_SHELL=$sh timeout 200 python tools/kd_profile.py 0 7 9 2>&1 | tail -3 | tee -a gpurun_out/${TAG}_shellab.log
-    done; done ;;
 kdprof)
     timeout 200 python tools/kd_profile.py 2>&1 | tail -9 | tee -a gpurun_out/${TAG}_kdprof.log ;;
 cellsweep)
@@ -75,6 +70,30 @@ projsweep)
         echo "== PLS_PROJ_KDIRECT=$kd PLS_PROJ_STAGES=$stg"
         PLS_PROJ_KDIRECT=$kd PLS_PROJ_STAGES=$stg timeout 200 python tools/profile_proj.py 128 4096 26 20 2>&1 | tail -1 | tee -a gpurun_out/${TAG}_projsweep.log
     done; done ;;
+traffic)
+    M="dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum"
+    timeout 600 ncu --replay-mode application --cache-control none --clock-control none --metrics $M \
+        -k regex:'kd_nn_verify_kernel|kd_nn_warp_kernel|kd_normals_warp_kernel|kd_residual_kernel' --launch-skip ${KDSKIP:-330} --launch-count ${KDCOUNT:-90} \
+        --csv --log-file gpurun_out/${TAG}_traffic_kd.csv python bench.py --quick --steps 8 --warmup 24 > gpurun_out/${TAG}_traffic_kd.log 2>&1
+    timeout 600 ncu --replay-mode application --cache-control none --clock-control none --metrics $M -k regex:'proj_icp_tma_kernel' \
+        --launch-skip 400 --launch-count 40 --csv --log-file gpurun_out/${TAG}_traffic_cfg5.csv python tools/profile_proj.py 128 4096 26 20 > gpurun_out/${TAG}_traffic_cfg5.log 2>&1
+    timeout 600 ncu --replay-mode application --cache-control none --clock-control none --metrics $M -k regex:'proj_icp_tma_kernel' \
+        --launch-skip 150 --launch-count 60 --csv --log-file gpurun_out/${TAG}_traffic_cfg3.csv python tools/profile_proj.py 128 2048 26 10 > gpurun_out/${TAG}_traffic_cfg3.log 2>&1
+    python tools/traffic_summary.py ${TAG} ${COMMIT:-unknown} ;;
+ncuresident)
+    for mb in ${RESIDENT:-0 64}; do
+        PLS_PROJ_RESIDENT_MB=$mb timeout 300 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,gpu__time_duration.sum,dram__throughput.avg.pct_of_peak_sustained_elapsed,lts__t_sectors_srcunit_tex_op_read.sum,lts__t_sectors_srcunit_tex_op_read_lookup_hit.sum --clock-control none --cache-control none -k regex:'proj_icp_tma_kernel' \
+            --launch-skip ${SKIP:-400} --launch-count ${COUNT:-4} --csv --log-file gpurun_out/${TAG}_resident_${mb}.csv python tools/profile_proj.py 128 4096 26 20 > gpurun_out/${TAG}_ncu_resident.log 2>&1
+        python - <<PY
+import csv
+lines=[l for l in open("gpurun_out/${TAG}_resident_${mb}.csv") if l.startswith('"')]
+by={}
+for r in csv.DictReader(lines):
+    by.setdefault(r["ID"],{})[r["Metric Name"]]=r["Metric Value"]
+for i,v in by.items():
+    print("resident $mb MB:", {k.split("__")[-1][:40]: x for k,x in v.items()})
+PY
+    done ;;
 residentsweep)
     for mb in ${RESIDENT:-0 32 48 56 64 80 96}; do
         echo "== PLS_PROJ_RESIDENT_MB=$mb"
