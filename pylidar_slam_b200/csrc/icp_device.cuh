@@ -6,17 +6,32 @@
 
 namespace pls {
 
-// Deterministic parallel sum of the block partial rows (256 threads, all must call): warp w sums the rows
-// w, w+8, ... of every accumulator (lane = accumulator, so a row is one coalesced 240-byte read and the loads
-// of a lane are independent), then the eight slices are added in fixed order.
+// Deterministic parallel sum of the block partial rows (THREADS = 256 or 128 threads, all must call): slice w of
+// eight sums the rows w, w+8, ... of every accumulator (lane = accumulator, so a row is one coalesced 240-byte read and
+// the loads of a lane are independent), then the eight slices are added in fixed order -- the same additions in the
+// same order whatever the block size (a 128-thread block gives two slices to each warp).
+template <int THREADS = 256>
 __device__ __forceinline__ void sum_partials_256(const double* __restrict__ partials, int num_blocks, double* sums) {
+    static_assert(THREADS == 256 || THREADS == 128, "sum_partials: 4 or 8 warps");
     __shared__ double slice_sum[8][NACC];
-    const int slice = threadIdx.x >> 5, a = threadIdx.x & 31;
+    const int a = threadIdx.x & 31;
     if (a < NACC) {
-        double s = 0.0;
-#pragma unroll 4
-        for (int b = slice; b < num_blocks; b += 8) s += __ldcg(partials + (size_t)b * NACC + a);
-        slice_sum[slice][a] = s;
+        for (int slice = threadIdx.x >> 5; slice < 8; slice += THREADS / 32) {
+            // sixteen rows in flight per lane (the additions keep their order; a missing row adds +0.0): the sum of a
+            // few hundred rows is a chain of L2 round trips otherwise
+            double s = 0.0;
+            for (int b0 = slice; b0 < num_blocks; b0 += 8 * 16) {
+                double v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int b = b0 + 8 * j;
+                    v[j] = b < num_blocks ? __ldcg(partials + (size_t)b * NACC + a) : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) s += v[j];
+            }
+            slice_sum[slice][a] = s;
+        }
     }
     __syncthreads();
     if (threadIdx.x < NACC) {
@@ -73,9 +88,10 @@ __device__ __forceinline__ void icp_solve_and_update(FrameResult* fr, const doub
     for (int i = 0; i < 6; ++i) fr->params[i] = prm[i];
 }
 
-// Called by every block of a 256-thread correspondence kernel after it stored its partial row: the block
+// Called by every block of a correspondence kernel (256 or 128 threads) after it stored its partial row: the block
 // that arrives last (ticket in fr->pad) sums all rows in the fixed order and runs the solve -- one launch
 // and one dependent-launch gap less per ICP iteration than a separate step kernel.
+template <int THREADS = 256>
 __device__ __forceinline__ void icp_finish_in_last_block(FrameResult* fr, const double* __restrict__ partials,
                                                          float threshold_delta) {
     __shared__ int s_last;
@@ -89,7 +105,7 @@ __device__ __forceinline__ void icp_finish_in_last_block(FrameResult* fr, const 
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    sum_partials_256(partials, (int)gridDim.x, s_sums);
+    sum_partials_256<THREADS>(partials, (int)gridDim.x, s_sums);
     __syncthreads();
     if (threadIdx.x < NACC) fr->last_sums[threadIdx.x] = s_sums[threadIdx.x];
     if (threadIdx.x != 0) return;

@@ -131,6 +131,7 @@ struct ProjMap {
     DBuf zbuf;              // [Kmax][H][W] u64
     bool valid = false;
     bool zbuf_clean = false; // the query z-buffer (tmp[3]) is known to be all-empty
+    int64_t built_lo = 0, built_hi = 0;  // pixel range the model currently covers (a rank of a sharded job builds its share)
 };
 
 struct FrameResult {        // mirrored to pinned host memory at the end of a frame
@@ -369,6 +370,11 @@ void grid_sample_device(pls_context* ctx, const T* xyz_dev, int64_t n, double vo
 uint32_t grid_sample_read_count(pls_context* ctx, bool* overflowed);
 // projmap.cu
 void projmap_reset(pls_context* ctx);
+// odometry.cu: would an ICP iteration over `work` items be split across the ranks (the rule of enqueue_icp_iterations)?
+bool icp_shards(pls_context* ctx, int64_t work);
+// comm.cu
+int comm_rank(pls_context* ctx);
+int comm_size(pls_context* ctx);
 void projmap_update(pls_context* ctx, const float* rel_pose_host, const float* vmap_dev);
 // odometry.cu
 void odometry_reset(pls_context* ctx);

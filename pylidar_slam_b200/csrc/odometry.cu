@@ -215,6 +215,16 @@ struct FrameInputSelect {
     }
 };
 
+}  // namespace
+
+bool icp_shards(pls_context* ctx, int64_t work) {
+    const int size = comm_size(ctx);
+    const int64_t shard_min = g_shard_min_override >= 0 ? g_shard_min_override : shard_min_default();
+    return size > 1 && work / size >= shard_min;
+}
+
+namespace {
+
 inline int grid_for(int64_t n, int threads = 256) {
     int64_t b = (n + threads - 1) / threads;
     int64_t cap = 8 * kNumSMs;
@@ -232,10 +242,9 @@ int enqueue_icp_iterations(pls_context* ctx, int64_t query_bound, int first, int
     // PLS_SHARD_MIN work items (queries / pixels) per rank every rank runs the whole iteration itself -- same inputs,
     // same deterministic kernels, hence the same bits on every rank, and no exchange at all.  (The bound is a host
     // value every rank computes alike, so the ranks always take the same branch.)
-    const int64_t shard_min = g_shard_min_override >= 0 ? g_shard_min_override : shard_min_default();
     if (size > 1) {
         const int64_t work = ctx->cfg.local_map_type == PLS_MAP_KDTREE ? query_bound : (int64_t)ctx->cfg.height * ctx->cfg.width;
-        if (work / size < shard_min) {
+        if (!icp_shards(ctx, work)) {
             rank = 0;
             size = 1;
         }
@@ -247,7 +256,8 @@ int enqueue_icp_iterations(pls_context* ctx, int64_t query_bound, int first, int
         bool solved = false;  // the kd kernels finish the iteration themselves on a single GPU
         if (ctx->cfg.local_map_type == PLS_MAP_KDTREE)
             blocks = kdmap_icp_iteration(ctx, query_bound, rank, size, it, size == 1 ? ctx->cfg.threshold_delta_pose : -1.f, &solved);
-        else blocks = projmap_icp_iteration(ctx, query_bound, rank, size);
+        else
+            blocks = projmap_icp_iteration(ctx, query_bound, rank, size);
         last_blocks = blocks;
         if (solved) continue;
         if (size > 1 && comm_is_p2p(ctx)) {

@@ -142,8 +142,9 @@ __device__ __forceinline__ bool model_point(const float* __restrict__ vmaps, con
     return false;
 }
 
+// (a rank of a sharded job keeps only the pixels [pix_lo, pix_hi) of its own tiles)
 __global__ void model_zbuf_kernel(const float* __restrict__ vmaps, const float* __restrict__ poses, int K, int head,
-                                  int slots, ProjConst pc, unsigned long long* __restrict__ zbuf) {
+                                  int slots, ProjConst pc, int pix_lo, int pix_hi, unsigned long long* __restrict__ zbuf) {
     const int64_t hw = (int64_t)pc.H * pc.W;
     const int64_t total = (int64_t)K * hw;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
@@ -152,7 +153,7 @@ __global__ void model_zbuf_kernel(const float* __restrict__ vmaps, const float* 
         if (!model_point(vmaps + (size_t)((head + k) % slots) * 3 * hw, poses + 16 * k, hw, src, p)) continue;
         int pix;
         float r;
-        if (project_to_pixel(p[0], p[1], p[2], pc, pix, r)) {
+        if (project_to_pixel(p[0], p[1], p[2], pc, pix, r) && pix >= pix_lo && pix < pix_hi) {
             unsigned long long key = ((unsigned long long)__float_as_uint(r) << 32) | (unsigned long long)(uint32_t)src;
             atomicMin(&zbuf[k * hw + pix], key);
         }
@@ -161,12 +162,12 @@ __global__ void model_zbuf_kernel(const float* __restrict__ vmaps, const float* 
 
 __global__ void model_resolve_kernel(const float* __restrict__ vmaps, const float* __restrict__ nmaps,
                                      const float* __restrict__ poses, int K, int head, int slots, int kcap, int64_t hw,
-                                     const unsigned long long* __restrict__ zbuf, float* __restrict__ model_v,
-                                     float4* __restrict__ model_n) {
-    const int64_t total = (int64_t)K * hw;
+                                     int64_t pix_lo, int64_t pix_hi, const unsigned long long* __restrict__ zbuf,
+                                     float* __restrict__ model_v, float4* __restrict__ model_n) {
+    const int64_t span = pix_hi - pix_lo, total = (int64_t)K * span;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t k = g / hw, pix = g - k * hw;
-        const unsigned long long key = zbuf[g];
+        const int64_t k = g / span, pix = pix_lo + (g - k * span);
+        const unsigned long long key = zbuf[k * hw + pix];
         float p[3] = {0.f, 0.f, 0.f}, n[3] = {0.f, 0.f, 0.f};
         if (key != ~0ull) {
             const int64_t src = (int64_t)(uint32_t)(key & 0xffffffffull);
@@ -192,8 +193,8 @@ __device__ __forceinline__ void load_T(const float* __restrict__ T, float* sT) {
 }
 
 __global__ void query_zbuf_kernel(const float4* __restrict__ queries, const uint32_t* __restrict__ nq_dev, int64_t nq_host,
-                                  const float* __restrict__ T, const int* __restrict__ done, ProjConst pc,
-                                  unsigned long long* __restrict__ zbuf) {
+                                  const float* __restrict__ T, const int* __restrict__ done, ProjConst pc, int pix_lo,
+                                  int pix_hi, unsigned long long* __restrict__ zbuf) {
     if (done && *done) return;
     __shared__ float sT[12];
     if (T) load_T(T, sT);
@@ -208,7 +209,7 @@ __global__ void query_zbuf_kernel(const float4* __restrict__ queries, const uint
         }
         int pix;
         float r;
-        if (project_to_pixel(p[0], p[1], p[2], pc, pix, r)) {
+        if (project_to_pixel(p[0], p[1], p[2], pc, pix, r) && pix >= pix_lo && pix < pix_hi) {
             unsigned long long key = ((unsigned long long)__float_as_uint(r) << 32) | (unsigned long long)(uint32_t)i;
             atomicMin(&zbuf[pix], key);
         }
@@ -217,12 +218,12 @@ __global__ void query_zbuf_kernel(const float4* __restrict__ queries, const uint
 
 // z-buffer winners -> the target vertex map of this iteration, float4 (p transformed, valid flag) per pixel
 __global__ void query_resolve_kernel(unsigned long long* __restrict__ zbuf, const float4* __restrict__ queries,
-                                     const float* __restrict__ T, const int* __restrict__ done, int64_t hw,
-                                     float4* __restrict__ tgt) {
+                                     const float* __restrict__ T, const int* __restrict__ done, int64_t pix_lo,
+                                     int64_t pix_hi, float4* __restrict__ tgt) {
     if (done && *done) return;
     __shared__ float sT[12];
     load_T(T, sT);
-    for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < hw; pix += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t pix = pix_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < pix_hi; pix += (int64_t)gridDim.x * blockDim.x) {
         const unsigned long long key = zbuf[pix];
         zbuf[pix] = ~0ull;  // leave the z-buffer cleared for the next iteration (no separate memset)
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -531,6 +532,8 @@ proj_icp_tma_kernel(const float* __restrict__ model_v, const float4* __restrict_
 #pragma unroll
     for (int a = 0; a < NACC; ++a) acc64[a] = (double)acc[a];
     block_reduce_store<PT_TILE>(acc64, partials + (size_t)blockIdx.x * NACC);
+    // (finishing the iteration in the CTA that arrives last -- as kd_residual_kernel does -- was measured and lost here:
+    // 1.51-1.54 vs 1.46 ms per cfg5 frame; the solve stays in icp_step_kernel)
 }
 
 // per-pixel association for the fine-grained API: flag + (q, n, p)
@@ -619,14 +622,29 @@ __global__ void normal_export_kernel(const float4* __restrict__ tiled, int K, in
     }
 }
 
-void rebuild_model(pls_context* ctx) {
+// The pixel range of the model this rank needs: all of it, or -- when the ICP iterations of this job are split across
+// ranks (icp_shards) and the TMA path applies -- the tiles the rank reduces (projmap_icp_iteration takes the same split).
+void model_range(pls_context* ctx, bool full, int64_t* lo, int64_t* hi) {
+    const int64_t hw = (int64_t)ctx->cfg.height * ctx->cfg.width;
+    *lo = 0;
+    *hi = hw;
+    if (full || hw % PT_TILE != 0 || !icp_shards(ctx, hw)) return;
+    const int64_t tiles = hw / PT_TILE;
+    const int rank = comm_rank(ctx), size = comm_size(ctx);
+    *lo = (tiles * rank / size) * PT_TILE;
+    *hi = (tiles * (rank + 1) / size) * PT_TILE;
+}
+
+void rebuild_model(pls_context* ctx, bool full = false) {
     ProjMap& pm = ctx->pm;
     cudaStream_t st = ctx->stream;
     const int H = ctx->cfg.height, W = ctx->cfg.width;
     const int64_t hw = (int64_t)H * W;
     const int K = pm.K;
     if (K == 0) return;
-    ProfileScope ps(ctx, 2, (double)K * hw * (24.0 + 24.0 + 16.0));
+    int64_t lo, hi;
+    model_range(ctx, full, &lo, &hi);
+    ProfileScope ps(ctx, 2, (double)K * (hw * 24.0 + (hi - lo) * (24.0 + 16.0)));
     pm.poses.reserve((size_t)ctx->cfg.local_map_size * 16 * sizeof(float) + 64, st);
     PLS_CUDA(cudaMemcpyAsync(pm.poses.p, pm.host_poses.data(), (size_t)K * 16 * sizeof(float), cudaMemcpyHostToDevice, st));
     pm.zbuf.reserve((size_t)(K > 1 ? K : 1) * hw * sizeof(unsigned long long), st);
@@ -634,18 +652,30 @@ void rebuild_model(pls_context* ctx) {
     const size_t model_floats = (size_t)((hw + PT_TILE - 1) / PT_TILE) * kcap * 3 * PT_TILE;
     pm.model_v.reserve(model_floats * sizeof(float), st);
     pm.model_n.reserve((size_t)((hw + PT_TILE - 1) / PT_TILE) * kcap * PT_TILE * sizeof(float4), st);
-    PLS_CUDA(cudaMemsetAsync(pm.zbuf.p, 0xff, (size_t)K * hw * sizeof(unsigned long long), st));
+    if (lo == 0 && hi == hw)
+        PLS_CUDA(cudaMemsetAsync(pm.zbuf.p, 0xff, (size_t)K * hw * sizeof(unsigned long long), st));
+    else  // only the rank's own pixel columns of each of the K z-buffers
+        PLS_CUDA(cudaMemset2DAsync(pm.zbuf.as<unsigned long long>() + lo, (size_t)hw * sizeof(unsigned long long), 0xff,
+                                   (size_t)(hi - lo) * sizeof(unsigned long long), (size_t)K, st));
     ProjConst pc = make_proj_const(H, W, ctx->cfg.up_fov_deg, ctx->cfg.down_fov_deg);
     const int slots = ctx->cfg.local_map_size + 1;
     model_zbuf_kernel<<<grid_for(K * hw, 256), 256, 0, st>>>(pm.vmaps.as<float>(), pm.poses.as<float>(), K, pm.head, slots,
-                                                             pc, pm.zbuf.as<unsigned long long>());
+                                                             pc, (int)lo, (int)hi, pm.zbuf.as<unsigned long long>());
     PLS_CHECK_LAUNCH();
-    model_resolve_kernel<<<grid_for(K * hw, 256), 256, 0, st>>>(pm.vmaps.as<float>(), pm.nmaps.as<float>(),
-                                                                pm.poses.as<float>(), K, pm.head, slots, kcap, hw,
-                                                                pm.zbuf.as<unsigned long long>(),
-                                                                pm.model_v.as<float>(), pm.model_n.as<float4>());
+    model_resolve_kernel<<<grid_for(K * (hi - lo), 256), 256, 0, st>>>(pm.vmaps.as<float>(), pm.nmaps.as<float>(),
+                                                                       pm.poses.as<float>(), K, pm.head, slots, kcap, hw, lo, hi,
+                                                                       pm.zbuf.as<unsigned long long>(),
+                                                                       pm.model_v.as<float>(), pm.model_n.as<float4>());
     PLS_CHECK_LAUNCH();
     pm.valid = true;
+    pm.built_lo = lo;
+    pm.built_hi = hi;
+}
+
+// Callers that read the whole model (export, the stand-alone search) on a rank that built only its share.
+void ensure_full_model(pls_context* ctx) {
+    const int64_t hw = (int64_t)ctx->cfg.height * ctx->cfg.width;
+    if (ctx->pm.valid && (ctx->pm.built_lo != 0 || ctx->pm.built_hi != hw)) rebuild_model(ctx, true);
 }
 
 }  // namespace
@@ -722,9 +752,6 @@ int projmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int n
     if (!pm.zbuf_clean) PLS_CUDA(cudaMemsetAsync(zbuf, 0xff, (size_t)hw * sizeof(unsigned long long), st));
     pm.zbuf_clean = false;
     ProjConst pc = make_proj_const(H, W, ctx->cfg.up_fov_deg, ctx->cfg.down_fov_deg);
-    query_zbuf_kernel<<<grid_for(query_bound, 256), 256, 0, st>>>(
-        ctx->query_ptr, reinterpret_cast<const uint32_t*>(&fr->counts[1]), 0, fr->T, &fr->done, pc, zbuf);
-    PLS_CHECK_LAUNCH();
     const int K = pm.K;
     // split of the K candidates between the TMA path and the direct-load path (at most 10 direct)
     static const int kdirect_env = getenv("PLS_PROJ_KDIRECT") ? atoi(getenv("PLS_PROJ_KDIRECT")) : 4;
@@ -734,11 +761,21 @@ int projmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int n
     const size_t stage_bytes = (size_t)(ktma * 3 + 4) * PT_TILE * sizeof(float);
     static const bool no_tma = getenv("PLS_PROJ_NO_TMA") != nullptr;
     static const int stages = getenv("PLS_PROJ_STAGES") ? atoi(getenv("PLS_PROJ_STAGES")) : 2;
+    const bool use_tma = !no_tma && hw % PT_TILE == 0 && stages >= 1 && stages <= PT_STAGES && stage_bytes * stages <= 200 * 1024;
+    // the pixels this rank reduces: whole 128-pixel tiles on the TMA path.  Only they take part in the z-buffer of the
+    // transformed queries and in the target map, and only they need the model (a sharded rank builds just its share)
+    const int64_t tiles = hw / PT_TILE;
+    const int64_t tile_begin = tiles * rank / num_ranks, tile_end = tiles * (rank + 1) / num_ranks;
+    const int64_t need_lo = use_tma ? tile_begin * PT_TILE : hw * rank / num_ranks;
+    const int64_t need_hi = use_tma ? tile_end * PT_TILE : hw * (rank + 1) / num_ranks;
+    if (need_lo < pm.built_lo || need_hi > pm.built_hi) rebuild_model(ctx, true);  // (the split rule changed since the update)
+    query_zbuf_kernel<<<grid_for(query_bound, 256), 256, 0, st>>>(
+        ctx->query_ptr, reinterpret_cast<const uint32_t*>(&fr->counts[1]), 0, fr->T, &fr->done, pc,
+        use_tma ? (int)need_lo : 0, use_tma ? (int)need_hi : (int)hw, zbuf);
+    PLS_CHECK_LAUNCH();
     int blocks;
-    if (!no_tma && hw % PT_TILE == 0 && stages >= 1 && stages <= PT_STAGES && stage_bytes * stages <= 200 * 1024) {
+    if (use_tma) {
         // TMA-staged persistent kernel over 128-pixel tiles; ranks take contiguous tile ranges
-        const int64_t tiles = hw / PT_TILE;
-        const int64_t tile_begin = tiles * rank / num_ranks, tile_end = tiles * (rank + 1) / num_ranks;
         const size_t smem = stage_bytes * stages;
         static bool attr_set = false;
         if (!attr_set) {
@@ -756,7 +793,8 @@ int projmap_icp_iteration(pls_context* ctx, int64_t query_bound, int rank, int n
         }
         ctx->partials.reserve((size_t)blocks * NACC * sizeof(double), st);
         ctx->tmp[7].reserve((size_t)hw * sizeof(float4), st);
-        query_resolve_kernel<<<grid_for(hw, 256), 256, 0, st>>>(zbuf, ctx->query_ptr, fr->T, &fr->done, hw, ctx->tmp[7].as<float4>());
+        query_resolve_kernel<<<grid_for(need_hi - need_lo, 256), 256, 0, st>>>(zbuf, ctx->query_ptr, fr->T, &fr->done, need_lo, need_hi,
+                                                                               ctx->tmp[7].as<float4>());
         PLS_CHECK_LAUNCH();
         // how much of this rank's share of the model asks to stay in the 126 MB L2 between iterations
         static const int resident_mb = getenv("PLS_PROJ_RESIDENT_MB") ? atoi(getenv("PLS_PROJ_RESIDENT_MB")) : 56;
@@ -851,6 +889,7 @@ int pls_projmap_model(pls_context* ctx, float* out_vmap, float* out_nmap) {
     PLS_API_BEGIN(ctx)
     map_stream_wait(ctx);
     PLS_REQUIRE(ctx->pm.valid, "pls_projmap_model: empty map");
+    ensure_full_model(ctx);
     const int64_t hw = (int64_t)ctx->cfg.height * ctx->cfg.width;
     const size_t bytes = (size_t)ctx->pm.K * 3 * hw * sizeof(float);
     auto put = [&](float* dst, const float* tiled, DBuf& stage) {
@@ -891,7 +930,8 @@ int pls_projmap_nn_search(pls_context* ctx, const float* queries, int64_t n, flo
     unsigned long long* zbuf = ctx->tmp[3].as<unsigned long long>();
     PLS_CUDA(cudaMemsetAsync(zbuf, 0xff, (size_t)hw * sizeof(unsigned long long), st));
     ProjConst pc = make_proj_const(H, W, ctx->cfg.up_fov_deg, ctx->cfg.down_fov_deg);
-    query_zbuf_kernel<<<grid_for(n, 256), 256, 0, st>>>(ctx->queries.as<float4>(), cnt, 0, nullptr, nullptr, pc, zbuf);
+    ensure_full_model(ctx);
+    query_zbuf_kernel<<<grid_for(n, 256), 256, 0, st>>>(ctx->queries.as<float4>(), cnt, 0, nullptr, nullptr, pc, 0, (int)hw, zbuf);
     PLS_CHECK_LAUNCH();
     ctx->tmp[1].reserve((size_t)hw, st);
     ctx->tmp[2].reserve((size_t)hw * sizeof(uint32_t), st);

@@ -124,7 +124,7 @@ mbench)
         [ "$n" -le "$NG" ] || continue
         for comm in ${COMMS:-p2p}; do
             timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29541 \
-                bench.py --gpus $n --steps 20 --warmup 5 --comm $comm > gpurun_out/${TAG}_bench_n${n}_${comm}.json 2> gpurun_out/${TAG}_bench_n${n}_${comm}.err
+                bench.py --gpus $n --steps 20 --warmup 5 --comm $comm ${BENCHARGS:-} > gpurun_out/${TAG}_bench_n${n}_${comm}.json 2> gpurun_out/${TAG}_bench_n${n}_${comm}.err
             python - <<PY
 import json
 try:
