@@ -306,7 +306,8 @@ PLS_API int pls_comm_p2p_init(pls_context* ctx, int num_ranks, int rank, const v
 PLS_API int pls_comm_destroy(pls_context* ctx);
 /* Sharding threshold: a frame's correspondences are split over the ranks only if every rank gets at least this many work
  * items (queries of the kd map / pixels of the projective map); below it every rank runs the whole frame itself and no
- * exchange takes place (identical inputs + deterministic kernels = identical poses).  Default 24576 (environment
+ * exchange takes place (identical inputs + deterministic kernels = identical poses).  Default 24576, a third of it for
+ * kd maps of 2 M points and more, where a query costs several times as much (environment
  * variable PLS_SHARD_MIN); a negative value restores the default.  Process-wide; every rank must set the same value. */
 PLS_API int pls_set_shard_min(int64_t work_items_per_rank);
 /* 1 if the last ICP of this context split its correspondences over the ranks, else 0. */

@@ -219,7 +219,10 @@ struct FrameInputSelect {
 
 bool icp_shards(pls_context* ctx, int64_t work) {
     const int size = comm_size(ctx);
-    const int64_t shard_min = g_shard_min_override >= 0 ? g_shard_min_override : shard_min_default();
+    int64_t shard_min = g_shard_min_override >= 0 ? g_shard_min_override : shard_min_default();
+    // a query against a multi-million-point kd map walks cold cell tables and misses L2: a third of the usual share
+    // already outweighs the exchange (BASELINE config 4: 131 k queries, 5 M points, still split at 8 ranks)
+    if (g_shard_min_override < 0 && ctx->cfg.local_map_type == PLS_MAP_KDTREE && ctx->kd.indexed >= 2000000) shard_min /= 3;
     return size > 1 && work / size >= shard_min;
 }
 

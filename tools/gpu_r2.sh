@@ -31,8 +31,8 @@ benchlong)
     tail -c 1500 gpurun_out/${TAG}_bench_default.json; tail -3 gpurun_out/${TAG}_bench_default.err ;;
 launches)
     timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches_cfg2.csv \
-        python bench.py --quick --steps 3 --warmup 24 > gpurun_out/${TAG}_bench_under_ncu.log 2>&1
-    python tools/summarize_launches.py gpurun_out/${TAG}_launches_cfg2.csv 3 > gpurun_out/${TAG}_launches_cfg2_summary.txt 2>&1
+        python bench.py --quick --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_under_ncu.log 2>&1
+    python tools/summarize_launches.py gpurun_out/${TAG}_launches_cfg2.csv 1 --last-frames 20 > gpurun_out/${TAG}_launches_cfg2_summary.txt 2>&1
     head -40 gpurun_out/${TAG}_launches_cfg2_summary.txt ;;
 ncukd)
     timeout 300 ncu --set full --clock-control none --import-source on -k regex:'kd_nn_warp_kernel|kd_normals_warp_kernel|kd_residual_kernel' \
@@ -118,6 +118,12 @@ mgpu)
     echo "== multi-GPU on $NG GPUs"
     timeout 900 python -m pytest tests/test_multi_gpu.py -q -m gpu --timeout 400 -rf -s -p no:cacheprovider > gpurun_out/${TAG}_pytest_mgpu.log 2>&1
     grep -E "mgpu_check|passed|failed|error" gpurun_out/${TAG}_pytest_mgpu.log | tail -12 ;;
+mcheck)
+    NG=$(python -c "import torch; print(torch.cuda.device_count())")
+    for spec in ${CHECKS:-"kdtree p2p stop" "projective p2p fixed"}; do
+        timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29547 \
+            tools/mgpu_check.py $spec 2>&1 | grep -E "mgpu_check|Error|error" | tail -3 | tee -a gpurun_out/${TAG}_mcheck_n${NG}.log
+    done ;;
 mbench)
     NG=$(python -c "import torch; print(torch.cuda.device_count())")
     for n in ${NS:-2}; do
