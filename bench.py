@@ -244,6 +244,16 @@ def b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def hold_clocks(ms=80.0):
+        """Keeps the GPU busy (L2-flush memsets, no step of the workload) right before a timed bracket: with the
+        driver's short runs (5 warm-up frames = 3 ms of GPU work after seconds of host-side set-up) the SM clock is
+        otherwise still ramping up inside the bracket."""
+        t0 = time.perf_counter()
+        while (time.perf_counter() - t0) * 1e3 < ms:
+            for _ in range(8):
+                flush_l2()
+            torch.cuda.synchronize(dev)
+
     def max_over_ranks(*vals):
         if world == 1:
             return vals
@@ -273,6 +283,7 @@ def b200_arm(args):
             timed = k > W_
             if k == W_ + 1:
                 ctx.call("pls_synchronize")
+                hold_clocks()
                 flush_l2()
                 barrier()
                 launches0 = ctx.launch_count()
@@ -333,6 +344,7 @@ def b200_arm(args):
         timed = k > W_
         if k == W_ + 1:
             gs_ctx.call("pls_synchronize")
+            hold_clocks()
             flush_l2()
             barrier()
             t_start = time.perf_counter()
@@ -379,6 +391,8 @@ def b200_arm(args):
         "steps": K_, "warmup": W_, "ms_per_step": 1e3 * t_dev / K_, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "height": H, "width": W, "voxel": VOXEL,
+                   "clock_hold": "80 ms of L2-flush memsets (no workload step) right before each timed bracket, so that the "
+                                 "SM clock is not still ramping up inside a 10 ms bracket",
                    "l2": "L2 flushed once before the timed bracket; every step streams a NEW 1.5 MB scan from HBM while the "
                          "~60 MB local map legitimately stays L2-resident across frames (production behaviour); "
                          "value_l2_flushed_every_step re-measures with a 256 MiB flush INSIDE the bracket before every frame",
@@ -393,7 +407,7 @@ def b200_arm(args):
                 "ms_per_step": 1e3 * t_e / K_},
         "gpu_launches": int(launches),
         "clocks": clock_info,
-        "roofline": {"bound": "hbm", "kernel": "kd_nn_verify_kernel + kd_nn_group_kernel + kd_normals_group_kernel<2> + kd_residual_kernel: "
+        "roofline": {"bound": "hbm", "kernel": "kd_nn_verify_kernel + kd_nn_warp_kernel + kd_normals_warp_kernel + kd_residual_kernel: "
                                "one executed ICP iteration (exact 1-NN, lazy 10-NN normals, point-to-plane reduction + fused solve)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source":
