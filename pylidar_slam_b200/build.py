@@ -12,6 +12,7 @@ STAMP = os.path.join(HERE, ".libplslam_b200.stamp")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
+FLAGS += os.environ.get("PLS_EXTRA_NVCC_FLAGS", "").split()   # development A/B builds (e.g. -DKD_NORMALS_BLOCKS=4)
 
 
 def _sources():

@@ -78,6 +78,34 @@ def test_a1_device_tensor_roundtrip(b200, orc):
     np.testing.assert_array_equal(s.cpu().numpy(), s_ref)
 
 
+def test_cuda_tensor_inputs_wait_for_the_torch_stream_that_produces_them(b200, orc):
+    """A CUDA tensor handed to the library may still be in the making on PyTorch's current stream (a slice copy, a
+    dtype conversion, a network's forward pass).  The library runs on its own non-blocking stream, so it has to order
+    itself after that stream (pls_wait_stream, issued by _lib.Context.call): here the input buffer is filled by a copy
+    queued BEHIND ~30 ms of matrix products; read too early it is still all zeros."""
+    rs = np.random.RandomState(11)
+    pts = (rs.randn(120000, 3) * 12).astype(np.float32)
+    wide = np.concatenate([pts, rs.randn(120000, 2).astype(np.float32)], axis=1)        # [n,5]: the cloud is a strided slice
+    src = torch.from_numpy(wide).cuda()
+    busy = torch.randn(4096, 4096, device="cuda")
+    s_ref, i_ref = orc.grid_sample(pts, 0.4)
+    for attempt in range(3):
+        buf = torch.zeros(120000, 3, device="cuda")
+        torch.cuda.synchronize()
+        for _ in range(24):
+            busy = (busy @ busy).clamp_(-1.0, 1.0)                                       # keeps PyTorch's stream busy
+        buf.copy_(src[:, :3])                                                            # ... and only then fills the input
+        s, i = b200.grid_sample(buf, 0.4)                                                # no synchronisation in between
+        np.testing.assert_array_equal(i.cpu().numpy(), i_ref)
+        np.testing.assert_array_equal(s.cpu().numpy(), s_ref)
+        # the same through a conversion the mirror itself enqueues (float64 -> float32 .contiguous() of a strided view)
+        for _ in range(24):
+            busy = (busy @ busy).clamp_(-1.0, 1.0)
+        view64 = src.double()[:, :3]
+        s2, i2 = b200.grid_sample(view64.float(), 0.4)
+        np.testing.assert_array_equal(i2.cpu().numpy(), i_ref)
+
+
 # --------------------------------------------------------------------------------------------- a2/a3
 def _pixel_mismatch(a, b):
     return float(np.mean(np.any(a != b, axis=0)))
