@@ -119,6 +119,9 @@ PLS_API int pls_wait_stream(pls_context* ctx, void* other_stream);
  * 73856093 x + 19349669 y + 83492791 z.  is_f64 selects float64 input points. */
 PLS_API int pls_voxel_hash(pls_context* ctx, const void* xyz, int is_f64, int64_t n, double voxel,
                    int64_t* coords_out /* [n,3] or NULL */, int64_t* hashes_out /* [n] */);
+/* voxelise with one voxel length per axis (pointcloud.py:55-79: voxel_x, voxel_y, voxel_z). */
+PLS_API int pls_voxel_hash_xyz(pls_context* ctx, const void* xyz, int is_f64, int64_t n, double voxel_x, double voxel_y,
+                       double voxel_z, int64_t* coords_out /* [n,3] or NULL */, int64_t* hashes_out /* [n] or NULL */);
 /* grid_sample / GridSample.filter (pointcloud.py:170-195, preprocessing.py:213-226):
  * one point per distinct hash (its first occurrence), ordered by ascending hash.
  * out_xyz [n,3] (same dtype as the input), out_idx [n] int64; *out_count = S. */
@@ -154,6 +157,10 @@ PLS_API int pls_project_pixels(pls_context* ctx, const float* xyz, int64_t n, in
 PLS_API int pls_build_projection_map(pls_context* ctx, const float* xyz, const float* channels,
                              int batch, int64_t n, int num_channels, int height, int width,
                              float up_fov_deg, float down_fov_deg, float* out);
+/* The same with the reference's `default_value` (projection.py:333,378-391): pixels no point lands on hold it. */
+PLS_API int pls_build_projection_map_filled(pls_context* ctx, const float* xyz, const float* channels,
+                                    int batch, int64_t n, int num_channels, int height, int width,
+                                    float up_fov_deg, float down_fov_deg, float default_value, float* out);
 
 /* ---- a4: box-filter normal map  (slam/common/geometry.py:240-295) ----------------- */
 PLS_API int pls_normal_map(pls_context* ctx, const float* vertex_map /* [B,3,H,W] */, int batch,

@@ -37,6 +37,7 @@ _SIGNATURES = {
     "pls_synchronize": [_P],
     "pls_wait_stream": [_P, _P],
     "pls_voxel_hash": [_P, _P, _I, _L, _D, _P, _P],
+    "pls_voxel_hash_xyz": [_P, _P, _I, _L, _D, _D, _D, _P, _P],
     "pls_grid_sample": [_P, _P, _I, _L, _D, _P, _P, C.POINTER(_L)],
     "pls_grid_sample_staged": [_P, _P, _I, _L, _D, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_L)],
     "pls_host_fingerprint": [_P, _L, C.POINTER(C.c_uint64)],
@@ -44,6 +45,7 @@ _SIGNATURES = {
     "pls_pinned_free": [_P],
     "pls_project_pixels": [_P, _P, _L, _I, _I, _F, _F, _P],
     "pls_build_projection_map": [_P, _P, _P, _I, _L, _I, _I, _I, _F, _F, _P],
+    "pls_build_projection_map_filled": [_P, _P, _P, _I, _L, _I, _I, _I, _F, _F, _F, _P],
     "pls_normal_map": [_P, _P, _I, _I, _I, _I, _P],
     "pls_compute_neighbors": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
     "pls_build_pose_matrix": [_P, _P, _I, _P],

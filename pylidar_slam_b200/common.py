@@ -60,9 +60,10 @@ def _empty_like_kind(x, shape, dtype=np.float32):
 # slam/common/pointcloud.py
 # ------------------------------------------------------------------------------------------
 def voxelise(pointcloud, voxel_x: float = 0.2, voxel_y: float = -1.0, voxel_z: float = -1.0, ctx=None):
-    """int64 voxel coordinates `(n, 3)` (pointcloud.py:54-79).  Only cubic voxels are on the hot path."""
+    """int64 voxel coordinates `(n, 3)` (pointcloud.py:54-79); voxel_y / voxel_z default to voxel_x."""
     ctx = ctx or default_context()
-    assert_debug(voxel_y in (-1.0, voxel_x) and voxel_z in (-1.0, voxel_x), "cubic voxels only")
+    voxel_y = voxel_x if voxel_y == -1.0 else voxel_y
+    voxel_z = voxel_x if voxel_z == -1.0 else voxel_z
     check_tensor(pointcloud, [-1, 3])
     is64 = (pointcloud.dtype == np.float64) if isinstance(pointcloud, np.ndarray) else (pointcloud.dtype == torch.float64)
     pc = np.ascontiguousarray(pointcloud) if isinstance(pointcloud, np.ndarray) else pointcloud.contiguous()
@@ -71,7 +72,8 @@ def voxelise(pointcloud, voxel_x: float = 0.2, voxel_y: float = -1.0, voxel_z: f
     n = pc.shape[0]
     coords = _empty_like_kind(pc, (n, 3), np.int64)
     hashes = _empty_like_kind(pc, (n,), np.int64)
-    ctx.call("pls_voxel_hash", _lib.ptr(pc), int(is64), n, float(voxel_x), _lib.ptr(coords), _lib.ptr(hashes))
+    ctx.call("pls_voxel_hash_xyz", _lib.ptr(pc), int(is64), n, float(voxel_x), float(voxel_y), float(voxel_z),
+             _lib.ptr(coords), _lib.ptr(hashes))
     return coords
 
 
@@ -215,9 +217,12 @@ class SphericalProjector:
     """SphericalProjector (projection.py:426-508): spherical range-image projection."""
 
     def __init__(self, height: Optional[int] = None, width: Optional[int] = None, num_channels: Optional[int] = None,
-                 up_fov: Optional[float] = None, down_fov: Optional[float] = None, ctx=None, **kwargs):
+                 up_fov: Optional[float] = None, down_fov: Optional[float] = None, conversion=None, ctx=None, **kwargs):
         self.height, self.width, self.num_channels = height, width, num_channels
         self.up_fov, self.down_fov = up_fov, down_fov
+        # the image channels of build_projection_map when no `transform` is passed: the reference's member transform,
+        # `xyz_conversion` by default (projection.py:76-95,439-446) -- the first three channels of the cloud
+        self.conversion = conversion
         self._ctx = ctx
 
     @property
@@ -238,17 +243,17 @@ class SphericalProjector:
     def build_projection_map(self, pointcloud, default_value: float = 0.0, height=None, width=None,
                              transform=None, **kwargs):
         """[B,N,C>=3] -> [B,C_dest,H,W]; the closest point per pixel survives (projection.py:331-418)."""
-        assert_debug(default_value == 0.0, "only default_value == 0 is on the hot path")
         check_tensor(pointcloud, [-1, -1, -1])
         H, W = height or self.height, width or self.width
         pc = _as_f32(pointcloud)
         B, N, _ = pc.shape
-        channels = _as_f32(transform(pc)) if transform is not None else (pc if pc.shape[2] != 3 else None)
+        transform = self.conversion if transform is None else transform      # Projector.swap (projection.py:322-329,368)
+        channels = _as_f32(transform(pc)) if transform is not None else None  # None: xyz_conversion, the xyz are scattered
         xyz = _as_f32(pc[:, :, :3])
         Cd = 3 if channels is None else channels.shape[2]
         out = _empty_like_kind(xyz, (B, Cd, H, W))
-        self.ctx.call("pls_build_projection_map", _lib.ptr(xyz), _lib.ptr(channels), B, N, Cd, H, W,
-                      float(self.up_fov), float(self.down_fov), _lib.ptr(out))
+        self.ctx.call("pls_build_projection_map_filled", _lib.ptr(xyz), _lib.ptr(channels), B, N, Cd, H, W,
+                      float(self.up_fov), float(self.down_fov), float(default_value), _lib.ptr(out))
         return out
 
 

@@ -26,12 +26,14 @@ template <typename T>
 __global__ void voxel_hash_kernel(const T* __restrict__ xyz, int64_t n, double voxel, long long* __restrict__ coords,
                                   long long* __restrict__ hashes, uint64_t* __restrict__ keys,
                                   uint32_t* __restrict__ vals, uint32_t* __restrict__ overflow = nullptr,
-                                  uint32_t stamp = 0) {
+                                  uint32_t stamp = 0, double voxel_y = -1.0, double voxel_z = -1.0) {
+    if (voxel_y < 0.0) voxel_y = voxel;   // voxelise's defaults (pointcloud.py:66-69)
+    if (voxel_z < 0.0) voxel_z = voxel;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double x = (double)xyz[3 * i], y = (double)xyz[3 * i + 1], z = (double)xyz[3 * i + 2];
         long long cx = __double2ll_rn(x / voxel);
-        long long cy = __double2ll_rn(y / voxel);
-        long long cz = __double2ll_rn(z / voxel);
+        long long cy = __double2ll_rn(y / voxel_y);
+        long long cz = __double2ll_rn(z / voxel_z);
         long long h = HX * cx + HY * cy + HZ * cz;
         if (coords) {
             coords[3 * i] = cx;
@@ -266,25 +268,32 @@ using namespace pls;
 
 extern "C" {
 
-int pls_voxel_hash(pls_context* ctx, const void* xyz, int is_f64, int64_t n, double voxel, int64_t* coords_out,
-                   int64_t* hashes_out) {
+int pls_voxel_hash_xyz(pls_context* ctx, const void* xyz, int is_f64, int64_t n, double voxel_x, double voxel_y, double voxel_z,
+                       int64_t* coords_out, int64_t* hashes_out) {
     PLS_API_BEGIN(ctx)
-    PLS_REQUIRE(xyz && n > 0 && voxel > 0.0, "pls_voxel_hash: need [n,3] points and voxel > 0");
+    PLS_REQUIRE(xyz && n > 0 && voxel_x > 0.0 && voxel_y > 0.0 && voxel_z > 0.0, "pls_voxel_hash: need [n,3] points and voxel sizes > 0");
     const size_t esz = is_f64 ? sizeof(double) : sizeof(float);
     const void* d_xyz = to_device(ctx, xyz, (size_t)n * 3 * esz, ctx->stage_in[0]);
     OutArg oc = out_arg(ctx, coords_out, (size_t)n * 3 * sizeof(int64_t), ctx->stage_out[0]);
     OutArg oh = out_arg(ctx, hashes_out, (size_t)n * sizeof(int64_t), ctx->stage_out[1]);
     if (is_f64)
-        voxel_hash_kernel<double><<<grid_for(n), 256, 0, ctx->stream>>>((const double*)d_xyz, n, voxel, (long long*)oc.dev,
-                                                                       (long long*)oh.dev, nullptr, nullptr);
+        voxel_hash_kernel<double><<<grid_for(n), 256, 0, ctx->stream>>>((const double*)d_xyz, n, voxel_x, (long long*)oc.dev,
+                                                                       (long long*)oh.dev, nullptr, nullptr, nullptr, 0, voxel_y,
+                                                                       voxel_z);
     else
-        voxel_hash_kernel<float><<<grid_for(n), 256, 0, ctx->stream>>>((const float*)d_xyz, n, voxel, (long long*)oc.dev,
-                                                                      (long long*)oh.dev, nullptr, nullptr);
+        voxel_hash_kernel<float><<<grid_for(n), 256, 0, ctx->stream>>>((const float*)d_xyz, n, voxel_x, (long long*)oc.dev,
+                                                                      (long long*)oh.dev, nullptr, nullptr, nullptr, 0, voxel_y,
+                                                                      voxel_z);
     PLS_CHECK_LAUNCH();
     finish_out(ctx, oc);
     finish_out(ctx, oh);
     PLS_CUDA(cudaStreamSynchronize(ctx->stream));
     PLS_API_END(ctx)
+}
+
+int pls_voxel_hash(pls_context* ctx, const void* xyz, int is_f64, int64_t n, double voxel, int64_t* coords_out,
+                   int64_t* hashes_out) {
+    return pls_voxel_hash_xyz(ctx, xyz, is_f64, n, voxel, voxel, voxel, coords_out, hashes_out);
 }
 
 int pls_grid_sample(pls_context* ctx, const void* xyz, int is_f64, int64_t n, double voxel, void* out_xyz,

@@ -322,7 +322,7 @@ __device__ __forceinline__ float ordered_to_float(int i) {
 // ---- module entry points used across translation units -----------------------------------------
 // projection.cu
 void launch_projection(pls_context* ctx, const float* xyz, const float* channels, int batch, int64_t n,
-                       int C, int H, int W, float up, float down, float* out, unsigned long long* zbuf);
+                       int C, int H, int W, float up, float down, float* out, unsigned long long* zbuf, float fill = 0.f);
 // float64 cloud [n,3] -> float32 vertex map [3,H,W]: pixel math, range comparison and validity in float64, values
 // rounded to float32 at the end (what the reference does with a float64 input, icp_odometry.py:331-352)
 void launch_projection_f64(pls_context* ctx, const double* xyz, int64_t n, int H, int W, float up, float down, float* out,

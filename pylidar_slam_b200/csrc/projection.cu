@@ -54,14 +54,14 @@ __global__ void zbuf_points_kernel(const float* __restrict__ xyz, int64_t n, con
 }
 
 __global__ void resolve_kernel(const unsigned long long* __restrict__ zbuf, const float* __restrict__ values,
-                               int batch, int64_t n, int C, int64_t hw, float* __restrict__ out) {
+                               int batch, int64_t n, int C, int64_t hw, float fill, float* __restrict__ out) {
     const int64_t total = (int64_t)batch * hw;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
         int64_t b = g / hw, pix = g - b * hw;
         unsigned long long key = zbuf[g];
         float* o = out + (size_t)b * C * hw + pix;
         if (key == ~0ull) {
-            for (int c = 0; c < C; ++c) o[(size_t)c * hw] = 0.f;
+            for (int c = 0; c < C; ++c) o[(size_t)c * hw] = fill;  // projection.py:378-391: the image starts as default_value
         } else {
             const float* v = values + ((size_t)b * n + (uint32_t)(key & 0xffffffffull)) * C;
             for (int c = 0; c < C; ++c) o[(size_t)c * hw] = v[c];
@@ -139,7 +139,7 @@ inline int grid_for(int64_t n, int threads = 256) {
 }  // namespace
 
 void launch_projection(pls_context* ctx, const float* xyz, const float* channels, int batch, int64_t n, int C, int H,
-                       int W, float up, float down, float* out, unsigned long long* zbuf) {
+                       int W, float up, float down, float* out, unsigned long long* zbuf, float fill) {
     cudaStream_t st = ctx->stream;
     const int64_t hw = (int64_t)H * W;
     PLS_REQUIRE(n < (1ll << 32), "projection: at most 2^32 points per cloud");
@@ -149,7 +149,7 @@ void launch_projection(pls_context* ctx, const float* xyz, const float* channels
         zbuf_kernel<<<grid_for((int64_t)batch * n), 256, 0, st>>>(xyz, batch, n, pc, zbuf);
         PLS_CHECK_LAUNCH();
     }
-    resolve_kernel<<<grid_for((int64_t)batch * hw), 256, 0, st>>>(zbuf, channels ? channels : xyz, batch, n, C, hw, out);
+    resolve_kernel<<<grid_for((int64_t)batch * hw), 256, 0, st>>>(zbuf, channels ? channels : xyz, batch, n, C, hw, fill, out);
     PLS_CHECK_LAUNCH();
 }
 
@@ -220,9 +220,9 @@ int pls_project_pixels(pls_context* ctx, const float* xyz, int64_t n, int height
     PLS_API_END(ctx)
 }
 
-int pls_build_projection_map(pls_context* ctx, const float* xyz, const float* channels, int batch, int64_t n,
-                             int num_channels, int height, int width, float up_fov_deg, float down_fov_deg,
-                             float* out) {
+static int build_projection_map_impl(pls_context* ctx, const float* xyz, const float* channels, int batch, int64_t n,
+                                     int num_channels, int height, int width, float up_fov_deg, float down_fov_deg,
+                                     float default_value, float* out) {
     PLS_API_BEGIN(ctx)
     PLS_REQUIRE(xyz && out && batch > 0 && n >= 0 && height > 0 && width > 0, "pls_build_projection_map: bad arguments");
     const int C = channels ? num_channels : 3;
@@ -233,10 +233,24 @@ int pls_build_projection_map(pls_context* ctx, const float* xyz, const float* ch
     OutArg o = out_arg(ctx, out, (size_t)batch * C * hw * sizeof(float), ctx->stage_out[0]);
     ctx->tmp[3].reserve((size_t)batch * hw * sizeof(unsigned long long), ctx->stream);
     launch_projection(ctx, d_xyz, d_ch, batch, n, C, height, width, up_fov_deg, down_fov_deg, (float*)o.dev,
-                      ctx->tmp[3].as<unsigned long long>());
+                      ctx->tmp[3].as<unsigned long long>(), default_value);
     finish_out(ctx, o);
     PLS_CUDA(cudaStreamSynchronize(ctx->stream));
     PLS_API_END(ctx)
+}
+
+int pls_build_projection_map(pls_context* ctx, const float* xyz, const float* channels, int batch, int64_t n,
+                             int num_channels, int height, int width, float up_fov_deg, float down_fov_deg,
+                             float* out) {
+    return build_projection_map_impl(ctx, xyz, channels, batch, n, num_channels, height, width, up_fov_deg, down_fov_deg, 0.f,
+                                     out);
+}
+
+int pls_build_projection_map_filled(pls_context* ctx, const float* xyz, const float* channels, int batch, int64_t n,
+                                    int num_channels, int height, int width, float up_fov_deg, float down_fov_deg,
+                                    float default_value, float* out) {
+    return build_projection_map_impl(ctx, xyz, channels, batch, n, num_channels, height, width, up_fov_deg, down_fov_deg,
+                                     default_value, out);
 }
 
 }  // extern "C"

@@ -255,6 +255,16 @@ class GaussNewtonPointToPlaneConfig(RigidAlignmentConfig):
     gauss_newton_config: Dict[str, Any] = field(default_factory=lambda: dict(max_iters=1))
 
 
+def _reject_mask(mask, n):
+    """`mask` of RigidAlignment.align ([1,n,1], alignment.py:96-121,158-182).  The reference cannot apply one: its cost
+    functions multiply the [b,n,6] Jacobian IN PLACE by `mask.unsqueeze(1)` ([b,1,n,1]; optimization.py:391-392,500-501),
+    which fails to broadcast -- every call with a mask ends in a RuntimeError.  Same error type here, after the
+    reference's own shape check."""
+    check_tensor(mask, [1, n, 1])
+    raise RuntimeError(f"output with shape [1, {n}, 6] doesn't match the broadcast shape [1, 1, {n}, 6] "
+                       f"(the reference's alignments cannot apply a mask: optimization.py:391-392, 500-501)")
+
+
 def _gn_settings(gn_cfg) -> dict:
     """GaussNewton(**gauss_newton_config) defaults (optimization.py:287-294, :61-208)."""
     d = dict(_cfg_to_dict(gn_cfg))
@@ -288,9 +298,10 @@ class GaussNewtonPointToPlaneAlignment(RigidAlignment):
 
     def align(self, ref_points, tgt_points, ref_normals=None, initial_estimate=None, mask=None, **kwargs):
         assert_debug(ref_normals is not None, "The argument 'ref_normals' is required for a point to plane alignemnt")
-        assert_debug(mask is None, "masks are not on the hot path")
         check_tensor(tgt_points, [1, -1, 3])
         n = tgt_points.shape[1]
+        if mask is not None:
+            _reject_mask(mask, n)
         check_tensor(ref_points, [1, n, 3])
         check_tensor(ref_normals, [1, n, 3])
         is_np = isinstance(tgt_points, np.ndarray)
@@ -345,10 +356,11 @@ class GaussNewtonPointToPointAlignment(RigidAlignment):
         assert_debug(not self.config.initialize_with_svd,
                      "initialize_with_svd fails inside the reference itself (registration.py:58-59 builds a [b,16,16] "
                      "tensor); use pylidar_slam_b200.common.weighted_procrustes and pass it as initial_estimate")
-        assert_debug(mask is None, "masks are not on the hot path")
         check_tensor(tgt_points, [1, -1, 3])
         n = tgt_points.shape[1]
         check_tensor(ref_points, [1, n, 3])
+        if mask is not None:
+            _reject_mask(mask, n)
         is_np = isinstance(tgt_points, np.ndarray)
         is64 = (tgt_points.dtype == (np.float64 if is_np else torch.float64))
         dt_np, dt_t = (np.float64, torch.float64) if is64 else (np.float32, torch.float32)

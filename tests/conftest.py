@@ -59,6 +59,11 @@ def golden_loss():
     return np.load(os.path.join(GOLDEN, "p2plane_loss.npz"))
 
 
+@pytest.fixture(scope="session")
+def golden_misc():
+    return np.load(os.path.join(GOLDEN, "misc.npz"))
+
+
 def chain_timestamps(points, seed):
     """Per-point acquisition times of the synthetic spinning LiDAR (same formula as tests/golden/make_golden_*.py)."""
     az = np.arctan2(points[:, 1].astype(np.float64), points[:, 0].astype(np.float64))

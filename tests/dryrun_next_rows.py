@@ -77,6 +77,14 @@ class FakeContext:
         if hashes:
             arr(hashes, (n,), np.int64)[:] = orc.voxel_hashes(c)
 
+    def pls_voxel_hash_xyz(self, xyz, is64, n, vx, vy, vz, coords, hashes):
+        pts = arr(xyz, (n, 3), np.float64 if is64 else np.float32).astype(np.float64)
+        c = np.rint(pts / np.array([vx, vy, vz])).astype(np.int64)       # round half to even, like np.round_ (pointcloud.py:73-75)
+        if coords:
+            arr(coords, (n, 3), np.int64)[:] = c
+        if hashes:
+            arr(hashes, (n,), np.int64)[:] = orc.voxel_hashes(c)
+
     def pls_grid_sample(self, xyz, is64, n, voxel, out, idx, count):
         dt = np.float64 if is64 else np.float32
         s, i = orc.grid_sample(arr(xyz, (n, 3), dt), voxel)

@@ -122,3 +122,24 @@ def test_hydra_config_node_and_yaml(ref):
         projector=ref.projection.SphericalProjector(height=H, width=W, up_fov=3.0, down_fov=-24.0),
         pose=ref.pose.Pose("euler"), device=torch.device("cpu"), viz_num_pointclouds=1)
     assert algo.config.local_map.type == "kdtree_local_map" and algo.config.max_num_alignments == 100
+
+
+def test_reference_alignments_cannot_apply_a_mask(ref):
+    """Why pylidar_slam_b200's alignments answer a `mask` with a RuntimeError: the reference does (its cost functions
+    multiply the [b,n,6] Jacobian in place by mask.unsqueeze(1), optimization.py:391-392,500-501)."""
+    import slam.odometry.alignment as alignment
+    import slam.common.pose as pose
+    n = 128
+    rs = np.random.RandomState(3)
+    pts = torch.from_numpy(rs.randn(1, n, 3).astype(np.float32))
+    nrm = torch.nn.functional.normalize(torch.from_numpy(rs.randn(1, n, 3).astype(np.float32)), dim=2)
+    mask = torch.ones(1, n, 1)
+    gn = dict(scheme="geman_mcclure", sigma=0.3, max_iters=1)
+    plane = alignment.GaussNewtonPointToPlaneAlignment(alignment.GaussNewtonPointToPlaneConfig(gauss_newton_config=gn),
+                                                       pose=pose.Pose("euler"))
+    point = alignment.GaussNewtonPointToPointAlignment(alignment.GNPointToPointConfig(gauss_newton_config=gn),
+                                                       pose=pose.Pose("euler"))
+    with pytest.raises(RuntimeError, match="broadcast"):
+        plane.align(pts, pts + 0.01, nrm, mask=mask)
+    with pytest.raises(RuntimeError, match="broadcast"):
+        point.align(pts, pts + 0.01, mask=mask)

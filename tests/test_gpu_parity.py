@@ -106,6 +106,15 @@ def test_cuda_tensor_inputs_wait_for_the_torch_stream_that_produces_them(b200, o
         np.testing.assert_array_equal(i2.cpu().numpy(), i_ref)
 
 
+def test_a1_voxelise_with_one_voxel_length_per_axis(b200, golden_misc):
+    """voxelise(pointcloud, voxel_x, voxel_y, voxel_z) (pointcloud.py:55-79): bit-exact against the reference."""
+    g = golden_misc
+    vx, vy, vz = (float(v) for v in g["vox_sizes"])
+    np.testing.assert_array_equal(b200.voxelise(g["vox_points"], vx, vy, vz), g["vox_coords"])
+    np.testing.assert_array_equal(b200.voxelise(torch.from_numpy(g["vox_points"]).cuda(), vx, vy, vz).cpu().numpy(), g["vox_coords"])
+    np.testing.assert_array_equal(b200.voxelise(g["vox_points"], vx), b200.voxelise(g["vox_points"], vx, vx, vx))
+
+
 # --------------------------------------------------------------------------------------------- a2/a3
 def _pixel_mismatch(a, b):
     return float(np.mean(np.any(a != b, axis=0)))
@@ -121,6 +130,21 @@ def test_a3_projection_golden(b200, golden_helpers):
     np.testing.assert_allclose(pix[ok], g["a3_pixels"][ok], atol=2e-3)
     vmap = proj.build_projection_map(pts)[0]
     assert _pixel_mismatch(vmap, g["a3_vmap"]) <= 2e-3   # points within an ulp of a .5 boundary
+
+
+def test_a3_projection_default_value_and_default_channels(b200, golden_misc):
+    """Projector.build_projection_map(default_value=...) (projection.py:333,378-391): pixels no point lands on hold the
+    value; with no `transform` a [B,N,4] cloud yields the three xyz channels (the projector's xyz_conversion)."""
+    g = golden_misc
+    proj = b200.SphericalProjector(height=16, width=256, up_fov=3.0, down_fov=-24.0)
+    out = proj.build_projection_map(g["proj_cloud"][None], default_value=float(g["proj_default"]))[0]
+    assert out.shape == g["proj_map"].shape == (3, 16, 256)
+    empty = np.all(g["proj_map"] == g["proj_default"], axis=0)
+    assert empty.any() and not empty.all()
+    assert _pixel_mismatch(out, g["proj_map"]) <= 2e-3          # points within an ulp of a .5 pixel boundary, as in a3
+    np.testing.assert_array_equal(np.all(out == g["proj_default"], axis=0)[empty], True)
+    four = proj.build_projection_map(g["proj_cloud"][None], default_value=2.0, transform=lambda x: x)[0]
+    assert four.shape == (4, 16, 256) and np.all(four[:, empty] == 2.0)
 
 
 @pytest.mark.parametrize("H,W", [(64, 2048), (128, 4096)])

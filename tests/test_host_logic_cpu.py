@@ -241,3 +241,22 @@ def test_pinned_pool_reuses_a_buffer_only_when_nothing_refers_to_it(monkeypatch)
     del held
     bigger = take(8192)                                      # limit reached: a free smaller buffer makes room
     assert bigger is not None and len(_lib.PinnedPool.buffers) == 3 and len(alloc.freed) == 1
+
+
+def test_voxelise_with_three_voxel_lengths_and_alignment_mask_error(b200, golden_misc):
+    """voxelise(voxel_x, voxel_y, voxel_z) reaches pls_voxel_hash_xyz with the three lengths; a `mask` handed to either
+    alignment ends in the reference's own error type (tests/test_dropin_reference.py shows the reference raising it)."""
+    g = golden_misc
+    vx, vy, vz = (float(v) for v in g["vox_sizes"])
+    np.testing.assert_array_equal(b200.voxelise(g["vox_points"], vx, vy, vz, ctx=dry.FakeContext()), g["vox_coords"])
+    n = 64
+    pts = np.random.RandomState(0).randn(1, n, 3).astype(np.float32)
+    mask = np.ones((1, n, 1), np.float32)
+    plane = b200.GaussNewtonPointToPlaneAlignment(b200.GaussNewtonPointToPlaneConfig(), ctx=dry.FakeContext())
+    point = b200.GaussNewtonPointToPointAlignment(b200.GNPointToPointConfig(), ctx=dry.FakeContext())
+    with pytest.raises(RuntimeError, match="broadcast"):
+        plane.align(pts, pts, pts, mask=mask)
+    with pytest.raises(RuntimeError, match="broadcast"):
+        point.align(pts, pts, mask=torch.from_numpy(mask))
+    with pytest.raises(AssertionError):                       # the reference's shape check comes first
+        plane.align(pts, pts, pts, mask=mask[:, :, 0])
