@@ -67,6 +67,18 @@ def committed_traffic(name):
         return None, None
 
 
+def committed_limiter():
+    """What bounds the kd correspondence family, from the committed ncu --set full capture (profiles/r2_kd_limiter.json):
+    issue-slot utilisation, instruction counts, stalls of the three kernels of a first ICP iteration."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r2_kd_limiter.json")))
+        return {"verdict": d["verdict"], "source": d["source"],
+                **{k: {"issue_active_pct": v["issue_active_pct"], "warp_instructions": v["warp_instructions"],
+                       "long_scoreboard_stall_per_issue": v["long_scoreboard_stall_per_issue"]} for k, v in d["kernels"].items()}}
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (rank 0 only)."""
 
@@ -420,6 +432,7 @@ def b200_arm(args):
                      "lower_bound": {"achieved": lower, "frac": lower / peak if peak else None,
                                      "note": "44 B per query + 16 B per touched map point: the ~60 MB map is L2-resident, so this "
                                              "latency-bound family cannot approach the HBM roofline at 32 k queries per frame"},
+                     "limiter": committed_limiter(),
                      "share_of_step": (nn_ms / K_) / frame_ms},
         "kernels": {"index_build_ms_per_frame": prof_idx[0] / K_, "grid_sample_ms_per_frame": prof_gs[0] / K_,
                     "correspondence_ms_per_frame": nn_ms / K_},
