@@ -269,11 +269,21 @@ int pls_create(const pls_config* cfg, pls_context** out) {
         if (cfg->stream) {
             ctx->stream = (cudaStream_t)cfg->stream;
         } else {
-            PLS_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+            // the frame's own work (subsample, ICP) is what the caller waits for: it outranks the local-map update that
+            // runs beside it on the second stream (PLS_STREAM_PRIORITY=0: both at the default priority, for A/B runs)
+            static const bool prio = !(getenv("PLS_STREAM_PRIORITY") && atoi(getenv("PLS_STREAM_PRIORITY")) == 0);
+            int least = 0, greatest = 0;
+            PLS_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            PLS_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio ? greatest : 0));
             ctx->own_stream = true;
         }
         ctx->stream_main = ctx->stream;
-        PLS_CUDA(cudaStreamCreateWithFlags(&ctx->stream_map, cudaStreamNonBlocking));
+        {
+            static const bool prio = !(getenv("PLS_STREAM_PRIORITY") && atoi(getenv("PLS_STREAM_PRIORITY")) == 0);
+            int least = 0, greatest = 0;
+            PLS_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            PLS_CUDA(cudaStreamCreateWithPriority(&ctx->stream_map, cudaStreamNonBlocking, prio ? least : 0));
+        }
         PLS_CUDA(cudaEventCreateWithFlags(&ctx->ev_map_done, cudaEventDisableTiming));
         ctx->pinned.reserve(kScalarOffset + 256);  // FrameResult, then the host copy of the u32 scalars
         ctx->scalars.reserve(sizeof(FrameResult) + 4096, ctx->stream);

@@ -59,13 +59,10 @@ __global__ void head_flags_kernel(const uint64_t* __restrict__ keys, int64_t n, 
         flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
 }
 
-// host_xyz / host_idx (nullable): a second copy of the outputs written straight into mapped pinned host memory --
-// the samples cross PCIe while the kernel runs and the host caller needs no separate device->host copy.
 template <typename T>
 __global__ void gather_samples_kernel(const T* __restrict__ xyz, const uint32_t* __restrict__ vals,
                                       const uint8_t* __restrict__ flags, const uint32_t* __restrict__ pos, int64_t n,
-                                      T* __restrict__ out_xyz, long long* __restrict__ out_idx,
-                                      T* __restrict__ host_xyz, long long* __restrict__ host_idx) {
+                                      T* __restrict__ out_xyz, long long* __restrict__ out_idx) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         if (!flags[i]) continue;
         uint32_t src = vals[i];
@@ -75,12 +72,29 @@ __global__ void gather_samples_kernel(const T* __restrict__ xyz, const uint32_t*
         out_xyz[3 * (size_t)dst] = x;
         out_xyz[3 * (size_t)dst + 1] = y;
         out_xyz[3 * (size_t)dst + 2] = z;
-        if (host_xyz) {
-            host_xyz[3 * (size_t)dst] = x;
-            host_xyz[3 * (size_t)dst + 1] = y;
-            host_xyz[3 * (size_t)dst + 2] = z;
-        }
-        if (host_idx) host_idx[dst] = (long long)src;
+    }
+}
+
+// The host copy of a subsample: `count` (a device scalar -- the host does not know it yet) rows of two device arrays
+// into mapped pinned host memory with 16-byte stores, a warp writing 512 contiguous bytes per instruction.  (Letting
+// the selection kernel itself write its 4- and 8-byte results across PCIe made that kernel 90 us slower; a DMA copy
+// would need the count on the host first, i.e. a second round trip.)
+__global__ void __launch_bounds__(256)
+copy_counted_to_host_kernel(const unsigned char* __restrict__ src_a, unsigned char* __restrict__ dst_a, size_t elem_a,
+                            const unsigned char* __restrict__ src_b, unsigned char* __restrict__ dst_b, size_t elem_b,
+                            const uint32_t* __restrict__ count_dev) {
+    const size_t na = (size_t)*count_dev * elem_a, nb = (size_t)*count_dev * elem_b;
+    const size_t va = na / 16, vb = nb / 16;
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = gtid; i < va + vb; i += stride) {
+        if (i < va) reinterpret_cast<uint4*>(dst_a)[i] = reinterpret_cast<const uint4*>(src_a)[i];
+        else reinterpret_cast<uint4*>(dst_b)[i - va] = reinterpret_cast<const uint4*>(src_b)[i - va];
+    }
+    if (gtid < 16) {
+        size_t o = va * 16 + gtid;
+        if (o < na) dst_a[o] = src_a[o];
+        o = vb * 16 + gtid;
+        if (o < nb) dst_b[o] = src_b[o];
     }
 }
 
@@ -93,8 +107,6 @@ struct GridSampleSelect {
     const T* xyz;
     T* out_xyz;
     long long* out_idx;
-    T* host_xyz;
-    long long* host_idx;
     struct State {};
     __device__ __forceinline__ uint32_t flags(int64_t i, State&) const { return (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u; }
     __device__ __forceinline__ void emit(int64_t i, int, uint32_t dst, const State&) const {
@@ -104,12 +116,6 @@ struct GridSampleSelect {
         out_xyz[3 * (size_t)dst] = x;
         out_xyz[3 * (size_t)dst + 1] = y;
         out_xyz[3 * (size_t)dst + 2] = z;
-        if (host_xyz) {
-            host_xyz[3 * (size_t)dst] = x;
-            host_xyz[3 * (size_t)dst + 1] = y;
-            host_xyz[3 * (size_t)dst + 2] = z;
-        }
-        if (host_idx) host_idx[dst] = (long long)src;
     }
 };
 
@@ -191,6 +197,19 @@ void grid_sample_device(pls_context* ctx, const T* xyz_dev, int64_t n, double vo
     ctx->gs_vals.reserve((size_t)n * sizeof(uint32_t), st);
     ctx->tmp[1].reserve((size_t)n, st);                    // head flags
     ctx->tmp[2].reserve((size_t)n * sizeof(uint32_t), st); // positions
+    if (host_xyz && host_idx && !out_idx_dev) {            // the host copy is made from device arrays: indices too
+        ctx->gs_out_idx.reserve((size_t)n * sizeof(long long), st);
+        out_idx_dev = ctx->gs_out_idx.as<long long>();
+    }
+    auto copy_to_host = [&]() {
+        if (!host_xyz || !host_idx) return;
+        const size_t bytes = (size_t)n * (3 * sizeof(T) + sizeof(long long));
+        copy_counted_to_host_kernel<<<grid_for((int64_t)(bytes / 16)), 256, 0, st>>>(
+            reinterpret_cast<const unsigned char*>(out_xyz_dev), reinterpret_cast<unsigned char*>(host_xyz), 3 * sizeof(T),
+            reinterpret_cast<const unsigned char*>(out_idx_dev), reinterpret_cast<unsigned char*>(host_idx), sizeof(long long),
+            scalar_u32(ctx, SC_GS_COUNT));
+        PLS_CHECK_LAUNCH();
+    };
     if (compact) {
         ctx->gs_seq += 1;
         if (ctx->gs_seq == 0) ctx->gs_seq = 1;
@@ -203,8 +222,9 @@ void grid_sample_device(pls_context* ctx, const T* xyz_dev, int64_t n, double vo
     uint32_t* sv;
     radix_sort_pairs(ctx, ctx->gs_keys.as<uint64_t>(), ctx->gs_vals.as<uint32_t>(), n, compact ? GS_COMPACT_BITS / 8 : 8, &sk, &sv);
     if (n <= SEL_MAX_N) {
-        GridSampleSelect<T> op{sk, sv, xyz_dev, out_xyz_dev, out_idx_dev, host_xyz, host_idx};
+        GridSampleSelect<T> op{sk, sv, xyz_dev, out_xyz_dev, out_idx_dev};
         select_launch(ctx, op, n, nullptr, scalar_u32(ctx, SC_GS_COUNT), nullptr);
+        copy_to_host();
         return;
     }
     // clouds beyond the single-wave selection: flags, scan, gather
@@ -212,9 +232,9 @@ void grid_sample_device(pls_context* ctx, const T* xyz_dev, int64_t n, double vo
     PLS_CHECK_LAUNCH();
     exclusive_scan_flags(ctx, ctx->tmp[1].as<uint8_t>(), n, ctx->tmp[2].as<uint32_t>(), scalar_u32(ctx, SC_GS_COUNT));
     gather_samples_kernel<T><<<grid_for(n), 256, 0, st>>>(xyz_dev, sv, ctx->tmp[1].as<uint8_t>(),
-                                                          ctx->tmp[2].as<uint32_t>(), n, out_xyz_dev, out_idx_dev,
-                                                          host_xyz, host_idx);
+                                                          ctx->tmp[2].as<uint32_t>(), n, out_xyz_dev, out_idx_dev);
     PLS_CHECK_LAUNCH();
+    copy_to_host();
 }
 
 // Voxelization.filter (preprocessing.py:71-97): coordinates, hashes and the per-voxel normal distribution.

@@ -32,6 +32,8 @@ t_pre, t_odo, prev = [], [], None
 for k in range(F):
     if k == WARM:
         calls.clear(); t_pre.clear(); t_odo.clear()
+        for slot in (0, 3, 4):
+            orig(algo.ctx, "pls_profile_enable", slot, 1)
     dd = {"numpy_pc": scans[k], "init_rpose": prev}
     t0 = time.perf_counter()
     pre.forward(dd)
@@ -45,4 +47,7 @@ n = F - WARM
 print(f"frame {1e6*(sum(t_pre)+sum(t_odo))/n:.0f} us = preprocessing {1e6*sum(t_pre)/n:.0f} + process_next_frame {1e6*sum(t_odo)/n:.0f}")
 for name, v in calls.items():
     print(f"   C ABI {name:32s} {1e6*sum(v)/n:8.1f} us/frame ({len(v)/n:.1f} calls)")
+for slot, name in ((4, "grid sample kernels"), (0, "ICP kernels"), (3, "index build (map stream)")):
+    ms, launches, _ = algo.ctx.profile(slot)
+    print(f"   device events, {name:26s} {1e3 * ms / n:8.1f} us/frame")
 print(f"   Python around the C ABI: {1e6*(sum(t_pre)+sum(t_odo)-sum(sum(v) for v in calls.values()))/n:.0f} us/frame")

@@ -144,6 +144,12 @@ PY
             tail -3 gpurun_out/${TAG}_bench_n${n}_${comm}.err
         done
     done ;;
+prioab)
+    for rep in 1 2; do for pr in 1 0; do
+        echo "== PLS_STREAM_PRIORITY=$pr"
+        PLS_STREAM_PRIORITY=$pr timeout 120 python tools/e2e_breakdown.py 2>&1 | tail -8 | tee -a gpurun_out/${TAG}_prioab.log
+        PLS_STREAM_PRIORITY=$pr timeout 120 python bench.py --quick --steps 40 --warmup 24 2>/dev/null | tail -1 | cut -c1-200
+    done; done ;;
 e2ebreak)
     timeout 120 python tools/e2e_breakdown.py 2>&1 | tail -8 | tee gpurun_out/${TAG}_e2e_breakdown.log ;;
 quicktime)
