@@ -301,6 +301,7 @@ int pls_create(const pls_config* cfg, pls_context** out) {
 int pls_destroy(pls_context* ctx) {
     if (!ctx) return PLS_E_INVALID;
     cudaSetDevice(ctx->cfg.device);
+    ctx->upd_pending = false;  // a map update that was never enqueued dies with the context
     cudaStreamSynchronize(ctx->stream_map);
     cudaStreamSynchronize(ctx->stream_main);
     comm_free(ctx);

@@ -347,7 +347,7 @@ int pls_grid_sample(pls_context* ctx, const void* xyz, int is_f64, int64_t n, do
 int pls_grid_sample_staged(pls_context* ctx, const void* xyz, int is_f64, int64_t n, double voxel,
                            const void** out_xyz_host, const int64_t** out_idx_host, const void** out_xyz_dev,
                            int64_t* out_count) {
-    PLS_API_BEGIN(ctx)
+    PLS_API_BEGIN_FRAME(ctx)
     PLS_REQUIRE(xyz && out_xyz_host && out_idx_host && out_count && n > 0 && voxel > 0.0, "pls_grid_sample_staged: bad arguments");
     const size_t esz = is_f64 ? sizeof(double) : sizeof(float);
     const void* d_xyz = to_device(ctx, xyz, (size_t)n * 3 * esz, ctx->stage_in[0]);
@@ -379,6 +379,7 @@ int pls_grid_sample_staged(pls_context* ctx, const void* xyz, int is_f64, int64_
         else
             grid_sample_device<float>(ctx, (const float*)d_xyz, n, voxel, dev_xyz.as<float>(), nullptr, compact,
                                       (float*)map_xyz, (long long*)map_idx);
+        flush_map_update(ctx);  // the last frame's local-map update is enqueued while the subsample runs
         bool overflowed = false;
         count = grid_sample_read_count(ctx, &overflowed);
         if (!(compact && overflowed)) break;  // hashes beyond 40 bits: once more on the raw 64-bit keys

@@ -193,6 +193,12 @@ struct pls_context {
     pls::DBuf frame_vmap_buf[2];        // [3][H][W] of the current frame (double-buffered: the previous one may
     pls::DBuf frame_pts_buf[2];         // still be read by the map-update stream); float4 packed valid points
     int frame_slot = 0;
+    // the local-map update of the last frame, decided but not yet enqueued: the next call enqueues it once its own
+    // first kernels are in flight (flush_map_update), so its ~25 us of launches leave the critical path of both calls
+    bool upd_pending = false, upd_insert = false;
+    float upd_T[16];
+    int upd_slot = 0;
+    long long upd_count = 0;
     pls::DBuf queries;                  // float4 queries P0 (owned storage)
     const float4* query_ptr = nullptr;  // the queries of the current frame (may alias frame_pts)
     pls::DBuf nn_prev;                  // previous-iteration match per query
@@ -209,7 +215,18 @@ struct pls_context {
     pls::ProfileSlot prof[pls::kProfileSlots];
 };
 
+namespace pls {
+void flush_map_update(pls_context* ctx);  // odometry.cu: enqueues the deferred local-map update of the last frame, if any
+}
+
 #define PLS_API_BEGIN(ctx)                               \
+    if (!(ctx)) return PLS_E_INVALID;                    \
+    try {                                                \
+        cudaSetDevice((ctx)->cfg.device);                \
+        pls::flush_map_update(ctx);
+
+/* entry points of the per-frame path: they enqueue the pending map update themselves, behind their own first kernels */
+#define PLS_API_BEGIN_FRAME(ctx)                         \
     if (!(ctx)) return PLS_E_INVALID;                    \
     try {                                                \
         cudaSetDevice((ctx)->cfg.device);

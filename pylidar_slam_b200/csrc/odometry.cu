@@ -7,6 +7,8 @@
 // One device->host copy of the FrameResult ends the frame.
 #include <stdlib.h>
 
+#include <chrono>
+
 #include "internal.cuh"
 #include "icp_device.cuh"
 #include "pose_device.cuh"
@@ -284,6 +286,32 @@ int enqueue_icp_iterations(pls_context* ctx, int64_t query_bound, int first, int
     return last_blocks;
 }
 
+// PLS_HOST_TRACE=1: host-side time of the phases of a frame (enqueue up to the ICP, the wait for the pose, the
+// map-update enqueue), averaged and printed every 64 frames -- a development aid for the end-to-end path.
+struct HostTrace {
+    bool on = getenv("PLS_HOST_TRACE") != nullptr;
+    double acc[4] = {0, 0, 0, 0};
+    int frames = 0, extra_rounds = 0;
+    std::chrono::steady_clock::time_point t;
+    void start() { if (on) t = std::chrono::steady_clock::now(); }
+    void lap(int k) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        acc[k] += std::chrono::duration<double, std::micro>(now - t).count();
+        t = now;
+    }
+    void end_frame() {
+        if (!on || ++frames < 64) return;
+        fprintf(stderr, "[plslam_b200 host trace] per frame: enqueue input+ICP %.1f us, wait for the pose %.1f us, "
+                        "map-update enqueue %.1f us, rest %.1f us; %d of %d frames needed a second round of ICP launches\n",
+                acc[0] / frames, acc[1] / frames, acc[2] / frames, acc[3] / frames, extra_rounds, frames);
+        frames = 0;
+        extra_rounds = 0;
+        acc[0] = acc[1] = acc[2] = acc[3] = 0;
+    }
+};
+HostTrace g_trace;
+
 // The ICP loop (icp_odometry.py:248-299) over ctx->query_ptr / counts[1]: iterations are enqueued without
 // host syncs and turn into no-ops once the device-side `done` flag latches.  To avoid paying for
 // max_num_alignments launches when ICP converges in 2-3, only `previous frame's count + 1` iterations are
@@ -303,12 +331,14 @@ int run_icp(pls_context* ctx, const float* T0_dev, int64_t query_bound) {
     if (upfront > max_it) upfront = max_it;
     int blocks = enqueue_icp_iterations(ctx, query_bound, 0, upfront);
     int enq = upfront;
+    g_trace.lap(0);
     while (enq < max_it) {
         // continue only if the device has not latched `done` (checked on the host: rare path)
         int flags[3];
         PLS_CUDA(cudaMemcpyAsync(flags, &fr->iters, sizeof(flags), cudaMemcpyDeviceToHost, st));
         PLS_CUDA(cudaStreamSynchronize(st));
         if (flags[2] /*done*/) break;
+        g_trace.extra_rounds += 1;
         const int more = (max_it - enq) < 4 ? (max_it - enq) : 4;
         blocks = enqueue_icp_iterations(ctx, query_bound, enq, enq + more);
         enq += more;
@@ -371,9 +401,37 @@ bool keyframe_decision(pls_context* ctx, const float* T) {
     return insert;
 }
 
+}  // namespace
+
+// The deferred local-map update (ICPFrameToModel.__update_map, icp_odometry.py:360-380) of the last frame: move / append /
+// evict + index rebuild, or the projective model rebuild, on the map stream.
+void flush_map_update(pls_context* ctx) {
+    if (!ctx->upd_pending) return;
+    ctx->upd_pending = false;
+    const bool kd = ctx->cfg.local_map_type == PLS_MAP_KDTREE;
+    DBuf& frame_vmap = ctx->frame_vmap_buf[ctx->upd_slot];
+    DBuf& frame_pts = ctx->frame_pts_buf[ctx->upd_slot];
+    map_stream_begin(ctx);
+    try {
+        if (kd) {
+            if (ctx->upd_insert) kdmap_update_packed(ctx, ctx->upd_T, frame_pts.as<float4>(), (int64_t)ctx->upd_count, true);
+            else kdmap_update_packed(ctx, ctx->upd_T, nullptr, 0, false);
+        } else {
+            projmap_update(ctx, ctx->upd_T, ctx->upd_insert ? frame_vmap.as<float>() : nullptr);
+        }
+    } catch (...) {
+        map_stream_end(ctx);
+        throw;
+    }
+    map_stream_end(ctx);
+}
+
+namespace {
+
 void process_frame_device(pls_context* ctx, const void* data_void, int layout, int64_t n, const float* init_pose,
                           float* out_pose, float* out_params, int* out_has_pose, double* out_info) {
     cudaStream_t st = ctx->stream;
+    g_trace.start();
     // float64 point layouts: same flow, the cloud is rounded to float32 for the queries / map insertion while the frame's
     // own vertex map is projected in float64 (icp_odometry.py:331-352)
     const bool is64 = layout == PLS_INPUT_NDARRAY_F64 || layout == PLS_INPUT_TENSOR_F64;
@@ -458,6 +516,7 @@ void process_frame_device(pls_context* ctx, const void* data_void, int layout, i
 
     if (first) {
         // icp_odometry.py:171-181: the first frame only initialises the map, via its vertex map
+        flush_map_update(ctx);
         map_stream_wait(ctx);
         if (kd) kdmap_update(ctx, eye, nullptr, 0, frame_vmap.as<float>(), H, W, -1);
         else projmap_update(ctx, eye, frame_vmap.as<float>());
@@ -502,29 +561,26 @@ void process_frame_device(pls_context* ctx, const void* data_void, int layout, i
         PLS_CUDA(cudaMemcpyAsync(ctx->tmp[6].p, init_pose, 16 * sizeof(float), cudaMemcpyHostToDevice, st));
         T0_dev = ctx->tmp[6].as<float>();
     }
-    map_stream_wait(ctx);  // the ICP below reads the local map the previous frame's update is still building
+    flush_map_update(ctx);  // (already enqueued by the grid-sample call of this frame, if there was one)
+    map_stream_wait(ctx);   // the ICP below reads the local map the previous frame's update is still building
     const int icp_blocks = run_icp(ctx, T0_dev, query_bound);
     fetch_result(ctx);
+    g_trace.lap(1);
     FrameResult* h = frame_result_host(ctx);
     ctx->last_icp_iters = h->iters;
     credit_icp_profile(ctx, h, icp_blocks);
     raise_status(ctx, h->status);
 
-    // ---- __update_map: enqueued on the map stream, it overlaps the NEXT frame's preprocessing
+    // ---- __update_map: decided now, enqueued (on the map stream, beside the NEXT frame's preprocessing) by the next call
     const bool insert = keyframe_decision(ctx, h->T);
-    map_stream_begin(ctx);
-    try {
-        if (kd) {
-            if (insert) kdmap_update_packed(ctx, h->T, frame_pts.as<float4>(), (int64_t)h->counts[2], true);
-            else kdmap_update_packed(ctx, h->T, nullptr, 0, false);
-        } else {
-            projmap_update(ctx, h->T, insert ? frame_vmap.as<float>() : nullptr);
-        }
-    } catch (...) {
-        map_stream_end(ctx);
-        throw;
-    }
-    map_stream_end(ctx);
+    ctx->upd_pending = true;
+    ctx->upd_insert = insert;
+    memcpy(ctx->upd_T, h->T, sizeof(ctx->upd_T));
+    ctx->upd_slot = ctx->frame_slot;
+    ctx->upd_count = (long long)h->counts[2];
+    static const bool eager = getenv("PLS_MAP_UPDATE_EAGER") != nullptr;  // A/B: enqueue before returning, as before
+    if (eager) flush_map_update(ctx);
+    g_trace.lap(2);
     ctx->frame_index += 1;
     if (out_pose) memcpy(out_pose, h->T, 16 * sizeof(float));
     if (out_params) memcpy(out_params, h->params, 6 * sizeof(float));
@@ -541,6 +597,8 @@ void process_frame_device(pls_context* ctx, const void* data_void, int layout, i
         out_info[8] = h->first_pt[0]; out_info[9] = h->first_pt[1]; out_info[10] = h->first_pt[2];
         out_info[11] = ctx->last_sharded ? 1.0 : 0.0;  // the correspondences were split over the ranks
     }
+    g_trace.lap(3);
+    g_trace.end_frame();
 }
 
 }  // namespace
@@ -627,7 +685,7 @@ int pls_register_frame(pls_context* ctx, const float* points, int64_t n, const f
 
 int pls_process_frame(pls_context* ctx, const void* data, int layout, int64_t n, const float* init_pose,
                       float* out_pose, float* out_params, int* out_has_pose, double* out_info) {
-    PLS_API_BEGIN(ctx)
+    PLS_API_BEGIN_FRAME(ctx)
     PLS_REQUIRE(data, "pls_process_frame: null data");
     // optional residency hint in the high bits: the caller knows where `data` lives (a device-resident grid-sample
     // result handed over by pls_grid_sample_staged, a CUDA tensor, a numpy array) and saves the classification
@@ -655,6 +713,8 @@ int pls_process_frame(pls_context* ctx, const void* data, int layout, int64_t n,
 int pls_process_frame_grid_sample(pls_context* ctx, const float* raw_points, int64_t n, double voxel, int layout,
                                   const float* init_pose, float* out_pose, float* out_params, int* out_has_pose,
                                   double* out_info) {
+    // (the pending map update is enqueued first here: with no host gap between the frames the next ICP would
+    // otherwise wait for an index build that started a subsample's worth of launches later)
     PLS_API_BEGIN(ctx)
     PLS_REQUIRE(raw_points && n > 0 && voxel > 0.0, "pls_process_frame_grid_sample: bad arguments");
     PLS_REQUIRE(layout == PLS_INPUT_NDARRAY || layout == PLS_INPUT_TENSOR, "grid-sampled input is a point layout");
