@@ -685,7 +685,7 @@ int pls_register_frame(pls_context* ctx, const float* points, int64_t n, const f
 
 int pls_process_frame(pls_context* ctx, const void* data, int layout, int64_t n, const float* init_pose,
                       float* out_pose, float* out_params, int* out_has_pose, double* out_info) {
-    PLS_API_BEGIN_FRAME(ctx)
+    PLS_API_BEGIN(ctx)  // (enqueues the last frame's map update first, unless this frame's grid-sample call already did)
     PLS_REQUIRE(data, "pls_process_frame: null data");
     // optional residency hint in the high bits: the caller knows where `data` lives (a device-resident grid-sample
     // result handed over by pls_grid_sample_staged, a CUDA tensor, a numpy array) and saves the classification
