@@ -247,7 +247,7 @@ namespace pls {
 
 // device scalar slots (u32) living behind the FrameResult in ctx->scalars
 enum { SC_GS_COUNT = 0, SC_QUERY_COUNT = 1, SC_NAN_COUNT = 2, SC_INSERT_COUNT = 3, SC_PROJ_NC = 4,
-       SC_WL0 = 5, SC_WL1 = 6,  // pending-normal worklist counters, one per iteration parity (kdmap.cu)
+       SC_SPARE0 = 5, SC_SPARE1 = 6,
        SC_GS_OVERFLOW = 7,
        SC_KD_COUNTERS = 8,      // four u64 counters of the kd search kernels (slots 8..15)
        SC_KD_LISTS = 16,        // per-iteration work-list counters of the kd search (kdmap.cu: KDL_*), 8 words

@@ -3,7 +3,7 @@
 // all digits taken in one upfront pass) and a single-pass exclusive scan of 0/1 flags.
 //
 // They replace np.unique's stable sort (slam/common/pointcloud.py:177,193) and feed the
-// LBVH index build that stands in for the per-frame KD-tree build (local_map.py:365-369).
+// cell-pyramid index build that stands in for the per-frame KD-tree build (local_map.py:365-369).
 #include "internal.cuh"
 
 namespace pls {

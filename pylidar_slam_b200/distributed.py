@@ -10,7 +10,7 @@ import numpy as np
 
 
 def query_shard(num_queries: int, rank: int, world: int) -> np.ndarray:
-    """kd map: rank r reduces queries r, r + world, ... (kd_icp_iter_kernel's q_begin/q_stride)."""
+    """kd map: rank r reduces queries r, r + world, ... (the kd kernels' q_begin/q_stride)."""
     return np.arange(rank, num_queries, world)
 
 

@@ -124,7 +124,7 @@ def _new(x, shape, dtype=torch.float32):
 
 
 class KdTreeLocalMap(LocalMap):
-    """KdTreeLocalMap (local_map.py:254-427) on the GPU: exact LBVH 1-NN + lazily cached 10-NN normals."""
+    """KdTreeLocalMap (local_map.py:254-427) on the GPU: exact 1-NN over the hashed cell pyramid + lazily cached 10-NN normals."""
 
     def __init__(self, config: KdTreeLocalMapConfig, projector=None, ctx: Optional[_lib.Context] = None, **kwargs):
         super().__init__(config)
