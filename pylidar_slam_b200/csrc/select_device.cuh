@@ -36,7 +36,7 @@ __device__ __forceinline__ unsigned long long sel_pack(unsigned long long flag, 
 
 // totals[0], totals[1] receive the sizes of the two outputs (n_dev, if given, overrides n with a device-side count).
 template <typename Op>
-__global__ void __launch_bounds__(SEL_THREADS)
+__global__ void __launch_bounds__(SEL_THREADS, 4)   // four tiles per SM resident: what SEL_MAX_N counts on
 select_kernel(Op op, int64_t n, const uint32_t* __restrict__ n_dev, unsigned long long* status, uint32_t epoch,
               uint32_t* __restrict__ total0, uint32_t* __restrict__ total1) {
     __shared__ uint32_t warp_sums[2][SEL_THREADS / 32];
