@@ -144,8 +144,15 @@ def ref_vs_port_note():
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def run_cpu_port(scans, warmup, steps, threads=None):
-    """The oracle port of the reference path on the host cores; returns (fps, ms/frame list)."""
+def run_cpu_port(scans, warmup, steps, threads=None, calibrate=False):
+    """The oracle port of the reference path on the host cores; returns (fps, ms/frame list, threads, {threads: ms}).
+
+    calibrate=True gives the CPU arm the torch thread count that is FASTEST on this host, not simply all of them: the path
+    is made of many small tensor ops, and 64 intra-op threads were measured slower than one on the 64-core B200 hosts
+    (SCALE_r01: 297 vs 369 ms/frame).  After the warm-up frames every candidate count replays the SAME next two frames on
+    a deep copy of the algorithm's state (local map, kd-tree, poses), twice; the fastest one runs the timed frames.  scipy's
+    cKDTree queries use every core (workers=-1) whatever is chosen."""
+    import copy
     import torch
     from oracle import icp_oracle as orc
     if threads:
@@ -153,18 +160,39 @@ def run_cpu_port(scans, warmup, steps, threads=None):
     cfg = orc.ICPConfig(max_num_alignments=MAX_ALIGN, data_key="input_data", local_map="kdtree", local_map_size=LM_SIZE,
                         scheme=SCHEME, sigma=SIGMA)
     algo = orc.ICPFrameToModelOracle(cfg, orc.Projector(H, W))
-    prev, times = None, []
-    for k in range(warmup + steps):
+
+    def frame(a, k, prev):
         t0 = time.perf_counter()
         s, _ = orc.grid_sample(scans[k], VOXEL)                       # GridSample.filter
         dd = {"input_data": torch.from_numpy(s), "init_rpose": prev}  # ToTensor
-        algo.process_next_frame(dd)
+        a.process_next_frame(dd)
         dt = time.perf_counter() - t0
-        if "odometry_pose" in dd:
-            prev = dd["odometry_pose"].astype(np.float64)
+        return dt, (dd["odometry_pose"].astype(np.float64) if "odometry_pose" in dd else prev)
+
+    prev, times, tried = None, [], {}
+    for k in range(warmup + steps):
+        if k == warmup and calibrate:
+            ncpu = os.cpu_count() or 1
+            cands = sorted({t for t in (1, 4, 8, 16, 32, ncpu) if t <= ncpu})
+            for thr in cands + cands[::-1]:                 # two rounds in opposite orders, the better one counts
+                torch.set_num_threads(thr)
+                a, p, dts = copy.deepcopy(algo), prev, []
+                for j in range(k, min(k + 2, len(scans))):
+                    dt, p = frame(a, j, p)
+                    dts.append(dt)
+                tried[thr] = min(tried.get(thr, 1e30), 1e3 * float(np.mean(dts)))
+            torch.set_num_threads(min(tried, key=tried.get))
+        dt, prev = frame(algo, k, prev)
         if k >= warmup:
             times.append(dt)
-    return len(times) / sum(times), times
+    return len(times) / sum(times), times, torch.get_num_threads(), tried
+
+
+def threads_note(best, tried):
+    if not tried:
+        return ""
+    return ("; torch intra-op threads calibrated after the warm-up on copies of the state (best of two rounds of two frames, ms/frame: "
+            + ", ".join(f"{t} thr {ms:.0f}" for t, ms in tried.items()) + f") -> {best}; host cores {os.cpu_count()}")
 
 
 def reference_arm(args):
@@ -177,16 +205,16 @@ def reference_arm(args):
     steps = min(args.steps, 30)
     scans = make_scans(warmup + steps)
     t0 = time.perf_counter()
-    fps, times = run_cpu_port(scans, warmup, steps)
+    fps, times, best, tried = run_cpu_port(scans, warmup, steps, calibrate=True)
     line = {
         "impl": "reference", "metric": "icp_odometry_frames_per_sec", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * float(np.mean(times)),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "height": H, "width": W, "voxel": VOXEL},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "torch_threads": best, "kind": "port",
                          "sample": f"frames {warmup}..{warmup + steps - 1} of the same seeded stream after {warmup} warm-up "
                                    f"frames (oracle/icp_oracle.py: torch CPU + scipy cKDTree workers=-1), "
-                                   f"{time.perf_counter() - t0:.1f} s wall" + ref_vs_port_note()},
+                                   f"{time.perf_counter() - t0:.1f} s wall" + threads_note(best, tried) + ref_vs_port_note()},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -444,10 +472,11 @@ def b200_arm(args):
     if world == 1 and not args.no_cpu:
         t0 = time.perf_counter()
         nb = min(len(scans), 30)
-        fps_cpu, times = run_cpu_port(scans[:nb], min(22, nb - 6), nb - min(22, nb - 6))
-        line["cpu_baseline"] = {"value": fps_cpu, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+        fps_cpu, times, best, tried = run_cpu_port(scans[:nb], min(22, nb - 6), nb - min(22, nb - 6), calibrate=True)
+        line["cpu_baseline"] = {"value": fps_cpu, "unit": "frames/s", "cores": os.cpu_count(), "torch_threads": best, "kind": "port",
                                 "sample": f"frames {min(22, nb - 6)}..{nb - 1} of the same stream (oracle port: torch CPU + scipy "
-                                          f"cKDTree workers=-1), {time.perf_counter() - t0:.1f} s wall" + ref_vs_port_note()}
+                                          f"cKDTree workers=-1), {time.perf_counter() - t0:.1f} s wall" + threads_note(best, tried)
+                                          + ref_vs_port_note()}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
