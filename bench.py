@@ -145,7 +145,8 @@ def ref_vs_port_note():
 
 # ------------------------------------------------------------------------------------------ CPU arm
 def run_cpu_port(scans, warmup, steps, threads=None, calibrate=False):
-    """The oracle port of the reference path on the host cores; returns (fps, ms/frame list, threads, {threads: ms}).
+    """The oracle port of the reference path on the host cores; returns (fps, ms/frame list, threads, {threads: ms},
+    last pose).
 
     calibrate=True gives the CPU arm the torch thread count that is FASTEST on this host, not simply all of them: the path
     is made of many small tensor ops, and 64 intra-op threads were measured slower than one on the 64-core B200 hosts
@@ -185,7 +186,7 @@ def run_cpu_port(scans, warmup, steps, threads=None, calibrate=False):
         dt, prev = frame(algo, k, prev)
         if k >= warmup:
             times.append(dt)
-    return len(times) / sum(times), times, torch.get_num_threads(), tried
+    return len(times) / sum(times), times, torch.get_num_threads(), tried, prev
 
 
 def threads_note(best, tried):
@@ -205,7 +206,7 @@ def reference_arm(args):
     steps = min(args.steps, 30)
     scans = make_scans(warmup + steps)
     t0 = time.perf_counter()
-    fps, times, best, tried = run_cpu_port(scans, warmup, steps, calibrate=True)
+    fps, times, best, tried, _ = run_cpu_port(scans, warmup, steps, calibrate=True)
     line = {
         "impl": "reference", "metric": "icp_odometry_frames_per_sec", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * float(np.mean(times)),
@@ -472,7 +473,7 @@ def b200_arm(args):
     if world == 1 and not args.no_cpu:
         t0 = time.perf_counter()
         nb = min(len(scans), 30)
-        fps_cpu, times, best, tried = run_cpu_port(scans[:nb], min(22, nb - 6), nb - min(22, nb - 6), calibrate=True)
+        fps_cpu, times, best, tried, _ = run_cpu_port(scans[:nb], min(22, nb - 6), nb - min(22, nb - 6), calibrate=True)
         line["cpu_baseline"] = {"value": fps_cpu, "unit": "frames/s", "cores": os.cpu_count(), "torch_threads": best, "kind": "port",
                                 "sample": f"frames {min(22, nb - 6)}..{nb - 1} of the same stream (oracle port: torch CPU + scipy "
                                           f"cKDTree workers=-1), {time.perf_counter() - t0:.1f} s wall" + threads_note(best, tried)
