@@ -1,4 +1,7 @@
 #!/bin/bash
+# ROUND-1 evidence script, kept so that profiles/r1_* stay reproducible at their commits (tools/gpu_r2.sh is the current
+# one).  The A/B stages `ab`, `later` and `abkeys` set toggles of kernels that were replaced in round 2 (PLS_KD_NGROUP*):
+# on the current tree they run the default build twice.
 # One GPU-box session of the round (outputs under gpurun_out/).  Stages are picked by name:
 #   bash tools/gpu_round.sh next subset launches nextprof ncufull full bench
 set -u
