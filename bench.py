@@ -10,9 +10,11 @@ sigma 0.3, <= 10 alignments, constant-velocity initialisation), on a seeded synt
 * `value`  : frames/s with every raw scan already resident in HBM; one C-ABI call per frame
              (pls_process_frame_grid_sample) on device pointers; ONE CUDA-event bracket on the library's
              stream around the K timed frames (closed after both of the library's streams have drained).
+             `value` is the MEDIAN of 3 such passes (fresh context, W warm-up frames, exactly K timed frames each; all
+             three are listed in config.repeats) -- with the driver's --steps 20 one bracket is a 10 ms sample.
 * `e2e`    : frames/s through the reference-shaped Python API (Preprocessing[GridSample, ToTensor]
              -> ICPFrameToModel.process_next_frame) from PINNED HOST buffers, host<->device copies
-             inside the timed region.
+             inside the timed region; the median of 3 passes as well.
 * roofline : the kd correspondence kernels of the executed ICP iterations (verify / 1-NN search / lazy 10-NN normals /
              reduction + fused solve), CUDA-event timed inside the library over the timed frames (a second pass, so
              that the event records do not perturb `value`).  `achieved` uses SURVEY.md 8d's algorithmic bytes with
@@ -42,6 +44,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 H, W, VOXEL = 64, 2048, 0.3
+REPEATS = 3   # independent passes behind `value` and behind `e2e` (the median pass is reported, all are listed)
 MAX_ALIGN, LM_SIZE, SCHEME, SIGMA = 10, 20, "geman_mcclure", 0.3
 WORKLOAD = ("cfg2: icp_odometry + grid_sample(0.3) preprocessing, synthetic 64x2048 rotating-LiDAR stream, "
             "kd-tree local map (20 frames), point-to-plane GN geman_mcclure 0.3, <=10 alignments, CV init")
@@ -352,8 +355,11 @@ def b200_arm(args):
 
     clocks = ClockSampler(local_rank, enabled=(rank == 0))
     clocks.start()
-    ms_dev, launches, _, stats = device_pass()
+    # `value` = the MEDIAN of REPEATS independent passes (fresh context, W warm-up frames, exactly K timed frames each):
+    # with the driver's --steps 20 one bracket is a 10 ms sample; every pass is listed in config.repeats
+    value_passes = [device_pass() for _ in range(1 if args.quick else REPEATS)]
     clock_info = clocks.stop()
+    ms_dev, launches, _, stats = sorted(value_passes, key=lambda r: r[0])[len(value_passes) // 2]
     if args.quick:
         (ms_dev,) = max_over_ranks(ms_dev)
         if world > 1:
@@ -371,37 +377,42 @@ def b200_arm(args):
     # ---------------- e2e: reference-shaped Python API from pinned host buffers
     pinned = [torch.from_numpy(s).pin_memory() for s in scans]
     host_scans = [p.numpy() for p in pinned]
-    pre = b200.Preprocessing(b200.PreprocessingConfig(filters={
-        "2": dict(filter_name="grid_sample", voxel_size=VOXEL, pointcloud_key="numpy_pc"),
-        "3": dict(filter_name="to_tensor", keys=dict(sample_points="input_data"))}))
-    algo = make_algo()
-    gs_ctx = algo.ctx
-    for f in pre.filters:
-        if hasattr(f, "ctx"):
-            f.ctx = gs_ctx
-    prev, h2d, d2h = None, 0, 0
-    t_start = 0.0
-    for k in range(n_frames):
-        timed = k > W_
-        if k == W_ + 1:
-            gs_ctx.call("pls_synchronize")
-            hold_clocks()
-            flush_l2()
-            barrier()
-            t_start = time.perf_counter()
-        dd = {"numpy_pc": host_scans[k], "init_rpose": prev}
-        pre.forward(dd)
-        algo.process_next_frame(dd)
-        if "odometry_pose" in dd:
-            prev = dd["odometry_pose"].astype(np.float64)
-        if timed:
-            S = dd["sample_points"].shape[0]
-            h2d += host_scans[k].nbytes + 64                  # the raw scan + the initial pose (the samples stay on the device)
-            d2h += S * 12 + S * 8 + 32 + 2176                 # samples + indices (filter outputs) + count + FrameResult block
-    gs_ctx.call("pls_synchronize")
-    t_e = time.perf_counter() - t_start
-    barrier()
-    del algo
+
+    def e2e_pass():
+        pre = b200.Preprocessing(b200.PreprocessingConfig(filters={
+            "2": dict(filter_name="grid_sample", voxel_size=VOXEL, pointcloud_key="numpy_pc"),
+            "3": dict(filter_name="to_tensor", keys=dict(sample_points="input_data"))}))
+        algo = make_algo()
+        gs_ctx = algo.ctx
+        for f in pre.filters:
+            if hasattr(f, "ctx"):
+                f.ctx = gs_ctx
+        prev, h2d, d2h = None, 0, 0
+        t_start = 0.0
+        for k in range(n_frames):
+            timed = k > W_
+            if k == W_ + 1:
+                gs_ctx.call("pls_synchronize")
+                hold_clocks()
+                flush_l2()
+                barrier()
+                t_start = time.perf_counter()
+            dd = {"numpy_pc": host_scans[k], "init_rpose": prev}
+            pre.forward(dd)
+            algo.process_next_frame(dd)
+            if "odometry_pose" in dd:
+                prev = dd["odometry_pose"].astype(np.float64)
+            if timed:
+                S = dd["sample_points"].shape[0]
+                h2d += host_scans[k].nbytes + 64              # the raw scan + the initial pose (the samples stay on the device)
+                d2h += S * 12 + S * 8 + 32 + 2176             # samples + indices (filter outputs) + count + FrameResult block
+        gs_ctx.call("pls_synchronize")
+        t = time.perf_counter() - t_start
+        barrier()
+        return t, h2d, d2h
+
+    e2e_passes = [e2e_pass() for _ in range(REPEATS)]     # same rule as `value`: the median pass
+    t_e, h2d, d2h = sorted(e2e_passes, key=lambda r: r[0])[len(e2e_passes) // 2]
 
     t_dev, t_e = max_over_ranks(ms_dev / 1e3, t_e)
 
@@ -438,6 +449,11 @@ def b200_arm(args):
                          "~60 MB local map legitimately stays L2-resident across frames (production behaviour); "
                          "value_l2_flushed_every_step re-measures with a 256 MiB flush INSIDE the bracket before every frame",
                    "value_l2_flushed_every_step": K_ / (ms_dev_flushed / 1e3),
+                   "repeats": {"rule": f"value and e2e are each the MEDIAN of {REPEATS} independent passes (fresh context, W warm-up "
+                                       f"frames, exactly K timed frames in one bracket); at N > 1 the max over ranks of the ranks' "
+                                       f"medians; the lists are rank 0's passes in run order",
+                               "value_ms_per_step": [r[0] / K_ for r in value_passes],
+                               "e2e_ms_per_step": [1e3 * r[0] / K_ for r in e2e_passes]},
                    "parallelism": "1 GPU" if world == 1 else
                    (f"{world} GPUs, map replicated; a frame's {stats['queries']} queries are below the sharding threshold "
                     f"(PLS_SHARD_MIN = 24576 per rank), so every rank runs the whole frame and no exchange takes place "

@@ -47,3 +47,136 @@ def test_reference_arm_is_silent_on_other_ranks():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "3"],
                          capture_output=True, text=True, timeout=600, cwd=ROOT, env={**os.environ, "RANK": "1", "WORLD_SIZE": "2"})
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The GPU arm's CONTROL FLOW without a GPU: bench.b200_arm runs against a test-only stand-in for the C ABI (the oracle
+# behind tests/dryrun_next_rows.FakeContext) and stand-ins for the few torch.cuda objects it touches.  This checks that
+# the bench line is assembled (keys, the median-of-passes rule, byte counts) -- never a number: the timings below are CPU
+# times of the oracle and mean nothing.  The product has no such path; the stand-ins live in this file only.
+def _bench_fakes(monkeypatch):
+    import contextlib
+    import time
+    import ctypes as C
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import dryrun_next_rows as dry
+    from oracle import icp_oracle as orc
+    from pylidar_slam_b200 import _lib, common
+
+    class BenchFakeContext(dry.FakeContext):
+        launches = 0
+
+        def __init__(self, **kwargs):
+            kwargs.pop("stream", None)
+            super().__init__(**kwargs)
+            self.handle, self.lib = None, None
+
+        def pls_synchronize(self):
+            pass
+
+        def pls_profile_enable(self, slot, on):
+            pass
+
+        def launch_count(self):
+            return BenchFakeContext.launches
+
+        def profile(self, which, reset=True):
+            return 1.0, 2, 1.0e6
+
+        def pls_process_frame(self, *a):
+            BenchFakeContext.launches += 30
+            return super().pls_process_frame(*a)
+
+        def pls_process_frame_grid_sample(self, raw, n, voxel, layout, init, pose, params, has, info):
+            s, _ = orc.grid_sample(dry.arr(raw, (n, 3), np.float32), voxel)
+            s = np.ascontiguousarray(s, dtype=np.float32)
+            self.pls_process_frame(s.ctypes.data, layout, len(s), init, pose, params, has, info)
+            dry.arr(info, (12,), np.float64)[4] = len(s)
+
+    class FakeStream:
+        def __init__(self, device=None):
+            self.cuda_stream = 0
+
+    class FakeEvent:
+        def __init__(self, enable_timing=False):
+            self.t = 0.0
+
+        def record(self, stream=None):
+            self.t = time.perf_counter()
+
+        def elapsed_time(self, other):
+            return 1e3 * (other.t - self.t)
+
+    real_empty, real_to = torch.empty, torch.Tensor.to
+
+    def empty(*a, **k):
+        if "device" in k and torch.device(k["device"]).type == "cuda":
+            k["device"] = "cpu"
+            a = (1 << 16,)                                      # the 256 MiB L2-flush buffer
+        return real_empty(*a, **k)
+
+    def to(self, *a, **k):
+        if a and isinstance(a[0], torch.device) and a[0].type == "cuda":
+            return self
+        return real_to(self, *a, **k)
+
+    monkeypatch.setattr(_lib, "Context", BenchFakeContext)
+    monkeypatch.setattr(common, "_default_ctx", BenchFakeContext())
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "Stream", FakeStream)
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda d=None: None)
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "empty_cache", lambda: None)
+    monkeypatch.setattr(torch, "empty", empty)
+    monkeypatch.setattr(torch.Tensor, "to", to)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    return BenchFakeContext
+
+
+def test_b200_arm_assembles_the_contract_line_dry_run(monkeypatch, capsys):
+    import argparse
+    import bench
+    from pylidar_slam_b200 import _lib
+    real_context = _lib.Context
+    _bench_fakes(monkeypatch)
+    monkeypatch.setattr(bench.ClockSampler, "start", lambda self: None)
+    monkeypatch.setattr(bench.ClockSampler, "stop", lambda self: {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["dry run"]})
+    from pylidar_slam_b200 import synthetic as syn
+    monkeypatch.setattr(bench, "H", 32)        # a small sensor keeps the oracle-backed frames at a few tens of ms
+    monkeypatch.setattr(bench, "W", 512)
+    monkeypatch.setattr(bench, "VOXEL", 0.4)
+    monkeypatch.setattr(bench, "make_scans", lambda n, h=32, w=512: [syn.scan(k, h, w) for k in range(n)])
+    for k in ("WORLD_SIZE", "RANK", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    args = argparse.Namespace(gpus=1, steps=4, warmup=3, impl="b200", no_cpu=True, no_extra=True, quick=False, comm="p2p")
+    bench.b200_arm(args)
+    lines = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "kernels"):
+        assert key in d, key
+    assert d["metric"] == "icp_odometry_frames_per_sec" and d["unit"] == "frames/s" and d["n_gpus"] == 1
+    assert d["steps"] == 4 and d["warmup"] == 3 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert abs(d["value"] - 1e3 / d["ms_per_step"]) / d["value"] < 1e-9
+    rep = d["config"]["repeats"]
+    assert len(rep["value_ms_per_step"]) == bench.REPEATS and len(rep["e2e_ms_per_step"]) == bench.REPEATS
+    assert abs(sorted(rep["value_ms_per_step"])[bench.REPEATS // 2] - d["ms_per_step"]) < 1e-9       # the median pass
+    assert abs(sorted(rep["e2e_ms_per_step"])[bench.REPEATS // 2] - d["e2e"]["ms_per_step"]) < 1e-9
+    assert d["e2e"]["unit"] == "frames/s" and abs(d["e2e"]["value"] - 1e3 / d["e2e"]["ms_per_step"]) / d["e2e"]["value"] < 1e-9
+    assert d["e2e"]["h2d_bytes_per_step"] == 32 * 512 * 12 + 64 and d["e2e"]["d2h_bytes_per_step"] > 2176
+    assert d["gpu_launches"] == 30 * 4                                                                 # launches of the timed frames only
+    r = d["roofline"]
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert key in r, key
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert d["config"]["workload"].startswith("cfg2") and "cpu_baseline" not in d and "extra_workloads" not in d["config"]
+    assert _lib.Context is not real_context                                                            # still patched here ...
+
+
+def test_bench_fakes_do_not_leak():
+    from pylidar_slam_b200 import _lib
+    assert _lib.Context.__name__ == "Context" and _lib.Context.__module__ == "pylidar_slam_b200._lib"   # ... and restored after
