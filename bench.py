@@ -36,6 +36,7 @@ import subprocess
 import sys
 import threading
 import time
+import traceback
 
 import numpy as np
 
@@ -417,14 +418,24 @@ def b200_arm(args):
     t_dev, t_e = max_over_ranks(ms_dev / 1e3, t_e)
 
     # ---------------- N > 1: sharded == single-GPU evidence on the benched stream (forced sharding, fixed iterations)
+    # (the two sections below are evidence beside the headline: if one of them fails, the line above them is still printed)
     parity = None
     if world > 1:
-        parity = sharded_vs_single(b200, make_algo, syn, dist, dev, rank, world, comm_used)
+        try:
+            parity = sharded_vs_single(b200, make_algo, syn, dist, dev, rank, world, comm_used)
+        except Exception as e:
+            traceback.print_exc()
+            parity = {"failed": f"{type(e).__name__}: {e}"}
 
     # ---------------- the HBM-sized configurations
     extra = None
     if not args.no_extra:
-        extra = extra_workloads(b200, _lib, syn, make_algo, stream, dev, rank, world, dist, peak, comm_used, max_over_ranks, barrier)
+        try:
+            extra = extra_workloads(b200, _lib, syn, make_algo, stream, dev, rank, world, dist, peak, comm_used, max_over_ranks,
+                                    barrier)
+        except Exception as e:
+            traceback.print_exc()
+            extra = {"failed": f"{type(e).__name__}: {e}"}
 
     if rank != 0:
         if world > 1:
