@@ -75,6 +75,13 @@ def _bench_fakes(monkeypatch):
         def pls_synchronize(self):
             pass
 
+        def pls_comm_p2p_handle(self, world, buf):          # distributed.init_comm's rendezvous (p2p mode)
+            for i in range(64):
+                buf[i] = (i + 1) % 256
+
+        def pls_comm_p2p_init(self, world, rank, raw):
+            assert len(raw) == 64 * world
+
         def pls_profile_enable(self, slot, on):
             pass
 
@@ -116,6 +123,13 @@ def _bench_fakes(monkeypatch):
             a = (1 << 16,)                                      # the 256 MiB L2-flush buffer
         return real_empty(*a, **k)
 
+    def on_cpu(fn):                                          # factory calls with device=cuda:* build CPU tensors here
+        def wrapped(*a, **k):
+            if "device" in k and k["device"] is not None and torch.device(k["device"]).type == "cuda":
+                k["device"] = "cpu"
+            return fn(*a, **k)
+        return wrapped
+
     def to(self, *a, **k):
         if a and isinstance(a[0], torch.device) and a[0].type == "cuda":
             return self
@@ -131,6 +145,8 @@ def _bench_fakes(monkeypatch):
     monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
     monkeypatch.setattr(torch.cuda, "empty_cache", lambda: None)
     monkeypatch.setattr(torch, "empty", empty)
+    monkeypatch.setattr(torch, "tensor", on_cpu(torch.tensor))
+    monkeypatch.setattr(torch, "zeros", on_cpu(torch.zeros))
     monkeypatch.setattr(torch.Tensor, "to", to)
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
     return BenchFakeContext
@@ -184,3 +200,66 @@ def test_b200_arm_assembles_the_contract_line_dry_run(monkeypatch, capsys):
 def test_bench_fakes_do_not_leak():
     from pylidar_slam_b200 import _lib
     assert _lib.Context.__name__ == "Context" and _lib.Context.__module__ == "pylidar_slam_b200._lib"   # ... and restored after
+
+
+# ---- the same dry run on TWO ranks (gloo): max over ranks, the barriers inside the repeated passes, the parity section
+class _Patch:
+    """monkeypatch's setattr / delenv for a worker process (nothing to undo: the process exits)."""
+
+    @staticmethod
+    def setattr(obj, name, value):
+        setattr(obj, name, value)
+
+    @staticmethod
+    def delenv(name, raising=False):
+        os.environ.pop(name, None)
+
+
+def _two_rank_worker(rank, world, port, out):
+    import argparse
+    import contextlib
+    import io
+    import torch
+    import torch.distributed as dist
+    import bench
+    from pylidar_slam_b200 import synthetic as syn
+    os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank), "WORLD_SIZE": str(world),
+                       "LOCAL_RANK": "0"})
+    _bench_fakes(_Patch)
+    real_init = dist.init_process_group
+    dist.init_process_group = lambda backend, device_id=None: real_init("gloo", rank=rank, world_size=world)
+    bench.ClockSampler.start = lambda self: None
+    bench.ClockSampler.stop = lambda self: {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["dry run"]} if self.enabled else None
+    bench.H, bench.W, bench.VOXEL = 32, 512, 0.4
+    bench.make_scans = lambda n, h=32, w=512: [syn.scan(k, h, w) for k in range(n)]
+    bench.extra_workloads = lambda *a, **k: {"stub": True}
+    torch.set_num_threads(1)
+    args = argparse.Namespace(gpus=world, steps=3, warmup=3, impl="b200", no_cpu=False, no_extra=False, quick=False, comm="p2p")
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        bench.b200_arm(args)
+    out[rank] = buf.getvalue()
+
+
+def test_b200_arm_two_ranks_dry_run():
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = mp.Manager().dict()
+    mp.spawn(_two_rank_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[1].strip() == ""                                     # rank 0 alone prints
+    lines = [l for l in out[0].splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and d["steps"] == 3 and d["warmup"] == 3 and "cpu_baseline" not in d   # CPU leg at N = 1 only
+    assert "2 GPUs" in d["config"]["parallelism"] and d["config"]["extra_workloads"] == {"stub": True}
+    par = d["config"]["sharded_vs_single"]
+    assert par["identical_across_ranks"] is True and par["max_rel_dt"] == 0.0 and par["max_dR"] == 0.0 and par["exchange"] == "p2p"
+    rep = d["config"]["repeats"]
+    assert len(rep["value_ms_per_step"]) == len(rep["e2e_ms_per_step"]) == 3
+    # the headline is the max over ranks of the ranks' medians: never below rank 0's own median
+    assert d["ms_per_step"] >= sorted(rep["value_ms_per_step"])[1] - 1e-9
+    assert d["e2e"]["ms_per_step"] >= sorted(rep["e2e_ms_per_step"])[1] - 1e-9
