@@ -37,6 +37,34 @@ def arr(addr, shape, dtype):
     return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
 
 
+def cuda_stand_ins(monkeypatch):
+    """TEST-ONLY: tensor factories and Tensor.to asked for a cuda device hand back CPU tensors, so that host logic written
+    for device tensors (the reference-shaped ICP loop, bench.py's control flow) can be stepped through without a GPU."""
+    real_to = torch.Tensor.to
+
+    def on_cpu(fn):
+        def wrapped(*a, **k):
+            if k.get("device") is not None and torch.device(k["device"]).type == "cuda":
+                k["device"] = "cpu"
+            return fn(*a, **k)
+        return wrapped
+
+    def to(self, *a, **k):
+        if a and isinstance(a[0], (torch.device, str)) and torch.device(a[0]).type == "cuda":
+            a = a[1:]
+            if not a and not k:
+                return self
+        if k.get("device") is not None and torch.device(k["device"]).type == "cuda":
+            k = {kk: v for kk, v in k.items() if kk != "device"}
+            if not a and not k:
+                return self
+        return real_to(self, *a, **k)
+
+    for name in ("empty", "zeros", "ones", "eye", "tensor", "full"):
+        monkeypatch.setattr(torch, name, on_cpu(getattr(torch, name)))
+    monkeypatch.setattr(torch.Tensor, "to", to)
+
+
 class FakeContext:
     def __init__(self, **kwargs):
         self.kwargs = kwargs
@@ -207,6 +235,90 @@ class FakeContext:
         out[0] = len(self.algo.losses[-1])
         if layout == _lib.INPUT_VERTEX_MAP:
             out[8:11] = self.algo.pc.reshape(-1, 3)[0].numpy()
+
+    # ---- the fine-grained plug-ins (LocalMap / RigidAlignment mirrors, the projector): the oracle's classes behind the
+    #      header's signatures
+    def pls_map_init(self):
+        k = self.kwargs
+        self.kd = orc.KdTreeLocalMap(k.get("local_map_size", 20), k.get("num_neighbors_normals", 10))
+        self.pm = None
+        if "height" in k:
+            self.pm = orc.ProjectiveLocalMap(orc.Projector(k["height"], k["width"], k.get("up_fov_deg", 3.0), k.get("down_fov_deg", -24.0)),
+                                             k.get("local_map_size", 20), k.get("normals_kernel_size", 5))
+
+    def _maps(self):
+        if not hasattr(self, "kd"):
+            self.pls_map_init()
+
+    def pls_kdmap_update_points(self, rel, pts, n):
+        self._maps()
+        self.kd.update(arr(rel, (4, 4), np.float32).copy(), new_points=None if not pts else arr(pts, (n, 3), np.float32).copy())
+
+    def pls_kdmap_update_vertex_map(self, rel, vm, H, W):
+        self._maps()
+        self.kd.update(arr(rel, (4, 4), np.float32).copy(), new_vertex_map=torch.from_numpy(arr(vm, (1, 3, H, W), np.float32).copy()))
+
+    def pls_kdmap_size(self, out):
+        self._maps()
+        out._obj.value = 0 if self.kd.points is None else self.kd.points.shape[0]
+
+    def pls_kdmap_points(self, out):
+        arr(out, self.kd.points.shape, np.float32)[:] = self.kd.points
+
+    def pls_kdmap_nn_search(self, q, n, nb, nrm, idx):
+        pts, normals, ids = self.kd.nearest_neighbor_search(arr(q, (n, 3), np.float32).copy())
+        arr(nb, (n, 3), np.float32)[:] = pts
+        if nrm:
+            arr(nrm, (n, 3), np.float32)[:] = normals
+        if idx:
+            arr(idx, (n,), np.int64)[:] = ids
+
+    def pls_projmap_update(self, rel, vm):
+        self._maps()
+        H, W = self.kwargs["height"], self.kwargs["width"]
+        self.pm.update(torch.from_numpy(arr(rel, (1, 4, 4), np.float32).copy()),
+                       None if not vm else torch.from_numpy(arr(vm, (1, 3, H, W), np.float32).copy()))
+
+    def pls_projmap_num_frames(self, out):
+        self._maps()
+        out._obj.value = 0 if self.pm.vmaps is None else self.pm.vmaps.shape[0]
+
+    def pls_projmap_model(self, out_v, out_n):
+        arr(out_v, tuple(self.pm.model_vmap.shape), np.float32)[:] = self.pm.model_vmap.numpy()
+        arr(out_n, tuple(self.pm.model_nmap.shape), np.float32)[:] = self.pm.model_nmap.numpy()
+
+    def pls_projmap_nn_search(self, q, n, nb, nrm, tgt, count):
+        a, b, c = self.pm.nearest_neighbor_search(torch.from_numpy(arr(q, (n, 3), np.float32).copy()))
+        nc = a.shape[1]
+        hw = self.kwargs["height"] * self.kwargs["width"]
+        arr(nb, (hw, 3), np.float32)[:nc] = a[0].numpy()
+        arr(nrm, (hw, 3), np.float32)[:nc] = b[0].numpy()
+        arr(tgt, (hw, 3), np.float32)[:nc] = c[0].numpy()
+        count._obj.value = nc
+
+    def pls_align_p2plane(self, ref, tgt, nrm, n, is64, scheme, sigma, max_iters, norm_stop, x0, dT, x, loss):
+        dt = np.float64 if is64 else np.float32
+        r, t, m = (torch.from_numpy(arr(p, (1, n, 3), dt).copy()) for p in (ref, tgt, nrm))
+        x0t = None if not x0 else torch.from_numpy(arr(x0, (1, 6), dt).copy())
+        try:
+            xo, lo, status = orc.gauss_newton_p2plane(r, t, m, SCHEME_NAMES[scheme], sigma, max_iters, norm_stop, x0t)
+        except orc.SingularHessian:
+            return _lib.check(None, _lib.PLS_E_SINGULAR)
+        arr(dT, (4, 4), dt)[:] = orc.build_pose_matrix(xo)[0].numpy()
+        arr(x, (6,), dt)[:] = xo[0].numpy()
+        arr(loss, (n,), dt)[:] = lo[0].numpy()
+        if status == "tiny_residual":
+            import logging
+            logging.warning("The residual norm is lower than threshold 1e-7. ")
+
+    def pls_build_projection_map_filled(self, xyz, channels, B, n, C_, H, W, up, down, default_value, out):
+        pts = torch.from_numpy(arr(xyz, (B, n, 3), np.float32).copy())
+        ch = None if not channels else torch.from_numpy(arr(channels, (B, n, C_), np.float32).copy())
+        m = orc.Projector(H, W, up, down).build_projection_map(pts, channels=ch, height=H, width=W)
+        if default_value != 0.0:   # pixels no point lands on (projection.py:378-391)
+            filled = orc.Projector(H, W, up, down).build_projection_map(pts, channels=torch.ones(B, n, 1), height=H, width=W)
+            m = torch.where(filled.expand_as(m) > 0, m, torch.full_like(m, default_value))
+        arr(out, (B, C_, H, W), np.float32)[:] = m.numpy()
 
     def pls_build_pose_matrix(self, params, batch, out):
         arr(out, (batch, 4, 4), np.float32)[:] = orc.build_pose_matrix(torch.from_numpy(arr(params, (batch, 6), np.float32).copy())).numpy()

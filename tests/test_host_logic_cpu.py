@@ -260,3 +260,99 @@ def test_voxelise_with_three_voxel_lengths_and_alignment_mask_error(b200, golden
         point.align(pts, pts, mask=torch.from_numpy(mask))
     with pytest.raises(AssertionError):                       # the reference's shape check comes first
         plane.align(pts, pts, pts, mask=mask[:, :, 0])
+
+
+# ---- the fine-grained plug-ins (LOCAL_MAP / RIGID_ALIGNMENT mirrors) and the reference-shaped loop built from them
+def test_local_map_and_alignment_plugins_plumbing(b200):
+    """KdTreeLocalMap / ProjectiveLocalMap / GaussNewtonPointToPlaneAlignment mirrors: argument marshalling, output
+    shapes for ndarray and tensor inputs, the NeighborhoodResult fields -- against the oracle's classes on the same data."""
+    H, W = 16, 128
+    proj = b200.SphericalProjector(height=H, width=W, up_fov=3.0, down_fov=-24.0)
+    vm0 = torch.from_numpy(syn.vertex_map_from_scan(syn.scan(0, H, W), H, W))
+    eye = torch.eye(4).unsqueeze(0)
+    rel = b200.Pose("euler").build_pose_matrix(torch.tensor([[0.3, 0.0, 0.0, 0.0, 0.0, 0.01]]))
+
+    kd = b200.KdTreeLocalMap(b200.KdTreeLocalMapConfig(local_map_size=3), projector=proj, ctx=dry.FakeContext(
+        local_map_size=3, num_neighbors_normals=10))
+    kd.init()
+    kd.update(eye, new_vertex_map=vm0)
+    ref = orc.KdTreeLocalMap(3, 10)
+    ref.update(np.eye(4, dtype=np.float32), new_vertex_map=vm0)
+    assert kd.num_points() == ref.points.shape[0] > 0
+    pts1 = syn.scan(1, H, W)
+    pts1 = pts1[np.linalg.norm(pts1, axis=1) > 0][::3].copy()
+    kd.update(rel, new_pc_data=torch.from_numpy(pts1))
+    ref.update(rel[0].numpy(), new_points=pts1)
+    np.testing.assert_array_equal(kd.points(), ref.points)
+    q = pts1[:50] + 0.01
+    want_p, want_n, _ = ref.nearest_neighbor_search(q)
+    for queries in (q, torch.from_numpy(q)):                    # ndarray in -> ndarrays out; tensor in -> [1,N,3] tensors
+        res = kd.nearest_neighbor_search(queries)
+        got_p, got_n, got_t = res.neighbor_points, res.neighbor_normals, res.new_target_points
+        if isinstance(queries, torch.Tensor):
+            assert got_p.shape == got_n.shape == got_t.shape == (1, 50, 3)
+            got_p, got_n, got_t = got_p[0].numpy(), got_n[0].numpy(), got_t[0].numpy()
+        np.testing.assert_array_equal(got_p, want_p)
+        np.testing.assert_array_equal(got_n, want_n)
+        np.testing.assert_array_equal(got_t, q)
+    kd.update(rel)                                              # no new frame: the map only moves
+    ref.update(rel[0].numpy())
+    np.testing.assert_array_equal(kd.points(), ref.points)
+
+    pm = b200.ProjectiveLocalMap(b200.ProjectiveLocalMapConfig(local_map_size=3), projector=proj, ctx=dry.FakeContext(
+        local_map_size=3, normals_kernel_size=5, height=H, width=W, up_fov_deg=3.0, down_fov_deg=-24.0))
+    pm.init()
+    rp = orc.ProjectiveLocalMap(orc.Projector(H, W), 3, 5)
+    vm1 = torch.from_numpy(syn.vertex_map_from_scan(syn.scan(1, H, W), H, W))
+    pm.update(eye, new_vertex_map=vm0)
+    rp.update(eye, new_vertex_map=vm0)
+    pm.update(rel, new_vertex_map=vm1)
+    rp.update(rel, new_vertex_map=vm1)
+    v, n = pm.model()
+    np.testing.assert_array_equal(v, rp.model_vmap.numpy())
+    np.testing.assert_array_equal(n, rp.model_nmap.numpy())
+    qs = torch.from_numpy(pts1)
+    a, b, c = rp.nearest_neighbor_search(qs)
+    res = pm.nearest_neighbor_search(qs)
+    assert res.neighbor_points.shape == a.shape and a.shape[1] > 0
+    np.testing.assert_array_equal(res.neighbor_points.numpy(), a.numpy())
+    np.testing.assert_array_equal(res.neighbor_normals.numpy(), b.numpy())
+    np.testing.assert_array_equal(res.new_target_points.numpy(), c.numpy())
+
+    al = b200.GaussNewtonPointToPlaneAlignment(b200.GaussNewtonPointToPlaneConfig(
+        gauss_newton_config=dict(scheme="geman_mcclure", sigma=0.3, max_iters=3, norm_stop_criterion=1e-9)), ctx=dry.FakeContext())
+    dT, x, loss = al.align(a, c, b)
+    x_ref, loss_ref, _ = orc.gauss_newton_p2plane(a, c, b, "geman_mcclure", 0.3, 3, 1e-9)
+    assert tuple(dT.shape) == (1, 4, 4) and tuple(x.shape) == (1, 6) and tuple(loss.shape) == (1, a.shape[1])
+    np.testing.assert_allclose(np.asarray(x), x_ref.numpy(), rtol=0, atol=1e-7)
+    np.testing.assert_allclose(np.asarray(dT), orc.build_pose_matrix(x_ref).numpy(), rtol=0, atol=1e-7)
+    np.testing.assert_allclose(np.asarray(loss), loss_ref.numpy(), rtol=0, atol=1e-7)
+
+
+@pytest.mark.parametrize("name,lm,key", [("kd_gn3", "kdtree", "numpy_pc"), ("proj_gn2", "projective", "vertex_map")])
+def test_fine_grained_icp_loop_host_logic_vs_reference_golden(b200, monkeypatch, name, lm, key):
+    """gauss_newton_config.max_iters > 1 takes ICPFrameToModel._process_fine_grained: input normalisation, query sampling,
+    the ICP loop, the key-frame policy and the pose bookkeeping run in Python over the plug-ins.  With the oracle behind the
+    C ABI the poses must reproduce the unmodified reference's (tests/golden/icp_gn.npz, made by make_golden_gn.py)."""
+    import os
+    import test_gpu_parity as G
+    dry.cuda_stand_ins(monkeypatch)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "icp_gn.npz"))
+    H, W = 32, 512
+    lmc = b200.KdTreeLocalMapConfig(local_map_size=4) if lm == "kdtree" else b200.ProjectiveLocalMapConfig(local_map_size=4)
+    cfg = b200.ICPFrameToModelConfig(
+        local_map=lmc, alignment=b200.GaussNewtonPointToPlaneConfig(gauss_newton_config=dict(
+            scheme="geman_mcclure", sigma=0.3, max_iters=int(g[f"{name}_gn_iters"]), norm_stop_criterion=1e-9)),
+        max_num_alignments=5, data_key=key, threshold_delta_pose=0.0)
+    algo = b200.ICPFrameToModel(cfg, projector=b200.SphericalProjector(height=H, width=W, up_fov=3.0, down_fov=-24.0),
+                                pose=b200.Pose("euler"), device="cuda:0")
+    assert algo._fine_grained
+    algo.init()
+    layout = "ndarray" if key == "numpy_pc" else "vertex_map"
+    poses = G._drive(algo, G._frames(syn, b200.grid_sample, layout, H, W, 0.4 if layout == "ndarray" else None), 6)
+    ref = g[f"{name}_poses"]
+    assert len(poses) == len(ref) == len(algo.get_relative_poses()) - 1
+    for k, (T, Tr) in enumerate(zip(poses, ref)):
+        dt, ang = G.pose_errors(T, Tr)
+        assert dt <= 1e-4 and ang <= 1e-5, (name, k, dt, ang)
+    assert int(algo.last_info[0]) == 5 and len(algo.last_losses) == 5
