@@ -11,18 +11,26 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def test_thread_calibration_does_not_disturb_the_stream():
+def test_thread_calibration_does_not_disturb_the_stream(monkeypatch):
     import torch
     import bench
     before = torch.get_num_threads()
     try:
         scans = bench.make_scans(5)
         _, t_plain, _, tried_plain, pose_plain = bench.run_cpu_port(scans, 2, 3, threads=1)
-        _, t_cal, best, tried, pose_cal = bench.run_cpu_port(scans, 2, 3, calibrate=True)
+        # one candidate (a "single-core host"): the calibration replays two frames twice on deep copies of the state, and the
+        # timed frames then run with the same thread count as the plain run -- the arithmetic must be IDENTICAL
+        monkeypatch.setattr(bench.os, "cpu_count", lambda: 1)
+        _, t_cal, best, tried, pose_cal = bench.run_cpu_port(scans, 2, 3, threads=1, calibrate=True)
         assert tried_plain == {} and len(t_plain) == len(t_cal) == 3
-        assert 1 in tried and best in tried and all(ms > 0 for ms in tried.values())
-        # same frames, same arithmetic: the calibration ran on deep copies of the state after the warm-up
-        np.testing.assert_allclose(pose_cal, pose_plain, rtol=0, atol=1e-6)
+        assert best == 1 and list(tried) == [1] and tried[1] > 0
+        np.testing.assert_array_equal(pose_cal, pose_plain)
+        monkeypatch.undo()
+        # several candidates: every one is tried, the fastest is kept
+        _, _, best, tried, pose_multi = bench.run_cpu_port(scans, 2, 2, calibrate=True)
+        assert set(tried) == {t for t in (1, 4, 8, 16, 32, os.cpu_count()) if t <= os.cpu_count()}
+        assert best == min(tried, key=tried.get) == torch.get_num_threads()
+        np.testing.assert_allclose(pose_multi[:3, 3], pose_plain[:3, 3], rtol=0, atol=0.2)   # (another frame: same motion model)
     finally:
         torch.set_num_threads(before)
 
