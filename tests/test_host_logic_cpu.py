@@ -356,3 +356,45 @@ def test_fine_grained_icp_loop_host_logic_vs_reference_golden(b200, monkeypatch,
         dt, ang = G.pose_errors(T, Tr)
         assert dt <= 1e-4 and ang <= 1e-5, (name, k, dt, ang)
     assert int(algo.last_info[0]) == 5 and len(algo.last_losses) == 5
+
+
+def test_fine_grained_icp_loop_tensor_layout_stop_rule_no_keyframe_and_distorted_key(b200, monkeypatch):
+    """The remaining branches of ICPFrameToModel._process_fine_grained against the oracle configured alike: a torch [N,3]
+    input (pixel queries), the default stop rule breaking the loop, frames that do NOT become key frames (the map only
+    moves, the motion accumulates until the thresholds are passed) and the `distorted` cloud passed through as odometry_pc."""
+    dry.cuda_stand_ins(monkeypatch)
+    H, W = 32, 512
+    kw = dict(max_num_alignments=6, threshold_delta_pose=1e-4, threshold_trans=2.0, threshold_rot=30.0)   # a key frame every 3rd
+    cfg = b200.ICPFrameToModelConfig(
+        local_map=b200.KdTreeLocalMapConfig(local_map_size=3), alignment=b200.GaussNewtonPointToPlaneConfig(
+            gauss_newton_config=dict(scheme="geman_mcclure", sigma=0.3, max_iters=2, norm_stop_criterion=1e-9)),
+        data_key="input_data", **kw)
+    algo = b200.ICPFrameToModel(cfg, projector=b200.SphericalProjector(height=H, width=W, up_fov=3.0, down_fov=-24.0),
+                                pose=b200.Pose("euler"), device="cuda:0")
+    algo.init()
+    ref = orc.ICPFrameToModelOracle(orc.ICPConfig(data_key="input_data", local_map="kdtree", local_map_size=3, scheme="geman_mcclure",
+                                                  sigma=0.3, gn_max_iters=2, gn_norm_stop=1e-9, **kw), orc.Projector(H, W))
+    prev_a = prev_b = None
+    keyframes, iters = [], []
+    for k in range(6):
+        pc, _ = orc.grid_sample(syn.scan(k, H, W), 0.4)
+        marker = np.full((5, 3), float(k), np.float32)                      # stands for the Distortion filter's output
+        da = {"input_data": torch.from_numpy(pc.copy()), "init_rpose": prev_a, "distorted": marker}
+        db = {"input_data": torch.from_numpy(pc.copy()), "init_rpose": prev_b, "distorted": marker}
+        size_before = algo.local_map.num_points() if k else 0
+        algo.process_next_frame(da)
+        ref.process_next_frame(db)
+        if k == 0:
+            assert "odometry_pose" not in da and "odometry_pose" not in db
+            continue
+        np.testing.assert_allclose(da["odometry_pose"], db["odometry_pose"], rtol=0, atol=1e-6)
+        assert da["odometry_pc"] is marker and da["odometry_pose"].dtype == np.float32
+        assert len(algo.last_losses) == len(ref.losses[-1])
+        iters.append(len(algo.last_losses))
+        keyframes.append(algo.local_map.num_points() != size_before)
+        assert algo.local_map.num_points() == ref.local_map.points.shape[0]
+        prev_a, prev_b = da["odometry_pose"].astype(np.float64), db["odometry_pose"].astype(np.float64)
+    assert not all(keyframes) and any(keyframes)                             # both branches of the key-frame policy ran
+    assert min(iters) < 6                                                    # the stop rule broke at least one loop
+    np.testing.assert_allclose(algo.get_relative_poses(), ref.get_relative_poses(), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(np.stack(algo.absolute_poses), np.stack(ref.absolute_poses), rtol=0, atol=1e-5)
