@@ -311,6 +311,14 @@ class FakeContext:
             import logging
             logging.warning("The residual norm is lower than threshold 1e-7. ")
 
+    def pls_register_frame(self, pts, n, T0, out_T, out_params, out_losses, out_iters):
+        init = torch.eye(4).unsqueeze(0) if not T0 else torch.from_numpy(arr(T0, (1, 4, 4), np.float32).copy())
+        params, T, losses = self.algo.register_new_frame(torch.from_numpy(arr(pts, (n, 3), np.float32).copy()), init)
+        arr(out_T, (4, 4), np.float32)[:] = T[0].numpy()
+        arr(out_params, (6,), np.float32)[:] = params.reshape(6).numpy()
+        arr(out_losses, (len(losses),), np.float32)[:] = losses
+        out_iters._obj.value = len(losses)
+
     def pls_build_projection_map_filled(self, xyz, channels, B, n, C_, H, W, up, down, default_value, out):
         pts = torch.from_numpy(arr(xyz, (B, n, 3), np.float32).copy())
         ch = None if not channels else torch.from_numpy(arr(channels, (B, n, C_), np.float32).copy())

@@ -398,3 +398,44 @@ def test_fine_grained_icp_loop_tensor_layout_stop_rule_no_keyframe_and_distorted
     assert min(iters) < 6                                                    # the stop rule broke at least one loop
     np.testing.assert_allclose(algo.get_relative_poses(), ref.get_relative_poses(), rtol=0, atol=1e-6)
     np.testing.assert_allclose(np.stack(algo.absolute_poses), np.stack(ref.absolute_poses), rtol=0, atol=1e-5)
+
+
+def test_point_to_plane_initial_estimates_and_register_new_frame_plumbing(b200):
+    """GaussNewtonPointToPlaneAlignment.align with an initial estimate given as parameters [1,6] or as a pose matrix
+    [1,4,4] (alignment.py:110-118), float64 inputs staying float64; ICPFrameToModel.register_new_frame (the fused ICP loop
+    as a stand-alone call, icp_odometry.py:248-299) returning (params [1,6], T [1,4,4], the executed iterations' losses)."""
+    g = torch.Generator().manual_seed(3)
+    n = 400
+    tgt = torch.randn(1, n, 3, generator=g)
+    nrm = torch.nn.functional.normalize(torch.randn(1, n, 3, generator=g), dim=-1)
+    x_true = torch.tensor([[0.02, -0.01, 0.015, 0.002, -0.001, 0.003]])
+    ref = orc.apply_transformation(tgt, orc.build_pose_matrix(x_true)) + 0.005 * torch.randn(1, n, 3, generator=g)
+    al = b200.GaussNewtonPointToPlaneAlignment(b200.GaussNewtonPointToPlaneConfig(
+        gauss_newton_config=dict(scheme="geman_mcclure", sigma=0.3, max_iters=4, norm_stop_criterion=1e-12)), ctx=dry.FakeContext())
+    x0 = torch.tensor([[0.01, 0.0, 0.01, 0.0, 0.0, 0.002]])
+    want, _, _ = orc.gauss_newton_p2plane(ref, tgt, nrm, "geman_mcclure", 0.3, 4, 1e-12, x0.clone())
+    _, x_a, _ = al.align(ref, tgt, nrm, initial_estimate=x0)
+    _, x_b, _ = al.align(ref, tgt, nrm, initial_estimate=orc.build_pose_matrix(x0))
+    np.testing.assert_allclose(np.asarray(x_a), want.numpy(), rtol=0, atol=1e-7)
+    np.testing.assert_allclose(np.asarray(x_b), want.numpy(), rtol=0, atol=2e-6)      # through the Euler round trip of x0
+    dT64, x64, loss64 = al.align(ref.double().numpy(), tgt.double().numpy(), nrm.double().numpy())
+    assert dT64.dtype == x64.dtype == loss64.dtype == np.float64 and dT64.shape == (1, 4, 4) and loss64.shape == (1, n)
+    with pytest.raises(AssertionError):
+        al.align(ref.double(), tgt.double(), nrm.double(), initial_estimate=orc.build_pose_matrix(x0).double())
+
+    H, W = 32, 512
+    cfg = b200.ICPFrameToModelConfig(local_map=b200.KdTreeLocalMapConfig(local_map_size=3),
+                                     alignment=b200.GaussNewtonPointToPlaneConfig(gauss_newton_config=dict(
+                                         scheme="geman_mcclure", sigma=0.3, max_iters=1)),
+                                     max_num_alignments=5, data_key="numpy_pc", threshold_delta_pose=0.0)
+    algo = b200.ICPFrameToModel(cfg, projector=b200.SphericalProjector(height=H, width=W, up_fov=3.0, down_fov=-24.0),
+                                device="cuda:0")
+    algo.init()
+    pc0, _ = orc.grid_sample(syn.scan(0, H, W), 0.4)
+    pc1, _ = orc.grid_sample(syn.scan(1, H, W), 0.4)
+    algo.process_next_frame({"numpy_pc": pc0})
+    params, T, losses = algo.register_new_frame(pc1, initial_estimate=np.eye(4, dtype=np.float32)[None])
+    assert params.shape == (1, 6) and T.shape == (1, 4, 4) and len(losses) == 5 and all(np.isfinite(losses))
+    np.testing.assert_allclose(T[0], orc.build_pose_matrix(torch.from_numpy(params))[0].numpy(), rtol=0, atol=1e-6)
+    gt = np.linalg.inv(syn.gt_pose(0)) @ syn.gt_pose(1)
+    assert np.linalg.norm(T[0, :3, 3] - gt[:3, 3]) < 0.05                      # one frame of the stream: ~0.8 m forward
