@@ -311,6 +311,19 @@ class FakeContext:
             import logging
             logging.warning("The residual norm is lower than threshold 1e-7. ")
 
+    def pls_project_pixels(self, xyz, n, H, W, up, down, out):
+        row, col = orc.Projector(H, W, up, down).pixels(torch.from_numpy(arr(xyz, (1, n, 3), np.float32).copy()))
+        arr(out, (n, 2), np.float32)[:] = torch.stack([row[0], col[0]], dim=1).numpy()
+
+    def pls_compute_neighbors(self, tgt, ref, fields, K, Cf, H, W, out_nb, out_nf):
+        t = torch.from_numpy(arr(tgt, (1, 3, H, W), np.float32).copy())
+        r = torch.from_numpy(arr(ref, (K, 3, H, W), np.float32).copy())
+        f = None if not fields else torch.from_numpy(arr(fields, (K, Cf, H, W), np.float32).copy())
+        nb, nf = orc.compute_neighbors(t, r, f)
+        arr(out_nb, (3, H, W), np.float32)[:] = nb[0].numpy()
+        if f is not None and out_nf:
+            arr(out_nf, (Cf, H, W), np.float32)[:] = nf[0].numpy()
+
     def pls_register_frame(self, pts, n, T0, out_T, out_params, out_losses, out_iters):
         init = torch.eye(4).unsqueeze(0) if not T0 else torch.from_numpy(arr(T0, (1, 4, 4), np.float32).copy())
         params, T, losses = self.algo.register_new_frame(torch.from_numpy(arr(pts, (n, 3), np.float32).copy()), init)

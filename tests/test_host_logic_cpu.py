@@ -439,3 +439,40 @@ def test_point_to_plane_initial_estimates_and_register_new_frame_plumbing(b200):
     np.testing.assert_allclose(T[0], orc.build_pose_matrix(torch.from_numpy(params))[0].numpy(), rtol=0, atol=1e-6)
     gt = np.linalg.inv(syn.gt_pose(0)) @ syn.gt_pose(1)
     assert np.linalg.norm(T[0, :3, 3] - gt[:3, 3]) < 0.05                      # one frame of the stream: ~0.8 m forward
+
+
+def test_slam_common_helper_mirrors_plumbing(b200, golden_helpers, golden_misc):
+    """The slam/common mirrors (voxelise / voxel_hashing / grid_sample, SphericalProjector, compute_normal_map,
+    compute_neighbors, Pose): the bodies of their GPU parity tests against the reference goldens, with the oracle behind
+    the C ABI -- argument order, batch handling, output shapes and dtypes, numpy and tensor inputs."""
+    import test_gpu_parity as G
+    G.test_a1_voxel_hash_golden(b200, golden_helpers)
+    G.test_a3_projection_golden(b200, golden_helpers)
+    G.test_a3_projection_default_value_and_default_channels(b200, golden_misc)
+    G.test_a16_pose_golden(b200, golden_helpers)
+    G.test_a6_compute_neighbors_golden(b200, golden_helpers)
+    G.test_a6_reference_geometry_property(b200)
+    G.test_a4_normal_map_golden_and_oracle(b200, orc, syn, golden_helpers)
+
+
+def test_more_gpu_parity_bodies_through_the_stand_in(b200, monkeypatch, caplog, golden_helpers, golden_misc):
+    """Bodies of further GPU parity tests (tests/test_gpu_parity.py) with the oracle behind the C ABI: the Gauss-Newton
+    step goldens of all seven schemes, its error behaviour, the local-map mirrors' life cycles, NaN handling, re-init,
+    device-tensor inputs -- the tests' own logic and the mirrors' plumbing, checked before GPU minutes are spent."""
+    import test_gpu_parity as G
+    dry.cuda_stand_ins(monkeypatch)
+    for scheme in G.SCHEMES:
+        G.test_gn_step_golden(b200, golden_helpers, scheme)
+    G.test_gn_multi_iter_and_known_answer(b200, golden_helpers)
+    G.test_gn_singular_raises_and_tiny_residual_warns(b200, orc, _Caplog(caplog))
+    G.test_align_bad_shape_is_assertion(b200)
+    G.test_kd_local_map_golden(b200, golden_helpers)
+    G.test_kd_map_lifecycle_vs_oracle(b200, orc, syn)
+    G.test_a5_projective_map_lifecycle_vs_oracle(b200, orc, syn)
+    G.test_preprocessing_chain_matches_reference_layout(b200, orc, syn)
+    G.test_icp_missing_key_and_bad_shape(b200)
+    G.test_nan_rows_and_nan_pixels_match_oracle(b200, orc, syn)
+    G.test_odometry_reinit_is_clean(b200, syn)
+    G.test_icp_device_tensor_input_and_outputs(b200, syn)
+    G.test_a1_voxelise_with_one_voxel_length_per_axis(b200, golden_misc)
+    G.test_a3_projection_with_channels_and_batch(b200, orc, syn)
