@@ -149,14 +149,14 @@ def ref_vs_port_note():
 
 # ------------------------------------------------------------------------------------------ CPU arm
 def run_cpu_port(scans, warmup, steps, threads=None, calibrate=False):
-    """The oracle port of the reference path on the host cores; returns (fps, ms/frame list, threads, {threads: ms},
-    last pose).
+    """The oracle port of the reference path on the host cores; returns (fps, ms/frame list, calibration dict, last pose).
 
-    calibrate=True gives the CPU arm the torch thread count that is FASTEST on this host, not simply all of them: the path
-    is made of many small tensor ops, and 64 intra-op threads were measured slower than one on the 64-core B200 hosts
-    (SCALE_r01: 297 vs 369 ms/frame).  After the warm-up frames every candidate count replays the SAME next two frames on
-    a deep copy of the algorithm's state (local map, kd-tree, poses), twice; the fastest one runs the timed frames.  scipy's
-    cKDTree queries use every core (workers=-1) whatever is chosen."""
+    calibrate=True gives the CPU arm the thread counts that are FASTEST on this host, not simply all of them: the path is
+    made of many small tensor ops and short kd-tree queries, and 64 intra-op threads were measured slower than one on the
+    64-core B200 hosts (SCALE_r01: 297 vs 369 ms/frame).  After the warm-up frames every candidate replays the SAME next two
+    frames on a deep copy of the algorithm's state (local map, kd-tree, poses), twice; first the torch intra-op thread
+    count (kd queries on all cores), then the worker count of scipy's cKDTree queries (pykdtree, which the reference uses,
+    is OpenMP-parallel); the fastest pair runs the timed frames."""
     import copy
     import torch
     from oracle import icp_oracle as orc
@@ -165,6 +165,7 @@ def run_cpu_port(scans, warmup, steps, threads=None, calibrate=False):
     cfg = orc.ICPConfig(max_num_alignments=MAX_ALIGN, data_key="input_data", local_map="kdtree", local_map_size=LM_SIZE,
                         scheme=SCHEME, sigma=SIGMA)
     algo = orc.ICPFrameToModelOracle(cfg, orc.Projector(H, W))
+    kd_default = orc._KD_WORKERS
 
     def frame(a, k, prev):
         t0 = time.perf_counter()
@@ -174,30 +175,48 @@ def run_cpu_port(scans, warmup, steps, threads=None, calibrate=False):
         dt = time.perf_counter() - t0
         return dt, (dd["odometry_pose"].astype(np.float64) if "odometry_pose" in dd else prev)
 
-    prev, times, tried = None, [], {}
-    for k in range(warmup + steps):
-        if k == warmup and calibrate:
-            ncpu = os.cpu_count() or 1
-            cands = sorted({t for t in (1, 4, 8, 16, 32, ncpu) if t <= ncpu})
-            for thr in cands + cands[::-1]:                 # two rounds in opposite orders, the better one counts
-                torch.set_num_threads(thr)
-                a, p, dts = copy.deepcopy(algo), prev, []
-                for j in range(k, min(k + 2, len(scans))):
-                    dt, p = frame(a, j, p)
-                    dts.append(dt)
-                tried[thr] = min(tried.get(thr, 1e30), 1e3 * float(np.mean(dts)))
-            torch.set_num_threads(min(tried, key=tried.get))
-        dt, prev = frame(algo, k, prev)
-        if k >= warmup:
-            times.append(dt)
-    return len(times) / sum(times), times, torch.get_num_threads(), tried, prev
+    def fastest(cands, apply, k, prev):
+        tried = {}
+        for c in cands + cands[::-1]:                       # two rounds in opposite orders, the better one counts
+            apply(c)
+            a, p, dts = copy.deepcopy(algo), prev, []
+            for j in range(k, min(k + 2, len(scans))):
+                dt, p = frame(a, j, p)
+                dts.append(dt)
+            tried[c] = min(tried.get(c, 1e30), 1e3 * float(np.mean(dts)))
+        best = min(tried, key=tried.get)
+        apply(best)
+        return best, tried
+
+    def set_kd_workers(w):
+        orc._KD_WORKERS = w
+
+    prev, times, cal = None, [], {}
+    try:
+        for k in range(warmup + steps):
+            if k == warmup and calibrate:
+                ncpu = os.cpu_count() or 1
+                cands = sorted({t for t in (1, 4, 8, 16, 32, ncpu) if t <= ncpu})
+                _, cal["torch_tried_ms"] = fastest(cands, torch.set_num_threads, k, prev)
+                kd_cands = sorted({w for w in (1, 8, 32) if w < ncpu}) + [-1]       # -1: all cores
+                cal["kd_workers"], cal["kd_tried_ms"] = fastest(kd_cands, set_kd_workers, k, prev)
+            dt, prev = frame(algo, k, prev)
+            if k >= warmup:
+                times.append(dt)
+        cal["torch_threads"] = torch.get_num_threads()
+        cal.setdefault("kd_workers", orc._KD_WORKERS)
+    finally:
+        orc._KD_WORKERS = kd_default
+    return len(times) / sum(times), times, cal, prev
 
 
-def threads_note(best, tried):
-    if not tried:
+def threads_note(cal):
+    if "torch_tried_ms" not in cal:
         return ""
-    return ("; torch intra-op threads calibrated after the warm-up on copies of the state (best of two rounds of two frames, ms/frame: "
-            + ", ".join(f"{t} thr {ms:.0f}" for t, ms in tried.items()) + f") -> {best}; host cores {os.cpu_count()}")
+    fmt = lambda d: ", ".join(f"{'all' if t == -1 else t}: {ms:.0f}" for t, ms in d.items())   # noqa: E731
+    return ("; thread counts calibrated after the warm-up on copies of the state (best of two rounds of two frames, ms/frame) -- "
+            f"torch intra-op threads {{{fmt(cal['torch_tried_ms'])}}} -> {cal['torch_threads']}, then cKDTree workers "
+            f"{{{fmt(cal['kd_tried_ms'])}}} -> {'all' if cal['kd_workers'] == -1 else cal['kd_workers']}; host cores {os.cpu_count()}")
 
 
 def reference_arm(args):
@@ -210,16 +229,17 @@ def reference_arm(args):
     steps = min(args.steps, 30)
     scans = make_scans(warmup + steps)
     t0 = time.perf_counter()
-    fps, times, best, tried, _ = run_cpu_port(scans, warmup, steps, calibrate=True)
+    fps, times, cal, _ = run_cpu_port(scans, warmup, steps, calibrate=True)
     line = {
         "impl": "reference", "metric": "icp_odometry_frames_per_sec", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * float(np.mean(times)),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "height": H, "width": W, "voxel": VOXEL},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "torch_threads": best, "kind": "port",
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "torch_threads": cal["torch_threads"],
+                         "kd_workers": cal["kd_workers"], "kind": "port",
                          "sample": f"frames {warmup}..{warmup + steps - 1} of the same seeded stream after {warmup} warm-up "
-                                   f"frames (oracle/icp_oracle.py: torch CPU + scipy cKDTree workers=-1), "
-                                   f"{time.perf_counter() - t0:.1f} s wall" + threads_note(best, tried) + ref_vs_port_note()},
+                                   f"frames (oracle/icp_oracle.py: torch CPU + scipy cKDTree), "
+                                   f"{time.perf_counter() - t0:.1f} s wall" + threads_note(cal) + ref_vs_port_note()},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -500,11 +520,11 @@ def b200_arm(args):
     if world == 1 and not args.no_cpu:
         t0 = time.perf_counter()
         nb = min(len(scans), 30)
-        fps_cpu, times, best, tried, _ = run_cpu_port(scans[:nb], min(22, nb - 6), nb - min(22, nb - 6), calibrate=True)
-        line["cpu_baseline"] = {"value": fps_cpu, "unit": "frames/s", "cores": os.cpu_count(), "torch_threads": best, "kind": "port",
+        fps_cpu, times, cal, _ = run_cpu_port(scans[:nb], min(22, nb - 6), nb - min(22, nb - 6), calibrate=True)
+        line["cpu_baseline"] = {"value": fps_cpu, "unit": "frames/s", "cores": os.cpu_count(), "torch_threads": cal["torch_threads"],
+                                "kd_workers": cal["kd_workers"], "kind": "port",
                                 "sample": f"frames {min(22, nb - 6)}..{nb - 1} of the same stream (oracle port: torch CPU + scipy "
-                                          f"cKDTree workers=-1), {time.perf_counter() - t0:.1f} s wall" + threads_note(best, tried)
-                                          + ref_vs_port_note()}
+                                          f"cKDTree), {time.perf_counter() - t0:.1f} s wall" + threads_note(cal) + ref_vs_port_note()}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

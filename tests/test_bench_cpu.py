@@ -14,22 +14,29 @@ sys.path.insert(0, ROOT)
 def test_thread_calibration_does_not_disturb_the_stream(monkeypatch):
     import torch
     import bench
+    from oracle import icp_oracle as orc
     before = torch.get_num_threads()
     try:
         scans = bench.make_scans(5)
-        _, t_plain, _, tried_plain, pose_plain = bench.run_cpu_port(scans, 2, 3, threads=1)
-        # one candidate (a "single-core host"): the calibration replays two frames twice on deep copies of the state, and the
-        # timed frames then run with the same thread count as the plain run -- the arithmetic must be IDENTICAL
+        _, t_plain, cal_plain, pose_plain = bench.run_cpu_port(scans, 2, 3, threads=1)
+        assert "torch_tried_ms" not in cal_plain and cal_plain["torch_threads"] == 1 and cal_plain["kd_workers"] == -1
+        # one torch candidate (a "single-core host"): the calibration replays two frames on deep copies of the state, and
+        # the timed frames then run with the same torch thread count as the plain run (kd queries are exact whatever the
+        # worker count) -- the arithmetic must be IDENTICAL
         monkeypatch.setattr(bench.os, "cpu_count", lambda: 1)
-        _, t_cal, best, tried, pose_cal = bench.run_cpu_port(scans, 2, 3, threads=1, calibrate=True)
-        assert tried_plain == {} and len(t_plain) == len(t_cal) == 3
-        assert best == 1 and list(tried) == [1] and tried[1] > 0
+        _, t_cal, cal, pose_cal = bench.run_cpu_port(scans, 2, 3, threads=1, calibrate=True)
+        assert len(t_plain) == len(t_cal) == 3
+        assert cal["torch_threads"] == 1 and list(cal["torch_tried_ms"]) == [1] and list(cal["kd_tried_ms"]) == [-1]
         np.testing.assert_array_equal(pose_cal, pose_plain)
         monkeypatch.undo()
-        # several candidates: every one is tried, the fastest is kept
-        _, _, best, tried, pose_multi = bench.run_cpu_port(scans, 2, 2, calibrate=True)
-        assert set(tried) == {t for t in (1, 4, 8, 16, 32, os.cpu_count()) if t <= os.cpu_count()}
-        assert best == min(tried, key=tried.get) == torch.get_num_threads()
+        # several candidates: every one is tried, the fastest is kept, the oracle's default is restored afterwards
+        n = os.cpu_count()
+        _, _, cal, pose_multi = bench.run_cpu_port(scans, 2, 2, calibrate=True)
+        assert set(cal["torch_tried_ms"]) == {t for t in (1, 4, 8, 16, 32, n) if t <= n}
+        assert set(cal["kd_tried_ms"]) == {w for w in (1, 8, 32) if w < n} | {-1}
+        assert cal["torch_threads"] == min(cal["torch_tried_ms"], key=cal["torch_tried_ms"].get) == torch.get_num_threads()
+        assert cal["kd_workers"] == min(cal["kd_tried_ms"], key=cal["kd_tried_ms"].get) and orc._KD_WORKERS == -1
+        assert "cKDTree workers" in bench.threads_note(cal)
         np.testing.assert_allclose(pose_multi[:3, 3], pose_plain[:3, 3], rtol=0, atol=0.2)   # (another frame: same motion model)
     finally:
         torch.set_num_threads(before)
@@ -48,6 +55,7 @@ def test_reference_arm_prints_one_contract_line():
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["value"] == d["value"] and cb["cores"] == os.cpu_count() and cb["torch_threads"] >= 1
+    assert cb["kd_workers"] in (-1, 1, 8, 32) and "calibrated" in cb["sample"]
     assert d["config"]["workload"].startswith("cfg2") and d["config"]["height"] == 64 and d["config"]["width"] == 2048
 
 
