@@ -186,7 +186,7 @@ def test_b200_arm_assembles_the_contract_line_dry_run(monkeypatch, capsys):
     def failing_extras(*a, **k):                # an extra workload that dies must not take the headline line with it
         raise RuntimeError("extra workload failed (dry run)")
     monkeypatch.setattr(bench, "extra_workloads", failing_extras)
-    args = argparse.Namespace(gpus=1, steps=4, warmup=3, impl="b200", no_cpu=True, no_extra=False, quick=False, comm="p2p")
+    args = argparse.Namespace(gpus=1, steps=4, warmup=3, impl="b200", no_cpu=False, no_extra=False, quick=False, comm="p2p")
     bench.b200_arm(args)
     lines = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -208,7 +208,10 @@ def test_b200_arm_assembles_the_contract_line_dry_run(monkeypatch, capsys):
     for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert key in r, key
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
-    assert d["config"]["workload"].startswith("cfg2") and "cpu_baseline" not in d
+    assert d["config"]["workload"].startswith("cfg2")
+    cb = d["cpu_baseline"]                                                                             # the CPU leg at N = 1
+    assert cb["kind"] == "port" and cb["unit"] == "frames/s" and cb["value"] > 0 and cb["cores"] == os.cpu_count()
+    assert cb["torch_threads"] >= 1 and "calibrated" in cb["sample"]
     assert d["config"]["extra_workloads"] == {"failed": "RuntimeError: extra workload failed (dry run)"}
     assert _lib.Context is not real_context                                                            # still patched here ...
 
