@@ -282,3 +282,22 @@ def test_b200_arm_two_ranks_dry_run():
     # the headline is the max over ranks of the ranks' medians: never below rank 0's own median
     assert d["ms_per_step"] >= sorted(rep["value_ms_per_step"])[1] - 1e-9
     assert d["e2e"]["ms_per_step"] >= sorted(rep["e2e_ms_per_step"])[1] - 1e-9
+
+
+def test_committed_evidence_files_feed_the_bench_line():
+    """bench.py attaches committed ncu evidence to its line (DRAM traffic per launch, the limiter digest, the
+    reference-vs-port timing) and silently reports None when a file is missing or malformed: pin the files and the keys."""
+    import bench
+    traffic, commit = bench.committed_traffic("kd_iteration_bytes_per_launch")
+    assert traffic and traffic > 1e6 and commit
+    for name in ("cfg3_proj_bytes_per_launch", "cfg5_proj_bytes_per_launch"):
+        t, c = bench.committed_traffic(name)
+        assert t and t > 1e7 and c == commit
+    lim = bench.committed_limiter()
+    assert lim and lim["verdict"] and lim["source"]
+    kernels = [k for k in lim if k not in ("verdict", "source")]
+    assert len(kernels) >= 3 and all(0 < lim[k]["issue_active_pct"] <= 100 and lim[k]["warp_instructions"] > 0 for k in kernels)
+    note = bench.ref_vs_port_note()
+    assert "unmodified reference" in note and "profiles/ref_vs_port.json" in note
+    peak, src = bench.measured_peaks()
+    assert 3000 < peak < 9000 and ("MEASURED_PEAKS" in src or "fallback" in src)
