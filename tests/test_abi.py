@@ -51,3 +51,28 @@ def test_product_path_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in text or f == "synthetic.py", f"{f} mentions the oracle"
+
+
+def test_sass_carries_the_blackwell_features_the_design_names():
+    """The projective correspondence kernel really issues TMA bulk copies completed on mbarriers (UBLKCP / SYNCS), the kd
+    kernels really reduce with warp-wide redux (CREDUX on sm_100a); nothing pulls in a library kernel (every kernel of
+    the .so is ours).  tools/sass_census.py over the built library; needs cuobjdump, no GPU."""
+    import shutil
+    import subprocess
+    import sys
+    if not (shutil.which("cuobjdump") or os.path.exists("/usr/local/cuda/bin/cuobjdump")):
+        pytest.skip("cuobjdump not available")
+    from pylidar_slam_b200 import build
+    build.build()
+    env = {**os.environ, "PATH": os.environ.get("PATH", "") + ":/usr/local/cuda/bin"}
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_census.py")], capture_output=True, text=True, env=env).stdout
+    rows = {l.split()[0]: l for l in out.splitlines() if l and not l.startswith("#")}
+
+    def count(kernel, op):
+        m = re.search(rf"\b{op}=(\d+)", rows[kernel])
+        return int(m.group(1)) if m else 0
+
+    assert "sm_100a" in out.splitlines()[0] and len(rows) > 60
+    assert count("proj_icp_tma_kernel", "UBLKCP") >= 1 and count("proj_icp_tma_kernel", "SYNCS") >= 1
+    assert count("kd_nn_warp_kernel", "CREDUX") >= 1 and count("kd_normals_warp_kernel", "CREDUX") >= 1
+    assert not any(k.startswith(("cub::", "thrust::", "cutlass", "cublas")) for k in rows)
