@@ -1,6 +1,8 @@
 """Development helper (runs without a GPU): the Python cost of one end-to-end frame of the reference-shaped API
 (GridSample -> ToTensor -> ICPFrameToModel.process_next_frame) with the C ABI replaced by a stand-in that returns at
-once (fixed sample count, identity pose).  What remains is what the interpreter adds to every frame.
+once (fixed sample count, identity pose).  What remains is what the interpreter adds to every frame.  (Without a GPU the
+pinned pool cannot allocate, so GridSample hands out pageable COPIES of the staged samples: about 30 us of memcpy per frame
+that a GPU box does not pay -- compare runs of this tool with each other, not with profiles/r2_e2e_breakdown.log.)
     python tools/host_overhead.py [frames] [--profile]"""
 import ctypes as C
 import os
