@@ -268,7 +268,12 @@ def b200_arm(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cpus = None
     if world > 1:
+        # one process per GPU on a two-socket host: every rank stays on its GPU's socket (launches, pinned buffers and the
+        # GPU's writes into mapped host memory do not cross the inter-socket link); a no-op wherever it cannot apply
+        from pylidar_slam_b200.distributed import pin_to_gpu_numa
+        numa_cpus = pin_to_gpu_numa(local_rank)
         dist.init_process_group("nccl", device_id=dev)
 
     W_, K_ = args.warmup, args.steps
@@ -490,6 +495,7 @@ def b200_arm(args):
                     f"(PLS_SHARD_MIN = 24576 per rank), so every rank runs the whole frame and no exchange takes place "
                     f"(frames sharded in the timed region: {stats['frames_sharded']}); the sharded path is measured on the "
                     f"HBM-sized configurations under extra_workloads ({comm_used[0]} exchange)"),
+                   "host_cpus_rank0": numa_cpus if numa_cpus else "not pinned",
                    **{k: v for k, v in stats.items() if k != "iters_total"}},
         "e2e": {"value": K_ / t_e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d / K_), "d2h_bytes_per_step": int(d2h / K_),
                 "ms_per_step": 1e3 * t_e / K_},

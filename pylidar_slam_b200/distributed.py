@@ -91,3 +91,54 @@ def init_comm(ctx, dist, rank: int, world: int, device, mode: str = "p2p") -> st
     raw = broadcast_unique_id(make_id, dist, rank, device)
     ctx.call("pls_comm_init", world, rank, raw, nccl_path)
     return "nccl"
+
+
+def parse_cpulist(text: str) -> set:
+    """'0-31,64-95' -> {0, ..., 31, 64, ..., 95} (the sysfs / cpuset list format)."""
+    cpus = set()
+    for part in text.strip().split(","):
+        part = part.strip()
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def format_cpulist(cpus) -> str:
+    out, run = [], []
+    for c in sorted(cpus) + [None]:
+        if run and (c is None or c != run[-1] + 1):
+            out.append(str(run[0]) if len(run) == 1 else f"{run[0]}-{run[-1]}")
+            run = []
+        if c is not None:
+            run.append(c)
+    return ",".join(out)
+
+
+def pin_to_gpu_numa(device_index: int, sysfs: str = "/sys", min_cpus: int = 8):
+    """One process per GPU on a two-socket box: keeps every thread of this process (the Python thread, the CUDA driver's
+    helpers, later pools) on the CPUs of the socket the GPU hangs off (`local_cpulist` of its PCI device), so that launches,
+    pinned host buffers (first touch) and the GPU's writes into mapped host memory do not cross the inter-socket link --
+    what `numactl --cpunodebind` does from outside.  Call it right after torch.cuda.set_device and BEFORE any pinned
+    allocation.  Returns the CPU list it pinned to, or None when there is nothing to do or anything is unavailable
+    (no sysfs entry, a cpuset that already is narrower, fewer than `min_cpus` CPUs left): never raises."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(os.path.join(sysfs, "bus", "pci", "devices", bdf, "local_cpulist")) as fh:
+            local = parse_cpulist(fh.read())
+        current = os.sched_getaffinity(0)
+        want = local & current
+        if len(want) < min_cpus or want == current:
+            return None
+        for tid in os.listdir("/proc/self/task"):
+            try:
+                os.sched_setaffinity(int(tid), want)
+            except OSError:
+                pass
+        return format_cpulist(want)
+    except Exception:  # noqa: BLE001  (an optimisation, never a reason to fail)
+        return None
+

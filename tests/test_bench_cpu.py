@@ -275,6 +275,7 @@ def test_b200_arm_two_ranks_dry_run():
     d = json.loads(lines[0])
     assert d["n_gpus"] == 2 and d["steps"] == 3 and d["warmup"] == 3 and "cpu_baseline" not in d   # CPU leg at N = 1 only
     assert "2 GPUs" in d["config"]["parallelism"] and d["config"]["extra_workloads"] == {"stub": True}
+    assert d["config"]["host_cpus_rank0"] == "not pinned"                                   # no GPU here: nothing to pin to
     par = d["config"]["sharded_vs_single"]
     assert par["identical_across_ranks"] is True and par["max_rel_dt"] == 0.0 and par["max_dR"] == 0.0 and par["exchange"] == "p2p"
     rep = d["config"]["repeats"]

@@ -128,3 +128,34 @@ def test_p2p_rendezvous_falls_back_to_nccl_on_every_rank_together():
             assert "pls_comm_destroy" in out[1][1] and "pls_comm_destroy" not in out[0][1]
         if scenario == "handle_fails_on_1":
             assert "pls_comm_p2p_init" not in out[0][1] and "pls_comm_p2p_init" not in out[1][1]
+
+
+def test_numa_pinning_helper(tmp_path, monkeypatch):
+    """pin_to_gpu_numa: the GPU's PCI `local_cpulist` intersected with the current affinity, applied to every thread of
+    the process; a no-op (None) when the entry is missing, when nothing would change or when too few CPUs would be left."""
+    import types
+    import pylidar_slam_b200.distributed as D
+    assert D.parse_cpulist("0-31,64-95\n") == set(range(32)) | set(range(64, 96))
+    assert D.parse_cpulist("3") == {3} and D.parse_cpulist("") == set()
+    assert D.format_cpulist(set(range(32)) | set(range(64, 96)) | {100}) == "0-31,64-95,100"
+    props = types.SimpleNamespace(pci_domain_id=0, pci_bus_id=0x1B, pci_device_id=0)
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda i: props)
+    dev = tmp_path / "bus" / "pci" / "devices" / "0000:1b:00.0"
+    dev.mkdir(parents=True)
+    (dev / "local_cpulist").write_text("0-31,64-95\n")
+    calls = []
+    monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(range(128)))
+    monkeypatch.setattr(os, "sched_setaffinity", lambda tid, cpus: calls.append((tid, set(cpus))))
+    got = D.pin_to_gpu_numa(0, sysfs=str(tmp_path))
+    assert got == "0-31,64-95"
+    tids = {int(t) for t in os.listdir("/proc/self/task")}
+    assert {t for t, _ in calls} == tids and all(c == set(range(32)) | set(range(64, 96)) for _, c in calls)
+    calls.clear()
+    monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(range(32)) | set(range(64, 96)))   # already there
+    assert D.pin_to_gpu_numa(0, sysfs=str(tmp_path)) is None and not calls
+    monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(range(28, 36)))                    # 4 CPUs would be left
+    assert D.pin_to_gpu_numa(0, sysfs=str(tmp_path)) is None and not calls
+    monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(range(128)))
+    assert D.pin_to_gpu_numa(0, sysfs=str(tmp_path / "nowhere")) is None and not calls               # no sysfs entry
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda i: (_ for _ in ()).throw(RuntimeError("no device")))
+    assert D.pin_to_gpu_numa(0, sysfs=str(tmp_path)) is None and not calls
