@@ -476,3 +476,17 @@ def test_more_gpu_parity_bodies_through_the_stand_in(b200, monkeypatch, caplog, 
     G.test_icp_device_tensor_input_and_outputs(b200, syn)
     G.test_a1_voxelise_with_one_voxel_length_per_axis(b200, golden_misc)
     G.test_a3_projection_with_channels_and_batch(b200, orc, syn)
+
+
+def test_example_script_runs_through_the_stand_in(b200, monkeypatch, capsys):
+    """examples/odometry_synthetic.py (the shipped pipeline through the reference-shaped API) stepped on a small sensor with
+    the oracle behind the C ABI: the script's own logic, and the poses it reports against the stream's ground truth."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "odometry_synthetic.py")
+    spec = importlib.util.spec_from_file_location("odometry_synthetic_example", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    poses, errors = mod.main(frames=5, height=32, width=512, voxel=0.4)
+    assert poses.shape == (5, 4, 4) and len(errors) == 4 and max(errors) < 0.05
+    assert "frames/s" in capsys.readouterr().out
